@@ -1,0 +1,652 @@
+/*
+ * lp_oracle.c — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Scalar C restatement of the hot path of pywr/pywr that this repository replaces on the GPU:
+ * the per-timestep, per-scenario loop of CythonGLPKSolver.solve.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load this library; the
+ * product (pywr_b200/) never does.
+ *
+ * What it follows in the reference (paths relative to /root/reference):
+ *   - bound typing / clipping            pywr/solvers/cython_glpk.pyx:66-95,932-959   (a5)
+ *   - storage / virtual storage bounds   pywr/solvers/cython_glpk.pyx:965-1019        (a6)
+ *   - objective assembly                 pywr/solvers/cython_glpk.pyx:880-897         (a3)
+ *   - aggregated-factor matrix rewrite   pywr/solvers/cython_glpk.pyx:903-926         (a4)
+ *   - basis carry-over per scenario      pywr/solvers/cython_glpk.pyx:197-232,1026,1063 (a7)
+ *   - result extraction                  pywr/solvers/cython_glpk.pyx:1068-1093       (a8)
+ *   - edge formulation equivalents       pywr/solvers/cython_glpk.pyx:1649-1918
+ *
+ * The LP arithmetic itself lives in GNU GLPK (glp_simplex), a third-party C library that is NOT
+ * vendored in the reference and is NOT installed in this image (no glpk.h / libglpk; the reference
+ * does not pin a version: setup.py:76-83 `libraries=["glpk"]`, CI uses glpk 5.0).  GLPK's simplex
+ * is therefore restated here by its published contract — minimise c'x s.t. lb <= Ax <= ub, x >= 0,
+ * warm-started from the scenario's previous basis, optimal vertex returned — as a dense bounded
+ * dual simplex with a primal clean-up phase.  Parity is anchored on the reference's own
+ * known-answer tests (tests/test_analytical.py, test_run.py, test_scenarios.py,
+ * test_agg_constraints.py, ... run with this oracle plugged into the built reference through
+ * oracle/pywr_oracle_solver.py) and cross-checked against scipy's HiGHS.
+ * Parity with GLPK on the long benchmark configurations is UNPINNED (GLPK cannot run here).
+ *
+ * Dictionary form.  Variables v = (x_0..x_{n-1}, r_0..r_{m-1}) with r = A x.  A basis is a split
+ * into m basic and n non-basic variables; T (m x n, dense) expresses the basic variables through
+ * the non-basic ones, v_head[i] = sum_j T[i][j] v_nb[j].  The slack basis is T = A.  All arithmetic
+ * that the CUDA kernels mirror is written with explicit fma() in a fixed order so that both sides
+ * can agree to the last bit.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/b200lp.h"
+
+#define ORC_TOL_PRIMAL 1e-9
+#define ORC_TOL_DUAL 1e-9
+#define ORC_TOL_PIVOT 1e-9
+#define ORC_TIE_REL 1e-9
+#define ORC_TIE_ABS 1e-12
+#define ORC_REFACTOR_PIVOTS 40
+
+enum { VS_BASIC = 1, VS_NL = 2, VS_NU = 3, VS_NF = 4, VS_NS = 5 }; /* GLPK's GLP_BS.. codes */
+
+typedef struct {
+    double *T;     /* [m*n] dictionary                               */
+    double *d;     /* [n] reduced costs for the true objective       */
+    int32_t *head; /* [m] variable in basic position i               */
+    int32_t *nb;   /* [n] variable in non-basic position j           */
+    int8_t *vstat; /* [n+m] per-variable status (the "basis")        */
+    double *vol;   /* [n_storage] device-state volume equivalent     */
+    int32_t npiv;  /* pivots since the last re-factorisation         */
+    int32_t valid; /* T/d/head/nb consistent with vstat              */
+    int32_t status;
+} orc_scen;
+
+typedef struct {
+    b200lp_structure s; /* deep copy */
+    int32_t S, m, n, NV, nnz;
+    double *A; /* dense m*n image of a_val (static part) */
+    orc_scen *sc;
+    int64_t pivots, refactors, steps;
+    int32_t first_bad, bad_code;
+    int32_t threads;
+} orc_handle;
+
+/* ------------------------------------------------------------------ helpers */
+
+static void *dup_mem(const void *p, size_t bytes) {
+    void *q = malloc(bytes ? bytes : 1);
+    if (p && bytes) memcpy(q, p, bytes);
+    return q;
+}
+
+static inline double ref_value(const orc_handle *h, int32_t ref, const double *slots, int32_t sidx) {
+    if (ref >= 0) return slots[(size_t)ref * h->S + sidx];
+    return h->s.consts[-ref - 1];
+}
+
+/* cython_glpk.pyx:934-945 + constraint_type :66-77: clip tiny values, FX when |lb-ub| < 1e-8 */
+static inline void type_bounds(double *lo, double *hi) {
+    if (fabs(*lo) < 1e-8) *lo = 0.0;
+    if (fabs(*hi) < 1e-8) *hi = 0.0;
+    if (fabs(*lo - *hi) < 1e-8) *hi = *lo;
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+
+void *orc_create(const b200lp_structure *s, int32_t S) {
+    if (!s || s->abi_version != B200LP_ABI_VERSION || S <= 0) return NULL;
+    orc_handle *h = (orc_handle *)calloc(1, sizeof(orc_handle));
+    h->s = *s;
+    int32_t m = s->n_rows, n = s->n_cols, N = s->n_nodes;
+    h->S = S; h->m = m; h->n = n; h->NV = m + n;
+    h->nnz = s->a_indptr[m];
+    h->s.a_indptr = dup_mem(s->a_indptr, sizeof(int32_t) * (m + 1));
+    h->s.a_col = dup_mem(s->a_col, sizeof(int32_t) * h->nnz);
+    h->s.a_val = dup_mem(s->a_val, sizeof(double) * h->nnz);
+    h->s.row_kind = dup_mem(s->row_kind, sizeof(int32_t) * m);
+    h->s.row_lb_ref = dup_mem(s->row_lb_ref, sizeof(int32_t) * m);
+    h->s.row_ub_ref = dup_mem(s->row_ub_ref, sizeof(int32_t) * m);
+    h->s.st_kind = dup_mem(s->st_kind, sizeof(int32_t) * s->n_storage);
+    h->s.st_vol_ref = dup_mem(s->st_vol_ref, sizeof(int32_t) * s->n_storage);
+    h->s.st_minv_ref = dup_mem(s->st_minv_ref, sizeof(int32_t) * s->n_storage);
+    h->s.st_maxv_ref = dup_mem(s->st_maxv_ref, sizeof(int32_t) * s->n_storage);
+    h->s.st_active_ref = dup_mem(s->st_active_ref, sizeof(int32_t) * s->n_storage);
+    int32_t ncost = s->cost_indptr[n];
+    h->s.cost_indptr = dup_mem(s->cost_indptr, sizeof(int32_t) * (n + 1));
+    h->s.cost_ref = dup_mem(s->cost_ref, sizeof(int32_t) * ncost);
+    h->s.cost_w = dup_mem(s->cost_w, sizeof(double) * ncost);
+    h->s.dyn_a_nz = dup_mem(s->dyn_a_nz, sizeof(int32_t) * s->n_dyn_a);
+    h->s.dyn_a_ref = dup_mem(s->dyn_a_ref, sizeof(int32_t) * s->n_dyn_a);
+    h->s.dyn_a_scale = dup_mem(s->dyn_a_scale, sizeof(double) * s->n_dyn_a);
+    int32_t nflow = s->flow_indptr[N];
+    h->s.flow_indptr = dup_mem(s->flow_indptr, sizeof(int32_t) * (N + 1));
+    h->s.flow_col = dup_mem(s->flow_col, sizeof(int32_t) * nflow);
+    h->s.flow_w = dup_mem(s->flow_w, sizeof(double) * nflow);
+    h->s.consts = dup_mem(s->consts, sizeof(double) * s->n_consts);
+
+    h->A = (double *)calloc((size_t)m * n + 1, sizeof(double));
+    for (int32_t i = 0; i < m; i++)
+        for (int32_t k = s->a_indptr[i]; k < s->a_indptr[i + 1]; k++)
+            h->A[(size_t)i * n + s->a_col[k]] += s->a_val[k];
+
+    h->sc = (orc_scen *)calloc(S, sizeof(orc_scen));
+    for (int32_t k = 0; k < S; k++) {
+        orc_scen *c = &h->sc[k];
+        c->T = (double *)calloc((size_t)m * n + 1, sizeof(double));
+        c->d = (double *)calloc(n + 1, sizeof(double));
+        c->head = (int32_t *)calloc(m + 1, sizeof(int32_t));
+        c->nb = (int32_t *)calloc(n + 1, sizeof(int32_t));
+        c->vstat = (int8_t *)calloc(m + n + 1, sizeof(int8_t));
+        c->vol = (double *)calloc(s->n_storage + 1, sizeof(double));
+    }
+    h->first_bad = -1;
+    return h;
+}
+
+void orc_destroy(void *hv) {
+    orc_handle *h = (orc_handle *)hv;
+    if (!h) return;
+    for (int32_t k = 0; k < h->S; k++) {
+        orc_scen *c = &h->sc[k];
+        free(c->T); free(c->d); free(c->head); free(c->nb); free(c->vstat); free(c->vol);
+    }
+    free(h->sc); free(h->A);
+    free((void *)h->s.a_indptr); free((void *)h->s.a_col); free((void *)h->s.a_val);
+    free((void *)h->s.row_kind); free((void *)h->s.row_lb_ref); free((void *)h->s.row_ub_ref);
+    free((void *)h->s.st_kind); free((void *)h->s.st_vol_ref); free((void *)h->s.st_minv_ref);
+    free((void *)h->s.st_maxv_ref); free((void *)h->s.st_active_ref);
+    free((void *)h->s.cost_indptr); free((void *)h->s.cost_ref); free((void *)h->s.cost_w);
+    free((void *)h->s.dyn_a_nz); free((void *)h->s.dyn_a_ref); free((void *)h->s.dyn_a_scale);
+    free((void *)h->s.flow_indptr); free((void *)h->s.flow_col); free((void *)h->s.flow_w);
+    free((void *)h->s.consts);
+    free(h);
+}
+
+/* Solver.reset(): is_first_solve = True (cython_glpk.pyx:757-759) -> every scenario restarts from
+ * the slack basis (all rows basic, all columns at their lower bound 0). */
+void orc_reset(void *hv, const double *vol0) {
+    orc_handle *h = (orc_handle *)hv;
+    for (int32_t k = 0; k < h->S; k++) {
+        orc_scen *c = &h->sc[k];
+        for (int32_t j = 0; j < h->n; j++) c->vstat[j] = VS_NL;
+        for (int32_t i = 0; i < h->m; i++) c->vstat[h->n + i] = VS_BASIC;
+        c->valid = 0; c->npiv = 0; c->status = 0;
+        for (int32_t q = 0; q < h->s.n_storage; q++) c->vol[q] = vol0 ? vol0[(size_t)q * h->S + k] : 0.0;
+    }
+    h->first_bad = -1; h->bad_code = 0;
+}
+
+/* ------------------------------------------------------------------ the dictionary simplex */
+
+typedef struct {
+    int32_t m, n;
+    double *T, *d, *dw;
+    int32_t *head, *nb;
+    int8_t *vstat;
+    const double *lo, *hi; /* [NV] bounds per variable */
+    double *xn;            /* [n] value of each non-basic position */
+    double *beta;          /* [m] value of each basic position     */
+    int64_t pivots;
+} dict;
+
+/* exchange basic position r with non-basic position q */
+static void dict_pivot(dict *D, int32_t r, int32_t q, int use_dw) {
+    const int32_t m = D->m, n = D->n;
+    double *T = D->T;
+    double *prow = T + (size_t)r * n;
+    const double inv = 1.0 / prow[q];
+    for (int32_t j = 0; j < n; j++)
+        if (j != q) prow[j] = -prow[j] * inv;
+    prow[q] = inv;
+    for (int32_t i = 0; i < m; i++) {
+        if (i == r) continue;
+        double *row = T + (size_t)i * n;
+        const double f = row[q];
+        for (int32_t j = 0; j < n; j++)
+            if (j != q) row[j] = fma(f, prow[j], row[j]);
+        row[q] = f * inv;
+    }
+    {
+        const double f = D->d[q];
+        for (int32_t j = 0; j < n; j++)
+            if (j != q) D->d[j] = fma(f, prow[j], D->d[j]);
+        D->d[q] = f * inv;
+    }
+    if (use_dw) {
+        const double f = D->dw[q];
+        for (int32_t j = 0; j < n; j++)
+            if (j != q) D->dw[j] = fma(f, prow[j], D->dw[j]);
+        D->dw[q] = f * inv;
+    }
+    int32_t t = D->head[r]; D->head[r] = D->nb[q]; D->nb[q] = t;
+    D->pivots++;
+}
+
+/* d_j = c_nb[j] + sum_i c_head[i] T[i][j]  (row variables have zero cost) */
+static void dict_reduced_costs(dict *D, const double *c) {
+    const int32_t m = D->m, n = D->n;
+    for (int32_t j = 0; j < n; j++) {
+        double acc = (D->nb[j] < n) ? c[D->nb[j]] : 0.0;
+        for (int32_t i = 0; i < m; i++) {
+            const int32_t v = D->head[i];
+            if (v < n) acc = fma(c[v], D->T[(size_t)i * n + j], acc);
+        }
+        D->d[j] = acc;
+    }
+}
+
+/* Rebuild T for the basis recorded in vstat by pivoting from the slack basis (Gauss-Jordan with
+ * partial pivoting over the rows that must become non-basic).  Returns 0, or -1 when singular. */
+static int dict_refactor(dict *D, const double *A) {
+    const int32_t m = D->m, n = D->n;
+    memcpy(D->T, A, sizeof(double) * (size_t)m * n);
+    for (int32_t i = 0; i < m; i++) D->head[i] = n + i;
+    for (int32_t j = 0; j < n; j++) D->nb[j] = j;
+    for (int32_t j = 0; j < n; j++) D->d[j] = 0.0; /* recomputed by the caller */
+    for (int32_t q = 0; q < n; q++) {
+        if (D->vstat[q] != VS_BASIC) continue;
+        int32_t r = -1; double best = ORC_TOL_PIVOT;
+        for (int32_t i = 0; i < m; i++) {
+            const int32_t v = D->head[i];
+            if (v < n || D->vstat[v] == VS_BASIC) continue; /* slot already used / row stays basic */
+            const double a = fabs(D->T[(size_t)i * n + q]);
+            if (a > best) { best = a; r = i; }
+        }
+        if (r < 0) return -1;
+        dict_pivot(D, r, q, 0);
+        D->pivots--; /* not a simplex pivot */
+    }
+    return 0;
+}
+
+static void dict_slack_basis(dict *D) {
+    for (int32_t j = 0; j < D->n; j++) D->vstat[j] = VS_NL;
+    for (int32_t i = 0; i < D->m; i++) D->vstat[D->n + i] = VS_BASIC;
+}
+
+/* status + value of every non-basic position for the current bounds; returns 1 if some reduced
+ * cost in `dj` is dual infeasible after the boxed variables have been put on their better bound */
+static int dict_place_nonbasics(dict *D, const double *dj) {
+    int infeas = 0;
+    for (int32_t j = 0; j < D->n; j++) {
+        const int32_t v = D->nb[j];
+        const double lo = D->lo[v], hi = D->hi[v];
+        int8_t st = D->vstat[v];
+        if (lo == hi) st = VS_NS;
+        else if (lo > -INFINITY && hi < INFINITY) {
+            if (dj[j] > ORC_TOL_DUAL) st = VS_NL;
+            else if (dj[j] < -ORC_TOL_DUAL) st = VS_NU;
+            else if (st != VS_NL && st != VS_NU) st = VS_NL;
+        } else if (lo > -INFINITY) { st = VS_NL; if (dj[j] < -ORC_TOL_DUAL) infeas = 1; }
+        else if (hi < INFINITY) { st = VS_NU; if (dj[j] > ORC_TOL_DUAL) infeas = 1; }
+        else { st = VS_NF; if (fabs(dj[j]) > ORC_TOL_DUAL) infeas = 1; }
+        D->vstat[v] = st;
+        D->xn[j] = (st == VS_NU) ? hi : (st == VS_NF ? 0.0 : lo);
+    }
+    return infeas;
+}
+
+static void dict_basic_values(dict *D) {
+    const int32_t m = D->m, n = D->n;
+    for (int32_t i = 0; i < m; i++) {
+        double acc = 0.0;
+        const double *row = D->T + (size_t)i * n;
+        for (int32_t j = 0; j < n; j++) acc = fma(row[j], D->xn[j], acc);
+        D->beta[i] = acc;
+    }
+}
+
+/* Runs the simplex from the current dictionary.  Returns a B200LP_ST_* code. */
+static int dict_solve(dict *D) {
+    const int32_t m = D->m, n = D->n;
+    const int32_t cap_bland = 20 * (m + n) + 50, cap_fail = 200 * (m + n) + 1000;
+    int shifted = dict_place_nonbasics(D, D->d);
+    /* cost shifting: make the working reduced costs dual feasible, fix the rest in the primal phase */
+    for (int32_t j = 0; j < n; j++) {
+        double w = D->d[j];
+        if (shifted) {
+            const int8_t st = D->vstat[D->nb[j]];
+            if ((st == VS_NL && w < -ORC_TOL_DUAL) || (st == VS_NU && w > ORC_TOL_DUAL) ||
+                (st == VS_NF && fabs(w) > ORC_TOL_DUAL)) w = 0.0;
+        }
+        D->dw[j] = w;
+    }
+    int phase = 0; /* 0: dual simplex on dw, 1: primal simplex on d */
+    for (int32_t it = 0;; it++) {
+        if (it > cap_fail) return B200LP_ST_ITERLIMIT;
+        const int bland = it > cap_bland;
+        dict_basic_values(D);
+        if (phase == 0) {
+            /* leaving variable: largest bound violation */
+            int32_t r = -1; double worst = 0.0; int dir = 0;
+            for (int32_t i = 0; i < m; i++) {
+                const int32_t v = D->head[i];
+                const double b = D->beta[i];
+                double viol = 0.0; int dd = 0;
+                if (b < D->lo[v] - ORC_TOL_PRIMAL * (1.0 + fabs(D->lo[v]))) { viol = D->lo[v] - b; dd = +1; }
+                else if (b > D->hi[v] + ORC_TOL_PRIMAL * (1.0 + fabs(D->hi[v]))) { viol = b - D->hi[v]; dd = -1; }
+                if (dd != 0 && (bland ? (r < 0) : (viol > worst))) { worst = viol; r = i; dir = dd; }
+            }
+            if (r < 0) {
+                if (!shifted) return B200LP_ST_OPTIMAL;
+                /* primal feasible for the shifted costs: finish with the primal simplex on the
+                 * true reduced costs (non-basic variables keep their bounds: moving a boxed one
+                 * now would destroy primal feasibility; it enters and flips in the ratio test) */
+                phase = 1; shifted = 0;
+                continue;
+            }
+            /* dual ratio test on row r */
+            const double *prow = D->T + (size_t)r * n;
+            double rmin = INFINITY;
+            for (int32_t j = 0; j < n; j++) {
+                const int8_t st = D->vstat[D->nb[j]];
+                const double a = prow[j] * (double)dir;
+                int ok = 0;
+                if (st == VS_NL) ok = a > ORC_TOL_PIVOT;
+                else if (st == VS_NU) ok = a < -ORC_TOL_PIVOT;
+                else if (st == VS_NF) ok = fabs(a) > ORC_TOL_PIVOT;
+                if (!ok) continue;
+                const double ratio = fabs(D->dw[j]) / fabs(a);
+                if (ratio < rmin) rmin = ratio;
+            }
+            if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
+            const double thr = rmin * (1.0 + ORC_TIE_REL) + ORC_TIE_ABS;
+            int32_t q = -1; double amax = 0.0;
+            for (int32_t j = 0; j < n; j++) {
+                const int8_t st = D->vstat[D->nb[j]];
+                const double a = prow[j] * (double)dir;
+                int ok = 0;
+                if (st == VS_NL) ok = a > ORC_TOL_PIVOT;
+                else if (st == VS_NU) ok = a < -ORC_TOL_PIVOT;
+                else if (st == VS_NF) ok = fabs(a) > ORC_TOL_PIVOT;
+                if (!ok) continue;
+                const double ratio = fabs(D->dw[j]) / fabs(a);
+                if (ratio > thr) continue;
+                if (bland ? (q < 0) : (fabs(a) > amax)) { amax = fabs(a); q = j; }
+            }
+            const int32_t vout = D->head[r];
+            dict_pivot(D, r, q, 1);
+            D->vstat[D->head[r]] = VS_BASIC;
+            D->vstat[vout] = (D->lo[vout] == D->hi[vout]) ? VS_NS : (dir > 0 ? VS_NL : VS_NU);
+            D->xn[q] = dir > 0 ? D->lo[vout] : D->hi[vout];
+        } else {
+            /* entering variable: largest dual infeasibility (Dantzig) */
+            int32_t q = -1; double worst = 0.0; int dir = 0;
+            for (int32_t j = 0; j < n; j++) {
+                const int8_t st = D->vstat[D->nb[j]];
+                const double dj = D->d[j];
+                int dd = 0;
+                if ((st == VS_NL || st == VS_NF) && dj < -ORC_TOL_DUAL) dd = +1;
+                else if ((st == VS_NU || st == VS_NF) && dj > ORC_TOL_DUAL) dd = -1;
+                if (dd != 0 && (bland ? (q < 0) : (fabs(dj) > worst))) { worst = fabs(dj); q = j; dir = dd; }
+            }
+            if (q < 0) return B200LP_ST_OPTIMAL;
+            const int32_t vin = D->nb[q];
+            /* primal ratio test down column q */
+            double tmin = D->hi[vin] - D->lo[vin]; /* own range: bound flip */
+            if (!(tmin < INFINITY)) tmin = INFINITY;
+            double step_min = INFINITY;
+            for (int32_t i = 0; i < m; i++) {
+                const int32_t v = D->head[i];
+                const double a = D->T[(size_t)i * n + q] * (double)dir;
+                double step = INFINITY;
+                if (a > ORC_TOL_PIVOT) { if (D->hi[v] < INFINITY) step = (D->hi[v] - D->beta[i]) / a; }
+                else if (a < -ORC_TOL_PIVOT) { if (D->lo[v] > -INFINITY) step = (D->lo[v] - D->beta[i]) / a; }
+                if (step < 0.0) step = 0.0;
+                if (step < step_min) step_min = step;
+            }
+            if (step_min == INFINITY && tmin == INFINITY) return B200LP_ST_UNBOUNDED;
+            if (tmin <= step_min) {
+                /* the entering variable reaches its own opposite bound first: no basis change */
+                D->vstat[vin] = dir > 0 ? VS_NU : VS_NL;
+                D->xn[q] = dir > 0 ? D->hi[vin] : D->lo[vin];
+                continue;
+            }
+            const double thr = step_min * (1.0 + ORC_TIE_REL) + ORC_TIE_ABS;
+            int32_t r = -1; double amax = 0.0; int hit_upper = 0;
+            for (int32_t i = 0; i < m; i++) {
+                const int32_t v = D->head[i];
+                const double a = D->T[(size_t)i * n + q] * (double)dir;
+                double step = INFINITY; int up = 0;
+                if (a > ORC_TOL_PIVOT) { if (D->hi[v] < INFINITY) { step = (D->hi[v] - D->beta[i]) / a; up = 1; } }
+                else if (a < -ORC_TOL_PIVOT) { if (D->lo[v] > -INFINITY) step = (D->lo[v] - D->beta[i]) / a; }
+                if (step < 0.0) step = 0.0;
+                if (step > thr) continue;
+                if (bland ? (r < 0) : (fabs(a) > amax)) { amax = fabs(a); r = i; hit_upper = up; }
+            }
+            const int32_t vout = D->head[r];
+            dict_pivot(D, r, q, 0);
+            D->vstat[D->head[r]] = VS_BASIC;
+            D->vstat[vout] = (D->lo[vout] == D->hi[vout]) ? VS_NS : (hit_upper ? VS_NU : VS_NL);
+            D->xn[q] = hit_upper ? D->hi[vout] : D->lo[vout];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ one scenario, one timestep */
+
+static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, const double *slots, double *node_flow,
+                              double *col_flow, double *objective, double *work, int64_t *pivots,
+                              int64_t *refactors) {
+    const b200lp_structure *s = &h->s;
+    const int32_t m = h->m, n = h->n, NV = h->NV, N = s->n_nodes, S = h->S;
+    orc_scen *c = &h->sc[sidx];
+    double *lo = work, *hi = lo + NV, *cost = hi + NV, *xn = cost + n, *beta = xn + n, *dw = beta + m,
+           *x = dw + n, *Ad = x + n;
+    int nan_seen = 0, bad_bounds = 0;
+
+    /* (a5/a6) bounds: columns are x >= 0 (cython_glpk.pyx:490-491) */
+    for (int32_t j = 0; j < n; j++) { lo[j] = 0.0; hi[j] = INFINITY; }
+    for (int32_t i = 0; i < m; i++) {
+        double l, u;
+        if (s->row_kind[i] == B200LP_ROW_FLOW) {
+            l = ref_value(h, s->row_lb_ref[i], slots, sidx);
+            u = ref_value(h, s->row_ub_ref[i], slots, sidx);
+            if (isnan(l) || isnan(u)) nan_seen = 1;
+            type_bounds(&l, &u);
+        } else {
+            const int32_t k = s->row_lb_ref[i];
+            const double maxv = ref_value(h, s->st_maxv_ref[k], slots, sidx);
+            const double minv = ref_value(h, s->st_minv_ref[k], slots, sidx);
+            const double vol = (s->st_vol_ref[k] == B200LP_REF_STATE) ? c->vol[k]
+                                                                       : ref_value(h, s->st_vol_ref[k], slots, sidx);
+            int active = 1;
+            if (s->st_kind[k] == B200LP_ST_KIND_VIRTUAL) active = ref_value(h, s->st_active_ref[k], slots, sidx) != 0.0;
+            if (isnan(maxv) || isnan(minv) || isnan(vol)) nan_seen = 1;
+            if (maxv == minv) { l = 0.0; u = 0.0; }
+            else if (!active) { l = -INFINITY; u = INFINITY; }
+            else {
+                const double avail = fmax(vol - minv, 0.0);
+                l = -avail / days;
+                u = fmax(maxv - vol, 0.0) / days;
+                type_bounds(&l, &u);
+            }
+        }
+        if (l > u) bad_bounds = 1;
+        lo[n + i] = l; hi[n + i] = u;
+    }
+    /* (a3) objective */
+    int cost_dynamic = 0;
+    for (int32_t j = 0; j < n; j++) {
+        double acc = 0.0;
+        for (int32_t k = s->cost_indptr[j]; k < s->cost_indptr[j + 1]; k++) {
+            if (s->cost_ref[k] >= 0) cost_dynamic = 1;
+            acc += s->cost_w[k] * ref_value(h, s->cost_ref[k], slots, sidx);
+        }
+        if (isnan(acc)) nan_seen = 1;
+        if (s->cost_clip && fabs(acc) < 1e-8) acc = 0.0;
+        cost[j] = acc;
+    }
+    /* (a4) dynamic matrix entries */
+    const double *A = h->A;
+    if (s->n_dyn_a > 0) {
+        memcpy(Ad, h->A, sizeof(double) * (size_t)m * n);
+        for (int32_t k = 0; k < s->n_dyn_a; k++) {
+            const int32_t nz = s->dyn_a_nz[k];
+            int32_t row = 0;
+            while (s->a_indptr[row + 1] <= nz) row++;
+            const double v = s->dyn_a_scale[k] * ref_value(h, s->dyn_a_ref[k], slots, sidx);
+            if (isnan(v)) nan_seen = 1;
+            /* replace the static contribution of this non-zero */
+            Ad[(size_t)row * n + s->a_col[nz]] += v - s->a_val[nz];
+        }
+        A = Ad;
+    }
+    if (nan_seen) { c->status = B200LP_ST_NAN; return c->status; }
+    if (bad_bounds) { c->status = B200LP_ST_INFEASIBLE; return c->status; }
+
+    dict D = {m, n, c->T, c->d, dw, c->head, c->nb, c->vstat, lo, hi, xn, beta, 0};
+    int need_refactor = !c->valid || s->n_dyn_a > 0 || c->npiv >= ORC_REFACTOR_PIVOTS;
+    const int fresh0 = need_refactor;
+    int st = 0;
+    /* attempt 0: warm start.  On failure, the role of retry_solve (cython_glpk.pyx:1034-1042):
+     * attempt 1 re-factorises the same basis (protects against drift of T), attempt 2 restarts
+     * from the standard (slack) basis. */
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (attempt == 1 && fresh0) continue;
+        if (attempt == 2) dict_slack_basis(&D);
+        if (attempt > 0) need_refactor = 1;
+        if (need_refactor) {
+            if (dict_refactor(&D, A) != 0) {
+                dict_slack_basis(&D);
+                dict_refactor(&D, A);
+            }
+            dict_reduced_costs(&D, cost);
+            c->npiv = 0; c->valid = 1; (*refactors)++;
+        } else if (cost_dynamic) {
+            dict_reduced_costs(&D, cost);
+        }
+        const int64_t p0 = D.pivots;
+        st = dict_solve(&D);
+        c->npiv += (int32_t)(D.pivots - p0);
+        if (st == B200LP_ST_OPTIMAL) break;
+    }
+    *pivots += D.pivots;
+    c->status = st;
+    if (st != B200LP_ST_OPTIMAL) { c->valid = 0; return st; }
+
+    /* (a8) primal values of the columns, objective, node flows */
+    for (int32_t j = 0; j < n; j++) {
+        const int32_t v = c->nb[j];
+        if (v < n) x[v] = xn[j];
+    }
+    dict_basic_values(&D);
+    for (int32_t i = 0; i < m; i++) {
+        const int32_t v = c->head[i];
+        if (v < n) x[v] = beta[i];
+    }
+    if (col_flow) for (int32_t j = 0; j < n; j++) col_flow[(size_t)j * S + sidx] = x[j];
+    if (objective) {
+        double acc = 0.0;
+        for (int32_t j = 0; j < n; j++) acc = fma(cost[j], x[j], acc);
+        objective[sidx] = acc;
+    }
+    if (node_flow) {
+        for (int32_t v = 0; v < N; v++) {
+            double acc = 0.0;
+            for (int32_t k = s->flow_indptr[v]; k < s->flow_indptr[v + 1]; k++)
+                acc = fma(s->flow_w[k], x[s->flow_col[k]], acc);
+            node_flow[(size_t)v * S + sidx] = acc;
+        }
+    }
+    return st;
+}
+
+/* The loop of CythonGLPKSolver.solve (cython_glpk.pyx:821-831), optionally split over host threads
+ * (contiguous scenario blocks, the reference-native way to use several cores: Scenario.slice,
+ * pywr/_core.pyx:108-128).  Returns the number of failed scenarios. */
+typedef struct {
+    orc_handle *h;
+    int32_t s0, s1;
+    double days;
+    const double *slots;
+    double *node_flow, *col_flow, *objective;
+    int nbad;
+    int32_t first_bad, bad_code;
+    int64_t pivots, refactors;
+} orc_job;
+
+static void *orc_worker(void *arg) {
+    orc_job *J = (orc_job *)arg;
+    orc_handle *h = J->h;
+    const int32_t m = h->m, n = h->n;
+    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + m + (size_t)m * n + 8));
+    J->nbad = 0; J->first_bad = -1; J->bad_code = 0; J->pivots = 0; J->refactors = 0;
+    for (int32_t k = J->s0; k < J->s1; k++) {
+        int st = orc_solve_scenario(h, k, J->days, J->slots, J->node_flow, J->col_flow, J->objective, work,
+                                    &J->pivots, &J->refactors);
+        if (st != B200LP_ST_OPTIMAL) {
+            J->nbad++;
+            if (J->first_bad < 0) { J->first_bad = k; J->bad_code = st; }
+        }
+    }
+    free(work);
+    return NULL;
+}
+
+int orc_step(void *hv, double days, const double *slots, double *node_flow, double *col_flow, double *objective) {
+    orc_handle *h = (orc_handle *)hv;
+    int nt = h->threads < 1 ? 1 : h->threads;
+    if (nt > h->S) nt = h->S;
+    orc_job *jobs = (orc_job *)calloc(nt, sizeof(orc_job));
+    pthread_t *tid = (pthread_t *)calloc(nt, sizeof(pthread_t));
+    for (int t = 0; t < nt; t++) {
+        jobs[t].h = h; jobs[t].days = days; jobs[t].slots = slots;
+        jobs[t].node_flow = node_flow; jobs[t].col_flow = col_flow; jobs[t].objective = objective;
+        jobs[t].s0 = (int32_t)((int64_t)h->S * t / nt);
+        jobs[t].s1 = (int32_t)((int64_t)h->S * (t + 1) / nt);
+    }
+    for (int t = 1; t < nt; t++) pthread_create(&tid[t], NULL, orc_worker, &jobs[t]);
+    orc_worker(&jobs[0]);
+    for (int t = 1; t < nt; t++) pthread_join(tid[t], NULL);
+    int nbad = 0;
+    h->first_bad = -1; h->bad_code = 0;
+    for (int t = 0; t < nt; t++) {
+        nbad += jobs[t].nbad;
+        h->pivots += jobs[t].pivots; h->refactors += jobs[t].refactors;
+        if (jobs[t].first_bad >= 0 && h->first_bad < 0) { h->first_bad = jobs[t].first_bad; h->bad_code = jobs[t].bad_code; }
+    }
+    h->steps++;
+    free(jobs); free(tid);
+    return nbad;
+}
+
+void orc_set_threads(void *hv, int32_t n) { ((orc_handle *)hv)->threads = n; }
+
+void orc_set_consts(void *hv, const double *consts) {
+    orc_handle *h = (orc_handle *)hv;
+    memcpy((void *)h->s.consts, consts, sizeof(double) * h->s.n_consts);
+}
+
+void orc_status(void *hv, int32_t *first_bad, int32_t *code) {
+    orc_handle *h = (orc_handle *)hv;
+    if (first_bad) *first_bad = h->first_bad;
+    if (code) *code = h->bad_code;
+}
+
+void orc_get_basis(void *hv, int32_t *row_stat, int32_t *col_stat) {
+    orc_handle *h = (orc_handle *)hv;
+    for (int32_t k = 0; k < h->S; k++) {
+        for (int32_t j = 0; j < h->n; j++) col_stat[(size_t)k * h->n + j] = h->sc[k].vstat[j];
+        for (int32_t i = 0; i < h->m; i++) row_stat[(size_t)k * h->m + i] = h->sc[k].vstat[h->n + i];
+    }
+}
+
+void orc_get_volume(void *hv, double *vol) {
+    orc_handle *h = (orc_handle *)hv;
+    for (int32_t q = 0; q < h->s.n_storage; q++)
+        for (int32_t k = 0; k < h->S; k++) vol[(size_t)q * h->S + k] = h->sc[k].vol[q];
+}
+
+void orc_set_volume(void *hv, const double *vol) {
+    orc_handle *h = (orc_handle *)hv;
+    for (int32_t q = 0; q < h->s.n_storage; q++)
+        for (int32_t k = 0; k < h->S; k++) h->sc[k].vol[q] = vol[(size_t)q * h->S + k];
+}
+
+void orc_counters(void *hv, int64_t *pivots, int64_t *refactors, int64_t *steps) {
+    orc_handle *h = (orc_handle *)hv;
+    if (pivots) *pivots = h->pivots;
+    if (refactors) *refactors = h->refactors;
+    if (steps) *steps = h->steps;
+}

@@ -1,0 +1,262 @@
+"""Pywr solver plug-in: ``Model(solver="b200")`` / ``"solver": {"name": "b200"}`` / ``PYWR_SOLVER=b200``.
+
+Host side of the B200 scenario-batched LP engine.  Mirrors the interface of the reference's
+``CythonGLPKSolver`` wrapper (``pywr/solvers/__init__.py:75-194``): ``setup(model)``,
+``solve(model)``, ``reset()``, ``stats``, ``settings`` and the attributes the reference test-suite
+reads (``use_unsafe_api``, ``set_fixed_*_once``, ``use_presolve``, ``retry_solve``,
+``save_routes_flows``, ``routes``, ``routes_flows_array``).
+
+Where the reference loops ``for scenario_index in model.scenarios.combinations:
+_solve_scenario(...)`` (``cython_glpk.pyx:821-831``), this solver gathers every dynamic bound /
+cost for ALL scenarios into scenario-contiguous planes of one pinned buffer (using the vectorised
+``get_all_*`` getters, ``pywr/_core.pyx:566-574,618-626,681-689,1202-1238``), makes ONE engine call
+per timestep, and commits the returned node flows with ``commit_all`` (``_core.pyx:485-489``).
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from .structure import LPStructure, build_structure
+
+try:  # the reference only defines GLPKError when its GLPK extension was built
+    from pywr.solvers import GLPKError as _BaseLPError
+except Exception:  # pragma: no cover - depends on the pywr build
+    _BaseLPError = Exception
+
+
+try:
+    from pywr.solvers import Solver as _SolverBase
+except Exception:  # pragma: no cover - pywr absent: the C-ABI / engine are still usable on their own
+    _SolverBase = object
+
+
+class B200LPError(_BaseLPError):
+    """NaN in a bound, cost or coefficient (role of ``GLPKError``, ``cython_glpk.pyx:286-335``)."""
+
+
+_STATUS_TEXT = {
+    1: "no primal feasible solution",
+    2: "no dual feasible solution",
+    3: "iteration limit exceeded",
+    4: "NaN detected",
+    5: "singular matrix",
+}
+
+
+class BatchedLPSolver(_SolverBase):
+    """Engine-agnostic host logic.  Subclasses provide ``_make_engine(structure, n_scenarios)``
+    returning an object with ``reset(vol0)``, ``step(days, slots, node_flow, col_flow, objective)``,
+    ``status()``, ``alloc_planes(n)``, ``set_consts(consts)``, ``close()`` and ``counters()``."""
+
+    name = "batched-lp"
+    formulation = "route"
+
+    def __init__(self, save_routes_flows=False, retry_solve=False, use_presolve=False, check_nan=True, **kwargs):
+        super().__init__()
+        self.save_routes_flows = save_routes_flows
+        self.retry_solve = retry_solve  # the engine always retries from the standard basis
+        self.use_presolve = use_presolve
+        self.check_nan = check_nan
+        self.use_unsafe_api = not check_nan
+        self.set_fixed_flows_once = False
+        self.set_fixed_costs_once = False
+        self.set_fixed_factors_once = False
+        self.engine_args = kwargs
+        self._engine = None
+        self._structure: LPStructure | None = None
+        self._model = None
+        self._stats = None
+        self.routes = None
+        self.routes_flows_array = None
+        self.last_objective = None
+
+    # -- reference attributes ---------------------------------------------------------------
+    @property
+    def stats(self):
+        return self._stats
+
+    @property
+    def settings(self):
+        return {
+            "use_presolve": self.use_presolve,
+            "save_routes_flows": self.save_routes_flows,
+            "retry_solve": self.retry_solve,
+            "set_fixed_flows_once": self.set_fixed_flows_once,
+            "set_fixed_costs_once": self.set_fixed_costs_once,
+            "set_fixed_factors_once": self.set_fixed_factors_once,
+            "formulation": self.formulation,
+        }
+
+    @property
+    def structure(self) -> LPStructure:
+        return self._structure
+
+    def _make_engine(self, structure, n_scenarios):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    # -- Solver API -----------------------------------------------------------------------------
+    def setup(self, model):
+        """Role of ``CythonGLPKSolver.setup`` (``cython_glpk.pyx:388-755``)."""
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        s = build_structure(model, self.formulation)
+        S = len(model.scenarios.combinations)
+        self._model = model
+        self._structure = s
+        self._S = S
+        self.routes = s.routes
+        self._engine = self._make_engine(s, S)
+        self._slots = self._engine.alloc_planes(max(s.n_slots, 1))
+        self._node_flow = self._engine.alloc_planes(s.n_nodes)
+        self._col_flow = self._engine.alloc_planes(s.n_cols) if self.save_routes_flows else None
+        self._objective = self._engine.alloc_planes(1)
+        self._has_flow = np.diff(s.flow_indptr) > 0
+        self.routes_flows_array = None
+        self._stats = {
+            "total": 0.0, "lp_solve": 0.0, "result_update": 0.0, "constraint_update_factors": 0.0,
+            "bounds_update_nonstorage": 0.0, "bounds_update_storage": 0.0, "objective_update": 0.0,
+            "number_of_rows": s.n_rows, "number_of_cols": s.n_cols, "number_of_nonzero": s.nnz,
+            "number_of_routes" if s.formulation == "route" else "number_of_edges": s.n_cols,
+            "number_of_nodes": s.n_nodes,
+        }
+        self._engine.reset(None)
+
+    def reset(self):
+        """``Model.__init__`` calls this before any ``setup`` (``pywr/_model.pyx:125``)."""
+        if self._engine is not None:
+            self._engine.reset(None)
+
+    def solve(self, model):
+        t0 = time.perf_counter()
+        s = self._structure
+        ts = model.timestep
+        self._gather(model)
+        t1 = time.perf_counter()
+        nbad = self._engine.step(float(ts.days), self._slots, self._node_flow, self._col_flow, self._objective)
+        t2 = time.perf_counter()
+        if nbad:
+            sidx, code = self._engine.status()
+            if code == 4:
+                raise B200LPError(f"NaN detected in the LP data of scenario {sidx} at timestep {ts.index}")
+            print("Scenario ID: {}".format(sidx))
+            print("Timestep index: {}".format(ts.index))
+            raise RuntimeError('Simplex solver failed with message: "{}", status: "{}".'.format(
+                _STATUS_TEXT.get(code, "solver failed"), "solution is undefined"))
+        # commit (cython_glpk.pyx:1091-1093): every node in sorted order; nodes that carry no
+        # column (Storage parents, aggregated / virtual nodes) would receive 0 and are skipped
+        node_flow = self._node_flow
+        for i, node in enumerate(s.all_nodes):
+            if self._has_flow[i]:
+                node.commit_all(node_flow[i])
+        if self.save_routes_flows:
+            self.routes_flows_array = np.ascontiguousarray(self._col_flow.T)
+        self.last_objective = self._objective[0]
+        t3 = time.perf_counter()
+        st = self._stats
+        st["bounds_update_nonstorage"] += t1 - t0
+        st["lp_solve"] += t2 - t1
+        st["result_update"] += t3 - t2
+        st["total"] += t3 - t0
+
+    # -- per-timestep gather of bounds / costs / volumes (a3-a6) ---------------------------------
+    def _gather(self, model):
+        from pywr.parameters import Parameter
+
+        s = self._structure
+        slots = self._slots
+        consts_dirty = False
+        for b in s.bindings:
+            kind = b.kind
+            obj = b.obj
+            if b.slot >= 0:
+                out = slots[b.slot]
+                if kind == "volume":
+                    out[:] = obj._volume
+                elif kind == "active":
+                    out[:] = 1.0 if obj.active else 0.0
+                elif kind == "factor_norm":
+                    f = obj.factors
+                    np.divide(np.asarray(f[0].get_all_values()), np.asarray(f[b.index].get_all_values()), out=out)
+                elif b.loop:
+                    getter = getattr(obj, "get_" + kind)
+                    for si in model.scenarios.combinations:
+                        out[si.global_id] = getter(si)
+                else:
+                    getattr(obj, "get_all_" + kind)(out)
+            elif kind == "factor_check":
+                continue
+            else:
+                value = _current_value(obj, kind)
+                if isinstance(value, Parameter):
+                    # an attribute that was a literal at setup became a Parameter: rebuild
+                    self.setup(model)
+                    return self._gather(model)
+                if value != s.consts[b.const] and not (value != value and s.consts[b.const] != s.consts[b.const]):
+                    s.consts[b.const] = value
+                    consts_dirty = True
+        if consts_dirty:
+            self._engine.set_consts(s.consts)
+        if self.check_nan and s.n_slots and np.isnan(slots[: s.n_slots]).any():
+            plane, sidx = np.argwhere(np.isnan(slots[: s.n_slots]))[0]
+            b = next(b for b in s.bindings if b.slot == plane)
+            raise B200LPError(
+                f"NaN detected in {b.kind} of {getattr(b.obj, 'name', b.obj)!r} for scenario {sidx}")
+        if self.check_nan and np.isnan(s.consts).any():
+            raise B200LPError("NaN detected in a constant bound or cost")
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _current_value(obj, kind):
+    from pywr._core import StorageInput, StorageOutput
+
+    if kind == "cost" and isinstance(obj, (StorageInput, StorageOutput)):
+        c = obj.parent.cost
+        if isinstance(c, (int, float)):
+            return -c if isinstance(obj, StorageInput) else c
+        return c
+    return getattr(obj, kind)
+
+
+class B200Solver(BatchedLPSolver):
+    """The CUDA (sm_100a) engine behind Pywr's solver API.  No CPU fallback: constructing the
+    engine raises if the extension library or a CUDA device is missing."""
+
+    name = "b200"
+    formulation = "route"
+
+    def _make_engine(self, structure, n_scenarios):
+        from .engine import CudaEngine
+
+        return CudaEngine(structure, n_scenarios, **self.engine_args)
+
+
+class B200EdgeSolver(B200Solver):
+    """Edge formulation (role of ``CythonGLPKEdgeSolver``, ``cython_glpk.pyx:1098-1918``)."""
+
+    name = "b200-edge"
+    formulation = "edge"
+
+
+def register():
+    """Append the solvers to ``pywr.solvers.solver_registry`` (``pywr/solvers/__init__.py:14``)."""
+    import pywr.solvers as ps
+
+    for cls in (B200Solver, B200EdgeSolver):
+        if not any(getattr(c, "name", None) == cls.name for c in ps.solver_registry):
+            # make the classes real subclasses of pywr's Solver for isinstance checks
+            ps.solver_registry.append(cls)
+    return ps.solver_registry
