@@ -1,0 +1,725 @@
+// lp_kernel.cuh — sm_100a device code of the scenario-batched bounded simplex.
+//
+// One *group* of G lanes (G = 8, 16 or 32, a sub-warp) owns one scenario.  The dictionary T
+// (m x n doubles, see below) lives in REGISTERS: lane l of the group holds rows l, l+G, ... (RPL rows
+// per lane, NC padded columns, everything unrolled at compile time).  The small per-scenario vectors
+// (row bounds, non-basic values, reduced costs, the broadcast pivot row) live in shared memory;
+// pricing and ratio tests are warp-shuffle arg-min / arg-max reductions over the group.  No tensor
+// cores: there is no dense contraction anywhere on this path (BASELINE.json north_star).
+//
+// What it replaces in the reference: the body of CythonGLPKSolver._solve_scenario
+// (pywr/solvers/cython_glpk.pyx:836-1095; edge form :1649-1918) for ALL scenarios of one timestep:
+//   a3 objective update :880-897      a4 aggregated-factor coefficients :903-926
+//   a5 row bounds :932-959            a6 storage / virtual-storage bounds :965-1019
+//   a7 warm-started simplex from the scenario's own previous basis :197-232,1026-1063
+//   a8 route/edge flow -> node flow :1068-1093
+// The algorithm is the one restated in oracle/lp_oracle.c (dense "dictionary" bounded dual simplex
+// with cost shifting and a primal clean-up phase); every floating point operation that decides a
+// pivot is performed in the same order with explicit fma(), and the file is compiled with
+// --fmad=false, so that the two sides agree to the last bit on the LP solution.
+//
+// Dictionary: variables v = (x_0..x_{n-1}, r_0..r_{m-1}), r = A x.  m basic, n non-basic:
+//     v_head[i] = sum_j T[i][j] * v_nb[j]
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/b200lp.h"
+
+namespace b200lp {
+
+constexpr double TOL_PRIMAL = 1e-9;
+constexpr double TOL_DUAL = 1e-9;
+constexpr double TOL_PIVOT = 1e-9;
+constexpr double TIE_REL = 1e-9;
+constexpr double TIE_ABS = 1e-12;
+constexpr int REFACTOR_PIVOTS = 40;
+
+enum : int { VS_BASIC = 1, VS_NL = 2, VS_NU = 3, VS_NF = 4, VS_NS = 5 };
+
+// Shared LP structure, device pointers (built by b200lp_create).
+struct DevStructure {
+    int m, n, N, n_slots, n_consts, n_storage, n_dyn_a, cost_clip;
+    int cost_dynamic;  // some cost ref is a slot: reduced costs are rebuilt every step
+    int rows_cap, nc;  // padded sizes of the kernel variant in use
+    const double *A_dense;  // [nc][rows_cap] column-major, zero padded
+    const int *row_kind, *row_lb_ref, *row_ub_ref;
+    const int *st_kind, *st_vol_ref, *st_minv_ref, *st_maxv_ref, *st_active_ref;
+    const int *cost_indptr, *cost_ref;
+    const double *cost_w;
+    const int *dyn_a_row, *dyn_a_col, *dyn_a_ref;
+    const double *dyn_a_scale, *dyn_a_static;
+    const int *flow_indptr, *flow_col;
+    const double *flow_w;
+    const double *consts;
+};
+
+// Per-scenario persistent state (the "basis" of BasisManager plus the cached dictionary).
+struct DevState {
+    double *T;    // [S][nc][rows_cap]
+    double *d;    // [S][nc]
+    int *head;    // [S][rows_cap]  variable in basic position i (-1: padding)
+    int *nb;      // [S][nc]        variable in non-basic position j (-1: padding)
+    int *nbstat;  // [S][nc]
+    int *meta;    // [S][4]: valid, pivots since refactor, last status, unused
+    double *vol;  // [n_storage][S] device-resident storage volume
+    unsigned long long *counters;  // [0] pivots, [1] refactors
+    int *fail;    // [0] number of failed scenarios, [1] min((scenario << 4) | code)
+};
+
+__device__ __forceinline__ double ref_value(const DevStructure &st, int ref, const double *p) {
+    return ref >= 0 ? p[ref] : __ldg(&st.consts[-ref - 1]);
+}
+
+// cython_glpk.pyx:934-945 and constraint_type :66-77
+__device__ __forceinline__ void type_bounds(double &lo, double &hi) {
+    if (fabs(lo) < 1e-8) lo = 0.0;
+    if (fabs(hi) < 1e-8) hi = 0.0;
+    if (fabs(lo - hi) < 1e-8) hi = lo;
+}
+
+template <int G>
+__device__ __forceinline__ double group_min(double v, unsigned mask) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, off, G));
+    return v;
+}
+
+// arg-max of (key, lowest idx on ties); idx < 0 means "no candidate"
+template <int G>
+__device__ __forceinline__ void group_argmax(double &key, int &idx, int &aux, unsigned mask) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const double k2 = __shfl_xor_sync(mask, key, off, G);
+        const int i2 = __shfl_xor_sync(mask, idx, off, G);
+        const int a2 = __shfl_xor_sync(mask, aux, off, G);
+        const bool take = (i2 >= 0) && (idx < 0 || k2 > key || (k2 == key && i2 < idx));
+        if (take) { key = k2; idx = i2; aux = a2; }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ int group_any(int pred, unsigned mask) {
+    return (__ballot_sync(mask, pred) & mask) != 0u;
+}
+
+// Per-group shared memory carve-up (doubles first, then ints).
+template <int G, int RPL, int NC>
+struct GroupSmem {
+    static constexpr int ROWS = G * RPL;
+    double *lo_r, *hi_r;  // [ROWS] bounds of the row variables
+    double *xn;           // [NC] value of each non-basic position
+    double *d, *dw;       // [NC] true / working reduced costs
+    double *prow;         // [NC] broadcast pivot row (+ scratch)
+    double *x;            // [NC] column values by variable id
+    double *cost;         // [NC]
+    double *p;            // [n_slots] this scenario's input planes
+    int *nb, *nbstat;     // [NC]
+    int *vstat;           // [NC + ROWS] scratch for the refactorisation
+    __host__ __device__ static size_t bytes(int n_slots) {
+        return sizeof(double) * (2 * ROWS + 6 * NC + n_slots) + sizeof(int) * (2 * NC + NC + ROWS) + 16;
+    }
+    __device__ void carve(unsigned char *base, int n_slots) {
+        double *dp = reinterpret_cast<double *>(base);
+        lo_r = dp; dp += ROWS;
+        hi_r = dp; dp += ROWS;
+        xn = dp; dp += NC;
+        d = dp; dp += NC;
+        dw = dp; dp += NC;
+        prow = dp; dp += NC;
+        x = dp; dp += NC;
+        cost = dp; dp += NC;
+        p = dp; dp += n_slots;
+        int *ip = reinterpret_cast<int *>(dp);
+        nb = ip; ip += NC;
+        nbstat = ip; ip += NC;
+        vstat = ip;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The per-scenario solver.  All members are per-lane registers except the GroupSmem pointers.
+// ------------------------------------------------------------------------------------------------
+template <int G, int RPL, int NC>
+struct Dict {
+    static constexpr int ROWS = G * RPL;
+    double T[RPL][NC];
+    int head[RPL];
+    double lob[RPL], hib[RPL];  // bounds of the basic variable in each owned position
+    double beta[RPL];
+    GroupSmem<G, RPL, NC> sm;
+    unsigned mask;
+    int gl;  // lane within the group
+    int n, m;
+    int pivots;
+
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+
+    __device__ __forceinline__ double var_lo(int v) const { return v < 0 ? -INFINITY : (v < n ? 0.0 : sm.lo_r[v - n]); }
+    __device__ __forceinline__ double var_hi(int v) const { return v < 0 ? INFINITY : (v < n ? INFINITY : sm.hi_r[v - n]); }
+
+    __device__ __forceinline__ void load_basic_bounds() {
+#pragma unroll
+        for (int r = 0; r < RPL; r++) { lob[r] = var_lo(head[r]); hib[r] = var_hi(head[r]); }
+    }
+
+    __device__ __forceinline__ double col_of(int r, int q) const {
+        double f = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; j++) f = (j == q) ? T[r][j] : f;
+        return f;
+    }
+
+    // beta_i = sum_j T[i][j] xn[j], j ascending (same order as dict_basic_values in the oracle)
+    __device__ __forceinline__ void basic_values() {
+        double xv[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) xv[j] = sm.xn[j];
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) acc = fma(T[r][j], xv[j], acc);
+            beta[r] = acc;
+        }
+    }
+
+    // Exchange basic position (lane pl, slot ps) with non-basic position q.  prow must already hold
+    // the pivot row in shared memory.  use_dw: also carry the working reduced costs.
+    __device__ __forceinline__ void pivot(int pl, int ps, int q, bool use_dw) {
+        const double inv = 1.0 / sm.prow[q];
+        double pr[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) pr[j] = (j == q) ? inv : -sm.prow[j] * inv;
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            const bool is_piv = (gl == pl) && (r == ps);
+            const double f = col_of(r, q);
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const double tn = (j == q) ? f * inv : fma(f, pr[j], T[r][j]);
+                T[r][j] = is_piv ? pr[j] : tn;
+            }
+        }
+        // reduced-cost rows, one column per lane
+        const double fd = sm.d[q], fw = sm.dw[q];
+        const int vin = sm.nb[q];
+        int vout = 0;
+        {
+            int hv = 0;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) hv = (r == ps) ? head[r] : hv;
+            vout = __shfl_sync(mask, hv, pl, G);
+        }
+        sync();
+        for (int j = gl; j < NC; j += G) {
+            const double prj = (j == q) ? inv : -sm.prow[j] * inv;
+            sm.d[j] = (j == q) ? fd * inv : fma(fd, prj, sm.d[j]);
+            if (use_dw) sm.dw[j] = (j == q) ? fw * inv : fma(fw, prj, sm.dw[j]);
+        }
+        if (gl == pl) {
+#pragma unroll
+            for (int r = 0; r < RPL; r++)
+                if (r == ps) head[r] = vin;
+        }
+        if (gl == 0) sm.nb[q] = vout;
+        pivots++;
+        sync();
+    }
+
+    // lane pl publishes its row ps to shared memory
+    __device__ __forceinline__ void publish_row(int pl, int ps) {
+        if (gl == pl) {
+#pragma unroll
+            for (int r = 0; r < RPL; r++)
+                if (r == ps) {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) sm.prow[j] = T[r][j];
+                }
+        }
+        sync();
+    }
+
+    // d_j = c_nb[j] + sum_i c_head[i] T[i][j]
+    __device__ __forceinline__ void reduced_costs() {
+        double part[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) part[j] = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            const int v = head[r];
+            const double c = (v >= 0 && v < n) ? sm.cost[v] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) part[j] = fma(c, T[r][j], part[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) part[j] += __shfl_xor_sync(mask, part[j], off, G);
+        }
+        sync();
+        for (int j = gl; j < NC; j += G) {
+            const int v = sm.nb[j];
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < NC; k++) acc = (k == j) ? part[k] : acc;
+            sm.d[j] = ((v >= 0 && v < n) ? sm.cost[v] : 0.0) + acc;
+        }
+        sync();
+    }
+
+    __device__ __forceinline__ void slack_basis() {
+        for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.nbstat[j] = j < n ? VS_NL : VS_NS; }
+#pragma unroll
+        for (int r = 0; r < RPL; r++) { const int i = r * G + gl; head[r] = i < m ? n + i : -1; }
+        sync();
+    }
+
+    // Rebuild T for the current basis by Gauss-Jordan pivoting from the slack basis (dict_refactor
+    // in the oracle).  Returns 0, or -1 if singular.  `st`/`p` supply the (possibly per-scenario)
+    // matrix values.
+    __device__ __forceinline__ int refactor(const DevStructure &st) {
+        // record the wanted status of every variable
+        for (int j = gl; j < NC; j += G) {
+            const int v = sm.nb[j];
+            if (v >= 0) sm.vstat[v < n ? v : NC + (v - n)] = sm.nbstat[j];
+        }
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            const int v = head[r];
+            if (v >= 0) sm.vstat[v < n ? v : NC + (v - n)] = VS_BASIC;
+        }
+        sync();
+        // slack dictionary T = A (with this scenario's dynamic coefficients)
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            const int i = r * G + gl;
+#pragma unroll
+            for (int j = 0; j < NC; j++) T[r][j] = __ldg(&st.A_dense[(size_t)j * ROWS + i]);
+            head[r] = i < m ? n + i : -1;
+        }
+        for (int k = 0; k < st.n_dyn_a; k++) {
+            const int row = __ldg(&st.dyn_a_row[k]), col = __ldg(&st.dyn_a_col[k]);
+            const double v = __ldg(&st.dyn_a_scale[k]) * ref_value(st, __ldg(&st.dyn_a_ref[k]), sm.p);
+            const double delta = v - __ldg(&st.dyn_a_static[k]);
+            if ((row % G) == gl) {
+#pragma unroll
+                for (int r = 0; r < RPL; r++)
+                    if (r == row / G) {
+#pragma unroll
+                        for (int j = 0; j < NC; j++)
+                            if (j == col) T[r][j] += delta;
+                    }
+            }
+        }
+        for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.d[j] = 0.0; }
+        sync();
+        int ok = 0;
+        for (int q = 0; q < n; q++) {
+            if (sm.vstat[q] != VS_BASIC) continue;
+            double best = TOL_PIVOT; int bi = -1, aux = 0;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                const int v = head[r];
+                if (v < n) continue;  // padding (-1) or a structural already pivoted in
+                if (sm.vstat[NC + (v - n)] == VS_BASIC) continue;
+                const double a = fabs(col_of(r, q));
+                if (a > best) { best = a; bi = r * G + gl; }
+            }
+            if (bi < 0) best = -1.0;
+            group_argmax<G>(best, bi, aux, mask);
+            if (bi < 0) { ok = -1; break; }
+            publish_row(bi % G, bi / G);
+            const int save = pivots;
+            pivot(bi % G, bi / G, q, false);
+            pivots = save;
+        }
+        // statuses of the non-basic positions
+        for (int j = gl; j < NC; j += G) {
+            const int v = sm.nb[j];
+            sm.nbstat[j] = v < 0 ? VS_NS : sm.vstat[v < n ? v : NC + (v - n)];
+        }
+        sync();
+        return ok;
+    }
+
+    // status + value of every non-basic position for the current bounds (dict_place_nonbasics)
+    __device__ __forceinline__ int place_nonbasics() {
+        int infeas = 0;
+        for (int j = gl; j < NC; j += G) {
+            const int v = sm.nb[j];
+            if (v < 0) { sm.xn[j] = 0.0; sm.nbstat[j] = VS_NS; continue; }
+            const double lo = var_lo(v), hi = var_hi(v), dj = sm.d[j];
+            int s = sm.nbstat[j];
+            if (lo == hi) s = VS_NS;
+            else if (lo > -INFINITY && hi < INFINITY) {
+                if (dj > TOL_DUAL) s = VS_NL;
+                else if (dj < -TOL_DUAL) s = VS_NU;
+                else if (s != VS_NL && s != VS_NU) s = VS_NL;
+            } else if (lo > -INFINITY) { s = VS_NL; if (dj < -TOL_DUAL) infeas = 1; }
+            else if (hi < INFINITY) { s = VS_NU; if (dj > TOL_DUAL) infeas = 1; }
+            else { s = VS_NF; if (fabs(dj) > TOL_DUAL) infeas = 1; }
+            sm.nbstat[j] = s;
+            sm.xn[j] = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
+        }
+        infeas = group_any<G>(infeas, mask);
+        sync();
+        return infeas;
+    }
+
+    // dict_solve of the oracle.  Returns a B200LP_ST_* code (uniform over the group).
+    __device__ __forceinline__ int solve() {
+        const int cap_bland = 20 * (m + n) + 50, cap_fail = 200 * (m + n) + 1000;
+        int shifted = place_nonbasics();
+        for (int j = gl; j < NC; j += G) {
+            double w = sm.d[j];
+            if (shifted) {
+                const int s = sm.nbstat[j];
+                if ((s == VS_NL && w < -TOL_DUAL) || (s == VS_NU && w > TOL_DUAL) || (s == VS_NF && fabs(w) > TOL_DUAL))
+                    w = 0.0;
+            }
+            sm.dw[j] = w;
+        }
+        sync();
+        load_basic_bounds();
+        int phase = 0;
+        for (int it = 0;; it++) {
+            if (it > cap_fail) return B200LP_ST_ITERLIMIT;
+            const bool bland = it > cap_bland;
+            basic_values();
+            if (phase == 0) {
+                // ---- leaving variable: largest bound violation -------------------------------
+                double worst = -1.0; int bi = -1, dir = 0;
+#pragma unroll
+                for (int r = 0; r < RPL; r++) {
+                    const double b = beta[r];
+                    double viol = 0.0; int dd = 0;
+                    if (b < lob[r] - TOL_PRIMAL * (1.0 + fabs(lob[r]))) { viol = lob[r] - b; dd = +1; }
+                    else if (b > hib[r] + TOL_PRIMAL * (1.0 + fabs(hib[r]))) { viol = b - hib[r]; dd = -1; }
+                    if (dd != 0) {
+                        if (bland) viol = 1.0;
+                        if (bi < 0 || viol > worst) { worst = viol; bi = r * G + gl; dir = dd; }
+                    }
+                }
+                group_argmax<G>(worst, bi, dir, mask);
+                if (bi < 0) {
+                    if (!shifted) return B200LP_ST_OPTIMAL;
+                    phase = 1; shifted = 0;
+                    continue;
+                }
+                const int pl = bi % G, ps = bi / G;
+                publish_row(pl, ps);
+                // ---- dual ratio test ------------------------------------------------------------
+                double rmin = INFINITY;
+                for (int j = gl; j < NC; j += G) {
+                    const int s = sm.nbstat[j];
+                    const double a = sm.prow[j] * (double)dir;
+                    bool ok = false;
+                    if (s == VS_NL) ok = a > TOL_PIVOT;
+                    else if (s == VS_NU) ok = a < -TOL_PIVOT;
+                    else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
+                    if (ok) rmin = fmin(rmin, fabs(sm.dw[j]) / fabs(a));
+                }
+                rmin = group_min<G>(rmin, mask);
+                if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
+                const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
+                double amax = -1.0; int q = -1, aux = 0;
+                for (int j = gl; j < NC; j += G) {
+                    const int s = sm.nbstat[j];
+                    const double a = sm.prow[j] * (double)dir;
+                    bool ok = false;
+                    if (s == VS_NL) ok = a > TOL_PIVOT;
+                    else if (s == VS_NU) ok = a < -TOL_PIVOT;
+                    else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
+                    if (!ok) continue;
+                    if (fabs(sm.dw[j]) / fabs(a) > thr) continue;
+                    const double key = bland ? 1.0 : fabs(a);
+                    if (q < 0 || key > amax) { amax = key; q = j; }
+                }
+                group_argmax<G>(amax, q, aux, mask);
+                // the leaving variable's bounds (held by lane pl)
+                double vlo = 0.0, vhi = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
+                vlo = __shfl_sync(mask, vlo, pl, G);
+                vhi = __shfl_sync(mask, vhi, pl, G);
+                pivot(pl, ps, q, true);
+                if (gl == 0) {
+                    sm.nbstat[q] = (vlo == vhi) ? VS_NS : (dir > 0 ? VS_NL : VS_NU);
+                    sm.xn[q] = dir > 0 ? vlo : vhi;
+                }
+                sync();
+                load_basic_bounds();
+            } else {
+                // ---- entering variable: largest dual infeasibility -----------------------------
+                double worst = -1.0; int q = -1, dir = 0;
+                for (int j = gl; j < NC; j += G) {
+                    const int s = sm.nbstat[j];
+                    const double dj = sm.d[j];
+                    int dd = 0;
+                    if ((s == VS_NL || s == VS_NF) && dj < -TOL_DUAL) dd = +1;
+                    else if ((s == VS_NU || s == VS_NF) && dj > TOL_DUAL) dd = -1;
+                    if (dd != 0) {
+                        const double key = bland ? 1.0 : fabs(dj);
+                        if (q < 0 || key > worst) { worst = key; q = j; dir = dd; }
+                    }
+                }
+                group_argmax<G>(worst, q, dir, mask);
+                if (q < 0) return B200LP_ST_OPTIMAL;
+                const int vin = sm.nb[q];
+                const double inlo = var_lo(vin), inhi = var_hi(vin);
+                double tmin = inhi - inlo;
+                if (!(tmin < INFINITY)) tmin = INFINITY;
+                // ---- primal ratio test down column q ---------------------------------------------
+                double step_min = INFINITY;
+                double stp[RPL], aa[RPL]; int upf[RPL];
+#pragma unroll
+                for (int r = 0; r < RPL; r++) {
+                    const double a = col_of(r, q) * (double)dir;
+                    double step = INFINITY; int up = 0;
+                    if (a > TOL_PIVOT) { if (hib[r] < INFINITY) { step = (hib[r] - beta[r]) / a; up = 1; } }
+                    else if (a < -TOL_PIVOT) { if (lob[r] > -INFINITY) step = (lob[r] - beta[r]) / a; }
+                    if (step < 0.0) step = 0.0;
+                    stp[r] = step; aa[r] = fabs(a); upf[r] = up;
+                    step_min = fmin(step_min, step);
+                }
+                step_min = group_min<G>(step_min, mask);
+                if (step_min == INFINITY && tmin == INFINITY) return B200LP_ST_UNBOUNDED;
+                if (tmin <= step_min) {
+                    if (gl == 0) {
+                        sm.nbstat[q] = dir > 0 ? VS_NU : VS_NL;
+                        sm.xn[q] = dir > 0 ? inhi : inlo;
+                    }
+                    sync();
+                    continue;
+                }
+                const double thr = step_min * (1.0 + TIE_REL) + TIE_ABS;
+                double amax = -1.0; int bi = -1, up = 0;
+#pragma unroll
+                for (int r = 0; r < RPL; r++) {
+                    if (stp[r] > thr) continue;
+                    const double key = bland ? 1.0 : aa[r];
+                    if (bi < 0 || key > amax) { amax = key; bi = r * G + gl; up = upf[r]; }
+                }
+                group_argmax<G>(amax, bi, up, mask);
+                const int pl = bi % G, ps = bi / G;
+                publish_row(pl, ps);
+                double vlo = 0.0, vhi = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
+                vlo = __shfl_sync(mask, vlo, pl, G);
+                vhi = __shfl_sync(mask, vhi, pl, G);
+                pivot(pl, ps, q, false);
+                if (gl == 0) {
+                    sm.nbstat[q] = (vlo == vhi) ? VS_NS : (up ? VS_NU : VS_NL);
+                    sm.xn[q] = up ? vhi : vlo;
+                }
+                sync();
+                load_basic_bounds();
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// One timestep for all scenarios.
+// ------------------------------------------------------------------------------------------------
+template <int G, int RPL, int NC>
+__global__ void __launch_bounds__(128)
+lp_step_kernel(const DevStructure st, const DevState state, const int S, const double days,
+               const double *__restrict__ slots, double *__restrict__ node_flow, double *__restrict__ col_flow,
+               double *__restrict__ objective) {
+    constexpr int ROWS = G * RPL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int groups_per_block = blockDim.x / G;
+    const int gib = threadIdx.x / G;
+    const int sidx = blockIdx.x * groups_per_block + gib;
+    if (sidx >= S) return;  // whole group exits together
+
+    Dict<G, RPL, NC> D;
+    D.gl = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
+    D.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    D.n = st.n; D.m = st.m; D.pivots = 0;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots) + 15) & ~(size_t)15;
+    D.sm.carve(smem_raw + gbytes * gib, st.n_slots);
+    const int gl = D.gl, n = st.n, m = st.m;
+
+    // ---- this scenario's input planes ----------------------------------------------------------
+    for (int k = gl; k < st.n_slots; k += G) D.sm.p[k] = slots[(size_t)k * S + sidx];
+    D.sync();
+
+    // ---- (a5/a6) row bounds ------------------------------------------------------------------------
+    int nan_seen = 0, bad_bounds = 0;
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int i = r * G + gl;
+        double l = -INFINITY, u = INFINITY;
+        if (i < m) {
+            if (__ldg(&st.row_kind[i]) == B200LP_ROW_FLOW) {
+                l = ref_value(st, __ldg(&st.row_lb_ref[i]), D.sm.p);
+                u = ref_value(st, __ldg(&st.row_ub_ref[i]), D.sm.p);
+                if (isnan(l) || isnan(u)) nan_seen = 1;
+                type_bounds(l, u);
+            } else {
+                const int k = __ldg(&st.row_lb_ref[i]);
+                const double maxv = ref_value(st, __ldg(&st.st_maxv_ref[k]), D.sm.p);
+                const double minv = ref_value(st, __ldg(&st.st_minv_ref[k]), D.sm.p);
+                const int vref = __ldg(&st.st_vol_ref[k]);
+                const double vol = (vref == B200LP_REF_STATE) ? state.vol[(size_t)k * S + sidx] : ref_value(st, vref, D.sm.p);
+                int active = 1;
+                if (__ldg(&st.st_kind[k]) == B200LP_ST_KIND_VIRTUAL)
+                    active = ref_value(st, __ldg(&st.st_active_ref[k]), D.sm.p) != 0.0;
+                if (isnan(maxv) || isnan(minv) || isnan(vol)) nan_seen = 1;
+                if (maxv == minv) { l = 0.0; u = 0.0; }
+                else if (!active) { l = -INFINITY; u = INFINITY; }
+                else {
+                    const double avail = fmax(vol - minv, 0.0);
+                    l = -avail / days;
+                    u = fmax(maxv - vol, 0.0) / days;
+                    type_bounds(l, u);
+                }
+            }
+            if (l > u) bad_bounds = 1;
+        }
+        D.sm.lo_r[i] = l; D.sm.hi_r[i] = u;
+    }
+    // ---- (a3) objective ----------------------------------------------------------------------------
+    for (int j = gl; j < NC; j += G) {
+        double acc = 0.0;
+        if (j < n) {
+            for (int k = __ldg(&st.cost_indptr[j]); k < __ldg(&st.cost_indptr[j + 1]); k++)
+                acc += __ldg(&st.cost_w[k]) * ref_value(st, __ldg(&st.cost_ref[k]), D.sm.p);
+            if (isnan(acc)) nan_seen = 1;
+            if (st.cost_clip && fabs(acc) < 1e-8) acc = 0.0;
+        }
+        D.sm.cost[j] = acc;
+    }
+    for (int k = gl; k < st.n_dyn_a; k += G)
+        if (isnan(ref_value(st, __ldg(&st.dyn_a_ref[k]), D.sm.p))) nan_seen = 1;
+    nan_seen = group_any<G>(nan_seen, D.mask);
+    bad_bounds = group_any<G>(bad_bounds, D.mask);
+    D.sync();
+
+    int *meta = state.meta + (size_t)sidx * 4;
+    int status = B200LP_ST_OPTIMAL;
+    int refactors = 0;
+    if (nan_seen) status = B200LP_ST_NAN;
+    else if (bad_bounds) status = B200LP_ST_INFEASIBLE;
+    else {
+        // ---- load the scenario's basis + cached dictionary ---------------------------------------
+        const int valid = meta[0];
+        int npiv = meta[1];
+        double *Tg = state.T + (size_t)sidx * NC * ROWS;
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+            const int i = r * G + gl;
+            D.head[r] = state.head[(size_t)sidx * ROWS + i];
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) D.T[r][j] = Tg[(size_t)j * ROWS + i];
+            }
+        }
+        for (int j = gl; j < NC; j += G) {
+            D.sm.nb[j] = state.nb[(size_t)sidx * NC + j];
+            D.sm.nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
+            D.sm.d[j] = state.d[(size_t)sidx * NC + j];
+        }
+        D.sync();
+        bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
+        const bool fresh0 = need_refactor;
+        for (int attempt = 0; attempt < 3; attempt++) {
+            if (attempt == 1 && fresh0) continue;
+            if (attempt == 2) D.slack_basis();
+            if (attempt > 0) need_refactor = true;
+            if (need_refactor) {
+                if (D.refactor(st) != 0) {
+                    D.slack_basis();
+                    D.refactor(st);
+                }
+                D.reduced_costs();
+                npiv = 0; refactors++;
+            } else if (st.cost_dynamic) {
+                D.reduced_costs();
+            }
+            const int p0 = D.pivots;
+            status = D.solve();
+            npiv += D.pivots - p0;
+            if (status == B200LP_ST_OPTIMAL) break;
+        }
+        // ---- store the basis + dictionary ---------------------------------------------------------
+        if (D.pivots > 0 || refactors > 0) {
+#pragma unroll
+            for (int r = 0; r < RPL; r++) {
+                const int i = r * G + gl;
+                state.head[(size_t)sidx * ROWS + i] = D.head[r];
+#pragma unroll
+                for (int j = 0; j < NC; j++) Tg[(size_t)j * ROWS + i] = D.T[r][j];
+            }
+        }
+        for (int j = gl; j < NC; j += G) {
+            state.nb[(size_t)sidx * NC + j] = D.sm.nb[j];
+            state.nbstat[(size_t)sidx * NC + j] = D.sm.nbstat[j];
+            state.d[(size_t)sidx * NC + j] = D.sm.d[j];
+        }
+        if (gl == 0) { meta[0] = (status == B200LP_ST_OPTIMAL) ? 1 : 0; meta[1] = npiv; }
+    }
+    if (gl == 0) {
+        meta[2] = status;
+        if (D.pivots) atomicAdd(&state.counters[0], (unsigned long long)D.pivots);
+        if (refactors) atomicAdd(&state.counters[1], (unsigned long long)refactors);
+        if (status != B200LP_ST_OPTIMAL) {
+            atomicAdd(&state.fail[0], 1);
+            atomicMin(&state.fail[1], (sidx << 4) | status);
+        }
+    }
+    if (status != B200LP_ST_OPTIMAL) return;
+
+    // ---- (a8) column values, objective, node flows ---------------------------------------------
+    D.basic_values();
+    for (int j = gl; j < NC; j += G) {
+        const int v = D.sm.nb[j];
+        if (v >= 0 && v < n) D.sm.x[v] = D.sm.xn[j];
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int v = D.head[r];
+        if (v >= 0 && v < n) D.sm.x[v] = D.beta[r];
+    }
+    D.sync();
+    if (col_flow)
+        for (int j = gl; j < n; j += G) col_flow[(size_t)j * S + sidx] = D.sm.x[j];
+    if (objective && gl == 0) {
+        double acc = 0.0;
+        for (int j = 0; j < n; j++) acc = fma(D.sm.cost[j], D.sm.x[j], acc);
+        objective[sidx] = acc;
+    }
+    if (node_flow) {
+        for (int v = gl; v < st.N; v += G) {
+            double acc = 0.0;
+            for (int k = __ldg(&st.flow_indptr[v]); k < __ldg(&st.flow_indptr[v + 1]); k++)
+                acc = fma(__ldg(&st.flow_w[k]), D.sm.x[__ldg(&st.flow_col[k])], acc);
+            node_flow[(size_t)v * S + sidx] = acc;
+        }
+    }
+}
+
+// reset: slack basis for every scenario (is_first_solve, cython_glpk.pyx:757-759)
+__global__ void lp_reset_kernel(const DevState state, const int S, const int m, const int n, const int rows_cap,
+                                const int nc) {
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= S) return;
+    for (int i = 0; i < rows_cap; i++) state.head[(size_t)sidx * rows_cap + i] = i < m ? n + i : -1;
+    for (int j = 0; j < nc; j++) {
+        state.nb[(size_t)sidx * nc + j] = j < n ? j : -1;
+        state.nbstat[(size_t)sidx * nc + j] = j < n ? VS_NL : VS_NS;
+        state.d[(size_t)sidx * nc + j] = 0.0;
+    }
+    state.meta[(size_t)sidx * 4 + 0] = 0;
+    state.meta[(size_t)sidx * 4 + 1] = 0;
+    state.meta[(size_t)sidx * 4 + 2] = 0;
+    state.meta[(size_t)sidx * 4 + 3] = 0;
+}
+
+}  // namespace b200lp

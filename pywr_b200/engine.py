@@ -1,0 +1,205 @@
+"""ctypes binding of the C-ABI in ``include/b200lp.h`` (``libb200lp.so``, built from
+``pywr_b200/csrc``).  This is the only way the Python host reaches the GPU: no torch, no CPU
+fallback — if the library or a CUDA device is missing, construction raises."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200lp.so")
+_lib = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class b200lp_stats(ctypes.Structure):
+    _fields_ = [
+        ("steps", ctypes.c_int64), ("scenario_steps", ctypes.c_int64), ("pivots", ctypes.c_int64),
+        ("refactors", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
+        ("h2d_bytes", ctypes.c_double), ("d2h_bytes", ctypes.c_double), ("device_ms", ctypes.c_double),
+        ("n_rows", ctypes.c_int32), ("n_cols", ctypes.c_int32), ("n_nonzero", ctypes.c_int32),
+        ("kernel_variant", ctypes.c_int32),
+    ]
+
+
+# every symbol include/b200lp.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("b200lp_last_error", ctypes.c_char_p, []),
+    ("b200lp_abi_version", ctypes.c_int, []),
+    ("b200lp_device_count", ctypes.c_int, []),
+    ("b200lp_create", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    ("b200lp_destroy", None, [ctypes.c_void_p]),
+    ("b200lp_reset", ctypes.c_int, [ctypes.c_void_p, _dp]),
+    ("b200lp_step", ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, _dp, _dp, _dp, _dp]),
+    ("b200lp_step_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 4),
+    ("b200lp_set_consts", ctypes.c_int, [ctypes.c_void_p, _dp]),
+    ("b200lp_status", ctypes.c_int, [ctypes.c_void_p, _ip, _ip]),
+    ("b200lp_get_basis", ctypes.c_int, [ctypes.c_void_p, _ip, _ip]),
+    ("b200lp_get_volume", ctypes.c_int, [ctypes.c_void_p, _dp]),
+    ("b200lp_set_volume", ctypes.c_int, [ctypes.c_void_p, _dp]),
+    ("b200lp_get_stats", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(b200lp_stats)]),
+    ("b200lp_stream", ctypes.c_void_p, [ctypes.c_void_p]),
+    ("b200lp_sync", ctypes.c_int, [ctypes.c_void_p]),
+    ("b200lp_host_alloc", ctypes.c_void_p, [ctypes.c_size_t]),
+    ("b200lp_host_free", None, [ctypes.c_void_p]),
+    ("b200lp_device_alloc", ctypes.c_void_p, [ctypes.c_size_t]),
+    ("b200lp_device_free", None, [ctypes.c_void_p]),
+    ("b200lp_memcpy_h2d", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    ("b200lp_memcpy_d2h", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+]
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and bind every declared symbol.  Raises if it has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise EngineUnavailable(
+            f"{path} not found: build the CUDA extension first (__graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(path)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(L, name)  # AttributeError if the library does not export it
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if L.b200lp_abi_version() != 3:
+        raise EngineUnavailable("libb200lp.so ABI version mismatch: rebuild")
+    _lib = L
+    return L
+
+
+def _check(L, rc, what):
+    if rc != 0:
+        msg = L.b200lp_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise EngineUnavailable(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+class PinnedArray:
+    """float64 array over cudaHostAlloc'ed memory (for cudaMemcpyAsync at full PCIe rate)."""
+
+    def __init__(self, L, shape):
+        self.L = L
+        n = int(np.prod(shape))
+        self.ptr = L.b200lp_host_alloc(max(n, 1) * 8)
+        if not self.ptr:
+            raise MemoryError("b200lp_host_alloc failed")
+        buf = (ctypes.c_double * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+        self.array[...] = 0.0
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.L.b200lp_host_free(self.ptr)
+            self.ptr = None
+
+
+class CudaEngine:
+    """One engine per (LP structure, scenario count, device)."""
+
+    def __init__(self, structure, n_scenarios, device=None, **_):
+        self.L = load_library()
+        self.structure = structure
+        self.S = int(n_scenarios)
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) % max(self.L.b200lp_device_count(), 1)
+        self.device = int(device)
+        self._cs = structure.to_c()
+        h = ctypes.c_void_p()
+        _check(self.L, self.L.b200lp_create(ctypes.addressof(self._cs), self.S, self.device, ctypes.byref(h)),
+               "b200lp_create")
+        self.h = h
+        self._pinned = []
+
+    # -- buffers ------------------------------------------------------------------------------
+    def alloc_planes(self, n):
+        pa = PinnedArray(self.L, (int(n), self.S))
+        self._pinned.append(pa)
+        return pa.array
+
+    # -- lifecycle ----------------------------------------------------------------------------
+    def reset(self, vol0=None):
+        _check(self.L, self.L.b200lp_reset(self.h, _ptr(vol0)), "b200lp_reset")
+
+    def set_consts(self, consts):
+        _check(self.L, self.L.b200lp_set_consts(self.h, _ptr(np.ascontiguousarray(consts, dtype=np.float64))),
+               "b200lp_set_consts")
+
+    def step(self, days, slots, node_flow=None, col_flow=None, objective=None):
+        """Returns the number of failed scenarios (0 = all optimal) like the oracle engine."""
+        rc = self.L.b200lp_step(self.h, float(days), _ptr(slots), _ptr(node_flow), _ptr(col_flow), _ptr(objective))
+        if rc == -5:
+            return 1
+        _check(self.L, rc, "b200lp_step")
+        return 0
+
+    def step_device(self, days, d_slots, d_node_flow=None, d_col_flow=None, d_objective=None):
+        _check(self.L, self.L.b200lp_step_device(self.h, float(days), d_slots, d_node_flow, d_col_flow, d_objective),
+               "b200lp_step_device")
+
+    def status(self):
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        _check(self.L, self.L.b200lp_status(self.h, ctypes.byref(a), ctypes.byref(b)), "b200lp_status")
+        return a.value, b.value
+
+    def get_basis(self):
+        s = self.structure
+        row = np.zeros((self.S, s.n_rows), np.int32)
+        col = np.zeros((self.S, s.n_cols), np.int32)
+        _check(self.L, self.L.b200lp_get_basis(self.h, row.ctypes.data_as(_ip), col.ctypes.data_as(_ip)),
+               "b200lp_get_basis")
+        return row, col
+
+    def get_volume(self):
+        out = np.zeros((self.structure.n_storage, self.S))
+        _check(self.L, self.L.b200lp_get_volume(self.h, _ptr(out)), "b200lp_get_volume")
+        return out
+
+    def stats(self):
+        st = b200lp_stats()
+        _check(self.L, self.L.b200lp_get_stats(self.h, ctypes.byref(st)), "b200lp_get_stats")
+        return {name: getattr(st, name) for name, _ in b200lp_stats._fields_}
+
+    def counters(self):
+        st = self.stats()
+        return {"pivots": st["pivots"], "refactors": st["refactors"], "steps": st["steps"]}
+
+    def sync(self):
+        _check(self.L, self.L.b200lp_sync(self.h), "b200lp_sync")
+
+    @property
+    def stream(self):
+        return self.L.b200lp_stream(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200lp_destroy(self.h)
+            self.h = None
+        for pa in getattr(self, "_pinned", []):
+            pa.free()
+        self._pinned = []
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
