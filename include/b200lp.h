@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 3
+#define B200LP_ABI_VERSION 4
 
 /* error codes */
 #define B200LP_OK 0
@@ -178,6 +178,107 @@ int b200lp_get_volume(b200lp_handle *h, double *volume);
 int b200lp_set_volume(b200lp_handle *h, const double *volume);
 
 int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
+
+/* =====================================================================================
+ * Device-resident run ("program"): the per-timestep inputs are produced ON the device, so that
+ * a whole run needs no host round trip — parameter values feeding the LP (a3-a6 producers,
+ * SURVEY.md section 8f rank 1), Storage.after mass balance (pywr/_core.pyx:1335-1361, a10) and the
+ * built-in recorders' per-scenario accumulation (pywr/recorders/_recorders.pyx, a11-a13).
+ *
+ * Every timestep the ops are evaluated in order for every scenario; op k writes slot op_dst[k].
+ * Integer arguments of op k are op_args[op_arg_ptr[k] .. op_arg_ptr[k+1]).
+ * ===================================================================================== */
+#define B200LP_OP_TABLE 1         /* args: table, offset.  values[clamp(t+offset)][column(scenario)]
+                                     DataFrameParameter / ArrayIndexed(Scenario)Parameter / profiles
+                                     pre-expanded over the run (pywr/parameters/_parameters.pyx:192-335,665-832) */
+#define B200LP_OP_AGG 2           /* args: func, n, ref*n.  AggregatedParameter (:1439-1557)              */
+#define B200LP_OP_CONTROL_CURVE 3 /* args: storage, n, curve_ref*n, value_ref*(n+1).
+                                     ControlCurveParameter.value (_control_curves.pyx:501-524)           */
+#define B200LP_OP_CC_INDEX 4      /* args: storage, n, curve_ref*n.  ControlCurveIndexParameter.index
+                                     (_control_curves.pyx:345-364); the index is stored as a double      */
+#define B200LP_OP_INDEXED 5       /* args: index_ref, n, ref*n.  IndexedArrayParameter.value (:1262-1312) */
+#define B200LP_OP_NEG 6           /* args: ref.  NegativeParameter                                        */
+#define B200LP_OP_MAX0 7          /* args: ref, threshold_ref.  MaxParameter: max(value, threshold)       */
+#define B200LP_OP_MIN0 8          /* args: ref, threshold_ref.  MinParameter: min(value, threshold)       */
+#define B200LP_OP_DIV 9           /* args: ref_a, ref_b.  a / b (AggregatedNode.get_factors_norm f0/fi,
+                                     pywr/_core.pyx:921-939; DivisionParameter)                          */
+
+#define B200LP_AGG_SUM 0
+#define B200LP_AGG_PRODUCT 1
+#define B200LP_AGG_MIN 2
+#define B200LP_AGG_MAX 3
+#define B200LP_AGG_MEAN 4
+
+/* table column selection */
+#define B200LP_COL_NONE (-1)     /* single column                                                        */
+#define B200LP_COL_SCENARIO (-2) /* one column per scenario combination (global_id)                      */
+                                 /* >= 0: ScenarioIndex.indices[axis] (pywr/_core.pyx:108-128)           */
+
+/* recorder kinds.  T = program steps.  "value" below is sum_k rec_w[k] * x[rec_col[k]], the node's
+ * flow after commit (+ AggregatedNode / compound-node sums), restated as a linear form of the columns */
+#define B200LP_REC_NODE_FLOW 1        /* [T][S]  value*factor                       (_recorders.pyx:611-617)   */
+#define B200LP_REC_NODE_DEFICIT 2     /* [T][S]  max_flow - value                   (:680-688)                 */
+#define B200LP_REC_NODE_SUPPLIED 3    /* [T][S]  value/max_flow, 1.0 on /0          (:723-734)                 */
+#define B200LP_REC_NODE_CURTAIL 4     /* [T][S]  1 - value/max_flow, 0.0 on /0      (:769-779)                 */
+#define B200LP_REC_STORAGE_VOLUME 5   /* [T][S]  volume after the mass balance      (:1175-1183)               */
+#define B200LP_REC_STORAGE_PC 6       /* [T][S]  volume / max_volume                                           */
+#define B200LP_REC_TOTAL_DEFICIT 7    /* [S]     += (max_flow - value)*days         (:1744-1753)               */
+#define B200LP_REC_TOTAL_FLOW 8       /* [S]     += value*factor*days               (:1768-1775)               */
+#define B200LP_REC_MEAN_FLOW 9        /* [S]     += value*factor   (the caller divides by T, :1795-1801)       */
+#define B200LP_REC_DEFICIT_FREQ 10    /* [S]     += 1 if |value-max_flow| > 1e-6   (:1808-1822)               */
+#define B200LP_REC_MIN_VOLUME 11      /* [S]     min(volume)                        (:1845-1852)               */
+
+typedef struct b200lp_program {
+    int32_t n_steps;     /* T: timesteps of the run                                                   */
+    int32_t n_ops;
+    int32_t n_tables;
+    int32_t n_axes;      /* scenario axes (model.scenarios.scenarios)                                 */
+    int32_t n_recorders;
+    int32_t reserved0;
+    const double *ts_days;      /* [T] Timestep.days (pywr/_core.pyx:276-301)                          */
+    const int32_t *op_kind;     /* [n_ops]                                                             */
+    const int32_t *op_dst;      /* [n_ops] slot written                                                */
+    const int32_t *op_arg_ptr;  /* [n_ops+1]                                                           */
+    const int32_t *op_args;
+    const int32_t *table_rows;  /* [n_tables] 1 (time-invariant) or T                                  */
+    const int32_t *table_cols;  /* [n_tables]                                                          */
+    const int32_t *table_axis;  /* [n_tables] B200LP_COL_*                                             */
+    const int64_t *table_offset; /* [n_tables] first element in table_data (row-major [rows][cols])    */
+    const double *table_data;
+    const int32_t *scen_index;  /* [n_axes][S] ScenarioIndex.indices                                   */
+    /* storage mass balance: net inflow of storage k = sum stflow_w * x[stflow_col] (commit through
+     * StorageInput/StorageOutput, _core.pyx:942-979; VirtualStorage: -sum factor*flow, :1483-1493)   */
+    const int32_t *stflow_indptr; /* [n_storage+1] */
+    const int32_t *stflow_col;
+    const double *stflow_w;
+    const double *initial_volume; /* [n_storage][S] Storage._volume after Model.reset                  */
+    const double *initial_pc;     /* [n_storage][S] Storage._current_pc after Model.reset              */
+    /* recorders */
+    const int32_t *rec_kind;    /* [n_recorders]                                                       */
+    const int32_t *rec_src;     /* [n_recorders] storage index for the storage kinds, else unused      */
+    const int32_t *rec_ref;     /* [n_recorders] ref of the node's max_flow (deficit kinds)            */
+    const double *rec_factor;   /* [n_recorders]                                                       */
+    const int32_t *rec_indptr;  /* [n_recorders+1] linear form of the node kinds                       */
+    const int32_t *rec_col;
+    const double *rec_w;
+} b200lp_program;
+
+/* Load (copy) a program; allocates the recorder outputs on the device and resets the run state. */
+int b200lp_load_program(b200lp_handle *h, const b200lp_program *p);
+/* Restart the loaded program: initial volumes, slack bases, zeroed recorders (Model.reset). */
+int b200lp_program_reset(b200lp_handle *h);
+/* Run timesteps [t0, t0+n) for all scenarios on the device.  Asynchronous on b200lp_stream();
+ * errors of individual scenarios are reported by b200lp_program_status after a b200lp_sync. */
+int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n);
+/* Number of failed scenarios so far, the first failing scenario (or -1), its status and timestep. */
+int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario, int32_t *code, int32_t *timestep);
+/* Copy recorder `rec` to the host: [T][S] doubles for the array kinds, [S] for the others. */
+int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out);
+/* Device pointer of recorder `rec` (for NCCL gathers by the caller) and its element count. */
+void *b200lp_recorder_device_ptr(b200lp_handle *h, int32_t rec, int64_t *count);
+/* Column values x [n][S] of the last executed timestep (host mirrors of node flows) and the current
+ * volumes / proportions [n_storage][S]; any pointer may be NULL. */
+int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, double *pc);
 
 /* the cudaStream_t all work of this handle is queued on (for CUDA-event timing by the caller) */
 void *b200lp_stream(b200lp_handle *h);

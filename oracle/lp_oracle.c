@@ -56,7 +56,9 @@ typedef struct {
     int32_t *nb;   /* [n] variable in non-basic position j           */
     int8_t *vstat; /* [n+m] per-variable status (the "basis")        */
     double *vol;   /* [n_storage] device-state volume equivalent     */
+    double *pc;    /* [n_storage] volume / max_volume (Storage._current_pc) */
     int32_t npiv;  /* pivots since the last re-factorisation         */
+    int32_t dead;  /* program mode: failed at an earlier timestep           */
     int32_t valid; /* T/d/head/nb consistent with vstat              */
     int32_t status;
 } orc_scen;
@@ -79,10 +81,15 @@ static void *dup_mem(const void *p, size_t bytes) {
     return q;
 }
 
-static inline double ref_value(const orc_handle *h, int32_t ref, const double *slots, int32_t sidx) {
-    if (ref >= 0) return slots[(size_t)ref * h->S + sidx];
+/* slots: planes [n_slots][S] (stride S, offset = scenario) in step mode, or this scenario's own
+ * slot vector (stride 1, offset 0) in program mode */
+typedef struct { const double *base; size_t stride, off; } slot_view;
+
+static inline double ref_value_v(const orc_handle *h, int32_t ref, slot_view sv) {
+    if (ref >= 0) return sv.base[(size_t)ref * sv.stride + sv.off];
     return h->s.consts[-ref - 1];
 }
+#define ref_value(h, ref, slots, sidx) ref_value_v(h, ref, sv)
 
 /* cython_glpk.pyx:934-945 + constraint_type :66-77: clip tiny values, FX when |lb-ub| < 1e-8 */
 static inline void type_bounds(double *lo, double *hi) {
@@ -138,17 +145,21 @@ void *orc_create(const b200lp_structure *s, int32_t S) {
         c->nb = (int32_t *)calloc(n + 1, sizeof(int32_t));
         c->vstat = (int8_t *)calloc(m + n + 1, sizeof(int8_t));
         c->vol = (double *)calloc(s->n_storage + 1, sizeof(double));
+        c->pc = (double *)calloc(s->n_storage + 1, sizeof(double));
     }
     h->first_bad = -1;
     return h;
 }
 
+void orc_unload_program(void *hv);
+
 void orc_destroy(void *hv) {
     orc_handle *h = (orc_handle *)hv;
     if (!h) return;
+    orc_unload_program(hv);
     for (int32_t k = 0; k < h->S; k++) {
         orc_scen *c = &h->sc[k];
-        free(c->T); free(c->d); free(c->head); free(c->nb); free(c->vstat); free(c->vol);
+        free(c->T); free(c->d); free(c->head); free(c->nb); free(c->vstat); free(c->vol); free(c->pc);
     }
     free(h->sc); free(h->A);
     free((void *)h->s.a_indptr); free((void *)h->s.a_col); free((void *)h->s.a_val);
@@ -425,7 +436,7 @@ static int dict_solve(dict *D) {
 
 /* ------------------------------------------------------------------ one scenario, one timestep */
 
-static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, const double *slots, double *node_flow,
+static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, slot_view sv, double *node_flow,
                               double *col_flow, double *objective, double *work, int64_t *pivots,
                               int64_t *refactors) {
     const b200lp_structure *s = &h->s;
@@ -535,6 +546,7 @@ static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, const do
         const int32_t v = c->head[i];
         if (v < n) x[v] = beta[i];
     }
+    /* x stays in `work` (ORC_WORK_X) for the program mode */
     if (col_flow) for (int32_t j = 0; j < n; j++) col_flow[(size_t)j * S + sidx] = x[j];
     if (objective) {
         double acc = 0.0;
@@ -573,7 +585,8 @@ static void *orc_worker(void *arg) {
     double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + m + (size_t)m * n + 8));
     J->nbad = 0; J->first_bad = -1; J->bad_code = 0; J->pivots = 0; J->refactors = 0;
     for (int32_t k = J->s0; k < J->s1; k++) {
-        int st = orc_solve_scenario(h, k, J->days, J->slots, J->node_flow, J->col_flow, J->objective, work,
+        slot_view sv = {J->slots, (size_t)h->S, (size_t)k};
+        int st = orc_solve_scenario(h, k, J->days, sv, J->node_flow, J->col_flow, J->objective, work,
                                     &J->pivots, &J->refactors);
         if (st != B200LP_ST_OPTIMAL) {
             J->nbad++;
@@ -649,4 +662,333 @@ void orc_counters(void *hv, int64_t *pivots, int64_t *refactors, int64_t *steps)
     if (pivots) *pivots = h->pivots;
     if (refactors) *refactors = h->refactors;
     if (steps) *steps = h->steps;
+}
+
+/* ================================================================================================
+ * Program mode: the whole run per scenario, restating what Pywr does around the solver each
+ * timestep (pywr/_model.pyx:626-631,839-860):
+ *   before(): parameters are evaluated from the state left by the previous timestep
+ *             (ops: pywr/parameters/_parameters.pyx:192-335,1262-1312,1439-1557,
+ *              _control_curves.pyx:345-364,501-524; Storage.get_current_pc pywr/_core.pyx:1027-1039)
+ *   solve():  orc_solve_scenario
+ *   after():  Storage.after mass balance with 1e-6 snapping (pywr/_core.pyx:1335-1361),
+ *             VirtualStorage.after (:1483-1493), then the recorders sample
+ *             (pywr/recorders/_recorders.pyx:611-617,680-688,723-734,769-779,1175-1183,
+ *              1744-1753,1768-1775,1795-1801,1808-1822,1845-1852).
+ * ============================================================================================== */
+typedef struct {
+    b200lp_program p; /* deep copy */
+    int loaded;
+    double **rec_out; /* [n_recorders] host outputs */
+    double *last_x;   /* [n][S] */
+    int32_t n_failed, fail_scenario, fail_code, fail_step;
+    pthread_mutex_t lock;
+} orc_program;
+
+static orc_program *orc_prog_of(orc_handle *h);
+
+/* the handle keeps the program in a side table (keeps orc_handle's layout untouched above) */
+#define ORC_MAX_PROGRAMS 64
+static struct { orc_handle *h; orc_program *pr; } g_programs[ORC_MAX_PROGRAMS];
+static pthread_mutex_t g_programs_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static orc_program *orc_prog_of(orc_handle *h) {
+    orc_program *r = NULL;
+    pthread_mutex_lock(&g_programs_lock);
+    for (int i = 0; i < ORC_MAX_PROGRAMS; i++)
+        if (g_programs[i].h == h) r = g_programs[i].pr;
+    pthread_mutex_unlock(&g_programs_lock);
+    return r;
+}
+
+static int rec_is_array(int32_t kind) { return kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC; }
+
+static void orc_free_program(orc_program *pr) {
+    if (!pr) return;
+    b200lp_program *p = &pr->p;
+    free((void *)p->ts_days); free((void *)p->op_kind); free((void *)p->op_dst); free((void *)p->op_arg_ptr);
+    free((void *)p->op_args); free((void *)p->table_rows); free((void *)p->table_cols); free((void *)p->table_axis);
+    free((void *)p->table_offset); free((void *)p->table_data); free((void *)p->scen_index);
+    free((void *)p->stflow_indptr); free((void *)p->stflow_col); free((void *)p->stflow_w);
+    free((void *)p->initial_volume); free((void *)p->initial_pc);
+    free((void *)p->rec_kind); free((void *)p->rec_src); free((void *)p->rec_ref); free((void *)p->rec_factor);
+    free((void *)p->rec_indptr); free((void *)p->rec_col); free((void *)p->rec_w);
+    if (pr->rec_out) for (int r = 0; r < p->n_recorders; r++) free(pr->rec_out[r]);
+    free(pr->rec_out); free(pr->last_x);
+    free(pr);
+}
+
+void orc_program_reset(void *hv) {
+    orc_handle *h = (orc_handle *)hv;
+    orc_program *pr = orc_prog_of(h);
+    if (!pr) return;
+    const b200lp_program *p = &pr->p;
+    orc_reset(h, p->initial_volume);
+    for (int32_t k = 0; k < h->S; k++) {
+        h->sc[k].dead = 0;
+        for (int32_t q = 0; q < h->s.n_storage; q++) h->sc[k].pc[q] = p->initial_pc[(size_t)q * h->S + k];
+    }
+    for (int r = 0; r < p->n_recorders; r++) {
+        const size_t count = rec_is_array(p->rec_kind[r]) ? (size_t)p->n_steps * h->S : (size_t)h->S;
+        for (size_t i = 0; i < count; i++) pr->rec_out[r][i] = (p->rec_kind[r] == B200LP_REC_MIN_VOLUME) ? INFINITY : 0.0;
+    }
+    pr->n_failed = 0; pr->fail_scenario = -1; pr->fail_code = 0; pr->fail_step = -1;
+}
+
+int orc_load_program(void *hv, const b200lp_program *src) {
+    orc_handle *h = (orc_handle *)hv;
+    if (!h || !src) return -1;
+    orc_program *pr = (orc_program *)calloc(1, sizeof(orc_program));
+    pr->p = *src;
+    b200lp_program *p = &pr->p;
+    const int32_t S = h->S, nst = h->s.n_storage;
+    p->ts_days = dup_mem(src->ts_days, sizeof(double) * src->n_steps);
+    p->op_kind = dup_mem(src->op_kind, sizeof(int32_t) * src->n_ops);
+    p->op_dst = dup_mem(src->op_dst, sizeof(int32_t) * src->n_ops);
+    p->op_arg_ptr = dup_mem(src->op_arg_ptr, sizeof(int32_t) * (src->n_ops + 1));
+    const int32_t nargs = src->n_ops ? src->op_arg_ptr[src->n_ops] : 0;
+    p->op_args = dup_mem(src->op_args, sizeof(int32_t) * nargs);
+    p->table_rows = dup_mem(src->table_rows, sizeof(int32_t) * src->n_tables);
+    p->table_cols = dup_mem(src->table_cols, sizeof(int32_t) * src->n_tables);
+    p->table_axis = dup_mem(src->table_axis, sizeof(int32_t) * src->n_tables);
+    p->table_offset = dup_mem(src->table_offset, sizeof(int64_t) * src->n_tables);
+    int64_t ndata = 0;
+    for (int t = 0; t < src->n_tables; t++) {
+        const int64_t end = src->table_offset[t] + (int64_t)src->table_rows[t] * src->table_cols[t];
+        if (end > ndata) ndata = end;
+    }
+    p->table_data = dup_mem(src->table_data, sizeof(double) * (size_t)ndata);
+    p->scen_index = dup_mem(src->scen_index, sizeof(int32_t) * (size_t)src->n_axes * S);
+    p->stflow_indptr = dup_mem(src->stflow_indptr, sizeof(int32_t) * (nst + 1));
+    const int32_t nsf = nst ? src->stflow_indptr[nst] : 0;
+    p->stflow_col = dup_mem(src->stflow_col, sizeof(int32_t) * nsf);
+    p->stflow_w = dup_mem(src->stflow_w, sizeof(double) * nsf);
+    p->initial_volume = dup_mem(src->initial_volume, sizeof(double) * (size_t)nst * S);
+    p->initial_pc = dup_mem(src->initial_pc, sizeof(double) * (size_t)nst * S);
+    p->rec_kind = dup_mem(src->rec_kind, sizeof(int32_t) * src->n_recorders);
+    p->rec_src = dup_mem(src->rec_src, sizeof(int32_t) * src->n_recorders);
+    p->rec_ref = dup_mem(src->rec_ref, sizeof(int32_t) * src->n_recorders);
+    p->rec_factor = dup_mem(src->rec_factor, sizeof(double) * src->n_recorders);
+    p->rec_indptr = dup_mem(src->rec_indptr, sizeof(int32_t) * (src->n_recorders + 1));
+    const int32_t nrc = src->n_recorders ? src->rec_indptr[src->n_recorders] : 0;
+    p->rec_col = dup_mem(src->rec_col, sizeof(int32_t) * nrc);
+    p->rec_w = dup_mem(src->rec_w, sizeof(double) * nrc);
+    pr->rec_out = (double **)calloc(src->n_recorders + 1, sizeof(double *));
+    for (int r = 0; r < src->n_recorders; r++) {
+        const size_t count = rec_is_array(src->rec_kind[r]) ? (size_t)src->n_steps * S : (size_t)S;
+        pr->rec_out[r] = (double *)calloc(count, sizeof(double));
+    }
+    pr->last_x = (double *)calloc((size_t)h->n * S + 1, sizeof(double));
+    pthread_mutex_init(&pr->lock, NULL);
+    pr->loaded = 1;
+    pthread_mutex_lock(&g_programs_lock);
+    int placed = 0;
+    for (int i = 0; i < ORC_MAX_PROGRAMS && !placed; i++) {
+        if (g_programs[i].h == h) { orc_free_program(g_programs[i].pr); g_programs[i].pr = pr; placed = 1; }
+    }
+    for (int i = 0; i < ORC_MAX_PROGRAMS && !placed; i++) {
+        if (g_programs[i].h == NULL) { g_programs[i].h = h; g_programs[i].pr = pr; placed = 1; }
+    }
+    pthread_mutex_unlock(&g_programs_lock);
+    if (!placed) { orc_free_program(pr); return -2; }
+    orc_program_reset(h);
+    return 0;
+}
+
+void orc_unload_program(void *hv) {
+    pthread_mutex_lock(&g_programs_lock);
+    for (int i = 0; i < ORC_MAX_PROGRAMS; i++)
+        if (g_programs[i].h == (orc_handle *)hv) { orc_free_program(g_programs[i].pr); g_programs[i].h = NULL; g_programs[i].pr = NULL; }
+    pthread_mutex_unlock(&g_programs_lock);
+}
+
+/* Storage.get_current_pc (pywr/_core.pyx:1027-1039) */
+static inline double clamp_pc(double pc) {
+    if (pc > 1.0 || isnan(pc)) return 1.0;
+    if (pc < 0.0) return 0.0;
+    return pc;
+}
+
+static inline double pref(const orc_handle *h, int32_t ref, const double *p) {
+    return ref >= 0 ? p[ref] : h->s.consts[-ref - 1];
+}
+
+static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, const orc_scen *c, int32_t sidx, int32_t t,
+                         double *p) {
+    for (int32_t k = 0; k < pg->n_ops; k++) {
+        const int32_t *a = pg->op_args + pg->op_arg_ptr[k];
+        double v = 0.0;
+        switch (pg->op_kind[k]) {
+        case B200LP_OP_TABLE: {
+            const int32_t tb = a[0];
+            int64_t row = 0;
+            if (pg->table_rows[tb] > 1) {
+                row = (int64_t)t + a[1];
+                if (row < 0) row = 0;
+                if (row > pg->table_rows[tb] - 1) row = pg->table_rows[tb] - 1;
+            }
+            const int32_t ax = pg->table_axis[tb];
+            const int32_t col = ax == B200LP_COL_NONE ? 0 : (ax == B200LP_COL_SCENARIO ? sidx : pg->scen_index[(size_t)ax * h->S + sidx]);
+            v = pg->table_data[pg->table_offset[tb] + row * pg->table_cols[tb] + col];
+        } break;
+        case B200LP_OP_AGG: {
+            const int32_t func = a[0], cnt = a[1];
+            if (func == B200LP_AGG_PRODUCT) { v = 1.0; for (int i = 0; i < cnt; i++) v *= pref(h, a[2 + i], p); }
+            else if (func == B200LP_AGG_SUM) { v = 0.0; for (int i = 0; i < cnt; i++) v += pref(h, a[2 + i], p); }
+            else if (func == B200LP_AGG_MAX) { v = -INFINITY; for (int i = 0; i < cnt; i++) { double w = pref(h, a[2 + i], p); if (w > v) v = w; } }
+            else if (func == B200LP_AGG_MIN) { v = INFINITY; for (int i = 0; i < cnt; i++) { double w = pref(h, a[2 + i], p); if (w < v) v = w; } }
+            else { v = 0.0; for (int i = 0; i < cnt; i++) v += pref(h, a[2 + i], p); v /= cnt; }
+        } break;
+        case B200LP_OP_CONTROL_CURVE: {
+            const int32_t cnt = a[1];
+            const double pc = clamp_pc(c->pc[a[0]]);
+            int32_t idx = cnt;
+            for (int i = 0; i < cnt; i++) if (pc >= pref(h, a[2 + i], p)) { idx = i; break; }
+            v = pref(h, a[2 + cnt + idx], p);
+        } break;
+        case B200LP_OP_CC_INDEX: {
+            const int32_t cnt = a[1];
+            const double pc = clamp_pc(c->pc[a[0]]);
+            int32_t idx = cnt;
+            for (int i = 0; i < cnt; i++) if (pc >= pref(h, a[2 + i], p)) { idx = i; break; }
+            v = (double)idx;
+        } break;
+        case B200LP_OP_INDEXED: {
+            int32_t idx = (int32_t)pref(h, a[0], p);
+            if (idx < 0) idx = 0;
+            if (idx > a[1] - 1) idx = a[1] - 1;
+            v = pref(h, a[2 + idx], p);
+        } break;
+        case B200LP_OP_NEG: v = -pref(h, a[0], p); break;
+        case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
+        case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
+        case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        default: v = NAN;
+        }
+        p[pg->op_dst[k]] = v;
+    }
+}
+
+typedef struct { orc_handle *h; orc_program *pr; int32_t s0, s1, t0, n; int64_t pivots, refactors; } orc_run_job;
+
+static void *orc_run_worker(void *arg) {
+    orc_run_job *J = (orc_run_job *)arg;
+    orc_handle *h = J->h;
+    orc_program *pr = J->pr;
+    const b200lp_program *pg = &pr->p;
+    const b200lp_structure *s = &h->s;
+    const int32_t m = h->m, n = h->n, S = h->S, nst = s->n_storage;
+    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + m + (size_t)m * n + 8));
+    double *x = work + 2 * (size_t)(m + n) + 3 * (size_t)n + m; /* ORC_WORK_X */
+    double *p = (double *)calloc(s->n_slots + 1, sizeof(double));
+    J->pivots = 0; J->refactors = 0;
+    for (int32_t k = J->s0; k < J->s1; k++) {
+        orc_scen *c = &h->sc[k];
+        for (int32_t t = J->t0; t < J->t0 + J->n && !c->dead; t++) {
+            const double days = pg->ts_days[t];
+            orc_eval_ops(h, pg, c, k, t, p);
+            slot_view sv = {p, 1, 0};
+            const int st = orc_solve_scenario(h, k, days, sv, NULL, NULL, NULL, work, &J->pivots, &J->refactors);
+            if (st != B200LP_ST_OPTIMAL) {
+                c->dead = 1;
+                pthread_mutex_lock(&pr->lock);
+                pr->n_failed++;
+                if (pr->fail_scenario < 0 || k < pr->fail_scenario) { pr->fail_scenario = k; pr->fail_code = st; pr->fail_step = t; }
+                pthread_mutex_unlock(&pr->lock);
+                break;
+            }
+            /* after(): storage mass balance */
+            for (int32_t q = 0; q < nst; q++) {
+                if (s->st_kind[q] == B200LP_ST_KIND_VIRTUAL && !(pref(h, s->st_active_ref[q], p) != 0.0)) continue;
+                double flow = 0.0;
+                for (int32_t e = pg->stflow_indptr[q]; e < pg->stflow_indptr[q + 1]; e++)
+                    flow = fma(pg->stflow_w[e], x[pg->stflow_col[e]], flow);
+                double vol = c->vol[q] + flow * days;
+                const double mxv = pref(h, s->st_maxv_ref[q], p), mnv = pref(h, s->st_minv_ref[q], p);
+                if (fabs(vol - mxv) < 1e-6) vol = mxv;
+                if (fabs(vol - mnv) < 1e-6) vol = mnv;
+                c->vol[q] = vol;
+                c->pc[q] = (mxv == 0.0) ? NAN : vol / mxv;
+            }
+            /* recorders */
+            for (int32_t r = 0; r < pg->n_recorders; r++) {
+                const int32_t kind = pg->rec_kind[r];
+                double *out = pr->rec_out[r];
+                double value = 0.0;
+                for (int32_t e = pg->rec_indptr[r]; e < pg->rec_indptr[r + 1]; e++)
+                    value = fma(pg->rec_w[e], x[pg->rec_col[e]], value);
+                const double f = pg->rec_factor[r];
+                switch (kind) {
+                case B200LP_REC_NODE_FLOW: out[(size_t)t * S + k] = value * f; break;
+                case B200LP_REC_NODE_DEFICIT: out[(size_t)t * S + k] = pref(h, pg->rec_ref[r], p) - value; break;
+                case B200LP_REC_NODE_SUPPLIED: { const double mf = pref(h, pg->rec_ref[r], p); out[(size_t)t * S + k] = mf == 0.0 ? 1.0 : value / mf; } break;
+                case B200LP_REC_NODE_CURTAIL: { const double mf = pref(h, pg->rec_ref[r], p); out[(size_t)t * S + k] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+                case B200LP_REC_STORAGE_VOLUME: out[(size_t)t * S + k] = c->vol[pg->rec_src[r]]; break;
+                case B200LP_REC_STORAGE_PC: out[(size_t)t * S + k] = c->pc[pg->rec_src[r]]; break;
+                case B200LP_REC_TOTAL_DEFICIT: out[k] += (pref(h, pg->rec_ref[r], p) - value) * days; break;
+                case B200LP_REC_TOTAL_FLOW: out[k] += value * f * days; break;
+                case B200LP_REC_MEAN_FLOW: out[k] += value * f; break;
+                case B200LP_REC_DEFICIT_FREQ: if (fabs(value - pref(h, pg->rec_ref[r], p)) > 1e-6) out[k] += 1.0; break;
+                case B200LP_REC_MIN_VOLUME: { const double v = c->vol[pg->rec_src[r]]; if (v < out[k]) out[k] = v; } break;
+                default: break;
+                }
+            }
+            if (t == J->t0 + J->n - 1)
+                for (int32_t j = 0; j < n; j++) pr->last_x[(size_t)j * S + k] = x[j];
+        }
+    }
+    free(work); free(p);
+    return NULL;
+}
+
+int orc_run(void *hv, int32_t t0, int32_t nsteps) {
+    orc_handle *h = (orc_handle *)hv;
+    orc_program *pr = orc_prog_of(h);
+    if (!pr || t0 < 0 || t0 + nsteps > pr->p.n_steps) return -1;
+    int nt = h->threads < 1 ? 1 : h->threads;
+    if (nt > h->S) nt = h->S;
+    orc_run_job *jobs = (orc_run_job *)calloc(nt, sizeof(orc_run_job));
+    pthread_t *tid = (pthread_t *)calloc(nt, sizeof(pthread_t));
+    for (int t = 0; t < nt; t++) {
+        jobs[t].h = h; jobs[t].pr = pr; jobs[t].t0 = t0; jobs[t].n = nsteps;
+        jobs[t].s0 = (int32_t)((int64_t)h->S * t / nt);
+        jobs[t].s1 = (int32_t)((int64_t)h->S * (t + 1) / nt);
+    }
+    for (int t = 1; t < nt; t++) pthread_create(&tid[t], NULL, orc_run_worker, &jobs[t]);
+    orc_run_worker(&jobs[0]);
+    for (int t = 1; t < nt; t++) pthread_join(tid[t], NULL);
+    for (int t = 0; t < nt; t++) { h->pivots += jobs[t].pivots; h->refactors += jobs[t].refactors; }
+    h->steps += nsteps;
+    free(jobs); free(tid);
+    return pr->n_failed;
+}
+
+void orc_program_status(void *hv, int32_t *n_failed, int32_t *scenario, int32_t *code, int32_t *timestep) {
+    orc_program *pr = orc_prog_of((orc_handle *)hv);
+    if (!pr) return;
+    if (n_failed) *n_failed = pr->n_failed;
+    if (scenario) *scenario = pr->fail_scenario;
+    if (code) *code = pr->fail_code;
+    if (timestep) *timestep = pr->fail_step;
+}
+
+int orc_fetch_recorder(void *hv, int32_t rec, double *out) {
+    orc_handle *h = (orc_handle *)hv;
+    orc_program *pr = orc_prog_of(h);
+    if (!pr || rec < 0 || rec >= pr->p.n_recorders) return -1;
+    const size_t count = rec_is_array(pr->p.rec_kind[rec]) ? (size_t)pr->p.n_steps * h->S : (size_t)h->S;
+    memcpy(out, pr->rec_out[rec], sizeof(double) * count);
+    return 0;
+}
+
+int orc_fetch_state(void *hv, double *col_flow, double *volume, double *pc) {
+    orc_handle *h = (orc_handle *)hv;
+    orc_program *pr = orc_prog_of(h);
+    if (col_flow && pr) memcpy(col_flow, pr->last_x, sizeof(double) * (size_t)h->n * h->S);
+    for (int32_t q = 0; q < h->s.n_storage; q++)
+        for (int32_t k = 0; k < h->S; k++) {
+            if (volume) volume[(size_t)q * h->S + k] = h->sc[k].vol[q];
+            if (pc) pc[(size_t)q * h->S + k] = h->sc[k].pc[q];
+        }
+    return 0;
 }

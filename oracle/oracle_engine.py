@@ -48,6 +48,16 @@ def lib():
         L.orc_get_volume.argtypes = [ctypes.c_void_p, dp]
         L.orc_set_volume.argtypes = [ctypes.c_void_p, dp]
         L.orc_counters.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int64)] * 3
+        L.orc_load_program.restype = ctypes.c_int
+        L.orc_load_program.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_program_reset.argtypes = [ctypes.c_void_p]
+        L.orc_run.restype = ctypes.c_int
+        L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
+        L.orc_program_status.argtypes = [ctypes.c_void_p] + [ip] * 4
+        L.orc_fetch_recorder.restype = ctypes.c_int
+        L.orc_fetch_recorder.argtypes = [ctypes.c_void_p, ctypes.c_int32, dp]
+        L.orc_fetch_state.restype = ctypes.c_int
+        L.orc_fetch_state.argtypes = [ctypes.c_void_p, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -100,6 +110,44 @@ class OracleEngine:
         v = [ctypes.c_int64() for _ in range(3)]
         self.L.orc_counters(self.h, *[ctypes.byref(x) for x in v])
         return {"pivots": v[0].value, "refactors": v[1].value, "steps": v[2].value}
+
+    # -- program mode (device-resident run semantics) ------------------------------------------
+    def load_program(self, prog):
+        self._cp = prog.to_c()
+        rc = self.L.orc_load_program(self.h, ctypes.addressof(self._cp))
+        if rc != 0:
+            raise RuntimeError(f"orc_load_program failed ({rc})")
+
+    def program_reset(self):
+        self.L.orc_program_reset(self.h)
+
+    def run(self, t0, n):
+        rc = self.L.orc_run(self.h, int(t0), int(n))
+        if rc < 0:
+            raise RuntimeError("orc_run: bad range or no program")
+        return rc
+
+    def sync(self):
+        pass
+
+    def program_status(self):
+        v = [ctypes.c_int32() for _ in range(4)]
+        self.L.orc_program_status(self.h, *[ctypes.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def fetch_recorder(self, r, shape):
+        out = np.zeros(shape, dtype=np.float64)
+        if self.L.orc_fetch_recorder(self.h, int(r), _dp(out)) != 0:
+            raise RuntimeError("orc_fetch_recorder failed")
+        return out
+
+    def fetch_state(self):
+        s = self.structure
+        x = np.zeros((s.n_cols, self.S))
+        vol = np.zeros((max(s.n_storage, 1), self.S))
+        pc = np.zeros((max(s.n_storage, 1), self.S))
+        self.L.orc_fetch_state(self.h, _dp(x), _dp(vol), _dp(pc))
+        return x, vol, pc
 
     def close(self):
         if self.h:

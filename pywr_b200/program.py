@@ -1,0 +1,505 @@
+"""Device-resident run: compile a Pywr model into a *program* the engine executes for all
+timesteps without host round trips (north_star: "flow commit, storage
+mass balance and the built-in recorders' per-scenario accumulation stay on device, so results reach
+the host only at recorder read-out").
+
+The compiler walks exactly the objects the reference's run loop touches each timestep
+(``Model.before/solve/after``, ``pywr/_model.pyx:626-631,825-860``):
+
+* every ``Parameter`` that feeds a bound, cost or capacity of the LP (the ``get_min_flow`` /
+  ``get_max_flow`` / ``get_cost`` / ``get_max_volume`` getters of ``pywr/_core.pyx``) is turned
+  into device ops (``include/b200lp.h`` ``B200LP_OP_*``) or, when it does not depend on model
+  state, expanded once into a table ``[timesteps][scenario members]`` that is uploaded to HBM;
+* ``Storage.after`` / ``VirtualStorage.after`` become the storage linear forms ``stflow_*``;
+* the built-in recorders named by north_star become ``B200LP_REC_*`` outputs.
+
+Anything outside that set raises :class:`Unsupported`; the caller then uses the per-timestep
+solver path (``pywr_b200.solver.B200Solver`` under ``Model.run``), which handles every model.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Any, Dict, List
+
+import numpy as np
+
+from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
+
+OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
+AGG = {"sum": 0, "product": 1, "min": 2, "max": 3, "mean": 4}
+COL_NONE, COL_SCENARIO = -1, -2
+(REC_NODE_FLOW, REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_STORAGE_VOLUME, REC_STORAGE_PC,
+ REC_TOTAL_DEFICIT, REC_TOTAL_FLOW, REC_MEAN_FLOW, REC_DEFICIT_FREQ, REC_MIN_VOLUME) = range(1, 12)
+ARRAY_KINDS = {REC_NODE_FLOW, REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_STORAGE_VOLUME, REC_STORAGE_PC}
+
+
+class Unsupported(Exception):
+    """The model uses something the device-resident run does not cover (yet)."""
+
+
+class b200lp_program(ctypes.Structure):
+    _i32p = ctypes.POINTER(ctypes.c_int32)
+    _i64p = ctypes.POINTER(ctypes.c_int64)
+    _f64p = ctypes.POINTER(ctypes.c_double)
+    _fields_ = [
+        ("n_steps", ctypes.c_int32), ("n_ops", ctypes.c_int32), ("n_tables", ctypes.c_int32),
+        ("n_axes", ctypes.c_int32), ("n_recorders", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("ts_days", _f64p),
+        ("op_kind", _i32p), ("op_dst", _i32p), ("op_arg_ptr", _i32p), ("op_args", _i32p),
+        ("table_rows", _i32p), ("table_cols", _i32p), ("table_axis", _i32p), ("table_offset", _i64p),
+        ("table_data", _f64p),
+        ("scen_index", _i32p),
+        ("stflow_indptr", _i32p), ("stflow_col", _i32p), ("stflow_w", _f64p),
+        ("initial_volume", _f64p), ("initial_pc", _f64p),
+        ("rec_kind", _i32p), ("rec_src", _i32p), ("rec_ref", _i32p), ("rec_factor", _f64p),
+        ("rec_indptr", _i32p), ("rec_col", _i32p), ("rec_w", _f64p),
+    ]
+
+
+_P_I32 = ("op_kind op_dst op_arg_ptr op_args table_rows table_cols table_axis scen_index stflow_indptr "
+          "stflow_col rec_kind rec_src rec_ref rec_indptr rec_col").split()
+_P_I64 = ["table_offset"]
+_P_F64 = "ts_days table_data stflow_w initial_volume initial_pc rec_factor rec_w".split()
+
+
+@dataclass
+class Program:
+    n_steps: int
+    n_axes: int
+    ts_days: np.ndarray
+    op_kind: np.ndarray
+    op_dst: np.ndarray
+    op_arg_ptr: np.ndarray
+    op_args: np.ndarray
+    table_rows: np.ndarray
+    table_cols: np.ndarray
+    table_axis: np.ndarray
+    table_offset: np.ndarray
+    table_data: np.ndarray
+    scen_index: np.ndarray
+    stflow_indptr: np.ndarray
+    stflow_col: np.ndarray
+    stflow_w: np.ndarray
+    initial_volume: np.ndarray
+    initial_pc: np.ndarray
+    rec_kind: np.ndarray
+    rec_src: np.ndarray
+    rec_ref: np.ndarray
+    rec_factor: np.ndarray
+    rec_indptr: np.ndarray
+    rec_col: np.ndarray
+    rec_w: np.ndarray
+    recorders: List[Any] = field(default_factory=list, repr=False)  # host objects, same order as rec_*
+
+    @property
+    def n_ops(self):
+        return int(self.op_kind.shape[0])
+
+    @property
+    def n_tables(self):
+        return int(self.table_rows.shape[0])
+
+    @property
+    def n_recorders(self):
+        return int(self.rec_kind.shape[0])
+
+    def rec_shape(self, r, S):
+        return (self.n_steps, S) if int(self.rec_kind[r]) in ARRAY_KINDS else (S,)
+
+    def to_c(self) -> b200lp_program:
+        cp = b200lp_program()
+        cp.n_steps, cp.n_ops, cp.n_tables = self.n_steps, self.n_ops, self.n_tables
+        cp.n_axes, cp.n_recorders = self.n_axes, self.n_recorders
+        keep = []
+        for names, dt, ct in ((_P_I32, np.int32, ctypes.c_int32), (_P_I64, np.int64, ctypes.c_int64),
+                              (_P_F64, np.float64, ctypes.c_double)):
+            for name in names:
+                arr = np.ascontiguousarray(getattr(self, name), dtype=dt).reshape(-1)
+                if arr.size == 0:
+                    arr = np.zeros(1, dt)
+                keep.append(arr)
+                setattr(cp, name, arr.ctypes.data_as(ctypes.POINTER(ct)))
+        cp._keepalive = keep
+        return cp
+
+    def save(self, path):
+        data = {name: np.asarray(getattr(self, name)) for name in _P_I32 + _P_I64 + _P_F64}
+        data["meta"] = np.array([self.n_steps, self.n_axes], np.int64)
+        np.savez_compressed(path, **data)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        n_steps, n_axes = (int(v) for v in z["meta"])
+        kw = {n: z[n].astype(np.int32) for n in _P_I32}
+        kw.update({n: z[n].astype(np.int64) for n in _P_I64})
+        kw.update({n: z[n].astype(np.float64) for n in _P_F64})
+        return cls(n_steps=n_steps, n_axes=n_axes, **kw)
+
+
+# ----------------------------------------------------------------------------------------------
+# compiler
+# ----------------------------------------------------------------------------------------------
+_VALUE_LEAVES = {  # state- and scenario-independent: sampled through their public ``value(ts, si)``
+    "MonthlyProfileParameter", "DailyProfileParameter", "WeeklyProfileParameter",
+    "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter",
+}
+_SCENARIO_PROFILES = {
+    "ScenarioMonthlyProfileParameter", "ScenarioDailyProfileParameter", "ScenarioWeeklyProfileParameter",
+    "ArrayIndexedScenarioMonthlyFactorsParameter",
+}
+
+
+class _Compiler:
+    def __init__(self, model, structure: LPStructure):
+        from pywr import _core
+
+        self.model = model
+        self.s = structure
+        self.S = len(model.scenarios.combinations)
+        ts = model.timestepper
+        self.T = len(ts)
+        self.timesteps = [_core.Timestep(ts._periods[i], i, ts._deltas[i]) for i in range(self.T)]
+        self.combinations = list(model.scenarios.combinations)
+        self.n_axes = len(model.scenarios.scenarios)
+        self.scen_index = np.zeros((max(self.n_axes, 1), self.S), np.int32)
+        for si in self.combinations:
+            idx = np.asarray(si.indices)
+            for a in range(self.n_axes):
+                self.scen_index[a, si.global_id] = idx[a]
+        self.consts = list(structure.consts)
+        self.n_slots = 0
+        self.ops = []      # (kind, dst, args)
+        self.tables = []   # (values[rows, cols], axis)
+        self.memo: Dict[int, int] = {}
+        self.storage_index = {id(st): k for k, st in enumerate(structure.storages)}
+
+    # -- small helpers ---------------------------------------------------------------------
+    def const(self, v) -> int:
+        self.consts.append(float(v))
+        return -len(self.consts)
+
+    def new_slot(self) -> int:
+        self.n_slots += 1
+        return self.n_slots - 1
+
+    def emit(self, kind, args) -> int:
+        dst = self.new_slot()
+        self.ops.append((kind, dst, [int(a) for a in args]))
+        return dst
+
+    def table(self, values, axis, offset=0) -> int:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert values.ndim == 2
+        if values.shape == (1, 1) and offset == 0:
+            return self.const(values[0, 0])
+        self.tables.append((values, COL_NONE if axis is None else int(axis)))
+        return self.emit(OP_TABLE, [len(self.tables) - 1, offset])
+
+    def representative(self, axis, member):
+        """A ScenarioIndex whose index on ``axis`` is ``member`` (other axes at 0)."""
+        from pywr._core import ScenarioIndex
+
+        idx = np.zeros(max(self.n_axes, 1), np.int32)
+        if axis is not None:
+            idx[axis] = member
+        return ScenarioIndex(0, idx)
+
+    # -- parameters -> refs ----------------------------------------------------------------
+    def value_ref(self, value) -> int:
+        from pywr.parameters import Parameter
+
+        if isinstance(value, Parameter):
+            return self.param(value)
+        return self.const(value)
+
+    def param(self, p) -> int:
+        key = id(p)
+        if key in self.memo:
+            return self.memo[key]
+        ref = self._param(p)
+        self.memo[key] = ref
+        return ref
+
+    def _param(self, p) -> int:
+        from .bridge import _bridge
+
+        name = type(p).__name__
+        if name == "ConstantParameter" or (getattr(p, "is_constant", False) and name != "ConstantScenarioParameter"):
+            return self.const(p.get_constant_value())
+        info = _bridge.parameter_arrays(p)
+        if info is not None:
+            values, axis = info["values"], info["axis"]
+            if info["col_map"] is not None:  # sliced / user-combination data: member -> loaded column
+                cmap = info["col_map"]
+                full = np.full((values.shape[0], len(cmap)), np.nan)
+                ok = cmap < values.shape[1]
+                full[:, ok] = values[:, cmap[ok]]
+                values = full
+            if values.shape[0] not in (1, self.T):
+                raise Unsupported(f"{name}: {values.shape[0]} rows for {self.T} timesteps")
+            return self.table(values, axis, int(info["offset"]))
+        if name in _VALUE_LEAVES:
+            si = self.representative(None, 0)
+            return self.table(np.array([[p.value(ts, si)] for ts in self.timesteps]), None)
+        if name in _SCENARIO_PROFILES:
+            axis = _bridge.scenario_axis(p)
+            size = self.model.scenarios.scenarios[axis].size
+            sis = [self.representative(axis, c) for c in range(size)]
+            return self.table(np.array([[p.value(ts, si) for si in sis] for ts in self.timesteps]), axis)
+        if name == "AggregatedParameter":
+            func = p.agg_func
+            if not isinstance(func, str) or func not in AGG:
+                raise Unsupported(f"AggregatedParameter agg_func {func!r}")
+            refs = [self.param(c) for c in p.parameters]
+            return self.emit(OP_AGG, [AGG[func], len(refs)] + refs)
+        if name == "ControlCurveParameter":
+            k = self.storage_of(p.storage_node)
+            curves = [self.param(c) for c in p.control_curves]
+            if p.parameters is not None:
+                vals = [self.param(c) for c in p.parameters]
+            else:
+                vals = [self.const(v) for v in np.asarray(p.values)]
+            if len(vals) != len(curves) + 1:
+                raise Unsupported("ControlCurveParameter: len(values) != len(control_curves)+1")
+            return self.emit(OP_CONTROL_CURVE, [k, len(curves)] + curves + vals)
+        if name == "ControlCurveIndexParameter":
+            k = self.storage_of(p.storage_node)
+            curves = [self.param(c) for c in p.control_curves]
+            return self.emit(OP_CC_INDEX, [k, len(curves)] + curves)
+        if name == "IndexedArrayParameter":
+            idx = self.param(p.index_parameter)
+            refs = [self.param(c) for c in p.params]
+            return self.emit(OP_INDEXED, [idx, len(refs)] + refs)
+        if name == "NegativeParameter":
+            return self.emit(OP_NEG, [self.param(p.parameter)])
+        if name == "MaxParameter":
+            return self.emit(OP_MAX0, [self.param(p.parameter), self.const(p.threshold)])
+        if name == "MinParameter":
+            return self.emit(OP_MIN0, [self.param(p.parameter), self.const(p.threshold)])
+        if name == "NegativeMaxParameter":
+            return self.emit(OP_MAX0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
+        if name == "NegativeMinParameter":
+            return self.emit(OP_MIN0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
+        raise Unsupported(f"parameter type {name} is not available on the device")
+
+    def storage_of(self, node) -> int:
+        k = self.storage_index.get(id(node))
+        if k is None or self.s.st_kind[k] == ST_KIND_VIRTUAL and type(node).__name__ != "VirtualStorage":
+            raise Unsupported(f"control curve on {type(node).__name__} {getattr(node, 'name', '')!r}")
+        return k
+
+    # -- bindings of the LP structure ------------------------------------------------------------
+    def binding_ref(self, b) -> int:
+        from pywr._core import StorageInput
+        from pywr.parameters import Parameter
+
+        kind, obj = b.kind, b.obj
+        if b.loop:
+            raise Unsupported(f"{type(obj).__name__}.get_{kind} is overridden in Python")
+        if kind == "volume":
+            return REF_STATE
+        if kind == "active":
+            if type(obj).__name__ != "VirtualStorage":
+                raise Unsupported(f"{type(obj).__name__}: activation / reset schedule is host-side")
+            return self.const(1.0)
+        if kind == "factor_norm":
+            f = obj.factors
+            return self.emit(OP_DIV, [self.param(f[0]), self.param(f[b.index])])
+        if kind == "cost" and type(obj).__name__ in ("StorageInput", "StorageOutput"):
+            value = obj.parent.cost
+            if isinstance(value, Parameter):
+                ref = self.param(value)
+                return self.emit(OP_NEG, [ref]) if isinstance(obj, StorageInput) else ref
+            return self.const(-value if isinstance(obj, StorageInput) else value)
+        value = getattr(obj, kind)
+        if kind == "min_flow" and value is None:
+            value = 0.0
+        return self.value_ref(value)
+
+
+def _flow_form(structure: LPStructure, node, node_id, depth=0):
+    """Linear form (col -> weight) of a node's flow after ``commit`` and ``after`` — the value the
+    recorders read (``AbstractNode._flow``).  Plain nodes: the solver's own sum (cython_glpk.pyx:
+    1078-1088).  Storage: outputs minus inputs (``_core.pyx:942-979``).  AggregatedNode: weighted
+    member sum (``_core.pyx:762-776``).  Compound nodes copy a sub-node (``nodes.py:880-887``...)."""
+    from pywr._core import AggregatedNode, Storage, VirtualStorage
+
+    s = structure
+    form: Dict[int, float] = {}
+
+    def add(other, w):
+        for c, v in other.items():
+            form[c] = form.get(c, 0.0) + w * v
+
+    if depth > 8:
+        raise Unsupported("node nesting too deep")
+    if isinstance(node, VirtualStorage):
+        for n, f in zip(node.nodes, node.factors):
+            add(_flow_form(s, n, node_id, depth + 1), -float(f))
+        return form
+    if isinstance(node, Storage):
+        for n in node.outputs:
+            add(_flow_form(s, n, node_id, depth + 1), 1.0)
+        for n in node.inputs:
+            add(_flow_form(s, n, node_id, depth + 1), -1.0)
+        return form
+    if isinstance(node, AggregatedNode):
+        weights = node.flow_weights
+        if weights is None:
+            weights = [1.0] * len(node.nodes)
+        for n, w in zip(node.nodes, weights):
+            add(_flow_form(s, n, node_id, depth + 1), float(w))
+        return form
+    cname = type(node).__name__
+    if cname in ("PiecewiseLink", "RiverGauge", "MultiSplitLink", "RiverSplit", "RiverSplitWithGauge"):
+        # after(): commit_all(sub-output flow)   (pywr/nodes.py:880-887)
+        return _flow_form(s, node.output, node_id, depth + 1)
+    if cname == "LossLink":
+        return _flow_form(s, node.net, node_id, depth + 1)  # pywr/nodes.py:1361-1364
+    if cname == "BreakLink":
+        return _flow_form(s, node.link, node_id, depth + 1)  # pywr/nodes.py:1168-1171
+    i = node_id.get(id(node))
+    if i is None:
+        raise Unsupported(f"node {getattr(node, 'name', node)!r} is not part of the LP")
+    for k in range(s.flow_indptr[i], s.flow_indptr[i + 1]):
+        c = int(s.flow_col[k])
+        form[c] = form.get(c, 0.0) + float(s.flow_w[k])
+    if not form and cname not in ("Input", "Output", "Link", "Catchment", "River", "StorageInput", "StorageOutput"):
+        raise Unsupported(f"flow of {cname} {getattr(node, 'name', '')!r} is computed on the host")
+    return form
+
+
+def _remap(refs, mapping):
+    return np.array([mapping.get(int(r), int(r)) if r >= 0 else int(r) for r in refs], np.int32)
+
+
+def compile_program(model, formulation="route", recorders=None):
+    """Returns ``(structure, program)`` for a model that has been ``setup()`` and ``reset()``.
+
+    ``structure`` is the LP structure with every input plane replaced by an op output or a constant
+    and the storage volumes device-resident; ``program`` holds ops, tables, storage linear forms,
+    initial state and recorders.  Raises :class:`Unsupported` when the model needs the host."""
+    from .bridge import _bridge
+
+    base = build_structure(model, formulation)
+    C = _Compiler(model, base)
+    S, T = C.S, C.T
+    node_id = {id(n): i for i, n in enumerate(base.all_nodes)}
+
+    # ---- LP inputs --------------------------------------------------------------------------
+    mapping = {}
+    for b in base.bindings:
+        if b.slot >= 0:
+            mapping[b.slot] = C.binding_ref(b)
+    max_flow_ref = {}
+    for b in base.bindings:
+        if b.kind == "max_flow":
+            max_flow_ref[id(b.obj)] = mapping[b.slot] if b.slot >= 0 else b.ref
+
+    # ---- storages -------------------------------------------------------------------------------
+    vol0 = np.zeros((max(base.n_storage, 1), S))
+    pc0 = np.zeros((max(base.n_storage, 1), S))
+    sf_indptr, sf_col, sf_w = [0], [], []
+    for k, st in enumerate(base.storages):
+        cname = type(st).__name__
+        if cname not in ("Storage", "Reservoir", "VirtualStorage"):
+            raise Unsupported(f"storage type {cname} keeps extra state on the host")
+        vol0[k] = np.asarray(st._volume)
+        pc0[k] = np.asarray(st._current_pc)
+        form = _flow_form(base, st, node_id)
+        for c in sorted(form):
+            sf_col.append(c)
+            sf_w.append(form[c])
+        sf_indptr.append(len(sf_col))
+
+    # ---- recorders ------------------------------------------------------------------------------
+    if recorders is None:
+        recorders = list(model.recorders)
+    rec_kind, rec_src, rec_ref, rec_factor, rec_indptr, rec_col, rec_w, rec_objs = [], [], [], [], [0], [], [], []
+    node_kinds = {
+        "NumpyArrayNodeRecorder": REC_NODE_FLOW, "NumpyArrayNodeDeficitRecorder": REC_NODE_DEFICIT,
+        "NumpyArrayNodeSuppliedRatioRecorder": REC_NODE_SUPPLIED,
+        "NumpyArrayNodeCurtailmentRatioRecorder": REC_NODE_CURTAIL,
+        "TotalDeficitNodeRecorder": REC_TOTAL_DEFICIT, "TotalFlowNodeRecorder": REC_TOTAL_FLOW,
+        "MeanFlowNodeRecorder": REC_MEAN_FLOW, "DeficitFrequencyNodeRecorder": REC_DEFICIT_FREQ,
+    }
+    needs_max_flow = {REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_TOTAL_DEFICIT, REC_DEFICIT_FREQ}
+    for rec in recorders:
+        cname = type(rec).__name__
+        if cname == "AggregatedRecorder":
+            continue  # reduces other recorders' values() on the host at read-out (a13)
+        node = _bridge.recorder_node(rec)
+        if cname in node_kinds:
+            kind = node_kinds[cname]
+            form = _flow_form(base, node, node_id)
+            ref = 0
+            if kind in needs_max_flow:
+                if id(node) not in max_flow_ref:
+                    raise Unsupported(f"{cname} on {type(node).__name__} without an LP max_flow")
+                ref = max_flow_ref[id(node)]
+            factor = float(getattr(rec, "factor", 1.0)) if kind in (REC_NODE_FLOW, REC_TOTAL_FLOW, REC_MEAN_FLOW) else 1.0
+            rec_kind.append(kind); rec_src.append(node_id.get(id(node), -1)); rec_ref.append(ref)
+            rec_factor.append(factor)
+            for c in sorted(form):
+                rec_col.append(c); rec_w.append(form[c])
+        elif cname in ("NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"):
+            k = C.storage_index.get(id(node))
+            if k is None:
+                raise Unsupported(f"{cname} on {type(node).__name__}")
+            if cname == "MinimumVolumeStorageRecorder":
+                kind = REC_MIN_VOLUME
+            else:
+                kind = REC_STORAGE_PC if rec.proportional else REC_STORAGE_VOLUME
+            rec_kind.append(kind); rec_src.append(k); rec_ref.append(0); rec_factor.append(1.0)
+        else:
+            raise Unsupported(f"recorder type {cname} is evaluated on the host")
+        rec_indptr.append(len(rec_col))
+        rec_objs.append(rec)
+
+    # ---- assemble --------------------------------------------------------------------------------
+    consts = np.asarray(C.consts, np.float64)
+    st_vol = np.full(base.n_storage, REF_STATE, np.int32)
+    s = LPStructure(
+        formulation=base.formulation, n_rows=base.n_rows, n_cols=base.n_cols, n_nodes=base.n_nodes,
+        cost_clip=base.cost_clip, a_indptr=base.a_indptr, a_col=base.a_col, a_val=base.a_val,
+        row_kind=base.row_kind,
+        row_lb_ref=np.where(base.row_kind == 0, _remap(base.row_lb_ref, mapping), base.row_lb_ref).astype(np.int32),
+        row_ub_ref=np.where(base.row_kind == 0, _remap(base.row_ub_ref, mapping), base.row_ub_ref).astype(np.int32),
+        st_kind=base.st_kind, st_vol_ref=st_vol, st_minv_ref=_remap(base.st_minv_ref, mapping),
+        st_maxv_ref=_remap(base.st_maxv_ref, mapping), st_active_ref=_remap(base.st_active_ref, mapping),
+        cost_indptr=base.cost_indptr, cost_ref=_remap(base.cost_ref, mapping), cost_w=base.cost_w,
+        dyn_a_nz=base.dyn_a_nz, dyn_a_ref=_remap(base.dyn_a_ref, mapping), dyn_a_scale=base.dyn_a_scale,
+        flow_indptr=base.flow_indptr, flow_col=base.flow_col, flow_w=base.flow_w,
+        consts=consts, n_slots=max(C.n_slots, 1),
+        node_names=base.node_names, row_names=base.row_names, col_names=base.col_names,
+        bindings=base.bindings, all_nodes=base.all_nodes, routes=base.routes, storages=base.storages,
+    )
+    op_arg_ptr, op_args = [0], []
+    for _, _, args in C.ops:
+        op_args.extend(args)
+        op_arg_ptr.append(len(op_args))
+    offsets, chunks, pos = [], [], 0
+    for values, _ in C.tables:
+        offsets.append(pos)
+        chunks.append(values.reshape(-1))
+        pos += values.size
+    i32 = lambda x: np.asarray(x, dtype=np.int32)  # noqa: E731
+    f64 = lambda x: np.asarray(x, dtype=np.float64)  # noqa: E731
+    prog = Program(
+        n_steps=T, n_axes=C.n_axes,
+        ts_days=f64([ts.days for ts in C.timesteps]),
+        op_kind=i32([k for k, _, _ in C.ops]), op_dst=i32([d for _, d, _ in C.ops]),
+        op_arg_ptr=i32(op_arg_ptr), op_args=i32(op_args),
+        table_rows=i32([v.shape[0] for v, _ in C.tables]), table_cols=i32([v.shape[1] for v, _ in C.tables]),
+        table_axis=i32([a for _, a in C.tables]), table_offset=np.asarray(offsets, np.int64),
+        table_data=np.concatenate(chunks) if chunks else np.zeros(0),
+        scen_index=C.scen_index.reshape(-1),
+        stflow_indptr=i32(sf_indptr), stflow_col=i32(sf_col), stflow_w=f64(sf_w),
+        initial_volume=vol0.reshape(-1), initial_pc=pc0.reshape(-1),
+        rec_kind=i32(rec_kind), rec_src=i32(rec_src), rec_ref=i32(rec_ref), rec_factor=f64(rec_factor),
+        rec_indptr=i32(rec_indptr), rec_col=i32(rec_col), rec_w=f64(rec_w), recorders=rec_objs,
+    )
+    return s, prog
