@@ -1,0 +1,233 @@
+"""Benchmark workloads (BASELINE.json `configs`): model documents, the
+synthetic stochastic inflow generator, and run-time construction of device programs.
+
+Two ways to obtain the program of a workload:
+  * ``build_model(...)`` + ``pywr_b200.program.compile_program`` — needs the reference framework
+    (baseline/_ref); this is what a user does and what ``benchmarks/make_fixtures.py`` runs;
+  * ``load_workload(...)`` — loads the structure + single-scenario program compiled by
+    make_fixtures.py (committed under benchmarks/fixtures/) and widens it to S scenarios by swapping in
+    the synthetic inflow table; needs only numpy, so ``bench.py`` runs on a box without Pywr.
+``tests/test_workloads.py`` checks that both give the same program.
+"""
+
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+
+FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures")
+
+# Summary statistics of column `flow` of the reference's examples/data/thames_stochastic_flow.gz
+# (36,524 daily values, m3/s): mean of log(flow) per calendar month, standard deviation and lag-1
+# autocorrelation of the de-seasonalised log flow.  Derived numbers, not the data.
+THAMES_LOG_MEAN_BY_MONTH = np.array([3.8735, 4.2096, 4.2449, 3.8334, 3.3088, 2.9321, 2.7325, 2.7017, 2.7557,
+                                     2.9138, 3.0789, 3.3541])
+THAMES_LOG_RESID_STD = 0.7006
+FLOW_FACTOR = 0.0864  # m3/s -> Ml/d, the models' `flow_factor` parameter
+
+SEEDS = {"two_reservoir": 20240901, "thames": 20240902, "two_reservoir_params": 20240904}
+
+
+def daily_index(start, years=None, end=None):
+    import pandas as pd
+
+    if end is None:
+        end = pd.Timestamp(start) + pd.DateOffset(years=years) - pd.Timedelta(days=1)
+    return pd.date_range(start, end, freq="D")
+
+
+def synthetic_inflow(months, n_scenarios, seed, first_scenario=0, rho=0.9):
+    """[T, n_scenarios] float64 daily inflow in model units.  Log-space AR(1) with lag-1 correlation
+    `rho` around the monthly log-mean of the Thames record, independent per scenario; scenario k of the
+    GLOBAL batch always gets the same series whatever the number of ranks (its generator is seeded
+    with (seed, k))."""
+    months = np.asarray(months)
+    T = months.shape[0]
+    mu = THAMES_LOG_MEAN_BY_MONTH[months - 1]
+    out = np.empty((T, n_scenarios))
+    sd = THAMES_LOG_RESID_STD
+    innov = sd * np.sqrt(1.0 - rho * rho)
+    try:
+        from scipy.signal import lfilter
+    except Exception:  # pragma: no cover
+        lfilter = None
+    for k in range(n_scenarios):
+        rng = np.random.default_rng([seed, first_scenario + k])
+        e = rng.standard_normal(T) * innov
+        e[0] = rng.standard_normal() * sd
+        if lfilter is not None:
+            z = lfilter([1.0], [1.0, -rho], e)
+        else:
+            z = np.empty(T)
+            z[0] = e[0]
+            for t in range(1, T):
+                z[t] = rho * z[t - 1] + e[t]
+        out[:, k] = np.exp(mu + z) * FLOW_FACTOR
+    return out
+
+
+# ---- model documents (same topology and numbers as the reference's example models, restated) -----
+def two_reservoir_document(start, end, control_curve=0.5):
+    """examples/two_reservoir: two catchments feeding two reservoirs with compensation releases
+    (river gauges), two demands and a controlled transfer from reservoir2 to reservoir1."""
+    return {
+        "metadata": {"title": "two reservoir (benchmark)", "minimum_version": "0.1"},
+        "timestepper": {"start": start, "end": end, "timestep": 1},
+        "nodes": [
+            {"name": "catchment1", "type": "catchment", "flow": 0.0},
+            {"name": "catchment2", "type": "catchment", "flow": 0.0},
+            {"name": "reservoir1", "type": "storage", "min_volume": 0, "max_volume": 200, "initial_volume": 200, "cost": -5},
+            {"name": "reservoir2", "type": "storage", "min_volume": 0, "max_volume": 200, "initial_volume": 200, "cost": -5},
+            {"name": "transfer", "type": "link", "cost": -500, "max_flow": "transfer_controller"},
+            {"name": "demand1", "type": "output", "max_flow": 1.8, "cost": -101},
+            {"name": "demand2", "type": "output", "max_flow": 1.0, "cost": -100},
+            {"name": "river1", "type": "link"},
+            {"name": "river2", "type": "link"},
+            {"name": "compensation1", "type": "rivergauge", "mrf": 0.6, "mrf_cost": -1000},
+            {"name": "compensation2", "type": "rivergauge", "mrf": 0.6, "mrf_cost": -1000},
+            {"name": "terminator", "type": "output"},
+        ],
+        "edges": [
+            ["catchment1", "reservoir1"], ["catchment2", "reservoir2"], ["reservoir1", "river1"],
+            ["reservoir2", "river2"], ["river1", "compensation1"], ["river2", "compensation2"],
+            ["compensation1", "terminator"], ["compensation2", "terminator"], ["reservoir2", "transfer"],
+            ["transfer", "reservoir1"], ["reservoir1", "demand1"], ["reservoir2", "demand2"],
+        ],
+        "parameters": {
+            "control_curve": {"type": "monthlyprofile", "values": [control_curve] * 12},
+            "transfer_controller": {"type": "controlcurve", "storage_node": "reservoir1",
+                                    "control_curve": "control_curve", "values": [0.0, 1.0]},
+        },
+        "recorders": {
+            "deficit1": {"type": "DeficitFrequencyNode", "node": "demand1"},
+            "deficit2": {"type": "DeficitFrequencyNode", "node": "demand2"},
+            "transferred": {"type": "totalflownode", "node": "transfer"},
+            "volume1": {"type": "NumpyArrayStorageRecorder", "node": "reservoir1"},
+            "volume2": {"type": "NumpyArrayStorageRecorder", "node": "reservoir2"},
+            "supplied1": {"type": "NumpyArrayNodeRecorder", "node": "demand1"},
+            "supplied2": {"type": "NumpyArrayNodeRecorder", "node": "demand2"},
+        },
+    }
+
+
+def thames_document(start, end):
+    """examples/thames: catchment -> river -> (minimum residual flow gauge -> sea | abstraction ->
+    reservoir -> demand) with demand saving driven by the reservoir's control curves."""
+    prof = lambda a, b: [a, a, a, a, b, b, b, b, a, a, a, a]  # noqa: E731
+    return {
+        "metadata": {"title": "thames (benchmark)", "minimum_version": "0.1"},
+        "timestepper": {"start": start, "end": end, "timestep": 1},
+        "nodes": [
+            {"name": "catchment1", "type": "catchment", "flow": 0.0},
+            {"name": "river1", "type": "link"},
+            {"name": "mrf1", "type": "rivergauge", "mrf": 0.6, "mrf_cost": -1000},
+            {"name": "term1", "type": "output"},
+            {"name": "reservoir1", "type": "storage", "max_volume": 200, "initial_volume": 200, "cost": -10},
+            {"name": "abs1", "type": "link", "max_flow": 3.5},
+            {"name": "demand1", "type": "output", "max_flow": "demand_max_flow", "cost": -500},
+        ],
+        "edges": [["catchment1", "river1"], ["river1", "mrf1"], ["mrf1", "term1"], ["river1", "abs1"],
+                  ["abs1", "reservoir1"], ["reservoir1", "demand1"]],
+        "parameters": {
+            "demand_baseline": {"type": "constant", "value": 1.7},
+            "demand_profile": {"type": "monthlyprofile", "values": prof(0.9, 1.2)},
+            "demand_max_flow": {"type": "aggregated", "agg_func": "product",
+                                "parameters": ["demand_baseline", "demand_profile", "demand_saving_factor"]},
+            "level1": {"type": "monthlyprofile", "values": [0.8, 0.85, 0.9, 0.92, 0.9, 0.85, 0.8, 0.7, 0.65, 0.7, 0.75, 0.8]},
+            "level2": {"type": "monthlyprofile", "values": [0.5, 0.55, 0.6, 0.62, 0.6, 0.55, 0.5, 0.4, 0.35, 0.4, 0.45, 0.5]},
+            "demand_saving_level": {"type": "controlcurveindex", "storage_node": "reservoir1",
+                                    "control_curves": ["level1", "level2"]},
+            "demand_saving_factor": {"type": "indexedarray", "index_parameter": "demand_saving_level",
+                                     "params": ["level0_factor", "level1_factor", "level2_factor"]},
+            "level0_factor": {"type": "constant", "value": 1.0},
+            "level1_factor": {"type": "monthlyprofile", "values": prof(0.95, 0.9)},
+            "level2_factor": {"type": "monthlyprofile", "values": prof(0.8, 0.75)},
+        },
+        "recorders": {
+            "volume": {"type": "NumpyArrayStorageRecorder", "node": "reservoir1"},
+            "supplied": {"type": "NumpyArrayNodeRecorder", "node": "demand1"},
+            "deficit": {"type": "TotalDeficitNodeRecorder", "node": "demand1"},
+        },
+    }
+
+
+WORKLOADS = {
+    # name: (document, start, years, inflow catchments, seed key)
+    "two_reservoir": dict(document=two_reservoir_document, start="2100-01-01", years=50,
+                          catchments=("catchment1", "catchment2"), seed="two_reservoir"),
+    "thames": dict(document=thames_document, start="2100-01-01", years=30, catchments=("catchment1",), seed="thames"),
+}
+
+
+def build_model(name, n_scenarios, years=None, solver=None, inflow=None, first_scenario=0):
+    """The workload as a live Pywr model (needs the reference framework): the document above plus a
+    Scenario("inflow", size=S) and an ArrayIndexedScenarioParameter with the synthetic inflow feeding
+    every catchment."""
+    from pywr.core import Scenario
+    from pywr.model import Model
+    from pywr.parameters import ArrayIndexedScenarioParameter
+
+    w = WORKLOADS[name]
+    years = years or w["years"]
+    idx = daily_index(w["start"], years=years)
+    doc = w["document"](str(idx[0].date()), str(idx[-1].date()))
+    kwargs = {"solver": solver} if solver else {}
+    model = Model.load(doc, **kwargs)
+    scenario = Scenario(model, "inflow", size=n_scenarios)
+    if inflow is None:
+        inflow = synthetic_inflow(idx.month.values, n_scenarios, SEEDS[w["seed"]], first_scenario)
+    param = ArrayIndexedScenarioParameter(model, scenario, inflow, name="inflow")
+    for c in w["catchments"]:
+        model.nodes[c].flow = param
+    return model
+
+
+def load_workload(name, n_scenarios, years=None, first_scenario=0, inflow=None):
+    """(structure, program, info) for S scenarios from the committed single-scenario fixture."""
+    from pywr_b200.program import Program
+    from pywr_b200.structure import LPStructure
+
+    w = WORKLOADS[name]
+    s = LPStructure.load(os.path.join(FIXTURES, f"{name}.pstructure.npz"))
+    base = Program.load(os.path.join(FIXTURES, f"{name}.program.npz"))
+    years = years or w["years"]
+    idx = daily_index(w["start"], years=years)
+    T = len(idx)
+    if T > base.n_steps:
+        raise ValueError(f"fixture holds {base.n_steps} timesteps, {T} requested")
+    S = int(n_scenarios)
+    if inflow is None:
+        inflow = synthetic_inflow(idx.month.values, S, SEEDS[w["seed"]], first_scenario)
+    assert inflow.shape == (T, S)
+    q = copy.copy(base)
+    q.n_steps = T
+    q.ts_days = base.ts_days[:T].copy()
+    rows, cols, axis, offs, chunks, pos = [], [], [], [], [], 0
+    for t in range(base.n_tables):
+        r0, c0 = int(base.table_rows[t]), int(base.table_cols[t])
+        data = base.table_data[base.table_offset[t]: base.table_offset[t] + r0 * c0].reshape(r0, c0)
+        if base.table_axis[t] >= 0:      # the inflow table (scenario axis "inflow")
+            data = inflow
+        elif r0 > 1:
+            data = data[:T]
+        rows.append(data.shape[0]); cols.append(data.shape[1]); axis.append(int(base.table_axis[t]))
+        offs.append(pos); chunks.append(np.ascontiguousarray(data).reshape(-1)); pos += data.size
+    q.table_rows, q.table_cols = np.array(rows, np.int32), np.array(cols, np.int32)
+    q.table_axis, q.table_offset = np.array(axis, np.int32), np.array(offs, np.int64)
+    q.table_data = np.concatenate(chunks)
+    q.scen_index = np.tile(np.arange(S, dtype=np.int32), (max(base.n_axes, 1), 1)).reshape(-1)
+    nst = max(s.n_storage, 1)
+    q.initial_volume = np.repeat(base.initial_volume.reshape(nst, -1)[:, :1], S, axis=1).reshape(-1)
+    q.initial_pc = np.repeat(base.initial_pc.reshape(nst, -1)[:, :1], S, axis=1).reshape(-1)
+    info = dict(name=name, n_scenarios=S, timesteps=T, rows=s.n_rows, cols=s.n_cols, nnz=s.nnz, nodes=s.n_nodes,
+                n_storage=s.n_storage, n_recorders=q.n_recorders,
+                n_array_recorders=int(np.sum((q.rec_kind >= 1) & (q.rec_kind <= 6))))
+    return s, q, info
+
+
+def algorithmic_bytes_per_scenario_step(info):
+    """B = 8(n + 2m) + 2(m + n) + 16 n_st + 8 N + 8 n_rec."""
+    m, n = info["rows"], info["cols"]
+    return 8 * (n + 2 * m) + 2 * (m + n) + 16 * info["n_storage"] + 8 * info["nodes"] + 8 * info["n_recorders"]

@@ -272,6 +272,10 @@ int b200lp_program_reset(b200lp_handle *h);
 int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n);
 /* Number of failed scenarios so far, the first failing scenario (or -1), its status and timestep. */
 int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario, int32_t *code, int32_t *timestep);
+/* Replace the contents of table `table` (same shape) from host memory — pinned memory is copied
+ * at full PCIe rate, asynchronously on b200lp_stream().  New inflow scenarios for the next run
+ * without rebuilding the program (the optimisation / ensemble outer loop). */
+int b200lp_update_table(b200lp_handle *h, int32_t table, const double *data);
 /* Copy recorder `rec` to the host: [T][S] doubles for the array kinds, [S] for the others. */
 int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out);
 /* Device pointer of recorder `rec` (for NCCL gathers by the caller) and its element count. */
@@ -279,6 +283,11 @@ void *b200lp_recorder_device_ptr(b200lp_handle *h, int32_t rec, int64_t *count);
 /* Column values x [n][S] of the last executed timestep (host mirrors of node flows) and the current
  * volumes / proportions [n_storage][S]; any pointer may be NULL. */
 int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, double *pc);
+
+/* CUDA-event stopwatch on the engine's stream: mark(0) = start, mark(1) = stop; elapsed_ms
+ * synchronises on the stop event.  (torch.cuda.Event only sees torch's own streams.) */
+int b200lp_mark(b200lp_handle *h, int32_t which);
+int b200lp_elapsed_ms(b200lp_handle *h, double *ms);
 
 /* the cudaStream_t all work of this handle is queued on (for CUDA-event timing by the caller) */
 void *b200lp_stream(b200lp_handle *h);

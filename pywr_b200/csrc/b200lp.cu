@@ -46,14 +46,33 @@ static void launch_variant(const DevStructure &st, const DevState &state, int S,
     lp_step_kernel<G, RPL, NC><<<grid, block, smem, stream>>>(st, state, S, days, slots, node_flow, col_flow, objective);
 }
 
+typedef void (*run_fn)(const DevStructure &, const DevState &, const DevProgram &, int S, int t0, int nsteps,
+                       cudaStream_t stream, int block);
+
+template <int G, int RPL, int NC>
+static void run_variant(const DevStructure &st, const DevState &state, const DevProgram &pg, int S, int t0, int nsteps,
+                        cudaStream_t stream, int block) {
+    const int groups_per_block = block / G;
+    const int grid = (S + groups_per_block - 1) / groups_per_block;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots + 2 * st.n_storage) + 15) & ~(size_t)15;
+    const size_t smem = gbytes * groups_per_block;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    lp_run_kernel<G, RPL, NC><<<grid, block, smem, stream>>>(st, state, pg, S, t0, nsteps);
+}
+
 struct Variant {
     int G, RPL, NC;
     launch_fn launch;
+    run_fn run;
     size_t (*smem_per_group)(int n_slots);
 };
 
 #define VARIANT(G, RPL, NC) \
-    { G, RPL, NC, &launch_variant<G, RPL, NC>, &GroupSmem<G, RPL, NC>::bytes }
+    { G, RPL, NC, &launch_variant<G, RPL, NC>, &run_variant<G, RPL, NC>, &GroupSmem<G, RPL, NC>::bytes }
 
 // ordered from the cheapest; the first one that fits (rows <= G*RPL, cols <= NC) is used
 static const Variant kVariants[] = {
@@ -79,6 +98,16 @@ struct b200lp_handle {
     int nnz = 0;
     int last_first_bad = -1, last_code = 0;
     b200lp_stats stats{};
+    // device-resident run
+    bool has_program = false;
+    DevProgram dp{};
+    std::vector<void *> prog_owned;
+    std::vector<double *> rec_ptr;   // device outputs
+    std::vector<int> rec_kind;
+    std::vector<double> init_vol, init_pc;
+    std::vector<int> table_rows, table_cols;
+    std::vector<long long> table_offset;
+    int prog_steps = 0;
 };
 
 template <typename T>
@@ -105,6 +134,13 @@ static cudaError_t dalloc(b200lp_handle *h, size_t count, T **out) {
     *out = p;
     return cudaMemset(p, 0, bytes);
 }
+
+__global__ void fill_kernel(double *p, size_t n, double v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static void free_program(b200lp_handle *h);
 
 extern "C" {
 
@@ -251,6 +287,7 @@ void b200lp_destroy(b200lp_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    free_program(h);
     for (void *p : h->owned) cudaFree(p);
     if (h->h_fail) cudaFreeHost(h->h_fail);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -455,6 +492,258 @@ int b200lp_memcpy_d2h(b200lp_handle *h, void *dst, const void *d_src, size_t byt
     if (!h) return fail(B200LP_E_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200LP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident run
+// ---------------------------------------------------------------------------------------------
+}  // extern "C" (reopened below)
+
+static void free_program(b200lp_handle *h) {
+    for (void *p : h->prog_owned) cudaFree(p);
+    h->prog_owned.clear(); h->rec_ptr.clear(); h->rec_kind.clear();
+    h->has_program = false;
+}
+
+template <typename T>
+static cudaError_t pupload(b200lp_handle *h, const T *src, size_t count, const T **out) {
+    T *p = nullptr;
+    const size_t bytes = sizeof(T) * (count ? count : 1);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    h->prog_owned.push_back(p);
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return e;
+    if (count && src) e = cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice);
+    *out = p;
+    return e;
+}
+
+static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC; }
+
+extern "C" {
+
+int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
+    if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
+    if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    free_program(h);
+    const size_t S = (size_t)h->S;
+    const int nst = h->ds.n_storage;
+    DevProgram &dp = h->dp;
+    dp = DevProgram{};
+    dp.n_steps = p->n_steps; dp.n_ops = p->n_ops; dp.n_tables = p->n_tables; dp.n_axes = p->n_axes;
+    dp.n_recorders = p->n_recorders;
+    // validate ops
+    const int nargs = p->n_ops ? p->op_arg_ptr[p->n_ops] : 0;
+    std::vector<int> table_ops;
+    for (int k = 0; k < p->n_ops; k++) {
+        if (p->op_dst[k] < 0 || p->op_dst[k] >= h->ds.n_slots) return fail(B200LP_E_INVALID, "op destination slot out of range");
+        if (p->op_kind[k] == B200LP_OP_TABLE) {
+            const int tb = p->op_args[p->op_arg_ptr[k]];
+            if (tb < 0 || tb >= p->n_tables) return fail(B200LP_E_INVALID, "table index out of range");
+            const int ax = p->table_axis[tb];
+            if (ax >= p->n_axes) return fail(B200LP_E_INVALID, "table axis out of range");
+            if (ax == B200LP_COL_SCENARIO && p->table_cols[tb] < h->S) return fail(B200LP_E_INVALID, "per-scenario table has too few columns");
+            table_ops.push_back(k);
+        }
+    }
+    dp.n_table_ops = (int)table_ops.size();
+    long long ndata = 0;
+    for (int t = 0; t < p->n_tables; t++) {
+        const long long end = (long long)p->table_offset[t] + (long long)p->table_rows[t] * p->table_cols[t];
+        if (end > ndata) ndata = end;
+    }
+    // scenario indices must address existing columns
+    for (int t = 0; t < p->n_tables; t++) {
+        const int ax = p->table_axis[t];
+        if (ax >= 0)
+            for (size_t s = 0; s < S; s++)
+                if (p->scen_index[(size_t)ax * S + s] < 0 || p->scen_index[(size_t)ax * S + s] >= p->table_cols[t])
+                    return fail(B200LP_E_INVALID, "scenario index exceeds table columns");
+    }
+#define PUP(field, src, count)                                                          \
+    do {                                                                                \
+        cudaError_t _e = pupload(h, src, (size_t)(count), &dp.field);                   \
+        if (_e != cudaSuccess) {                                                        \
+            free_program(h);                                                            \
+            return fail(B200LP_E_CUDA, std::string("program upload " #field ": ") + cudaGetErrorString(_e)); \
+        }                                                                               \
+    } while (0)
+    PUP(ts_days, p->ts_days, p->n_steps);
+    PUP(op_kind, p->op_kind, p->n_ops);
+    PUP(op_dst, p->op_dst, p->n_ops);
+    PUP(op_arg_ptr, p->op_arg_ptr, p->n_ops + 1);
+    PUP(op_args, p->op_args, nargs);
+    PUP(table_op, table_ops.data(), table_ops.size());
+    PUP(table_rows, p->table_rows, p->n_tables);
+    PUP(table_cols, p->table_cols, p->n_tables);
+    PUP(table_axis, p->table_axis, p->n_tables);
+    PUP(table_offset, reinterpret_cast<const long long *>(p->table_offset), p->n_tables);
+    PUP(table_data, p->table_data, ndata);
+    PUP(scen_index, p->scen_index, (size_t)p->n_axes * S);
+    PUP(stflow_indptr, p->stflow_indptr, nst + 1);
+    PUP(stflow_col, p->stflow_col, nst ? p->stflow_indptr[nst] : 0);
+    PUP(stflow_w, p->stflow_w, nst ? p->stflow_indptr[nst] : 0);
+    PUP(rec_kind, p->rec_kind, p->n_recorders);
+    PUP(rec_src, p->rec_src, p->n_recorders);
+    PUP(rec_ref, p->rec_ref, p->n_recorders);
+    PUP(rec_indptr, p->rec_indptr, p->n_recorders + 1);
+    PUP(rec_col, p->rec_col, p->n_recorders ? p->rec_indptr[p->n_recorders] : 0);
+    PUP(rec_factor, p->rec_factor, p->n_recorders);
+    PUP(rec_w, p->rec_w, p->n_recorders ? p->rec_indptr[p->n_recorders] : 0);
+#undef PUP
+    h->stats.h2d_bytes += (double)ndata * 8.0;
+    auto palloc = [&](size_t bytes, void **out) -> cudaError_t {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
+        if (e == cudaSuccess) h->prog_owned.push_back(*out);
+        return e;
+    };
+    h->rec_kind.assign(p->rec_kind, p->rec_kind + p->n_recorders);
+    h->rec_ptr.resize(p->n_recorders);
+    for (int r = 0; r < p->n_recorders; r++) {
+        const size_t count = rec_is_array(p->rec_kind[r]) ? (size_t)p->n_steps * S : S;
+        void *q = nullptr;
+        if (palloc(sizeof(double) * count, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "recorder output allocation failed"); }
+        h->rec_ptr[r] = (double *)q;
+    }
+    void *q = nullptr;
+    if (palloc(sizeof(double *) * (p->n_recorders + 1), &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+    if (p->n_recorders) cudaMemcpy(q, h->rec_ptr.data(), sizeof(double *) * p->n_recorders, cudaMemcpyHostToDevice);
+    dp.rec_out = (double *const *)q;
+    if (palloc(sizeof(double) * S * (nst ? nst : 1), &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+    dp.pc = (double *)q;
+    if (palloc(sizeof(double) * S * h->ds.n, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+    dp.last_x = (double *)q;
+    if (palloc(sizeof(int) * S, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+    dp.fail_step = (int *)q;
+    h->table_rows.assign(p->table_rows, p->table_rows + p->n_tables);
+    h->table_cols.assign(p->table_cols, p->table_cols + p->n_tables);
+    h->table_offset.assign(p->table_offset, p->table_offset + p->n_tables);
+    h->init_vol.assign(p->initial_volume, p->initial_volume + (size_t)nst * S);
+    h->init_pc.assign(p->initial_pc, p->initial_pc + (size_t)nst * S);
+    h->prog_steps = p->n_steps;
+    h->has_program = true;
+    return b200lp_program_reset(h);
+}
+
+int b200lp_program_reset(b200lp_handle *h) {
+    if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+    int rc = b200lp_reset(h, h->ds.n_storage ? h->init_vol.data() : nullptr);
+    if (rc != 0) return rc;
+    const size_t S = (size_t)h->S;
+    if (h->ds.n_storage)
+        CUDA_TRY(cudaMemcpyAsync(h->dp.pc, h->init_pc.data(), sizeof(double) * S * h->ds.n_storage, cudaMemcpyHostToDevice, h->stream));
+    for (size_t r = 0; r < h->rec_ptr.size(); r++) {
+        const size_t count = rec_is_array(h->rec_kind[r]) ? (size_t)h->prog_steps * S : S;
+        if (h->rec_kind[r] == B200LP_REC_MIN_VOLUME) {
+            fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->rec_ptr[r], count, INFINITY);
+            h->stats.kernel_launches++;
+        } else {
+            CUDA_TRY(cudaMemsetAsync(h->rec_ptr[r], 0, sizeof(double) * count, h->stream));
+        }
+    }
+    CUDA_TRY(cudaMemsetAsync(h->dp.last_x, 0, sizeof(double) * S * h->ds.n, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->dp.fail_step, 0xff, sizeof(int) * S, h->stream));
+    h->h_fail[0] = 0; h->h_fail[1] = INT_MAX;
+    CUDA_TRY(cudaMemcpyAsync(h->state.fail, h->h_fail, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200LP_OK;
+}
+
+int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n) {
+    if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+    if (t0 < 0 || n <= 0 || t0 + n > h->prog_steps) return fail(B200LP_E_INVALID, "timestep range outside the program");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Variant &V = kVariants[h->variant];
+    V.run(h->ds, h->state, h->dp, h->S, t0, n, h->stream, h->block);
+    h->stats.kernel_launches++;
+    h->stats.steps += n;
+    h->stats.scenario_steps += (int64_t)n * h->S;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200LP_E_CUDA, std::string("run kernel launch: ") + cudaGetErrorString(e));
+    return B200LP_OK;
+}
+
+int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario, int32_t *code, int32_t *timestep) {
+    if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->h_fail, h->state.fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int sc = -1, cd = 0, ts = -1;
+    if (h->h_fail[0] > 0) {
+        sc = h->h_fail[1] >> 4; cd = h->h_fail[1] & 15;
+        CUDA_TRY(cudaMemcpy(&ts, h->dp.fail_step + sc, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (n_failed) *n_failed = h->h_fail[0];
+    if (scenario) *scenario = sc;
+    if (code) *code = cd;
+    if (timestep) *timestep = ts;
+    return B200LP_OK;
+}
+
+int b200lp_update_table(b200lp_handle *h, int32_t table, const double *data) {
+    if (!h || !h->has_program || !data) return fail(B200LP_E_INVALID, "no program loaded / null data");
+    if (table < 0 || table >= h->dp.n_tables) return fail(B200LP_E_INVALID, "table index out of range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t count = (size_t)h->table_rows[table] * h->table_cols[table];
+    CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(h->dp.table_data) + h->table_offset[table], data, sizeof(double) * count,
+                             cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (double)count * 8.0;
+    return B200LP_OK;
+}
+
+int b200lp_mark(b200lp_handle *h, int32_t which) {
+    if (!h) return fail(B200LP_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(which ? h->ev1 : h->ev0, h->stream));
+    return B200LP_OK;
+}
+
+int b200lp_elapsed_ms(b200lp_handle *h, double *ms) {
+    if (!h || !ms) return fail(B200LP_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = (double)f;
+    return B200LP_OK;
+}
+
+int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out) {
+    if (!h || !h->has_program || !out) return fail(B200LP_E_INVALID, "no program loaded / null output");
+    if (rec < 0 || rec >= (int)h->rec_ptr.size()) return fail(B200LP_E_INVALID, "recorder index out of range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t count = rec_is_array(h->rec_kind[rec]) ? (size_t)h->prog_steps * h->S : (size_t)h->S;
+    CUDA_TRY(cudaMemcpyAsync(out, h->rec_ptr[rec], sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += (double)count * 8.0;
+    return B200LP_OK;
+}
+
+void *b200lp_recorder_device_ptr(b200lp_handle *h, int32_t rec, int64_t *count) {
+    if (!h || !h->has_program || rec < 0 || rec >= (int)h->rec_ptr.size()) return nullptr;
+    if (count) *count = rec_is_array(h->rec_kind[rec]) ? (int64_t)h->prog_steps * h->S : (int64_t)h->S;
+    return h->rec_ptr[rec];
+}
+
+int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, double *pc) {
+    if (!h) return fail(B200LP_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S;
+    if (col_flow) {
+        if (!h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+        CUDA_TRY(cudaMemcpyAsync(col_flow, h->dp.last_x, sizeof(double) * S * h->ds.n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (volume && h->ds.n_storage)
+        CUDA_TRY(cudaMemcpyAsync(volume, h->state.vol, sizeof(double) * S * h->ds.n_storage, cudaMemcpyDeviceToHost, h->stream));
+    if (pc && h->ds.n_storage) {
+        if (!h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+        CUDA_TRY(cudaMemcpyAsync(pc, h->dp.pc, sizeof(double) * S * h->ds.n_storage, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200LP_OK;
 }

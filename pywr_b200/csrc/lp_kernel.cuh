@@ -523,34 +523,16 @@ struct Dict {
 };
 
 // ------------------------------------------------------------------------------------------------
-// One timestep for all scenarios.
+// Per-timestep pipeline pieces shared by the step kernel and the run kernel.
 // ------------------------------------------------------------------------------------------------
+
+// (a5/a6) row bounds and (a3) objective from this scenario's slot vector sm.p.  `vol` points at the
+// storage volumes of this scenario (element k at vol[k*vol_stride]).  Returns 0, B200LP_ST_NAN or
+// B200LP_ST_INFEASIBLE (inconsistent bounds), uniform over the group.
 template <int G, int RPL, int NC>
-__global__ void __launch_bounds__(128)
-lp_step_kernel(const DevStructure st, const DevState state, const int S, const double days,
-               const double *__restrict__ slots, double *__restrict__ node_flow, double *__restrict__ col_flow,
-               double *__restrict__ objective) {
-    constexpr int ROWS = G * RPL;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int groups_per_block = blockDim.x / G;
-    const int gib = threadIdx.x / G;
-    const int sidx = blockIdx.x * groups_per_block + gib;
-    if (sidx >= S) return;  // whole group exits together
-
-    Dict<G, RPL, NC> D;
-    D.gl = threadIdx.x % G;
-    const int lane = threadIdx.x & 31;
-    D.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
-    D.n = st.n; D.m = st.m; D.pivots = 0;
-    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots) + 15) & ~(size_t)15;
-    D.sm.carve(smem_raw + gbytes * gib, st.n_slots);
+__device__ __forceinline__ int assemble_lp(const DevStructure &st, Dict<G, RPL, NC> &D, const double days,
+                                           const double *vol, const size_t vol_stride) {
     const int gl = D.gl, n = st.n, m = st.m;
-
-    // ---- this scenario's input planes ----------------------------------------------------------
-    for (int k = gl; k < st.n_slots; k += G) D.sm.p[k] = slots[(size_t)k * S + sidx];
-    D.sync();
-
-    // ---- (a5/a6) row bounds ------------------------------------------------------------------------
     int nan_seen = 0, bad_bounds = 0;
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
@@ -567,17 +549,17 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
                 const double maxv = ref_value(st, __ldg(&st.st_maxv_ref[k]), D.sm.p);
                 const double minv = ref_value(st, __ldg(&st.st_minv_ref[k]), D.sm.p);
                 const int vref = __ldg(&st.st_vol_ref[k]);
-                const double vol = (vref == B200LP_REF_STATE) ? state.vol[(size_t)k * S + sidx] : ref_value(st, vref, D.sm.p);
+                const double v = (vref == B200LP_REF_STATE) ? vol[(size_t)k * vol_stride] : ref_value(st, vref, D.sm.p);
                 int active = 1;
                 if (__ldg(&st.st_kind[k]) == B200LP_ST_KIND_VIRTUAL)
                     active = ref_value(st, __ldg(&st.st_active_ref[k]), D.sm.p) != 0.0;
-                if (isnan(maxv) || isnan(minv) || isnan(vol)) nan_seen = 1;
+                if (isnan(maxv) || isnan(minv) || isnan(v)) nan_seen = 1;
                 if (maxv == minv) { l = 0.0; u = 0.0; }
                 else if (!active) { l = -INFINITY; u = INFINITY; }
                 else {
-                    const double avail = fmax(vol - minv, 0.0);
+                    const double avail = fmax(v - minv, 0.0);
                     l = -avail / days;
-                    u = fmax(maxv - vol, 0.0) / days;
+                    u = fmax(maxv - v, 0.0) / days;
                     type_bounds(l, u);
                 }
             }
@@ -585,7 +567,6 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
         }
         D.sm.lo_r[i] = l; D.sm.hi_r[i] = u;
     }
-    // ---- (a3) objective ----------------------------------------------------------------------------
     for (int j = gl; j < NC; j += G) {
         double acc = 0.0;
         if (j < n) {
@@ -601,69 +582,137 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
     nan_seen = group_any<G>(nan_seen, D.mask);
     bad_bounds = group_any<G>(bad_bounds, D.mask);
     D.sync();
+    return nan_seen ? B200LP_ST_NAN : (bad_bounds ? B200LP_ST_INFEASIBLE : 0);
+}
 
-    int *meta = state.meta + (size_t)sidx * 4;
+// (a7) warm-started solve with the oracle's retry ladder (role of retry_solve, cython_glpk.pyx:1034-1042)
+template <int G, int RPL, int NC>
+__device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC> &D, int &valid, int &npiv,
+                                        int &refactors) {
+    bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
+    const bool fresh0 = need_refactor;
     int status = B200LP_ST_OPTIMAL;
-    int refactors = 0;
-    if (nan_seen) status = B200LP_ST_NAN;
-    else if (bad_bounds) status = B200LP_ST_INFEASIBLE;
-    else {
-        // ---- load the scenario's basis + cached dictionary ---------------------------------------
-        const int valid = meta[0];
-        int npiv = meta[1];
-        double *Tg = state.T + (size_t)sidx * NC * ROWS;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (attempt == 1 && fresh0) continue;
+        if (attempt == 2) D.slack_basis();
+        if (attempt > 0) need_refactor = true;
+        if (need_refactor) {
+            if (D.refactor(st) != 0) {
+                D.slack_basis();
+                D.refactor(st);
+            }
+            D.reduced_costs();
+            npiv = 0; refactors++; valid = 1;
+        } else if (st.cost_dynamic) {
+            D.reduced_costs();
+        }
+        const int p0 = D.pivots;
+        status = D.solve();
+        npiv += D.pivots - p0;
+        if (status == B200LP_ST_OPTIMAL) break;
+    }
+    if (status != B200LP_ST_OPTIMAL) valid = 0;
+    return status;
+}
+
+// (a8) primal values of the columns into sm.x
+template <int G, int RPL, int NC>
+__device__ __forceinline__ void extract_columns(Dict<G, RPL, NC> &D) {
+    D.basic_values();
+    for (int j = D.gl; j < NC; j += G) {
+        const int v = D.sm.nb[j];
+        if (v >= 0 && v < D.n) D.sm.x[v] = D.sm.xn[j];
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int v = D.head[r];
+        if (v >= 0 && v < D.n) D.sm.x[v] = D.beta[r];
+    }
+    D.sync();
+}
+
+template <int G, int RPL, int NC>
+__device__ __forceinline__ void load_state(const DevState &state, Dict<G, RPL, NC> &D, const int sidx, const int valid) {
+    constexpr int ROWS = G * RPL;
+    const double *Tg = state.T + (size_t)sidx * NC * ROWS;
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int i = r * G + D.gl;
+        D.head[r] = state.head[(size_t)sidx * ROWS + i];
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < NC; j++) D.T[r][j] = Tg[(size_t)j * ROWS + i];
+        }
+    }
+    for (int j = D.gl; j < NC; j += G) {
+        D.sm.nb[j] = state.nb[(size_t)sidx * NC + j];
+        D.sm.nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
+        D.sm.d[j] = state.d[(size_t)sidx * NC + j];
+    }
+    D.sync();
+}
+
+template <int G, int RPL, int NC>
+__device__ __forceinline__ void store_state(const DevState &state, Dict<G, RPL, NC> &D, const int sidx, const bool store_T) {
+    constexpr int ROWS = G * RPL;
+    double *Tg = state.T + (size_t)sidx * NC * ROWS;
+    if (store_T) {
 #pragma unroll
         for (int r = 0; r < RPL; r++) {
-            const int i = r * G + gl;
-            D.head[r] = state.head[(size_t)sidx * ROWS + i];
-            if (valid) {
+            const int i = r * G + D.gl;
+            state.head[(size_t)sidx * ROWS + i] = D.head[r];
 #pragma unroll
-                for (int j = 0; j < NC; j++) D.T[r][j] = Tg[(size_t)j * ROWS + i];
-            }
+            for (int j = 0; j < NC; j++) Tg[(size_t)j * ROWS + i] = D.T[r][j];
         }
-        for (int j = gl; j < NC; j += G) {
-            D.sm.nb[j] = state.nb[(size_t)sidx * NC + j];
-            D.sm.nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
-            D.sm.d[j] = state.d[(size_t)sidx * NC + j];
-        }
-        D.sync();
-        bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
-        const bool fresh0 = need_refactor;
-        for (int attempt = 0; attempt < 3; attempt++) {
-            if (attempt == 1 && fresh0) continue;
-            if (attempt == 2) D.slack_basis();
-            if (attempt > 0) need_refactor = true;
-            if (need_refactor) {
-                if (D.refactor(st) != 0) {
-                    D.slack_basis();
-                    D.refactor(st);
-                }
-                D.reduced_costs();
-                npiv = 0; refactors++;
-            } else if (st.cost_dynamic) {
-                D.reduced_costs();
-            }
-            const int p0 = D.pivots;
-            status = D.solve();
-            npiv += D.pivots - p0;
-            if (status == B200LP_ST_OPTIMAL) break;
-        }
-        // ---- store the basis + dictionary ---------------------------------------------------------
-        if (D.pivots > 0 || refactors > 0) {
-#pragma unroll
-            for (int r = 0; r < RPL; r++) {
-                const int i = r * G + gl;
-                state.head[(size_t)sidx * ROWS + i] = D.head[r];
-#pragma unroll
-                for (int j = 0; j < NC; j++) Tg[(size_t)j * ROWS + i] = D.T[r][j];
-            }
-        }
-        for (int j = gl; j < NC; j += G) {
-            state.nb[(size_t)sidx * NC + j] = D.sm.nb[j];
-            state.nbstat[(size_t)sidx * NC + j] = D.sm.nbstat[j];
-            state.d[(size_t)sidx * NC + j] = D.sm.d[j];
-        }
-        if (gl == 0) { meta[0] = (status == B200LP_ST_OPTIMAL) ? 1 : 0; meta[1] = npiv; }
+    }
+    for (int j = D.gl; j < NC; j += G) {
+        state.nb[(size_t)sidx * NC + j] = D.sm.nb[j];
+        state.nbstat[(size_t)sidx * NC + j] = D.sm.nbstat[j];
+        state.d[(size_t)sidx * NC + j] = D.sm.d[j];
+    }
+}
+
+template <int G, int RPL, int NC>
+__device__ __forceinline__ void init_group(Dict<G, RPL, NC> &D, const DevStructure &st, unsigned char *smem_raw,
+                                           const int gib, const int extra_doubles) {
+    D.gl = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
+    D.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    D.n = st.n; D.m = st.m; D.pivots = 0;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots + extra_doubles) + 15) & ~(size_t)15;
+    D.sm.carve(smem_raw + gbytes * gib, st.n_slots + extra_doubles);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One timestep for all scenarios (the per-timestep Solver.solve path).
+// ------------------------------------------------------------------------------------------------
+template <int G, int RPL, int NC>
+__global__ void __launch_bounds__(128)
+lp_step_kernel(const DevStructure st, const DevState state, const int S, const double days,
+               const double *__restrict__ slots, double *__restrict__ node_flow, double *__restrict__ col_flow,
+               double *__restrict__ objective) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int groups_per_block = blockDim.x / G;
+    const int gib = threadIdx.x / G;
+    const int sidx = blockIdx.x * groups_per_block + gib;
+    if (sidx >= S) return;  // whole group exits together
+
+    Dict<G, RPL, NC> D;
+    init_group(D, st, smem_raw, gib, 0);
+    const int gl = D.gl, n = st.n;
+
+    for (int k = gl; k < st.n_slots; k += G) D.sm.p[k] = slots[(size_t)k * S + sidx];
+    D.sync();
+
+    int status = assemble_lp(st, D, days, state.vol + sidx, (size_t)S);
+    int *meta = state.meta + (size_t)sidx * 4;
+    int refactors = 0;
+    if (status == 0) {
+        int valid = meta[0], npiv = meta[1];
+        load_state(state, D, sidx, valid);
+        status = solve_lp(st, D, valid, npiv, refactors);
+        store_state(state, D, sidx, D.pivots > 0 || refactors > 0);
+        if (gl == 0) { meta[0] = valid; meta[1] = npiv; }
     }
     if (gl == 0) {
         meta[2] = status;
@@ -676,18 +725,7 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
     }
     if (status != B200LP_ST_OPTIMAL) return;
 
-    // ---- (a8) column values, objective, node flows ---------------------------------------------
-    D.basic_values();
-    for (int j = gl; j < NC; j += G) {
-        const int v = D.sm.nb[j];
-        if (v >= 0 && v < n) D.sm.x[v] = D.sm.xn[j];
-    }
-#pragma unroll
-    for (int r = 0; r < RPL; r++) {
-        const int v = D.head[r];
-        if (v >= 0 && v < n) D.sm.x[v] = D.beta[r];
-    }
-    D.sync();
+    extract_columns(D);
     if (col_flow)
         for (int j = gl; j < n; j += G) col_flow[(size_t)j * S + sidx] = D.sm.x[j];
     if (objective && gl == 0) {
@@ -701,6 +739,218 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
             for (int k = __ldg(&st.flow_indptr[v]); k < __ldg(&st.flow_indptr[v + 1]); k++)
                 acc = fma(__ldg(&st.flow_w[k]), D.sm.x[__ldg(&st.flow_col[k])], acc);
             node_flow[(size_t)v * S + sidx] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident run: timesteps [t0, t0+nsteps) for all scenarios in ONE launch.  The dictionary
+// stays in registers across timesteps; parameters, storage mass balance and recorders are evaluated
+// here, so nothing returns to the host until read-out.
+// ------------------------------------------------------------------------------------------------
+struct DevProgram {
+    int n_steps, n_ops, n_tables, n_axes, n_recorders, n_table_ops;
+    const double *ts_days;
+    const int *op_kind, *op_dst, *op_arg_ptr, *op_args;
+    const int *table_op;  // [n_table_ops] indices of the B200LP_OP_TABLE ops (prefetched one step ahead)
+    const int *table_rows, *table_cols, *table_axis;
+    const long long *table_offset;
+    const double *table_data;
+    const int *scen_index;
+    const int *stflow_indptr, *stflow_col;
+    const double *stflow_w;
+    const int *rec_kind, *rec_src, *rec_ref, *rec_indptr, *rec_col;
+    const double *rec_factor, *rec_w;
+    double *const *rec_out;  // [n_recorders] device outputs
+    double *pc;              // [n_storage][S]
+    double *last_x;          // [n][S]
+    int *fail_step;          // [S]
+};
+
+__device__ __forceinline__ double clamp_pc(double pc) {  // Storage.get_current_pc, pywr/_core.pyx:1027-1039
+    if (pc > 1.0 || isnan(pc)) return 1.0;
+    if (pc < 0.0) return 0.0;
+    return pc;
+}
+
+__device__ __forceinline__ double table_lookup(const DevProgram &pg, const int *a, const int t, const int sidx, const int S) {
+    const int tb = a[0];
+    long long row = 0;
+    const int rows = __ldg(&pg.table_rows[tb]);
+    if (rows > 1) {
+        row = (long long)t + a[1];
+        if (row < 0) row = 0;
+        if (row > rows - 1) row = rows - 1;
+    }
+    const int ax = __ldg(&pg.table_axis[tb]);
+    const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
+    return __ldg(&pg.table_data[__ldg(&pg.table_offset[tb]) + row * __ldg(&pg.table_cols[tb]) + col]);
+}
+
+// scalar interpreter for the non-table ops (lane 0 of the group); same arithmetic as orc_eval_ops
+__device__ __forceinline__ void eval_ops(const DevStructure &st, const DevProgram &pg, double *p, const double *pc) {
+    for (int k = 0; k < pg.n_ops; k++) {
+        const int kind = __ldg(&pg.op_kind[k]);
+        if (kind == B200LP_OP_TABLE) continue;
+        const int *a = pg.op_args + __ldg(&pg.op_arg_ptr[k]);
+        double v = 0.0;
+        switch (kind) {
+        case B200LP_OP_AGG: {
+            const int func = a[0], cnt = a[1];
+            if (func == B200LP_AGG_PRODUCT) { v = 1.0; for (int i = 0; i < cnt; i++) v *= ref_value(st, a[2 + i], p); }
+            else if (func == B200LP_AGG_SUM) { v = 0.0; for (int i = 0; i < cnt; i++) v += ref_value(st, a[2 + i], p); }
+            else if (func == B200LP_AGG_MAX) { v = -INFINITY; for (int i = 0; i < cnt; i++) { const double w = ref_value(st, a[2 + i], p); if (w > v) v = w; } }
+            else if (func == B200LP_AGG_MIN) { v = INFINITY; for (int i = 0; i < cnt; i++) { const double w = ref_value(st, a[2 + i], p); if (w < v) v = w; } }
+            else { v = 0.0; for (int i = 0; i < cnt; i++) v += ref_value(st, a[2 + i], p); v /= cnt; }
+        } break;
+        case B200LP_OP_CONTROL_CURVE: {
+            const int cnt = a[1];
+            const double c = clamp_pc(pc[a[0]]);
+            int idx = cnt;
+            for (int i = 0; i < cnt; i++) if (c >= ref_value(st, a[2 + i], p)) { idx = i; break; }
+            v = ref_value(st, a[2 + cnt + idx], p);
+        } break;
+        case B200LP_OP_CC_INDEX: {
+            const int cnt = a[1];
+            const double c = clamp_pc(pc[a[0]]);
+            int idx = cnt;
+            for (int i = 0; i < cnt; i++) if (c >= ref_value(st, a[2 + i], p)) { idx = i; break; }
+            v = (double)idx;
+        } break;
+        case B200LP_OP_INDEXED: {
+            int idx = (int)ref_value(st, a[0], p);
+            if (idx < 0) idx = 0;
+            if (idx > a[1] - 1) idx = a[1] - 1;
+            v = ref_value(st, a[2 + idx], p);
+        } break;
+        case B200LP_OP_NEG: v = -ref_value(st, a[0], p); break;
+        case B200LP_OP_MAX0: { const double x = ref_value(st, a[0], p), th = ref_value(st, a[1], p); v = x > th ? x : th; } break;
+        case B200LP_OP_MIN0: { const double x = ref_value(st, a[0], p), th = ref_value(st, a[1], p); v = x < th ? x : th; } break;
+        case B200LP_OP_DIV: v = ref_value(st, a[0], p) / ref_value(st, a[1], p); break;
+        default: v = NAN;
+        }
+        p[__ldg(&pg.op_dst[k])] = v;
+    }
+}
+
+template <int G, int RPL, int NC>
+__global__ void __launch_bounds__(128)
+lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, const int S, const int t0,
+              const int nsteps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int groups_per_block = blockDim.x / G;
+    const int gib = threadIdx.x / G;
+    const int sidx = blockIdx.x * groups_per_block + gib;
+    if (sidx >= S) return;
+
+    Dict<G, RPL, NC> D;
+    init_group(D, st, smem_raw, gib, 2 * st.n_storage);
+    const int gl = D.gl, n = st.n, nst = st.n_storage;
+    double *vol = D.sm.p + st.n_slots;  // [n_storage]
+    double *pc = vol + nst;             // [n_storage]
+
+    int *meta = state.meta + (size_t)sidx * 4;
+    if (meta[2] != B200LP_ST_OPTIMAL) return;  // failed at an earlier timestep
+    int valid = meta[0], npiv = meta[1], refactors = 0;
+    load_state(state, D, sidx, valid);
+    for (int k = gl; k < nst; k += G) { vol[k] = state.vol[(size_t)k * S + sidx]; pc[k] = pg.pc[(size_t)k * S + sidx]; }
+    D.sync();
+
+    // table values are fetched one timestep ahead (lane j owns table op j, j + G, ...)
+    constexpr int MAXPF = 4;
+    double pf[MAXPF];
+#pragma unroll
+    for (int u = 0; u < MAXPF; u++) {
+        const int j = gl + u * G;
+        pf[u] = 0.0;
+        if (j < pg.n_table_ops) {
+            const int k = __ldg(&pg.table_op[j]);
+            pf[u] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t0, sidx, S);
+        }
+    }
+
+    int status = B200LP_ST_OPTIMAL;
+    int t = t0;
+    for (; t < t0 + nsteps; t++) {
+        const double days = __ldg(&pg.ts_days[t]);
+        // ---- before(): parameters -------------------------------------------------------------
+#pragma unroll
+        for (int u = 0; u < MAXPF; u++) {
+            const int j = gl + u * G;
+            if (j < pg.n_table_ops) {
+                const int k = __ldg(&pg.table_op[j]);
+                D.sm.p[__ldg(&pg.op_dst[k])] = pf[u];
+                if (t + 1 < t0 + nsteps) pf[u] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t + 1, sidx, S);
+            }
+        }
+        for (int j = gl + MAXPF * G; j < pg.n_table_ops; j += G) {  // more table ops than prefetch slots
+            const int k = __ldg(&pg.table_op[j]);
+            D.sm.p[__ldg(&pg.op_dst[k])] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t, sidx, S);
+        }
+        D.sync();
+        if (gl == 0) eval_ops(st, pg, D.sm.p, pc);
+        D.sync();
+        // ---- solve() ------------------------------------------------------------------------------
+        status = assemble_lp(st, D, days, vol, (size_t)1);
+        if (status == 0) status = solve_lp(st, D, valid, npiv, refactors);
+        if (status != B200LP_ST_OPTIMAL) break;
+        extract_columns(D);
+        // ---- after(): storage mass balance (Storage.after, pywr/_core.pyx:1335-1361) ---------------
+        for (int k = gl; k < nst; k += G) {
+            if (__ldg(&st.st_kind[k]) == B200LP_ST_KIND_VIRTUAL &&
+                !(ref_value(st, __ldg(&st.st_active_ref[k]), D.sm.p) != 0.0))
+                continue;
+            double flow = 0.0;
+            for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
+                flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+            double v = vol[k] + flow * days;
+            const double mxv = ref_value(st, __ldg(&st.st_maxv_ref[k]), D.sm.p);
+            const double mnv = ref_value(st, __ldg(&st.st_minv_ref[k]), D.sm.p);
+            if (fabs(v - mxv) < 1e-6) v = mxv;
+            if (fabs(v - mnv) < 1e-6) v = mnv;
+            vol[k] = v;
+            pc[k] = (mxv == 0.0) ? NAN : v / mxv;
+        }
+        D.sync();
+        // ---- recorders -------------------------------------------------------------------------------
+        for (int r = gl; r < pg.n_recorders; r += G) {
+            const int kind = __ldg(&pg.rec_kind[r]);
+            double *out = pg.rec_out[r];
+            double value = 0.0;
+            for (int e = __ldg(&pg.rec_indptr[r]); e < __ldg(&pg.rec_indptr[r + 1]); e++)
+                value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
+            const double f = __ldg(&pg.rec_factor[r]);
+            const size_t ts_at = (size_t)t * S + sidx;
+            switch (kind) {
+            case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
+            case B200LP_REC_NODE_DEFICIT: out[ts_at] = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p) - value; break;
+            case B200LP_REC_NODE_SUPPLIED: { const double mf = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p); out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
+            case B200LP_REC_NODE_CURTAIL: { const double mf = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p); out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+            case B200LP_REC_STORAGE_VOLUME: out[ts_at] = vol[__ldg(&pg.rec_src[r])]; break;
+            case B200LP_REC_STORAGE_PC: out[ts_at] = pc[__ldg(&pg.rec_src[r])]; break;
+            case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p) - value) * days; break;
+            case B200LP_REC_TOTAL_FLOW: out[sidx] += value * f * days; break;
+            case B200LP_REC_MEAN_FLOW: out[sidx] += value * f; break;
+            case B200LP_REC_DEFICIT_FREQ: if (fabs(value - ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p)) > 1e-6) out[sidx] += 1.0; break;
+            case B200LP_REC_MIN_VOLUME: { const double v = vol[__ldg(&pg.rec_src[r])]; if (v < out[sidx]) out[sidx] = v; } break;
+            default: break;
+            }
+        }
+        D.sync();
+    }
+    // ---- persist ------------------------------------------------------------------------------------
+    store_state(state, D, sidx, true);
+    for (int k = gl; k < nst; k += G) { state.vol[(size_t)k * S + sidx] = vol[k]; pg.pc[(size_t)k * S + sidx] = pc[k]; }
+    if (status == B200LP_ST_OPTIMAL)
+        for (int j = gl; j < n; j += G) pg.last_x[(size_t)j * S + sidx] = D.sm.x[j];
+    if (gl == 0) {
+        meta[0] = valid; meta[1] = npiv; meta[2] = status;
+        if (D.pivots) atomicAdd(&state.counters[0], (unsigned long long)D.pivots);
+        if (refactors) atomicAdd(&state.counters[1], (unsigned long long)refactors);
+        if (status != B200LP_ST_OPTIMAL) {
+            pg.fail_step[sidx] = t;
+            atomicAdd(&state.fail[0], 1);
+            atomicMin(&state.fail[1], (sidx << 4) | status);
         }
     }
 }

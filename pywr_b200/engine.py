@@ -55,6 +55,16 @@ SYMBOLS = [
     ("b200lp_device_free", None, [ctypes.c_void_p]),
     ("b200lp_memcpy_h2d", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     ("b200lp_memcpy_d2h", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    ("b200lp_load_program", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("b200lp_program_reset", ctypes.c_int, [ctypes.c_void_p]),
+    ("b200lp_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]),
+    ("b200lp_program_status", ctypes.c_int, [ctypes.c_void_p, _ip, _ip, _ip, _ip]),
+    ("b200lp_update_table", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp]),
+    ("b200lp_mark", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    ("b200lp_elapsed_ms", ctypes.c_int, [ctypes.c_void_p, _dp]),
+    ("b200lp_fetch_recorder", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp]),
+    ("b200lp_recorder_device_ptr", ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
+    ("b200lp_fetch_state", ctypes.c_int, [ctypes.c_void_p, _dp, _dp, _dp]),
 ]
 
 
@@ -185,6 +195,60 @@ class CudaEngine:
 
     def sync(self):
         _check(self.L, self.L.b200lp_sync(self.h), "b200lp_sync")
+
+    # -- device-resident run -----------------------------------------------------------------
+    def load_program(self, prog):
+        self._cp = prog.to_c()
+        _check(self.L, self.L.b200lp_load_program(self.h, ctypes.addressof(self._cp)), "b200lp_load_program")
+
+    def program_reset(self):
+        _check(self.L, self.L.b200lp_program_reset(self.h), "b200lp_program_reset")
+
+    def run(self, t0, n):
+        """Queues timesteps [t0, t0+n) on the engine's stream (asynchronous)."""
+        _check(self.L, self.L.b200lp_run(self.h, int(t0), int(n)), "b200lp_run")
+        return 0
+
+    def program_status(self):
+        v = [ctypes.c_int32() for _ in range(4)]
+        _check(self.L, self.L.b200lp_program_status(self.h, *[ctypes.byref(x) for x in v]), "b200lp_program_status")
+        return tuple(x.value for x in v)
+
+    def fetch_recorder(self, r, shape, out=None):
+        if out is None:
+            out = np.zeros(shape, dtype=np.float64)
+        _check(self.L, self.L.b200lp_fetch_recorder(self.h, int(r), _ptr(out)), "b200lp_fetch_recorder")
+        return out
+
+    def update_table(self, table, data):
+        """Asynchronous upload of one table (use a pinned array from alloc_pinned for full PCIe rate)."""
+        _check(self.L, self.L.b200lp_update_table(self.h, int(table), _ptr(data)), "b200lp_update_table")
+
+    def alloc_pinned(self, shape):
+        pa = PinnedArray(self.L, tuple(int(v) for v in shape))
+        self._pinned.append(pa)
+        return pa.array
+
+    def mark(self, which):
+        _check(self.L, self.L.b200lp_mark(self.h, int(which)), "b200lp_mark")
+
+    def elapsed_ms(self):
+        ms = ctypes.c_double()
+        _check(self.L, self.L.b200lp_elapsed_ms(self.h, ctypes.byref(ms)), "b200lp_elapsed_ms")
+        return ms.value
+
+    def recorder_device_ptr(self, r):
+        n = ctypes.c_int64()
+        p = self.L.b200lp_recorder_device_ptr(self.h, int(r), ctypes.byref(n))
+        return p, n.value
+
+    def fetch_state(self):
+        s = self.structure
+        x = np.zeros((s.n_cols, self.S))
+        vol = np.zeros((max(s.n_storage, 1), self.S))
+        pc = np.zeros((max(s.n_storage, 1), self.S))
+        _check(self.L, self.L.b200lp_fetch_state(self.h, _ptr(x), _ptr(vol), _ptr(pc)), "b200lp_fetch_state")
+        return x, vol, pc
 
     @property
     def stream(self):

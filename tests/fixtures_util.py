@@ -78,3 +78,99 @@ def synth_batch(structure, trace, S, T, seed):
             u[rng.random(S) < 0.05] = 1.0
             out[t, k] = lo + u * (hi - lo)
     return out, trace["days"][:T]
+
+
+# ---- device-run ("program") fixtures -------------------------------------------------------------
+def program_cases():
+    return sorted(os.path.basename(p)[: -len(".program.npz")] for p in glob.glob(os.path.join(GOLDEN, "*.program.npz")))
+
+
+def load_program_case(name):
+    from pywr_b200.program import Program
+
+    s = LPStructure.load(os.path.join(GOLDEN, name + ".pstructure.npz"))
+    prog = Program.load(os.path.join(GOLDEN, name + ".program.npz"))
+    z = np.load(os.path.join(GOLDEN, name + ".expected.npz"))
+    expected = [z[f"rec{i}"] for i in range(prog.n_recorders)]
+    return s, prog, expected, [str(n) for n in z["names"]]
+
+
+def n_scenarios_of(s, prog):
+    return int(prog.initial_volume.size // max(s.n_storage, 1)) if s.n_storage else int(prog.scen_index.size // max(prog.n_axes, 1))
+
+
+def run_program(engine, prog, chunks=None):
+    """Executes a loaded program on an engine (oracle or CUDA) and returns all recorder outputs."""
+    engine.load_program(prog)
+    T = prog.n_steps
+    if chunks is None:
+        engine.run(0, T)
+    else:
+        t = 0
+        for c in chunks:
+            c = min(c, T - t)
+            if c <= 0:
+                break
+            engine.run(t, c)
+            t += c
+        if t < T:
+            engine.run(t, T - t)
+    engine.sync()
+    status = engine.program_status()
+    outs = [engine.fetch_recorder(r, prog.rec_shape(r, engine.S)) for r in range(prog.n_recorders)]
+    return outs, status, engine.fetch_state()
+
+
+def widen_program(s, prog, S, seed, sigma=0.35):
+    """Scenario batch of size S from a single-scenario program: every time-varying single-column table
+    becomes a per-scenario table (column = scenario id) whose columns are the original series scaled
+    by a smooth log-normal AR(1) factor, so that scenarios diverge (different bases, different
+    control-curve crossings).  Initial state is tiled."""
+    import copy
+
+    from pywr_b200.program import COL_SCENARIO
+
+    S0 = n_scenarios_of(s, prog)
+    rng = np.random.default_rng(seed)
+    q = copy.copy(prog)
+    T = prog.n_steps
+    rows, cols, axis, offs = list(prog.table_rows), list(prog.table_cols), list(prog.table_axis), []
+    chunks, pos = [], 0
+    pick = rng.integers(0, S0, size=S)
+    for t in range(prog.n_tables):
+        data = prog.table_data[prog.table_offset[t]: prog.table_offset[t] + rows[t] * cols[t]].reshape(rows[t], cols[t])
+        if rows[t] == T and (cols[t] == 1 or axis[t] >= 0) and np.ptp(data) > 0:
+            if axis[t] >= 0:
+                base = data[:, prog.scen_index.reshape(prog.n_axes, S0)[axis[t]][pick]]
+            else:
+                base = np.repeat(data, S, axis=1)
+            z = np.zeros((T, S))
+            e = rng.normal(0.0, sigma * np.sqrt(1 - 0.98**2), size=(T, S))
+            z[0] = rng.normal(0.0, sigma, size=S)
+            for i in range(1, T):
+                z[i] = 0.98 * z[i - 1] + e[i]
+            data = base * np.exp(z)
+            cols[t], axis[t] = S, COL_SCENARIO
+        offs.append(pos)
+        chunks.append(np.ascontiguousarray(data).reshape(-1))
+        pos += data.size
+    q.table_rows, q.table_cols = np.array(rows, np.int32), np.array(cols, np.int32)
+    q.table_axis, q.table_offset = np.array(axis, np.int32), np.array(offs, np.int64)
+    q.table_data = np.concatenate(chunks) if chunks else np.zeros(0)
+    q.scen_index = prog.scen_index.reshape(max(prog.n_axes, 1), S0)[:, pick].reshape(-1).astype(np.int32)
+    nst = max(s.n_storage, 1)
+    q.initial_volume = prog.initial_volume.reshape(nst, S0)[:, pick].reshape(-1)
+    q.initial_pc = prog.initial_pc.reshape(nst, S0)[:, pick].reshape(-1)
+    return q
+
+
+def rel_diff(a, b):
+    """max |a-b| / max(1,|b|), treating identical infinities / NaNs as equal"""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    with np.errstate(invalid="ignore"):
+        d = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d = np.where(same, 0.0, d)
+    return float(np.max(np.where(np.isnan(d), np.inf, d)))

@@ -1,0 +1,93 @@
+"""Generates the device-run golden fixtures (BUILD container only; needs baseline/_ref and
+/root/reference).  For each model: (1) a HOST run of the reference framework (Model.run) with the CPU
+oracle as solver and the reference's own recorder classes -> expected recorder arrays; (2) the
+compiled program + LP structure (pywr_b200.program.compile_program) so that the GPU box can replay
+the run through the C-ABI without Pywr.
+
+usage: python tests/golden/make_golden_programs.py
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from pywr.model import Model  # noqa: E402
+from pywr.recorders import (DeficitFrequencyNodeRecorder, MeanFlowNodeRecorder, MinimumVolumeStorageRecorder,  # noqa: E402
+                            NumpyArrayNodeCurtailmentRatioRecorder, NumpyArrayNodeDeficitRecorder,
+                            NumpyArrayNodeRecorder, NumpyArrayNodeSuppliedRatioRecorder, NumpyArrayStorageRecorder,
+                            TotalDeficitNodeRecorder, TotalFlowNodeRecorder)
+
+import oracle.pywr_oracle_solver  # noqa: E402,F401
+from pywr_b200.program import compile_program  # noqa: E402
+
+REF = os.environ.get("PYWR_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+CASES = [
+    ("thames", "examples/thames/thames.json", "route", "2102-12-31"),
+    ("thames", "examples/thames/thames.json", "edge", "2100-12-31"),
+    ("two_reservoir", "examples/two_reservoir/two_reservoir.json", "route", "2110-12-31"),
+    ("demand_saving2", "tests/models/demand_saving2.json", "route", None),
+    ("reservoir2", "tests/models/reservoir2.json", "route", None),
+    ("three_storage", "tests/models/three_storage.json", "route", None),
+    ("timeseries3", "tests/models/timeseries3.json", "route", None),
+]
+
+
+def add_recorders(m):
+    recs = []
+    for n in list(m.nodes):
+        cn = type(n).__name__
+        if cn in ("Storage", "Reservoir"):
+            recs += [NumpyArrayStorageRecorder(m, n, name=f"vol_{n.name}"),
+                     NumpyArrayStorageRecorder(m, n, proportional=True, name=f"pc_{n.name}"),
+                     MinimumVolumeStorageRecorder(m, n, name=f"minv_{n.name}")]
+        elif cn in ("Output", "Link", "Input", "Catchment", "River", "RiverGauge"):
+            recs.append(NumpyArrayNodeRecorder(m, n, name=f"flow_{n.name}"))
+            if cn == "Output":
+                recs += [NumpyArrayNodeDeficitRecorder(m, n, name=f"def_{n.name}"),
+                         TotalDeficitNodeRecorder(m, n, name=f"tdef_{n.name}"),
+                         NumpyArrayNodeSuppliedRatioRecorder(m, n, name=f"sr_{n.name}"),
+                         NumpyArrayNodeCurtailmentRatioRecorder(m, n, name=f"cr_{n.name}"),
+                         TotalFlowNodeRecorder(m, n, name=f"tf_{n.name}", factor=2.0),
+                         MeanFlowNodeRecorder(m, n, name=f"mf_{n.name}"),
+                         DeficitFrequencyNodeRecorder(m, n, name=f"df_{n.name}")]
+    return recs
+
+
+def load(path, formulation, end):
+    m = Model.load(os.path.join(REF, path), solver="oracle" if formulation == "route" else "oracle-edge")
+    if end:
+        m.timestepper.end = end
+    for r in list(m.recorders):  # keep only the recorders added below
+        pass
+    return m
+
+
+def run_case(name, path, formulation, end):
+    m = load(path, formulation, end)
+    recs = add_recorders(m)
+    m.run()
+    expected = {r.name: (np.array(r.data) if hasattr(r, "data") else np.array(r.values())) for r in recs}
+    m2 = load(path, formulation, end)
+    recs2 = add_recorders(m2)
+    m2.setup()
+    s, prog = compile_program(m2, formulation, recorders=recs2)
+    base = os.path.join(OUT, f"{name}.{formulation}")
+    s.save(base + ".pstructure.npz")
+    prog.save(base + ".program.npz")
+    np.savez_compressed(base + ".expected.npz", names=np.array([r.name for r in prog.recorders]),
+                        **{f"rec{i}": expected[r.name] for i, r in enumerate(prog.recorders)})
+    print(f"{name}.{formulation}: T={prog.n_steps} S={len(m2.scenarios.combinations)} ops={prog.n_ops} "
+          f"tables={prog.n_tables} recorders={prog.n_recorders} slots={s.n_slots}")
+
+
+if __name__ == "__main__":
+    for case in CASES:
+        run_case(*case)

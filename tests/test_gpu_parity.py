@@ -4,7 +4,7 @@ sides run the same pivoting rules with the same fma placement we assert 1e-9 and
 import numpy as np
 import pytest
 
-from fixtures_util import golden_cases, load_case, replay, synth_batch
+from fixtures_util import rel_diff, golden_cases, load_case, replay, synth_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +17,7 @@ def _engines(s, S):
 
 
 def _rel(a, b):
-    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+    return rel_diff(a, b)
 
 
 @pytest.mark.parametrize("name", golden_cases())

@@ -1,0 +1,73 @@
+"""GPU tests (-m gpu) of the device-resident run: CUDA run kernel through the C-ABI against the
+oracle's program mode and against the recorder arrays of the reference framework's host run."""
+import numpy as np
+import pytest
+
+from fixtures_util import rel_diff, load_program_case, n_scenarios_of, program_cases, run_program, widen_program
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return rel_diff(a, b)
+
+
+def _engines(s, S):
+    from oracle.oracle_engine import OracleEngine
+    from pywr_b200.engine import CudaEngine
+
+    return OracleEngine(s, S, threads=8), CudaEngine(s, S, device=0)
+
+
+@pytest.mark.parametrize("name", program_cases())
+def test_program_matches_reference_host_run_and_oracle(name):
+    s, prog, expected, names = load_program_case(name)
+    cpu, gpu = _engines(s, n_scenarios_of(s, prog))
+    o_cpu, st_cpu, x_cpu = run_program(cpu, prog)
+    o_gpu, st_gpu, x_gpu = run_program(gpu, prog)
+    assert st_gpu == st_cpu and st_gpu[0] == 0
+    T = prog.n_steps
+    for out_g, out_c, exp, nm in zip(o_gpu, o_cpu, expected, names):
+        assert _rel(out_g, out_c) <= 1e-9, (nm, _rel(out_g, out_c))
+        if nm.startswith(("mf_", "df_")):
+            out_g = out_g / T
+        # north_star: flows and volumes within 1e-6 relative of the reference run
+        assert _rel(out_g, exp) <= 1e-9, (nm, _rel(out_g, exp))
+    for a, b in zip(x_gpu, x_cpu):
+        assert _rel(a, b) <= 1e-9
+    gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name,S,seed", [("two_reservoir.route", 1024, 1), ("thames.route", 2048, 2),
+                                          ("thames.edge", 333, 3), ("demand_saving2.route", 64, 4)])
+def test_widened_program_parity(name, S, seed):
+    """Scenario batches at benchmark-like sizes: every recorder, the final volumes, the last column
+    flows and the pivot count agree with the oracle."""
+    s, prog, _, names = load_program_case(name)
+    q = widen_program(s, prog, S, seed)
+    cpu, gpu = _engines(s, S)
+    o_cpu, st_cpu, x_cpu = run_program(cpu, q)
+    o_gpu, st_gpu, x_gpu = run_program(gpu, q, chunks=[50, 200])
+    assert st_gpu == st_cpu
+    worst = 0.0
+    for out_g, out_c, nm in zip(o_gpu, o_cpu, names):
+        worst = max(worst, _rel(out_g, out_c))
+        assert _rel(out_g, out_c) <= 1e-9, (nm, _rel(out_g, out_c))
+    for a, b in zip(x_gpu, x_cpu):
+        assert _rel(a, b) <= 1e-9
+    if st_cpu[0] == 0:
+        assert gpu.counters()["pivots"] == cpu.counters()["pivots"]
+    print(f"{name} S={S}: worst relative difference over {len(names)} recorders = {worst:.2e}")
+    gpu.close(); cpu.close()
+
+
+def test_program_reset_reproduces():
+    s, prog, _, _ = load_program_case("thames.route")
+    cpu, gpu = _engines(s, n_scenarios_of(s, prog))
+    a, _, _ = run_program(gpu, prog)
+    gpu.program_reset()
+    gpu.run(0, prog.n_steps); gpu.sync()
+    b = [gpu.fetch_recorder(r, prog.rec_shape(r, gpu.S)) for r in range(prog.n_recorders)]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    gpu.close(); cpu.close()
