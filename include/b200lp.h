@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 4
+#define B200LP_ABI_VERSION 5
 
 /* error codes */
 #define B200LP_OK 0
@@ -246,8 +246,10 @@ typedef struct b200lp_program {
     const int64_t *table_offset; /* [n_tables] first element in table_data (row-major [rows][cols])    */
     const double *table_data;
     const int32_t *scen_index;  /* [n_axes][S] ScenarioIndex.indices                                   */
-    /* storage mass balance: net inflow of storage k = sum stflow_w * x[stflow_col] (commit through
-     * StorageInput/StorageOutput, _core.pyx:942-979; VirtualStorage: -sum factor*flow, :1483-1493)   */
+    /* storage mass balance.  Storage: the net inflow committed through StorageInput/StorageOutput
+     * (_core.pyx:942-979) is exactly the activity of the storage's own LP row (+1 on columns ending in
+     * its outputs, -1 on columns starting at its inputs, cython_glpk.pyx:578-601), which the engine
+     * reads directly.  VirtualStorage (-sum factor*flow, :1483-1493): sum stflow_w * x[stflow_col].  */
     const int32_t *stflow_indptr; /* [n_storage+1] */
     const int32_t *stflow_col;
     const double *stflow_w;
@@ -258,6 +260,10 @@ typedef struct b200lp_program {
     const int32_t *rec_src;     /* [n_recorders] storage index for the storage kinds, else unused      */
     const int32_t *rec_ref;     /* [n_recorders] ref of the node's max_flow (deficit kinds)            */
     const double *rec_factor;   /* [n_recorders]                                                       */
+    const int32_t *rec_row;     /* [n_recorders] >= 0: the node's flow is the activity of this LP row
+                                   (non-storage row of a plain Input/Link/Output node: coefficient 1 on
+                                   every column through the node, cython_glpk.pyx:515-550); -1: use the
+                                   linear form below                                                   */
     const int32_t *rec_indptr;  /* [n_recorders+1] linear form of the node kinds                       */
     const int32_t *rec_col;
     const double *rec_w;

@@ -443,7 +443,7 @@ static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, slot_vie
     const int32_t m = h->m, n = h->n, NV = h->NV, N = s->n_nodes, S = h->S;
     orc_scen *c = &h->sc[sidx];
     double *lo = work, *hi = lo + NV, *cost = hi + NV, *xn = cost + n, *beta = xn + n, *dw = beta + m,
-           *x = dw + n, *Ad = x + n;
+           *x = dw + n, *ract = x + n, *Ad = ract + m;
     int nan_seen = 0, bad_bounds = 0;
 
     /* (a5/a6) bounds: columns are x >= 0 (cython_glpk.pyx:490-491) */
@@ -544,7 +544,12 @@ static int orc_solve_scenario(orc_handle *h, int32_t sidx, double days, slot_vie
     dict_basic_values(&D);
     for (int32_t i = 0; i < m; i++) {
         const int32_t v = c->head[i];
-        if (v < n) x[v] = beta[i];
+        if (v < n) x[v] = beta[i]; else ract[v - n] = beta[i];
+    }
+    /* activities of the non-basic rows: they sit on a bound */
+    for (int32_t j = 0; j < n; j++) {
+        const int32_t v = c->nb[j];
+        if (v >= n) ract[v - n] = xn[j];
     }
     /* x stays in `work` (ORC_WORK_X) for the program mode */
     if (col_flow) for (int32_t j = 0; j < n; j++) col_flow[(size_t)j * S + sidx] = x[j];
@@ -582,7 +587,7 @@ static void *orc_worker(void *arg) {
     orc_job *J = (orc_job *)arg;
     orc_handle *h = J->h;
     const int32_t m = h->m, n = h->n;
-    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + m + (size_t)m * n + 8));
+    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + 2 * m + (size_t)m * n + 8));
     J->nbad = 0; J->first_bad = -1; J->bad_code = 0; J->pivots = 0; J->refactors = 0;
     for (int32_t k = J->s0; k < J->s1; k++) {
         slot_view sv = {J->slots, (size_t)h->S, (size_t)k};
@@ -711,7 +716,7 @@ static void orc_free_program(orc_program *pr) {
     free((void *)p->table_offset); free((void *)p->table_data); free((void *)p->scen_index);
     free((void *)p->stflow_indptr); free((void *)p->stflow_col); free((void *)p->stflow_w);
     free((void *)p->initial_volume); free((void *)p->initial_pc);
-    free((void *)p->rec_kind); free((void *)p->rec_src); free((void *)p->rec_ref); free((void *)p->rec_factor);
+    free((void *)p->rec_kind); free((void *)p->rec_row); free((void *)p->rec_src); free((void *)p->rec_ref); free((void *)p->rec_factor);
     free((void *)p->rec_indptr); free((void *)p->rec_col); free((void *)p->rec_w);
     if (pr->rec_out) for (int r = 0; r < p->n_recorders; r++) free(pr->rec_out[r]);
     free(pr->rec_out); free(pr->last_x);
@@ -767,6 +772,7 @@ int orc_load_program(void *hv, const b200lp_program *src) {
     p->initial_pc = dup_mem(src->initial_pc, sizeof(double) * (size_t)nst * S);
     p->rec_kind = dup_mem(src->rec_kind, sizeof(int32_t) * src->n_recorders);
     p->rec_src = dup_mem(src->rec_src, sizeof(int32_t) * src->n_recorders);
+    p->rec_row = dup_mem(src->rec_row, sizeof(int32_t) * src->n_recorders);
     p->rec_ref = dup_mem(src->rec_ref, sizeof(int32_t) * src->n_recorders);
     p->rec_factor = dup_mem(src->rec_factor, sizeof(double) * src->n_recorders);
     p->rec_indptr = dup_mem(src->rec_indptr, sizeof(int32_t) * (src->n_recorders + 1));
@@ -878,8 +884,12 @@ static void *orc_run_worker(void *arg) {
     const b200lp_program *pg = &pr->p;
     const b200lp_structure *s = &h->s;
     const int32_t m = h->m, n = h->n, S = h->S, nst = s->n_storage;
-    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + m + (size_t)m * n + 8));
+    double *work = (double *)malloc(sizeof(double) * (2 * (size_t)(m + n) + 4 * n + 2 * m + (size_t)m * n + 8));
     double *x = work + 2 * (size_t)(m + n) + 3 * (size_t)n + m; /* ORC_WORK_X */
+    double *ract = x + n;                                       /* row activities */
+    int32_t *st_row = (int32_t *)calloc(nst + 1, sizeof(int32_t));
+    for (int32_t i = 0; i < m; i++)
+        if (s->row_kind[i] == B200LP_ROW_STORAGE) st_row[s->row_lb_ref[i]] = i;
     double *p = (double *)calloc(s->n_slots + 1, sizeof(double));
     J->pivots = 0; J->refactors = 0;
     for (int32_t k = J->s0; k < J->s1; k++) {
@@ -901,8 +911,10 @@ static void *orc_run_worker(void *arg) {
             for (int32_t q = 0; q < nst; q++) {
                 if (s->st_kind[q] == B200LP_ST_KIND_VIRTUAL && !(pref(h, s->st_active_ref[q], p) != 0.0)) continue;
                 double flow = 0.0;
-                for (int32_t e = pg->stflow_indptr[q]; e < pg->stflow_indptr[q + 1]; e++)
-                    flow = fma(pg->stflow_w[e], x[pg->stflow_col[e]], flow);
+                if (s->st_kind[q] == B200LP_ST_KIND_STORAGE) flow = ract[st_row[q]];
+                else
+                    for (int32_t e = pg->stflow_indptr[q]; e < pg->stflow_indptr[q + 1]; e++)
+                        flow = fma(pg->stflow_w[e], x[pg->stflow_col[e]], flow);
                 double vol = c->vol[q] + flow * days;
                 const double mxv = pref(h, s->st_maxv_ref[q], p), mnv = pref(h, s->st_minv_ref[q], p);
                 if (fabs(vol - mxv) < 1e-6) vol = mxv;
@@ -915,8 +927,10 @@ static void *orc_run_worker(void *arg) {
                 const int32_t kind = pg->rec_kind[r];
                 double *out = pr->rec_out[r];
                 double value = 0.0;
-                for (int32_t e = pg->rec_indptr[r]; e < pg->rec_indptr[r + 1]; e++)
-                    value = fma(pg->rec_w[e], x[pg->rec_col[e]], value);
+                if (pg->rec_row[r] >= 0) value = ract[pg->rec_row[r]];
+                else
+                    for (int32_t e = pg->rec_indptr[r]; e < pg->rec_indptr[r + 1]; e++)
+                        value = fma(pg->rec_w[e], x[pg->rec_col[e]], value);
                 const double f = pg->rec_factor[r];
                 switch (kind) {
                 case B200LP_REC_NODE_FLOW: out[(size_t)t * S + k] = value * f; break;
@@ -937,7 +951,7 @@ static void *orc_run_worker(void *arg) {
                 for (int32_t j = 0; j < n; j++) pr->last_x[(size_t)j * S + k] = x[j];
         }
     }
-    free(work); free(p);
+    free(work); free(p); free(st_row);
     return NULL;
 }
 

@@ -36,7 +36,7 @@ static void launch_variant(const DevStructure &st, const DevState &state, int S,
                            double *node_flow, double *col_flow, double *objective, cudaStream_t stream, int block) {
     const int groups_per_block = block / G;
     const int grid = (S + groups_per_block - 1) / groups_per_block;
-    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots) + 15) & ~(size_t)15;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
     const size_t smem = gbytes * groups_per_block;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
@@ -54,8 +54,8 @@ static void run_variant(const DevStructure &st, const DevState &state, const Dev
                         cudaStream_t stream, int block) {
     const int groups_per_block = block / G;
     const int grid = (S + groups_per_block - 1) / groups_per_block;
-    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots + 2 * st.n_storage) + 15) & ~(size_t)15;
-    const size_t smem = gbytes * groups_per_block;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
+    const size_t smem = gbytes * groups_per_block + sizeof(int) * (size_t)(pg.n_code + 4);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
         cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -193,14 +193,44 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
     for (int k = 0; k < s->cost_indptr[n]; k++)
         if (s->cost_ref[k] >= 0) ds.cost_dynamic = 1;
 
-    // validate refs
-    auto ref_ok = [&](int ref) { return ref >= 0 ? ref < s->n_slots : (-ref - 1) < s->n_consts; };
+    ds.vol_base = s->n_slots + s->n_consts;
+    ds.pc_base = ds.vol_base + s->n_storage;
+    ds.n_val = ds.pc_base + s->n_storage;
+    const int n_slots = s->n_slots, n_consts = s->n_consts;
+    // validate refs and resolve them to indices into the per-scenario value vector V
+    auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
+    auto vidx = [&](int ref) { return ref >= 0 ? ref : n_slots + (-ref - 1); };
+    std::vector<int> row_class(rows_cap, ROWC_PAD), row_a(rows_cap, 0), row_b(rows_cap, 0);
+    std::vector<int> st_row(s->n_storage ? s->n_storage : 1, 0);
     for (int i = 0; i < m; i++) {
         if (s->row_kind[i] == B200LP_ROW_FLOW) {
             if (!ref_ok(s->row_lb_ref[i]) || !ref_ok(s->row_ub_ref[i])) { delete h; return fail(B200LP_E_INVALID, "row ref out of range"); }
-        } else if (s->row_lb_ref[i] < 0 || s->row_lb_ref[i] >= s->n_storage) { delete h; return fail(B200LP_E_INVALID, "storage index out of range"); }
+            row_class[i] = (s->row_lb_ref[i] < 0 && s->row_ub_ref[i] < 0) ? ROWC_STATIC : ROWC_FLOW;
+            row_a[i] = vidx(s->row_lb_ref[i]); row_b[i] = vidx(s->row_ub_ref[i]);
+        } else {
+            if (s->row_lb_ref[i] < 0 || s->row_lb_ref[i] >= s->n_storage) { delete h; return fail(B200LP_E_INVALID, "storage index out of range"); }
+            row_class[i] = ROWC_STORAGE; row_a[i] = s->row_lb_ref[i];
+            st_row[s->row_lb_ref[i]] = i;
+        }
         for (int k = s->a_indptr[i]; k < s->a_indptr[i + 1]; k++)
             if (s->a_col[k] < 0 || s->a_col[k] >= n) { delete h; return fail(B200LP_E_INVALID, "column index out of range"); }
+    }
+    std::vector<int> st_vol(s->n_storage), st_minv(s->n_storage), st_maxv(s->n_storage), st_act(s->n_storage);
+    for (int k = 0; k < s->n_storage; k++) {
+        if (s->st_vol_ref[k] != B200LP_REF_STATE && !ref_ok(s->st_vol_ref[k])) { delete h; return fail(B200LP_E_INVALID, "storage volume ref out of range"); }
+        if (!ref_ok(s->st_minv_ref[k]) || !ref_ok(s->st_maxv_ref[k]) || !ref_ok(s->st_active_ref[k])) { delete h; return fail(B200LP_E_INVALID, "storage ref out of range"); }
+        st_vol[k] = s->st_vol_ref[k] == B200LP_REF_STATE ? ds.vol_base + k : vidx(s->st_vol_ref[k]);
+        st_minv[k] = vidx(s->st_minv_ref[k]); st_maxv[k] = vidx(s->st_maxv_ref[k]); st_act[k] = vidx(s->st_active_ref[k]);
+    }
+    const int ncost = s->cost_indptr[n];
+    std::vector<int> cost_idx(ncost), dyn_idx(s->n_dyn_a);
+    for (int k = 0; k < ncost; k++) {
+        if (!ref_ok(s->cost_ref[k])) { delete h; return fail(B200LP_E_INVALID, "cost ref out of range"); }
+        cost_idx[k] = vidx(s->cost_ref[k]);
+    }
+    for (int k = 0; k < s->n_dyn_a; k++) {
+        if (!ref_ok(s->dyn_a_ref[k])) { delete h; return fail(B200LP_E_INVALID, "coefficient ref out of range"); }
+        dyn_idx[k] = vidx(s->dyn_a_ref[k]);
     }
 
     std::vector<double> A((size_t)nc * rows_cap, 0.0);
@@ -224,20 +254,21 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
         }                                                                         \
     } while (0)
     UP(A_dense, A.data(), A.size());
-    UP(row_kind, s->row_kind, m);
-    UP(row_lb_ref, s->row_lb_ref, m);
-    UP(row_ub_ref, s->row_ub_ref, m);
+    UP(row_class, row_class.data(), rows_cap);
+    UP(row_a, row_a.data(), rows_cap);
+    UP(row_b, row_b.data(), rows_cap);
     UP(st_kind, s->st_kind, s->n_storage);
-    UP(st_vol_ref, s->st_vol_ref, s->n_storage);
-    UP(st_minv_ref, s->st_minv_ref, s->n_storage);
-    UP(st_maxv_ref, s->st_maxv_ref, s->n_storage);
-    UP(st_active_ref, s->st_active_ref, s->n_storage);
+    UP(st_vol_idx, st_vol.data(), s->n_storage);
+    UP(st_minv_idx, st_minv.data(), s->n_storage);
+    UP(st_maxv_idx, st_maxv.data(), s->n_storage);
+    UP(st_active_idx, st_act.data(), s->n_storage);
+    UP(st_row, st_row.data(), s->n_storage);
     UP(cost_indptr, s->cost_indptr, n + 1);
-    UP(cost_ref, s->cost_ref, s->cost_indptr[n]);
-    UP(cost_w, s->cost_w, s->cost_indptr[n]);
+    UP(cost_idx, cost_idx.data(), ncost);
+    UP(cost_w, s->cost_w, ncost);
     UP(dyn_a_row, dyn_row.data(), s->n_dyn_a);
     UP(dyn_a_col, dyn_col.data(), s->n_dyn_a);
-    UP(dyn_a_ref, s->dyn_a_ref, s->n_dyn_a);
+    UP(dyn_a_idx, dyn_idx.data(), s->n_dyn_a);
     UP(dyn_a_scale, s->dyn_a_scale, s->n_dyn_a);
     UP(dyn_a_static, dyn_static.data(), s->n_dyn_a);
     UP(flow_indptr, s->flow_indptr, N + 1);
@@ -535,23 +566,83 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     const int nst = h->ds.n_storage;
     DevProgram &dp = h->dp;
     dp = DevProgram{};
-    dp.n_steps = p->n_steps; dp.n_ops = p->n_ops; dp.n_tables = p->n_tables; dp.n_axes = p->n_axes;
+    dp.n_steps = p->n_steps; dp.n_tables = p->n_tables; dp.n_axes = p->n_axes;
     dp.n_recorders = p->n_recorders;
-    // validate ops
+    // validate ops; table ops get one descriptor each, everything else is pre-decoded into `code`
+    // with every operand resolved to an index into V
     const int nargs = p->n_ops ? p->op_arg_ptr[p->n_ops] : 0;
-    std::vector<int> table_ops;
+    const int n_slots = h->ds.n_slots, n_consts = h->ds.n_consts, nstor = h->ds.n_storage;
+    auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
+    auto vidx = [&](int ref) { return ref >= 0 ? ref : n_slots + (-ref - 1); };
+    std::vector<int> tab_dst, tab_table, tab_offset, code;
     for (int k = 0; k < p->n_ops; k++) {
-        if (p->op_dst[k] < 0 || p->op_dst[k] >= h->ds.n_slots) return fail(B200LP_E_INVALID, "op destination slot out of range");
-        if (p->op_kind[k] == B200LP_OP_TABLE) {
-            const int tb = p->op_args[p->op_arg_ptr[k]];
+        if (p->op_dst[k] < 0 || p->op_dst[k] >= n_slots) return fail(B200LP_E_INVALID, "op destination slot out of range");
+        const int *a = p->op_args + p->op_arg_ptr[k];
+        const int na = p->op_arg_ptr[k + 1] - p->op_arg_ptr[k];
+        const int kind = p->op_kind[k];
+        if (kind == B200LP_OP_TABLE) {
+            if (na < 2) return fail(B200LP_E_INVALID, "table op needs 2 arguments");
+            const int tb = a[0];
             if (tb < 0 || tb >= p->n_tables) return fail(B200LP_E_INVALID, "table index out of range");
             const int ax = p->table_axis[tb];
             if (ax >= p->n_axes) return fail(B200LP_E_INVALID, "table axis out of range");
             if (ax == B200LP_COL_SCENARIO && p->table_cols[tb] < h->S) return fail(B200LP_E_INVALID, "per-scenario table has too few columns");
-            table_ops.push_back(k);
+            tab_dst.push_back(p->op_dst[k]); tab_table.push_back(tb); tab_offset.push_back(a[1]);
+            continue;
         }
+        std::vector<int> out;
+        auto refs = [&](int from, int count) -> bool {
+            if (from + count > na) return false;
+            for (int i = 0; i < count; i++) {
+                if (!ref_ok(a[from + i])) return false;
+                out.push_back(vidx(a[from + i]));
+            }
+            return true;
+        };
+        bool ok = true;
+        switch (kind) {
+        case B200LP_OP_AGG:
+            ok = na >= 2 && a[0] >= 0 && a[0] <= B200LP_AGG_MEAN && a[1] >= 1;
+            if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, a[1]); }
+            break;
+        case B200LP_OP_CONTROL_CURVE:
+            ok = na >= 2 && a[0] >= 0 && a[0] < nstor && a[1] >= 0;
+            if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, 2 * a[1] + 1); }
+            break;
+        case B200LP_OP_CC_INDEX:
+            ok = na >= 2 && a[0] >= 0 && a[0] < nstor && a[1] >= 0;
+            if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, a[1]); }
+            break;
+        case B200LP_OP_INDEXED:
+            ok = na >= 2 && a[1] >= 1 && ref_ok(a[0]);
+            if (ok) { out.push_back(vidx(a[0])); out.push_back(a[1]); ok = refs(2, a[1]); }
+            break;
+        case B200LP_OP_NEG: ok = refs(0, 1); break;
+        case B200LP_OP_MAX0: case B200LP_OP_MIN0: case B200LP_OP_DIV: ok = refs(0, 2); break;
+        default: ok = false;
+        }
+        if (!ok) return fail(B200LP_E_INVALID, "malformed op");
+        code.push_back(kind); code.push_back(p->op_dst[k]); code.push_back((int)out.size());
+        code.insert(code.end(), out.begin(), out.end());
     }
-    dp.n_table_ops = (int)table_ops.size();
+    (void)nargs;
+    dp.n_table_ops = (int)tab_dst.size();
+    dp.n_code = (int)code.size();
+    std::vector<int> rec_idx(p->n_recorders ? p->n_recorders : 1, 0);
+    for (int r = 0; r < p->n_recorders; r++) {
+        const int kind = p->rec_kind[r];
+        const bool needs_ref = kind == B200LP_REC_NODE_DEFICIT || kind == B200LP_REC_NODE_SUPPLIED || kind == B200LP_REC_NODE_CURTAIL ||
+                               kind == B200LP_REC_TOTAL_DEFICIT || kind == B200LP_REC_DEFICIT_FREQ;
+        if (needs_ref) {
+            if (!ref_ok(p->rec_ref[r])) return fail(B200LP_E_INVALID, "recorder max_flow ref out of range");
+            rec_idx[r] = vidx(p->rec_ref[r]);
+        }
+        const bool storage_kind = kind == B200LP_REC_STORAGE_VOLUME || kind == B200LP_REC_STORAGE_PC || kind == B200LP_REC_MIN_VOLUME;
+        if (storage_kind && (p->rec_src[r] < 0 || p->rec_src[r] >= nstor)) return fail(B200LP_E_INVALID, "recorder storage index out of range");
+        if (p->rec_row[r] >= h->ds.m) return fail(B200LP_E_INVALID, "recorder row out of range");
+        for (int e = p->rec_indptr[r]; e < p->rec_indptr[r + 1]; e++)
+            if (p->rec_col[e] < 0 || p->rec_col[e] >= h->ds.n) return fail(B200LP_E_INVALID, "recorder column out of range");
+    }
     long long ndata = 0;
     for (int t = 0; t < p->n_tables; t++) {
         const long long end = (long long)p->table_offset[t] + (long long)p->table_rows[t] * p->table_cols[t];
@@ -574,11 +665,10 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
         }                                                                               \
     } while (0)
     PUP(ts_days, p->ts_days, p->n_steps);
-    PUP(op_kind, p->op_kind, p->n_ops);
-    PUP(op_dst, p->op_dst, p->n_ops);
-    PUP(op_arg_ptr, p->op_arg_ptr, p->n_ops + 1);
-    PUP(op_args, p->op_args, nargs);
-    PUP(table_op, table_ops.data(), table_ops.size());
+    PUP(tab_dst, tab_dst.data(), tab_dst.size());
+    PUP(tab_table, tab_table.data(), tab_table.size());
+    PUP(tab_offset, tab_offset.data(), tab_offset.size());
+    PUP(code, code.data(), code.size());
     PUP(table_rows, p->table_rows, p->n_tables);
     PUP(table_cols, p->table_cols, p->n_tables);
     PUP(table_axis, p->table_axis, p->n_tables);
@@ -590,7 +680,8 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     PUP(stflow_w, p->stflow_w, nst ? p->stflow_indptr[nst] : 0);
     PUP(rec_kind, p->rec_kind, p->n_recorders);
     PUP(rec_src, p->rec_src, p->n_recorders);
-    PUP(rec_ref, p->rec_ref, p->n_recorders);
+    PUP(rec_idx, rec_idx.data(), p->n_recorders);
+    PUP(rec_row, p->rec_row, p->n_recorders);
     PUP(rec_indptr, p->rec_indptr, p->n_recorders + 1);
     PUP(rec_col, p->rec_col, p->n_recorders ? p->rec_indptr[p->n_recorders] : 0);
     PUP(rec_factor, p->rec_factor, p->n_recorders);

@@ -3,7 +3,7 @@
 // One *group* of G lanes (G = 8, 16 or 32, a sub-warp) owns one scenario.  The dictionary T
 // (m x n doubles, see below) lives in REGISTERS: lane l of the group holds rows l, l+G, ... (RPL rows
 // per lane, NC padded columns, everything unrolled at compile time).  The small per-scenario vectors
-// (row bounds, non-basic values, reduced costs, the broadcast pivot row) live in shared memory;
+// (values, bounds, non-basic values, reduced costs, the broadcast pivot row) live in shared memory;
 // pricing and ratio tests are warp-shuffle arg-min / arg-max reductions over the group.  No tensor
 // cores: there is no dense contraction anywhere on this path (BASELINE.json north_star).
 //
@@ -13,6 +13,9 @@
 //   a5 row bounds :932-959            a6 storage / virtual-storage bounds :965-1019
 //   a7 warm-started simplex from the scenario's own previous basis :197-232,1026-1063
 //   a8 route/edge flow -> node flow :1068-1093
+// and, in the device-resident run kernel, what Pywr does around the solver every timestep:
+//   parameters (pywr/parameters/_parameters.pyx, _control_curves.pyx), Storage.after
+//   (pywr/_core.pyx:1335-1361, a10) and the built-in recorders (pywr/recorders/_recorders.pyx, a11-a13).
 // The algorithm is the one restated in oracle/lp_oracle.c (dense "dictionary" bounded dual simplex
 // with cost shifting and a primal clean-up phase); every floating point operation that decides a
 // pivot is performed in the same order with explicit fma(), and the file is compiled with
@@ -20,6 +23,11 @@
 //
 // Dictionary: variables v = (x_0..x_{n-1}, r_0..r_{m-1}), r = A x.  m basic, n non-basic:
 //     v_head[i] = sum_j T[i][j] * v_nb[j]
+//
+// Everything a timestep needs per scenario is addressed through ONE shared-memory value vector
+//     V = [ slots (per-step inputs / op outputs) | constants | storage volumes | storage pc ]
+// whose indices are resolved on the host (b200lp_create), so the per-timestep path has no
+// "slot or constant?" branches and no global-memory indirections.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -37,18 +45,21 @@ constexpr double TIE_ABS = 1e-12;
 constexpr int REFACTOR_PIVOTS = 40;
 
 enum : int { VS_BASIC = 1, VS_NL = 2, VS_NU = 3, VS_NF = 4, VS_NS = 5 };
+enum : int { ROWC_STATIC = 0, ROWC_FLOW = 1, ROWC_STORAGE = 2, ROWC_PAD = 3 };
 
-// Shared LP structure, device pointers (built by b200lp_create).
+// Shared LP structure, device pointers (built by b200lp_create).  All *_idx are indices into V.
 struct DevStructure {
     int m, n, N, n_slots, n_consts, n_storage, n_dyn_a, cost_clip;
-    int cost_dynamic;  // some cost ref is a slot: reduced costs are rebuilt every step
+    int cost_dynamic;  // some cost term is a slot: reduced costs are rebuilt every step
     int rows_cap, nc;  // padded sizes of the kernel variant in use
+    int n_val, vol_base, pc_base;
     const double *A_dense;  // [nc][rows_cap] column-major, zero padded
-    const int *row_kind, *row_lb_ref, *row_ub_ref;
-    const int *st_kind, *st_vol_ref, *st_minv_ref, *st_maxv_ref, *st_active_ref;
-    const int *cost_indptr, *cost_ref;
+    const int *row_class;   // [rows_cap] ROWC_*
+    const int *row_a, *row_b;  // [rows_cap] V index of lb / ub, or (storage k, unused)
+    const int *st_kind, *st_vol_idx, *st_minv_idx, *st_maxv_idx, *st_active_idx, *st_row;
+    const int *cost_indptr, *cost_idx;
     const double *cost_w;
-    const int *dyn_a_row, *dyn_a_col, *dyn_a_ref;
+    const int *dyn_a_row, *dyn_a_col, *dyn_a_idx;
     const double *dyn_a_scale, *dyn_a_static;
     const int *flow_indptr, *flow_col;
     const double *flow_w;
@@ -67,10 +78,6 @@ struct DevState {
     unsigned long long *counters;  // [0] pivots, [1] refactors
     int *fail;    // [0] number of failed scenarios, [1] min((scenario << 4) | code)
 };
-
-__device__ __forceinline__ double ref_value(const DevStructure &st, int ref, const double *p) {
-    return ref >= 0 ? p[ref] : __ldg(&st.consts[-ref - 1]);
-}
 
 // cython_glpk.pyx:934-945 and constraint_type :66-77
 __device__ __forceinline__ void type_bounds(double &lo, double &hi) {
@@ -100,37 +107,40 @@ __device__ __forceinline__ void group_argmax(double &key, int &idx, int &aux, un
 }
 
 template <int G>
-__device__ __forceinline__ int group_any(int pred, unsigned mask) {
-    return (__ballot_sync(mask, pred) & mask) != 0u;
+__device__ __forceinline__ unsigned group_ballot(int pred, unsigned mask) {
+    return __ballot_sync(mask, pred) & mask;
 }
 
 // Per-group shared memory carve-up (doubles first, then ints).
 template <int G, int RPL, int NC>
 struct GroupSmem {
     static constexpr int ROWS = G * RPL;
-    double *lo_r, *hi_r;  // [ROWS] bounds of the row variables
-    double *xn;           // [NC] value of each non-basic position
-    double *d, *dw;       // [NC] true / working reduced costs
-    double *prow;         // [NC] broadcast pivot row (+ scratch)
-    double *x;            // [NC] column values by variable id
-    double *cost;         // [NC]
-    double *p;            // [n_slots] this scenario's input planes
-    int *nb, *nbstat;     // [NC]
-    int *vstat;           // [NC + ROWS] scratch for the refactorisation
-    __host__ __device__ static size_t bytes(int n_slots) {
-        return sizeof(double) * (2 * ROWS + 6 * NC + n_slots) + sizeof(int) * (2 * NC + NC + ROWS) + 16;
+    static constexpr int NB = 1 + NC + ROWS;  // bounds arrays are indexed by variable id + 1
+    double *V;         // [n_val] slots | consts | vol | pc
+    double *LO, *HI;   // [NB] bounds of every variable (entry 0: padding variable, free)
+    double *xn;        // [NC] value of each non-basic position
+    double *d, *dw;    // [NC] true / working reduced costs
+    double *prow;      // [NC] broadcast pivot row
+    double *x;         // [NC] column values by variable id
+    double *ract;      // [ROWS] row activities by row id
+    double *cost;      // [NC]
+    int *nb, *nbstat;  // [NC]
+    int *vstat;        // [NC + ROWS] scratch for the refactorisation
+    __host__ __device__ static size_t bytes(int n_val) {
+        return sizeof(double) * (n_val + 2 * NB + 6 * NC + ROWS) + sizeof(int) * (3 * NC + ROWS) + 16;
     }
-    __device__ void carve(unsigned char *base, int n_slots) {
+    __device__ void carve(unsigned char *base, int n_val) {
         double *dp = reinterpret_cast<double *>(base);
-        lo_r = dp; dp += ROWS;
-        hi_r = dp; dp += ROWS;
+        V = dp; dp += n_val;
+        LO = dp; dp += NB;
+        HI = dp; dp += NB;
         xn = dp; dp += NC;
         d = dp; dp += NC;
         dw = dp; dp += NC;
         prow = dp; dp += NC;
         x = dp; dp += NC;
+        ract = dp; dp += ROWS;
         cost = dp; dp += NC;
-        p = dp; dp += n_slots;
         int *ip = reinterpret_cast<int *>(dp);
         nb = ip; ip += NC;
         nbstat = ip; ip += NC;
@@ -156,12 +166,9 @@ struct Dict {
 
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 
-    __device__ __forceinline__ double var_lo(int v) const { return v < 0 ? -INFINITY : (v < n ? 0.0 : sm.lo_r[v - n]); }
-    __device__ __forceinline__ double var_hi(int v) const { return v < 0 ? INFINITY : (v < n ? INFINITY : sm.hi_r[v - n]); }
-
     __device__ __forceinline__ void load_basic_bounds() {
 #pragma unroll
-        for (int r = 0; r < RPL; r++) { lob[r] = var_lo(head[r]); hib[r] = var_hi(head[r]); }
+        for (int r = 0; r < RPL; r++) { lob[r] = sm.LO[head[r] + 1]; hib[r] = sm.HI[head[r] + 1]; }
     }
 
     __device__ __forceinline__ double col_of(int r, int q) const {
@@ -277,8 +284,7 @@ struct Dict {
     }
 
     // Rebuild T for the current basis by Gauss-Jordan pivoting from the slack basis (dict_refactor
-    // in the oracle).  Returns 0, or -1 if singular.  `st`/`p` supply the (possibly per-scenario)
-    // matrix values.
+    // in the oracle).  Returns 0, or -1 if singular.
     __device__ __forceinline__ int refactor(const DevStructure &st) {
         // record the wanted status of every variable
         for (int j = gl; j < NC; j += G) {
@@ -301,7 +307,7 @@ struct Dict {
         }
         for (int k = 0; k < st.n_dyn_a; k++) {
             const int row = __ldg(&st.dyn_a_row[k]), col = __ldg(&st.dyn_a_col[k]);
-            const double v = __ldg(&st.dyn_a_scale[k]) * ref_value(st, __ldg(&st.dyn_a_ref[k]), sm.p);
+            const double v = __ldg(&st.dyn_a_scale[k]) * sm.V[__ldg(&st.dyn_a_idx[k])];
             const double delta = v - __ldg(&st.dyn_a_static[k]);
             if ((row % G) == gl) {
 #pragma unroll
@@ -316,6 +322,7 @@ struct Dict {
         for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.d[j] = 0.0; }
         sync();
         int ok = 0;
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             if (sm.vstat[q] != VS_BASIC) continue;
             double best = TOL_PIVOT; int bi = -1, aux = 0;
@@ -349,29 +356,31 @@ struct Dict {
         int infeas = 0;
         for (int j = gl; j < NC; j += G) {
             const int v = sm.nb[j];
-            if (v < 0) { sm.xn[j] = 0.0; sm.nbstat[j] = VS_NS; continue; }
-            const double lo = var_lo(v), hi = var_hi(v), dj = sm.d[j];
+            const double lo = sm.LO[v + 1], hi = sm.HI[v + 1], dj = sm.d[j];
             int s = sm.nbstat[j];
-            if (lo == hi) s = VS_NS;
-            else if (lo > -INFINITY && hi < INFINITY) {
-                if (dj > TOL_DUAL) s = VS_NL;
-                else if (dj < -TOL_DUAL) s = VS_NU;
-                else if (s != VS_NL && s != VS_NU) s = VS_NL;
-            } else if (lo > -INFINITY) { s = VS_NL; if (dj < -TOL_DUAL) infeas = 1; }
-            else if (hi < INFINITY) { s = VS_NU; if (dj > TOL_DUAL) infeas = 1; }
-            else { s = VS_NF; if (fabs(dj) > TOL_DUAL) infeas = 1; }
+            double xv;
+            if (v < 0) { s = VS_NS; xv = 0.0; }
+            else {
+                if (lo == hi) s = VS_NS;
+                else if (lo > -INFINITY && hi < INFINITY) {
+                    if (dj > TOL_DUAL) s = VS_NL;
+                    else if (dj < -TOL_DUAL) s = VS_NU;
+                    else if (s != VS_NL && s != VS_NU) s = VS_NL;
+                } else if (lo > -INFINITY) { s = VS_NL; if (dj < -TOL_DUAL) infeas = 1; }
+                else if (hi < INFINITY) { s = VS_NU; if (dj > TOL_DUAL) infeas = 1; }
+                else { s = VS_NF; if (fabs(dj) > TOL_DUAL) infeas = 1; }
+                xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
+            }
             sm.nbstat[j] = s;
-            sm.xn[j] = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
+            sm.xn[j] = xv;
         }
-        infeas = group_any<G>(infeas, mask);
+        infeas = group_ballot<G>(infeas, mask) != 0u;
         sync();
         return infeas;
     }
 
-    // dict_solve of the oracle.  Returns a B200LP_ST_* code (uniform over the group).
-    __device__ __forceinline__ int solve() {
-        const int cap_bland = 20 * (m + n) + 50, cap_fail = 200 * (m + n) + 1000;
-        int shifted = place_nonbasics();
+    // working reduced costs of the (possibly cost-shifted) dual phase
+    __device__ __forceinline__ void init_dw(int shifted) {
         for (int j = gl; j < NC; j += G) {
             double w = sm.d[j];
             if (shifted) {
@@ -382,12 +391,21 @@ struct Dict {
             sm.dw[j] = w;
         }
         sync();
+    }
+
+    // dict_solve of the oracle.  Returns a B200LP_ST_* code (uniform over the group).
+    __device__ __forceinline__ int solve() {
+        const int cap_bland = 20 * (m + n) + 50, cap_fail = 200 * (m + n) + 1000;
+        int shifted = place_nonbasics();
+        bool dw_ready = false;
         load_basic_bounds();
         int phase = 0;
+#pragma unroll 1
         for (int it = 0;; it++) {
             if (it > cap_fail) return B200LP_ST_ITERLIMIT;
             const bool bland = it > cap_bland;
             basic_values();
+            int pl, ps, q, to_upper;
             if (phase == 0) {
                 // ---- leaving variable: largest bound violation -------------------------------
                 double worst = -1.0; int bi = -1, dir = 0;
@@ -402,13 +420,14 @@ struct Dict {
                         if (bi < 0 || viol > worst) { worst = viol; bi = r * G + gl; dir = dd; }
                     }
                 }
-                group_argmax<G>(worst, bi, dir, mask);
-                if (bi < 0) {
+                if (group_ballot<G>(bi >= 0, mask) == 0u) {  // primal feasible
                     if (!shifted) return B200LP_ST_OPTIMAL;
                     phase = 1; shifted = 0;
                     continue;
                 }
-                const int pl = bi % G, ps = bi / G;
+                group_argmax<G>(worst, bi, dir, mask);
+                if (!dw_ready) { init_dw(shifted); dw_ready = true; }
+                pl = bi % G; ps = bi / G;
                 publish_row(pl, ps);
                 // ---- dual ratio test ------------------------------------------------------------
                 double rmin = INFINITY;
@@ -424,7 +443,8 @@ struct Dict {
                 rmin = group_min<G>(rmin, mask);
                 if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
                 const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
-                double amax = -1.0; int q = -1, aux = 0;
+                double amax = -1.0; int aux = 0;
+                q = -1;
                 for (int j = gl; j < NC; j += G) {
                     const int s = sm.nbstat[j];
                     const double a = sm.prow[j] * (double)dir;
@@ -438,22 +458,11 @@ struct Dict {
                     if (q < 0 || key > amax) { amax = key; q = j; }
                 }
                 group_argmax<G>(amax, q, aux, mask);
-                // the leaving variable's bounds (held by lane pl)
-                double vlo = 0.0, vhi = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
-                vlo = __shfl_sync(mask, vlo, pl, G);
-                vhi = __shfl_sync(mask, vhi, pl, G);
-                pivot(pl, ps, q, true);
-                if (gl == 0) {
-                    sm.nbstat[q] = (vlo == vhi) ? VS_NS : (dir > 0 ? VS_NL : VS_NU);
-                    sm.xn[q] = dir > 0 ? vlo : vhi;
-                }
-                sync();
-                load_basic_bounds();
+                to_upper = dir < 0;  // leaving variable goes to the bound it violated
             } else {
                 // ---- entering variable: largest dual infeasibility -----------------------------
-                double worst = -1.0; int q = -1, dir = 0;
+                double worst = -1.0; int dir = 0;
+                q = -1;
                 for (int j = gl; j < NC; j += G) {
                     const int s = sm.nbstat[j];
                     const double dj = sm.d[j];
@@ -468,7 +477,7 @@ struct Dict {
                 group_argmax<G>(worst, q, dir, mask);
                 if (q < 0) return B200LP_ST_OPTIMAL;
                 const int vin = sm.nb[q];
-                const double inlo = var_lo(vin), inhi = var_hi(vin);
+                const double inlo = sm.LO[vin + 1], inhi = sm.HI[vin + 1];
                 double tmin = inhi - inlo;
                 if (!(tmin < INFINITY)) tmin = INFINITY;
                 // ---- primal ratio test down column q ---------------------------------------------
@@ -503,21 +512,23 @@ struct Dict {
                     if (bi < 0 || key > amax) { amax = key; bi = r * G + gl; up = upf[r]; }
                 }
                 group_argmax<G>(amax, bi, up, mask);
-                const int pl = bi % G, ps = bi / G;
+                pl = bi % G; ps = bi / G;
                 publish_row(pl, ps);
-                double vlo = 0.0, vhi = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
-                vlo = __shfl_sync(mask, vlo, pl, G);
-                vhi = __shfl_sync(mask, vhi, pl, G);
-                pivot(pl, ps, q, false);
-                if (gl == 0) {
-                    sm.nbstat[q] = (vlo == vhi) ? VS_NS : (up ? VS_NU : VS_NL);
-                    sm.xn[q] = up ? vhi : vlo;
-                }
-                sync();
-                load_basic_bounds();
+                to_upper = up;
             }
+            // ---- the pivot (single call site for both phases) ---------------------------------
+            double vlo = 0.0, vhi = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
+            vlo = __shfl_sync(mask, vlo, pl, G);
+            vhi = __shfl_sync(mask, vhi, pl, G);
+            pivot(pl, ps, q, phase == 0);
+            if (gl == 0) {
+                sm.nbstat[q] = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
+                sm.xn[q] = to_upper ? vhi : vlo;
+            }
+            sync();
+            load_basic_bounds();
         }
     }
 };
@@ -526,63 +537,132 @@ struct Dict {
 // Per-timestep pipeline pieces shared by the step kernel and the run kernel.
 // ------------------------------------------------------------------------------------------------
 
-// (a5/a6) row bounds and (a3) objective from this scenario's slot vector sm.p.  `vol` points at the
-// storage volumes of this scenario (element k at vol[k*vol_stride]).  Returns 0, B200LP_ST_NAN or
-// B200LP_ST_INFEASIBLE (inconsistent bounds), uniform over the group.
 template <int G, int RPL, int NC>
-__device__ __forceinline__ int assemble_lp(const DevStructure &st, Dict<G, RPL, NC> &D, const double days,
-                                           const double *vol, const size_t vol_stride) {
-    const int gl = D.gl, n = st.n, m = st.m;
-    int nan_seen = 0, bad_bounds = 0;
+__device__ __forceinline__ void init_group(Dict<G, RPL, NC> &D, const DevStructure &st, unsigned char *smem_raw,
+                                           const int gib) {
+    D.gl = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
+    D.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    D.n = st.n; D.m = st.m; D.pivots = 0;
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
+    D.sm.carve(smem_raw + gbytes * gib, st.n_val);
+}
+
+// Row descriptors of the rows a lane owns (registers, loaded once per launch).
+template <int RPL>
+struct RowDesc {
+    int cls[RPL], a[RPL], b[RPL];
+};
+
+// constants -> V, bounds of columns / padding, bounds of the rows whose refs are both constants,
+// and the objective when no cost is an input.  Called once per launch after V's constants and
+// volumes are in place.
+template <int G, int RPL, int NC>
+__device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, RPL, NC> &D, RowDesc<RPL> &rd) {
+    constexpr int ROWS = G * RPL;
+    const int gl = D.gl, n = st.n;
+    for (int k = gl; k < st.n_consts; k += G) D.sm.V[st.n_slots + k] = __ldg(&st.consts[k]);
+    for (int v = gl; v < 1 + NC; v += G) {  // entry 0 (padding variable) and the columns x >= 0
+        const bool col = v >= 1 && v <= n;
+        D.sm.LO[v] = col ? 0.0 : -INFINITY;
+        D.sm.HI[v] = INFINITY;
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int i = r * G + gl;
+        rd.cls[r] = __ldg(&st.row_class[i]);
+        rd.a[r] = __ldg(&st.row_a[i]);
+        rd.b[r] = __ldg(&st.row_b[i]);
+    }
+    D.sync();
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
         const int i = r * G + gl;
         double l = -INFINITY, u = INFINITY;
-        if (i < m) {
-            if (__ldg(&st.row_kind[i]) == B200LP_ROW_FLOW) {
-                l = ref_value(st, __ldg(&st.row_lb_ref[i]), D.sm.p);
-                u = ref_value(st, __ldg(&st.row_ub_ref[i]), D.sm.p);
-                if (isnan(l) || isnan(u)) nan_seen = 1;
-                type_bounds(l, u);
-            } else {
-                const int k = __ldg(&st.row_lb_ref[i]);
-                const double maxv = ref_value(st, __ldg(&st.st_maxv_ref[k]), D.sm.p);
-                const double minv = ref_value(st, __ldg(&st.st_minv_ref[k]), D.sm.p);
-                const int vref = __ldg(&st.st_vol_ref[k]);
-                const double v = (vref == B200LP_REF_STATE) ? vol[(size_t)k * vol_stride] : ref_value(st, vref, D.sm.p);
-                int active = 1;
-                if (__ldg(&st.st_kind[k]) == B200LP_ST_KIND_VIRTUAL)
-                    active = ref_value(st, __ldg(&st.st_active_ref[k]), D.sm.p) != 0.0;
-                if (isnan(maxv) || isnan(minv) || isnan(v)) nan_seen = 1;
-                if (maxv == minv) { l = 0.0; u = 0.0; }
-                else if (!active) { l = -INFINITY; u = INFINITY; }
-                else {
-                    const double avail = fmax(v - minv, 0.0);
-                    l = -avail / days;
-                    u = fmax(maxv - v, 0.0) / days;
-                    type_bounds(l, u);
-                }
-            }
-            if (l > u) bad_bounds = 1;
+        if (rd.cls[r] == ROWC_STATIC) {
+            l = D.sm.V[rd.a[r]]; u = D.sm.V[rd.b[r]];
+            type_bounds(l, u);
         }
-        D.sm.lo_r[i] = l; D.sm.hi_r[i] = u;
+        D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
     }
-    for (int j = gl; j < NC; j += G) {
+    (void)ROWS;
+}
+
+// (a3) objective c_j = sum w * V[idx], clipped (cython_glpk.pyx:886-897)
+template <int G, int RPL, int NC>
+__device__ __forceinline__ int assemble_costs(const DevStructure &st, Dict<G, RPL, NC> &D) {
+    int nan_seen = 0;
+    for (int j = D.gl; j < NC; j += G) {
         double acc = 0.0;
-        if (j < n) {
+        if (j < st.n) {
             for (int k = __ldg(&st.cost_indptr[j]); k < __ldg(&st.cost_indptr[j + 1]); k++)
-                acc += __ldg(&st.cost_w[k]) * ref_value(st, __ldg(&st.cost_ref[k]), D.sm.p);
+                acc += __ldg(&st.cost_w[k]) * D.sm.V[__ldg(&st.cost_idx[k])];
             if (isnan(acc)) nan_seen = 1;
             if (st.cost_clip && fabs(acc) < 1e-8) acc = 0.0;
         }
         D.sm.cost[j] = acc;
     }
-    for (int k = gl; k < st.n_dyn_a; k += G)
-        if (isnan(ref_value(st, __ldg(&st.dyn_a_ref[k]), D.sm.p))) nan_seen = 1;
-    nan_seen = group_any<G>(nan_seen, D.mask);
-    bad_bounds = group_any<G>(bad_bounds, D.mask);
+    return nan_seen;
+}
+
+// (a5/a6) bounds of the rows that depend on per-step values.  Returns 0, B200LP_ST_NAN or
+// B200LP_ST_INFEASIBLE (inconsistent bounds), uniform over the group.  `static_flags` carries the
+// NaN / inconsistency flags of the static part (bit 0 NaN, bit 1 bad bounds).
+template <int G, int RPL, int NC>
+__device__ __forceinline__ int assemble_dynamic(const DevStructure &st, Dict<G, RPL, NC> &D, const RowDesc<RPL> &rd,
+                                                const double days, int flags) {
+    const int n = st.n;
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        const int i = r * G + D.gl;
+        if (rd.cls[r] == ROWC_FLOW) {
+            double l = D.sm.V[rd.a[r]], u = D.sm.V[rd.b[r]];
+            if (isnan(l) || isnan(u)) flags |= 1;
+            type_bounds(l, u);
+            if (l > u) flags |= 2;
+            D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
+        } else if (rd.cls[r] == ROWC_STORAGE) {
+            const int k = rd.a[r];
+            const double maxv = D.sm.V[__ldg(&st.st_maxv_idx[k])];
+            const double minv = D.sm.V[__ldg(&st.st_minv_idx[k])];
+            const double v = D.sm.V[__ldg(&st.st_vol_idx[k])];
+            const bool active = D.sm.V[__ldg(&st.st_active_idx[k])] != 0.0;  // plain storages point at a constant 1
+            if (isnan(maxv) || isnan(minv) || isnan(v)) flags |= 1;
+            double l, u;
+            if (maxv == minv) { l = 0.0; u = 0.0; }
+            else if (!active) { l = -INFINITY; u = INFINITY; }
+            else {
+                const double avail = fmax(v - minv, 0.0);
+                l = -avail / days;
+                u = fmax(maxv - v, 0.0) / days;
+                type_bounds(l, u);
+            }
+            if (l > u) flags |= 2;
+            D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
+        }
+    }
+    if (st.cost_dynamic) flags |= assemble_costs(st, D);
+    for (int k = D.gl; k < st.n_dyn_a; k += G)
+        if (isnan(D.sm.V[__ldg(&st.dyn_a_idx[k])])) flags |= 1;
+    const unsigned nanb = group_ballot<G>(flags & 1, D.mask), badb = group_ballot<G>(flags & 2, D.mask);
     D.sync();
-    return nan_seen ? B200LP_ST_NAN : (bad_bounds ? B200LP_ST_INFEASIBLE : 0);
+    return nanb ? B200LP_ST_NAN : (badb ? B200LP_ST_INFEASIBLE : 0);
+}
+
+// static part of the flags: NaN constants / inconsistent constant bounds
+template <int G, int RPL, int NC>
+__device__ __forceinline__ int static_flags(const DevStructure &st, Dict<G, RPL, NC> &D, const RowDesc<RPL> &rd) {
+    int flags = 0;
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+        if (rd.cls[r] == ROWC_STATIC) {
+            const double l = D.sm.V[rd.a[r]], u = D.sm.V[rd.b[r]];
+            if (isnan(l) || isnan(u)) flags |= 1;
+            const int i = r * G + D.gl;
+            if (D.sm.LO[1 + st.n + i] > D.sm.HI[1 + st.n + i]) flags |= 2;
+        }
+    }
+    return flags;
 }
 
 // (a7) warm-started solve with the oracle's retry ladder (role of retry_solve, cython_glpk.pyx:1034-1042)
@@ -592,6 +672,7 @@ __device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC>
     bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
     const bool fresh0 = need_refactor;
     int status = B200LP_ST_OPTIMAL;
+#pragma unroll 1
     for (int attempt = 0; attempt < 3; attempt++) {
         if (attempt == 1 && fresh0) continue;
         if (attempt == 2) D.slack_basis();
@@ -615,18 +696,21 @@ __device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC>
     return status;
 }
 
-// (a8) primal values of the columns into sm.x
+// (a8) primal values of the columns into sm.x and the activities of the rows into sm.ract
 template <int G, int RPL, int NC>
-__device__ __forceinline__ void extract_columns(Dict<G, RPL, NC> &D) {
+__device__ __forceinline__ void extract_solution(Dict<G, RPL, NC> &D) {
     D.basic_values();
+    const int n = D.n;
     for (int j = D.gl; j < NC; j += G) {
         const int v = D.sm.nb[j];
-        if (v >= 0 && v < D.n) D.sm.x[v] = D.sm.xn[j];
+        if (v >= n) D.sm.ract[v - n] = D.sm.xn[j];
+        else if (v >= 0) D.sm.x[v] = D.sm.xn[j];
     }
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
         const int v = D.head[r];
-        if (v >= 0 && v < D.n) D.sm.x[v] = D.beta[r];
+        if (v >= n) D.sm.ract[v - n] = D.beta[r];
+        else if (v >= 0) D.sm.x[v] = D.beta[r];
     }
     D.sync();
 }
@@ -649,7 +733,6 @@ __device__ __forceinline__ void load_state(const DevState &state, Dict<G, RPL, N
         D.sm.nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
         D.sm.d[j] = state.d[(size_t)sidx * NC + j];
     }
-    D.sync();
 }
 
 template <int G, int RPL, int NC>
@@ -672,17 +755,6 @@ __device__ __forceinline__ void store_state(const DevState &state, Dict<G, RPL, 
     }
 }
 
-template <int G, int RPL, int NC>
-__device__ __forceinline__ void init_group(Dict<G, RPL, NC> &D, const DevStructure &st, unsigned char *smem_raw,
-                                           const int gib, const int extra_doubles) {
-    D.gl = threadIdx.x % G;
-    const int lane = threadIdx.x & 31;
-    D.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
-    D.n = st.n; D.m = st.m; D.pivots = 0;
-    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_slots + extra_doubles) + 15) & ~(size_t)15;
-    D.sm.carve(smem_raw + gbytes * gib, st.n_slots + extra_doubles);
-}
-
 // ------------------------------------------------------------------------------------------------
 // One timestep for all scenarios (the per-timestep Solver.solve path).
 // ------------------------------------------------------------------------------------------------
@@ -698,18 +770,23 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
     if (sidx >= S) return;  // whole group exits together
 
     Dict<G, RPL, NC> D;
-    init_group(D, st, smem_raw, gib, 0);
+    init_group(D, st, smem_raw, gib);
     const int gl = D.gl, n = st.n;
 
-    for (int k = gl; k < st.n_slots; k += G) D.sm.p[k] = slots[(size_t)k * S + sidx];
-    D.sync();
+    for (int k = gl; k < st.n_slots; k += G) D.sm.V[k] = slots[(size_t)k * S + sidx];
+    for (int k = gl; k < st.n_storage; k += G) D.sm.V[st.vol_base + k] = state.vol[(size_t)k * S + sidx];
+    RowDesc<RPL> rd;
+    prepare_static(st, D, rd);
+    int flags = static_flags(st, D, rd);
+    if (!st.cost_dynamic) flags |= assemble_costs(st, D);
+    int status = assemble_dynamic(st, D, rd, days, flags);
 
-    int status = assemble_lp(st, D, days, state.vol + sidx, (size_t)S);
     int *meta = state.meta + (size_t)sidx * 4;
     int refactors = 0;
     if (status == 0) {
         int valid = meta[0], npiv = meta[1];
         load_state(state, D, sidx, valid);
+        D.sync();
         status = solve_lp(st, D, valid, npiv, refactors);
         store_state(state, D, sidx, D.pivots > 0 || refactors > 0);
         if (gl == 0) { meta[0] = valid; meta[1] = npiv; }
@@ -725,7 +802,7 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
     }
     if (status != B200LP_ST_OPTIMAL) return;
 
-    extract_columns(D);
+    extract_solution(D);
     if (col_flow)
         for (int j = gl; j < n; j += G) col_flow[(size_t)j * S + sidx] = D.sm.x[j];
     if (objective && gl == 0) {
@@ -749,17 +826,21 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
 // here, so nothing returns to the host until read-out.
 // ------------------------------------------------------------------------------------------------
 struct DevProgram {
-    int n_steps, n_ops, n_tables, n_axes, n_recorders, n_table_ops;
+    int n_steps, n_tables, n_axes, n_recorders, n_table_ops, n_code;
     const double *ts_days;
-    const int *op_kind, *op_dst, *op_arg_ptr, *op_args;
-    const int *table_op;  // [n_table_ops] indices of the B200LP_OP_TABLE ops (prefetched one step ahead)
+    // table ops, one descriptor each (prefetched one timestep ahead by the lane that owns it)
+    const int *tab_dst;      // [n_table_ops] V index written
+    const int *tab_table;    // [n_table_ops]
+    const int *tab_offset;   // [n_table_ops]
     const int *table_rows, *table_cols, *table_axis;
     const long long *table_offset;
     const double *table_data;
     const int *scen_index;
+    // all other ops, pre-decoded: kind, dst, nargs, args... (V indices / storage ids / small ints)
+    const int *code;
     const int *stflow_indptr, *stflow_col;
     const double *stflow_w;
-    const int *rec_kind, *rec_src, *rec_ref, *rec_indptr, *rec_col;
+    const int *rec_kind, *rec_src, *rec_idx, *rec_row, *rec_indptr, *rec_col;
     const double *rec_factor, *rec_w;
     double *const *rec_out;  // [n_recorders] device outputs
     double *pc;              // [n_storage][S]
@@ -773,65 +854,67 @@ __device__ __forceinline__ double clamp_pc(double pc) {  // Storage.get_current_
     return pc;
 }
 
-__device__ __forceinline__ double table_lookup(const DevProgram &pg, const int *a, const int t, const int sidx, const int S) {
-    const int tb = a[0];
-    long long row = 0;
-    const int rows = __ldg(&pg.table_rows[tb]);
-    if (rows > 1) {
-        row = (long long)t + a[1];
-        if (row < 0) row = 0;
-        if (row > rows - 1) row = rows - 1;
-    }
-    const int ax = __ldg(&pg.table_axis[tb]);
-    const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
-    return __ldg(&pg.table_data[__ldg(&pg.table_offset[tb]) + row * __ldg(&pg.table_cols[tb]) + col]);
-}
-
-// scalar interpreter for the non-table ops (lane 0 of the group); same arithmetic as orc_eval_ops
-__device__ __forceinline__ void eval_ops(const DevStructure &st, const DevProgram &pg, double *p, const double *pc) {
-    for (int k = 0; k < pg.n_ops; k++) {
-        const int kind = __ldg(&pg.op_kind[k]);
-        if (kind == B200LP_OP_TABLE) continue;
-        const int *a = pg.op_args + __ldg(&pg.op_arg_ptr[k]);
+// scalar interpreter for the non-table ops (lane 0 of the group); same arithmetic as orc_eval_ops.
+// `code` is in shared memory; every operand is an index into V.
+__device__ __forceinline__ void eval_ops(const int *code, const int n_code, double *V, const int pc_base) {
+    int pos = 0;
+    while (pos < n_code) {
+        const int kind = code[pos], dst = code[pos + 1], na = code[pos + 2];
+        const int *a = code + pos + 3;
+        pos += 3 + na;
         double v = 0.0;
         switch (kind) {
         case B200LP_OP_AGG: {
             const int func = a[0], cnt = a[1];
-            if (func == B200LP_AGG_PRODUCT) { v = 1.0; for (int i = 0; i < cnt; i++) v *= ref_value(st, a[2 + i], p); }
-            else if (func == B200LP_AGG_SUM) { v = 0.0; for (int i = 0; i < cnt; i++) v += ref_value(st, a[2 + i], p); }
-            else if (func == B200LP_AGG_MAX) { v = -INFINITY; for (int i = 0; i < cnt; i++) { const double w = ref_value(st, a[2 + i], p); if (w > v) v = w; } }
-            else if (func == B200LP_AGG_MIN) { v = INFINITY; for (int i = 0; i < cnt; i++) { const double w = ref_value(st, a[2 + i], p); if (w < v) v = w; } }
-            else { v = 0.0; for (int i = 0; i < cnt; i++) v += ref_value(st, a[2 + i], p); v /= cnt; }
+            if (func == B200LP_AGG_PRODUCT) { v = 1.0; for (int i = 0; i < cnt; i++) v *= V[a[2 + i]]; }
+            else if (func == B200LP_AGG_SUM) { v = 0.0; for (int i = 0; i < cnt; i++) v += V[a[2 + i]]; }
+            else if (func == B200LP_AGG_MAX) { v = -INFINITY; for (int i = 0; i < cnt; i++) { const double w = V[a[2 + i]]; if (w > v) v = w; } }
+            else if (func == B200LP_AGG_MIN) { v = INFINITY; for (int i = 0; i < cnt; i++) { const double w = V[a[2 + i]]; if (w < v) v = w; } }
+            else { v = 0.0; for (int i = 0; i < cnt; i++) v += V[a[2 + i]]; v /= cnt; }
         } break;
         case B200LP_OP_CONTROL_CURVE: {
             const int cnt = a[1];
-            const double c = clamp_pc(pc[a[0]]);
+            const double c = clamp_pc(V[pc_base + a[0]]);
             int idx = cnt;
-            for (int i = 0; i < cnt; i++) if (c >= ref_value(st, a[2 + i], p)) { idx = i; break; }
-            v = ref_value(st, a[2 + cnt + idx], p);
+            for (int i = 0; i < cnt; i++) if (c >= V[a[2 + i]]) { idx = i; break; }
+            v = V[a[2 + cnt + idx]];
         } break;
         case B200LP_OP_CC_INDEX: {
             const int cnt = a[1];
-            const double c = clamp_pc(pc[a[0]]);
+            const double c = clamp_pc(V[pc_base + a[0]]);
             int idx = cnt;
-            for (int i = 0; i < cnt; i++) if (c >= ref_value(st, a[2 + i], p)) { idx = i; break; }
+            for (int i = 0; i < cnt; i++) if (c >= V[a[2 + i]]) { idx = i; break; }
             v = (double)idx;
         } break;
         case B200LP_OP_INDEXED: {
-            int idx = (int)ref_value(st, a[0], p);
+            int idx = (int)V[a[0]];
             if (idx < 0) idx = 0;
             if (idx > a[1] - 1) idx = a[1] - 1;
-            v = ref_value(st, a[2 + idx], p);
+            v = V[a[2 + idx]];
         } break;
-        case B200LP_OP_NEG: v = -ref_value(st, a[0], p); break;
-        case B200LP_OP_MAX0: { const double x = ref_value(st, a[0], p), th = ref_value(st, a[1], p); v = x > th ? x : th; } break;
-        case B200LP_OP_MIN0: { const double x = ref_value(st, a[0], p), th = ref_value(st, a[1], p); v = x < th ? x : th; } break;
-        case B200LP_OP_DIV: v = ref_value(st, a[0], p) / ref_value(st, a[1], p); break;
+        case B200LP_OP_NEG: v = -V[a[0]]; break;
+        case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
+        case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
+        case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
         default: v = NAN;
         }
-        p[__ldg(&pg.op_dst[k])] = v;
+        V[dst] = v;
     }
 }
+
+// one table op owned by a lane: value(t) = ptr[clamp(t + off) * stride]
+struct TableDesc {
+    const double *ptr;
+    int rows, stride, off, dst;
+    __device__ __forceinline__ double at(int t) const {
+        long long row = 0;
+        if (rows > 1) {
+            row = (long long)t + off;
+            row = row < 0 ? 0 : (row > rows - 1 ? rows - 1 : row);
+        }
+        return __ldg(ptr + row * stride);
+    }
+};
 
 template <int G, int RPL, int NC>
 __global__ void __launch_bounds__(128)
@@ -841,98 +924,157 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
     const int groups_per_block = blockDim.x / G;
     const int gib = threadIdx.x / G;
     const int sidx = blockIdx.x * groups_per_block + gib;
+    // the pre-decoded op code is shared by the groups of the block
+    const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
+    int *code = reinterpret_cast<int *>(smem_raw + gbytes * groups_per_block);
+    for (int k = threadIdx.x; k < pg.n_code; k += blockDim.x) code[k] = __ldg(&pg.code[k]);
+    __syncthreads();
     if (sidx >= S) return;
 
     Dict<G, RPL, NC> D;
-    init_group(D, st, smem_raw, gib, 2 * st.n_storage);
+    init_group(D, st, smem_raw, gib);
     const int gl = D.gl, n = st.n, nst = st.n_storage;
-    double *vol = D.sm.p + st.n_slots;  // [n_storage]
-    double *pc = vol + nst;             // [n_storage]
+    double *V = D.sm.V;
 
     int *meta = state.meta + (size_t)sidx * 4;
     if (meta[2] != B200LP_ST_OPTIMAL) return;  // failed at an earlier timestep
     int valid = meta[0], npiv = meta[1], refactors = 0;
     load_state(state, D, sidx, valid);
-    for (int k = gl; k < nst; k += G) { vol[k] = state.vol[(size_t)k * S + sidx]; pc[k] = pg.pc[(size_t)k * S + sidx]; }
+    for (int k = gl; k < nst; k += G) {
+        V[st.vol_base + k] = state.vol[(size_t)k * S + sidx];
+        V[st.pc_base + k] = pg.pc[(size_t)k * S + sidx];
+    }
+    RowDesc<RPL> rd;
+    prepare_static(st, D, rd);
+    int sflags = static_flags(st, D, rd);
+    if (!st.cost_dynamic) sflags |= assemble_costs(st, D);
     D.sync();
 
-    // table values are fetched one timestep ahead (lane j owns table op j, j + G, ...)
-    constexpr int MAXPF = 4;
+    // table ops: lane j owns op j, j + G, ...; values are fetched one timestep ahead
+    constexpr int MAXPF = 2;
+    TableDesc td[MAXPF];
     double pf[MAXPF];
 #pragma unroll
     for (int u = 0; u < MAXPF; u++) {
         const int j = gl + u * G;
-        pf[u] = 0.0;
+        td[u].ptr = pg.table_data; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = -1;
         if (j < pg.n_table_ops) {
-            const int k = __ldg(&pg.table_op[j]);
-            pf[u] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t0, sidx, S);
+            const int tb = __ldg(&pg.tab_table[j]);
+            const int ax = __ldg(&pg.table_axis[tb]);
+            const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
+            td[u].ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
+            td[u].rows = __ldg(&pg.table_rows[tb]);
+            td[u].stride = __ldg(&pg.table_cols[tb]);
+            td[u].off = __ldg(&pg.tab_offset[j]);
+            td[u].dst = __ldg(&pg.tab_dst[j]);
         }
+        pf[u] = td[u].dst >= 0 ? td[u].at(t0) : 0.0;
+    }
+    // recorder owned by this lane (recorders beyond G are handled by the generic loop below)
+    int rk = 0, rrow = -1, ridx = 0, rsrc = 0, rbeg = 0, rend = 0;
+    double rfac = 1.0;
+    double *rout = nullptr;
+    if (gl < pg.n_recorders) {
+        rk = __ldg(&pg.rec_kind[gl]); rrow = __ldg(&pg.rec_row[gl]); ridx = __ldg(&pg.rec_idx[gl]);
+        rsrc = __ldg(&pg.rec_src[gl]); rbeg = __ldg(&pg.rec_indptr[gl]); rend = __ldg(&pg.rec_indptr[gl + 1]);
+        rfac = __ldg(&pg.rec_factor[gl]); rout = pg.rec_out[gl];
+    }
+    // storage owned by this lane
+    int sk = -1, s_row = 0, s_max = 0, s_min = 0, s_act = 0, s_beg = 0, s_end = 0;
+    if (gl < nst) {
+        sk = __ldg(&st.st_kind[gl]); s_row = __ldg(&st.st_row[gl]);
+        s_max = __ldg(&st.st_maxv_idx[gl]); s_min = __ldg(&st.st_minv_idx[gl]); s_act = __ldg(&st.st_active_idx[gl]);
+        s_beg = __ldg(&pg.stflow_indptr[gl]); s_end = __ldg(&pg.stflow_indptr[gl + 1]);
     }
 
     int status = B200LP_ST_OPTIMAL;
     int t = t0;
+#pragma unroll 1
     for (; t < t0 + nsteps; t++) {
         const double days = __ldg(&pg.ts_days[t]);
         // ---- before(): parameters -------------------------------------------------------------
 #pragma unroll
         for (int u = 0; u < MAXPF; u++) {
-            const int j = gl + u * G;
-            if (j < pg.n_table_ops) {
-                const int k = __ldg(&pg.table_op[j]);
-                D.sm.p[__ldg(&pg.op_dst[k])] = pf[u];
-                if (t + 1 < t0 + nsteps) pf[u] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t + 1, sidx, S);
+            if (td[u].dst >= 0) {
+                V[td[u].dst] = pf[u];
+                if (t + 1 < t0 + nsteps) pf[u] = td[u].at(t + 1);
             }
         }
         for (int j = gl + MAXPF * G; j < pg.n_table_ops; j += G) {  // more table ops than prefetch slots
-            const int k = __ldg(&pg.table_op[j]);
-            D.sm.p[__ldg(&pg.op_dst[k])] = table_lookup(pg, pg.op_args + __ldg(&pg.op_arg_ptr[k]), t, sidx, S);
+            const int tb = __ldg(&pg.tab_table[j]);
+            const int ax = __ldg(&pg.table_axis[tb]);
+            const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
+            TableDesc q;
+            q.ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
+            q.rows = __ldg(&pg.table_rows[tb]); q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
+            V[__ldg(&pg.tab_dst[j])] = q.at(t);
         }
         D.sync();
-        if (gl == 0) eval_ops(st, pg, D.sm.p, pc);
-        D.sync();
+        if (pg.n_code > 0) {
+            if (gl == 0) eval_ops(code, pg.n_code, V, st.pc_base);
+            D.sync();
+        }
         // ---- solve() ------------------------------------------------------------------------------
-        status = assemble_lp(st, D, days, vol, (size_t)1);
+        status = assemble_dynamic(st, D, rd, days, sflags);
         if (status == 0) status = solve_lp(st, D, valid, npiv, refactors);
         if (status != B200LP_ST_OPTIMAL) break;
-        extract_columns(D);
+        extract_solution(D);
         // ---- after(): storage mass balance (Storage.after, pywr/_core.pyx:1335-1361) ---------------
-        for (int k = gl; k < nst; k += G) {
-            if (__ldg(&st.st_kind[k]) == B200LP_ST_KIND_VIRTUAL &&
-                !(ref_value(st, __ldg(&st.st_active_ref[k]), D.sm.p) != 0.0))
-                continue;
+        if (sk >= 0 && (sk == B200LP_ST_KIND_STORAGE || V[s_act] != 0.0)) {
             double flow = 0.0;
-            for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
-                flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
-            double v = vol[k] + flow * days;
-            const double mxv = ref_value(st, __ldg(&st.st_maxv_ref[k]), D.sm.p);
-            const double mnv = ref_value(st, __ldg(&st.st_minv_ref[k]), D.sm.p);
+            if (sk == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[s_row];
+            else
+                for (int e = s_beg; e < s_end; e++) flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+            double v = V[st.vol_base + gl] + flow * days;
+            const double mxv = V[s_max], mnv = V[s_min];
             if (fabs(v - mxv) < 1e-6) v = mxv;
             if (fabs(v - mnv) < 1e-6) v = mnv;
-            vol[k] = v;
-            pc[k] = (mxv == 0.0) ? NAN : v / mxv;
+            V[st.vol_base + gl] = v;
+            V[st.pc_base + gl] = (mxv == 0.0) ? NAN : v / mxv;
+        }
+        for (int k = gl + G; k < nst; k += G) {  // more storages than lanes
+            const int kind = __ldg(&st.st_kind[k]);
+            if (kind == B200LP_ST_KIND_VIRTUAL && !(V[__ldg(&st.st_active_idx[k])] != 0.0)) continue;
+            double flow = 0.0;
+            if (kind == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[__ldg(&st.st_row[k])];
+            else
+                for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
+                    flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+            double v = V[st.vol_base + k] + flow * days;
+            const double mxv = V[__ldg(&st.st_maxv_idx[k])], mnv = V[__ldg(&st.st_minv_idx[k])];
+            if (fabs(v - mxv) < 1e-6) v = mxv;
+            if (fabs(v - mnv) < 1e-6) v = mnv;
+            V[st.vol_base + k] = v;
+            V[st.pc_base + k] = (mxv == 0.0) ? NAN : v / mxv;
         }
         D.sync();
         // ---- recorders -------------------------------------------------------------------------------
         for (int r = gl; r < pg.n_recorders; r += G) {
-            const int kind = __ldg(&pg.rec_kind[r]);
-            double *out = pg.rec_out[r];
+            int kind = rk, row = rrow, idx = ridx, src = rsrc, beg = rbeg, end = rend;
+            double f = rfac;
+            double *out = rout;
+            if (r >= G) {
+                kind = __ldg(&pg.rec_kind[r]); row = __ldg(&pg.rec_row[r]); idx = __ldg(&pg.rec_idx[r]);
+                src = __ldg(&pg.rec_src[r]); beg = __ldg(&pg.rec_indptr[r]); end = __ldg(&pg.rec_indptr[r + 1]);
+                f = __ldg(&pg.rec_factor[r]); out = pg.rec_out[r];
+            }
             double value = 0.0;
-            for (int e = __ldg(&pg.rec_indptr[r]); e < __ldg(&pg.rec_indptr[r + 1]); e++)
-                value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
-            const double f = __ldg(&pg.rec_factor[r]);
+            if (row >= 0) value = D.sm.ract[row];
+            else
+                for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
             const size_t ts_at = (size_t)t * S + sidx;
             switch (kind) {
             case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
-            case B200LP_REC_NODE_DEFICIT: out[ts_at] = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p) - value; break;
-            case B200LP_REC_NODE_SUPPLIED: { const double mf = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p); out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
-            case B200LP_REC_NODE_CURTAIL: { const double mf = ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p); out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
-            case B200LP_REC_STORAGE_VOLUME: out[ts_at] = vol[__ldg(&pg.rec_src[r])]; break;
-            case B200LP_REC_STORAGE_PC: out[ts_at] = pc[__ldg(&pg.rec_src[r])]; break;
-            case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p) - value) * days; break;
+            case B200LP_REC_NODE_DEFICIT: out[ts_at] = V[idx] - value; break;
+            case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
+            case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+            case B200LP_REC_STORAGE_VOLUME: out[ts_at] = V[st.vol_base + src]; break;
+            case B200LP_REC_STORAGE_PC: out[ts_at] = V[st.pc_base + src]; break;
+            case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (V[idx] - value) * days; break;
             case B200LP_REC_TOTAL_FLOW: out[sidx] += value * f * days; break;
             case B200LP_REC_MEAN_FLOW: out[sidx] += value * f; break;
-            case B200LP_REC_DEFICIT_FREQ: if (fabs(value - ref_value(st, __ldg(&pg.rec_ref[r]), D.sm.p)) > 1e-6) out[sidx] += 1.0; break;
-            case B200LP_REC_MIN_VOLUME: { const double v = vol[__ldg(&pg.rec_src[r])]; if (v < out[sidx]) out[sidx] = v; } break;
+            case B200LP_REC_DEFICIT_FREQ: if (fabs(value - V[idx]) > 1e-6) out[sidx] += 1.0; break;
+            case B200LP_REC_MIN_VOLUME: { const double v = V[st.vol_base + src]; if (v < out[sidx]) out[sidx] = v; } break;
             default: break;
             }
         }
@@ -940,7 +1082,10 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
     }
     // ---- persist ------------------------------------------------------------------------------------
     store_state(state, D, sidx, true);
-    for (int k = gl; k < nst; k += G) { state.vol[(size_t)k * S + sidx] = vol[k]; pg.pc[(size_t)k * S + sidx] = pc[k]; }
+    for (int k = gl; k < nst; k += G) {
+        state.vol[(size_t)k * S + sidx] = V[st.vol_base + k];
+        pg.pc[(size_t)k * S + sidx] = V[st.pc_base + k];
+    }
     if (status == B200LP_ST_OPTIMAL)
         for (int j = gl; j < n; j += G) pg.last_x[(size_t)j * S + sidx] = D.sm.x[j];
     if (gl == 0) {

@@ -82,7 +82,7 @@ def load_library(path: str = LIB_PATH):
         fn = getattr(L, name)  # AttributeError if the library does not export it
         fn.restype = restype
         fn.argtypes = argtypes
-    if L.b200lp_abi_version() != 4:
+    if L.b200lp_abi_version() != 5:
         raise EngineUnavailable("libb200lp.so ABI version mismatch: rebuild")
     _lib = L
     return L

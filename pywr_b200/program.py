@@ -54,12 +54,12 @@ class b200lp_program(ctypes.Structure):
         ("stflow_indptr", _i32p), ("stflow_col", _i32p), ("stflow_w", _f64p),
         ("initial_volume", _f64p), ("initial_pc", _f64p),
         ("rec_kind", _i32p), ("rec_src", _i32p), ("rec_ref", _i32p), ("rec_factor", _f64p),
-        ("rec_indptr", _i32p), ("rec_col", _i32p), ("rec_w", _f64p),
+        ("rec_row", _i32p), ("rec_indptr", _i32p), ("rec_col", _i32p), ("rec_w", _f64p),
     ]
 
 
 _P_I32 = ("op_kind op_dst op_arg_ptr op_args table_rows table_cols table_axis scen_index stflow_indptr "
-          "stflow_col rec_kind rec_src rec_ref rec_indptr rec_col").split()
+          "stflow_col rec_kind rec_src rec_ref rec_row rec_indptr rec_col").split()
 _P_I64 = ["table_offset"]
 _P_F64 = "ts_days table_data stflow_w initial_volume initial_pc rec_factor rec_w".split()
 
@@ -88,6 +88,7 @@ class Program:
     rec_src: np.ndarray
     rec_ref: np.ndarray
     rec_factor: np.ndarray
+    rec_row: np.ndarray
     rec_indptr: np.ndarray
     rec_col: np.ndarray
     rec_w: np.ndarray
@@ -419,6 +420,8 @@ def compile_program(model, formulation="route", recorders=None):
     if recorders is None:
         recorders = list(model.recorders)
     rec_kind, rec_src, rec_ref, rec_factor, rec_indptr, rec_col, rec_w, rec_objs = [], [], [], [], [0], [], [], []
+    rec_row = []
+    flow_row = {name[len("flow:"):]: i for i, name in enumerate(base.row_names) if name.startswith("flow:")}
     node_kinds = {
         "NumpyArrayNodeRecorder": REC_NODE_FLOW, "NumpyArrayNodeDeficitRecorder": REC_NODE_DEFICIT,
         "NumpyArrayNodeSuppliedRatioRecorder": REC_NODE_SUPPLIED,
@@ -443,6 +446,8 @@ def compile_program(model, formulation="route", recorders=None):
             factor = float(getattr(rec, "factor", 1.0)) if kind in (REC_NODE_FLOW, REC_TOTAL_FLOW, REC_MEAN_FLOW) else 1.0
             rec_kind.append(kind); rec_src.append(node_id.get(id(node), -1)); rec_ref.append(ref)
             rec_factor.append(factor)
+            # plain Input/Link/Output node: its flow is the activity of its own LP row
+            rec_row.append(flow_row.get(getattr(node, "fully_qualified_name", None), -1) if id(node) in node_id else -1)
             for c in sorted(form):
                 rec_col.append(c); rec_w.append(form[c])
         elif cname in ("NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"):
@@ -453,7 +458,7 @@ def compile_program(model, formulation="route", recorders=None):
                 kind = REC_MIN_VOLUME
             else:
                 kind = REC_STORAGE_PC if rec.proportional else REC_STORAGE_VOLUME
-            rec_kind.append(kind); rec_src.append(k); rec_ref.append(0); rec_factor.append(1.0)
+            rec_kind.append(kind); rec_src.append(k); rec_ref.append(0); rec_factor.append(1.0); rec_row.append(-1)
         else:
             raise Unsupported(f"recorder type {cname} is evaluated on the host")
         rec_indptr.append(len(rec_col))
@@ -499,7 +504,7 @@ def compile_program(model, formulation="route", recorders=None):
         scen_index=C.scen_index.reshape(-1),
         stflow_indptr=i32(sf_indptr), stflow_col=i32(sf_col), stflow_w=f64(sf_w),
         initial_volume=vol0.reshape(-1), initial_pc=pc0.reshape(-1),
-        rec_kind=i32(rec_kind), rec_src=i32(rec_src), rec_ref=i32(rec_ref), rec_factor=f64(rec_factor),
+        rec_kind=i32(rec_kind), rec_src=i32(rec_src), rec_ref=i32(rec_ref), rec_factor=f64(rec_factor), rec_row=i32(rec_row),
         rec_indptr=i32(rec_indptr), rec_col=i32(rec_col), rec_w=f64(rec_w), recorders=rec_objs,
     )
     return s, prog
