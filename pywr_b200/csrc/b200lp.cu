@@ -74,10 +74,13 @@ struct Variant {
 #define VARIANT(G, RPL, NC) \
     { G, RPL, NC, &launch_variant<G, RPL, NC>, &run_variant<G, RPL, NC>, &GroupSmem<G, RPL, NC>::bytes }
 
-// ordered from the cheapest; the first one that fits (rows <= G*RPL, cols <= NC) is used
+// ordered from the cheapest; the first one that fits (rows <= G*RPL, cols <= NC) is used unless
+// B200LP_VARIANT forces another one that fits.  Variants 8.. pack several scenarios into one warp
+// (G < 32 lanes per scenario, more rows per lane): fewer, fatter warps for latency-bound batches.
 static const Variant kVariants[] = {
     VARIANT(8, 1, 4),   VARIANT(16, 1, 8),  VARIANT(32, 1, 8),  VARIANT(32, 1, 13),
     VARIANT(32, 1, 16), VARIANT(32, 1, 24), VARIANT(32, 2, 16), VARIANT(32, 2, 32),
+    VARIANT(16, 2, 13), VARIANT(8, 4, 13),  VARIANT(8, 2, 8),   VARIANT(4, 4, 8),
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 

@@ -108,6 +108,7 @@ __device__ __forceinline__ void group_argmax(double &key, int &idx, int &aux, un
 
 template <int G>
 __device__ __forceinline__ unsigned group_ballot(int pred, unsigned mask) {
+    if (G == 32) return __ballot_sync(0xffffffffu, pred);
     return __ballot_sync(mask, pred) & mask;
 }
 
@@ -164,7 +165,10 @@ struct Dict {
     int n, m;
     int pivots;
 
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ unsigned gmask() const { return G == 32 ? 0xffffffffu : mask; }
+    __device__ __forceinline__ void sync() const {
+        if (G == 32) __syncwarp(); else __syncwarp(mask);
+    }
 
     __device__ __forceinline__ void load_basic_bounds() {
 #pragma unroll
@@ -217,7 +221,7 @@ struct Dict {
             int hv = 0;
 #pragma unroll
             for (int r = 0; r < RPL; r++) hv = (r == ps) ? head[r] : hv;
-            vout = __shfl_sync(mask, hv, pl, G);
+            vout = __shfl_sync(gmask(), hv, pl, G);
         }
         sync();
         for (int j = gl; j < NC; j += G) {
@@ -263,7 +267,7 @@ struct Dict {
 #pragma unroll
         for (int j = 0; j < NC; j++) {
 #pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1) part[j] += __shfl_xor_sync(mask, part[j], off, G);
+            for (int off = G / 2; off > 0; off >>= 1) part[j] += __shfl_xor_sync(gmask(), part[j], off, G);
         }
         sync();
         for (int j = gl; j < NC; j += G) {
@@ -309,14 +313,12 @@ struct Dict {
             const int row = __ldg(&st.dyn_a_row[k]), col = __ldg(&st.dyn_a_col[k]);
             const double v = __ldg(&st.dyn_a_scale[k]) * sm.V[__ldg(&st.dyn_a_idx[k])];
             const double delta = v - __ldg(&st.dyn_a_static[k]);
-            if ((row % G) == gl) {
+            const bool mine = (row % G) == gl;
 #pragma unroll
-                for (int r = 0; r < RPL; r++)
-                    if (r == row / G) {
+            for (int r = 0; r < RPL; r++) {
 #pragma unroll
-                        for (int j = 0; j < NC; j++)
-                            if (j == col) T[r][j] += delta;
-                    }
+                for (int j = 0; j < NC; j++)  // select, not an indexed store: T must stay in registers
+                    T[r][j] = (mine && r == row / G && j == col) ? T[r][j] + delta : T[r][j];
             }
         }
         for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.d[j] = 0.0; }
@@ -335,7 +337,7 @@ struct Dict {
                 if (a > best) { best = a; bi = r * G + gl; }
             }
             if (bi < 0) best = -1.0;
-            group_argmax<G>(best, bi, aux, mask);
+            group_argmax<G>(best, bi, aux, gmask());
             if (bi < 0) { ok = -1; break; }
             publish_row(bi % G, bi / G);
             const int save = pivots;
@@ -351,30 +353,27 @@ struct Dict {
         return ok;
     }
 
-    // status + value of every non-basic position for the current bounds (dict_place_nonbasics)
+    // status + value of every non-basic position for the current bounds (dict_place_nonbasics),
+    // written with selects: all lanes follow one instruction stream
     __device__ __forceinline__ int place_nonbasics() {
         int infeas = 0;
         for (int j = gl; j < NC; j += G) {
             const int v = sm.nb[j];
             const double lo = sm.LO[v + 1], hi = sm.HI[v + 1], dj = sm.d[j];
-            int s = sm.nbstat[j];
-            double xv;
+            const int s0 = sm.nbstat[j];
+            const bool lo_fin = lo > -INFINITY, hi_fin = hi < INFINITY, fx = lo == hi;
+            const bool dpos = dj > TOL_DUAL, dneg = dj < -TOL_DUAL;
+            const int s_box = dpos ? VS_NL : (dneg ? VS_NU : ((s0 == VS_NL || s0 == VS_NU) ? s0 : VS_NL));
+            int s = lo_fin ? (hi_fin ? s_box : VS_NL) : (hi_fin ? VS_NU : VS_NF);
+            s = fx ? VS_NS : s;
+            const bool bad = lo_fin ? (!hi_fin && dneg) : (hi_fin ? dpos : (dpos || dneg));
+            double xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
             if (v < 0) { s = VS_NS; xv = 0.0; }
-            else {
-                if (lo == hi) s = VS_NS;
-                else if (lo > -INFINITY && hi < INFINITY) {
-                    if (dj > TOL_DUAL) s = VS_NL;
-                    else if (dj < -TOL_DUAL) s = VS_NU;
-                    else if (s != VS_NL && s != VS_NU) s = VS_NL;
-                } else if (lo > -INFINITY) { s = VS_NL; if (dj < -TOL_DUAL) infeas = 1; }
-                else if (hi < INFINITY) { s = VS_NU; if (dj > TOL_DUAL) infeas = 1; }
-                else { s = VS_NF; if (fabs(dj) > TOL_DUAL) infeas = 1; }
-                xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
-            }
+            infeas |= (!fx && bad && v >= 0) ? 1 : 0;
             sm.nbstat[j] = s;
             sm.xn[j] = xv;
         }
-        infeas = group_ballot<G>(infeas, mask) != 0u;
+        infeas = group_ballot<G>(infeas, gmask()) != 0u;
         sync();
         return infeas;
     }
@@ -420,12 +419,12 @@ struct Dict {
                         if (bi < 0 || viol > worst) { worst = viol; bi = r * G + gl; dir = dd; }
                     }
                 }
-                if (group_ballot<G>(bi >= 0, mask) == 0u) {  // primal feasible
+                if (group_ballot<G>(bi >= 0, gmask()) == 0u) {  // primal feasible
                     if (!shifted) return B200LP_ST_OPTIMAL;
                     phase = 1; shifted = 0;
                     continue;
                 }
-                group_argmax<G>(worst, bi, dir, mask);
+                group_argmax<G>(worst, bi, dir, gmask());
                 if (!dw_ready) { init_dw(shifted); dw_ready = true; }
                 pl = bi % G; ps = bi / G;
                 publish_row(pl, ps);
@@ -440,7 +439,7 @@ struct Dict {
                     else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
                     if (ok) rmin = fmin(rmin, fabs(sm.dw[j]) / fabs(a));
                 }
-                rmin = group_min<G>(rmin, mask);
+                rmin = group_min<G>(rmin, gmask());
                 if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
                 const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
                 double amax = -1.0; int aux = 0;
@@ -457,7 +456,7 @@ struct Dict {
                     const double key = bland ? 1.0 : fabs(a);
                     if (q < 0 || key > amax) { amax = key; q = j; }
                 }
-                group_argmax<G>(amax, q, aux, mask);
+                group_argmax<G>(amax, q, aux, gmask());
                 to_upper = dir < 0;  // leaving variable goes to the bound it violated
             } else {
                 // ---- entering variable: largest dual infeasibility -----------------------------
@@ -474,7 +473,7 @@ struct Dict {
                         if (q < 0 || key > worst) { worst = key; q = j; dir = dd; }
                     }
                 }
-                group_argmax<G>(worst, q, dir, mask);
+                group_argmax<G>(worst, q, dir, gmask());
                 if (q < 0) return B200LP_ST_OPTIMAL;
                 const int vin = sm.nb[q];
                 const double inlo = sm.LO[vin + 1], inhi = sm.HI[vin + 1];
@@ -493,7 +492,7 @@ struct Dict {
                     stp[r] = step; aa[r] = fabs(a); upf[r] = up;
                     step_min = fmin(step_min, step);
                 }
-                step_min = group_min<G>(step_min, mask);
+                step_min = group_min<G>(step_min, gmask());
                 if (step_min == INFINITY && tmin == INFINITY) return B200LP_ST_UNBOUNDED;
                 if (tmin <= step_min) {
                     if (gl == 0) {
@@ -511,7 +510,7 @@ struct Dict {
                     const double key = bland ? 1.0 : aa[r];
                     if (bi < 0 || key > amax) { amax = key; bi = r * G + gl; up = upf[r]; }
                 }
-                group_argmax<G>(amax, bi, up, mask);
+                group_argmax<G>(amax, bi, up, gmask());
                 pl = bi % G; ps = bi / G;
                 publish_row(pl, ps);
                 to_upper = up;
@@ -520,8 +519,8 @@ struct Dict {
             double vlo = 0.0, vhi = 0.0;
 #pragma unroll
             for (int r = 0; r < RPL; r++) { vlo = (r == ps) ? lob[r] : vlo; vhi = (r == ps) ? hib[r] : vhi; }
-            vlo = __shfl_sync(mask, vlo, pl, G);
-            vhi = __shfl_sync(mask, vhi, pl, G);
+            vlo = __shfl_sync(gmask(), vlo, pl, G);
+            vhi = __shfl_sync(gmask(), vhi, pl, G);
             pivot(pl, ps, q, phase == 0);
             if (gl == 0) {
                 sm.nbstat[q] = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
@@ -548,18 +547,18 @@ __device__ __forceinline__ void init_group(Dict<G, RPL, NC> &D, const DevStructu
     D.sm.carve(smem_raw + gbytes * gib, st.n_val);
 }
 
-// Row descriptors of the rows a lane owns (registers, loaded once per launch).
+// Row descriptors of the rows a lane owns (registers, loaded once per launch).  Every lane evaluates
+// BOTH bound formulas each timestep and selects (no divergent branches): a/b are the V indices of
+// lb/ub for flow rows (also for rows whose bounds are constants), vol/minv/maxv/act those of the
+// storage formula (pointing at harmless entries for the other rows).
 template <int RPL>
 struct RowDesc {
-    int cls[RPL], a[RPL], b[RPL];
+    int cls[RPL], a[RPL], b[RPL], vol[RPL], minv[RPL], maxv[RPL], act[RPL];
 };
 
-// constants -> V, bounds of columns / padding, bounds of the rows whose refs are both constants,
-// and the objective when no cost is an input.  Called once per launch after V's constants and
-// volumes are in place.
+// constants -> V, bounds of columns / padding.  Called once per launch.
 template <int G, int RPL, int NC>
 __device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, RPL, NC> &D, RowDesc<RPL> &rd) {
-    constexpr int ROWS = G * RPL;
     const int gl = D.gl, n = st.n;
     for (int k = gl; k < st.n_consts; k += G) D.sm.V[st.n_slots + k] = __ldg(&st.consts[k]);
     for (int v = gl; v < 1 + NC; v += G) {  // entry 0 (padding variable) and the columns x >= 0
@@ -573,19 +572,18 @@ __device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, R
         rd.cls[r] = __ldg(&st.row_class[i]);
         rd.a[r] = __ldg(&st.row_a[i]);
         rd.b[r] = __ldg(&st.row_b[i]);
+        rd.vol[r] = rd.minv[r] = rd.maxv[r] = rd.act[r] = 0;
+        if (rd.cls[r] == ROWC_STORAGE) {
+            const int k = rd.a[r];
+            rd.vol[r] = __ldg(&st.st_vol_idx[k]); rd.minv[r] = __ldg(&st.st_minv_idx[k]);
+            rd.maxv[r] = __ldg(&st.st_maxv_idx[k]); rd.act[r] = __ldg(&st.st_active_idx[k]);
+            rd.a[r] = rd.b[r] = 0;
+        }
+        if (rd.cls[r] == ROWC_PAD) {  // padding rows are free
+            D.sm.LO[1 + n + i] = -INFINITY; D.sm.HI[1 + n + i] = INFINITY;
+        }
     }
     D.sync();
-#pragma unroll
-    for (int r = 0; r < RPL; r++) {
-        const int i = r * G + gl;
-        double l = -INFINITY, u = INFINITY;
-        if (rd.cls[r] == ROWC_STATIC) {
-            l = D.sm.V[rd.a[r]]; u = D.sm.V[rd.b[r]];
-            type_bounds(l, u);
-        }
-        D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
-    }
-    (void)ROWS;
 }
 
 // (a3) objective c_j = sum w * V[idx], clipped (cython_glpk.pyx:886-897)
@@ -605,38 +603,36 @@ __device__ __forceinline__ int assemble_costs(const DevStructure &st, Dict<G, RP
     return nan_seen;
 }
 
-// (a5/a6) bounds of the rows that depend on per-step values.  Returns 0, B200LP_ST_NAN or
-// B200LP_ST_INFEASIBLE (inconsistent bounds), uniform over the group.  `static_flags` carries the
-// NaN / inconsistency flags of the static part (bit 0 NaN, bit 1 bad bounds).
+// (a5/a6) bounds of every row from the value vector V.  Branch-free per lane: both the flow formula
+// (cython_glpk.pyx:932-959) and the storage formula (:965-1019) are evaluated and the row's class
+// selects.  Returns 0, B200LP_ST_NAN or B200LP_ST_INFEASIBLE (inconsistent bounds), uniform over the
+// group.  `flags` carries NaN flags found elsewhere (bit 0).
 template <int G, int RPL, int NC>
-__device__ __forceinline__ int assemble_dynamic(const DevStructure &st, Dict<G, RPL, NC> &D, const RowDesc<RPL> &rd,
-                                                const double days, int flags) {
+__device__ __forceinline__ int assemble_rows(const DevStructure &st, Dict<G, RPL, NC> &D, const RowDesc<RPL> &rd,
+                                             const double days, int flags) {
     const int n = st.n;
+    const bool unit_days = days == 1.0;  // x / 1.0 == x exactly: skip the divisions on daily timesteps
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
         const int i = r * G + D.gl;
-        if (rd.cls[r] == ROWC_FLOW) {
-            double l = D.sm.V[rd.a[r]], u = D.sm.V[rd.b[r]];
-            if (isnan(l) || isnan(u)) flags |= 1;
-            type_bounds(l, u);
-            if (l > u) flags |= 2;
-            D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
-        } else if (rd.cls[r] == ROWC_STORAGE) {
-            const int k = rd.a[r];
-            const double maxv = D.sm.V[__ldg(&st.st_maxv_idx[k])];
-            const double minv = D.sm.V[__ldg(&st.st_minv_idx[k])];
-            const double v = D.sm.V[__ldg(&st.st_vol_idx[k])];
-            const bool active = D.sm.V[__ldg(&st.st_active_idx[k])] != 0.0;  // plain storages point at a constant 1
-            if (isnan(maxv) || isnan(minv) || isnan(v)) flags |= 1;
-            double l, u;
-            if (maxv == minv) { l = 0.0; u = 0.0; }
-            else if (!active) { l = -INFINITY; u = INFINITY; }
-            else {
-                const double avail = fmax(v - minv, 0.0);
-                l = -avail / days;
-                u = fmax(maxv - v, 0.0) / days;
-                type_bounds(l, u);
-            }
+        // flow formula
+        const double fl = D.sm.V[rd.a[r]], fu = D.sm.V[rd.b[r]];
+        const bool fnan = isnan(fl) || isnan(fu);
+        // storage formula
+        const double maxv = D.sm.V[rd.maxv[r]], minv = D.sm.V[rd.minv[r]], v = D.sm.V[rd.vol[r]];
+        const bool active = D.sm.V[rd.act[r]] != 0.0;  // plain storages point at a constant 1
+        const bool snan = isnan(maxv) || isnan(minv) || isnan(v);
+        const double avail = fmax(v - minv, 0.0), room = fmax(maxv - v, 0.0);
+        const double sl = unit_days ? -avail : -avail / days;
+        const double su = unit_days ? room : room / days;
+        const bool is_st = rd.cls[r] == ROWC_STORAGE;
+        double l = is_st ? sl : fl, u = is_st ? su : fu;
+        type_bounds(l, u);  // clipping / FX typing is the same for both (cython_glpk.pyx:934-945,981-984)
+        const bool freed = is_st && !active, fixed0 = is_st && maxv == minv;
+        l = freed ? -INFINITY : l; u = freed ? INFINITY : u;
+        l = fixed0 ? 0.0 : l; u = fixed0 ? 0.0 : u;
+        if (rd.cls[r] != ROWC_PAD) {
+            if (is_st ? snan : fnan) flags |= 1;
             if (l > u) flags |= 2;
             D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
         }
@@ -644,25 +640,13 @@ __device__ __forceinline__ int assemble_dynamic(const DevStructure &st, Dict<G, 
     if (st.cost_dynamic) flags |= assemble_costs(st, D);
     for (int k = D.gl; k < st.n_dyn_a; k += G)
         if (isnan(D.sm.V[__ldg(&st.dyn_a_idx[k])])) flags |= 1;
-    const unsigned nanb = group_ballot<G>(flags & 1, D.mask), badb = group_ballot<G>(flags & 2, D.mask);
-    D.sync();
-    return nanb ? B200LP_ST_NAN : (badb ? B200LP_ST_INFEASIBLE : 0);
-}
-
-// static part of the flags: NaN constants / inconsistent constant bounds
-template <int G, int RPL, int NC>
-__device__ __forceinline__ int static_flags(const DevStructure &st, Dict<G, RPL, NC> &D, const RowDesc<RPL> &rd) {
-    int flags = 0;
-#pragma unroll
-    for (int r = 0; r < RPL; r++) {
-        if (rd.cls[r] == ROWC_STATIC) {
-            const double l = D.sm.V[rd.a[r]], u = D.sm.V[rd.b[r]];
-            if (isnan(l) || isnan(u)) flags |= 1;
-            const int i = r * G + D.gl;
-            if (D.sm.LO[1 + st.n + i] > D.sm.HI[1 + st.n + i]) flags |= 2;
-        }
+    int status = 0;
+    if (group_ballot<G>(flags, D.gmask())) {  // rare
+        const unsigned nanb = group_ballot<G>(flags & 1, D.gmask());
+        status = nanb ? B200LP_ST_NAN : B200LP_ST_INFEASIBLE;
     }
-    return flags;
+    D.sync();
+    return status;
 }
 
 // (a7) warm-started solve with the oracle's retry ladder (role of retry_solve, cython_glpk.pyx:1034-1042)
@@ -699,7 +683,8 @@ __device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC>
 // (a8) primal values of the columns into sm.x and the activities of the rows into sm.ract
 template <int G, int RPL, int NC>
 __device__ __forceinline__ void extract_solution(Dict<G, RPL, NC> &D) {
-    D.basic_values();
+    // D.beta is current: solve() returns B200LP_ST_OPTIMAL right after basic_values() with the final
+    // non-basic values (the oracle recomputes it from the same inputs: identical bits)
     const int n = D.n;
     for (int j = D.gl; j < NC; j += G) {
         const int v = D.sm.nb[j];
@@ -759,7 +744,7 @@ __device__ __forceinline__ void store_state(const DevState &state, Dict<G, RPL, 
 // One timestep for all scenarios (the per-timestep Solver.solve path).
 // ------------------------------------------------------------------------------------------------
 template <int G, int RPL, int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (RPL == 1 ? 3 : 1))
 lp_step_kernel(const DevStructure st, const DevState state, const int S, const double days,
                const double *__restrict__ slots, double *__restrict__ node_flow, double *__restrict__ col_flow,
                double *__restrict__ objective) {
@@ -775,11 +760,12 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
 
     for (int k = gl; k < st.n_slots; k += G) D.sm.V[k] = slots[(size_t)k * S + sidx];
     for (int k = gl; k < st.n_storage; k += G) D.sm.V[st.vol_base + k] = state.vol[(size_t)k * S + sidx];
+    D.sync();
     RowDesc<RPL> rd;
     prepare_static(st, D, rd);
-    int flags = static_flags(st, D, rd);
+    int flags = 0;
     if (!st.cost_dynamic) flags |= assemble_costs(st, D);
-    int status = assemble_dynamic(st, D, rd, days, flags);
+    int status = assemble_rows(st, D, rd, days, flags);
 
     int *meta = state.meta + (size_t)sidx * 4;
     int refactors = 0;
@@ -917,7 +903,7 @@ struct TableDesc {
 };
 
 template <int G, int RPL, int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (RPL == 1 ? 3 : 1))
 lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, const int S, const int t0,
               const int nsteps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -944,9 +930,10 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         V[st.vol_base + k] = state.vol[(size_t)k * S + sidx];
         V[st.pc_base + k] = pg.pc[(size_t)k * S + sidx];
     }
+    D.sync();
     RowDesc<RPL> rd;
     prepare_static(st, D, rd);
-    int sflags = static_flags(st, D, rd);
+    int sflags = 0;
     if (!st.cost_dynamic) sflags |= assemble_costs(st, D);
     D.sync();
 
@@ -970,14 +957,19 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         }
         pf[u] = td[u].dst >= 0 ? td[u].at(t0) : 0.0;
     }
-    // recorder owned by this lane (recorders beyond G are handled by the generic loop below)
+    // recorder owned by this lane (recorders beyond G are handled by the generic loop below).
+    // Per-scenario accumulators stay in a register for the whole launch.
     int rk = 0, rrow = -1, ridx = 0, rsrc = 0, rbeg = 0, rend = 0;
-    double rfac = 1.0;
-    double *rout = nullptr;
+    double rfac = 1.0, racc = 0.0;
+    double *rout = nullptr;   // array kinds: next element to write; others: the accumulator's home
+    bool r_array = false;
     if (gl < pg.n_recorders) {
         rk = __ldg(&pg.rec_kind[gl]); rrow = __ldg(&pg.rec_row[gl]); ridx = __ldg(&pg.rec_idx[gl]);
         rsrc = __ldg(&pg.rec_src[gl]); rbeg = __ldg(&pg.rec_indptr[gl]); rend = __ldg(&pg.rec_indptr[gl + 1]);
-        rfac = __ldg(&pg.rec_factor[gl]); rout = pg.rec_out[gl];
+        rfac = __ldg(&pg.rec_factor[gl]);
+        r_array = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
+        rout = pg.rec_out[gl] + (r_array ? (size_t)t0 * S + sidx : (size_t)sidx);
+        if (!r_array) racc = *rout;
     }
     // storage owned by this lane
     int sk = -1, s_row = 0, s_max = 0, s_min = 0, s_act = 0, s_beg = 0, s_end = 0;
@@ -986,12 +978,13 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         s_max = __ldg(&st.st_maxv_idx[gl]); s_min = __ldg(&st.st_minv_idx[gl]); s_act = __ldg(&st.st_active_idx[gl]);
         s_beg = __ldg(&pg.stflow_indptr[gl]); s_end = __ldg(&pg.stflow_indptr[gl + 1]);
     }
+    const double *days_p = pg.ts_days + t0;
 
     int status = B200LP_ST_OPTIMAL;
     int t = t0;
 #pragma unroll 1
     for (; t < t0 + nsteps; t++) {
-        const double days = __ldg(&pg.ts_days[t]);
+        const double days = __ldg(days_p++);
         // ---- before(): parameters -------------------------------------------------------------
 #pragma unroll
         for (int u = 0; u < MAXPF; u++) {
@@ -1000,14 +993,16 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                 if (t + 1 < t0 + nsteps) pf[u] = td[u].at(t + 1);
             }
         }
-        for (int j = gl + MAXPF * G; j < pg.n_table_ops; j += G) {  // more table ops than prefetch slots
-            const int tb = __ldg(&pg.tab_table[j]);
-            const int ax = __ldg(&pg.table_axis[tb]);
-            const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
-            TableDesc q;
-            q.ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
-            q.rows = __ldg(&pg.table_rows[tb]); q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
-            V[__ldg(&pg.tab_dst[j])] = q.at(t);
+        if (pg.n_table_ops > MAXPF * G) {
+            for (int j = gl + MAXPF * G; j < pg.n_table_ops; j += G) {  // more table ops than prefetch slots
+                const int tb = __ldg(&pg.tab_table[j]);
+                const int ax = __ldg(&pg.table_axis[tb]);
+                const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
+                TableDesc q;
+                q.ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
+                q.rows = __ldg(&pg.table_rows[tb]); q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
+                V[__ldg(&pg.tab_dst[j])] = q.at(t);
+            }
         }
         D.sync();
         if (pg.n_code > 0) {
@@ -1015,7 +1010,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             D.sync();
         }
         // ---- solve() ------------------------------------------------------------------------------
-        status = assemble_dynamic(st, D, rd, days, sflags);
+        status = assemble_rows(st, D, rd, days, sflags);
         if (status == 0) status = solve_lp(st, D, valid, npiv, refactors);
         if (status != B200LP_ST_OPTIMAL) break;
         extract_solution(D);
@@ -1032,54 +1027,78 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             V[st.vol_base + gl] = v;
             V[st.pc_base + gl] = (mxv == 0.0) ? NAN : v / mxv;
         }
-        for (int k = gl + G; k < nst; k += G) {  // more storages than lanes
-            const int kind = __ldg(&st.st_kind[k]);
-            if (kind == B200LP_ST_KIND_VIRTUAL && !(V[__ldg(&st.st_active_idx[k])] != 0.0)) continue;
-            double flow = 0.0;
-            if (kind == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[__ldg(&st.st_row[k])];
-            else
-                for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
-                    flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
-            double v = V[st.vol_base + k] + flow * days;
-            const double mxv = V[__ldg(&st.st_maxv_idx[k])], mnv = V[__ldg(&st.st_minv_idx[k])];
-            if (fabs(v - mxv) < 1e-6) v = mxv;
-            if (fabs(v - mnv) < 1e-6) v = mnv;
-            V[st.vol_base + k] = v;
-            V[st.pc_base + k] = (mxv == 0.0) ? NAN : v / mxv;
+        if (nst > G) {
+            for (int k = gl + G; k < nst; k += G) {  // more storages than lanes
+                const int kind = __ldg(&st.st_kind[k]);
+                if (kind == B200LP_ST_KIND_VIRTUAL && !(V[__ldg(&st.st_active_idx[k])] != 0.0)) continue;
+                double flow = 0.0;
+                if (kind == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[__ldg(&st.st_row[k])];
+                else
+                    for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
+                        flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+                double v = V[st.vol_base + k] + flow * days;
+                const double mxv = V[__ldg(&st.st_maxv_idx[k])], mnv = V[__ldg(&st.st_minv_idx[k])];
+                if (fabs(v - mxv) < 1e-6) v = mxv;
+                if (fabs(v - mnv) < 1e-6) v = mnv;
+                V[st.vol_base + k] = v;
+                V[st.pc_base + k] = (mxv == 0.0) ? NAN : v / mxv;
+            }
         }
         D.sync();
-        // ---- recorders -------------------------------------------------------------------------------
-        for (int r = gl; r < pg.n_recorders; r += G) {
-            int kind = rk, row = rrow, idx = ridx, src = rsrc, beg = rbeg, end = rend;
-            double f = rfac;
-            double *out = rout;
-            if (r >= G) {
-                kind = __ldg(&pg.rec_kind[r]); row = __ldg(&pg.rec_row[r]); idx = __ldg(&pg.rec_idx[r]);
-                src = __ldg(&pg.rec_src[r]); beg = __ldg(&pg.rec_indptr[r]); end = __ldg(&pg.rec_indptr[r + 1]);
-                f = __ldg(&pg.rec_factor[r]); out = pg.rec_out[r];
-            }
+        // ---- recorders (the lane's own one; selects instead of a divergent switch) ----------------------
+        if (rk != 0) {
             double value = 0.0;
-            if (row >= 0) value = D.sm.ract[row];
+            if (rrow >= 0) value = D.sm.ract[rrow];
             else
-                for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
-            const size_t ts_at = (size_t)t * S + sidx;
-            switch (kind) {
-            case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
-            case B200LP_REC_NODE_DEFICIT: out[ts_at] = V[idx] - value; break;
-            case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
-            case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
-            case B200LP_REC_STORAGE_VOLUME: out[ts_at] = V[st.vol_base + src]; break;
-            case B200LP_REC_STORAGE_PC: out[ts_at] = V[st.pc_base + src]; break;
-            case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (V[idx] - value) * days; break;
-            case B200LP_REC_TOTAL_FLOW: out[sidx] += value * f * days; break;
-            case B200LP_REC_MEAN_FLOW: out[sidx] += value * f; break;
-            case B200LP_REC_DEFICIT_FREQ: if (fabs(value - V[idx]) > 1e-6) out[sidx] += 1.0; break;
-            case B200LP_REC_MIN_VOLUME: { const double v = V[st.vol_base + src]; if (v < out[sidx]) out[sidx] = v; } break;
-            default: break;
+                for (int e = rbeg; e < rend; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
+            const double mf = V[ridx];
+            const double vv = V[st.vol_base + rsrc], pv = V[st.pc_base + rsrc];
+            if (r_array) {
+                double o;
+                if (rk == B200LP_REC_NODE_SUPPLIED) o = mf == 0.0 ? 1.0 : value / mf;
+                else if (rk == B200LP_REC_NODE_CURTAIL) o = mf == 0.0 ? 0.0 : 1.0 - value / mf;
+                else o = rk == B200LP_REC_NODE_FLOW ? value * rfac
+                       : (rk == B200LP_REC_NODE_DEFICIT ? mf - value : (rk == B200LP_REC_STORAGE_VOLUME ? vv : pv));
+                *rout = o;
+                rout += S;
+            } else {
+                const double add = rk == B200LP_REC_TOTAL_DEFICIT ? (mf - value) * days
+                                 : (rk == B200LP_REC_TOTAL_FLOW ? value * rfac * days
+                                 : (rk == B200LP_REC_MEAN_FLOW ? value * rfac
+                                 : ((rk == B200LP_REC_DEFICIT_FREQ && fabs(value - mf) > 1e-6) ? 1.0 : 0.0)));
+                racc = rk == B200LP_REC_MIN_VOLUME ? fmin(racc, vv) : racc + add;
+            }
+        }
+        if (pg.n_recorders > G) {
+            for (int r = gl + G; r < pg.n_recorders; r += G) {
+                const int kind = __ldg(&pg.rec_kind[r]), row = __ldg(&pg.rec_row[r]), idx = __ldg(&pg.rec_idx[r]);
+                const int src = __ldg(&pg.rec_src[r]), beg = __ldg(&pg.rec_indptr[r]), end = __ldg(&pg.rec_indptr[r + 1]);
+                const double f = __ldg(&pg.rec_factor[r]);
+                double *out = pg.rec_out[r];
+                double value = 0.0;
+                if (row >= 0) value = D.sm.ract[row];
+                else
+                    for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
+                const size_t ts_at = (size_t)t * S + sidx;
+                switch (kind) {
+                case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
+                case B200LP_REC_NODE_DEFICIT: out[ts_at] = V[idx] - value; break;
+                case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
+                case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+                case B200LP_REC_STORAGE_VOLUME: out[ts_at] = V[st.vol_base + src]; break;
+                case B200LP_REC_STORAGE_PC: out[ts_at] = V[st.pc_base + src]; break;
+                case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (V[idx] - value) * days; break;
+                case B200LP_REC_TOTAL_FLOW: out[sidx] += value * f * days; break;
+                case B200LP_REC_MEAN_FLOW: out[sidx] += value * f; break;
+                case B200LP_REC_DEFICIT_FREQ: if (fabs(value - V[idx]) > 1e-6) out[sidx] += 1.0; break;
+                case B200LP_REC_MIN_VOLUME: { const double v = V[st.vol_base + src]; if (v < out[sidx]) out[sidx] = v; } break;
+                default: break;
+                }
             }
         }
         D.sync();
     }
+    if (rk != 0 && !r_array) *rout = racc;
     // ---- persist ------------------------------------------------------------------------------------
     store_state(state, D, sidx, true);
     for (int k = gl; k < nst; k += G) {
