@@ -631,7 +631,7 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     (void)nargs;
     dp.n_table_ops = (int)tab_dst.size();
     dp.n_code = (int)code.size();
-    std::vector<int> rec_idx(p->n_recorders ? p->n_recorders : 1, 0);
+    std::vector<int> rec_idx(p->n_recorders ? p->n_recorders : 1, 0), rec_src(p->n_recorders ? p->n_recorders : 1, 0);
     for (int r = 0; r < p->n_recorders; r++) {
         const int kind = p->rec_kind[r];
         const bool needs_ref = kind == B200LP_REC_NODE_DEFICIT || kind == B200LP_REC_NODE_SUPPLIED || kind == B200LP_REC_NODE_CURTAIL ||
@@ -642,6 +642,7 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
         }
         const bool storage_kind = kind == B200LP_REC_STORAGE_VOLUME || kind == B200LP_REC_STORAGE_PC || kind == B200LP_REC_MIN_VOLUME;
         if (storage_kind && (p->rec_src[r] < 0 || p->rec_src[r] >= nstor)) return fail(B200LP_E_INVALID, "recorder storage index out of range");
+        rec_src[r] = storage_kind ? p->rec_src[r] : 0;  // the kernel reads V[vol_base + src] unconditionally
         if (p->rec_row[r] >= h->ds.m) return fail(B200LP_E_INVALID, "recorder row out of range");
         for (int e = p->rec_indptr[r]; e < p->rec_indptr[r + 1]; e++)
             if (p->rec_col[e] < 0 || p->rec_col[e] >= h->ds.n) return fail(B200LP_E_INVALID, "recorder column out of range");
@@ -682,7 +683,7 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     PUP(stflow_col, p->stflow_col, nst ? p->stflow_indptr[nst] : 0);
     PUP(stflow_w, p->stflow_w, nst ? p->stflow_indptr[nst] : 0);
     PUP(rec_kind, p->rec_kind, p->n_recorders);
-    PUP(rec_src, p->rec_src, p->n_recorders);
+    PUP(rec_src, rec_src.data(), p->n_recorders);
     PUP(rec_idx, rec_idx.data(), p->n_recorders);
     PUP(rec_row, p->rec_row, p->n_recorders);
     PUP(rec_indptr, p->rec_indptr, p->n_recorders + 1);
@@ -841,5 +842,11 @@ int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, doubl
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return B200LP_OK;
 }
+
+#ifdef B200LP_PHASE_TIMING
+int b200lp_debug_phase_cycles(unsigned long long *out16) {
+    return cudaMemcpyFromSymbol(out16, b200lp::g_phase_cycles, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 }  // extern "C"

@@ -37,6 +37,15 @@
 
 namespace b200lp {
 
+#ifdef B200LP_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(k) do { if (sidx == 0 && gl == 0) { const long long _c = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(_c - _pc)); _pc = _c; } } while (0)
+#define PHASE_INIT long long _pc = clock64();
+#else
+#define PHASE_MARK(k)
+#define PHASE_INIT
+#endif
+
 constexpr double TOL_PRIMAL = 1e-9;
 constexpr double TOL_DUAL = 1e-9;
 constexpr double TOL_PIVOT = 1e-9;
@@ -112,40 +121,38 @@ __device__ __forceinline__ unsigned group_ballot(int pred, unsigned mask) {
     return __ballot_sync(mask, pred) & mask;
 }
 
-// Per-group shared memory carve-up (doubles first, then ints).
+// Per-group shared memory: a fixed-layout block (compile-time offsets, so every access is one LDS/STS
+// with an immediate offset) followed by the value vector V (run-time length).  Per-column arrays are
+// padded to a multiple of G (NCP) so that "one column per lane" loops have no lane-dependent branch.
+template <int G, int RPL, int NC>
+struct GroupFixed {
+    static constexpr int ROWS = G * RPL;
+    static constexpr int NB = 1 + NC + ROWS;  // bounds arrays are indexed by variable id + 1
+    static constexpr int NCP = ((NC + G - 1) / G) * G;
+    double LO[NB], HI[NB];  // bounds of every variable (entry 0: padding variable, free)
+    double xn[NCP];         // value of each non-basic position
+    double d[NCP], dw[NCP]; // true / working reduced costs
+    double prow[NCP];       // broadcast pivot row
+    double x[NCP];          // column values by variable id
+    double cost[NCP];
+    double ract[ROWS];      // row activities by row id
+    int nb[NCP], nbstat[NCP];
+    int vstat[NCP + ROWS];  // scratch for the refactorisation
+};
+
 template <int G, int RPL, int NC>
 struct GroupSmem {
     static constexpr int ROWS = G * RPL;
-    static constexpr int NB = 1 + NC + ROWS;  // bounds arrays are indexed by variable id + 1
-    double *V;         // [n_val] slots | consts | vol | pc
-    double *LO, *HI;   // [NB] bounds of every variable (entry 0: padding variable, free)
-    double *xn;        // [NC] value of each non-basic position
-    double *d, *dw;    // [NC] true / working reduced costs
-    double *prow;      // [NC] broadcast pivot row
-    double *x;         // [NC] column values by variable id
-    double *ract;      // [ROWS] row activities by row id
-    double *cost;      // [NC]
-    int *nb, *nbstat;  // [NC]
-    int *vstat;        // [NC + ROWS] scratch for the refactorisation
+    static constexpr int NCP = GroupFixed<G, RPL, NC>::NCP;
+    GroupFixed<G, RPL, NC> *f;
+    double *V;  // [n_val + 1] slots | consts | vol | pc | one scratch entry for idle lanes
     __host__ __device__ static size_t bytes(int n_val) {
-        return sizeof(double) * (n_val + 2 * NB + 6 * NC + ROWS) + sizeof(int) * (3 * NC + ROWS) + 16;
+        return ((sizeof(GroupFixed<G, RPL, NC>) + 15) & ~(size_t)15) + sizeof(double) * (size_t)(n_val + 2);
     }
     __device__ void carve(unsigned char *base, int n_val) {
-        double *dp = reinterpret_cast<double *>(base);
-        V = dp; dp += n_val;
-        LO = dp; dp += NB;
-        HI = dp; dp += NB;
-        xn = dp; dp += NC;
-        d = dp; dp += NC;
-        dw = dp; dp += NC;
-        prow = dp; dp += NC;
-        x = dp; dp += NC;
-        ract = dp; dp += ROWS;
-        cost = dp; dp += NC;
-        int *ip = reinterpret_cast<int *>(dp);
-        nb = ip; ip += NC;
-        nbstat = ip; ip += NC;
-        vstat = ip;
+        f = reinterpret_cast<GroupFixed<G, RPL, NC> *>(base);
+        V = reinterpret_cast<double *>(base + ((sizeof(GroupFixed<G, RPL, NC>) + 15) & ~(size_t)15));
+        (void)n_val;
     }
 };
 
@@ -155,6 +162,7 @@ struct GroupSmem {
 template <int G, int RPL, int NC>
 struct Dict {
     static constexpr int ROWS = G * RPL;
+    static constexpr int NCP = GroupFixed<G, RPL, NC>::NCP;
     double T[RPL][NC];
     int head[RPL];
     double lob[RPL], hib[RPL];  // bounds of the basic variable in each owned position
@@ -172,7 +180,7 @@ struct Dict {
 
     __device__ __forceinline__ void load_basic_bounds() {
 #pragma unroll
-        for (int r = 0; r < RPL; r++) { lob[r] = sm.LO[head[r] + 1]; hib[r] = sm.HI[head[r] + 1]; }
+        for (int r = 0; r < RPL; r++) { lob[r] = sm.f->LO[head[r] + 1]; hib[r] = sm.f->HI[head[r] + 1]; }
     }
 
     __device__ __forceinline__ double col_of(int r, int q) const {
@@ -186,7 +194,7 @@ struct Dict {
     __device__ __forceinline__ void basic_values() {
         double xv[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) xv[j] = sm.xn[j];
+        for (int j = 0; j < NC; j++) xv[j] = sm.f->xn[j];
 #pragma unroll
         for (int r = 0; r < RPL; r++) {
             double acc = 0.0;
@@ -199,10 +207,10 @@ struct Dict {
     // Exchange basic position (lane pl, slot ps) with non-basic position q.  prow must already hold
     // the pivot row in shared memory.  use_dw: also carry the working reduced costs.
     __device__ __forceinline__ void pivot(int pl, int ps, int q, bool use_dw) {
-        const double inv = 1.0 / sm.prow[q];
+        const double inv = 1.0 / sm.f->prow[q];
         double pr[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) pr[j] = (j == q) ? inv : -sm.prow[j] * inv;
+        for (int j = 0; j < NC; j++) pr[j] = (j == q) ? inv : -sm.f->prow[j] * inv;
 #pragma unroll
         for (int r = 0; r < RPL; r++) {
             const bool is_piv = (gl == pl) && (r == ps);
@@ -214,8 +222,8 @@ struct Dict {
             }
         }
         // reduced-cost rows, one column per lane
-        const double fd = sm.d[q], fw = sm.dw[q];
-        const int vin = sm.nb[q];
+        const double fd = sm.f->d[q], fw = sm.f->dw[q];
+        const int vin = sm.f->nb[q];
         int vout = 0;
         {
             int hv = 0;
@@ -224,17 +232,17 @@ struct Dict {
             vout = __shfl_sync(gmask(), hv, pl, G);
         }
         sync();
-        for (int j = gl; j < NC; j += G) {
-            const double prj = (j == q) ? inv : -sm.prow[j] * inv;
-            sm.d[j] = (j == q) ? fd * inv : fma(fd, prj, sm.d[j]);
-            if (use_dw) sm.dw[j] = (j == q) ? fw * inv : fma(fw, prj, sm.dw[j]);
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            const double prj = (j == q) ? inv : -sm.f->prow[j] * inv;
+            sm.f->d[j] = (j == q) ? fd * inv : fma(fd, prj, sm.f->d[j]);
+            if (use_dw) sm.f->dw[j] = (j == q) ? fw * inv : fma(fw, prj, sm.f->dw[j]);
         }
         if (gl == pl) {
 #pragma unroll
             for (int r = 0; r < RPL; r++)
                 if (r == ps) head[r] = vin;
         }
-        if (gl == 0) sm.nb[q] = vout;
+        if (gl == 0) sm.f->nb[q] = vout;
         pivots++;
         sync();
     }
@@ -246,7 +254,7 @@ struct Dict {
             for (int r = 0; r < RPL; r++)
                 if (r == ps) {
 #pragma unroll
-                    for (int j = 0; j < NC; j++) sm.prow[j] = T[r][j];
+                    for (int j = 0; j < NC; j++) sm.f->prow[j] = T[r][j];
                 }
         }
         sync();
@@ -260,7 +268,7 @@ struct Dict {
 #pragma unroll
         for (int r = 0; r < RPL; r++) {
             const int v = head[r];
-            const double c = (v >= 0 && v < n) ? sm.cost[v] : 0.0;
+            const double c = (v >= 0 && v < n) ? sm.f->cost[v] : 0.0;
 #pragma unroll
             for (int j = 0; j < NC; j++) part[j] = fma(c, T[r][j], part[j]);
         }
@@ -270,18 +278,18 @@ struct Dict {
             for (int off = G / 2; off > 0; off >>= 1) part[j] += __shfl_xor_sync(gmask(), part[j], off, G);
         }
         sync();
-        for (int j = gl; j < NC; j += G) {
-            const int v = sm.nb[j];
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            const int v = sm.f->nb[j];
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < NC; k++) acc = (k == j) ? part[k] : acc;
-            sm.d[j] = ((v >= 0 && v < n) ? sm.cost[v] : 0.0) + acc;
+            sm.f->d[j] = ((v >= 0 && v < n) ? sm.f->cost[v] : 0.0) + acc;
         }
         sync();
     }
 
     __device__ __forceinline__ void slack_basis() {
-        for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.nbstat[j] = j < n ? VS_NL : VS_NS; }
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) { sm.f->nb[j] = j < n ? j : -1; sm.f->nbstat[j] = j < n ? VS_NL : VS_NS; }
 #pragma unroll
         for (int r = 0; r < RPL; r++) { const int i = r * G + gl; head[r] = i < m ? n + i : -1; }
         sync();
@@ -291,14 +299,14 @@ struct Dict {
     // in the oracle).  Returns 0, or -1 if singular.
     __device__ __forceinline__ int refactor(const DevStructure &st) {
         // record the wanted status of every variable
-        for (int j = gl; j < NC; j += G) {
-            const int v = sm.nb[j];
-            if (v >= 0) sm.vstat[v < n ? v : NC + (v - n)] = sm.nbstat[j];
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            const int v = sm.f->nb[j];
+            if (v >= 0) sm.f->vstat[v < n ? v : NCP + (v - n)] = sm.f->nbstat[j];
         }
 #pragma unroll
         for (int r = 0; r < RPL; r++) {
             const int v = head[r];
-            if (v >= 0) sm.vstat[v < n ? v : NC + (v - n)] = VS_BASIC;
+            if (v >= 0) sm.f->vstat[v < n ? v : NCP + (v - n)] = VS_BASIC;
         }
         sync();
         // slack dictionary T = A (with this scenario's dynamic coefficients)
@@ -321,18 +329,18 @@ struct Dict {
                     T[r][j] = (mine && r == row / G && j == col) ? T[r][j] + delta : T[r][j];
             }
         }
-        for (int j = gl; j < NC; j += G) { sm.nb[j] = j < n ? j : -1; sm.d[j] = 0.0; }
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) { sm.f->nb[j] = j < n ? j : -1; sm.f->d[j] = 0.0; }
         sync();
         int ok = 0;
 #pragma unroll 1
         for (int q = 0; q < n; q++) {
-            if (sm.vstat[q] != VS_BASIC) continue;
+            if (sm.f->vstat[q] != VS_BASIC) continue;
             double best = TOL_PIVOT; int bi = -1, aux = 0;
 #pragma unroll
             for (int r = 0; r < RPL; r++) {
                 const int v = head[r];
                 if (v < n) continue;  // padding (-1) or a structural already pivoted in
-                if (sm.vstat[NC + (v - n)] == VS_BASIC) continue;
+                if (sm.f->vstat[NCP + (v - n)] == VS_BASIC) continue;
                 const double a = fabs(col_of(r, q));
                 if (a > best) { best = a; bi = r * G + gl; }
             }
@@ -345,9 +353,9 @@ struct Dict {
             pivots = save;
         }
         // statuses of the non-basic positions
-        for (int j = gl; j < NC; j += G) {
-            const int v = sm.nb[j];
-            sm.nbstat[j] = v < 0 ? VS_NS : sm.vstat[v < n ? v : NC + (v - n)];
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            const int v = sm.f->nb[j];
+            sm.f->nbstat[j] = v < 0 ? VS_NS : sm.f->vstat[v < n ? v : NCP + (v - n)];
         }
         sync();
         return ok;
@@ -357,10 +365,10 @@ struct Dict {
     // written with selects: all lanes follow one instruction stream
     __device__ __forceinline__ int place_nonbasics() {
         int infeas = 0;
-        for (int j = gl; j < NC; j += G) {
-            const int v = sm.nb[j];
-            const double lo = sm.LO[v + 1], hi = sm.HI[v + 1], dj = sm.d[j];
-            const int s0 = sm.nbstat[j];
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            const int v = sm.f->nb[j];
+            const double lo = sm.f->LO[v + 1], hi = sm.f->HI[v + 1], dj = sm.f->d[j];
+            const int s0 = sm.f->nbstat[j];
             const bool lo_fin = lo > -INFINITY, hi_fin = hi < INFINITY, fx = lo == hi;
             const bool dpos = dj > TOL_DUAL, dneg = dj < -TOL_DUAL;
             const int s_box = dpos ? VS_NL : (dneg ? VS_NU : ((s0 == VS_NL || s0 == VS_NU) ? s0 : VS_NL));
@@ -370,8 +378,8 @@ struct Dict {
             double xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
             if (v < 0) { s = VS_NS; xv = 0.0; }
             infeas |= (!fx && bad && v >= 0) ? 1 : 0;
-            sm.nbstat[j] = s;
-            sm.xn[j] = xv;
+            sm.f->nbstat[j] = s;
+            sm.f->xn[j] = xv;
         }
         infeas = group_ballot<G>(infeas, gmask()) != 0u;
         sync();
@@ -380,14 +388,14 @@ struct Dict {
 
     // working reduced costs of the (possibly cost-shifted) dual phase
     __device__ __forceinline__ void init_dw(int shifted) {
-        for (int j = gl; j < NC; j += G) {
-            double w = sm.d[j];
+        _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+            double w = sm.f->d[j];
             if (shifted) {
-                const int s = sm.nbstat[j];
+                const int s = sm.f->nbstat[j];
                 if ((s == VS_NL && w < -TOL_DUAL) || (s == VS_NU && w > TOL_DUAL) || (s == VS_NF && fabs(w) > TOL_DUAL))
                     w = 0.0;
             }
-            sm.dw[j] = w;
+            sm.f->dw[j] = w;
         }
         sync();
     }
@@ -430,29 +438,29 @@ struct Dict {
                 publish_row(pl, ps);
                 // ---- dual ratio test ------------------------------------------------------------
                 double rmin = INFINITY;
-                for (int j = gl; j < NC; j += G) {
-                    const int s = sm.nbstat[j];
-                    const double a = sm.prow[j] * (double)dir;
+                _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+                    const int s = sm.f->nbstat[j];
+                    const double a = sm.f->prow[j] * (double)dir;
                     bool ok = false;
                     if (s == VS_NL) ok = a > TOL_PIVOT;
                     else if (s == VS_NU) ok = a < -TOL_PIVOT;
                     else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
-                    if (ok) rmin = fmin(rmin, fabs(sm.dw[j]) / fabs(a));
+                    if (ok) rmin = fmin(rmin, fabs(sm.f->dw[j]) / fabs(a));
                 }
                 rmin = group_min<G>(rmin, gmask());
                 if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
                 const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
                 double amax = -1.0; int aux = 0;
                 q = -1;
-                for (int j = gl; j < NC; j += G) {
-                    const int s = sm.nbstat[j];
-                    const double a = sm.prow[j] * (double)dir;
+                _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+                    const int s = sm.f->nbstat[j];
+                    const double a = sm.f->prow[j] * (double)dir;
                     bool ok = false;
                     if (s == VS_NL) ok = a > TOL_PIVOT;
                     else if (s == VS_NU) ok = a < -TOL_PIVOT;
                     else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
                     if (!ok) continue;
-                    if (fabs(sm.dw[j]) / fabs(a) > thr) continue;
+                    if (fabs(sm.f->dw[j]) / fabs(a) > thr) continue;
                     const double key = bland ? 1.0 : fabs(a);
                     if (q < 0 || key > amax) { amax = key; q = j; }
                 }
@@ -462,9 +470,9 @@ struct Dict {
                 // ---- entering variable: largest dual infeasibility -----------------------------
                 double worst = -1.0; int dir = 0;
                 q = -1;
-                for (int j = gl; j < NC; j += G) {
-                    const int s = sm.nbstat[j];
-                    const double dj = sm.d[j];
+                _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
+                    const int s = sm.f->nbstat[j];
+                    const double dj = sm.f->d[j];
                     int dd = 0;
                     if ((s == VS_NL || s == VS_NF) && dj < -TOL_DUAL) dd = +1;
                     else if ((s == VS_NU || s == VS_NF) && dj > TOL_DUAL) dd = -1;
@@ -475,8 +483,8 @@ struct Dict {
                 }
                 group_argmax<G>(worst, q, dir, gmask());
                 if (q < 0) return B200LP_ST_OPTIMAL;
-                const int vin = sm.nb[q];
-                const double inlo = sm.LO[vin + 1], inhi = sm.HI[vin + 1];
+                const int vin = sm.f->nb[q];
+                const double inlo = sm.f->LO[vin + 1], inhi = sm.f->HI[vin + 1];
                 double tmin = inhi - inlo;
                 if (!(tmin < INFINITY)) tmin = INFINITY;
                 // ---- primal ratio test down column q ---------------------------------------------
@@ -496,8 +504,8 @@ struct Dict {
                 if (step_min == INFINITY && tmin == INFINITY) return B200LP_ST_UNBOUNDED;
                 if (tmin <= step_min) {
                     if (gl == 0) {
-                        sm.nbstat[q] = dir > 0 ? VS_NU : VS_NL;
-                        sm.xn[q] = dir > 0 ? inhi : inlo;
+                        sm.f->nbstat[q] = dir > 0 ? VS_NU : VS_NL;
+                        sm.f->xn[q] = dir > 0 ? inhi : inlo;
                     }
                     sync();
                     continue;
@@ -523,8 +531,8 @@ struct Dict {
             vhi = __shfl_sync(gmask(), vhi, pl, G);
             pivot(pl, ps, q, phase == 0);
             if (gl == 0) {
-                sm.nbstat[q] = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
-                sm.xn[q] = to_upper ? vhi : vlo;
+                sm.f->nbstat[q] = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
+                sm.f->xn[q] = to_upper ? vhi : vlo;
             }
             sync();
             load_basic_bounds();
@@ -545,6 +553,11 @@ __device__ __forceinline__ void init_group(Dict<G, RPL, NC> &D, const DevStructu
     D.n = st.n; D.m = st.m; D.pivots = 0;
     const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
     D.sm.carve(smem_raw + gbytes * gib, st.n_val);
+    for (int j = NC + D.gl; j < D.NCP; j += G) {  // padding columns: never eligible, all zeros
+        D.sm.f->nb[j] = -1; D.sm.f->nbstat[j] = VS_NS;
+        D.sm.f->d[j] = 0.0; D.sm.f->dw[j] = 0.0; D.sm.f->prow[j] = 0.0; D.sm.f->xn[j] = 0.0;
+        D.sm.f->x[j] = 0.0; D.sm.f->cost[j] = 0.0;
+    }
 }
 
 // Row descriptors of the rows a lane owns (registers, loaded once per launch).  Every lane evaluates
@@ -563,8 +576,8 @@ __device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, R
     for (int k = gl; k < st.n_consts; k += G) D.sm.V[st.n_slots + k] = __ldg(&st.consts[k]);
     for (int v = gl; v < 1 + NC; v += G) {  // entry 0 (padding variable) and the columns x >= 0
         const bool col = v >= 1 && v <= n;
-        D.sm.LO[v] = col ? 0.0 : -INFINITY;
-        D.sm.HI[v] = INFINITY;
+        D.sm.f->LO[v] = col ? 0.0 : -INFINITY;
+        D.sm.f->HI[v] = INFINITY;
     }
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
@@ -580,7 +593,7 @@ __device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, R
             rd.a[r] = rd.b[r] = 0;
         }
         if (rd.cls[r] == ROWC_PAD) {  // padding rows are free
-            D.sm.LO[1 + n + i] = -INFINITY; D.sm.HI[1 + n + i] = INFINITY;
+            D.sm.f->LO[1 + n + i] = -INFINITY; D.sm.f->HI[1 + n + i] = INFINITY;
         }
     }
     D.sync();
@@ -598,7 +611,7 @@ __device__ __forceinline__ int assemble_costs(const DevStructure &st, Dict<G, RP
             if (isnan(acc)) nan_seen = 1;
             if (st.cost_clip && fabs(acc) < 1e-8) acc = 0.0;
         }
-        D.sm.cost[j] = acc;
+        D.sm.f->cost[j] = acc;
     }
     return nan_seen;
 }
@@ -634,7 +647,7 @@ __device__ __forceinline__ int assemble_rows(const DevStructure &st, Dict<G, RPL
         if (rd.cls[r] != ROWC_PAD) {
             if (is_st ? snan : fnan) flags |= 1;
             if (l > u) flags |= 2;
-            D.sm.LO[1 + n + i] = l; D.sm.HI[1 + n + i] = u;
+            D.sm.f->LO[1 + n + i] = l; D.sm.f->HI[1 + n + i] = u;
         }
     }
     if (st.cost_dynamic) flags |= assemble_costs(st, D);
@@ -680,22 +693,22 @@ __device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC>
     return status;
 }
 
-// (a8) primal values of the columns into sm.x and the activities of the rows into sm.ract
+// (a8) primal values of the columns into sm.f->x and the activities of the rows into sm.f->ract
 template <int G, int RPL, int NC>
 __device__ __forceinline__ void extract_solution(Dict<G, RPL, NC> &D) {
     // D.beta is current: solve() returns B200LP_ST_OPTIMAL right after basic_values() with the final
     // non-basic values (the oracle recomputes it from the same inputs: identical bits)
     const int n = D.n;
-    for (int j = D.gl; j < NC; j += G) {
-        const int v = D.sm.nb[j];
-        if (v >= n) D.sm.ract[v - n] = D.sm.xn[j];
-        else if (v >= 0) D.sm.x[v] = D.sm.xn[j];
+    _Pragma("unroll") for (int j = D.gl; j < D.NCP; j += G) {
+        const int v = D.sm.f->nb[j];
+        if (v >= n) D.sm.f->ract[v - n] = D.sm.f->xn[j];
+        else if (v >= 0) D.sm.f->x[v] = D.sm.f->xn[j];
     }
 #pragma unroll
     for (int r = 0; r < RPL; r++) {
         const int v = D.head[r];
-        if (v >= n) D.sm.ract[v - n] = D.beta[r];
-        else if (v >= 0) D.sm.x[v] = D.beta[r];
+        if (v >= n) D.sm.f->ract[v - n] = D.beta[r];
+        else if (v >= 0) D.sm.f->x[v] = D.beta[r];
     }
     D.sync();
 }
@@ -714,9 +727,9 @@ __device__ __forceinline__ void load_state(const DevState &state, Dict<G, RPL, N
         }
     }
     for (int j = D.gl; j < NC; j += G) {
-        D.sm.nb[j] = state.nb[(size_t)sidx * NC + j];
-        D.sm.nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
-        D.sm.d[j] = state.d[(size_t)sidx * NC + j];
+        D.sm.f->nb[j] = state.nb[(size_t)sidx * NC + j];
+        D.sm.f->nbstat[j] = state.nbstat[(size_t)sidx * NC + j];
+        D.sm.f->d[j] = state.d[(size_t)sidx * NC + j];
     }
 }
 
@@ -734,9 +747,9 @@ __device__ __forceinline__ void store_state(const DevState &state, Dict<G, RPL, 
         }
     }
     for (int j = D.gl; j < NC; j += G) {
-        state.nb[(size_t)sidx * NC + j] = D.sm.nb[j];
-        state.nbstat[(size_t)sidx * NC + j] = D.sm.nbstat[j];
-        state.d[(size_t)sidx * NC + j] = D.sm.d[j];
+        state.nb[(size_t)sidx * NC + j] = D.sm.f->nb[j];
+        state.nbstat[(size_t)sidx * NC + j] = D.sm.f->nbstat[j];
+        state.d[(size_t)sidx * NC + j] = D.sm.f->d[j];
     }
 }
 
@@ -790,17 +803,17 @@ lp_step_kernel(const DevStructure st, const DevState state, const int S, const d
 
     extract_solution(D);
     if (col_flow)
-        for (int j = gl; j < n; j += G) col_flow[(size_t)j * S + sidx] = D.sm.x[j];
+        for (int j = gl; j < n; j += G) col_flow[(size_t)j * S + sidx] = D.sm.f->x[j];
     if (objective && gl == 0) {
         double acc = 0.0;
-        for (int j = 0; j < n; j++) acc = fma(D.sm.cost[j], D.sm.x[j], acc);
+        for (int j = 0; j < n; j++) acc = fma(D.sm.f->cost[j], D.sm.f->x[j], acc);
         objective[sidx] = acc;
     }
     if (node_flow) {
         for (int v = gl; v < st.N; v += G) {
             double acc = 0.0;
             for (int k = __ldg(&st.flow_indptr[v]); k < __ldg(&st.flow_indptr[v + 1]); k++)
-                acc = fma(__ldg(&st.flow_w[k]), D.sm.x[__ldg(&st.flow_col[k])], acc);
+                acc = fma(__ldg(&st.flow_w[k]), D.sm.f->x[__ldg(&st.flow_col[k])], acc);
             node_flow[(size_t)v * S + sidx] = acc;
         }
     }
@@ -944,7 +957,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
 #pragma unroll
     for (int u = 0; u < MAXPF; u++) {
         const int j = gl + u * G;
-        td[u].ptr = pg.table_data; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = -1;
+        td[u].ptr = pg.ts_days; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = st.n_val;  // scratch
         if (j < pg.n_table_ops) {
             const int tb = __ldg(&pg.tab_table[j]);
             const int ax = __ldg(&pg.table_axis[tb]);
@@ -955,7 +968,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             td[u].off = __ldg(&pg.tab_offset[j]);
             td[u].dst = __ldg(&pg.tab_dst[j]);
         }
-        pf[u] = td[u].dst >= 0 ? td[u].at(t0) : 0.0;
+        pf[u] = td[u].at(t0);
     }
     // recorder owned by this lane (recorders beyond G are handled by the generic loop below).
     // Per-scenario accumulators stay in a register for the whole launch.
@@ -982,16 +995,15 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
 
     int status = B200LP_ST_OPTIMAL;
     int t = t0;
+    PHASE_INIT
 #pragma unroll 1
     for (; t < t0 + nsteps; t++) {
         const double days = __ldg(days_p++);
         // ---- before(): parameters -------------------------------------------------------------
 #pragma unroll
-        for (int u = 0; u < MAXPF; u++) {
-            if (td[u].dst >= 0) {
-                V[td[u].dst] = pf[u];
-                if (t + 1 < t0 + nsteps) pf[u] = td[u].at(t + 1);
-            }
+        for (int u = 0; u < MAXPF; u++) {  // every lane, no branch: idle lanes target the scratch entry
+            V[td[u].dst] = pf[u];
+            pf[u] = td[u].at(t + 1);  // clamped to the table's last row
         }
         if (pg.n_table_ops > MAXPF * G) {
             for (int j = gl + MAXPF * G; j < pg.n_table_ops; j += G) {  // more table ops than prefetch slots
@@ -1005,21 +1017,27 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             }
         }
         D.sync();
+        PHASE_MARK(0);
         if (pg.n_code > 0) {
-            if (gl == 0) eval_ops(code, pg.n_code, V, st.pc_base);
+            // every lane interprets the (tiny) op list and stores the same values: no divergent region
+            eval_ops(code, pg.n_code, V, st.pc_base);
             D.sync();
         }
         // ---- solve() ------------------------------------------------------------------------------
+        PHASE_MARK(1);
         status = assemble_rows(st, D, rd, days, sflags);
+        PHASE_MARK(2);
         if (status == 0) status = solve_lp(st, D, valid, npiv, refactors);
+        PHASE_MARK(3);
         if (status != B200LP_ST_OPTIMAL) break;
         extract_solution(D);
+        PHASE_MARK(4);
         // ---- after(): storage mass balance (Storage.after, pywr/_core.pyx:1335-1361) ---------------
         if (sk >= 0 && (sk == B200LP_ST_KIND_STORAGE || V[s_act] != 0.0)) {
             double flow = 0.0;
-            if (sk == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[s_row];
+            if (sk == B200LP_ST_KIND_STORAGE) flow = D.sm.f->ract[s_row];
             else
-                for (int e = s_beg; e < s_end; e++) flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+                for (int e = s_beg; e < s_end; e++) flow = fma(__ldg(&pg.stflow_w[e]), D.sm.f->x[__ldg(&pg.stflow_col[e])], flow);
             double v = V[st.vol_base + gl] + flow * days;
             const double mxv = V[s_max], mnv = V[s_min];
             if (fabs(v - mxv) < 1e-6) v = mxv;
@@ -1032,10 +1050,10 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                 const int kind = __ldg(&st.st_kind[k]);
                 if (kind == B200LP_ST_KIND_VIRTUAL && !(V[__ldg(&st.st_active_idx[k])] != 0.0)) continue;
                 double flow = 0.0;
-                if (kind == B200LP_ST_KIND_STORAGE) flow = D.sm.ract[__ldg(&st.st_row[k])];
+                if (kind == B200LP_ST_KIND_STORAGE) flow = D.sm.f->ract[__ldg(&st.st_row[k])];
                 else
                     for (int e = __ldg(&pg.stflow_indptr[k]); e < __ldg(&pg.stflow_indptr[k + 1]); e++)
-                        flow = fma(__ldg(&pg.stflow_w[e]), D.sm.x[__ldg(&pg.stflow_col[e])], flow);
+                        flow = fma(__ldg(&pg.stflow_w[e]), D.sm.f->x[__ldg(&pg.stflow_col[e])], flow);
                 double v = V[st.vol_base + k] + flow * days;
                 const double mxv = V[__ldg(&st.st_maxv_idx[k])], mnv = V[__ldg(&st.st_minv_idx[k])];
                 if (fabs(v - mxv) < 1e-6) v = mxv;
@@ -1045,12 +1063,13 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             }
         }
         D.sync();
+        PHASE_MARK(5);
         // ---- recorders (the lane's own one; selects instead of a divergent switch) ----------------------
         if (rk != 0) {
             double value = 0.0;
-            if (rrow >= 0) value = D.sm.ract[rrow];
+            if (rrow >= 0) value = D.sm.f->ract[rrow];
             else
-                for (int e = rbeg; e < rend; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
+                for (int e = rbeg; e < rend; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.f->x[__ldg(&pg.rec_col[e])], value);
             const double mf = V[ridx];
             const double vv = V[st.vol_base + rsrc], pv = V[st.pc_base + rsrc];
             if (r_array) {
@@ -1076,9 +1095,9 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                 const double f = __ldg(&pg.rec_factor[r]);
                 double *out = pg.rec_out[r];
                 double value = 0.0;
-                if (row >= 0) value = D.sm.ract[row];
+                if (row >= 0) value = D.sm.f->ract[row];
                 else
-                    for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.x[__ldg(&pg.rec_col[e])], value);
+                    for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.f->x[__ldg(&pg.rec_col[e])], value);
                 const size_t ts_at = (size_t)t * S + sidx;
                 switch (kind) {
                 case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
@@ -1097,6 +1116,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             }
         }
         D.sync();
+        PHASE_MARK(6);
     }
     if (rk != 0 && !r_array) *rout = racc;
     // ---- persist ------------------------------------------------------------------------------------
@@ -1106,7 +1126,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         pg.pc[(size_t)k * S + sidx] = V[st.pc_base + k];
     }
     if (status == B200LP_ST_OPTIMAL)
-        for (int j = gl; j < n; j += G) pg.last_x[(size_t)j * S + sidx] = D.sm.x[j];
+        for (int j = gl; j < n; j += G) pg.last_x[(size_t)j * S + sidx] = D.sm.f->x[j];
     if (gl == 0) {
         meta[0] = valid; meta[1] = npiv; meta[2] = status;
         if (D.pivots) atomicAdd(&state.counters[0], (unsigned long long)D.pivots);
