@@ -1,0 +1,94 @@
+"""GPU tests (-m gpu) of the drop-in boundary as a Pywr user sees it: the reference framework
+(baseline/_ref) drives the CUDA engine through its own solver API — Model(solver="b200").run() —
+and through the device-resident run; results are compared with the same model solved by the CPU
+oracle plugged in the same way."""
+import numpy as np
+import pytest
+
+from fixtures_util import rel_diff
+
+pytestmark = pytest.mark.gpu
+pywr = pytest.importorskip("pywr")
+
+
+def _recorder_values(model):
+    out = {}
+    for rec in model.recorders:
+        if type(rec).__name__ == "AggregatedRecorder":
+            out[rec.name] = np.array([rec.aggregated_value()])
+        elif hasattr(rec, "data"):
+            out[rec.name] = np.array(rec.data)
+        else:
+            out[rec.name] = np.array(rec.values())
+    return out
+
+
+@pytest.mark.parametrize("name,S", [("thames", 7), ("two_reservoir", 33)])
+def test_model_run_with_b200_solver_matches_oracle_solver(name, S):
+    import oracle.pywr_oracle_solver  # noqa: F401
+    import pywr_b200  # noqa: F401  (registers "b200")
+    from benchmarks.workloads import build_model
+
+    m_cpu = build_model(name, S, years=1, solver="oracle")
+    m_gpu = build_model(name, S, years=1, solver="b200")
+    assert m_gpu.solver.name == "b200"
+    r_cpu = m_cpu.run()
+    r_gpu = m_gpu.run()
+    assert r_gpu.timestep.index == r_cpu.timestep.index == 364          # schedule: bit-exact
+    assert r_gpu.num_scenarios == S and r_gpu.solver_name == "b200"
+    assert r_gpu.solver_stats["number_of_rows"] == r_cpu.solver_stats["number_of_rows"] > 0
+    a, b = _recorder_values(m_gpu), _recorder_values(m_cpu)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert rel_diff(a[k], b[k]) <= 1e-9, k
+    for n_gpu, n_cpu in zip(m_gpu.nodes, m_cpu.nodes):
+        assert rel_diff(n_gpu.flow, n_cpu.flow) <= 1e-9, n_gpu.name
+    st = m_gpu.solver._engine.stats()
+    assert st["kernel_launches"] >= 365 and st["h2d_bytes"] > 0
+
+
+@pytest.mark.parametrize("name,S", [("thames", 64), ("two_reservoir", 100)])
+def test_run_on_device_matches_host_run(name, S):
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from benchmarks.workloads import build_model
+    from pywr_b200.device_run import run_on_device
+
+    m_host = build_model(name, S, years=1, solver="oracle")
+    m_host.run()
+    m_dev = build_model(name, S, years=1, solver="null")
+    res = run_on_device(m_dev)
+    assert res.timesteps == 365 and res.num_scenarios == S
+    a, b = _recorder_values(m_dev), _recorder_values(m_host)
+    for k in b:
+        assert rel_diff(a[k], b[k]) <= 1e-9, k
+    for n_dev, n_host in zip(m_dev.nodes, m_host.nodes):
+        assert rel_diff(n_dev.flow, n_host.flow) <= 1e-9, n_dev.name
+        if hasattr(n_host, "volume"):
+            assert rel_diff(n_dev.volume, n_host.volume) <= 1e-9
+    df = m_dev.recorders[next(iter(b))].to_dataframe() if hasattr(m_dev.recorders[next(iter(b))], "to_dataframe") else None
+    assert df is None or df.shape[1] == S
+
+
+def test_infeasible_model_raises_like_the_reference():
+    import pywr_b200  # noqa: F401
+    from pywr.core import Input, Model, Output
+
+    model = Model(solver="b200")
+    a = Input(model, "a", min_flow=10.0, max_flow=10.0)
+    b = Output(model, "b", max_flow=5.0)
+    a.connect(b)
+    with pytest.raises(RuntimeError, match="Simplex solver failed"):
+        model.run()
+
+
+def test_nan_raises_lp_error():
+    import pywr_b200  # noqa: F401
+    from pywr.core import Input, Model, Output
+    from pywr_b200.solver import B200LPError
+
+    model = Model(solver="b200")
+    a = Input(model, "a", max_flow=float("nan"))
+    b = Output(model, "b", max_flow=5.0, cost=-1)
+    a.connect(b)
+    with pytest.raises(B200LPError):
+        model.run()
