@@ -2,6 +2,7 @@
 // device memory, host<->device copies and kernel dispatch.  No torch, no Python, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -55,7 +56,7 @@ static void run_variant(const DevStructure &st, const DevState &state, const Dev
     const int groups_per_block = block / G;
     const int grid = (S + groups_per_block - 1) / groups_per_block;
     const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
-    const size_t smem = gbytes * groups_per_block + sizeof(int) * (size_t)(pg.n_code + 4);
+    const size_t smem = gbytes * groups_per_block + sizeof(int) * (size_t)(((pg.n_code + 3) & ~3) + pg.n_fop_levels * 32 * FOP_WORDS + 4);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
         cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -199,6 +200,7 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
     ds.vol_base = s->n_slots + s->n_consts;
     ds.pc_base = ds.vol_base + s->n_storage;
     ds.n_val = ds.pc_base + s->n_storage;
+    ds.k_base = ds.n_val;
     const int n_slots = s->n_slots, n_consts = s->n_consts;
     // validate refs and resolve them to indices into the per-scenario value vector V
     auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
@@ -631,6 +633,97 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     (void)nargs;
     dp.n_table_ops = (int)tab_dst.size();
     dp.n_code = (int)code.size();
+    // ---- lane-parallel schedule of the non-table ops (falls back to the interpreter when an op does not fit)
+    std::vector<int> fop;
+    int n_levels = 0;
+    {
+        const int KB = h->ds.k_base;
+        const int G = kVariants[h->variant].G;
+        std::vector<int> slot_level(n_slots, 0);
+        struct FastOp { int level; int w[FOP_WORDS]; };
+        std::vector<FastOp> ops;
+        bool ok = true;
+        size_t pos = 0;
+        while (ok && pos < code.size()) {
+            const int kind = code[pos], dst = code[pos + 1], na = code[pos + 2];
+            const int *a = code.data() + pos + 3;
+            pos += 3 + na;
+            FastOp f{}; f.w[1] = dst;
+            std::vector<int> deps;
+            auto pad = [&](int from, int neutral) { for (int i = from; i < 6; i++) f.w[2 + i] = KB + neutral; };
+            switch (kind) {
+            case B200LP_OP_AGG: {
+                const int func = a[0], cnt = a[1];
+                if (cnt > 6 || func == B200LP_AGG_MEAN) { ok = false; break; }
+                f.w[0] = func == B200LP_AGG_PRODUCT ? FOP_PROD : func == B200LP_AGG_SUM ? FOP_SUM : func == B200LP_AGG_MIN ? FOP_MIN : FOP_MAX;
+                for (int i = 0; i < cnt; i++) { f.w[2 + i] = a[2 + i]; deps.push_back(a[2 + i]); }
+                pad(cnt, func == B200LP_AGG_PRODUCT ? K_ONE : func == B200LP_AGG_SUM ? K_ZERO : func == B200LP_AGG_MIN ? K_PINF : K_NINF);
+            } break;
+            case B200LP_OP_CONTROL_CURVE: case B200LP_OP_CC_INDEX: {
+                const int cnt = a[1];
+                if (cnt > 2) { ok = false; break; }
+                f.w[0] = FOP_CC;
+                f.w[2] = h->ds.pc_base + a[0];
+                f.w[3] = cnt >= 1 ? a[2] : KB + K_NINF;   // no curve: always the first value
+                f.w[4] = cnt >= 2 ? a[3] : KB + K_PINF;
+                for (int i = 0; i < cnt; i++) deps.push_back(a[2 + i]);
+                if (kind == B200LP_OP_CONTROL_CURVE) {
+                    const int *v = a + 2 + cnt;             // cnt + 1 values
+                    f.w[5] = v[0]; f.w[6] = cnt >= 1 ? v[1] : v[0]; f.w[7] = cnt >= 2 ? v[2] : (cnt >= 1 ? v[1] : v[0]);
+                    for (int i = 0; i <= cnt; i++) deps.push_back(v[i]);
+                } else {
+                    f.w[5] = KB + K_ZERO; f.w[6] = cnt >= 1 ? KB + K_ONE : KB + K_ZERO; f.w[7] = cnt >= 2 ? KB + K_TWO : f.w[6];
+                }
+            } break;
+            case B200LP_OP_INDEXED: {
+                const int cnt = a[1];
+                if (cnt > 4) { ok = false; break; }
+                f.w[0] = FOP_INDEXED; f.w[2] = a[0]; deps.push_back(a[0]);
+                for (int i = 0; i < 4; i++) { f.w[3 + i] = a[2 + (i < cnt ? i : cnt - 1)]; }
+                for (int i = 0; i < cnt; i++) deps.push_back(a[2 + i]);
+                f.w[7] = KB + K_ZERO;
+            } break;
+            case B200LP_OP_NEG: f.w[0] = FOP_NEG; f.w[2] = a[0]; deps.push_back(a[0]); pad(1, K_ZERO); break;
+            case B200LP_OP_MAX0: case B200LP_OP_MIN0: case B200LP_OP_DIV:
+                f.w[0] = kind == B200LP_OP_MAX0 ? FOP_MAX0 : kind == B200LP_OP_MIN0 ? FOP_MIN0 : FOP_DIV;
+                f.w[2] = a[0]; f.w[3] = a[1]; deps.push_back(a[0]); deps.push_back(a[1]); pad(2, K_ONE);
+                break;
+            default: ok = false;
+            }
+            if (!ok) break;
+            int lev = 0;
+            for (int dref : deps) if (dref < n_slots) lev = std::max(lev, slot_level[dref]);
+            // an op that reads a storage's pc / volume does so at level >= 0 too; ops writing dst raise its level
+            f.level = lev;
+            slot_level[dst] = lev + 1;
+            ops.push_back(f);
+        }
+        if (ok && !ops.empty()) {
+            int maxlev = 0;
+            for (auto &f : ops) maxlev = std::max(maxlev, f.level);
+            n_levels = maxlev + 1;
+            std::vector<int> count(n_levels, 0);
+            if (n_levels > FOP_MAXLEV) ok = false;
+            for (auto &f : ops) if (++count[f.level] > G) ok = false;
+            if (ok) {
+                fop.assign((size_t)n_levels * 32 * FOP_WORDS, 0);
+                for (int lev = 0; lev < n_levels; lev++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        int *w = fop.data() + ((size_t)lev * 32 + lane) * FOP_WORDS;
+                        w[0] = FOP_NONE; w[1] = KB + K_SCRATCH;
+                        for (int i = 2; i < FOP_WORDS; i++) w[i] = KB + K_ONE;
+                    }
+                std::fill(count.begin(), count.end(), 0);
+                for (auto &f : ops) {
+                    int *w = fop.data() + ((size_t)f.level * 32 + count[f.level]++) * FOP_WORDS;
+                    for (int i = 0; i < FOP_WORDS; i++) w[i] = f.w[i];
+                }
+            }
+        }
+        if (!ok) { n_levels = 0; fop.clear(); }
+        if (getenv("B200LP_NO_FAST_OPS")) { n_levels = 0; fop.clear(); }
+    }
+    dp.n_fop_levels = n_levels;
     std::vector<int> rec_idx(p->n_recorders ? p->n_recorders : 1, 0), rec_src(p->n_recorders ? p->n_recorders : 1, 0);
     for (int r = 0; r < p->n_recorders; r++) {
         const int kind = p->rec_kind[r];
@@ -673,6 +766,7 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     PUP(tab_table, tab_table.data(), tab_table.size());
     PUP(tab_offset, tab_offset.data(), tab_offset.size());
     PUP(code, code.data(), code.size());
+    PUP(fop, fop.data(), fop.size());
     PUP(table_rows, p->table_rows, p->n_tables);
     PUP(table_cols, p->table_cols, p->n_tables);
     PUP(table_axis, p->table_axis, p->n_tables);

@@ -59,6 +59,11 @@ constexpr int REFACTOR_PIVOTS = 40;
 
 enum : int { VS_BASIC = 1, VS_NL = 2, VS_NU = 3, VS_NF = 4, VS_NS = 5 };
 enum : int { ROWC_STATIC = 0, ROWC_FLOW = 1, ROWC_STORAGE = 2, ROWC_PAD = 3 };
+enum : int { K_SCRATCH = 0, K_ZERO = 1, K_ONE = 2, K_TWO = 3, K_PINF = 4, K_NINF = 5, K_COUNT = 6 };
+// lane-parallel "fast ops" (one op per lane and dependency level)
+enum : int { FOP_NONE = 0, FOP_PROD = 1, FOP_SUM = 2, FOP_MIN = 3, FOP_MAX = 4, FOP_CC = 5, FOP_INDEXED = 6, FOP_NEG = 7,
+             FOP_MAX0 = 8, FOP_MIN0 = 9, FOP_DIV = 10 };
+constexpr int FOP_MAXLEV = 4, FOP_WORDS = 8;  // kind, dst, a0..a5
 
 // Shared LP structure, device pointers (built by b200lp_create).  All *_idx are indices into V.
 struct DevStructure {
@@ -66,6 +71,7 @@ struct DevStructure {
     int cost_dynamic;  // some cost term is a slot: reduced costs are rebuilt every step
     int rows_cap, nc;  // padded sizes of the kernel variant in use
     int n_val, vol_base, pc_base;
+    int k_base;  // V[k_base + K_*]: scratch entry for idle lanes and built-in constants
     const double *A_dense;  // [nc][rows_cap] column-major, zero padded
     const int *row_class;   // [rows_cap] ROWC_*
     const int *row_a, *row_b;  // [rows_cap] V index of lb / ub, or (storage k, unused)
@@ -171,9 +177,9 @@ struct GroupSmem {
     static constexpr int ROWS = G * RPL;
     static constexpr int NCP = GroupFixed<G, RPL, NC>::NCP;
     GroupFixed<G, RPL, NC> *f;
-    double *V;  // [n_val + 1] slots | consts | vol | pc | one scratch entry for idle lanes
+    double *V;  // [n_val + K_COUNT] slots | consts | vol | pc | scratch + built-in constants (K_*)
     __host__ __device__ static size_t bytes(int n_val) {
-        return ((sizeof(GroupFixed<G, RPL, NC>) + 15) & ~(size_t)15) + sizeof(double) * (size_t)(n_val + 2);
+        return ((sizeof(GroupFixed<G, RPL, NC>) + 15) & ~(size_t)15) + sizeof(double) * (size_t)(n_val + K_COUNT + 1);
     }
     __device__ void carve(unsigned char *base, int n_val) {
         f = reinterpret_cast<GroupFixed<G, RPL, NC> *>(base);
@@ -626,6 +632,10 @@ template <int G, int RPL, int NC>
 __device__ __forceinline__ void prepare_static(const DevStructure &st, Dict<G, RPL, NC> &D, RowDesc<RPL> &rd) {
     const int gl = D.gl, n = st.n;
     for (int k = gl; k < st.n_consts; k += G) D.sm.V[st.n_slots + k] = __ldg(&st.consts[k]);
+    if (gl == 0) {
+        double *K = D.sm.V + st.k_base;
+        K[K_SCRATCH] = 0.0; K[K_ZERO] = 0.0; K[K_ONE] = 1.0; K[K_TWO] = 2.0; K[K_PINF] = INFINITY; K[K_NINF] = -INFINITY;
+    }
     for (int v = gl; v < 1 + NC; v += G) {  // entry 0 (padding variable) and the columns x >= 0
         const bool col = v >= 1 && v <= n;
         D.sm.f->LO[v] = col ? 0.0 : -INFINITY;
@@ -896,6 +906,9 @@ struct DevProgram {
     const int *scen_index;
     // all other ops, pre-decoded: kind, dst, nargs, args... (V indices / storage ids / small ints)
     const int *code;
+    // lane-parallel schedule of the same ops (n_fop_levels == 0: use the interpreter)
+    int n_fop_levels;
+    const int *fop;  // [n_fop_levels][32][FOP_WORDS]
     const int *stflow_indptr, *stflow_col;
     const double *stflow_w;
     const int *rec_kind, *rec_src, *rec_idx, *rec_row, *rec_indptr, *rec_col;
@@ -960,6 +973,41 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, doub
     }
 }
 
+// One dependency level of the lane-parallel op schedule: lane `gl` evaluates the op whose descriptor is
+// d[0..8) = kind, dst, a0..a5 (indices into V; unused operands point at neutral built-in constants).
+// Lanes of one level normally share a kind, so the branch on `kind` does not diverge.  Arithmetic order is the
+// interpreter's (and the reference's: AggregatedParameter multiplies / adds in parameter order).
+__device__ __forceinline__ void eval_fast_op(const int *d, double *V) {
+    const int kind = d[0];
+    if (kind == FOP_NONE) return;  // idle lane at this level
+    const double a0 = V[d[2]], a1 = V[d[3]], a2 = V[d[4]], a3 = V[d[5]], a4 = V[d[6]], a5 = V[d[7]];
+    double r;
+    if (kind == FOP_CC) {  // a0 = pc, a1/a2 = curves (descending), a3..a5 = values
+        const double c = clamp_pc(a0);
+        r = c >= a1 ? a3 : (c >= a2 ? a4 : a5);
+    } else if (kind == FOP_PROD) {
+        r = ((((a0 * a1) * a2) * a3) * a4) * a5;
+    } else if (kind == FOP_INDEXED) {  // a0 = index (as double), a1..a4 = choices (padded with the last one)
+        const int ix = (int)a0;
+        r = ix <= 0 ? a1 : (ix == 1 ? a2 : (ix == 2 ? a3 : a4));
+    } else if (kind == FOP_SUM) {
+        r = ((((a0 + a1) + a2) + a3) + a4) + a5;
+    } else if (kind == FOP_MAX) {
+        r = -INFINITY; r = a0 > r ? a0 : r; r = a1 > r ? a1 : r; r = a2 > r ? a2 : r; r = a3 > r ? a3 : r; r = a4 > r ? a4 : r; r = a5 > r ? a5 : r;
+    } else if (kind == FOP_MIN) {
+        r = INFINITY; r = a0 < r ? a0 : r; r = a1 < r ? a1 : r; r = a2 < r ? a2 : r; r = a3 < r ? a3 : r; r = a4 < r ? a4 : r; r = a5 < r ? a5 : r;
+    } else if (kind == FOP_NEG) {
+        r = -a0;
+    } else if (kind == FOP_MAX0) {
+        r = a0 > a1 ? a0 : a1;
+    } else if (kind == FOP_MIN0) {
+        r = a0 < a1 ? a0 : a1;
+    } else {
+        r = a0 / a1;
+    }
+    V[d[1]] = r;
+}
+
 // one table op owned by a lane: value(t) = ptr[clamp(t + off) * stride]
 struct TableDesc {
     const double *ptr;
@@ -986,6 +1034,8 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
     const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
     int *code = reinterpret_cast<int *>(smem_raw + gbytes * groups_per_block);
     for (int k = threadIdx.x; k < pg.n_code; k += blockDim.x) code[k] = __ldg(&pg.code[k]);
+    int *fop = code + ((pg.n_code + 3) & ~3);
+    for (int k = threadIdx.x; k < pg.n_fop_levels * 32 * FOP_WORDS; k += blockDim.x) fop[k] = __ldg(&pg.fop[k]);
     __syncthreads();
     if (sidx >= S) return;
 
@@ -1016,7 +1066,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
 #pragma unroll
     for (int u = 0; u < MAXPF; u++) {
         const int j = gl + u * G;
-        td[u].ptr = pg.ts_days; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = st.n_val;  // scratch
+        td[u].ptr = pg.ts_days; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = st.k_base + K_SCRATCH;
         if (j < pg.n_table_ops) {
             const int tb = __ldg(&pg.tab_table[j]);
             const int ax = __ldg(&pg.table_axis[tb]);
@@ -1079,8 +1129,14 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         }
         D.sync();
         PHASE_MARK(0);
-        if (pg.n_code > 0) {
-            // every lane interprets the (tiny) op list and stores the same values: no divergent region
+        if (pg.n_fop_levels > 0) {
+            // lane-parallel schedule: one op per lane per dependency level, branch-free
+            for (int lev = 0; lev < pg.n_fop_levels; lev++) {
+                eval_fast_op(fop + (lev * 32 + (gl & 31)) * FOP_WORDS, V);
+                D.sync();
+            }
+        } else if (pg.n_code > 0) {
+            // generic interpreter: every lane evaluates the op list and stores the same values
             eval_ops(code, pg.n_code, V, st.pc_base);
             D.sync();
         }
