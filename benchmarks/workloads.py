@@ -184,6 +184,35 @@ def build_model(name, n_scenarios, years=None, solver=None, inflow=None, first_s
     return model
 
 
+def build_model_param_sets(n_param_sets, n_inflow, years=30, solver=None, seed=None):
+    """BASELINE.json config 5 / SURVEY.md 8(d): the optimisation-style batch.  two_reservoir with two
+    scenario axes, "params" (one control-curve monthly profile per candidate parameter set, the outer
+    loop of the reference's optimisation wrappers, pywr/optimisation/platypus.py:115-154, flattened
+    into scenarios) x "inflow"; S = n_param_sets * n_inflow combinations in Pywr's own order
+    (pywr/_core.pyx:210-240: the last axis varies fastest)."""
+    from pywr.core import Scenario
+    from pywr.model import Model
+    from pywr.parameters import ArrayIndexedScenarioParameter, ScenarioMonthlyProfileParameter
+
+    w = WORKLOADS["two_reservoir"]
+    idx = daily_index(w["start"], years=years)
+    doc = w["document"](str(idx[0].date()), str(idx[-1].date()))
+    del doc["parameters"]["control_curve"]
+    doc["parameters"]["transfer_controller"]["control_curve"] = 0.5   # replaced below
+    kwargs = {"solver": solver} if solver else {}
+    model = Model.load(doc, **kwargs)
+    params = Scenario(model, "params", size=n_param_sets)
+    inflow_axis = Scenario(model, "inflow", size=n_inflow)
+    rng = np.random.default_rng(SEEDS["two_reservoir_params"] if seed is None else seed)
+    curve = ScenarioMonthlyProfileParameter(model, params, rng.uniform(0.0, 1.0, size=(n_param_sets, 12)), name="control_curve")
+    model.parameters["transfer_controller"].control_curves = [curve]
+    inflow = synthetic_inflow(idx.month.values, n_inflow, SEEDS["two_reservoir"])
+    flow = ArrayIndexedScenarioParameter(model, inflow_axis, inflow, name="inflow")
+    for c in w["catchments"]:
+        model.nodes[c].flow = flow
+    return model
+
+
 def load_workload(name, n_scenarios, years=None, first_scenario=0, inflow=None):
     """(structure, program, info) for S scenarios from the committed single-scenario fixture."""
     from pywr_b200.program import Program

@@ -93,6 +93,7 @@ class Program:
     rec_col: np.ndarray
     rec_w: np.ndarray
     recorders: List[Any] = field(default_factory=list, repr=False)  # host objects, same order as rec_*
+    rec_names: List[str] = field(default_factory=list)
 
     @property
     def n_ops(self):
@@ -128,6 +129,7 @@ class Program:
     def save(self, path):
         data = {name: np.asarray(getattr(self, name)) for name in _P_I32 + _P_I64 + _P_F64}
         data["meta"] = np.array([self.n_steps, self.n_axes], np.int64)
+        data["rec_names"] = np.array(self.rec_names if self.rec_names else [""] * self.n_recorders)
         np.savez_compressed(path, **data)
 
     @classmethod
@@ -137,7 +139,8 @@ class Program:
         kw = {n: z[n].astype(np.int32) for n in _P_I32}
         kw.update({n: z[n].astype(np.int64) for n in _P_I64})
         kw.update({n: z[n].astype(np.float64) for n in _P_F64})
-        return cls(n_steps=n_steps, n_axes=n_axes, **kw)
+        names = [str(x) for x in z["rec_names"]] if "rec_names" in z.files else []
+        return cls(n_steps=n_steps, n_axes=n_axes, rec_names=names, **kw)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -506,5 +509,6 @@ def compile_program(model, formulation="route", recorders=None):
         initial_volume=vol0.reshape(-1), initial_pc=pc0.reshape(-1),
         rec_kind=i32(rec_kind), rec_src=i32(rec_src), rec_ref=i32(rec_ref), rec_factor=f64(rec_factor), rec_row=i32(rec_row),
         rec_indptr=i32(rec_indptr), rec_col=i32(rec_col), rec_w=f64(rec_w), recorders=rec_objs,
+        rec_names=[str(getattr(r, "name", "")) for r in rec_objs],
     )
     return s, prog
