@@ -213,6 +213,54 @@ def build_model_param_sets(n_param_sets, n_inflow, years=30, solver=None, seed=N
     return model
 
 
+def synthetic_network_document(n_reaches=12, seed=20240903, start="2100-01-01", end="2100-03-31"):
+    """A generated river network (scaled by `n_reaches`): a main stem of river
+    reaches, each with a catchment inflow, some with a tributary reservoir (storage + demand + spill
+    back to the stem), abstraction demands, a minimum-residual-flow gauge every few reaches, one
+    aggregated node capping total abstraction and a transfer between two reservoirs.  Meant for the
+    edge formulation (routes multiply with every confluence)."""
+    rng = np.random.default_rng(seed)
+    nodes, edges, params = [], [], {}
+    prev = None
+    reservoirs, abstractions = [], []
+    for r in range(n_reaches):
+        c, link = f"catch{r:03d}", f"reach{r:03d}"
+        params[f"inflow{r:03d}"] = {"type": "monthlyprofile", "values": [float(v) for v in rng.uniform(2.0, 12.0, 12)]}
+        nodes.append({"name": c, "type": "catchment", "flow": f"inflow{r:03d}"})
+        nodes.append({"name": link, "type": "link"})
+        edges.append([c, link])
+        if prev is not None:
+            edges.append([prev, link])
+        prev = link
+        if r % 3 == 1:  # tributary reservoir fed from the reach, supplying a demand, spilling downstream
+            res, dem, ab = f"res{r:03d}", f"town{r:03d}", f"abs{r:03d}"
+            nodes.append({"name": ab, "type": "link", "max_flow": float(rng.uniform(3.0, 8.0)), "cost": 1.0})
+            nodes.append({"name": res, "type": "storage", "max_volume": float(rng.uniform(80, 300)),
+                          "initial_volume_pc": 0.8, "cost": -float(rng.uniform(2, 20))})
+            nodes.append({"name": dem, "type": "output", "max_flow": float(rng.uniform(2.0, 7.0)), "cost": -float(rng.uniform(200, 600))})
+            edges += [[link, ab], [ab, res], [res, dem]]
+            reservoirs.append(res); abstractions.append(ab)
+        if r % 4 == 2:  # direct river abstraction
+            dem = f"farm{r:03d}"
+            nodes.append({"name": dem, "type": "output", "max_flow": float(rng.uniform(0.5, 3.0)), "cost": -float(rng.uniform(50, 150))})
+            edges.append([link, dem])
+        if r % 5 == 4:  # gauge with a minimum residual flow on the stem
+            g = f"gauge{r:03d}"
+            nodes.append({"name": g, "type": "rivergauge", "mrf": float(rng.uniform(1.0, 4.0)), "mrf_cost": -1000.0})
+            edges.append([link, g])
+            prev = g
+    nodes.append({"name": "sea", "type": "output"})
+    edges.append([prev, "sea"])
+    if len(reservoirs) >= 2:
+        nodes.append({"name": "transfer", "type": "link", "max_flow": 2.0, "cost": 5.0})
+        edges += [[reservoirs[-1], "transfer"], ["transfer", reservoirs[0]]]
+    if len(abstractions) >= 2:
+        nodes.append({"name": "licence", "type": "aggregatednode", "nodes": abstractions, "max_flow": float(4.0 * len(abstractions))})
+    return {"metadata": {"title": "generated network", "minimum_version": "0.1"},
+            "timestepper": {"start": start, "end": end, "timestep": 1},
+            "nodes": nodes, "edges": edges, "parameters": params, "recorders": {}}
+
+
 def load_workload(name, n_scenarios, years=None, first_scenario=0, inflow=None):
     """(structure, program, info) for S scenarios from the committed single-scenario fixture."""
     from pywr_b200.program import Program

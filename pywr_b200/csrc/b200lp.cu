@@ -12,6 +12,7 @@
 
 #include "../../include/b200lp.h"
 #include "lp_kernel.cuh"
+#include "lp_kernel_cta.cuh"
 
 using namespace b200lp;
 
@@ -89,6 +90,8 @@ struct b200lp_handle {
     int device = 0;
     int S = 0;
     int variant = -1;
+    bool use_cta = false;  // one CTA per scenario, dictionary in shared memory (lp_kernel_cta.cuh)
+    size_t cta_smem = 0;
     int block = 128;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -172,20 +175,31 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
         int v = atoi(force);
         if (v >= 0 && v < kNumVariants && m <= kVariants[v].G * kVariants[v].RPL && n <= kVariants[v].NC) variant = v;
     }
-    if (variant < 0) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "LP of %d rows x %d columns exceeds the register-resident simplex variants", m, n);
-        return fail(B200LP_E_UNSUPPORTED, buf);
+    constexpr int CTA_THREADS = 128;
+    bool use_cta = false;
+    size_t cta_smem = 0;
+    if (variant < 0 || getenv("B200LP_FORCE_CTA")) {
+        const int n_val = s->n_slots + s->n_consts + 2 * s->n_storage;
+        cta_smem = CtaDict<CTA_THREADS>::bytes(m, n, n_val);
+        if (cta_smem > 227 * 1024) {
+            char buf[200];
+            snprintf(buf, sizeof buf, "LP of %d rows x %d columns needs %zu KB of shared memory (limit 227 KB): "
+                     "beyond the simplex kernels of this build", m, n, cta_smem / 1024);
+            return fail(B200LP_E_UNSUPPORTED, buf);
+        }
+        use_cta = true;
+        variant = 0;
     }
     CUDA_TRY(cudaSetDevice(device));
     b200lp_handle *h = new b200lp_handle();
     h->device = device; h->S = n_scenarios; h->variant = variant;
+    h->use_cta = use_cta; h->cta_smem = cta_smem;
     if (const char *b = getenv("B200LP_BLOCK")) {
         int v = atoi(b);
         if (v >= 32 && v <= 128 && v % 32 == 0) h->block = v;
     }
     const Variant &V = kVariants[variant];
-    const int rows_cap = V.G * V.RPL, nc = V.NC;
+    const int rows_cap = use_cta ? m : V.G * V.RPL, nc = use_cta ? n : V.NC;
     const size_t S = (size_t)n_scenarios;
     h->nnz = s->a_indptr[m];
 
@@ -312,7 +326,7 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
         b200lp_destroy(h);
         return fail(B200LP_E_CUDA, "stream / event / pinned allocation failed");
     }
-    h->stats.n_rows = m; h->stats.n_cols = n; h->stats.n_nonzero = h->nnz; h->stats.kernel_variant = variant;
+    h->stats.n_rows = m; h->stats.n_cols = n; h->stats.n_nonzero = h->nnz; h->stats.kernel_variant = use_cta ? 100 : variant;
     *out = h;
     int rc = b200lp_reset(h, nullptr);
     if (rc != 0) { b200lp_destroy(h); *out = nullptr; return rc; }
@@ -363,8 +377,18 @@ int b200lp_set_consts(b200lp_handle *h, const double *consts) {
 
 static int launch_step(b200lp_handle *h, double days, const double *d_slots, double *d_node_flow, double *d_col_flow,
                        double *d_objective) {
-    const Variant &V = kVariants[h->variant];
-    V.launch(h->ds, h->state, h->S, days, d_slots, d_node_flow, d_col_flow, d_objective, h->stream, h->block);
+    if (h->use_cta) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(lp_step_kernel_cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_set = true;
+        }
+        lp_step_kernel_cta<128><<<h->S, 128, h->cta_smem, h->stream>>>(h->ds, h->state, h->S, days, d_slots, d_node_flow,
+                                                                      d_col_flow, d_objective);
+    } else {
+        const Variant &V = kVariants[h->variant];
+        V.launch(h->ds, h->state, h->S, days, d_slots, d_node_flow, d_col_flow, d_objective, h->stream, h->block);
+    }
     h->stats.kernel_launches++;
     h->stats.steps++;
     h->stats.scenario_steps += h->S;
@@ -564,6 +588,9 @@ extern "C" {
 int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
     if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
+    if (h->use_cta)
+        return fail(B200LP_E_UNSUPPORTED, "the device-resident run needs a register-resident kernel variant; "
+                                          "this LP uses the CTA-per-scenario kernel (per-timestep path only)");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     free_program(h);

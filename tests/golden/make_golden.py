@@ -46,6 +46,9 @@ CASES = [
     ("timeseries2", "tests/models/timeseries2.json", "route", 30),
     ("timeseries3", "tests/models/timeseries3.json", "route", 30),
     ("piecewise1", "tests/models/piecewise1.json", "edge", 5),
+    # generated networks beyond the register-resident kernel variants (CTA-per-scenario kernel)
+    ("network24", "generated:24", "edge", 25),
+    ("network12", "generated:12", "route", 25),
 ]
 
 
@@ -56,7 +59,12 @@ class Recorder:
 
 def run_case(name, path, formulation, max_steps):
     solver = "oracle" if formulation == "route" else "oracle-edge"
-    model = Model.load(os.path.join(REF, path), solver=solver)
+    if path.startswith("generated:"):
+        from benchmarks.workloads import synthetic_network_document
+
+        model = Model.load(synthetic_network_document(n_reaches=int(path.split(":")[1])), solver=solver)
+    else:
+        model = Model.load(os.path.join(REF, path), solver=solver)
     model.solver.save_routes_flows = True
     model.setup()
     rec = Recorder()

@@ -87,3 +87,37 @@ def test_reset_restarts_from_the_standard_basis():
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name,S,T", [("network24.edge", 96, 25), ("network12.route", 200, 25)])
+def test_cta_kernel_on_larger_networks(name, S, T):
+    """LPs beyond the register-resident variants run on the CTA-per-scenario shared-memory kernel."""
+    s, tr = load_case(name)
+    slots, days = synth_batch(s, tr, S, T, seed=13)
+    cpu, gpu = _engines(s, S)
+    assert gpu.stats()["kernel_variant"] == 100
+    r_cpu = replay(cpu, s, slots, days)
+    r_gpu = replay(gpu, s, slots, days)
+    assert np.array_equal(r_cpu[3] > 0, r_gpu[3] > 0)
+    good = r_cpu[3] == 0
+    for k in range(3):
+        assert _rel(r_gpu[k][good], r_cpu[k][good]) <= 1e-9
+    if good.all():
+        rb_c, cb_c = cpu.get_basis(); rb_g, cb_g = gpu.get_basis()
+        assert np.array_equal(rb_c, rb_g) and np.array_equal(cb_c, cb_g)
+        assert cpu.counters()["pivots"] == gpu.counters()["pivots"]
+    gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name", ["two_reservoir.route", "thames.edge", "loss_link_parameter.route", "virtual_storage1.route"])
+def test_cta_kernel_forced_on_small_models(name, monkeypatch):
+    """The same golden traces through the CTA kernel (B200LP_FORCE_CTA): both kernel families agree."""
+    monkeypatch.setenv("B200LP_FORCE_CTA", "1")
+    s, tr = load_case(name)
+    S = tr["slots"].shape[2]
+    cpu, gpu = _engines(s, S)
+    assert gpu.stats()["kernel_variant"] == 100
+    nf, cf, ob, nbad = replay(gpu, s, tr["slots"], tr["days"])
+    assert nbad.sum() == 0
+    assert _rel(nf, tr["node_flow"]) <= 1e-9 and _rel(cf, tr["col_flow"]) <= 1e-9 and _rel(ob, tr["objective"]) <= 1e-9
+    gpu.close(); cpu.close()
