@@ -316,6 +316,37 @@ def main():
                "sample": f"whole workload once ({S} x {T}); oracle/lp_oracle.c program mode on {cores} threads "
                          "(GLPK is not installable in this image)"}
 
+    # ---- the same engine driven by the reference framework itself (only where Pywr is importable) ----
+    pywr_extra = None
+    if world == 1 and not args.no_e2e:
+        try:
+            ref_dir = os.path.join(ROOT, "baseline", "_ref")
+            if os.path.isdir(os.path.join(ref_dir, "pywr")) and ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
+            import pywr_b200
+
+            pywr_b200.register()  # the package was imported before Pywr was importable
+            from benchmarks.workloads import build_model
+            from pywr_b200.device_run import run_on_device
+
+            yrs = 2
+            m1 = build_model(args.workload, S, years=yrs, solver="b200")
+            res1 = m1.run()
+            steps1 = (res1.timestep.index + 1) * S
+            m2 = build_model(args.workload, S, years=yrs, solver="null")
+            res2 = run_on_device(m2)
+            pywr_extra = {
+                "model_run_solver_b200": {"value": steps1 / res1.time_taken, "unit": UNIT, "years": yrs,
+                                          "note": "Model.run(): Pywr's own before()/after() on the host every timestep, "
+                                                  "one b200lp_step per timestep"},
+                "run_on_device": {"value": res2.speed, "unit": UNIT, "years": yrs, "compile_s": res2.time_compile,
+                                  "readout_s": res2.time_readout,
+                                  "note": "pywr_b200.device_run.run_on_device(model): whole run in one kernel launch, "
+                                          "recorders written back into Pywr's objects"},
+            }
+        except Exception as exc:  # Pywr not available on this box
+            pywr_extra = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -324,7 +355,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "failed_scenarios": nfail, "wall_ms_per_step_including_reset": wall / args.steps * 1e3,
             "pivots_per_scenario_timestep": (st1["pivots"] - st0["pivots"]) / max(1, units * args.steps),
-            "kernel_variant": st1["kernel_variant"], "gather_ms": gather_ms,
+            "kernel_variant": st1["kernel_variant"], "gather_ms": gather_ms, "through_pywr": pywr_extra,
         }
         print(json.dumps(line))
     eng.close()
