@@ -1,0 +1,98 @@
+"""the generated ~2,000-node network (edge formulation, LP 3,994 x 2,672)
+on the batched restarted-PDHG path, S scenarios x T daily steps replayed from the committed fixture
+(benchmarks/make_network_fixture.py).  Scenario k scales every recorded input plane by one
+log-normal factor (scenario 0: factor 1, so its objective must equal HiGHS's recorded optimum).
+
+Prints one JSON line: scenario-timesteps/s, PDHG iterations, and the achieved HBM bandwidth of the
+iteration kernels against the algorithmic bytes per scenario-iteration  8 (7 n + 5 m_r + 2 nnz_r).
+
+usage: python benchmarks/pdhg_bench.py [--scenarios 8192] [--steps 12] [--tol 2.5e-8]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from pywr_b200.engine import CudaEngine  # noqa: E402
+from pywr_b200.structure import LPStructure  # noqa: E402
+
+FIX = os.path.join(ROOT, "benchmarks", "fixtures", "network600.edge")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scenarios", type=int, default=8192)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--tol", type=float, default=None)
+    ap.add_argument("--seed", type=int, default=20240903)
+    a = ap.parse_args()
+    s = LPStructure.load(FIX + ".structure.npz")
+    tr = np.load(FIX + ".trace.npz")
+    S, T = a.scenarios, min(a.steps, len(tr["days"]))
+    rng = np.random.default_rng(a.seed)
+    factor = np.exp(rng.normal(0.0, 0.25, size=S))
+    factor[0] = 1.0
+    vol_slots = sorted({int(r) for r in s.st_vol_ref if r >= 0})
+    eng = CudaEngine(s, S, device=0)
+    st0 = eng.stats()
+    assert st0["kernel_variant"] == 200, "expected the PDHG path"
+    if a.tol is not None:
+        eng.set_option("pdhg_tol", a.tol)
+    slots = eng.alloc_planes(s.n_slots)
+    nf = eng.alloc_planes(s.n_nodes)
+    ob = eng.alloc_planes(1)
+    eng.reset(None)
+    rows = []
+    t_all = time.perf_counter()
+    for t in range(T):
+        base = tr["slots"][t][:, 0]
+        slots[:] = np.where(np.isfinite(base), base, 0.0)[:, None] * factor[None, :]
+        inf = ~np.isfinite(base)
+        slots[inf] = base[inf][:, None]
+        slots[vol_slots] = base[vol_slots][:, None]   # volumes are state, not scaled
+        before = eng.stats()
+        w0 = time.perf_counter()
+        nbad = eng.step(float(tr["days"][t]), slots, nf, None, ob)
+        wall = time.perf_counter() - w0
+        after = eng.stats()
+        ref = float(tr["objective_highs"][t, 0])
+        rows.append({"t": t, "wall_s": wall, "device_ms": after["device_ms"] - before["device_ms"],
+                     "iters": after["pdhg_iterations"] - before["pdhg_iterations"], "failed": int(nbad),
+                     "obj_rel_err_vs_highs": abs(float(ob[0, 0]) - ref) / max(1.0, abs(ref))})
+        print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
+    total_wall = time.perf_counter() - t_all
+    st = eng.stats()
+    n, m_r, nnz_r = s.n_cols, st["reduced_rows"], st["reduced_nonzero"]
+    bytes_iter = 8 * (7 * n + 5 * m_r + 2 * nnz_r)
+    dev_s = sum(r["device_ms"] for r in rows) / 1e3
+    # every scenario runs until ALL of its batch has converged only in launch count, not in traffic:
+    # converged scenario pairs return before touching memory, so traffic follows scenario-iterations
+    it_total = st["pdhg_iterations"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbps_sustained", peaks.get("hbm_gbps", 6541.8))) if isinstance(peaks, dict) else 6541.8
+    out = {"metric": "scenario-timesteps/sec (PDHG path, config 4)", "value": S * T / dev_s, "unit": "scenario-timesteps/s",
+           "e2e_value": S * T / total_wall, "scenarios": S, "steps": T, "rows": s.n_rows, "cols": n, "nnz": s.nnz,
+           "reduced_rows": m_r, "reduced_nnz": nnz_r, "tol": a.tol if a.tol is not None else 2.5e-8,
+           "iterations_per_scenario_step": it_total / (S * T), "first_step_iterations_per_scenario": rows[0]["iters"] / S,
+           "warm_iterations_per_scenario_step": (it_total - rows[0]["iters"]) / max(1, S * (T - 1)),
+           "device_s": dev_s, "wall_s": total_wall, "failed": int(sum(r["failed"] for r in rows)),
+           "max_obj_rel_err_vs_highs_scenario0": max(r["obj_rel_err_vs_highs"] for r in rows),
+           "roofline": {"bound": "hbm", "achieved": bytes_iter * it_total / dev_s / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_iter * it_total / dev_s / 1e9 / peak, "bytes_per_scenario_iteration": bytes_iter},
+           "kernel_launches": st["kernel_launches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]}
+    print(json.dumps(out))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

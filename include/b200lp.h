@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 5
+#define B200LP_ABI_VERSION 6
 
 /* error codes */
 #define B200LP_OK 0
@@ -127,7 +127,10 @@ typedef struct b200lp_stats {
     int64_t kernel_launches; /* launches of this library's kernels                                   */
     double h2d_bytes, d2h_bytes;
     double device_ms;        /* CUDA-event time of the solve kernels                                 */
-    int32_t n_rows, n_cols, n_nonzero, kernel_variant;
+    int32_t n_rows, n_cols, n_nonzero;
+    int32_t kernel_variant;  /* index of the register variant; 100: CTA-per-scenario simplex; 200: PDHG */
+    int64_t pdhg_iterations; /* PDHG path: scenario-iterations since create                           */
+    int32_t reduced_rows, reduced_nonzero; /* PDHG path: rows / non-zeros left by the structural presolve */
 } b200lp_stats;
 
 const char *b200lp_last_error(void);
@@ -178,6 +181,17 @@ int b200lp_get_volume(b200lp_handle *h, double *volume);
 int b200lp_set_volume(b200lp_handle *h, const double *volume);
 
 int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
+
+/*
+ * Engine selection is automatic (b200lp_create): register-resident simplex for LPs up to 64 rows x 32
+ * columns, CTA-per-scenario shared-memory simplex up to 227 KB of dictionary, and beyond that the
+ * batched restarted-PDHG path (first-order; role of glp_simplex for networks too large for shared
+ * memory).  The environment variables B200LP_FORCE_CTA / B200LP_FORCE_PDHG force the larger engines.
+ * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 2.5e-8: objectives within 1e-7 relative), "pdhg_max_iter"
+ * (default 200000), "pdhg_check" (iterations between convergence tests, default 64).
+ * The simplex engines accept and ignore pdhg_* options.
+ */
+int b200lp_set_option(b200lp_handle *h, const char *name, double value);
 
 /* =====================================================================================
  * Device-resident run ("program"): the per-timestep inputs are produced ON the device, so that

@@ -13,6 +13,7 @@
 #include "../../include/b200lp.h"
 #include "lp_kernel.cuh"
 #include "lp_kernel_cta.cuh"
+#include "pdhg_engine.cuh"
 
 using namespace b200lp;
 
@@ -115,6 +116,7 @@ struct b200lp_handle {
     std::vector<int> table_rows, table_cols;
     std::vector<long long> table_offset;
     int prog_steps = 0;
+    struct PdhgEngine *pdhg = nullptr;  // restarted-PDHG path (pdhg_engine.cuh): LPs beyond the simplex kernels
 };
 
 template <typename T>
@@ -149,6 +151,8 @@ __global__ void fill_kernel(double *p, size_t n, double v) {
 
 static void free_program(b200lp_handle *h);
 
+#include "pdhg_host.inc"
+
 extern "C" {
 
 const char *b200lp_last_error(void) { return g_last_error.c_str(); }
@@ -175,18 +179,15 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
         int v = atoi(force);
         if (v >= 0 && v < kNumVariants && m <= kVariants[v].G * kVariants[v].RPL && n <= kVariants[v].NC) variant = v;
     }
+    if (getenv("B200LP_FORCE_PDHG")) return create_pdhg(s, n_scenarios, device, out);
     constexpr int CTA_THREADS = 128;
     bool use_cta = false;
     size_t cta_smem = 0;
     if (variant < 0 || getenv("B200LP_FORCE_CTA")) {
         const int n_val = s->n_slots + s->n_consts + 2 * s->n_storage;
         cta_smem = CtaDict<CTA_THREADS>::bytes(m, n, n_val);
-        if (cta_smem > 227 * 1024) {
-            char buf[200];
-            snprintf(buf, sizeof buf, "LP of %d rows x %d columns needs %zu KB of shared memory (limit 227 KB): "
-                     "beyond the simplex kernels of this build", m, n, cta_smem / 1024);
-            return fail(B200LP_E_UNSUPPORTED, buf);
-        }
+        // beyond shared memory: the batched restarted-PDHG path (pdhg_engine.cuh)
+        if (cta_smem > 227 * 1024) return create_pdhg(s, n_scenarios, device, out);
         use_cta = true;
         variant = 0;
     }
@@ -338,6 +339,7 @@ void b200lp_destroy(b200lp_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_program(h);
+    pdhg_destroy(h);
     for (void *p : h->owned) cudaFree(p);
     if (h->h_fail) cudaFreeHost(h->h_fail);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -350,6 +352,7 @@ void b200lp_destroy(b200lp_handle *h) {
 int b200lp_reset(b200lp_handle *h, const double *initial_volume) {
     if (!h) return fail(B200LP_E_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->pdhg) return pdhg_reset(h, initial_volume);
     const int threads = 128;
     lp_reset_kernel<<<(h->S + threads - 1) / threads, threads, 0, h->stream>>>(h->state, h->S, h->ds.m, h->ds.n,
                                                                              h->ds.rows_cap, h->ds.nc);
@@ -368,6 +371,7 @@ int b200lp_reset(b200lp_handle *h, const double *initial_volume) {
 int b200lp_set_consts(b200lp_handle *h, const double *consts) {
     if (!h || !consts) return fail(B200LP_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->pdhg) return pdhg_set_consts(h, consts);
     if (h->ds.n_consts > 0) {
         CUDA_TRY(cudaMemcpyAsync(h->d_consts, consts, sizeof(double) * h->ds.n_consts, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -402,6 +406,8 @@ int b200lp_step_device(b200lp_handle *h, double days, const double *d_slots, dou
     if (!h) return fail(B200LP_E_INVALID, "null handle");
     if (!(days > 0.0)) return fail(B200LP_E_INVALID, "days must be positive");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->pdhg)  // iterates to convergence: synchronises with the host between batches of iterations
+        return pdhg_step_device(h, days, d_slots ? d_slots : h->d_slots, d_node_flow, d_col_flow, d_objective);
     return launch_step(h, days, d_slots ? d_slots : h->d_slots, d_node_flow, d_col_flow, d_objective);
 }
 
@@ -411,6 +417,7 @@ int b200lp_step(b200lp_handle *h, double days, const double *slots, double *node
     if (!(days > 0.0)) return fail(B200LP_E_INVALID, "days must be positive");
     if (h->ds.n_slots > 0 && !slots) return fail(B200LP_E_INVALID, "slots is NULL but the structure has input planes");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->pdhg) return pdhg_step_host(h, days, slots, node_flow, col_flow, objective);
     const size_t S = (size_t)h->S;
     if (h->ds.n_slots > 0) {
         const size_t bytes = sizeof(double) * S * h->ds.n_slots;
@@ -461,6 +468,7 @@ int b200lp_status(b200lp_handle *h, int32_t *first_bad_scenario, int32_t *code) 
 
 int b200lp_get_basis(b200lp_handle *h, int32_t *row_stat, int32_t *col_stat) {
     if (!h || !row_stat || !col_stat) return fail(B200LP_E_INVALID, "null argument");
+    if (h->pdhg) return fail(B200LP_E_UNSUPPORTED, "the PDHG path carries (x, y, omega) between timesteps, not a basis");
     CUDA_TRY(cudaSetDevice(h->device));
     const int m = h->ds.m, n = h->ds.n, rows_cap = h->ds.rows_cap, nc = h->ds.nc;
     const size_t S = (size_t)h->S;
@@ -505,10 +513,22 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->h_counters, h->state.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->stats.pivots = (int64_t)h->h_counters[0];
-    h->stats.refactors = (int64_t)h->h_counters[1];
+    if (h->pdhg) {
+        h->stats.pdhg_iterations = (int64_t)h->h_counters[0];
+    } else {
+        h->stats.pivots = (int64_t)h->h_counters[0];
+        h->stats.refactors = (int64_t)h->h_counters[1];
+    }
     *out = h->stats;
     return B200LP_OK;
+}
+
+int b200lp_set_option(b200lp_handle *h, const char *name, double value) {
+    if (!h || !name) return fail(B200LP_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->pdhg) return pdhg_set_option(h, name, value);
+    if (!strncmp(name, "pdhg_", 5)) return B200LP_OK;  // simplex engines ignore the PDHG options
+    return fail(B200LP_E_INVALID, std::string("unknown option ") + name);
 }
 
 void *b200lp_stream(b200lp_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -586,6 +606,7 @@ static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind
 extern "C" {
 
 int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
+    if (h && h->pdhg) return fail(B200LP_E_UNSUPPORTED, "device-resident programs are not available on the PDHG path yet");
     if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
     if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
     if (h->use_cta)

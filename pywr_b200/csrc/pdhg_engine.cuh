@@ -1,0 +1,629 @@
+// pdhg_engine.cuh — batched restarted PDHG for networks whose dictionary does not fit the simplex
+// kernels (BASELINE.json north_star: "for networks too large for shared memory there is a batched
+// restarted-PDHG path, whose SpMM over scenario-contiguous vectors uses coalesced, vectorised 128-bit
+// loads and shared-memory staging").
+//
+// What it replaces in the reference: CythonGLPKEdgeSolver._solve_scenario for every scenario of one
+// timestep (pywr/solvers/cython_glpk.pyx:1649-1918; bound typing :66-95,:932-1019; costs :880-897;
+// result extraction :1899-1911).  GLPK's simplex is replaced by a first-order method, so parity with
+// the reference is by objective and feasibility residuals (tests/test_gpu_pdhg.py), not by vertex.
+//
+// Layout: every per-scenario vector is a stack of planes [item][ld] with the scenario index
+// contiguous (ld = S rounded up to 2); one thread owns TWO neighbouring scenarios and moves them with
+// one 128-bit load / store, a warp moves 512 contiguous bytes per plane row.  The constraint matrix is
+// shared by all scenarios: each CTA stages the CSC (x update) or CSR (y update) slice of its chunk of
+// columns / rows in shared memory once and every thread reads it as a broadcast.
+//
+// Algorithm (same steps, same names as oracle/pdhg_oracle.py):
+//   1. structural presolve on the host (PdhgPlan): singleton rows -> column bounds, never-binding rows
+//      dropped;  2. Ruiz + Pock-Chambolle scaling, ||A|| by power iteration;
+//   3. reflected restarted Halpern PDHG, restart / convergence tests every `check` iterations on
+//      deterministic two-stage reductions;  4. warm start from the scenario's previous timestep;
+//   5. bound snapping and un-scaling, node flows.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/b200lp.h"
+
+namespace b200lp {
+
+constexpr double PD_BIG = 1e300;
+constexpr int PD_THREADS = 128;   // 256 scenarios per CTA
+constexpr int PD_CH = 16;         // columns / rows per CTA in the iteration kernels
+constexpr int PD_CHK = 64;        // columns / rows per CTA in the check kernels
+constexpr int PD_MAXE = 512;      // matrix entries staged in shared memory per CTA
+enum : int { Q_DX2 = 0, Q_DDX2, Q_POBJ, Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR, Q_DRESC, Q_DOBJC, Q_COUNT };
+
+struct PdhgDev {
+    int m, n, m_r, N, n_slots, n_storage, cost_clip, S, ld, nch;
+    const int *row_kind, *row_lb_ref, *row_ub_ref;
+    const int *st_kind, *st_vol_ref, *st_minv_ref, *st_maxv_ref, *st_active_ref;
+    const int *cost_indptr, *cost_ref;
+    const double *cost_w;
+    const int *flow_indptr, *flow_col;
+    const double *flow_w;
+    const double *consts;
+    const int *keep;                    // [m_r] original row of each reduced row
+    const int *sing_ptr, *sing_row;     // per column: singleton rows that bound it
+    const double *sing_coef;
+    const double *dr, *dc;              // row / column scaling
+    const int *csr_ptr, *csr_col;       // reduced, scaled matrix by rows
+    const double *csr_val;
+    const int *csc_ptr, *csc_row;       // ... and by columns
+    const double *csc_val;
+    double eta, tol;
+    int max_iter, check;
+};
+
+struct PdhgState {
+    double *x, *xa, *xb, *c, *lc, *uc, *tx;  // [n][ld]
+    double *y, *ya, *lo, *hi, *ty;           // [m_r][ld]
+    double *omega, *bnorm, *cnorm, *r0, *rprev, *objective;  // [ld]
+    int *kbase, *done, *status, *valid, *action, *iters;     // [ld]
+    double *vol;    // [n_storage][S] device-resident storage volumes (st_vol_ref == B200LP_REF_STATE)
+    double *part;   // [Q_COUNT][nch][ld] partial sums of the check kernels
+    int *it0;       // [1] iterations done so far in this solve
+    int *n_active;  // [1] scenarios still iterating after the last check
+    unsigned long long *total_iters;  // [1] scenario-iterations since create
+};
+
+__device__ __forceinline__ double pd_ref(const PdhgDev &P, const double *__restrict__ slots, const int ref, const int s) {
+    return ref >= 0 ? slots[(size_t)ref * P.S + s] : __ldg(&P.consts[-ref - 1]);
+}
+__device__ __forceinline__ double pd_clip8(const double v) { return fabs(v) < 1e-8 ? 0.0 : v; }
+__device__ __forceinline__ double pd_fin(const double v) { return fabs(v) < PD_BIG ? v : 0.0; }
+
+// (lb, ub) of ORIGINAL row i for scenario s: cython_glpk.pyx:1753-1840 (same typing as :932-1019)
+__device__ __forceinline__ void pd_row_bounds(const PdhgDev &P, const double *__restrict__ slots, const double *__restrict__ vol,
+                                              const int i, const int s, const double days, double &lo, double &hi) {
+    if (__ldg(&P.row_kind[i]) == B200LP_ROW_FLOW) {
+        lo = pd_clip8(pd_ref(P, slots, __ldg(&P.row_lb_ref[i]), s));
+        hi = pd_clip8(pd_ref(P, slots, __ldg(&P.row_ub_ref[i]), s));
+    } else {
+        const int q = __ldg(&P.row_lb_ref[i]);
+        const double maxv = pd_ref(P, slots, __ldg(&P.st_maxv_ref[q]), s), minv = pd_ref(P, slots, __ldg(&P.st_minv_ref[q]), s);
+        const int vref = __ldg(&P.st_vol_ref[q]);
+        const double v = vref == B200LP_REF_STATE ? vol[(size_t)q * P.S + s] : pd_ref(P, slots, vref, s);
+        const bool active = __ldg(&P.st_kind[q]) == B200LP_ST_KIND_STORAGE || pd_ref(P, slots, __ldg(&P.st_active_ref[q]), s) != 0.0;
+        if (maxv == minv) { lo = 0.0; hi = 0.0; return; }
+        if (!active) { lo = -INFINITY; hi = INFINITY; return; }
+        lo = pd_clip8(-fmax(v - minv, 0.0) / days);
+        hi = pd_clip8(fmax(maxv - v, 0.0) / days);
+        if (isnan(maxv) || isnan(minv) || isnan(v)) lo = NAN;
+    }
+    if (fabs(lo - hi) < 1e-8) hi = lo;
+}
+
+// ---- per-timestep assembly (one thread per scenario and row / column) --------------------------------
+__global__ void pdhg_assemble_rows(const PdhgDev P, const PdhgState Z, const double *__restrict__ slots, const double days) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (s >= P.ld) return;
+    double lo = 0.0, hi = 0.0;
+    if (s < P.S) {
+        pd_row_bounds(P, slots, Z.vol, __ldg(&P.keep[r]), s, days, lo, hi);
+        if (isnan(lo) || isnan(hi)) atomicMax(&Z.status[s], B200LP_ST_NAN);
+        else if (lo > hi) atomicMax(&Z.status[s], B200LP_ST_INFEASIBLE);
+        const double d = __ldg(&P.dr[r]);
+        lo *= d; hi *= d;
+    }
+    Z.lo[(size_t)r * P.ld + s] = lo;
+    Z.hi[(size_t)r * P.ld + s] = hi;
+}
+
+__global__ void pdhg_assemble_cols(const PdhgDev P, const PdhgState Z, const double *__restrict__ slots, const double days) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (s >= P.ld) return;
+    double lc = 0.0, uc = 0.0, c = 0.0;
+    if (s < P.S) {
+        uc = INFINITY;
+        bool bad = false;
+        for (int e = __ldg(&P.sing_ptr[j]); e < __ldg(&P.sing_ptr[j + 1]); e++) {
+            double l, u;
+            pd_row_bounds(P, slots, Z.vol, __ldg(&P.sing_row[e]), s, days, l, u);
+            bad |= isnan(l) || isnan(u);
+            const double a = __ldg(&P.sing_coef[e]);
+            const double l2 = a > 0.0 ? l / a : u / a, u2 = a > 0.0 ? u / a : l / a;
+            lc = fmax(lc, l2); uc = fmin(uc, u2);
+        }
+        for (int e = __ldg(&P.cost_indptr[j]); e < __ldg(&P.cost_indptr[j + 1]); e++)
+            c += __ldg(&P.cost_w[e]) * pd_ref(P, slots, __ldg(&P.cost_ref[e]), s);
+        if (P.cost_clip && fabs(c) < 1e-8) c = 0.0;
+        if (bad || isnan(c)) atomicMax(&Z.status[s], B200LP_ST_NAN);
+        else if (lc > uc + 1e-9) atomicMax(&Z.status[s], B200LP_ST_INFEASIBLE);
+        uc = fmax(uc, lc);
+        const double d = __ldg(&P.dc[j]);
+        c *= d; lc /= d; uc /= d;
+    }
+    Z.c[(size_t)j * P.ld + s] = c;
+    Z.lc[(size_t)j * P.ld + s] = lc;
+    Z.uc[(size_t)j * P.ld + s] = uc;
+}
+
+// norms, cold / warm start, anchors (one thread per scenario; plane rows are read coalesced)
+__global__ void pdhg_prepare(const PdhgDev P, const PdhgState Z) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ld) return;
+    const size_t ld = P.ld;
+    if (s == 0) { *Z.it0 = 0; *Z.n_active = 0; }
+    if (s >= P.S || Z.status[s] != B200LP_ST_OPTIMAL) {
+        Z.done[s] = 1; Z.iters[s] = 0;
+        return;
+    }
+    double b2 = 0.0, c2 = 0.0;
+    for (int r = 0; r < P.m_r; r++) {
+        const double b = fmax(fabs(pd_fin(Z.lo[r * ld + s])), fabs(pd_fin(Z.hi[r * ld + s])));
+        b2 = fma(b, b, b2);
+    }
+    const bool warm = Z.valid[s] != 0;
+    for (int j = 0; j < P.n; j++) {
+        const double c = Z.c[j * ld + s], l = Z.lc[j * ld + s], u = Z.uc[j * ld + s];
+        c2 = fma(c, c, c2);
+        b2 = fma(pd_fin(l), pd_fin(l), b2);
+        b2 = fma(pd_fin(u), pd_fin(u), b2);
+        const double x = warm ? Z.x[j * ld + s] : 0.0;
+        const double xc = fmin(fmax(x, l), u);
+        Z.x[j * ld + s] = xc; Z.xa[j * ld + s] = xc;
+    }
+    for (int r = 0; r < P.m_r; r++) {
+        const double y = warm ? Z.y[r * ld + s] : 0.0;
+        Z.y[r * ld + s] = y; Z.ya[r * ld + s] = y;
+    }
+    const double bnorm = sqrt(b2), cnorm = sqrt(c2);
+    Z.bnorm[s] = bnorm; Z.cnorm[s] = cnorm;
+    if (!warm) Z.omega[s] = (bnorm > 0.0 && cnorm > 0.0) ? cnorm / bnorm : 1.0;
+    Z.valid[s] = 1;
+    Z.kbase[s] = 0; Z.r0[s] = -1.0; Z.rprev[s] = INFINITY;
+    Z.done[s] = 0; Z.iters[s] = 0; Z.action[s] = 0;
+}
+
+// shared-memory staging of the matrix slice [e0, e1) of a chunk (entries beyond PD_MAXE stay in L2)
+struct PdStage {
+    int ptr[PD_CHK + 1];
+    int idx[PD_MAXE];
+    double val[PD_MAXE];
+};
+template <int CH>
+__device__ __forceinline__ void pd_stage(PdStage &sh, const int *__restrict__ ptr, const int *__restrict__ idx,
+                                         const double *__restrict__ val, const int i0, const int cnt) {
+    for (int k = threadIdx.x; k <= cnt; k += blockDim.x) sh.ptr[k] = __ldg(&ptr[i0 + k]);
+    __syncthreads();
+    const int e0 = sh.ptr[0], ne = min(sh.ptr[cnt] - e0, PD_MAXE);
+    for (int k = threadIdx.x; k < ne; k += blockDim.x) { sh.idx[k] = __ldg(&idx[e0 + k]); sh.val[k] = __ldg(&val[e0 + k]); }
+    __syncthreads();
+}
+#define PD_ENTRY(sh, gidx, gval, e, e0, I, A)                                      \
+    do {                                                                          \
+        const int _k = (e) - (e0);                                                \
+        if (_k < PD_MAXE) { I = sh.idx[_k]; A = sh.val[_k]; }                     \
+        else { I = __ldg(&(gidx)[e]); A = __ldg(&(gval)[e]); }                    \
+    } while (0)
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, const double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+__device__ __forceinline__ double pd_clamp(const double v, const double lo, const double hi) { return fmin(fmax(v, lo), hi); }
+
+// ---- x half-step:  xn = clip(x - tau (c - A^T y));  xb = 2 xn - x;  x <- w xb + (1 - w) xa -------------
+__global__ void __launch_bounds__(PD_THREADS) pdhg_x_kernel(const PdhgDev P, const PdhgState Z, const int j_in_batch) {
+    __shared__ PdStage sh;
+    const int j0 = blockIdx.y * PD_CH, cnt = min(PD_CH, P.n - j0);
+    pd_stage<PD_CH>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const int2 dn = *reinterpret_cast<const int2 *>(Z.done + s0);
+    if (dn.x && dn.y) return;
+    const int2 kb = *reinterpret_cast<const int2 *>(Z.kbase + s0);
+    const int it = *Z.it0 + j_in_batch;
+    const double2 om = ld2(Z.omega + s0);
+    const double tau0 = P.eta / om.x, tau1 = P.eta / om.y;
+    const double k0 = (double)(it - kb.x), k1 = (double)(it - kb.y);
+    const double w0 = (k0 + 1.0) / (k0 + 2.0), w1 = (k1 + 1.0) / (k1 + 2.0);
+    const size_t ld = P.ld;
+    const int e0 = sh.ptr[0];
+#pragma unroll 4
+    for (int jj = 0; jj < cnt; jj++) {
+        const size_t at = (size_t)(j0 + jj) * ld + s0;
+        double2 g = ld2(Z.c + at);
+        const double2 x = ld2(Z.x + at), l = ld2(Z.lc + at), u = ld2(Z.uc + at), a = ld2(Z.xa + at);
+        for (int e = sh.ptr[jj]; e < sh.ptr[jj + 1]; e++) {
+            int r; double v;
+            PD_ENTRY(sh, P.csc_row, P.csc_val, e, e0, r, v);
+            const double2 y = ld2(Z.y + (size_t)r * ld + s0);
+            g.x = fma(-v, y.x, g.x); g.y = fma(-v, y.y, g.y);
+        }
+        const double xn0 = pd_clamp(fma(-tau0, g.x, x.x), l.x, u.x), xn1 = pd_clamp(fma(-tau1, g.y, x.y), l.y, u.y);
+        double2 xb, xo;
+        xb.x = 2.0 * xn0 - x.x; xb.y = 2.0 * xn1 - x.y;
+        xo.x = dn.x ? x.x : fma(w0, xb.x, (1.0 - w0) * a.x);
+        xo.y = dn.y ? x.y : fma(w1, xb.y, (1.0 - w1) * a.y);
+        st2(Z.xb + at, xb);
+        st2(Z.x + at, xo);
+    }
+}
+
+// ---- y half-step:  v = y - sigma A xb;  yn = v - sigma clip(v / sigma, -hi, -lo);  y <- w (2 yn - y) + (1 - w) ya
+__global__ void __launch_bounds__(PD_THREADS) pdhg_y_kernel(const PdhgDev P, const PdhgState Z, const int j_in_batch) {
+    __shared__ PdStage sh;
+    const int i0 = blockIdx.y * PD_CH, cnt = min(PD_CH, P.m_r - i0);
+    pd_stage<PD_CH>(sh, P.csr_ptr, P.csr_col, P.csr_val, i0, cnt);
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const int2 dn = *reinterpret_cast<const int2 *>(Z.done + s0);
+    if (dn.x && dn.y) return;
+    const int2 kb = *reinterpret_cast<const int2 *>(Z.kbase + s0);
+    const int it = *Z.it0 + j_in_batch;
+    const double2 om = ld2(Z.omega + s0);
+    const double sg0 = P.eta * om.x, sg1 = P.eta * om.y;
+    const double k0 = (double)(it - kb.x), k1 = (double)(it - kb.y);
+    const double w0 = (k0 + 1.0) / (k0 + 2.0), w1 = (k1 + 1.0) / (k1 + 2.0);
+    const size_t ld = P.ld;
+    const int e0 = sh.ptr[0];
+#pragma unroll 4
+    for (int ii = 0; ii < cnt; ii++) {
+        const size_t at = (size_t)(i0 + ii) * ld + s0;
+        const double2 y = ld2(Z.y + at), lo = ld2(Z.lo + at), hi = ld2(Z.hi + at), a = ld2(Z.ya + at);
+        double2 ax; ax.x = 0.0; ax.y = 0.0;
+        for (int e = sh.ptr[ii]; e < sh.ptr[ii + 1]; e++) {
+            int c; double v;
+            PD_ENTRY(sh, P.csr_col, P.csr_val, e, e0, c, v);
+            const double2 xb = ld2(Z.xb + (size_t)c * ld + s0);
+            ax.x = fma(v, xb.x, ax.x); ax.y = fma(v, xb.y, ax.y);
+        }
+        const double v0 = fma(-sg0, ax.x, y.x), v1 = fma(-sg1, ax.y, y.y);
+        const double yn0 = v0 - sg0 * pd_clamp(v0 / sg0, -hi.x, -lo.x), yn1 = v1 - sg1 * pd_clamp(v1 / sg1, -hi.y, -lo.y);
+        double2 yo;
+        yo.x = dn.x ? y.x : fma(w0, 2.0 * yn0 - y.x, (1.0 - w0) * a.x);
+        yo.y = dn.y ? y.y : fma(w1, 2.0 * yn1 - y.y, (1.0 - w1) * a.y);
+        st2(Z.y + at, yo);
+    }
+}
+
+// ---- check, pass 1 (columns): tx = xn = T_x(z); partial sums |xn - x|^2, |xn - xa|^2, c.xn ------------
+__global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols1(const PdhgDev P, const PdhgState Z) {
+    __shared__ PdStage sh;
+    const int j0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.n - j0);
+    pd_stage<PD_CHK>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const size_t ld = P.ld;
+    const double2 om = ld2(Z.omega + s0);
+    const double tau0 = P.eta / om.x, tau1 = P.eta / om.y;
+    double2 dx2 = {0.0, 0.0}, ddx2 = {0.0, 0.0}, pobj = {0.0, 0.0};
+    const int e0 = sh.ptr[0];
+    for (int jj = 0; jj < cnt; jj++) {
+        const size_t at = (size_t)(j0 + jj) * ld + s0;
+        const double2 c = ld2(Z.c + at);
+        double2 g = c;
+        const double2 x = ld2(Z.x + at), l = ld2(Z.lc + at), u = ld2(Z.uc + at), a = ld2(Z.xa + at);
+        for (int e = sh.ptr[jj]; e < sh.ptr[jj + 1]; e++) {
+            int r; double v;
+            PD_ENTRY(sh, P.csc_row, P.csc_val, e, e0, r, v);
+            const double2 y = ld2(Z.y + (size_t)r * ld + s0);
+            g.x = fma(-v, y.x, g.x); g.y = fma(-v, y.y, g.y);
+        }
+        double2 xn;
+        xn.x = pd_clamp(fma(-tau0, g.x, x.x), l.x, u.x); xn.y = pd_clamp(fma(-tau1, g.y, x.y), l.y, u.y);
+        st2(Z.tx + at, xn);
+        dx2.x = fma(xn.x - x.x, xn.x - x.x, dx2.x); dx2.y = fma(xn.y - x.y, xn.y - x.y, dx2.y);
+        ddx2.x = fma(xn.x - a.x, xn.x - a.x, ddx2.x); ddx2.y = fma(xn.y - a.y, xn.y - a.y, ddx2.y);
+        pobj.x = fma(c.x, xn.x, pobj.x); pobj.y = fma(c.y, xn.y, pobj.y);
+    }
+    const size_t pstride = (size_t)P.nch * ld, pat = (size_t)blockIdx.y * ld + s0;
+    st2(Z.part + Q_DX2 * pstride + pat, dx2);
+    st2(Z.part + Q_DDX2 * pstride + pat, ddx2);
+    st2(Z.part + Q_POBJ * pstride + pat, pobj);
+}
+
+// ---- check, pass 2 (rows): ty = yn = T_y(z); primal residual, fixed-point terms, dual objective (rows) ---
+__global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, const PdhgState Z) {
+    __shared__ PdStage sh;
+    const int i0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.m_r - i0);
+    pd_stage<PD_CHK>(sh, P.csr_ptr, P.csr_col, P.csr_val, i0, cnt);
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const size_t ld = P.ld;
+    const double2 om = ld2(Z.omega + s0);
+    const double sg[2] = {P.eta * om.x, P.eta * om.y};
+    double acc[6][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // pr2 dy2 cross ddy2 dobj dinf2
+    const int e0 = sh.ptr[0];
+    for (int ii = 0; ii < cnt; ii++) {
+        const size_t at = (size_t)(i0 + ii) * ld + s0;
+        const double2 y2 = ld2(Z.y + at), lo2 = ld2(Z.lo + at), hi2 = ld2(Z.hi + at), a2 = ld2(Z.ya + at);
+        double axn[2] = {0.0, 0.0}, ax[2] = {0.0, 0.0};
+        for (int e = sh.ptr[ii]; e < sh.ptr[ii + 1]; e++) {
+            int c; double v;
+            PD_ENTRY(sh, P.csr_col, P.csr_val, e, e0, c, v);
+            const double2 xn = ld2(Z.tx + (size_t)c * ld + s0), x = ld2(Z.x + (size_t)c * ld + s0);
+            axn[0] = fma(v, xn.x, axn[0]); axn[1] = fma(v, xn.y, axn[1]);
+            ax[0] = fma(v, x.x, ax[0]); ax[1] = fma(v, x.y, ax[1]);
+        }
+        const double y[2] = {y2.x, y2.y}, lo[2] = {lo2.x, lo2.y}, hi[2] = {hi2.x, hi2.y}, ya[2] = {a2.x, a2.y};
+        double yn[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double axb = 2.0 * axn[q] - ax[q];
+            const double v = fma(-sg[q], axb, y[q]);
+            yn[q] = v - sg[q] * pd_clamp(v / sg[q], -hi[q], -lo[q]);
+            const double viol = axn[q] - pd_clamp(axn[q], lo[q], hi[q]);
+            const double dy = yn[q] - y[q];
+            const double yp = fmax(yn[q], 0.0), ym = fmax(-yn[q], 0.0);
+            acc[0][q] = fma(viol, viol, acc[0][q]);
+            acc[1][q] = fma(dy, dy, acc[1][q]);
+            acc[2][q] = fma(dy, axn[q] - ax[q], acc[2][q]);
+            acc[3][q] = fma(yn[q] - ya[q], yn[q] - ya[q], acc[3][q]);
+            acc[4][q] += pd_fin(lo[q]) * yp - pd_fin(hi[q]) * ym;
+            const double il = fabs(lo[q]) < PD_BIG ? 0.0 : yp, ih = fabs(hi[q]) < PD_BIG ? 0.0 : ym;
+            acc[5][q] = fma(il, il, fma(ih, ih, acc[5][q]));
+        }
+        double2 o; o.x = yn[0]; o.y = yn[1];
+        st2(Z.ty + at, o);
+    }
+    const size_t pstride = (size_t)P.nch * ld, pat = (size_t)blockIdx.y * ld + s0;
+    const int qs[6] = {Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR};
+#pragma unroll
+    for (int k = 0; k < 6; k++) { double2 o; o.x = acc[k][0]; o.y = acc[k][1]; st2(Z.part + qs[k] * pstride + pat, o); }
+}
+
+// ---- check, pass 3 (columns): reduced costs of yn: dual residual and dual objective (columns) -----------
+__global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols2(const PdhgDev P, const PdhgState Z) {
+    __shared__ PdStage sh;
+    const int j0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.n - j0);
+    pd_stage<PD_CHK>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const size_t ld = P.ld;
+    double dres[2] = {0.0, 0.0}, dobj[2] = {0.0, 0.0};
+    const int e0 = sh.ptr[0];
+    for (int jj = 0; jj < cnt; jj++) {
+        const size_t at = (size_t)(j0 + jj) * ld + s0;
+        double2 g = ld2(Z.c + at);
+        const double2 l2 = ld2(Z.lc + at), u2 = ld2(Z.uc + at);
+        for (int e = sh.ptr[jj]; e < sh.ptr[jj + 1]; e++) {
+            int r; double v;
+            PD_ENTRY(sh, P.csc_row, P.csc_val, e, e0, r, v);
+            const double2 y = ld2(Z.ty + (size_t)r * ld + s0);
+            g.x = fma(-v, y.x, g.x); g.y = fma(-v, y.y, g.y);
+        }
+        const double rc[2] = {g.x, g.y}, l[2] = {l2.x, l2.y}, u[2] = {u2.x, u2.y};
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double rp = fmax(rc[q], 0.0), rm = fmax(-rc[q], 0.0);
+            const double il = fabs(l[q]) < PD_BIG ? 0.0 : rp, iu = fabs(u[q]) < PD_BIG ? 0.0 : rm;
+            dres[q] = fma(il, il, fma(iu, iu, dres[q]));
+            dobj[q] += pd_fin(l[q]) * rp - pd_fin(u[q]) * rm;
+        }
+    }
+    const size_t pstride = (size_t)P.nch * ld, pat = (size_t)blockIdx.y * ld + s0;
+    double2 o; o.x = dres[0]; o.y = dres[1]; st2(Z.part + Q_DRESC * pstride + pat, o);
+    o.x = dobj[0]; o.y = dobj[1]; st2(Z.part + Q_DOBJC * pstride + pat, o);
+}
+
+__global__ void pdhg_advance(const PdhgState Z, const int check) { *Z.it0 += check; *Z.n_active = 0; }
+
+// ---- decision per scenario: converged / restart / continue (fixed summation order: deterministic) -------
+__global__ void pdhg_decide(const PdhgDev P, const PdhgState Z, const int nch_cols, const int nch_rows) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ld) return;
+    if (Z.done[s]) { Z.action[s] = 0; return; }
+    const size_t ld = P.ld, pstride = (size_t)P.nch * ld;
+    double q[Q_COUNT];
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; k++) {
+        const bool rows = (k >= Q_PR2 && k <= Q_DINFR);
+        const int nc = rows ? nch_rows : nch_cols;
+        double acc = 0.0;
+        for (int ch = 0; ch < nc; ch++) acc += Z.part[k * pstride + (size_t)ch * ld + s];
+        q[k] = acc;
+    }
+    const double omega = Z.omega[s], tau = P.eta / omega, sig = P.eta * omega;
+    const int it = *Z.it0;
+    const double r = sqrt(fmax(q[Q_DX2] / tau - 2.0 * q[Q_CROSS] + q[Q_DY2] / sig, 0.0));
+    const double pobj = q[Q_POBJ], dobj = q[Q_DOBJR] + q[Q_DOBJC];
+    const double rel = fmax(fmax(sqrt(q[Q_PR2]) / (1.0 + Z.bnorm[s]), sqrt(q[Q_DINFR] + q[Q_DRESC]) / (1.0 + Z.cnorm[s])),
+                            fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj)));
+    double r0 = Z.r0[s];
+    if (r0 < 0.0) r0 = r;
+    const int k = it - Z.kbase[s];
+    int action = 0;
+    if (rel < P.tol || it >= P.max_iter || !(rel == rel)) {
+        action = 2;
+        Z.done[s] = 1;
+        Z.status[s] = rel < P.tol ? B200LP_ST_OPTIMAL : (rel == rel ? B200LP_ST_ITERLIMIT : B200LP_ST_NAN);
+        Z.iters[s] = it;
+        atomicAdd(Z.total_iters, (unsigned long long)it);
+    } else {
+        if (r <= 0.2 * r0 || (r <= 0.8 * r0 && r > Z.rprev[s]) || (double)k >= 0.36 * (double)it) {
+            action = 1;
+            const double ddx = sqrt(q[Q_DDX2]), ddy = sqrt(q[Q_DDY2]);
+            if (ddx > 1e-12 && ddy > 1e-12) Z.omega[s] = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+            Z.kbase[s] = it;
+            r0 = -1.0;
+        }
+        atomicAdd(Z.n_active, 1);
+    }
+    Z.r0[s] = r0; Z.rprev[s] = r;
+    Z.action[s] = action;
+}
+
+// restart / convergence: z := anchor := T(z)
+__global__ void __launch_bounds__(PD_THREADS) pdhg_apply(const PdhgDev P, const PdhgState Z) {
+    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= P.ld) return;
+    const int2 ac = *reinterpret_cast<const int2 *>(Z.action + s0);
+    if (!ac.x && !ac.y) return;
+    const size_t ld = P.ld;
+    const int i0 = blockIdx.y * PD_CHK;
+    for (int ii = 0; ii < PD_CHK; ii++) {
+        const int i = i0 + ii;
+        if (i >= P.n + P.m_r) return;
+        const bool col = i < P.n;
+        const size_t at = (size_t)(col ? i : i - P.n) * ld + s0;
+        double *z = col ? Z.x : Z.y, *za = col ? Z.xa : Z.ya;
+        const double *t = col ? Z.tx : Z.ty;
+        const double2 tn = ld2(t + at);
+        double2 zo = ld2(z + at), ao = ld2(za + at);
+        if (ac.x) { zo.x = tn.x; ao.x = tn.x; }
+        if (ac.y) { zo.y = tn.y; ao.y = tn.y; }
+        st2(z + at, zo); st2(za + at, ao);
+    }
+}
+
+// ---- step 5: bound snapping, un-scaling (into the xb planes), objective, node flows -------------------------
+__global__ void pdhg_unscale(const PdhgDev P, const PdhgState Z, double *__restrict__ col_flow) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (s >= P.S) return;
+    const size_t at = (size_t)j * P.ld + s;
+    const double d = __ldg(&P.dc[j]);
+    double x = Z.x[at] * d;
+    const double l = Z.lc[at] * d, u = Z.uc[at] * d;
+    if (fabs(x - l) <= 1e-9 * (1.0 + fabs(l))) x = l;
+    if (fabs(x - u) <= 1e-9 * (1.0 + fabs(pd_fin(u)))) x = u;
+    Z.xb[at] = x;
+    if (col_flow) col_flow[(size_t)j * P.S + s] = x;
+}
+
+__global__ void pdhg_objective(const PdhgDev P, const PdhgState Z, double *__restrict__ objective) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.S) return;
+    double acc = 0.0;
+    for (int j = 0; j < P.n; j++) acc = fma(Z.c[(size_t)j * P.ld + s] / __ldg(&P.dc[j]), Z.xb[(size_t)j * P.ld + s], acc);
+    Z.objective[s] = acc;
+    if (objective) objective[s] = acc;
+}
+
+// node_flow[v] = sum_k flow_w[k] x[flow_col[k]]  (cython_glpk.pyx:1899-1911)
+__global__ void pdhg_node_flow(const PdhgDev P, const PdhgState Z, double *__restrict__ node_flow) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (s >= P.S) return;
+    double acc = 0.0;
+    for (int k = __ldg(&P.flow_indptr[v]); k < __ldg(&P.flow_indptr[v + 1]); k++)
+        acc = fma(__ldg(&P.flow_w[k]), Z.xb[(size_t)__ldg(&P.flow_col[k]) * P.ld + s], acc);
+    node_flow[(size_t)v * P.S + s] = acc;
+}
+
+__global__ void pdhg_clear_status(const PdhgDev P, const PdhgState Z) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.ld) Z.status[s] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host side: plan (presolve + scaling), memory, the per-timestep driver.
+// ------------------------------------------------------------------------------------------------------
+struct PdhgPlan {
+    int m = 0, n = 0, m_r = 0;
+    std::vector<int> keep, sing_ptr, sing_row;
+    std::vector<double> sing_coef, dr, dc;
+    std::vector<int> csr_ptr, csr_col, csc_ptr, csc_row;
+    std::vector<double> csr_val, csc_val;
+    double norm_a = 1.0, eta = 1.0;
+
+    void build(const b200lp_structure *s, const double *consts) {
+        m = s->n_rows; n = s->n_cols;
+        // rows with duplicates merged
+        std::vector<std::vector<std::pair<int, double>>> rows(m);
+        for (int i = 0; i < m; i++) {
+            auto &r = rows[i];
+            for (int k = s->a_indptr[i]; k < s->a_indptr[i + 1]; k++) r.push_back({s->a_col[k], s->a_val[k]});
+            std::sort(r.begin(), r.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+            size_t w = 0;
+            for (size_t k = 0; k < r.size(); k++) {
+                if (w > 0 && r[w - 1].first == r[k].first) r[w - 1].second += r[k].second;
+                else r[w++] = r[k];
+            }
+            r.resize(w);
+        }
+        keep.clear();
+        std::vector<std::vector<std::pair<int, double>>> sing(n);
+        for (int i = 0; i < m; i++) {
+            int cnt = 0, last = -1;
+            bool nonneg = true;
+            for (size_t k = 0; k < rows[i].size(); k++) {
+                if (rows[i][k].second != 0.0) { cnt++; last = (int)k; }
+                if (rows[i][k].second < 0.0) nonneg = false;
+            }
+            if (cnt == 1) { sing[rows[i][last].first].push_back({i, rows[i][last].second}); continue; }
+            if (s->row_kind[i] == B200LP_ROW_FLOW && cnt > 0 && nonneg && s->row_lb_ref[i] < 0 && s->row_ub_ref[i] < 0) {
+                const double lb = consts[-s->row_lb_ref[i] - 1], ub = consts[-s->row_ub_ref[i] - 1];
+                if (lb < 1e-8 && ub >= PD_BIG) continue;  // can never bind on x >= 0
+            }
+            keep.push_back(i);
+        }
+        m_r = (int)keep.size();
+        sing_ptr.assign(n + 1, 0); sing_row.clear(); sing_coef.clear();
+        for (int j = 0; j < n; j++) {
+            for (auto &e : sing[j]) { sing_row.push_back(e.first); sing_coef.push_back(e.second); }
+            sing_ptr[j + 1] = (int)sing_row.size();
+        }
+        // reduced CSR
+        csr_ptr.assign(m_r + 1, 0); csr_col.clear(); csr_val.clear();
+        for (int r = 0; r < m_r; r++) {
+            for (auto &e : rows[keep[r]])
+                if (e.second != 0.0) { csr_col.push_back(e.first); csr_val.push_back(e.second); }
+            csr_ptr[r + 1] = (int)csr_col.size();
+        }
+        const int nnz = (int)csr_col.size();
+        dr.assign(m_r, 1.0); dc.assign(n, 1.0);
+        std::vector<double> rn(m_r), cn(n);
+        for (int sweep = 0; sweep <= 10; sweep++) {  // 10 Ruiz sweeps (max norm) + 1 Pock-Chambolle (1-norm)
+            std::fill(rn.begin(), rn.end(), 0.0); std::fill(cn.begin(), cn.end(), 0.0);
+            for (int r = 0; r < m_r; r++)
+                for (int k = csr_ptr[r]; k < csr_ptr[r + 1]; k++) {
+                    const double a = std::fabs(csr_val[k]);
+                    if (sweep < 10) { rn[r] = std::max(rn[r], a); cn[csr_col[k]] = std::max(cn[csr_col[k]], a); }
+                    else { rn[r] += a; cn[csr_col[k]] += a; }
+                }
+            for (auto &v : rn) v = v > 0.0 ? std::sqrt(v) : 1.0;
+            for (auto &v : cn) v = v > 0.0 ? std::sqrt(v) : 1.0;
+            for (int r = 0; r < m_r; r++) {
+                for (int k = csr_ptr[r]; k < csr_ptr[r + 1]; k++) csr_val[k] = csr_val[k] / rn[r] / cn[csr_col[k]];
+                dr[r] /= rn[r];
+            }
+            for (int j = 0; j < n; j++) dc[j] /= cn[j];
+        }
+        // final values straight from the original coefficients (same as the oracle: diag(dr) A diag(dc))
+        {
+            int k = 0;
+            for (int r = 0; r < m_r; r++)
+                for (auto &e : rows[keep[r]])
+                    if (e.second != 0.0) { csr_val[k] = dr[r] * e.second * dc[e.first]; k++; }
+        }
+        // CSC
+        csc_ptr.assign(n + 1, 0); csc_row.assign(nnz, 0); csc_val.assign(nnz, 0.0);
+        for (int k = 0; k < nnz; k++) csc_ptr[csr_col[k] + 1]++;
+        for (int j = 0; j < n; j++) csc_ptr[j + 1] += csc_ptr[j];
+        std::vector<int> pos(csc_ptr.begin(), csc_ptr.end() - 1);
+        for (int r = 0; r < m_r; r++)
+            for (int k = csr_ptr[r]; k < csr_ptr[r + 1]; k++) { const int p = pos[csr_col[k]]++; csc_row[p] = r; csc_val[p] = csr_val[k]; }
+        // ||A||_2 by power iteration on A^T A
+        std::vector<double> v(n, 1.0 / std::sqrt((double)n)), t(m_r), w(n);
+        double nv = 0.0;
+        for (int itp = 0; itp < 300; itp++) {
+            for (int r = 0; r < m_r; r++) {
+                double acc = 0.0;
+                for (int k = csr_ptr[r]; k < csr_ptr[r + 1]; k++) acc += csr_val[k] * v[csr_col[k]];
+                t[r] = acc;
+            }
+            std::fill(w.begin(), w.end(), 0.0);
+            for (int r = 0; r < m_r; r++)
+                for (int k = csr_ptr[r]; k < csr_ptr[r + 1]; k++) w[csr_col[k]] += csr_val[k] * t[r];
+            nv = 0.0;
+            for (double a : w) nv += a * a;
+            nv = std::sqrt(nv);
+            if (nv == 0.0) break;
+            for (int j = 0; j < n; j++) v[j] = w[j] / nv;
+        }
+        norm_a = nv > 0.0 ? std::sqrt(nv) : 1.0;
+        eta = 0.99 / norm_a;
+    }
+};
+
+}  // namespace b200lp

@@ -28,6 +28,7 @@ class b200lp_stats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_double), ("d2h_bytes", ctypes.c_double), ("device_ms", ctypes.c_double),
         ("n_rows", ctypes.c_int32), ("n_cols", ctypes.c_int32), ("n_nonzero", ctypes.c_int32),
         ("kernel_variant", ctypes.c_int32),
+        ("pdhg_iterations", ctypes.c_int64), ("reduced_rows", ctypes.c_int32), ("reduced_nonzero", ctypes.c_int32),
     ]
 
 
@@ -47,6 +48,7 @@ SYMBOLS = [
     ("b200lp_get_volume", ctypes.c_int, [ctypes.c_void_p, _dp]),
     ("b200lp_set_volume", ctypes.c_int, [ctypes.c_void_p, _dp]),
     ("b200lp_get_stats", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(b200lp_stats)]),
+    ("b200lp_set_option", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     ("b200lp_stream", ctypes.c_void_p, [ctypes.c_void_p]),
     ("b200lp_sync", ctypes.c_int, [ctypes.c_void_p]),
     ("b200lp_host_alloc", ctypes.c_void_p, [ctypes.c_size_t]),
@@ -82,7 +84,7 @@ def load_library(path: str = LIB_PATH):
         fn = getattr(L, name)  # AttributeError if the library does not export it
         fn.restype = restype
         fn.argtypes = argtypes
-    if L.b200lp_abi_version() != 5:
+    if L.b200lp_abi_version() != 6:
         raise EngineUnavailable("libb200lp.so ABI version mismatch: rebuild")
     _lib = L
     return L
@@ -195,6 +197,9 @@ class CudaEngine:
 
     def sync(self):
         _check(self.L, self.L.b200lp_sync(self.h), "b200lp_sync")
+
+    def set_option(self, name, value):
+        _check(self.L, self.L.b200lp_set_option(self.h, name.encode(), float(value)), "b200lp_set_option")
 
     # -- device-resident run -----------------------------------------------------------------
     def load_program(self, prog):

@@ -43,10 +43,12 @@ def replay(engine, structure, slots_seq, days_seq, want_cols=True):
     return out_nf, out_cf, out_ob, nbad
 
 
-def synth_batch(structure, trace, S, T, seed):
+def synth_batch(structure, trace, S, T, seed, common=False):
     """A scenario batch of size S built from a recorded single-model trace: every recorded plane is
     tiled over scenarios and perturbed (flows scaled log-normally, volumes redrawn uniformly within
-    the storage bounds), so that scenarios take different paths through the simplex."""
+    the storage bounds), so that scenarios take different paths through the simplex.  `common`: one
+    factor per scenario for all planes (a wetter / drier scenario) - keeps the edge-form LPs, whose
+    planes are coupled through mass-balance rows, feasible."""
     rng = np.random.default_rng(seed)
     base = trace["slots"]  # [T0, n_slots, S0]
     T0, n_slots, S0 = base.shape
@@ -58,6 +60,8 @@ def synth_batch(structure, trace, S, T, seed):
     maxv_of = {int(v): (int(mx), int(mn)) for v, mx, mn in zip(structure.st_vol_ref, structure.st_maxv_ref,
                                                                  structure.st_minv_ref) if v >= 0}
     scale = np.exp(rng.normal(0.0, 0.4, size=(n_slots, S)))
+    if common:
+        scale = np.repeat(np.exp(rng.normal(0.0, 0.4, size=(1, S))), n_slots, axis=0)
     for t in range(T):
         plane = base[t][:, pick]
         for k in range(n_slots):

@@ -1,0 +1,112 @@
+"""GPU parity of the restarted-PDHG path (pywr_b200/csrc/pdhg_engine.cuh) through the C-ABI:
+objective within 1e-7 relative of the simplex oracle (north_star tolerance), primal feasibility,
+iteration counts against the numpy restatement, status codes, warm starts, options."""
+import os
+
+import numpy as np
+import pytest
+
+from fixtures_util import load_case, replay, synth_batch
+from lp_numpy import residuals
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-7
+
+
+@pytest.fixture()
+def force_pdhg(monkeypatch):
+    monkeypatch.setenv("B200LP_FORCE_PDHG", "1")
+
+
+def _gpu(s, S):
+    from pywr_b200.engine import CudaEngine
+
+    eng = CudaEngine(s, S, device=0)
+    assert eng.stats()["kernel_variant"] == 200
+    return eng
+
+
+@pytest.mark.parametrize("case,S", [("network24.edge", 33), ("two_reservoir.edge", 64), ("thames.edge", 7)])
+def test_pdhg_objective_and_feasibility(force_pdhg, case, S):
+    from oracle.oracle_engine import OracleEngine
+
+    s, tr = load_case(case)
+    T = 5
+    slots, days = synth_batch(s, tr, S, T, seed=11, common=True)
+    gpu = _gpu(s, S)
+    g = replay(gpu, s, slots, days)
+    c = replay(OracleEngine(s, S), s, slots, days)
+    assert g[3].sum() == 0 and c[3].sum() == 0
+    err = np.abs(g[2] - c[2]) / np.maximum(1.0, np.abs(c[2]))
+    assert err.max() < TOL, f"objective rel diff {err.max():.3e}"
+    for t in range(T):
+        for k in (0, S // 2, S - 1):
+            viol, obj = residuals(s, slots[t], k, float(days[t]), g[1][t, :, k])
+            assert viol < 1e-5 * max(1.0, np.abs(g[1][t, :, k]).max())
+            assert abs(obj - g[2][t, k]) <= 1e-9 * max(1.0, abs(obj))
+    # node flows are the column flows through the flow map (cython_glpk.pyx:1899-1911)
+    F = np.zeros((s.n_nodes, s.n_cols))
+    for v in range(s.n_nodes):
+        for k in range(s.flow_indptr[v], s.flow_indptr[v + 1]):
+            F[v, s.flow_col[k]] += s.flow_w[k]
+    assert np.allclose(np.einsum("vj,tjs->tvs", F, g[1]), g[0], rtol=1e-12, atol=1e-9)
+    st = gpu.stats()
+    assert st["pdhg_iterations"] > 0 and 0 < st["reduced_rows"] < s.n_rows
+    gpu.close()
+
+
+def test_pdhg_iterations_match_numpy_restatement(force_pdhg):
+    from oracle.pdhg_oracle import PdhgOracleEngine
+
+    s, tr = load_case("network24.edge")
+    S, T = 4, 3
+    slots, days = synth_batch(s, tr, S, T, seed=3, common=True)
+    gpu = _gpu(s, S)
+    cpu = PdhgOracleEngine(s, S)
+    g = replay(gpu, s, slots, days)
+    c = replay(cpu, s, slots, days)
+    assert np.max(np.abs(g[2] - c[2]) / np.maximum(1.0, np.abs(c[2]))) < TOL
+    it_gpu, it_cpu = gpu.stats()["pdhg_iterations"], cpu.stats()["pdhg_iterations"]
+    # same algorithm, same restart tests: the iteration totals agree up to rounding-driven restart shifts
+    assert abs(it_gpu - it_cpu) <= 0.2 * it_cpu + 2 * cpu.check * S * T, (it_gpu, it_cpu)
+    gpu.close()
+
+
+def test_pdhg_nan_and_options(force_pdhg):
+    s, tr = load_case("network24.edge")
+    S = 5
+    slots, days = synth_batch(s, tr, S, 2, seed=9, common=True)
+    gpu = _gpu(s, S)
+    gpu.set_option("pdhg_tol", 1e-5)
+    a = replay(gpu, s, slots, days)
+    assert a[3].sum() == 0
+    loose = gpu.stats()["pdhg_iterations"]
+    gpu.set_option("pdhg_tol", 1e-8)
+    b = replay(gpu, s, slots, days)
+    assert gpu.stats()["pdhg_iterations"] - loose > loose
+    assert np.max(np.abs(a[2] - b[2]) / np.maximum(1.0, np.abs(b[2]))) < 1e-4
+    bad = slots.copy()
+    used = int(next(r for r in list(s.row_lb_ref) + list(s.row_ub_ref) if r >= 0))
+    bad[:, used, 2] = np.nan
+    c = replay(gpu, s, bad, days)
+    assert (c[3] == 1).all() and gpu.status() == (2, 4)   # B200LP_ST_NAN, pywr GLPKError (cython_glpk.pyx:286-335)
+    gpu.close()
+
+
+def test_pdhg_warm_start(force_pdhg):
+    s, tr = load_case("network24.edge")
+    S = 8
+    slots, days = synth_batch(s, tr, S, 1, seed=2, common=True)
+    gpu = _gpu(s, S)
+    sl = gpu.alloc_planes(s.n_slots)
+    sl[:] = slots[0]
+    ob = gpu.alloc_planes(1)
+    gpu.reset(None)
+    assert gpu.step(float(days[0]), sl, None, None, ob) == 0
+    cold = gpu.stats()["pdhg_iterations"]
+    first = ob.copy()
+    assert gpu.step(float(days[0]), sl, None, None, ob) == 0
+    warm = gpu.stats()["pdhg_iterations"] - cold
+    assert warm <= 64 * S < cold
+    assert np.allclose(first, ob, rtol=1e-7)
+    gpu.close()
