@@ -65,6 +65,9 @@ def main():
         rows.append({"t": t, "wall_s": wall, "device_ms": after["device_ms"] - before["device_ms"],
                      "iters": after["pdhg_iterations"] - before["pdhg_iterations"], "failed": int(nbad),
                      "obj_rel_err_vs_highs": abs(float(ob[0, 0]) - ref) / max(1.0, abs(ref))})
+        if nbad:
+            bad, code = eng.status()
+            rows[-1].update(first_bad=bad, code=code, factor=float(factor[bad]))
         print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
     total_wall = time.perf_counter() - t_all
     st = eng.stats()
@@ -79,10 +82,10 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbps_sustained", peaks.get("hbm_gbps", 6541.8))) if isinstance(peaks, dict) else 6541.8
+    peak = float(peaks.get("hbm_gbs", 6541.8)) if isinstance(peaks, dict) else 6541.8
     out = {"metric": "scenario-timesteps/sec (PDHG path, config 4)", "value": S * T / dev_s, "unit": "scenario-timesteps/s",
            "e2e_value": S * T / total_wall, "scenarios": S, "steps": T, "rows": s.n_rows, "cols": n, "nnz": s.nnz,
-           "reduced_rows": m_r, "reduced_nnz": nnz_r, "tol": a.tol if a.tol is not None else 2.5e-8,
+           "reduced_rows": m_r, "reduced_nnz": nnz_r, "tol": a.tol if a.tol is not None else 1e-8,
            "iterations_per_scenario_step": it_total / (S * T), "first_step_iterations_per_scenario": rows[0]["iters"] / S,
            "warm_iterations_per_scenario_step": (it_total - rows[0]["iters"]) / max(1, S * (T - 1)),
            "device_s": dev_s, "wall_s": total_wall, "failed": int(sum(r["failed"] for r in rows)),

@@ -187,7 +187,7 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
  * columns, CTA-per-scenario shared-memory simplex up to 227 KB of dictionary, and beyond that the
  * batched restarted-PDHG path (first-order; role of glp_simplex for networks too large for shared
  * memory).  The environment variables B200LP_FORCE_CTA / B200LP_FORCE_PDHG force the larger engines.
- * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 2.5e-8: objectives within 1e-7 relative), "pdhg_max_iter"
+ * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 1e-8: objectives within 1e-7 relative), "pdhg_max_iter"
  * (default 200000), "pdhg_check" (iterations between convergence tests, default 64).
  * The simplex engines accept and ignore pdhg_* options.
  */

@@ -236,7 +236,7 @@ def snap_unscale(plan, xs, lc, uc):
 class PdhgOracleEngine:
     """Same duck-typed interface as ``pywr_b200.engine.CudaEngine`` (per-timestep path)."""
 
-    def __init__(self, structure, n_scenarios, tol=2.5e-8, max_iter=200000, check=64, **_):
+    def __init__(self, structure, n_scenarios, tol=1e-8, max_iter=200000, check=64, **_):
         self.structure = structure
         self.S = int(n_scenarios)
         self.plan = PdhgPlan(structure)

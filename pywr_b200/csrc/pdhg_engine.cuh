@@ -35,7 +35,8 @@ namespace b200lp {
 
 constexpr double PD_BIG = 1e300;
 constexpr int PD_THREADS = 128;   // 256 scenarios per CTA
-constexpr int PD_CH = 16;         // columns / rows per CTA in the iteration kernels
+constexpr int PD_CH = 8;          // columns / rows per CTA in the iteration kernels (dense phase)
+constexpr int PD_CH_TAIL = 2;     // ... when few scenario pairs still iterate (latency-bound tail)
 constexpr int PD_CHK = 64;        // columns / rows per CTA in the check kernels
 constexpr int PD_MAXE = 512;      // matrix entries staged in shared memory per CTA
 enum : int { Q_DX2 = 0, Q_DDX2, Q_POBJ, Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR, Q_DRESC, Q_DOBJC, Q_COUNT };
@@ -70,6 +71,8 @@ struct PdhgState {
     double *part;   // [Q_COUNT][nch][ld] partial sums of the check kernels
     int *it0;       // [1] iterations done so far in this solve
     int *n_active;  // [1] scenarios still iterating after the last check
+    int *plist;     // [ld/2] scenario pairs with at least one scenario still iterating, ascending
+    int *n_pairs;   // [1]
     unsigned long long *total_iters;  // [1] scenario-iterations since create
 };
 
@@ -211,14 +214,17 @@ __device__ __forceinline__ void st2(double *p, const double2 v) { *reinterpret_c
 __device__ __forceinline__ double pd_clamp(const double v, const double lo, const double hi) { return fmin(fmax(v, lo), hi); }
 
 // ---- x half-step:  xn = clip(x - tau (c - A^T y));  xb = 2 xn - x;  x <- w xb + (1 - w) xa -------------
+template <int CH>
 __global__ void __launch_bounds__(PD_THREADS) pdhg_x_kernel(const PdhgDev P, const PdhgState Z, const int j_in_batch) {
     __shared__ PdStage sh;
-    const int j0 = blockIdx.y * PD_CH, cnt = min(PD_CH, P.n - j0);
-    pd_stage<PD_CH>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int np = *Z.n_pairs;
+    if ((int)(blockIdx.x * blockDim.x) >= np) return;  // converged scenarios cost nothing: pairs are compacted
+    const int j0 = blockIdx.y * CH, cnt = min(CH, P.n - j0);
+    pd_stage<CH>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const int s0 = 2 * Z.plist[pt];
     const int2 dn = *reinterpret_cast<const int2 *>(Z.done + s0);
-    if (dn.x && dn.y) return;
     const int2 kb = *reinterpret_cast<const int2 *>(Z.kbase + s0);
     const int it = *Z.it0 + j_in_batch;
     const double2 om = ld2(Z.omega + s0);
@@ -249,14 +255,17 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_x_kernel(const PdhgDev P, con
 }
 
 // ---- y half-step:  v = y - sigma A xb;  yn = v - sigma clip(v / sigma, -hi, -lo);  y <- w (2 yn - y) + (1 - w) ya
+template <int CH>
 __global__ void __launch_bounds__(PD_THREADS) pdhg_y_kernel(const PdhgDev P, const PdhgState Z, const int j_in_batch) {
     __shared__ PdStage sh;
-    const int i0 = blockIdx.y * PD_CH, cnt = min(PD_CH, P.m_r - i0);
-    pd_stage<PD_CH>(sh, P.csr_ptr, P.csr_col, P.csr_val, i0, cnt);
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int np = *Z.n_pairs;
+    if ((int)(blockIdx.x * blockDim.x) >= np) return;
+    const int i0 = blockIdx.y * CH, cnt = min(CH, P.m_r - i0);
+    pd_stage<CH>(sh, P.csr_ptr, P.csr_col, P.csr_val, i0, cnt);
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const int s0 = 2 * Z.plist[pt];
     const int2 dn = *reinterpret_cast<const int2 *>(Z.done + s0);
-    if (dn.x && dn.y) return;
     const int2 kb = *reinterpret_cast<const int2 *>(Z.kbase + s0);
     const int it = *Z.it0 + j_in_batch;
     const double2 om = ld2(Z.omega + s0);
@@ -288,10 +297,13 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_y_kernel(const PdhgDev P, con
 // ---- check, pass 1 (columns): tx = xn = T_x(z); partial sums |xn - x|^2, |xn - xa|^2, c.xn ------------
 __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols1(const PdhgDev P, const PdhgState Z) {
     __shared__ PdStage sh;
+    const int np = *Z.n_pairs;
+    if ((int)(blockIdx.x * blockDim.x) >= np) return;
     const int j0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.n - j0);
     pd_stage<PD_CHK>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const int s0 = 2 * Z.plist[pt];
     const size_t ld = P.ld;
     const double2 om = ld2(Z.omega + s0);
     const double tau0 = P.eta / om.x, tau1 = P.eta / om.y;
@@ -324,10 +336,13 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols1(const PdhgDev P, co
 // ---- check, pass 2 (rows): ty = yn = T_y(z); primal residual, fixed-point terms, dual objective (rows) ---
 __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, const PdhgState Z) {
     __shared__ PdStage sh;
+    const int np = *Z.n_pairs;
+    if ((int)(blockIdx.x * blockDim.x) >= np) return;
     const int i0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.m_r - i0);
     pd_stage<PD_CHK>(sh, P.csr_ptr, P.csr_col, P.csr_val, i0, cnt);
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const int s0 = 2 * Z.plist[pt];
     const size_t ld = P.ld;
     const double2 om = ld2(Z.omega + s0);
     const double sg[2] = {P.eta * om.x, P.eta * om.y};
@@ -374,10 +389,13 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, con
 // ---- check, pass 3 (columns): reduced costs of yn: dual residual and dual objective (columns) -----------
 __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols2(const PdhgDev P, const PdhgState Z) {
     __shared__ PdStage sh;
+    const int np = *Z.n_pairs;
+    if ((int)(blockIdx.x * blockDim.x) >= np) return;
     const int j0 = blockIdx.y * PD_CHK, cnt = min(PD_CHK, P.n - j0);
     pd_stage<PD_CHK>(sh, P.csc_ptr, P.csc_row, P.csc_val, j0, cnt);
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= np) return;
+    const int s0 = 2 * Z.plist[pt];
     const size_t ld = P.ld;
     double dres[2] = {0.0, 0.0}, dobj[2] = {0.0, 0.0};
     const int e0 = sh.ptr[0];
@@ -454,8 +472,9 @@ __global__ void pdhg_decide(const PdhgDev P, const PdhgState Z, const int nch_co
 
 // restart / convergence: z := anchor := T(z)
 __global__ void __launch_bounds__(PD_THREADS) pdhg_apply(const PdhgDev P, const PdhgState Z) {
-    const int s0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (s0 >= P.ld) return;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= *Z.n_pairs) return;
+    const int s0 = 2 * Z.plist[pt];
     const int2 ac = *reinterpret_cast<const int2 *>(Z.action + s0);
     if (!ac.x && !ac.y) return;
     const size_t ld = P.ld;
@@ -473,6 +492,30 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_apply(const PdhgDev P, const 
         if (ac.y) { zo.y = tn.y; ao.y = tn.y; }
         st2(z + at, zo); st2(za + at, ao);
     }
+}
+
+// ascending list of the scenario pairs that still iterate (one CTA; block-wide exclusive scan)
+__global__ void __launch_bounds__(1024) pdhg_compact(const PdhgDev P, const PdhgState Z) {
+    __shared__ int warp_sum[32];
+    __shared__ int base;
+    const int npairs = P.ld / 2;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < npairs; p0 += 1024) {
+        const int p = p0 + threadIdx.x;
+        const int flag = (p < npairs && !(Z.done[2 * p] && Z.done[2 * p + 1])) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_sum[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int k = 0; k < w; k++) off += warp_sum[k];
+        if (flag) Z.plist[off + __popc(bal & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 32; k++) t += warp_sum[k]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *Z.n_pairs = base;
 }
 
 // ---- step 5: bound snapping, un-scaling (into the xb planes), objective, node flows -------------------------

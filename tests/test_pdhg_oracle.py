@@ -9,7 +9,7 @@ from lp_numpy import residuals
 from oracle.oracle_engine import OracleEngine
 from oracle.pdhg_oracle import PdhgOracleEngine, PdhgPlan
 
-TOL = 1e-7  # north_star: per-timestep objectives within 1e-7 relative (engine default KKT tolerance 2.5e-8)
+TOL = 1e-7  # north_star: per-timestep objectives within 1e-7 relative (engine default KKT tolerance 1e-8)
 
 
 def test_presolve_shapes():
