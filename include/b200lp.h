@@ -290,6 +290,16 @@ int b200lp_program_reset(b200lp_handle *h);
 /* Run timesteps [t0, t0+n) for all scenarios on the device.  Asynchronous on b200lp_stream();
  * errors of individual scenarios are reported by b200lp_program_status after a b200lp_sync. */
 int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n);
+/*
+ * One whole run with HOST buffers, pipelined: Model.reset, then the T timesteps in `n_chunks` time
+ * slices; while slice c is being solved, the rows of the time-indexed tables that slice c+1 needs are
+ * uploaded and the array-recorder rows slice c-1 produced are downloaded (three streams, both PCIe
+ * directions busy at once).  table_src[k] (may be NULL, as may the array itself): new contents of table
+ * k, same shape; rec_dst[r] (may be NULL): receives recorder r.  Pinned buffers (b200lp_host_alloc)
+ * are needed for the copies to overlap.  Synchronous; results equal b200lp_update_table +
+ * b200lp_program_reset + b200lp_run(0, T) + b200lp_fetch_recorder.
+ */
+int b200lp_run_pipelined(b200lp_handle *h, int32_t n_chunks, const double *const *table_src, double *const *rec_dst);
 /* Number of failed scenarios so far, the first failing scenario (or -1), its status and timestep. */
 int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario, int32_t *code, int32_t *timestep);
 /* Replace the contents of table `table` (same shape) from host memory — pinned memory is copied

@@ -117,6 +117,8 @@ struct b200lp_handle {
     std::vector<int> table_rows, table_cols;
     std::vector<long long> table_offset;
     int prog_steps = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of b200lp_run_pipelined
+    std::vector<cudaEvent_t> pipe_events;
     struct PdhgEngine *pdhg = nullptr;  // restarted-PDHG path (pdhg_engine.cuh): LPs beyond the simplex kernels
 };
 
@@ -344,6 +346,9 @@ void b200lp_destroy(b200lp_handle *h) {
     for (void *p : h->owned) cudaFree(p);
     if (h->h_fail) cudaFreeHost(h->h_fail);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    for (cudaEvent_t e : h->pipe_events) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -903,6 +908,72 @@ int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n) {
     h->stats.scenario_steps += (int64_t)n * h->S;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B200LP_E_CUDA, std::string("run kernel launch: ") + cudaGetErrorString(e));
+    return B200LP_OK;
+}
+
+int b200lp_run_pipelined(b200lp_handle *h, int32_t n_chunks, const double *const *table_src, double *const *rec_dst) {
+    if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int T = h->prog_steps;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > T) n_chunks = T;
+    if (!h->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    if (!h->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    while ((int)h->pipe_events.size() < 2 * n_chunks + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_events.push_back(e);
+    }
+    int rc = b200lp_program_reset(h);  // Model.reset: initial volumes, slack bases, cleared recorders (synchronises)
+    if (rc != 0) return rc;
+    const size_t S = (size_t)h->S;
+    double *tables = const_cast<double *>(h->dp.table_data);
+    const int n_tables = h->dp.n_tables, n_rec = (int)h->rec_ptr.size();
+    // tables that do not advance with time go up first, whole
+    if (table_src)
+        for (int k = 0; k < n_tables; k++)
+            if (table_src[k] && h->table_rows[k] != T) {
+                const size_t count = (size_t)h->table_rows[k] * h->table_cols[k];
+                CUDA_TRY(cudaMemcpyAsync(tables + h->table_offset[k], table_src[k], sizeof(double) * count, cudaMemcpyHostToDevice, h->s_in));
+                h->stats.h2d_bytes += (double)count * 8.0;
+            }
+    int rows_up = 0;  // rows [0, rows_up) of the time-indexed tables are on the device (or queued)
+    for (int c = 0; c < n_chunks; c++) {
+        const int t0 = (int)((long long)T * c / n_chunks), t1 = (int)((long long)T * (c + 1) / n_chunks);
+        // the kernel reads one row ahead (prefetch of timestep t+1, clamped to the last row)
+        const int need = std::min(T, t1 + 1);
+        if (table_src && need > rows_up)
+            for (int k = 0; k < n_tables; k++)
+                if (table_src[k] && h->table_rows[k] == T) {
+                    const size_t cols = (size_t)h->table_cols[k], off = (size_t)rows_up * cols, count = (size_t)(need - rows_up) * cols;
+                    CUDA_TRY(cudaMemcpyAsync(tables + h->table_offset[k] + off, table_src[k] + off, sizeof(double) * count,
+                                             cudaMemcpyHostToDevice, h->s_in));
+                    h->stats.h2d_bytes += (double)count * 8.0;
+                }
+        rows_up = std::max(rows_up, need);
+        cudaEvent_t ev_in = h->pipe_events[2 * c], ev_run = h->pipe_events[2 * c + 1];
+        CUDA_TRY(cudaEventRecord(ev_in, h->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_in, 0));
+        rc = b200lp_run(h, t0, t1 - t0);
+        if (rc != 0) return rc;
+        CUDA_TRY(cudaEventRecord(ev_run, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_out, ev_run, 0));
+        if (rec_dst)
+            for (int r = 0; r < n_rec; r++) {
+                if (!rec_dst[r]) continue;
+                if (rec_is_array(h->rec_kind[r])) {
+                    const size_t off = (size_t)t0 * S, count = (size_t)(t1 - t0) * S;
+                    CUDA_TRY(cudaMemcpyAsync(rec_dst[r] + off, h->rec_ptr[r] + off, sizeof(double) * count, cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += (double)count * 8.0;
+                } else if (c == n_chunks - 1) {
+                    CUDA_TRY(cudaMemcpyAsync(rec_dst[r], h->rec_ptr[r], sizeof(double) * S, cudaMemcpyDeviceToHost, h->s_out));
+                    h->stats.d2h_bytes += (double)S * 8.0;
+                }
+            }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->s_in));
     return B200LP_OK;
 }
 

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("b200lp_load_program", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     ("b200lp_program_reset", ctypes.c_int, [ctypes.c_void_p]),
     ("b200lp_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]),
+    ("b200lp_run_pipelined", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     ("b200lp_program_status", ctypes.c_int, [ctypes.c_void_p, _ip, _ip, _ip, _ip]),
     ("b200lp_update_table", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp]),
     ("b200lp_mark", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
@@ -204,6 +205,7 @@ class CudaEngine:
     # -- device-resident run -----------------------------------------------------------------
     def load_program(self, prog):
         self._cp = prog.to_c()
+        self._prog = prog
         _check(self.L, self.L.b200lp_load_program(self.h, ctypes.addressof(self._cp)), "b200lp_load_program")
 
     def program_reset(self):
@@ -213,6 +215,22 @@ class CudaEngine:
         """Queues timesteps [t0, t0+n) on the engine's stream (asynchronous)."""
         _check(self.L, self.L.b200lp_run(self.h, int(t0), int(n)), "b200lp_run")
         return 0
+
+    def run_pipelined(self, tables=None, outs=None, chunks=16):
+        """Whole run with host buffers (reset, upload, solve, read-out overlapped in time slices).
+        tables: {table index: array}; outs: list with one array (or None) per recorder."""
+        nt, nr = self._prog.n_tables, self._prog.n_recorders
+        tp = (ctypes.c_void_p * max(nt, 1))()
+        for k, a in (tables or {}).items():
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            tp[k] = a.ctypes.data
+        rp = (ctypes.c_void_p * max(nr, 1))()
+        for r, a in enumerate(outs or []):
+            if a is not None:
+                assert a.dtype == np.float64 and a.flags.c_contiguous
+                rp[r] = a.ctypes.data
+        _check(self.L, self.L.b200lp_run_pipelined(self.h, int(chunks), tp if tables else None, rp if outs else None),
+               "b200lp_run_pipelined")
 
     def program_status(self):
         v = [ctypes.c_int32() for _ in range(4)]

@@ -53,4 +53,4 @@ def test_warm_start_is_cheaper():
     sl = eng.alloc_planes(s.n_slots)
     sl[:] = tr["slots"][0]
     eng.step(float(tr["days"][0]), sl, None, None, None)   # same LP again, warm
-    assert int(eng.last_iterations[0]) <= eng.check < cold
+    assert int(eng.last_iterations[0]) <= 4 * eng.check < cold
