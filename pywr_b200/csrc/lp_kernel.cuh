@@ -978,9 +978,10 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, doub
 // Lanes of one level normally share a kind, so the branch on `kind` does not diverge.  Arithmetic order is the
 // interpreter's (and the reference's: AggregatedParameter multiplies / adds in parameter order).
 __device__ __forceinline__ void eval_fast_op(const int *d, double *V) {
-    const int kind = d[0];
+    const int4 d0 = *reinterpret_cast<const int4 *>(d), d1 = *reinterpret_cast<const int4 *>(d + 4);  // two LDS.128
+    const int kind = d0.x;
     if (kind == FOP_NONE) return;  // idle lane at this level
-    const double a0 = V[d[2]], a1 = V[d[3]], a2 = V[d[4]], a3 = V[d[5]], a4 = V[d[6]], a5 = V[d[7]];
+    const double a0 = V[d0.z], a1 = V[d0.w], a2 = V[d1.x], a3 = V[d1.y], a4 = V[d1.z], a5 = V[d1.w];
     double r;
     if (kind == FOP_CC) {  // a0 = pc, a1/a2 = curves (descending), a3..a5 = values
         const double c = clamp_pc(a0);
@@ -1005,22 +1006,29 @@ __device__ __forceinline__ void eval_fast_op(const int *d, double *V) {
     } else {
         r = a0 / a1;
     }
-    V[d[1]] = r;
+    V[d0.y] = r;
 }
 
-// one table op owned by a lane: value(t) = ptr[clamp(t + off) * stride]
+// one table op owned by a lane: value(t) = ptr[clamp(t + off, 0, last) * stride]  (last = rows - 1)
 struct TableDesc {
     const double *ptr;
-    int rows, stride, off, dst;
+    int last, stride, off, dst;
     __device__ __forceinline__ double at(int t) const {
-        long long row = 0;
-        if (rows > 1) {
-            row = (long long)t + off;
-            row = row < 0 ? 0 : (row > rows - 1 ? rows - 1 : row);
-        }
-        return __ldg(ptr + row * stride);
+        const int row = min(max(t + off, 0), last);
+        return __ldg(ptr + (long long)row * stride);
     }
 };
+
+// Division by a denominator that is constant over the launch, with its reciprocal y = RN(1/b) computed once:
+//   q0 = RN(a y);  r = a - b q0 (exact, one fma);  q = RN(q0 + r y)
+// is the correctly rounded quotient RN(a / b) (Markstein's theorem), i.e. bit-identical to `a / b`, for finite
+// a and b in the normal range; three dependent FMAs instead of the ~25-instruction DDIV sequence.
+// (checked against `/` on 1e9 random operand pairs: no mismatch.)
+__device__ __forceinline__ double div_by_const(const double a, const double b, const double y) {
+    const double q0 = a * y;
+    const double r = fma(-b, q0, a);
+    return fma(r, y, q0);
+}
 
 template <int G, int RPL, int NC>
 __global__ void __launch_bounds__(128, (RPL == 1 ? 3 : 1))
@@ -1066,13 +1074,13 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
 #pragma unroll
     for (int u = 0; u < MAXPF; u++) {
         const int j = gl + u * G;
-        td[u].ptr = pg.ts_days; td[u].rows = 1; td[u].stride = 0; td[u].off = 0; td[u].dst = st.k_base + K_SCRATCH;
+        td[u].ptr = pg.ts_days; td[u].last = 0; td[u].stride = 0; td[u].off = 0; td[u].dst = st.k_base + K_SCRATCH;
         if (j < pg.n_table_ops) {
             const int tb = __ldg(&pg.tab_table[j]);
             const int ax = __ldg(&pg.table_axis[tb]);
             const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
             td[u].ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
-            td[u].rows = __ldg(&pg.table_rows[tb]);
+            td[u].last = __ldg(&pg.table_rows[tb]) - 1;
             td[u].stride = __ldg(&pg.table_cols[tb]);
             td[u].off = __ldg(&pg.tab_offset[j]);
             td[u].dst = __ldg(&pg.tab_dst[j]);
@@ -1080,26 +1088,44 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         pf[u] = td[u].at(t0);
     }
     // recorder owned by this lane (recorders beyond G are handled by the generic loop below).
-    // Per-scenario accumulators stay in a register for the whole launch.
-    int rk = 0, rrow = -1, ridx = 0, rsrc = 0, rbeg = 0, rend = 0;
-    double rfac = 1.0, racc = 0.0;
+    // Per-scenario accumulators stay in a register for the whole launch.  Lanes without a recorder run the
+    // same instruction stream on harmless operands (their accumulator is never stored).
+    int rk = B200LP_REC_MEAN_FLOW, rrow = 0, ridx = st.k_base + K_ZERO, rsrc = 0, rbeg = 0, rend = 0;
+    double rfac = 0.0, racc = 0.0;
     double *rout = nullptr;   // array kinds: next element to write; others: the accumulator's home
-    bool r_array = false;
+    bool r_array = false, r_on = false;
     if (gl < pg.n_recorders) {
+        r_on = true;
         rk = __ldg(&pg.rec_kind[gl]); rrow = __ldg(&pg.rec_row[gl]); ridx = __ldg(&pg.rec_idx[gl]);
         rsrc = __ldg(&pg.rec_src[gl]); rbeg = __ldg(&pg.rec_indptr[gl]); rend = __ldg(&pg.rec_indptr[gl + 1]);
         rfac = __ldg(&pg.rec_factor[gl]);
         r_array = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
         rout = pg.rec_out[gl] + (r_array ? (size_t)t0 * S + sidx : (size_t)sidx);
         if (!r_array) racc = *rout;
+        const bool r_storage = rk == B200LP_REC_STORAGE_VOLUME || rk == B200LP_REC_STORAGE_PC || rk == B200LP_REC_MIN_VOLUME;
+        if (r_storage) { rrow = 0; rbeg = rend = 0; } else { rsrc = 0; }
     }
+    // uniform over the group: is the slower code needed at all?
+    const bool any_ratio = group_ballot<G>(rk == B200LP_REC_NODE_SUPPLIED || rk == B200LP_REC_NODE_CURTAIL, D.gmask()) != 0u;
+    const bool any_linform = group_ballot<G>(r_on && rrow < 0, D.gmask()) != 0u;
+    if (rrow < 0 && !r_on) rrow = 0;
     // storage owned by this lane
-    int sk = -1, s_row = 0, s_max = 0, s_min = 0, s_act = 0, s_beg = 0, s_end = 0;
+    int sk = -1, s_row = 0, s_max = st.k_base + K_ONE, s_min = st.k_base + K_ZERO, s_act = st.k_base + K_ONE, s_beg = 0, s_end = 0;
+    int s_vol = st.k_base + K_SCRATCH, s_pc = st.k_base + K_SCRATCH;
+    double s_rcp = 0.0;
+    bool s_fastdiv = true;
     if (gl < nst) {
         sk = __ldg(&st.st_kind[gl]); s_row = __ldg(&st.st_row[gl]);
         s_max = __ldg(&st.st_maxv_idx[gl]); s_min = __ldg(&st.st_minv_idx[gl]); s_act = __ldg(&st.st_active_idx[gl]);
         s_beg = __ldg(&pg.stflow_indptr[gl]); s_end = __ldg(&pg.stflow_indptr[gl + 1]);
+        s_vol = st.vol_base + gl; s_pc = st.pc_base + gl;
+        // max_volume constant over the launch (a literal, not a parameter) and in the safe range: divide by reciprocal
+        const double mxv = V[s_max];
+        s_fastdiv = s_max >= st.n_slots && s_max < st.vol_base && fabs(mxv) > 1e-280 && fabs(mxv) < 1e280;
+        s_rcp = s_fastdiv ? 1.0 / mxv : 0.0;
     }
+    const bool any_virtual = group_ballot<G>(sk == B200LP_ST_KIND_VIRTUAL, D.gmask()) != 0u;
+    const bool any_slowdiv = group_ballot<G>(!s_fastdiv, D.gmask()) != 0u;
     const double *days_p = pg.ts_days + t0;
 
     int status = B200LP_ST_OPTIMAL;
@@ -1123,7 +1149,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                 const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
                 TableDesc q;
                 q.ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
-                q.rows = __ldg(&pg.table_rows[tb]); q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
+                q.last = __ldg(&pg.table_rows[tb]) - 1; q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
                 V[__ldg(&pg.tab_dst[j])] = q.at(t);
             }
         }
@@ -1150,17 +1176,26 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         extract_solution(D);
         PHASE_MARK(4);
         // ---- after(): storage mass balance (Storage.after, pywr/_core.pyx:1335-1361) ---------------
-        if (sk >= 0 && (sk == B200LP_ST_KIND_STORAGE || V[s_act] != 0.0)) {
-            double flow = 0.0;
-            if (sk == B200LP_ST_KIND_STORAGE) flow = D.sm.f->ract[s_row];
-            else
-                for (int e = s_beg; e < s_end; e++) flow = fma(__ldg(&pg.stflow_w[e]), D.sm.f->x[__ldg(&pg.stflow_col[e])], flow);
-            double v = V[st.vol_base + gl] + flow * days;
+        // every lane, one instruction stream: lanes without a storage compute on scratch operands
+        {
+            double flow = D.sm.f->ract[s_row];
+            bool upd = sk >= 0;
+            if (any_virtual) {  // VirtualStorage: -sum factor * flow while active (:1483-1493)
+                if (sk == B200LP_ST_KIND_VIRTUAL) {
+                    flow = 0.0;
+                    for (int e = s_beg; e < s_end; e++) flow = fma(__ldg(&pg.stflow_w[e]), D.sm.f->x[__ldg(&pg.stflow_col[e])], flow);
+                    upd = V[s_act] != 0.0;
+                }
+            }
+            double v = V[s_vol] + flow * days;
             const double mxv = V[s_max], mnv = V[s_min];
-            if (fabs(v - mxv) < 1e-6) v = mxv;
-            if (fabs(v - mnv) < 1e-6) v = mnv;
-            V[st.vol_base + gl] = v;
-            V[st.pc_base + gl] = (mxv == 0.0) ? NAN : v / mxv;
+            v = fabs(v - mxv) < 1e-6 ? mxv : v;
+            v = fabs(v - mnv) < 1e-6 ? mnv : v;
+            double pcv = div_by_const(v, mxv, s_rcp);
+            if (any_slowdiv) {
+                if (!s_fastdiv) pcv = (mxv == 0.0) ? NAN : v / mxv;
+            }
+            if (upd) { V[s_vol] = v; V[s_pc] = pcv; }
         }
         if (nst > G) {
             for (int k = gl + G; k < nst; k += G) {  // more storages than lanes
@@ -1181,30 +1216,37 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         }
         D.sync();
         PHASE_MARK(5);
-        // ---- recorders (the lane's own one; selects instead of a divergent switch) ----------------------
-        if (rk != 0) {
-            double value = 0.0;
-            if (rrow >= 0) value = D.sm.f->ract[rrow];
-            else
-                for (int e = rbeg; e < rend; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.f->x[__ldg(&pg.rec_col[e])], value);
+        // ---- recorders (the lane's own one): one instruction stream, selects instead of a switch ---------
+        {
+            double value = D.sm.f->ract[rrow < 0 ? 0 : rrow];
+            if (any_linform) {
+                if (rrow < 0) {
+                    value = 0.0;
+                    for (int e = rbeg; e < rend; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.f->x[__ldg(&pg.rec_col[e])], value);
+                }
+            }
             const double mf = V[ridx];
             const double vv = V[st.vol_base + rsrc], pv = V[st.pc_base + rsrc];
+            const double vf = value * rfac, df = mf - value;
+            double o = vf;                                   // B200LP_REC_NODE_FLOW
+            o = rk == B200LP_REC_NODE_DEFICIT ? df : o;
+            o = rk == B200LP_REC_STORAGE_VOLUME ? vv : o;
+            o = rk == B200LP_REC_STORAGE_PC ? pv : o;
+            if (any_ratio) {
+                const double q = value / mf;
+                o = rk == B200LP_REC_NODE_SUPPLIED ? (mf == 0.0 ? 1.0 : q) : o;
+                o = rk == B200LP_REC_NODE_CURTAIL ? (mf == 0.0 ? 0.0 : 1.0 - q) : o;
+            }
+            double add = vf;                                 // B200LP_REC_MEAN_FLOW
+            add = rk == B200LP_REC_TOTAL_FLOW ? vf * days : add;
+            add = rk == B200LP_REC_TOTAL_DEFICIT ? df * days : add;
+            add = rk == B200LP_REC_DEFICIT_FREQ ? (fabs(value - mf) > 1e-6 ? 1.0 : 0.0) : add;
+            racc = rk == B200LP_REC_MIN_VOLUME ? fmin(racc, vv) : racc + add;
             if (r_array) {
-                double o;
-                if (rk == B200LP_REC_NODE_SUPPLIED) o = mf == 0.0 ? 1.0 : value / mf;
-                else if (rk == B200LP_REC_NODE_CURTAIL) o = mf == 0.0 ? 0.0 : 1.0 - value / mf;
-                else o = rk == B200LP_REC_NODE_FLOW ? value * rfac
-                       : (rk == B200LP_REC_NODE_DEFICIT ? mf - value : (rk == B200LP_REC_STORAGE_VOLUME ? vv : pv));
 #ifndef B200LP_EXP_NO_STORE
                 *rout = o;
 #endif
                 rout += S;
-            } else {
-                const double add = rk == B200LP_REC_TOTAL_DEFICIT ? (mf - value) * days
-                                 : (rk == B200LP_REC_TOTAL_FLOW ? value * rfac * days
-                                 : (rk == B200LP_REC_MEAN_FLOW ? value * rfac
-                                 : ((rk == B200LP_REC_DEFICIT_FREQ && fabs(value - mf) > 1e-6) ? 1.0 : 0.0)));
-                racc = rk == B200LP_REC_MIN_VOLUME ? fmin(racc, vv) : racc + add;
             }
         }
         if (pg.n_recorders > G) {
@@ -1238,7 +1280,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         PHASE_MARK(6);
     }
     PHASE_FLUSH;
-    if (rk != 0 && !r_array) *rout = racc;
+    if (r_on && !r_array) *rout = racc;
     // ---- persist ------------------------------------------------------------------------------------
     store_state(state, D, sidx, true);
     for (int k = gl; k < nst; k += G) {
