@@ -188,7 +188,9 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
  * batched restarted-PDHG path (first-order; role of glp_simplex for networks too large for shared
  * memory).  The environment variables B200LP_FORCE_CTA / B200LP_FORCE_PDHG force the larger engines.
  * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 1e-8: objectives within 1e-7 relative), "pdhg_max_iter"
- * (default 200000), "pdhg_check" (iterations between convergence tests, default 64).
+ * (default 200000), "pdhg_check" (iterations between convergence tests, default 64), "pdhg_tail" (when no
+ * more than this many scenarios still iterate they finish in the CTA-per-scenario shared-memory kernel;
+ * default 1024, 0 disables).
  * The simplex engines accept and ignore pdhg_* options.
  */
 int b200lp_set_option(b200lp_handle *h, const char *name, double value);

@@ -58,6 +58,8 @@ struct PdhgDev {
     const double *csr_val;
     const int *csc_ptr, *csc_row;       // ... and by columns
     const double *csc_val;
+    const int *long_rows;               // rows with more than PD_LONG entries (aggregated nodes): summed by a whole warp in the tail kernel
+    int n_long;
     double eta, tol;
     int max_iter, check;
 };
@@ -518,6 +520,259 @@ __global__ void __launch_bounds__(1024) pdhg_compact(const PdhgDev P, const Pdhg
     if (threadIdx.x == 0) *Z.n_pairs = base;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tail: ONE CTA PER SCENARIO, every vector of the scenario in shared memory, the whole remaining solve
+// (iterations, convergence tests, restarts) inside one launch.  Used when only a few scenarios still
+// iterate: on the streaming path they cost a full launch pair per iteration (latency bound, scattered
+// 16-byte accesses); here an iteration is two passes over shared memory with the shared matrix read
+// through L1/L2.  Same arithmetic per element as the streaming kernels; the reductions of the check are
+// block-wide (different summation order, same quantities).
+// ------------------------------------------------------------------------------------------------------
+constexpr int PD_TAIL_THREADS = 512;
+constexpr int PD_TAIL_CPT = 6, PD_TAIL_RPT = 3;  // columns / rows owned by a thread: n <= 3072, m_r <= 1536
+constexpr int PD_TAIL_CE = 3;                    // matrix entries per owned column cached in registers (rows: CSR in shared memory)
+constexpr int PD_LONG = 12, PD_MAX_LONG = 64;     // "long" rows and how many of them the tail kernel supports    // matrix entries per owned column / row cached in registers
+__host__ __device__ inline size_t pd_tail_smem_bytes(int n, int m_r, int nnz) {
+    // vectors, reduction scratch, long-row sums, then the CSR of the shared matrix (values + 16-bit column indices)
+    return sizeof(double) * ((size_t)6 * n + (size_t)5 * m_r + 32 * Q_COUNT + Q_COUNT + 8 + 2 * PD_MAX_LONG + (size_t)nnz) +
+           sizeof(unsigned short) * (size_t)(nnz + 8);
+}
+inline bool pd_tail_fits(int n, int m_r, int nnz, int n_long) {
+    return n_long <= PD_MAX_LONG && n <= 65535 && n <= PD_TAIL_CPT * PD_TAIL_THREADS && m_r <= PD_TAIL_RPT * PD_TAIL_THREADS &&
+           pd_tail_smem_bytes(n, m_r, nnz) <= 227 * 1024;
+}
+
+// the owned slices of the shared matrix, cached in registers for the whole launch (entries beyond the
+// cached ones - e.g. the 200-entry licence row - are read through L1/L2)
+struct PdTailCols {
+    int row[PD_TAIL_CPT][PD_TAIL_CE];
+    double val[PD_TAIL_CPT][PD_TAIL_CE];
+    unsigned more;  // bit k: column slot k has entries beyond the cached ones (rare)
+};
+struct PdTailRows {
+    int beg[PD_TAIL_RPT], end[PD_TAIL_RPT];  // entry range in the shared-memory CSR (empty for long rows)
+    int lidx[PD_TAIL_RPT];                   // >= 0: the row is a long one, its sums come from the cooperative pass
+};
+
+// sums of the long rows, one warp per row: out[2r] = A_i . u, out[2r+1] = A_i . v (lanes stride over the entries)
+__device__ __forceinline__ void pd_tail_long_rows(const PdhgDev &P, const double *rval, const unsigned short *rcol, const double *u,
+                                                  const double *v, double *out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < P.n_long; r += PD_TAIL_THREADS / 32) {
+        const int i = __ldg(&P.long_rows[r]);
+        double a = 0.0, b = 0.0;
+        for (int e = __ldg(&P.csr_ptr[i]) + lane; e < __ldg(&P.csr_ptr[i + 1]); e += 32) {
+            const int cc = rcol[e];
+            const double w = rval[e];
+            a = fma(w, u[cc], a); b = fma(w, v[cc], b);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if (lane == 0) { out[2 * r] = a; out[2 * r + 1] = b; }
+    }
+}
+
+// g = g0 - sum_e val_e * v[row_e] over column slot k = column j (entries in matrix order, as in the streaming kernels)
+__device__ __forceinline__ double pd_tail_coldot(const PdhgDev &P, const PdTailCols &C, const int k, const int j, const double g0,
+                                                 const double *v) {
+    double g = g0;
+#pragma unroll
+    for (int e = 0; e < PD_TAIL_CE; e++) g = fma(-C.val[k][e], v[C.row[k][e]], g);   // absent entries: value 0, row 0
+    if (C.more & (1u << k))
+        for (int e = __ldg(&P.csc_ptr[j]) + PD_TAIL_CE; e < __ldg(&P.csc_ptr[j + 1]); e++) g = fma(-__ldg(&P.csc_val[e]), v[__ldg(&P.csc_row[e])], g);
+    return g;
+}
+
+__global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const PdhgDev P, const PdhgState Z) {
+    extern __shared__ __align__(16) unsigned char pd_tail_raw[];
+    const int b = blockIdx.x;
+    if ((b >> 1) >= *Z.n_pairs) return;
+    const int s = 2 * Z.plist[b >> 1] + (b & 1);
+    if (Z.done[s]) return;
+    const int n = P.n, m = P.m_r, tid = threadIdx.x;
+    constexpr int NT = PD_TAIL_THREADS;
+    double *x = reinterpret_cast<double *>(pd_tail_raw), *xa = x + n, *xb = xa + n, *c = xb + n, *lc = c + n, *uc = lc + n;
+    double *y = uc + n, *ya = y + m, *lo = ya + m, *hi = lo + m, *ty = hi + m;
+    double *red = ty + m;              // [32][Q_COUNT] per-warp partial sums
+    double *tot = red + 32 * Q_COUNT;  // [Q_COUNT] totals, then decision and omega
+    double *axl = tot + Q_COUNT + 8;   // [2 * n_long] sums of the long rows
+    const int nnz = __ldg(&P.csr_ptr[m]);
+    double *rval = axl + 2 * PD_MAX_LONG;                                  // [nnz] CSR values
+    unsigned short *rcol = reinterpret_cast<unsigned short *>(rval + nnz);  // [nnz] CSR column indices
+    for (int e = tid; e < nnz; e += NT) { rval[e] = __ldg(&P.csr_val[e]); rcol[e] = (unsigned short)__ldg(&P.csr_col[e]); }
+    const size_t ld = P.ld;
+    PdTailCols C;
+    PdTailRows R;
+    C.more = 0u;
+#pragma unroll
+    for (int k = 0; k < PD_TAIL_CPT; k++) {
+        const int j = tid + k * NT;
+        int beg = 0, end = 0;
+        if (j < n) { beg = __ldg(&P.csc_ptr[j]); end = __ldg(&P.csc_ptr[j + 1]); }
+        if (end - beg > PD_TAIL_CE) C.more |= 1u << k;
+#pragma unroll
+        for (int e = 0; e < PD_TAIL_CE; e++) {
+            const bool has = beg + e < end;
+            C.row[k][e] = has ? __ldg(&P.csc_row[beg + e]) : 0;
+            C.val[k][e] = has ? __ldg(&P.csc_val[beg + e]) : 0.0;
+        }
+        if (j < n) {
+            const size_t at = (size_t)j * ld + s;
+            x[j] = Z.x[at]; xa[j] = Z.xa[at]; c[j] = Z.c[at]; lc[j] = Z.lc[at]; uc[j] = Z.uc[at];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PD_TAIL_RPT; k++) {
+        const int i = tid + k * NT;
+        R.beg[k] = R.end[k] = 0; R.lidx[k] = -1;
+        if (i < m) {
+            R.beg[k] = __ldg(&P.csr_ptr[i]); R.end[k] = __ldg(&P.csr_ptr[i + 1]);
+            if (R.end[k] - R.beg[k] > PD_LONG) {
+                for (int r = 0; r < P.n_long; r++) if (__ldg(&P.long_rows[r]) == i) R.lidx[k] = r;
+                R.end[k] = R.beg[k];  // the warp pass owns this row
+            }
+            const size_t at = (size_t)i * ld + s;
+            y[i] = Z.y[at]; ya[i] = Z.ya[at]; lo[i] = Z.lo[at]; hi[i] = Z.hi[at];
+        }
+    }
+    double omega = Z.omega[s], r0 = Z.r0[s], rprev = Z.rprev[s];
+    int kbase = Z.kbase[s], it = *Z.it0, status = -1;
+    const double bnorm = Z.bnorm[s], cnorm = Z.cnorm[s];
+    __syncthreads();
+    while (status < 0) {
+        const double tau = P.eta / omega, sig = P.eta * omega;
+        for (int q = 0; q < P.check; q++) {
+            const double kk = (double)(it - kbase), w = (kk + 1.0) / (kk + 2.0);
+#pragma unroll
+            for (int k = 0; k < PD_TAIL_CPT; k++) {  // x half-step
+                const int j = tid + k * NT;
+                if (j < n) {
+                    const double g = pd_tail_coldot(P, C, k, j, c[j], y);
+                    const double xo = x[j], xn = pd_clamp(fma(-tau, g, xo), lc[j], uc[j]);
+                    const double b2 = 2.0 * xn - xo;
+                    xb[j] = b2;
+                    x[j] = fma(w, b2, (1.0 - w) * xa[j]);
+                }
+            }
+            __syncthreads();
+            if (P.n_long > 0) { pd_tail_long_rows(P, rval, rcol, xb, xb, axl); __syncthreads(); }
+#pragma unroll
+            for (int k = 0; k < PD_TAIL_RPT; k++) {  // y half-step
+                const int i = tid + k * NT;
+                if (i < m) {
+                    double ax = R.lidx[k] >= 0 ? axl[2 * R.lidx[k]] : 0.0;
+                    for (int e = R.beg[k]; e < R.end[k]; e++) ax = fma(rval[e], xb[rcol[e]], ax);
+                    const double yo = y[i], v = fma(-sig, ax, yo);
+                    const double yn = v - sig * pd_clamp(v / sig, -hi[i], -lo[i]);
+                    y[i] = fma(w, 2.0 * yn - yo, (1.0 - w) * ya[i]);
+                }
+            }
+            __syncthreads();
+            it++;
+        }
+        // ---- check at T(z): xn -> xb, yn -> ty -------------------------------------------------------
+        double acc[Q_COUNT];
+#pragma unroll
+        for (int q = 0; q < Q_COUNT; q++) acc[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < PD_TAIL_CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < n) {
+                const double g = pd_tail_coldot(P, C, k, j, c[j], y);
+                const double xn = pd_clamp(fma(-tau, g, x[j]), lc[j], uc[j]);
+                xb[j] = xn;
+                acc[Q_DX2] = fma(xn - x[j], xn - x[j], acc[Q_DX2]);
+                acc[Q_DDX2] = fma(xn - xa[j], xn - xa[j], acc[Q_DDX2]);
+                acc[Q_POBJ] = fma(c[j], xn, acc[Q_POBJ]);
+            }
+        }
+        __syncthreads();
+        if (P.n_long > 0) { pd_tail_long_rows(P, rval, rcol, xb, x, axl); __syncthreads(); }
+#pragma unroll
+        for (int k = 0; k < PD_TAIL_RPT; k++) {
+            const int i = tid + k * NT;
+            if (i < m) {
+                double axn = R.lidx[k] >= 0 ? axl[2 * R.lidx[k]] : 0.0, ax = R.lidx[k] >= 0 ? axl[2 * R.lidx[k] + 1] : 0.0;
+                for (int e = R.beg[k]; e < R.end[k]; e++) { const double w2 = rval[e]; const int cc = rcol[e]; axn = fma(w2, xb[cc], axn); ax = fma(w2, x[cc], ax); }
+                const double v = fma(-sig, 2.0 * axn - ax, y[i]);
+                const double yn = v - sig * pd_clamp(v / sig, -hi[i], -lo[i]);
+                ty[i] = yn;
+                const double viol = axn - pd_clamp(axn, lo[i], hi[i]), dy = yn - y[i];
+                const double yp = fmax(yn, 0.0), ym = fmax(-yn, 0.0);
+                acc[Q_PR2] = fma(viol, viol, acc[Q_PR2]);
+                acc[Q_DY2] = fma(dy, dy, acc[Q_DY2]);
+                acc[Q_CROSS] = fma(dy, axn - ax, acc[Q_CROSS]);
+                acc[Q_DDY2] = fma(yn - ya[i], yn - ya[i], acc[Q_DDY2]);
+                acc[Q_DOBJR] += pd_fin(lo[i]) * yp - pd_fin(hi[i]) * ym;
+                const double il = fabs(lo[i]) < PD_BIG ? 0.0 : yp, ih = fabs(hi[i]) < PD_BIG ? 0.0 : ym;
+                acc[Q_DINFR] = fma(il, il, fma(ih, ih, acc[Q_DINFR]));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PD_TAIL_CPT; k++) {
+            const int j = tid + k * NT;
+            if (j < n) {
+                const double g = pd_tail_coldot(P, C, k, j, c[j], ty);
+                const double rp = fmax(g, 0.0), rm = fmax(-g, 0.0);
+                const double il = fabs(lc[j]) < PD_BIG ? 0.0 : rp, iu = fabs(uc[j]) < PD_BIG ? 0.0 : rm;
+                acc[Q_DRESC] = fma(il, il, fma(iu, iu, acc[Q_DRESC]));
+                acc[Q_DOBJC] += pd_fin(lc[j]) * rp - pd_fin(uc[j]) * rm;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q_COUNT; q++) {
+            double v = acc[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if ((tid & 31) == 0) red[(tid >> 5) * Q_COUNT + q] = v;
+        }
+        __syncthreads();
+        if (tid < Q_COUNT) {
+            double v = 0.0;
+            for (int wv = 0; wv < NT / 32; wv++) v += red[wv * Q_COUNT + tid];
+            tot[tid] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {  // same decision as pdhg_decide
+            const double r = sqrt(fmax(tot[Q_DX2] / tau - 2.0 * tot[Q_CROSS] + tot[Q_DY2] / sig, 0.0));
+            const double pobj = tot[Q_POBJ], dobj = tot[Q_DOBJR] + tot[Q_DOBJC];
+            const double rel = fmax(fmax(sqrt(tot[Q_PR2]) / (1.0 + bnorm), sqrt(tot[Q_DINFR] + tot[Q_DRESC]) / (1.0 + cnorm)),
+                                    fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj)));
+            if (r0 < 0.0) r0 = r;
+            const int k = it - kbase;
+            double dec = 0.0;  // 0 continue, 1 restart, 2.. finished with status dec - 2
+            if (rel < P.tol || it >= P.max_iter || !(rel == rel)) {
+                dec = 2.0 + (rel < P.tol ? B200LP_ST_OPTIMAL : (rel == rel ? B200LP_ST_ITERLIMIT : B200LP_ST_NAN));
+            } else if (r <= 0.2 * r0 || (r <= 0.8 * r0 && r > rprev) || (double)k >= 0.36 * (double)it) {
+                dec = 1.0;
+                const double ddx = sqrt(tot[Q_DDX2]), ddy = sqrt(tot[Q_DDY2]);
+                if (ddx > 1e-12 && ddy > 1e-12) omega = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+                r0 = -1.0;
+            }
+            rprev = r;
+            tot[Q_COUNT] = dec; tot[Q_COUNT + 1] = omega;
+        }
+        __syncthreads();
+        const double dec = tot[Q_COUNT];
+        omega = tot[Q_COUNT + 1];
+        if (dec >= 1.0) {  // restart or finished: z := anchor := T(z)
+            for (int j = tid; j < n; j += NT) { const double v = xb[j]; x[j] = v; xa[j] = v; }
+            for (int i = tid; i < m; i += NT) { const double v = ty[i]; y[i] = v; ya[i] = v; }
+            kbase = it;
+            if (dec >= 2.0) status = (int)(dec - 2.0);
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += NT) { const size_t at = (size_t)j * ld + s; Z.x[at] = x[j]; Z.xa[at] = x[j]; }
+    for (int i = tid; i < m; i += NT) { const size_t at = (size_t)i * ld + s; Z.y[at] = y[i]; Z.ya[at] = y[i]; }
+    if (tid == 0) {
+        Z.omega[s] = omega; Z.kbase[s] = kbase; Z.r0[s] = r0; Z.rprev[s] = rprev;
+        Z.done[s] = 1; Z.status[s] = status; Z.iters[s] = it;
+        atomicAdd(Z.total_iters, (unsigned long long)it);
+    }
+}
+
 // ---- step 5: bound snapping, un-scaling (into the xb planes), objective, node flows -------------------------
 __global__ void pdhg_unscale(const PdhgDev P, const PdhgState Z, double *__restrict__ col_flow) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -568,6 +823,7 @@ struct PdhgPlan {
     std::vector<int> csr_ptr, csr_col, csc_ptr, csc_row;
     std::vector<double> csr_val, csc_val;
     double norm_a = 1.0, eta = 1.0;
+    std::vector<int> long_rows;
 
     void build(const b200lp_structure *s, const double *consts) {
         m = s->n_rows; n = s->n_cols;
@@ -614,6 +870,9 @@ struct PdhgPlan {
             csr_ptr[r + 1] = (int)csr_col.size();
         }
         const int nnz = (int)csr_col.size();
+        long_rows.clear();
+        for (int r = 0; r < m_r; r++)
+            if (csr_ptr[r + 1] - csr_ptr[r] > PD_LONG) long_rows.push_back(r);
         dr.assign(m_r, 1.0); dc.assign(n, 1.0);
         std::vector<double> rn(m_r), cn(n);
         for (int sweep = 0; sweep <= 10; sweep++) {  // 10 Ruiz sweeps (max norm) + 1 Pock-Chambolle (1-norm)

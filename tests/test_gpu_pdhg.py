@@ -110,3 +110,21 @@ def test_pdhg_warm_start(force_pdhg):
     assert warm <= 4 * 64 * S and warm * 4 < cold
     assert np.allclose(first, ob, rtol=1e-7)
     gpu.close()
+
+
+def test_pdhg_tail_kernel_agrees_with_streaming_path(force_pdhg):
+    """The CTA-per-scenario shared-memory tail kernel and the streaming kernels are the same algorithm:
+    same objectives within tolerance, iteration totals within a restart or two."""
+    s, tr = load_case("network24.edge")
+    S, T = 40, 3
+    slots, days = synth_batch(s, tr, S, T, seed=17, common=True)
+    res, iters = [], []
+    for tail in (0, 4096):
+        gpu = _gpu(s, S)
+        gpu.set_option("pdhg_tail", tail)
+        res.append(replay(gpu, s, slots, days))
+        iters.append(gpu.stats()["pdhg_iterations"])
+        gpu.close()
+    assert res[0][3].sum() == 0 and res[1][3].sum() == 0
+    assert np.max(np.abs(res[0][2] - res[1][2]) / np.maximum(1.0, np.abs(res[1][2]))) < TOL
+    assert abs(iters[0] - iters[1]) <= 0.25 * iters[0] + 64 * S * T, iters
