@@ -22,7 +22,10 @@ Algorithm (identical on both sides; every step below has the same name in the CU
          x' = clip(x - tau (c - A^T y), lc, uc)
          y' = v - sigma clip(v / sigma, -hi, -lo),   v = y - sigma A (2 x' - x)
      every ``check`` iterations: KKT residuals of T(z); converged -> stop; restart (anchor := T(z),
-     primal weight omega updated from the movement since the last restart) when the fixed-point
+     primal weight omega updated from the movement since the last restart if both iterates moved by more
+     than 1e-5 of their norm; if only y moved and the primal residual dominates (x pinned at its bounds)
+     omega *= 4, if only x moved and the primal residual does not dominate omega /= 4; always within 1e4 of
+     ||c||/||b||) when the fixed-point
      residual fell to 20 %, or to 80 % and is growing again, or after 36 % of all iterations;
   4. warm start: every scenario keeps (x, y, omega) from its previous timestep (role of the carried-over
      basis, cython_glpk.pyx:197-232);
@@ -35,6 +38,7 @@ import scipy.sparse as sp
 REF_STATE = -(2 ** 31)
 BIG = 1e300
 ST_OPTIMAL, ST_INFEASIBLE, ST_ITERLIMIT, ST_NAN = 0, 1, 3, 4
+OMEGA_MOVE, OMEGA_SPAN, OMEGA_KICK = 1e-5, 1e4, 4.0
 
 
 def _fin(a):
@@ -216,8 +220,19 @@ def solve_scaled(plan, lo, hi, c, lc, uc, x, y, omega, valid, tol, max_iter, che
             return xn, yn, omega, it, (ST_OPTIMAL if rel < tol else ST_ITERLIMIT), restarts
         if r <= 0.2 * r0 or (r <= 0.8 * r0 and r > rprev) or k >= 0.36 * it:
             ddx, ddy = np.linalg.norm(xn - xa), np.linalg.norm(yn - ya)
-            if ddx > 1e-12 and ddy > 1e-12:
+            # update the primal weight only when both iterates really moved since the last restart (a warm-started,
+            # already optimal x barely moves and the ratio of two noise terms would blow omega up), bounded around
+            # the initial weight
+            om0 = cnorm / bnorm if (bnorm > 0 and cnorm > 0) else 1.0
+            mx, my = ddx > OMEGA_MOVE * np.linalg.norm(xn), ddy > OMEGA_MOVE * np.linalg.norm(yn)
+            e_p, e_d, e_g = pr / (1.0 + bnorm), np.sqrt(dres2) / (1.0 + cnorm), abs(pobj - dobj) / (1.0 + abs(pobj) + abs(dobj))
+            if mx and my:
                 omega = np.exp(0.5 * np.log(ddy / ddx) + 0.5 * np.log(omega))
+            elif my and e_p >= max(e_d, e_g):
+                omega *= OMEGA_KICK      # x pinned at its bounds, primal infeasible: let the dual move faster
+            elif mx and e_p < max(e_d, e_g):
+                omega /= OMEGA_KICK      # y settled, primal feasible but not optimal: let x move faster
+            omega = min(max(omega, om0 / OMEGA_SPAN), om0 * OMEGA_SPAN)
             x, y = xn.copy(), yn.copy()
             xa, ya = xn.copy(), yn.copy()
             kbase, r0, restarts = it, -1.0, restarts + 1

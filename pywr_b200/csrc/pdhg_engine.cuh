@@ -39,7 +39,24 @@ constexpr int PD_CH = 8;          // columns / rows per CTA in the iteration ker
 constexpr int PD_CH_TAIL = 2;     // ... when few scenario pairs still iterate (latency-bound tail)
 constexpr int PD_CHK = 64;        // columns / rows per CTA in the check kernels
 constexpr int PD_MAXE = 512;      // matrix entries staged in shared memory per CTA
-enum : int { Q_DX2 = 0, Q_DDX2, Q_POBJ, Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR, Q_DRESC, Q_DOBJC, Q_COUNT };
+enum : int { Q_DX2 = 0, Q_DDX2, Q_POBJ, Q_XN2, Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR, Q_YN2, Q_DRESC, Q_DOBJC, Q_COUNT };
+// primal weight update at a restart: only when both iterates moved by more than this fraction of their norm since the
+// last restart (a warm-started x that is already optimal barely moves: the ratio of two noise terms would blow omega up),
+// and never further than this factor from the initial weight ||c|| / ||b||
+constexpr double PD_OMEGA_MOVE = 1e-5, PD_OMEGA_SPAN = 1e4, PD_OMEGA_KICK = 4.0;
+
+// omega after a restart (same rule as oracle/pdhg_oracle.py::solve_scaled): the PDLP movement rule when both iterates
+// moved; a bounded kick when only one of them moved and the residual it has to repair dominates the error
+__device__ __forceinline__ double pd_new_omega(const double omega, const double ddx, const double ddy, const double xn, const double yn,
+                                               const double e_p, const double e_d, const double e_g, const double bnorm, const double cnorm) {
+    const double om0 = (bnorm > 0.0 && cnorm > 0.0) ? cnorm / bnorm : 1.0;
+    const bool mx = ddx > PD_OMEGA_MOVE * xn, my = ddy > PD_OMEGA_MOVE * yn;
+    double om = omega;
+    if (mx && my) om = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+    else if (my && e_p >= fmax(e_d, e_g)) om = omega * PD_OMEGA_KICK;
+    else if (mx && e_p < fmax(e_d, e_g)) om = omega / PD_OMEGA_KICK;
+    return fmin(fmax(om, om0 / PD_OMEGA_SPAN), om0 * PD_OMEGA_SPAN);
+}
 
 struct PdhgDev {
     int m, n, m_r, N, n_slots, n_storage, cost_clip, S, ld, nch;
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols1(const PdhgDev P, co
     const size_t ld = P.ld;
     const double2 om = ld2(Z.omega + s0);
     const double tau0 = P.eta / om.x, tau1 = P.eta / om.y;
-    double2 dx2 = {0.0, 0.0}, ddx2 = {0.0, 0.0}, pobj = {0.0, 0.0};
+    double2 dx2 = {0.0, 0.0}, ddx2 = {0.0, 0.0}, pobj = {0.0, 0.0}, xn2 = {0.0, 0.0};
     const int e0 = sh.ptr[0];
     for (int jj = 0; jj < cnt; jj++) {
         const size_t at = (size_t)(j0 + jj) * ld + s0;
@@ -328,11 +345,13 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_cols1(const PdhgDev P, co
         dx2.x = fma(xn.x - x.x, xn.x - x.x, dx2.x); dx2.y = fma(xn.y - x.y, xn.y - x.y, dx2.y);
         ddx2.x = fma(xn.x - a.x, xn.x - a.x, ddx2.x); ddx2.y = fma(xn.y - a.y, xn.y - a.y, ddx2.y);
         pobj.x = fma(c.x, xn.x, pobj.x); pobj.y = fma(c.y, xn.y, pobj.y);
+        xn2.x = fma(xn.x, xn.x, xn2.x); xn2.y = fma(xn.y, xn.y, xn2.y);
     }
     const size_t pstride = (size_t)P.nch * ld, pat = (size_t)blockIdx.y * ld + s0;
     st2(Z.part + Q_DX2 * pstride + pat, dx2);
     st2(Z.part + Q_DDX2 * pstride + pat, ddx2);
     st2(Z.part + Q_POBJ * pstride + pat, pobj);
+    st2(Z.part + Q_XN2 * pstride + pat, xn2);
 }
 
 // ---- check, pass 2 (rows): ty = yn = T_y(z); primal residual, fixed-point terms, dual objective (rows) ---
@@ -348,7 +367,7 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, con
     const size_t ld = P.ld;
     const double2 om = ld2(Z.omega + s0);
     const double sg[2] = {P.eta * om.x, P.eta * om.y};
-    double acc[6][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // pr2 dy2 cross ddy2 dobj dinf2
+    double acc[7][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};  // pr2 dy2 cross ddy2 dobj dinf2 yn2
     const int e0 = sh.ptr[0];
     for (int ii = 0; ii < cnt; ii++) {
         const size_t at = (size_t)(i0 + ii) * ld + s0;
@@ -378,14 +397,15 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, con
             acc[4][q] += pd_fin(lo[q]) * yp - pd_fin(hi[q]) * ym;
             const double il = fabs(lo[q]) < PD_BIG ? 0.0 : yp, ih = fabs(hi[q]) < PD_BIG ? 0.0 : ym;
             acc[5][q] = fma(il, il, fma(ih, ih, acc[5][q]));
+            acc[6][q] = fma(yn[q], yn[q], acc[6][q]);
         }
         double2 o; o.x = yn[0]; o.y = yn[1];
         st2(Z.ty + at, o);
     }
     const size_t pstride = (size_t)P.nch * ld, pat = (size_t)blockIdx.y * ld + s0;
-    const int qs[6] = {Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR};
+    const int qs[7] = {Q_PR2, Q_DY2, Q_CROSS, Q_DDY2, Q_DOBJR, Q_DINFR, Q_YN2};
 #pragma unroll
-    for (int k = 0; k < 6; k++) { double2 o; o.x = acc[k][0]; o.y = acc[k][1]; st2(Z.part + qs[k] * pstride + pat, o); }
+    for (int k = 0; k < 7; k++) { double2 o; o.x = acc[k][0]; o.y = acc[k][1]; st2(Z.part + qs[k] * pstride + pat, o); }
 }
 
 // ---- check, pass 3 (columns): reduced costs of yn: dual residual and dual objective (columns) -----------
@@ -436,7 +456,7 @@ __global__ void pdhg_decide(const PdhgDev P, const PdhgState Z, const int nch_co
     double q[Q_COUNT];
 #pragma unroll
     for (int k = 0; k < Q_COUNT; k++) {
-        const bool rows = (k >= Q_PR2 && k <= Q_DINFR);
+        const bool rows = (k >= Q_PR2 && k <= Q_YN2);
         const int nc = rows ? nch_rows : nch_cols;
         double acc = 0.0;
         for (int ch = 0; ch < nc; ch++) acc += Z.part[k * pstride + (size_t)ch * ld + s];
@@ -446,8 +466,9 @@ __global__ void pdhg_decide(const PdhgDev P, const PdhgState Z, const int nch_co
     const int it = *Z.it0;
     const double r = sqrt(fmax(q[Q_DX2] / tau - 2.0 * q[Q_CROSS] + q[Q_DY2] / sig, 0.0));
     const double pobj = q[Q_POBJ], dobj = q[Q_DOBJR] + q[Q_DOBJC];
-    const double rel = fmax(fmax(sqrt(q[Q_PR2]) / (1.0 + Z.bnorm[s]), sqrt(q[Q_DINFR] + q[Q_DRESC]) / (1.0 + Z.cnorm[s])),
-                            fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj)));
+    const double e_p = sqrt(q[Q_PR2]) / (1.0 + Z.bnorm[s]), e_d = sqrt(q[Q_DINFR] + q[Q_DRESC]) / (1.0 + Z.cnorm[s]);
+    const double e_g = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
+    const double rel = fmax(fmax(e_p, e_d), e_g);
     double r0 = Z.r0[s];
     if (r0 < 0.0) r0 = r;
     const int k = it - Z.kbase[s];
@@ -461,8 +482,8 @@ __global__ void pdhg_decide(const PdhgDev P, const PdhgState Z, const int nch_co
     } else {
         if (r <= 0.2 * r0 || (r <= 0.8 * r0 && r > Z.rprev[s]) || (double)k >= 0.36 * (double)it) {
             action = 1;
-            const double ddx = sqrt(q[Q_DDX2]), ddy = sqrt(q[Q_DDY2]);
-            if (ddx > 1e-12 && ddy > 1e-12) Z.omega[s] = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+            Z.omega[s] = pd_new_omega(omega, sqrt(q[Q_DDX2]), sqrt(q[Q_DDY2]), sqrt(q[Q_XN2]), sqrt(q[Q_YN2]), e_p, e_d, e_g,
+                                      Z.bnorm[s], Z.cnorm[s]);
             Z.kbase[s] = it;
             r0 = -1.0;
         }
@@ -684,6 +705,7 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
                 acc[Q_DX2] = fma(xn - x[j], xn - x[j], acc[Q_DX2]);
                 acc[Q_DDX2] = fma(xn - xa[j], xn - xa[j], acc[Q_DDX2]);
                 acc[Q_POBJ] = fma(c[j], xn, acc[Q_POBJ]);
+                acc[Q_XN2] = fma(xn, xn, acc[Q_XN2]);
             }
         }
         __syncthreads();
@@ -706,6 +728,7 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
                 acc[Q_DOBJR] += pd_fin(lo[i]) * yp - pd_fin(hi[i]) * ym;
                 const double il = fabs(lo[i]) < PD_BIG ? 0.0 : yp, ih = fabs(hi[i]) < PD_BIG ? 0.0 : ym;
                 acc[Q_DINFR] = fma(il, il, fma(ih, ih, acc[Q_DINFR]));
+                acc[Q_YN2] = fma(yn, yn, acc[Q_YN2]);
             }
         }
         __syncthreads();
@@ -737,8 +760,9 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
         if (tid == 0) {  // same decision as pdhg_decide
             const double r = sqrt(fmax(tot[Q_DX2] / tau - 2.0 * tot[Q_CROSS] + tot[Q_DY2] / sig, 0.0));
             const double pobj = tot[Q_POBJ], dobj = tot[Q_DOBJR] + tot[Q_DOBJC];
-            const double rel = fmax(fmax(sqrt(tot[Q_PR2]) / (1.0 + bnorm), sqrt(tot[Q_DINFR] + tot[Q_DRESC]) / (1.0 + cnorm)),
-                                    fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj)));
+            const double e_p = sqrt(tot[Q_PR2]) / (1.0 + bnorm), e_d = sqrt(tot[Q_DINFR] + tot[Q_DRESC]) / (1.0 + cnorm);
+            const double e_g = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
+            const double rel = fmax(fmax(e_p, e_d), e_g);
             if (r0 < 0.0) r0 = r;
             const int k = it - kbase;
             double dec = 0.0;  // 0 continue, 1 restart, 2.. finished with status dec - 2
@@ -746,8 +770,7 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
                 dec = 2.0 + (rel < P.tol ? B200LP_ST_OPTIMAL : (rel == rel ? B200LP_ST_ITERLIMIT : B200LP_ST_NAN));
             } else if (r <= 0.2 * r0 || (r <= 0.8 * r0 && r > rprev) || (double)k >= 0.36 * (double)it) {
                 dec = 1.0;
-                const double ddx = sqrt(tot[Q_DDX2]), ddy = sqrt(tot[Q_DDY2]);
-                if (ddx > 1e-12 && ddy > 1e-12) omega = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+                omega = pd_new_omega(omega, sqrt(tot[Q_DDX2]), sqrt(tot[Q_DDY2]), sqrt(tot[Q_XN2]), sqrt(tot[Q_YN2]), e_p, e_d, e_g, bnorm, cnorm);
                 r0 = -1.0;
             }
             rprev = r;
