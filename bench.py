@@ -77,9 +77,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=2.0):
+        """nvidia-smi needs a few hundred ms to start: do not begin a short timed region before it samples."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, window=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -88,6 +94,10 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        lines = [ln for ts, ln in self.lines if window is None or window[0] - 0.05 <= ts <= window[1] + 0.15]
+        if not lines:  # timed region shorter than the sampling period: the samples around it (warm-up, also under load)
+            lines = [ln for _, ln in self.lines]
+        self.lines = lines
         sm, mx, reasons = [], [], set()
         for line in self.lines:
             f = [x.strip() for x in line.split(",")]
@@ -185,6 +195,8 @@ def main():
         import torch
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -210,14 +222,15 @@ def main():
     units = S * T
 
     # ---- value: inputs resident in HBM, CUDA events on the engine's stream -------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         eng.program_reset()
         eng.run(0, T)
     eng.sync()
     st0 = eng.stats()
-    sampler = ClockSampler(local_rank)
+    sampler.wait_first()
     barrier()
-    sampler.start()
     kernel_ms = []
     eng.sync()
     barrier()
@@ -231,7 +244,7 @@ def main():
     eng.sync()
     barrier()
     wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop((t_wall0, t_wall0 + wall))
     st1 = eng.stats()
     nfail = eng.program_status()[0]
     dev_time = max_over_ranks(sum(kernel_ms) / 1e3)
