@@ -94,6 +94,7 @@ class Program:
     rec_w: np.ndarray
     recorders: List[Any] = field(default_factory=list, repr=False)  # host objects, same order as rec_*
     rec_names: List[str] = field(default_factory=list)
+    host_recorders: List[Any] = field(default_factory=list, repr=False)  # kept alive by the host mirror protocol
 
     @property
     def n_ops(self):
@@ -380,12 +381,16 @@ def _remap(refs, mapping):
     return np.array([mapping.get(int(r), int(r)) if r >= 0 else int(r) for r in refs], np.int32)
 
 
-def compile_program(model, formulation="route", recorders=None):
+def compile_program(model, formulation="route", recorders=None, allow_host_recorders=False):
     """Returns ``(structure, program)`` for a model that has been ``setup()`` and ``reset()``.
 
     ``structure`` is the LP structure with every input plane replaced by an op output or a constant
     and the storage volumes device-resident; ``program`` holds ops, tables, storage linear forms,
-    initial state and recorders.  Raises :class:`Unsupported` when the model needs the host."""
+    initial state and recorders.  Raises :class:`Unsupported` when the model needs the host.
+
+    ``allow_host_recorders``: recorders the device cannot evaluate (event / parameter / custom Python
+    recorders ...) do not raise; they are returned in ``program.host_recorders`` and the caller keeps
+    them alive with the host mirror protocol (``device_run.run_on_device``)."""
     from .bridge import _bridge
 
     base = build_structure(model, formulation)
@@ -433,11 +438,30 @@ def compile_program(model, formulation="route", recorders=None):
         "MeanFlowNodeRecorder": REC_MEAN_FLOW, "DeficitFrequencyNodeRecorder": REC_DEFICIT_FREQ,
     }
     needs_max_flow = {REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_TOTAL_DEFICIT, REC_DEFICIT_FREQ}
+    host_recorders = []
     for rec in recorders:
         cname = type(rec).__name__
         if cname == "AggregatedRecorder":
             continue  # reduces other recorders' values() on the host at read-out (a13)
-        node = _bridge.recorder_node(rec)
+        try:
+            node = _bridge.recorder_node(rec)
+        except Exception:
+            node = None
+        if allow_host_recorders and (node is None or (cname not in node_kinds and cname not in (
+                "NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"))):
+            host_recorders.append(rec)
+            continue
+        if allow_host_recorders:
+            try:  # a supported class on a node the device cannot express goes to the host as well
+                if cname in node_kinds:
+                    _flow_form(base, node, node_id)
+                    if node_kinds[cname] in needs_max_flow and id(node) not in max_flow_ref:
+                        raise Unsupported("no LP max_flow")
+                elif C.storage_index.get(id(node)) is None:
+                    raise Unsupported("not a device storage")
+            except Unsupported:
+                host_recorders.append(rec)
+                continue
         if cname in node_kinds:
             kind = node_kinds[cname]
             form = _flow_form(base, node, node_id)
@@ -511,4 +535,5 @@ def compile_program(model, formulation="route", recorders=None):
         rec_indptr=i32(rec_indptr), rec_col=i32(rec_col), rec_w=f64(rec_w), recorders=rec_objs,
         rec_names=[str(getattr(r, "name", "")) for r in rec_objs],
     )
+    prog.host_recorders = host_recorders
     return s, prog

@@ -92,3 +92,43 @@ def test_nan_raises_lp_error():
     a.connect(b)
     with pytest.raises(B200LPError):
         model.run()
+
+
+def test_host_mirror_protocol_on_the_gpu():
+    """SURVEY 8f rank 2 on the CUDA engine: a parameter recorder and a custom Python recorder stay on the host,
+    fed by per-timestep mirrors of node flows / storage volumes; device recorders run on the device."""
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from benchmarks.workloads import build_model
+    from pywr.recorders import NumpyArrayParameterRecorder, Recorder
+    from pywr_b200.device_run import run_on_device
+
+    class FlowAndVolume(Recorder):
+        def __init__(self, model, node, storage, **kw):
+            super().__init__(model, **kw)
+            self.node, self.storage = node, storage
+
+        def setup(self):
+            self.data = np.zeros((len(self.model.timestepper), len(self.model.scenarios.combinations)))
+
+        def reset(self):
+            self.data[...] = 0.0
+
+        def after(self):
+            self.data[self.model.timestepper.current.index] = np.asarray(self.node.flow) + 0.5 * np.asarray(self.storage.volume)
+
+    def make(solver):
+        m = build_model("two_reservoir", 24, years=1, solver=solver)
+        storage = [n for n in m.nodes if hasattr(n, "volume")][0]
+        node = [n for n in m.nodes if type(n).__name__ == "Output"][0]
+        param = [p for p in m.parameters if type(p).__name__ == "ControlCurveParameter"][0]
+        FlowAndVolume(m, node, storage, name="custom")
+        NumpyArrayParameterRecorder(m, param, name="param")
+        return m
+
+    m_host = make("oracle"); m_host.run()
+    m_dev = make("null"); res = run_on_device(m_dev)
+    assert sorted(res.host_recorders) == ["custom", "param"]
+    a, b = _recorder_values(m_dev), _recorder_values(m_host)
+    for k in b:
+        assert rel_diff(a[k], b[k]) <= 1e-9, k
+    assert np.ptp(b["custom"]) > 0

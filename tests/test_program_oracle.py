@@ -84,3 +84,53 @@ def test_run_on_device_with_pywr_objects():
     assert np.allclose(m2.nodes["reservoir1"].volume, m1.nodes["reservoir1"].volume, rtol=1e-12)
     assert np.allclose(m2.nodes["demand1"].flow, m1.nodes["demand1"].flow, rtol=1e-12)
     assert r2[0].to_dataframe().shape == (365, 5)
+
+
+def test_host_mirror_protocol_keeps_host_recorders_alive():
+    """recorders the device cannot evaluate (a parameter recorder, a custom Python recorder
+    reading node.flow / storage.volume every timestep) run on the host against mirrored state and see
+    exactly what they see in a host run; device recorders of the same model are unaffected."""
+    pytest.importorskip("pywr")
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.recorders import NumpyArrayNodeRecorder, NumpyArrayParameterRecorder, NumpyArrayStorageRecorder, Recorder
+    from pywr_b200.device_run import run_on_device
+    from pywr_b200.program import Unsupported
+
+    class FlowAndVolume(Recorder):
+        def __init__(self, model, node, storage, **kw):
+            super().__init__(model, **kw)
+            self.node, self.storage = node, storage
+
+        def setup(self):
+            self.data = np.zeros((len(self.model.timestepper), len(self.model.scenarios.combinations)))
+
+        def reset(self):
+            self.data[...] = 0.0
+
+        def after(self):
+            ts = self.model.timestepper.current
+            self.data[ts.index] = np.asarray(self.node.flow) ** 2 + np.asarray(self.storage.volume)
+
+    def make():
+        m = Model.load(path, solver="oracle")
+        m.timestepper.end = "2100-06-30"
+        level = [p for p in m.parameters if type(p).__name__ == "ControlCurveIndexParameter"][0]
+        return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"]), NumpyArrayNodeRecorder(m, m.nodes["demand1"]),
+                   FlowAndVolume(m, m.nodes["demand1"], m.nodes["reservoir1"], name="custom"),
+                   NumpyArrayParameterRecorder(m, m.parameters["demand_max_flow"], name="param")], level
+
+    m1, r1, _ = make(); m1.run()
+    m2, r2, _ = make(); res = run_on_device(m2, engine_factory=OracleEngine)
+    assert sorted(res.host_recorders) == ["custom", "param"]
+    for a, b in zip(r1, r2):
+        assert _rel(np.array(b.data), np.array(a.data)) <= 1e-12, b.name
+    assert np.ptp(np.array(r1[2].data)) > 0 and np.ptp(np.array(r1[3].data)) > 0
+    m3, _, _ = make()
+    with pytest.raises(Unsupported):
+        run_on_device(m3, engine_factory=OracleEngine, host_mirror=False)
