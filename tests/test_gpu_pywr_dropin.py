@@ -118,7 +118,7 @@ def test_host_mirror_protocol_on_the_gpu():
 
     def make(solver):
         m = build_model("two_reservoir", 24, years=1, solver=solver)
-        storage = [n for n in m.nodes if hasattr(n, "volume")][0]
+        storage = [n for n in m.nodes if type(n).__name__ == "Storage"][0]
         node = [n for n in m.nodes if type(n).__name__ == "Output"][0]
         param = [p for p in m.parameters if type(p).__name__ == "ControlCurveParameter"][0]
         FlowAndVolume(m, node, storage, name="custom")
