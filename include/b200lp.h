@@ -219,6 +219,13 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
 #define B200LP_OP_DIV 9           /* args: ref_a, ref_b.  a / b (AggregatedNode.get_factors_norm f0/fi,
                                      pywr/_core.pyx:921-939; DivisionParameter)                          */
 
+#define B200LP_OP_STORAGE_RESET 10 /* args: storage, flag_ref, initial_volume_ref, initial_pc_ref.  Scheduled reset of a
+                                     (virtual) storage in node.before(), i.e. BEFORE the parameters of the timestep are
+                                     evaluated (AnnualVirtualStorage / SeasonalVirtualStorage / MonthlyVirtualStorage,
+                                     pywr/nodes.py:596-757 -> Storage._reset_storage_only, pywr/_core.pyx:1294-1333):
+                                     flag 1: volume = max_volume, pc = max_volume / max_volume;  flag 2: volume and pc =
+                                     the initial ones;  0: nothing.  The op's slot receives the flag.                 */
+
 #define B200LP_AGG_SUM 0
 #define B200LP_AGG_PRODUCT 1
 #define B200LP_AGG_MIN 2

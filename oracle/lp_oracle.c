@@ -819,7 +819,7 @@ static inline double pref(const orc_handle *h, int32_t ref, const double *p) {
     return ref >= 0 ? p[ref] : h->s.consts[-ref - 1];
 }
 
-static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, const orc_scen *c, int32_t sidx, int32_t t,
+static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen *c, int32_t sidx, int32_t t,
                          double *p) {
     for (int32_t k = 0; k < pg->n_ops; k++) {
         const int32_t *a = pg->op_args + pg->op_arg_ptr[k];
@@ -869,6 +869,18 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, const or
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_STORAGE_RESET: {  /* node.before(): Storage._reset_storage_only, pywr/_core.pyx:1294-1333 */
+            const int32_t q = a[0];
+            v = pref(h, a[1], p);
+            if (v == 1.0) {
+                const double mxv = pref(h, h->s.st_maxv_ref[q], p);
+                c->vol[q] = mxv;
+                c->pc[q] = (mxv == 0.0) ? NAN : mxv / mxv;
+            } else if (v == 2.0) {
+                c->vol[q] = pref(h, a[2], p);
+                c->pc[q] = pref(h, a[3], p);
+            }
+        } break;
         default: v = NAN;
         }
         p[pg->op_dst[k]] = v;

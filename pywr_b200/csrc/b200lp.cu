@@ -119,6 +119,7 @@ struct b200lp_handle {
     int prog_steps = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of b200lp_run_pipelined
     std::vector<cudaEvent_t> pipe_events;
+    std::vector<int> h_st_maxv_idx;  // V index of every storage's max_volume (host copy, for op pre-decoding)
     struct PdhgEngine *pdhg = nullptr;  // restarted-PDHG path (pdhg_engine.cuh): LPs beyond the simplex kernels
 };
 
@@ -245,6 +246,7 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
         st_vol[k] = s->st_vol_ref[k] == B200LP_REF_STATE ? ds.vol_base + k : vidx(s->st_vol_ref[k]);
         st_minv[k] = vidx(s->st_minv_ref[k]); st_maxv[k] = vidx(s->st_maxv_ref[k]); st_act[k] = vidx(s->st_active_ref[k]);
     }
+    h->h_st_maxv_idx = st_maxv;
     const int ncost = s->cost_indptr[n];
     std::vector<int> cost_idx(ncost), dyn_idx(s->n_dyn_a);
     for (int k = 0; k < ncost; k++) {
@@ -678,6 +680,13 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
             break;
         case B200LP_OP_NEG: ok = refs(0, 1); break;
         case B200LP_OP_MAX0: case B200LP_OP_MIN0: case B200LP_OP_DIV: ok = refs(0, 2); break;
+        case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
+            ok = na >= 4 && a[0] >= 0 && a[0] < nstor;
+            if (ok) {
+                out.push_back(h->ds.vol_base + a[0]); out.push_back(h->ds.pc_base + a[0]); out.push_back(h->h_st_maxv_idx[a[0]]);
+                ok = refs(1, 3);
+            }
+            break;
         default: ok = false;
         }
         if (!ok) return fail(B200LP_E_INVALID, "malformed op");

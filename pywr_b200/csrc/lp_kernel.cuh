@@ -967,6 +967,11 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, doub
         case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
+        case B200LP_OP_STORAGE_RESET: {  // node.before(): Storage._reset_storage_only (pywr/_core.pyx:1294-1333)
+            v = V[a[3]];                 // a: volume, pc, max_volume, flag, initial volume, initial pc (V indices)
+            if (v == 1.0) { const double mxv = V[a[2]]; V[a[0]] = mxv; V[a[1]] = (mxv == 0.0) ? NAN : mxv / mxv; }
+            else if (v == 2.0) { V[a[0]] = V[a[4]]; V[a[1]] = V[a[5]]; }
+        } break;
         default: v = NAN;
         }
         V[dst] = v;

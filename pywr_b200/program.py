@@ -28,6 +28,9 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
+OP_STORAGE_RESET = 10
+# virtual storages whose reset / activation follows the calendar only (pywr/nodes.py:596-757)
+SCHEDULED_STORAGES = ("AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage")
 AGG = {"sum": 0, "product": 1, "min": 2, "max": 3, "mean": 4}
 COL_NONE, COL_SCENARIO = -1, -2
 (REC_NODE_FLOW, REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_STORAGE_VOLUME, REC_STORAGE_PC,
@@ -296,6 +299,34 @@ class _Compiler:
             raise Unsupported(f"control curve on {type(node).__name__} {getattr(node, 'name', '')!r}")
         return k
 
+    # -- calendar-driven virtual storages ----------------------------------------------------------
+    def schedule(self, node):
+        """(reset[T], active[T]) of an Annual / Seasonal / MonthlyVirtualStorage, obtained by running the
+        reference's OWN ``before(ts)`` over the calendar of the run (it depends on dates and the node's
+        internal counters only, never on flows or volumes): reset[t] is 0, 1 (volume := max_volume) or
+        2 (volume := initial volume), active[t] the ``active`` flag the LP row sees in timestep t."""
+        from pywr.parameters import Parameter
+        from .bridge import _bridge
+
+        key = ("schedule", id(node))
+        if key in self.memo:
+            return self.memo[key]
+        if isinstance(node.max_volume, Parameter):
+            raise Unsupported(f"{type(node).__name__} with a max_volume parameter")
+        sentinel = np.full(self.S, -1.2345e300)
+        reset = np.zeros(self.T)
+        active = np.zeros(self.T)
+        node.reset()
+        for t, ts in enumerate(self.timesteps):
+            _bridge.set_storage_state(node, sentinel, sentinel)
+            node.before(ts)
+            if np.asarray(node.volume)[0] != sentinel[0]:
+                reset[t] = 2.0 if getattr(node, "reset_to_initial_volume", False) else 1.0
+            active[t] = 1.0 if node.active else 0.0
+        node.reset()
+        self.memo[key] = (reset, active)
+        return self.memo[key]
+
     # -- bindings of the LP structure ------------------------------------------------------------
     def binding_ref(self, b) -> int:
         from pywr._core import StorageInput
@@ -307,6 +338,8 @@ class _Compiler:
         if kind == "volume":
             return REF_STATE
         if kind == "active":
+            if type(obj).__name__ in SCHEDULED_STORAGES:
+                return self.table(self.schedule(obj)[1].reshape(-1, 1), None)
             if type(obj).__name__ != "VirtualStorage":
                 raise Unsupported(f"{type(obj).__name__}: activation / reset schedule is host-side")
             return self.const(1.0)
@@ -412,12 +445,22 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     vol0 = np.zeros((max(base.n_storage, 1), S))
     pc0 = np.zeros((max(base.n_storage, 1), S))
     sf_indptr, sf_col, sf_w = [0], [], []
+    reset_ops = []
     for k, st in enumerate(base.storages):
         cname = type(st).__name__
-        if cname not in ("Storage", "Reservoir", "VirtualStorage"):
+        if cname not in ("Storage", "Reservoir", "VirtualStorage") + SCHEDULED_STORAGES:
             raise Unsupported(f"storage type {cname} keeps extra state on the host")
         vol0[k] = np.asarray(st._volume)
         pc0[k] = np.asarray(st._current_pc)
+        if cname in SCHEDULED_STORAGES:
+            # node.before() of the reference resets the volume on calendar dates BEFORE the parameters of that
+            # timestep are evaluated: one op at the head of the op list, fed by the precomputed schedule
+            reset, _ = C.schedule(st)
+            if reset.any():
+                flag = C.table(reset.reshape(-1, 1), None)
+                init_v = C.table(vol0[k].reshape(1, -1).copy(), COL_SCENARIO) if np.ptp(vol0[k]) > 0 else C.const(vol0[k][0])
+                init_p = C.table(pc0[k].reshape(1, -1).copy(), COL_SCENARIO) if np.ptp(pc0[k]) > 0 else C.const(pc0[k][0])
+                reset_ops.append((OP_STORAGE_RESET, C.new_slot(), [k, flag, init_v, init_p]))
         form = _flow_form(base, st, node_id)
         for c in sorted(form):
             sf_col.append(c)
@@ -509,6 +552,12 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         node_names=base.node_names, row_names=base.row_names, col_names=base.col_names,
         bindings=base.bindings, all_nodes=base.all_nodes, routes=base.routes, storages=base.storages,
     )
+    if reset_ops:
+        # op order = Model.before(): node.before() (scheduled resets) first, then the parameters.  Table ops
+        # depend on nothing and go to the very front (the CUDA kernel hoists them anyway).
+        tables_first = [op for op in C.ops if op[0] == OP_TABLE]
+        others = [op for op in C.ops if op[0] != OP_TABLE]
+        C.ops = tables_first + [(kind, dst, [int(a) for a in args]) for kind, dst, args in reset_ops] + others
     op_arg_ptr, op_args = [0], []
     for _, _, args in C.ops:
         op_args.extend(args)

@@ -37,14 +37,41 @@ CASES = [
     ("reservoir2", "tests/models/reservoir2.json", "route", None),
     ("three_storage", "tests/models/three_storage.json", "route", None),
     ("timeseries3", "tests/models/timeseries3.json", "route", None),
+    # calendar-driven virtual storages (licences): scheduled resets / activation on the device
+    ("seasonal_virtual_storage", "tests/models/seasonal_virtual_storage.json", "route", None),
+    ("annual_virtual_storage", "licence:annual", "route", None),
+    ("annual_virtual_storage_initial", "licence:annual_initial", "route", None),
+    ("monthly_virtual_storage", "licence:monthly", "route", None),
 ]
+
+
+def licence_document(kind):
+    """Variants of the reference's seasonal_virtual_storage.json with the other calendar-driven licence types."""
+    import copy
+    import json
+
+    doc = json.load(open(os.path.join(REF, "tests/models/seasonal_virtual_storage.json")))
+    lic = doc["nodes"][3]
+    if kind.startswith("annual"):
+        lic["type"] = "AnnualVirtualStorage"
+        lic.pop("end_day"); lic.pop("end_month")
+        lic.update(reset_month=4, max_volume=1500, initial_volume=900)
+        doc["timestepper"]["end"] = "2017-06-30"
+        if kind == "annual_initial":
+            lic["reset_to_initial_volume"] = True
+    elif kind == "monthly":
+        lic["type"] = "MonthlyVirtualStorage"
+        for k in ("end_day", "end_month", "reset_day", "reset_month"):
+            lic.pop(k)
+        lic.update(months=2, initial_months=1, max_volume=400, initial_volume=250)
+    return copy.deepcopy(doc)
 
 
 def add_recorders(m):
     recs = []
     for n in list(m.nodes):
         cn = type(n).__name__
-        if cn in ("Storage", "Reservoir"):
+        if cn in ("Storage", "Reservoir", "AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage"):
             recs += [NumpyArrayStorageRecorder(m, n, name=f"vol_{n.name}"),
                      NumpyArrayStorageRecorder(m, n, proportional=True, name=f"pc_{n.name}"),
                      MinimumVolumeStorageRecorder(m, n, name=f"minv_{n.name}")]
@@ -62,7 +89,8 @@ def add_recorders(m):
 
 
 def load(path, formulation, end):
-    m = Model.load(os.path.join(REF, path), solver="oracle" if formulation == "route" else "oracle-edge")
+    src = licence_document(path.split(":")[1]) if path.startswith("licence:") else os.path.join(REF, path)
+    m = Model.load(src, solver="oracle" if formulation == "route" else "oracle-edge")
     if end:
         m.timestepper.end = end
     for r in list(m.recorders):  # keep only the recorders added below
@@ -89,5 +117,7 @@ def run_case(name, path, formulation, end):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for case in CASES:
-        run_case(*case)
+        if not only or case[0] in only:
+            run_case(*case)
