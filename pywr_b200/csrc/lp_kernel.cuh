@@ -35,6 +35,10 @@
 
 #include "../../include/b200lp.h"
 
+#ifndef B200LP_RUN_MIN_BLOCKS
+#define B200LP_RUN_MIN_BLOCKS 3
+#endif
+
 namespace b200lp {
 
 #ifdef B200LP_PHASE_TIMING
@@ -1036,7 +1040,7 @@ __device__ __forceinline__ double div_by_const(const double a, const double b, c
 }
 
 template <int G, int RPL, int NC>
-__global__ void __launch_bounds__(128, (RPL == 1 ? 3 : 1))
+__global__ void __launch_bounds__(128, (RPL == 1 ? B200LP_RUN_MIN_BLOCKS : 1))
 lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, const int S, const int t0,
               const int nsteps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200lp.so")
+LIB_PATH = os.environ.get("B200LP_LIB") or os.path.join(_HERE, "libb200lp.so")  # B200LP_LIB: experiment builds
 _lib = None
 
 _dp = ctypes.POINTER(ctypes.c_double)
