@@ -128,3 +128,38 @@ def test_pdhg_tail_kernel_agrees_with_streaming_path(force_pdhg):
     assert res[0][3].sum() == 0 and res[1][3].sum() == 0
     assert np.max(np.abs(res[0][2] - res[1][2]) / np.maximum(1.0, np.abs(res[1][2]))) < TOL
     assert abs(iters[0] - iters[1]) <= 0.25 * iters[0] + 64 * S * T, iters
+
+
+def test_pdhg_is_selected_for_the_2000_node_network_and_matches_highs():
+    """SURVEY 8(d) config 4 fixture (2,073 nodes, LP 3,994 x 2,672): no simplex kernel fits, b200lp_create picks
+    the PDHG engine by itself; scenario 0 replays the recorded planes and must reproduce HiGHS's optimum of
+    every recorded timestep, scenario 1 is a world with half the inflow (no reference: convergence, and it
+    cannot do better than scenario 0)."""
+    from pywr_b200.engine import CudaEngine
+    from pywr_b200.structure import LPStructure
+
+    fix = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures", "network600.edge")
+    s = LPStructure.load(fix + ".structure.npz")
+    tr = np.load(fix + ".trace.npz")
+    S, T = 2, 5
+    gpu = CudaEngine(s, S, device=0)
+    st = gpu.stats()
+    assert st["kernel_variant"] == 200 and st["reduced_rows"] < st["n_rows"] // 2
+    vol_slots = sorted({int(r) for r in s.st_vol_ref if r >= 0})
+    slots = gpu.alloc_planes(s.n_slots)
+    cf = gpu.alloc_planes(s.n_cols)
+    ob = gpu.alloc_planes(1)
+    gpu.reset(None)
+    for t in range(T):
+        base = tr["slots"][t][:, 0]
+        fin = np.isfinite(base)
+        slots[:, 0] = base
+        slots[:, 1] = np.where(fin, base * 0.5, base)
+        slots[vol_slots, 1] = base[vol_slots]
+        assert gpu.step(float(tr["days"][t]), slots, None, cf, ob) == 0
+        ref = float(tr["objective_highs"][t, 0])
+        assert abs(ob[0, 0] - ref) <= TOL * max(1.0, abs(ref)), (t, ob[0, 0], ref)
+        assert ob[0, 1] >= ob[0, 0] - 1e-6 * abs(ob[0, 0])     # less water cannot give a better objective
+        assert cf.min() >= 0.0 and cf[:, 1].sum() < cf[:, 0].sum()
+    assert gpu.stats()["pdhg_iterations"] > 0
+    gpu.close()
