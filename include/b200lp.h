@@ -189,8 +189,9 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
  * memory).  The environment variables B200LP_FORCE_CTA / B200LP_FORCE_PDHG force the larger engines.
  * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 1e-8: objectives within 1e-7 relative), "pdhg_max_iter"
  * (default 200000), "pdhg_check" (iterations between convergence tests, default 64), "pdhg_tail" (when no
- * more than this many scenarios still iterate they finish in the CTA-per-scenario shared-memory kernel;
- * default 1024, 0 disables).
+ * more than this many scenarios still iterate after a batch of the streaming kernels they finish in the
+ * CTA-per-scenario shared-memory kernel; default: no limit whenever one scenario's vectors fit 227 KB of
+ * shared memory - measured 1.4x faster than streaming at 8,192 scenarios; 0: streaming kernels only).
  * The simplex engines accept and ignore pdhg_* options.
  */
 int b200lp_set_option(b200lp_handle *h, const char *name, double value);

@@ -20,7 +20,7 @@ Algorithm (identical on both sides; every step below has the same name in the CU
   3. reflected restarted Halpern PDHG (r2HPDHG):  z+ = w (2 T(z) - z) + (1 - w) z_anchor,
      w = (k+1)/(k+2), T = one PDHG step
          x' = clip(x - tau (c - A^T y), lc, uc)
-         y' = v - sigma clip(v / sigma, -hi, -lo),   v = y - sigma A (2 x' - x)
+         y' = v - clip(v, -sigma hi, -sigma lo),   v = y - sigma A (2 x' - x)
      every ``check`` iterations: KKT residuals of T(z); converged -> stop; restart (anchor := T(z),
      primal weight omega updated from the movement since the last restart if both iterates moved by more
      than 1e-5 of their norm; if only y moved and the primal residual dominates (x pinned at its bounds)
@@ -171,7 +171,7 @@ def assemble(plan, slots_k, days, vol_k):
 def pdhg_operator(plan, x, y, tau, sig, lo, hi, c, lc, uc):
     xn = np.clip(x - tau * (c - plan.AT @ y), lc, uc)
     v = y - sig * (plan.A @ (2.0 * xn - x))
-    yn = v - sig * np.clip(v / sig, -hi, -lo)
+    yn = v - np.clip(v, -sig * hi, -sig * lo)
     return xn, yn
 
 

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_x_kernel(const PdhgDev P, con
     }
 }
 
-// ---- y half-step:  v = y - sigma A xb;  yn = v - sigma clip(v / sigma, -hi, -lo);  y <- w (2 yn - y) + (1 - w) ya
+// ---- y half-step:  v = y - sigma A xb;  yn = v - clip(v, -sigma hi, -sigma lo);  y <- w (2 yn - y) + (1 - w) ya
 template <int CH>
 __global__ void __launch_bounds__(PD_THREADS) pdhg_y_kernel(const PdhgDev P, const PdhgState Z, const int j_in_batch) {
     __shared__ PdStage sh;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_y_kernel(const PdhgDev P, con
             ax.x = fma(v, xb.x, ax.x); ax.y = fma(v, xb.y, ax.y);
         }
         const double v0 = fma(-sg0, ax.x, y.x), v1 = fma(-sg1, ax.y, y.y);
-        const double yn0 = v0 - sg0 * pd_clamp(v0 / sg0, -hi.x, -lo.x), yn1 = v1 - sg1 * pd_clamp(v1 / sg1, -hi.y, -lo.y);
+        const double yn0 = v0 - pd_clamp(v0, -sg0 * hi.x, -sg0 * lo.x), yn1 = v1 - pd_clamp(v1, -sg1 * hi.y, -sg1 * lo.y);
         double2 yo;
         yo.x = dn.x ? y.x : fma(w0, 2.0 * yn0 - y.x, (1.0 - w0) * a.x);
         yo.y = dn.y ? y.y : fma(w1, 2.0 * yn1 - y.y, (1.0 - w1) * a.y);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(PD_THREADS) pdhg_chk_rows(const PdhgDev P, con
         for (int q = 0; q < 2; q++) {
             const double axb = 2.0 * axn[q] - ax[q];
             const double v = fma(-sg[q], axb, y[q]);
-            yn[q] = v - sg[q] * pd_clamp(v / sg[q], -hi[q], -lo[q]);
+            yn[q] = v - pd_clamp(v, -sg[q] * hi[q], -sg[q] * lo[q]);
             const double viol = axn[q] - pd_clamp(axn[q], lo[q], hi[q]);
             const double dy = yn[q] - y[q];
             const double yp = fmax(yn[q], 0.0), ym = fmax(-yn[q], 0.0);
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
                     double ax = R.lidx[k] >= 0 ? axl[2 * R.lidx[k]] : 0.0;
                     for (int e = R.beg[k]; e < R.end[k]; e++) ax = fma(rval[e], xb[rcol[e]], ax);
                     const double yo = y[i], v = fma(-sig, ax, yo);
-                    const double yn = v - sig * pd_clamp(v / sig, -hi[i], -lo[i]);
+                    const double yn = v - pd_clamp(v, -sig * hi[i], -sig * lo[i]);
                     y[i] = fma(w, 2.0 * yn - yo, (1.0 - w) * ya[i]);
                 }
             }
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(PD_TAIL_THREADS, 1) pdhg_tail_kernel(const Pdh
                 double axn = R.lidx[k] >= 0 ? axl[2 * R.lidx[k]] : 0.0, ax = R.lidx[k] >= 0 ? axl[2 * R.lidx[k] + 1] : 0.0;
                 for (int e = R.beg[k]; e < R.end[k]; e++) { const double w2 = rval[e]; const int cc = rcol[e]; axn = fma(w2, xb[cc], axn); ax = fma(w2, x[cc], ax); }
                 const double v = fma(-sig, 2.0 * axn - ax, y[i]);
-                const double yn = v - sig * pd_clamp(v / sig, -hi[i], -lo[i]);
+                const double yn = v - pd_clamp(v, -sig * hi[i], -sig * lo[i]);
                 ty[i] = yn;
                 const double viol = axn - pd_clamp(axn, lo[i], hi[i]), dy = yn - y[i];
                 const double yp = fmax(yn, 0.0), ym = fmax(-yn, 0.0);
