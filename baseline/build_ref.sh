@@ -37,4 +37,9 @@ def open_file(*a, **k):
     raise ImportError("PyTables stub")
 PY
 rm -rf "$TMP"
+# The reference's own test-suite (test modules + model documents), staged next to the install so that it can also
+# be run against the CUDA engine on the GPU box (oracle/run_reference_tests.sh b200).  baseline/_ref/ is
+# git-ignored: nothing of the reference enters the history.
+rm -rf "$HERE/_ref/_reftests"
+cp -r "$REF/tests" "$HERE/_ref/_reftests"
 echo "built pywr into $HERE/_ref"

@@ -5,11 +5,14 @@ set -uo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 SOLVER="${1:-oracle}"; shift || true
 REF="${PYWR_REFERENCE:-/root/reference}"
+TESTS="$REF/tests"
+# GPU box: /root/reference does not exist there; baseline/build_ref.sh stages the suite next to the install
+[ -d "$TESTS" ] || TESTS="$ROOT/baseline/_ref/_reftests"
 WORK="$(mktemp -d /tmp/refsuite.XXXXXX)"
 cd "$WORK"
 B200_REFSUITE_SOLVER="$SOLVER" PYTHONPATH="$ROOT:$ROOT/baseline/_ref" \
-  python -m pytest "$REF/tests" -p oracle.refsuite_plugin -p no:cacheprovider -q --no-header \
+  python -m pytest "$TESTS" -p oracle.refsuite_plugin -p no:cacheprovider -q --no-header \
   --rootdir "$WORK" -o addopts="" \
   --continue-on-collection-errors \
-  --ignore "$REF/tests/test_bisect.py" --ignore "$REF/tests/test_notebook.py" \
+  --ignore "$TESTS/test_bisect.py" --ignore "$TESTS/test_notebook.py" \
   -k "not TestSpecifyingSolver" "$@"
