@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 6
+#define B200LP_ABI_VERSION 7
 
 /* error codes */
 #define B200LP_OK 0
@@ -291,6 +291,13 @@ typedef struct b200lp_program {
     const int32_t *rec_indptr;  /* [n_recorders+1] linear form of the node kinds                       */
     const int32_t *rec_col;
     const double *rec_w;
+    /* RollingVirtualStorage (pywr/_core.pyx:1496-1536): st_roll_len[k] = timesteps - 1 of storage k (0: not rolling).
+     * The engine keeps a ring buffer [st_roll_len[k]][S] per rolling storage, filled with st_roll_init[k] (the node's
+     * _initial_utilisation) at reset; every timestep the entry of (t mod len) is added back to the volume
+     * (Storage.after with adjustment: volume clamped to [min_volume, max_volume]) and then overwritten with the
+     * volume used in this timestep (-flow * days).  Either pointer may be NULL when no storage is rolling. */
+    const int32_t *st_roll_len;  /* [n_storage] */
+    const double *st_roll_init;  /* [n_storage] */
 } b200lp_program;
 
 /* Load (copy) a program; allocates the recorder outputs on the device and resets the run state. */

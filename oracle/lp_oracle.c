@@ -687,6 +687,10 @@ typedef struct {
     double **rec_out; /* [n_recorders] host outputs */
     double *last_x;   /* [n][S] */
     int32_t n_failed, fail_scenario, fail_code, fail_step;
+    int32_t n_roll_storage;
+    double **roll_mem;   /* [n_storage] ring buffers [len][S] of the rolling virtual storages (NULL: not rolling) */
+    int32_t *roll_len;   /* [n_storage] */
+    double *roll_init;   /* [n_storage] */
     pthread_mutex_t lock;
 } orc_program;
 
@@ -720,6 +724,8 @@ static void orc_free_program(orc_program *pr) {
     free((void *)p->rec_indptr); free((void *)p->rec_col); free((void *)p->rec_w);
     if (pr->rec_out) for (int r = 0; r < p->n_recorders; r++) free(pr->rec_out[r]);
     free(pr->rec_out); free(pr->last_x);
+    if (pr->roll_mem) for (int q = 0; q < pr->n_roll_storage; q++) free(pr->roll_mem[q]);
+    free(pr->roll_mem); free(pr->roll_len); free(pr->roll_init);
     free(pr);
 }
 
@@ -737,6 +743,9 @@ void orc_program_reset(void *hv) {
         const size_t count = rec_is_array(p->rec_kind[r]) ? (size_t)p->n_steps * h->S : (size_t)h->S;
         for (size_t i = 0; i < count; i++) pr->rec_out[r][i] = (p->rec_kind[r] == B200LP_REC_MIN_VOLUME) ? INFINITY : 0.0;
     }
+    for (int32_t q = 0; q < pr->n_roll_storage; q++)
+        if (pr->roll_mem[q])
+            for (size_t i = 0; i < (size_t)pr->roll_len[q] * h->S; i++) pr->roll_mem[q][i] = pr->roll_init[q];
     pr->n_failed = 0; pr->fail_scenario = -1; pr->fail_code = 0; pr->fail_step = -1;
 }
 
@@ -785,6 +794,16 @@ int orc_load_program(void *hv, const b200lp_program *src) {
         pr->rec_out[r] = (double *)calloc(count, sizeof(double));
     }
     pr->last_x = (double *)calloc((size_t)h->n * S + 1, sizeof(double));
+    pr->n_roll_storage = h->s.n_storage;
+    pr->roll_mem = (double **)calloc(h->s.n_storage + 1, sizeof(double *));
+    pr->roll_len = (int32_t *)calloc(h->s.n_storage + 1, sizeof(int32_t));
+    pr->roll_init = (double *)calloc(h->s.n_storage + 1, sizeof(double));
+    for (int32_t q = 0; q < h->s.n_storage; q++) {
+        pr->roll_len[q] = src->st_roll_len ? src->st_roll_len[q] : 0;
+        pr->roll_init[q] = (src->st_roll_init && pr->roll_len[q] > 0) ? src->st_roll_init[q] : 0.0;
+        if (pr->roll_len[q] > 0) pr->roll_mem[q] = (double *)calloc((size_t)pr->roll_len[q] * S, sizeof(double));
+    }
+    p->st_roll_len = NULL; p->st_roll_init = NULL;  /* the copies above are the ones in use */
     pthread_mutex_init(&pr->lock, NULL);
     pr->loaded = 1;
     pthread_mutex_lock(&g_programs_lock);
@@ -929,6 +948,12 @@ static void *orc_run_worker(void *arg) {
                         flow = fma(pg->stflow_w[e], x[pg->stflow_col[e]], flow);
                 double vol = c->vol[q] + flow * days;
                 const double mxv = pref(h, s->st_maxv_ref[q], p), mnv = pref(h, s->st_minv_ref[q], p);
+                if (pr->roll_len[q] > 0) {  /* RollingVirtualStorage.after, pywr/_core.pyx:1522-1536 + :1345-1349 */
+                    double *mem = pr->roll_mem[q] + (size_t)(t % pr->roll_len[q]) * S + k;
+                    vol += *mem;
+                    vol = fmin(mxv, fmax(mnv, vol));
+                    *mem = -flow * days;
+                }
                 if (fabs(vol - mxv) < 1e-6) vol = mxv;
                 if (fabs(vol - mnv) < 1e-6) vol = mnv;
                 c->vol[q] = vol;

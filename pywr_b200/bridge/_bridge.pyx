@@ -14,7 +14,7 @@ recorder / node objects so that ``recorder.data``, ``values()``, ``aggregated_va
 import numpy as np
 cimport numpy as np
 
-from pywr._core cimport AbstractNode, AbstractStorage
+from pywr._core cimport AbstractNode, AbstractStorage, RollingVirtualStorage
 from pywr.parameters._parameters cimport (
     Parameter, ConstantScenarioParameter, ArrayIndexedParameter, ArrayIndexedScenarioParameter,
     DataFrameParameter, ScenarioMonthlyProfileParameter, ScenarioDailyProfileParameter,
@@ -84,6 +84,11 @@ def set_node_flow(AbstractNode node, double[:] flow):
     for i in range(node._flow.shape[0]):
         node._flow[i] = flow[i]
         node._prev_flow[i] = flow[i]
+
+
+def rolling_initial_utilisation(RollingVirtualStorage node):
+    """``RollingVirtualStorage._initial_utilisation`` (pywr/_core.pyx:1500-1514): what the ring buffer holds at reset."""
+    return node._initial_utilisation
 
 
 def set_storage_state(AbstractStorage node, double[:] volume, double[:] pc):

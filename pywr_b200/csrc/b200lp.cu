@@ -114,6 +114,8 @@ struct b200lp_handle {
     std::vector<double *> rec_ptr;   // device outputs
     std::vector<int> rec_kind;
     std::vector<double> init_vol, init_pc;
+    std::vector<int> roll_len, roll_off;   // rolling virtual storages: ring-buffer rows per storage
+    std::vector<double> roll_init;
     std::vector<int> table_rows, table_cols;
     std::vector<long long> table_offset;
     int prog_steps = 0;
@@ -872,6 +874,28 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     dp.last_x = (double *)q;
     if (palloc(sizeof(int) * S, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
     dp.fail_step = (int *)q;
+    // rolling virtual storages: one ring buffer [len][S] each, rows stacked in one allocation
+    h->roll_len.assign(nst ? nst : 1, 0); h->roll_off.assign(nst ? nst : 1, 0); h->roll_init.assign(nst ? nst : 1, 0.0);
+    dp.roll_len = nullptr; dp.roll_off = nullptr; dp.roll_mem = nullptr;
+    {
+        int rows = 0;
+        for (int k = 0; k < nst; k++) {
+            h->roll_len[k] = p->st_roll_len ? std::max(0, p->st_roll_len[k]) : 0;
+            h->roll_init[k] = (p->st_roll_init && h->roll_len[k] > 0) ? p->st_roll_init[k] : 0.0;
+            h->roll_off[k] = rows;
+            rows += h->roll_len[k];
+        }
+        if (rows > 0) {
+            if (palloc(sizeof(double) * (size_t)rows * S, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+            dp.roll_mem = (double *)q;
+            if (palloc(sizeof(int) * nst, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+            cudaMemcpy(q, h->roll_len.data(), sizeof(int) * nst, cudaMemcpyHostToDevice);
+            dp.roll_len = (const int *)q;
+            if (palloc(sizeof(int) * nst, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+            cudaMemcpy(q, h->roll_off.data(), sizeof(int) * nst, cudaMemcpyHostToDevice);
+            dp.roll_off = (const int *)q;
+        }
+    }
     h->table_rows.assign(p->table_rows, p->table_rows + p->n_tables);
     h->table_cols.assign(p->table_cols, p->table_cols + p->n_tables);
     h->table_offset.assign(p->table_offset, p->table_offset + p->n_tables);
@@ -898,6 +922,14 @@ int b200lp_program_reset(b200lp_handle *h) {
             CUDA_TRY(cudaMemsetAsync(h->rec_ptr[r], 0, sizeof(double) * count, h->stream));
         }
     }
+    if (h->dp.roll_mem)
+        for (int k = 0; k < h->ds.n_storage; k++)
+            if (h->roll_len[k] > 0) {
+                const size_t count = (size_t)h->roll_len[k] * S;
+                fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->dp.roll_mem + (size_t)h->roll_off[k] * S, count,
+                                                                                 h->roll_init[k]);
+                h->stats.kernel_launches++;
+            }
     CUDA_TRY(cudaMemsetAsync(h->dp.last_x, 0, sizeof(double) * S * h->ds.n, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->dp.fail_step, 0xff, sizeof(int) * S, h->stream));
     h->h_fail[0] = 0; h->h_fail[1] = INT_MAX;

@@ -919,6 +919,8 @@ struct DevProgram {
     const double *rec_factor, *rec_w;
     double *const *rec_out;  // [n_recorders] device outputs
     double *pc;              // [n_storage][S]
+    const int *roll_len, *roll_off;  // [n_storage] ring-buffer length / first row of the rolling virtual storages
+    double *roll_mem;        // [sum roll_len][S]
     double *last_x;          // [n][S]
     int *fail_step;          // [S]
 };
@@ -1133,6 +1135,13 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         s_fastdiv = s_max >= st.n_slots && s_max < st.vol_base && fabs(mxv) > 1e-280 && fabs(mxv) < 1e280;
         s_rcp = s_fastdiv ? 1.0 / mxv : 0.0;
     }
+    int s_rlen = 0;
+    double *s_rmem = nullptr;
+    if (gl < nst && pg.roll_len != nullptr) {
+        s_rlen = __ldg(&pg.roll_len[gl]);
+        s_rmem = pg.roll_mem + (size_t)__ldg(&pg.roll_off[gl]) * S + sidx;
+    }
+    const bool any_rolling = group_ballot<G>(s_rlen > 0, D.gmask()) != 0u;
     const bool any_virtual = group_ballot<G>(sk == B200LP_ST_KIND_VIRTUAL, D.gmask()) != 0u;
     const bool any_slowdiv = group_ballot<G>(!s_fastdiv, D.gmask()) != 0u;
     const double *days_p = pg.ts_days + t0;
@@ -1198,6 +1207,14 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             }
             double v = V[s_vol] + flow * days;
             const double mxv = V[s_max], mnv = V[s_min];
+            if (any_rolling) {  // RollingVirtualStorage.after (pywr/_core.pyx:1522-1536): refund what was used len steps ago
+                if (s_rlen > 0 && upd) {
+                    double *mem = s_rmem + (size_t)(t % s_rlen) * S;
+                    v += *mem;
+                    v = fmin(mxv, fmax(mnv, v));
+                    *mem = -flow * days;
+                }
+            }
             v = fabs(v - mxv) < 1e-6 ? mxv : v;
             v = fabs(v - mnv) < 1e-6 ? mnv : v;
             double pcv = div_by_const(v, mxv, s_rcp);
@@ -1217,6 +1234,12 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                         flow = fma(__ldg(&pg.stflow_w[e]), D.sm.f->x[__ldg(&pg.stflow_col[e])], flow);
                 double v = V[st.vol_base + k] + flow * days;
                 const double mxv = V[__ldg(&st.st_maxv_idx[k])], mnv = V[__ldg(&st.st_minv_idx[k])];
+                if (pg.roll_len != nullptr && __ldg(&pg.roll_len[k]) > 0) {
+                    double *mem = pg.roll_mem + ((size_t)__ldg(&pg.roll_off[k]) + (size_t)(t % __ldg(&pg.roll_len[k]))) * S + sidx;
+                    v += *mem;
+                    v = fmin(mxv, fmax(mnv, v));
+                    *mem = -flow * days;
+                }
                 if (fabs(v - mxv) < 1e-6) v = mxv;
                 if (fabs(v - mnv) < 1e-6) v = mnv;
                 V[st.vol_base + k] = v;

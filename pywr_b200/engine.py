@@ -85,7 +85,7 @@ def load_library(path: str = LIB_PATH):
         fn = getattr(L, name)  # AttributeError if the library does not export it
         fn.restype = restype
         fn.argtypes = argtypes
-    if L.b200lp_abi_version() != 6:
+    if L.b200lp_abi_version() != 7:
         raise EngineUnavailable("libb200lp.so ABI version mismatch: rebuild")
     _lib = L
     return L

@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass, field
-from typing import Any, Dict, List
+from typing import Optional,  Any, Dict, List
 
 import numpy as np
 
@@ -58,6 +58,7 @@ class b200lp_program(ctypes.Structure):
         ("initial_volume", _f64p), ("initial_pc", _f64p),
         ("rec_kind", _i32p), ("rec_src", _i32p), ("rec_ref", _i32p), ("rec_factor", _f64p),
         ("rec_row", _i32p), ("rec_indptr", _i32p), ("rec_col", _i32p), ("rec_w", _f64p),
+        ("st_roll_len", _i32p), ("st_roll_init", _f64p),
     ]
 
 
@@ -98,6 +99,8 @@ class Program:
     recorders: List[Any] = field(default_factory=list, repr=False)  # host objects, same order as rec_*
     rec_names: List[str] = field(default_factory=list)
     host_recorders: List[Any] = field(default_factory=list, repr=False)  # kept alive by the host mirror protocol
+    st_roll_len: Optional[np.ndarray] = None   # [n_storage] RollingVirtualStorage: timesteps - 1 (0: not rolling)
+    st_roll_init: Optional[np.ndarray] = None  # [n_storage] its _initial_utilisation
 
     @property
     def n_ops(self):
@@ -127,12 +130,20 @@ class Program:
                     arr = np.zeros(1, dt)
                 keep.append(arr)
                 setattr(cp, name, arr.ctypes.data_as(ctypes.POINTER(ct)))
+        n_st = max(len(self.stflow_indptr) - 1, 1)
+        rl = np.zeros(n_st, np.int32) if self.st_roll_len is None else np.ascontiguousarray(self.st_roll_len, np.int32)
+        ri = np.zeros(n_st, np.float64) if self.st_roll_init is None else np.ascontiguousarray(self.st_roll_init, np.float64)
+        keep += [rl, ri]
+        cp.st_roll_len = rl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        cp.st_roll_init = ri.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         cp._keepalive = keep
         return cp
 
     def save(self, path):
         data = {name: np.asarray(getattr(self, name)) for name in _P_I32 + _P_I64 + _P_F64}
         data["meta"] = np.array([self.n_steps, self.n_axes], np.int64)
+        if self.st_roll_len is not None:
+            data["st_roll_len"], data["st_roll_init"] = np.asarray(self.st_roll_len, np.int32), np.asarray(self.st_roll_init, np.float64)
         data["rec_names"] = np.array(self.rec_names if self.rec_names else [""] * self.n_recorders)
         np.savez_compressed(path, **data)
 
@@ -144,6 +155,8 @@ class Program:
         kw.update({n: z[n].astype(np.int64) for n in _P_I64})
         kw.update({n: z[n].astype(np.float64) for n in _P_F64})
         names = [str(x) for x in z["rec_names"]] if "rec_names" in z.files else []
+        if "st_roll_len" in z.files:
+            kw["st_roll_len"], kw["st_roll_init"] = z["st_roll_len"].astype(np.int32), z["st_roll_init"].astype(np.float64)
         return cls(n_steps=n_steps, n_axes=n_axes, rec_names=names, **kw)
 
 
@@ -340,7 +353,7 @@ class _Compiler:
         if kind == "active":
             if type(obj).__name__ in SCHEDULED_STORAGES:
                 return self.table(self.schedule(obj)[1].reshape(-1, 1), None)
-            if type(obj).__name__ != "VirtualStorage":
+            if type(obj).__name__ not in ("VirtualStorage", "RollingVirtualStorage"):
                 raise Unsupported(f"{type(obj).__name__}: activation / reset schedule is host-side")
             return self.const(1.0)
         if kind == "factor_norm":
@@ -446,12 +459,17 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     pc0 = np.zeros((max(base.n_storage, 1), S))
     sf_indptr, sf_col, sf_w = [0], [], []
     reset_ops = []
+    roll_len = np.zeros(max(base.n_storage, 1), np.int32)
+    roll_init = np.zeros(max(base.n_storage, 1), np.float64)
     for k, st in enumerate(base.storages):
         cname = type(st).__name__
-        if cname not in ("Storage", "Reservoir", "VirtualStorage") + SCHEDULED_STORAGES:
+        if cname not in ("Storage", "Reservoir", "VirtualStorage", "RollingVirtualStorage") + SCHEDULED_STORAGES:
             raise Unsupported(f"storage type {cname} keeps extra state on the host")
         vol0[k] = np.asarray(st._volume)
         pc0[k] = np.asarray(st._current_pc)
+        if cname == "RollingVirtualStorage":
+            roll_len[k] = int(st.timesteps) - 1
+            roll_init[k] = float(_bridge.rolling_initial_utilisation(st))
         if cname in SCHEDULED_STORAGES:
             # node.before() of the reference resets the volume on calendar dates BEFORE the parameters of that
             # timestep are evaluated: one op at the head of the op list, fed by the precomputed schedule
@@ -585,4 +603,6 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         rec_names=[str(getattr(r, "name", "")) for r in rec_objs],
     )
     prog.host_recorders = host_recorders
+    if roll_len.any():
+        prog.st_roll_len, prog.st_roll_init = roll_len, roll_init
     return s, prog

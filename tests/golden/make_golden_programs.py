@@ -42,6 +42,9 @@ CASES = [
     ("annual_virtual_storage", "licence:annual", "route", None),
     ("annual_virtual_storage_initial", "licence:annual_initial", "route", None),
     ("monthly_virtual_storage", "licence:monthly", "route", None),
+    # rolling licence: per-scenario ring buffer of past use on the device
+    ("rolling_virtual_storage", "tests/models/rolling_virtual_storage.json", "route", None),
+    ("rolling_virtual_storage_long", "licence:rolling", "route", None),
 ]
 
 
@@ -59,6 +62,11 @@ def licence_document(kind):
         doc["timestepper"]["end"] = "2017-06-30"
         if kind == "annual_initial":
             lic["reset_to_initial_volume"] = True
+    elif kind == "rolling":   # 30-day rolling licence smaller than the demand over the window
+        lic["type"] = "RollingVirtualStorage"
+        for k in ("end_day", "end_month", "reset_day", "reset_month"):
+            lic.pop(k)
+        lic.update(days=30, max_volume=200, initial_volume=120)
     elif kind == "monthly":
         lic["type"] = "MonthlyVirtualStorage"
         for k in ("end_day", "end_month", "reset_day", "reset_month"):
@@ -71,7 +79,8 @@ def add_recorders(m):
     recs = []
     for n in list(m.nodes):
         cn = type(n).__name__
-        if cn in ("Storage", "Reservoir", "AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage"):
+        if cn in ("Storage", "Reservoir", "AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage",
+                  "RollingVirtualStorage"):
             recs += [NumpyArrayStorageRecorder(m, n, name=f"vol_{n.name}"),
                      NumpyArrayStorageRecorder(m, n, proportional=True, name=f"pc_{n.name}"),
                      MinimumVolumeStorageRecorder(m, n, name=f"minv_{n.name}")]
