@@ -729,6 +729,17 @@ static void orc_free_program(orc_program *pr) {
     free(pr);
 }
 
+/* replace the contents of table `table` (same shape): b200lp_update_table */
+int orc_update_table(void *hv, int32_t table, const double *data) {
+    orc_handle *h = (orc_handle *)hv;
+    orc_program *pr = orc_prog_of(h);
+    if (!pr || !data || table < 0 || table >= pr->p.n_tables) return -1;
+    const b200lp_program *p = &pr->p;
+    memcpy((double *)p->table_data + p->table_offset[table], data,
+           sizeof(double) * (size_t)p->table_rows[table] * p->table_cols[table]);
+    return 0;
+}
+
 void orc_program_reset(void *hv) {
     orc_handle *h = (orc_handle *)hv;
     orc_program *pr = orc_prog_of(h);

@@ -51,6 +51,8 @@ def lib():
         L.orc_load_program.restype = ctypes.c_int
         L.orc_load_program.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_program_reset.argtypes = [ctypes.c_void_p]
+        L.orc_update_table.restype = ctypes.c_int
+        L.orc_update_table.argtypes = [ctypes.c_void_p, ctypes.c_int32, dp]
         L.orc_run.restype = ctypes.c_int
         L.orc_run.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
         L.orc_program_status.argtypes = [ctypes.c_void_p] + [ip] * 4
@@ -120,6 +122,11 @@ class OracleEngine:
 
     def program_reset(self):
         self.L.orc_program_reset(self.h)
+
+    def update_table(self, table, data):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if self.L.orc_update_table(self.h, int(table), _dp(data)) != 0:
+            raise RuntimeError("orc_update_table: bad table index or no program")
 
     def run(self, t0, n):
         rc = self.L.orc_run(self.h, int(t0), int(n))

@@ -1,0 +1,123 @@
+"""Population-at-once evaluation of a Pywr optimisation problem (BASELINE.json config 5).
+
+The reference's optimisation wrappers evaluate ONE candidate solution per ``Model.run()``
+(``pywr/optimisation/platypus.py:115-154``: set the variable parameters, run every scenario, read
+``aggregated_value()`` of the objective / constraint recorders).  Here the whole population of a
+generation becomes one more scenario axis: every variable parameter turns into a table with one column
+per candidate (``program._Compiler``, ``population_axis``), all ``P x S`` combinations run in one
+device-resident batch, and the objectives of candidate ``p`` are the recorder values aggregated over the
+combinations that carry ``p`` — with the reference's own ``Aggregator`` so that the numbers are what
+``evaluate`` returns for that candidate.
+
+    ev = PopulationEvaluator(make_model, population_size=256)      # make_model() -> pywr Model
+    objectives, constraints = ev.evaluate(X)                       # X: [P, n_variables]
+
+Supported variable parameters: ``ConstantParameter`` and ``MonthlyProfileParameter`` (double variables).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .program import ARRAY_KINDS, Unsupported, compile_program
+
+POPULATION_AXIS = "b200_population"
+
+
+class PopulationEvaluator:
+    def __init__(self, make_model, population_size, engine_factory=None, formulation="route"):
+        from pywr.core import Scenario
+        from pywr.optimisation import cache_constraints, cache_objectives, cache_variable_parameters
+        from .bridge import _bridge
+
+        self._bridge = _bridge
+        self.P = int(population_size)
+        self.model = model = make_model()
+        Scenario(model, POPULATION_AXIS, size=self.P)
+        model.setup()
+        self.variables, self.variable_map = cache_variable_parameters(model)
+        self.objectives = cache_objectives(model)
+        self.constraints = cache_constraints(model)
+        for var in self.variables:
+            if var.integer_size:
+                raise Unsupported(f"integer variables ({var.name!r}) in a population batch")
+        self.axis = [sc.name for sc in model.scenarios.scenarios].index(POPULATION_AXIS)
+        self.structure, self.program = compile_program(model, formulation, population_axis=self.axis)
+        missing = [v.name for v in self.variables if id(v) not in self.program.variable_tables]
+        if missing:
+            raise Unsupported(f"variable parameters {missing} do not feed the LP or a device recorder")
+        self.S = len(model.scenarios.combinations)
+        self.member = np.array([np.asarray(si.indices)[self.axis] for si in model.scenarios.combinations])
+        if engine_factory is None:
+            from .engine import CudaEngine
+
+            engine_factory = CudaEngine
+        self.engine = engine_factory(self.structure, self.S)
+        self.engine.load_program(self.program)
+        self.n_variables = self.variable_map[-1]
+        self.evaluations = 0
+
+    # -- one generation -----------------------------------------------------------------------------
+    def evaluate(self, X):
+        """``X[p]`` = the flat variable vector of candidate ``p`` in the reference's order
+        (``cache_variable_parameters``).  Returns ``(objectives [P, n_obj], constraints [P, n_con])`` with the
+        reference's sign convention (maximised objectives negated) and duplication of double-bounded
+        constraints."""
+        from pywr.recorders._recorders import Aggregator
+
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.shape != (self.P, self.n_variables):
+            raise ValueError(f"population must have shape {(self.P, self.n_variables)}, got {X.shape}")
+        prog, eng = self.program, self.engine
+        T = prog.n_steps
+        for i, var in enumerate(self.variables):
+            cols = X[:, self.variable_map[i]: self.variable_map[i + 1]]
+            k = prog.variable_tables[id(var)]
+            if type(var).__name__ == "ConstantParameter":
+                data = cols[:, 0].reshape(1, self.P)
+            else:                                   # MonthlyProfileParameter: value(ts) = values[ts.month - 1]
+                data = cols[:, prog.months - 1].T   # [T, P]
+            assert data.shape == (int(prog.table_rows[k]), int(prog.table_cols[k])), (data.shape, k)
+            eng.update_table(k, np.ascontiguousarray(data))
+        eng.program_reset()
+        eng.run(0, T)
+        eng.sync()
+        n_failed, scen, code, tstep = eng.program_status()
+        if n_failed:
+            raise RuntimeError(f"{n_failed} scenario(s) failed; first: scenario {scen} (candidate {self.member[scen]}), "
+                               f"status {code}, timestep {tstep}")
+        for r, rec in enumerate(prog.recorders):
+            out = eng.fetch_recorder(r, prog.rec_shape(r, self.S))
+            if int(prog.rec_kind[r]) in ARRAY_KINDS:
+                self._bridge.set_array_recorder(rec, out)
+            else:
+                self._bridge.set_constant_recorder(rec, out)
+        # MeanFlow / DeficitFrequency recorders divide by timestepper.current.index in finish() (parked past the end)
+        self.model.timestepper.reset()
+        for ts in self.model.timestepper:
+            self.model.timestep = ts
+        for rec in prog.recorders:
+            rec.finish()
+        self.evaluations += 1
+
+        def per_member(rec):
+            values = np.asarray(rec.values(), dtype=np.float64)
+            agg = Aggregator(rec.agg_func)
+            return np.array([agg.aggregate_1d(np.ascontiguousarray(values[self.member == p]), ignore_nan=rec.ignore_nan)
+                             for p in range(self.P)])
+
+        objectives = np.empty((self.P, len(self.objectives)))
+        for j, rec in enumerate(self.objectives):
+            sign = 1.0 if rec.is_objective == "minimise" else -1.0
+            objectives[:, j] = sign * per_member(rec)
+        cons = []
+        for c in self.constraints:
+            v = per_member(c)
+            cons += [v, v] if c.is_double_bounded_constraint else [v]
+        constraints = np.stack(cons, axis=1) if cons else np.empty((self.P, 0))
+        return objectives, constraints
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None

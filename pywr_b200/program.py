@@ -99,6 +99,8 @@ class Program:
     recorders: List[Any] = field(default_factory=list, repr=False)  # host objects, same order as rec_*
     rec_names: List[str] = field(default_factory=list)
     host_recorders: List[Any] = field(default_factory=list, repr=False)  # kept alive by the host mirror protocol
+    variable_tables: Dict[int, int] = field(default_factory=dict, repr=False)  # id(variable parameter) -> table
+    months: Optional[np.ndarray] = None        # [T] calendar month of every timestep (population batches)
     st_roll_len: Optional[np.ndarray] = None   # [n_storage] RollingVirtualStorage: timesteps - 1 (0: not rolling)
     st_roll_init: Optional[np.ndarray] = None  # [n_storage] its _initial_utilisation
 
@@ -196,6 +198,10 @@ class _Compiler:
         self.tables = []   # (values[rows, cols], axis)
         self.memo: Dict[int, int] = {}
         self.storage_index = {id(st): k for k, st in enumerate(structure.storages)}
+        # optimisation batch: variable parameters become tables over this scenario axis, one column
+        # per candidate solution, so that a whole population is evaluated in one run (optimisation.PopulationEvaluator)
+        self.population_axis = None
+        self.variable_tables: Dict[int, int] = {}   # id(parameter) -> table index
 
     # -- small helpers ---------------------------------------------------------------------
     def const(self, v) -> int:
@@ -248,6 +254,15 @@ class _Compiler:
         from .bridge import _bridge
 
         name = type(p).__name__
+        if self.population_axis is not None and getattr(p, "is_variable", False):
+            if name not in ("ConstantParameter", "MonthlyProfileParameter"):
+                raise Unsupported(f"variable parameter of type {name} in a population batch")
+            P = self.model.scenarios.scenarios[self.population_axis].size
+            si = self.representative(None, 0)
+            rows = [[p.get_constant_value()] * P] if name == "ConstantParameter" else [[p.value(ts, si)] * P for ts in self.timesteps]
+            self.tables.append((np.ascontiguousarray(rows, dtype=np.float64), int(self.population_axis)))
+            self.variable_tables[id(p)] = len(self.tables) - 1
+            return self.emit(OP_TABLE, [len(self.tables) - 1, 0])
         if name == "ConstantParameter" or (getattr(p, "is_constant", False) and name != "ConstantScenarioParameter"):
             return self.const(p.get_constant_value())
         info = _bridge.parameter_arrays(p)
@@ -427,7 +442,7 @@ def _remap(refs, mapping):
     return np.array([mapping.get(int(r), int(r)) if r >= 0 else int(r) for r in refs], np.int32)
 
 
-def compile_program(model, formulation="route", recorders=None, allow_host_recorders=False):
+def compile_program(model, formulation="route", recorders=None, allow_host_recorders=False, population_axis=None):
     """Returns ``(structure, program)`` for a model that has been ``setup()`` and ``reset()``.
 
     ``structure`` is the LP structure with every input plane replaced by an op output or a constant
@@ -441,6 +456,7 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
 
     base = build_structure(model, formulation)
     C = _Compiler(model, base)
+    C.population_axis = population_axis
     S, T = C.S, C.T
     node_id = {id(n): i for i, n in enumerate(base.all_nodes)}
 
@@ -603,6 +619,8 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         rec_names=[str(getattr(r, "name", "")) for r in rec_objs],
     )
     prog.host_recorders = host_recorders
+    prog.variable_tables = dict(C.variable_tables)
+    prog.months = np.array([ts.month for ts in C.timesteps], np.int32)
     if roll_len.any():
         prog.st_roll_len, prog.st_roll_init = roll_len, roll_init
     return s, prog

@@ -132,3 +132,11 @@ def test_host_mirror_protocol_on_the_gpu():
     for k in b:
         assert rel_diff(a[k], b[k]) <= 1e-9, k
     assert np.ptp(b["custom"]) > 0
+
+
+def test_population_evaluator_on_the_gpu():
+    """SURVEY 8f rank 4 on the CUDA engine: 12 candidates x 4 inflow scenarios in one batch, every candidate's
+    objectives / constraint equal to the reference's per-candidate evaluate (host run with the oracle solver)."""
+    from test_optimisation import check_population
+
+    check_population(None, P=12, n_inflow=4)
