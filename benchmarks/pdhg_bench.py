@@ -32,7 +32,11 @@ def main():
     ap.add_argument("--tol", type=float, default=None)
     ap.add_argument("--seed", type=int, default=20240903)
     ap.add_argument("--tail", type=int, default=None, help="pdhg_tail option: scenarios handed to the CTA-per-scenario kernel")
+    ap.add_argument("--engine", choices=["auto", "pdhg", "rsx"], default="pdhg",
+                    help="method of the large-LP path: pdhg (iterations), rsx (revised simplex), auto (what b200lp_create picks)")
     a = ap.parse_args()
+    if a.engine != "auto":
+        os.environ["B200LP_LARGE_ENGINE"] = a.engine
     s = LPStructure.load(FIX + ".structure.npz")
     tr = np.load(FIX + ".trace.npz")
     S, T = a.scenarios, min(a.steps, len(tr["days"]))
@@ -42,7 +46,8 @@ def main():
     vol_slots = sorted({int(r) for r in s.st_vol_ref if r >= 0})
     eng = CudaEngine(s, S, device=0)
     st0 = eng.stats()
-    assert st0["kernel_variant"] == 200, "expected the PDHG path"
+    assert st0["kernel_variant"] in (200, 300), "expected the large-LP path"
+    rsx = st0["kernel_variant"] == 300
     if a.tol is not None:
         eng.set_option("pdhg_tol", a.tol)
     if a.tail is not None:
@@ -66,7 +71,8 @@ def main():
         after = eng.stats()
         ref = float(tr["objective_highs"][t, 0])
         rows.append({"t": t, "wall_s": wall, "device_ms": after["device_ms"] - before["device_ms"],
-                     "iters": after["pdhg_iterations"] - before["pdhg_iterations"], "failed": int(nbad),
+                     "iters": after["pdhg_iterations"] - before["pdhg_iterations"], "pivots": after["pivots"] - before["pivots"],
+                     "failed": int(nbad),
                      "obj_rel_err_vs_highs": abs(float(ob[0, 0]) - ref) / max(1.0, abs(ref))})
         if nbad:
             bad, code = eng.status()
@@ -100,6 +106,22 @@ def main():
                         if a.tail == 0 else None),
            "engine": "streaming kernels only" if a.tail == 0 else "streaming first batch, then CTA-per-scenario shared-memory kernel",
            "kernel_launches": st["kernel_launches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]}
+    if rsx:
+        # revised simplex: HBM traffic is dominated by the one full read of the scenario's basis inverse per
+        # scenario-timestep (beta = -W g); pivots add rows / columns / the sparse rank-1 update
+        ldw = (m_r + 1) & ~1
+        wbytes = 8 * m_r * ldw
+        for k in ("iterations_per_scenario_step", "first_step_iterations_per_scenario", "warm_iterations_per_scenario_step"):
+            out.pop(k)
+        warm = rows[1:] if len(rows) > 1 else rows
+        warm_s = sum(r["device_ms"] for r in warm) / 1e3
+        out.update({"metric": "scenario-timesteps/sec (revised simplex, config 4)", "engine": "revised simplex, explicit basis inverse in HBM, one CTA per scenario",
+                    "pivots": st["pivots"], "refactors": st["refactors"], "pivots_per_scenario_step": st["pivots"] / (S * T),
+                    "first_step_device_s": rows[0]["device_ms"] / 1e3,
+                    "warm_value": S * len(warm) / warm_s if warm_s > 0 else None,
+                    "roofline": {"bound": "hbm", "achieved": wbytes * S * len(warm) / warm_s / 1e9 if warm_s > 0 else None, "peak": peak, "unit": "GB/s",
+                                 "frac": (wbytes * S * len(warm) / warm_s / 1e9 / peak) if warm_s > 0 else None,
+                                 "bytes_per_scenario_timestep": wbytes, "note": "warm timesteps; algorithmic bytes = one read of W per scenario-timestep"}})
     print(json.dumps(out))
     eng.close()
 

@@ -1,0 +1,44 @@
+// rsx_host.cpp — host instantiation of pywr_b200/csrc/rsx_core.cuh with a one-thread context.
+// TEST INFRASTRUCTURE ONLY (see oracle/oracle_engine.py): it lets the revised-simplex core be checked against
+// the dictionary oracle and HiGHS in a container without a GPU.  The product library instantiates the same
+// core for the device only.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../pywr_b200/csrc/rsx_core.cuh"
+
+namespace {
+struct HostCtx {
+    int tid = 0, nt = 1, lane = 0, nl = 1, warp = 0, nw = 1;
+    void sync() {}
+    bool leader() const { return true; }
+    int atomic_inc(int *p) { return (*p)++; }
+    double warp_sum(double v) { return v; }
+    void argmax(double &, int &, int &) {}
+    double min(double v) { return v; }
+    int bor(int v) { return v; }
+};
+}  // namespace
+
+extern "C" int rsx_host_run(int m, int n, const int *csr_ptr, const int *csr_col, const double *csr_val, const int *csc_ptr,
+                            const int *csc_row, const double *csc_val, int cost_dynamic, double *W, int *head,
+                            unsigned char *stat, double *d, int *info, const double *c, const double *lc, const double *uc,
+                            const double *lo, const double *hi, double *x, int cold, int *pivots, int *refactors) {
+    rsx::Lp P;
+    P.m = m; P.n = n; P.ldw = (m + 1) & ~1;
+    P.csr_ptr = csr_ptr; P.csr_col = csr_col; P.csr_val = csr_val;
+    P.csc_ptr = csc_ptr; P.csc_row = csc_row; P.csc_val = csc_val;
+    P.cost_dynamic = cost_dynamic;
+    rsx::Scen S;
+    S.W = W; S.head = head; S.stat = stat; S.d = d; S.info = info;
+    S.c = c; S.lc = lc; S.uc = uc; S.lo = lo; S.hi = hi; S.x = x; S.ld = 1;
+    unsigned char *buf = (unsigned char *)calloc(rsx::work_bytes(m, n) + 64, 1);
+    rsx::Work K;
+    rsx::work_carve(K, buf, m, n);
+    HostCtx cx;
+    int pv = 0, rf = 0;
+    const int st = rsx::run_scenario(cx, P, S, K, cold, pv, rf);
+    *pivots += pv; *refactors += rf;
+    free(buf);
+    return st;
+}

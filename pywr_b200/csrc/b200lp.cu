@@ -15,6 +15,7 @@
 #include "lp_kernel.cuh"
 #include "lp_kernel_cta.cuh"
 #include "pdhg_engine.cuh"
+#include "rsx_kernels.cuh"
 
 using namespace b200lp;
 
@@ -523,7 +524,11 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->h_counters, h->state.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->pdhg) {
+    if (h->pdhg && pdhg_is_rsx(h)) {
+        CUDA_TRY(cudaMemcpy(h->h_counters, pdhg_rsx_counters(h), 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        h->stats.pivots = (int64_t)h->h_counters[0];
+        h->stats.refactors = (int64_t)h->h_counters[1];
+    } else if (h->pdhg) {
         h->stats.pdhg_iterations = (int64_t)h->h_counters[0];
     } else {
         h->stats.pivots = (int64_t)h->h_counters[0];

@@ -1,0 +1,558 @@
+// rsx_core.cuh — bounded revised simplex with an explicit basis inverse, one CTA per scenario.
+//
+// Role (BASELINE.json north_star): the warm-started per-scenario simplex for networks whose dense dictionary
+// does not fit shared memory (config 4: 2,073 nodes, edge formulation, 1,242 x 2,672 after the structural
+// presolve).  It replaces CythonGLPKEdgeSolver._solve_scenario's glp_simplex call with the scenario's own
+// previous basis (pywr/solvers/cython_glpk.pyx:197-232 BasisManager, :1026-1063 solve + save basis, retry
+// ladder :1034-1042) on the LP assembled by the PDHG front end (same presolve, scaling and planes:
+// pdhg_engine.cuh), and returns a VERTEX, which the first-order path does not.
+//
+// Formulation: variables v = (x, r), r = A x, i.e. [A | -I] v = 0;  m basic, n non-basic variables,
+// v_B = T v_N with the dictionary T = -W N, W = B^-1.  The dictionary itself (m x n) does not fit, so only
+// W (m x m doubles, row-major, in HBM: 12.3 MB per scenario for config 4) is kept per scenario and the
+// pivot row / column are formed on demand from the shared sparse A:
+//     row r of T:     T[r][j] = -rho . A_j  (structural j),   +rho_k  (slack of row k),   rho = W[r][:]
+//     column q of T:  T[:][q] = -w,  w = W M_q,  M_q = A_q or -e_k
+// Pivoting rules, tolerances and the dual-then-primal phase structure are those of the dictionary simplex
+// (lp_kernel.cuh::Dict::solve, oracle/lp_oracle.c::dict_solve): largest violation leaves, ratio test on the
+// (shifted) reduced costs with ties -> largest pivot -> lowest index, then Dantzig primal with bound flips.
+//
+// Working vectors (bounds, reduced costs, pivot row, beta, rho, w, basis heads, statuses) live in shared
+// memory for the whole scenario solve; W is streamed: one full read per scenario-timestep (beta = -W g) plus,
+// per pivot, one row, a few columns and the rank-1 update restricted to the non-zeros of rho and w.
+//
+// The file compiles for the device (DevCtx, rsx_kernels.cuh) and, unchanged, for the host with a one-thread
+// context (oracle/rsx_host.cpp).  The host build is TEST infrastructure only: it lets the algorithm be checked
+// against the dictionary oracle and HiGHS in a container without a GPU.  The product library contains the
+// device instantiation only (no CPU fallback).
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define RSX_FN __device__ __forceinline__
+#define RSX_HD __host__ __device__ inline
+#else
+#define RSX_FN static inline
+#define RSX_HD static inline
+#endif
+
+namespace rsx {
+
+constexpr double TOL_PRIMAL = 1e-9, TOL_DUAL = 1e-9, TOL_PIVOT = 1e-9, TIE_REL = 1e-9, TIE_ABS = 1e-12;
+constexpr double BIG = 1e300;        // |bound| >= BIG is infinite (same convention as pdhg_engine.cuh)
+constexpr double DROP = 1e-14;       // |w_i| below this is treated as zero in the rank-1 update
+enum : int { V_BASIC = 1, V_NL = 2, V_NU = 3, V_NF = 4, V_NS = 5 };
+// B200LP_ST_* codes (include/b200lp.h) + one internal code
+enum : int { R_OPTIMAL = 0, R_INFEASIBLE = 1, R_UNBOUNDED = 2, R_ITERLIMIT = 3, R_NAN = 4, R_SINGULAR = 5, R_NUMERIC = 100 };
+
+struct Lp {  // shared by all scenarios
+    int m, n, ldw;  // ldw: row stride of W (m rounded up to even)
+    const int *csr_ptr, *csr_col;
+    const double *csr_val;
+    const int *csc_ptr, *csc_row;
+    const double *csc_val;
+    int cost_dynamic;  // costs change between timesteps: reduced costs are rebuilt every solve
+};
+
+struct Scen {  // one scenario: persistent state + this timestep's planes (element stride ld)
+    double *W;            // [m][ldw]
+    int *head;            // [m]
+    unsigned char *stat;  // [n+m]
+    double *d;            // [n+m]
+    int *info;            // [4]: valid, pivots since the last refactorisation, refactorisations, unused
+    const double *c, *lc, *uc, *lo, *hi;
+    double *x;
+    size_t ld;
+};
+
+struct Work {  // block-shared
+    double *LO, *HI, *d, *dw, *alpha;  // [n+m]
+    double *rho, *w, *beta, *g;        // [m]
+    int *head, *list_k, *list_i;       // [m]
+    unsigned char *stat;               // [n+m]
+    int *cnt;                          // [8]
+};
+
+RSX_HD size_t work_bytes(int m, int n) {
+    const size_t nv = (size_t)n + m;
+    return 8 * (5 * nv + 4 * (size_t)m) + 4 * (3 * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
+}
+RSX_FN void work_carve(Work &K, unsigned char *base, int m, int n) {
+    const size_t nv = (size_t)n + m;
+    double *p = reinterpret_cast<double *>(base);
+    K.LO = p; p += nv; K.HI = p; p += nv; K.d = p; p += nv; K.dw = p; p += nv; K.alpha = p; p += nv;
+    K.rho = p; p += m; K.w = p; p += m; K.beta = p; p += m; K.g = p; p += m;
+    int *q = reinterpret_cast<int *>(p);
+    K.head = q; q += m; K.list_k = q; q += m; K.list_i = q; q += m;
+    K.cnt = q; q += 8;
+    K.stat = reinterpret_cast<unsigned char *>(q);
+}
+
+// value of a non-basic variable
+RSX_FN double nb_value(const Work &K, int v) {
+    const int s = K.stat[v];
+    return s == V_NU ? K.HI[v] : (s == V_NF ? 0.0 : K.LO[v]);
+}
+
+template <class CX>
+RSX_FN void load_bounds(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int n = P.n, nv = P.n + P.m;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        double lo, hi;
+        if (v < n) { lo = S.lc[(size_t)v * S.ld]; hi = S.uc[(size_t)v * S.ld]; }
+        else { lo = S.lo[(size_t)(v - n) * S.ld]; hi = S.hi[(size_t)(v - n) * S.ld]; }
+        K.LO[v] = lo <= -BIG ? -INFINITY : lo;
+        K.HI[v] = hi >= BIG ? INFINITY : hi;
+    }
+    cx.sync();
+}
+
+// slack basis: W = -I, every structural non-basic at its lower bound, d = c
+template <class CX>
+RSX_FN void cold_init(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int m = P.m, n = P.n, nv = n + m;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        K.stat[v] = v < n ? V_NL : V_BASIC;
+        K.d[v] = v < n ? S.c[(size_t)v * S.ld] : 0.0;
+    }
+    for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = n + i;
+    const size_t tot = (size_t)m * P.ldw;
+    for (size_t e = cx.tid; e < tot; e += cx.nt) S.W[e] = 0.0;
+    cx.sync();
+    for (int i = cx.tid; i < m; i += cx.nt) S.W[(size_t)i * P.ldw + i] = -1.0;
+    cx.sync();
+}
+
+template <class CX>
+RSX_FN void load_rho(CX &cx, const Lp &P, const Scen &S, Work &K, int r) {
+    const double *row = S.W + (size_t)r * P.ldw;
+    for (int k = cx.tid; k < P.m; k += cx.nt) K.rho[k] = row[k];
+    cx.sync();
+}
+
+// alpha[v] = T[r][v] for every non-basic v (0 for basic ones); needs rho
+template <class CX>
+RSX_FN void compute_alpha(CX &cx, const Lp &P, Work &K) {
+    const int n = P.n, nv = P.n + P.m;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        double a = 0.0;
+        if (K.stat[v] != V_BASIC) {
+            if (v < n) {
+                for (int e = P.csc_ptr[v]; e < P.csc_ptr[v + 1]; e++) a = fma(K.rho[P.csc_row[e]], P.csc_val[e], a);
+                a = -a;
+            } else {
+                a = K.rho[v - n];
+            }
+        }
+        K.alpha[v] = a;
+    }
+    cx.sync();
+}
+
+// w = W M_q
+template <class CX>
+RSX_FN void compute_w(CX &cx, const Lp &P, const Scen &S, Work &K, int q) {
+    const int m = P.m, n = P.n;
+    if (q < n) {
+        const int e0 = P.csc_ptr[q], e1 = P.csc_ptr[q + 1];
+        for (int i = cx.tid; i < m; i += cx.nt) {
+            const double *row = S.W + (size_t)i * P.ldw;
+            double a = 0.0;
+            for (int e = e0; e < e1; e++) a = fma(row[P.csc_row[e]], P.csc_val[e], a);
+            K.w[i] = a;
+        }
+    } else {
+        const int k = q - n;
+        for (int i = cx.tid; i < m; i += cx.nt) K.w[i] = -S.W[(size_t)i * P.ldw + k];
+    }
+    cx.sync();
+}
+
+// rank-1 update of W for the exchange in basic position r (rho = old row r, w = W M_q), restricted to the
+// non-zeros of rho and w.  On return rho holds the new row r.
+template <class CX>
+RSX_FN void update_W(CX &cx, const Lp &P, const Scen &S, Work &K, int r) {
+    const int m = P.m;
+    if (cx.leader()) { K.cnt[0] = 0; K.cnt[1] = 0; }
+    cx.sync();
+    const double inv = 1.0 / K.w[r];
+    for (int k = cx.tid; k < m; k += cx.nt) {
+        const double v = K.rho[k];
+        if (v != 0.0) K.list_k[cx.atomic_inc(&K.cnt[0])] = k;
+        K.rho[k] = v * inv;
+    }
+    for (int i = cx.tid; i < m; i += cx.nt)
+        if (i != r && fabs(K.w[i]) > DROP) K.list_i[cx.atomic_inc(&K.cnt[1])] = i;
+    cx.sync();
+    const int nk = K.cnt[0], ni = K.cnt[1];
+    const bool sparse = nk * 4 < m;
+    double *rowr = S.W + (size_t)r * P.ldw;
+    if (sparse) { for (int t = cx.tid; t < nk; t += cx.nt) { const int k = K.list_k[t]; rowr[k] = K.rho[k]; } }
+    else { for (int k = cx.tid; k < m; k += cx.nt) rowr[k] = K.rho[k]; }
+    for (int li = cx.warp; li < ni; li += cx.nw) {
+        const int i = K.list_i[li];
+        const double wi = -K.w[i];
+        double *row = S.W + (size_t)i * P.ldw;
+        if (sparse) {
+            for (int t = cx.lane; t < nk; t += cx.nl) { const int k = K.list_k[t]; row[k] = fma(wi, K.rho[k], row[k]); }
+        } else {
+#pragma unroll 4
+            for (int k = cx.lane; k < m; k += cx.nl) row[k] = fma(wi, K.rho[k], row[k]);
+        }
+    }
+    cx.sync();
+}
+
+// reduced costs from scratch: y = W^T c_B, d_j = c_j - y . A_j (structural), y_k (slack of row k)
+template <class CX>
+RSX_FN void compute_d(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int m = P.m, n = P.n, nv = n + m;
+    for (int i = cx.tid; i < m; i += cx.nt) { const int v = K.head[i]; K.rho[i] = v < n ? S.c[(size_t)v * S.ld] : 0.0; }
+    cx.sync();
+    for (int k = cx.tid; k < m; k += cx.nt) {
+        double acc = 0.0;
+        for (int i = 0; i < m; i++) {
+            const double cb = K.rho[i];
+            if (cb != 0.0) acc = fma(cb, S.W[(size_t)i * P.ldw + k], acc);
+        }
+        K.g[k] = acc;
+    }
+    cx.sync();
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        double dv = 0.0;
+        if (K.stat[v] != V_BASIC) {
+            if (v < n) {
+                double a = 0.0;
+                for (int e = P.csc_ptr[v]; e < P.csc_ptr[v + 1]; e++) a = fma(K.g[P.csc_row[e]], P.csc_val[e], a);
+                dv = S.c[(size_t)v * S.ld] - a;
+            } else {
+                dv = K.g[v - n];
+            }
+        }
+        K.d[v] = dv;
+    }
+    cx.sync();
+}
+
+// status of every non-basic variable for the current bounds (lp_kernel.cuh::place_nonbasics_lane);
+// returns 1 if some reduced cost is dual infeasible for the bound the variable has to sit on
+template <class CX>
+RSX_FN int place_nonbasics(CX &cx, const Lp &P, Work &K) {
+    const int nv = P.n + P.m;
+    int infeas = 0;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        const int s0 = K.stat[v];
+        if (s0 == V_BASIC) continue;
+        const double lo = K.LO[v], hi = K.HI[v], dj = K.d[v];
+        const bool lo_fin = lo > -INFINITY, hi_fin = hi < INFINITY, fx = lo == hi;
+        const bool dpos = dj > TOL_DUAL, dneg = dj < -TOL_DUAL;
+        const int s_box = dpos ? V_NL : (dneg ? V_NU : ((s0 == V_NL || s0 == V_NU) ? s0 : V_NL));
+        int s = lo_fin ? (hi_fin ? s_box : V_NL) : (hi_fin ? V_NU : V_NF);
+        if (fx) s = V_NS;
+        const bool bad = lo_fin ? (!hi_fin && dneg) : (hi_fin ? dpos : (dpos || dneg));
+        if (!fx && bad) infeas = 1;
+        K.stat[v] = (unsigned char)s;
+    }
+    infeas = cx.bor(infeas);
+    return infeas;
+}
+
+// beta = -W g,  g = N x_N  (one full read of W)
+template <class CX>
+RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int m = P.m, n = P.n;
+    for (int i = cx.tid; i < m; i += cx.nt) {
+        double acc = 0.0;
+        for (int e = P.csr_ptr[i]; e < P.csr_ptr[i + 1]; e++) {
+            const int j = P.csr_col[e];
+            if (K.stat[j] != V_BASIC) acc = fma(P.csr_val[e], nb_value(K, j), acc);
+        }
+        if (K.stat[n + i] != V_BASIC) acc -= nb_value(K, n + i);
+        K.g[i] = acc;
+    }
+    cx.sync();
+    for (int i = cx.warp; i < m; i += cx.nw) {
+        const double *row = S.W + (size_t)i * P.ldw;
+        double a0 = 0.0, a1 = 0.0;
+        int k = cx.lane;
+        for (; k + cx.nl < m; k += 2 * cx.nl) { a0 = fma(row[k], K.g[k], a0); a1 = fma(row[k + cx.nl], K.g[k + cx.nl], a1); }
+        if (k < m) a0 = fma(row[k], K.g[k], a0);
+        const double acc = cx.warp_sum(a0 + a1);
+        if (cx.lane == 0) K.beta[i] = -acc;
+    }
+    cx.sync();
+}
+
+template <class CX>
+RSX_FN void init_dw(CX &cx, const Lp &P, Work &K, int shifted) {
+    const int nv = P.n + P.m;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        double w = K.d[v];
+        if (shifted) {
+            const int s = K.stat[v];
+            if ((s == V_NL && w < -TOL_DUAL) || (s == V_NU && w > TOL_DUAL) || (s == V_NF && fabs(w) > TOL_DUAL)) w = 0.0;
+        }
+        K.dw[v] = w;
+    }
+    cx.sync();
+}
+
+// exchange basic position r (variable p) with non-basic q; rho, alpha (row r) and w (column q) are current
+template <class CX>
+RSX_FN void do_pivot(CX &cx, const Lp &P, const Scen &S, Work &K, int r, int q, int to_upper, bool use_dw) {
+    const int m = P.m, nv = P.n + P.m;
+    const int p = K.head[r];
+    const double plo = K.LO[p], phi = K.HI[p];
+    const double a_rq = -K.w[r];
+    const double target = to_upper ? phi : plo;
+    const double theta = (target - K.beta[r]) / a_rq;  // change of v_q
+    const double xq_old = nb_value(K, q);
+    const double rd = K.d[q] / a_rq, rw = use_dw ? K.dw[q] / a_rq : 0.0;
+    cx.sync();
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        if (K.stat[v] == V_BASIC || v == q) continue;
+        K.d[v] = fma(-rd, K.alpha[v], K.d[v]);
+        if (use_dw) K.dw[v] = fma(-rw, K.alpha[v], K.dw[v]);
+    }
+    for (int i = cx.tid; i < m; i += cx.nt)
+        if (i != r) K.beta[i] = fma(-theta, K.w[i], K.beta[i]);
+    cx.sync();
+    if (cx.leader()) {
+        K.d[p] = rd; K.dw[p] = use_dw ? rw : rd;
+        K.d[q] = 0.0; K.dw[q] = 0.0;
+        K.beta[r] = xq_old + theta;
+        K.head[r] = q;
+        K.stat[q] = V_BASIC;
+        K.stat[p] = (unsigned char)((plo == phi) ? V_NS : (to_upper ? V_NU : V_NL));
+    }
+    update_W(cx, P, S, K, r);  // syncs
+}
+
+// the simplex proper (Dict::solve): dual phase on the (shifted) reduced costs, then primal clean-up
+template <class CX>
+RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
+    const int m = P.m, nv = P.n + P.m;
+    const int cap_bland = 20 * nv + 50, cap_fail = 200 * nv + 1000;
+    int shifted = place_nonbasics(cx, P, K);
+    cx.sync();
+    compute_beta(cx, P, S, K);
+    bool dw_ready = false;
+    int phase = 0;
+    for (int it = 0;; it++) {
+        if (it > cap_fail) return R_ITERLIMIT;
+        const bool bland = it > cap_bland;
+        int r, q, to_upper;
+        if (phase == 0) {
+            double worst = -1.0; int bi = -1, bd = 0;
+            for (int i = cx.tid; i < m; i += cx.nt) {
+                const int v = K.head[i];
+                const double b = K.beta[i], lo = K.LO[v], hi = K.HI[v];
+                double viol = 0.0; int dd = 0;
+                if (b < lo - TOL_PRIMAL * (1.0 + fabs(lo))) { viol = lo - b; dd = 1; }
+                else if (b > hi + TOL_PRIMAL * (1.0 + fabs(hi))) { viol = b - hi; dd = -1; }
+                if (b != b) { viol = INFINITY; dd = 2; }
+                if (dd != 0) {
+                    if (bland) viol = 1.0;
+                    if (bi < 0 || viol > worst) { worst = viol; bi = i; bd = dd; }
+                }
+            }
+            cx.argmax(worst, bi, bd);
+            if (bi < 0) {
+                if (!shifted) return R_OPTIMAL;
+                phase = 1; shifted = 0;
+                continue;
+            }
+            if (bd == 2) return R_NUMERIC;
+            if (!dw_ready) { init_dw(cx, P, K, shifted); dw_ready = true; }
+            r = bi;
+            const double dir = (double)bd;
+            load_rho(cx, P, S, K, r);
+            compute_alpha(cx, P, K);
+            double rmin = INFINITY;
+            for (int v = cx.tid; v < nv; v += cx.nt) {
+                const int s = K.stat[v];
+                const double a = K.alpha[v] * dir;
+                const bool ok = (s == V_NL && a > TOL_PIVOT) || (s == V_NU && a < -TOL_PIVOT) || (s == V_NF && fabs(a) > TOL_PIVOT);
+                if (ok) rmin = fmin(rmin, fabs(K.dw[v]) / fabs(a));
+            }
+            rmin = cx.min(rmin);
+            if (rmin == INFINITY) return R_INFEASIBLE;
+            const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
+            double amax = -1.0; int aux = 0;
+            q = -1;
+            for (int v = cx.tid; v < nv; v += cx.nt) {
+                const int s = K.stat[v];
+                const double a = K.alpha[v] * dir;
+                const bool ok = (s == V_NL && a > TOL_PIVOT) || (s == V_NU && a < -TOL_PIVOT) || (s == V_NF && fabs(a) > TOL_PIVOT);
+                if (!ok) continue;
+                if (fabs(K.dw[v]) / fabs(a) > thr) continue;
+                const double key = bland ? 1.0 : fabs(a);
+                if (q < 0 || key > amax) { amax = key; q = v; }
+            }
+            cx.argmax(amax, q, aux);
+            to_upper = bd < 0;  // the leaving variable goes to the bound it violated
+            compute_w(cx, P, S, K, q);
+            if (!(fabs(K.alpha[q] + K.w[r]) <= 1e-6 * (1.0 + fabs(K.alpha[q])))) return R_NUMERIC;  // W has drifted
+        } else {
+            double worst = -1.0; int dirn = 0;
+            q = -1;
+            for (int v = cx.tid; v < nv; v += cx.nt) {
+                const int s = K.stat[v];
+                if (s == V_BASIC || s == V_NS) continue;
+                const double dj = K.d[v];
+                int dd = 0;
+                if ((s == V_NL || s == V_NF) && dj < -TOL_DUAL) dd = 1;
+                else if ((s == V_NU || s == V_NF) && dj > TOL_DUAL) dd = -1;
+                if (dd != 0) {
+                    const double key = bland ? 1.0 : fabs(dj);
+                    if (q < 0 || key > worst) { worst = key; q = v; dirn = dd; }
+                }
+            }
+            cx.argmax(worst, q, dirn);
+            if (q < 0) return R_OPTIMAL;
+            const double dir = (double)dirn;
+            const double inlo = K.LO[q], inhi = K.HI[q];
+            double tmin = inhi - inlo;
+            if (!(tmin < INFINITY)) tmin = INFINITY;
+            compute_w(cx, P, S, K, q);
+            double step_min = INFINITY;
+            for (int i = cx.tid; i < m; i += cx.nt) {
+                const double a = -K.w[i] * dir;
+                const int v = K.head[i];
+                double step = INFINITY;
+                if (a > TOL_PIVOT) { if (K.HI[v] < INFINITY) step = (K.HI[v] - K.beta[i]) / a; }
+                else if (a < -TOL_PIVOT) { if (K.LO[v] > -INFINITY) step = (K.LO[v] - K.beta[i]) / a; }
+                if (step < 0.0) step = 0.0;
+                step_min = fmin(step_min, step);
+            }
+            step_min = cx.min(step_min);
+            if (step_min == INFINITY && tmin == INFINITY) return R_UNBOUNDED;
+            if (tmin <= step_min) {  // bound flip of the entering variable
+                const double delta = dir * tmin;
+                for (int i = cx.tid; i < m; i += cx.nt) K.beta[i] = fma(-delta, K.w[i], K.beta[i]);
+                if (cx.leader()) K.stat[q] = (unsigned char)(dirn > 0 ? V_NU : V_NL);
+                cx.sync();
+                continue;
+            }
+            const double thr = step_min * (1.0 + TIE_REL) + TIE_ABS;
+            double amax = -1.0; int bi = -1, up = 0;
+            for (int i = cx.tid; i < m; i += cx.nt) {
+                const double a = -K.w[i] * dir;
+                const int v = K.head[i];
+                double step = INFINITY; int u = 0;
+                if (a > TOL_PIVOT) { if (K.HI[v] < INFINITY) { step = (K.HI[v] - K.beta[i]) / a; u = 1; } }
+                else if (a < -TOL_PIVOT) { if (K.LO[v] > -INFINITY) step = (K.LO[v] - K.beta[i]) / a; }
+                if (step < 0.0) step = 0.0;
+                if (step > thr) continue;
+                const double key = bland ? 1.0 : fabs(a);
+                if (bi < 0 || key > amax) { amax = key; bi = i; up = u; }
+            }
+            cx.argmax(amax, bi, up);
+            if (bi < 0) return R_NUMERIC;
+            r = bi; to_upper = up;
+            load_rho(cx, P, S, K, r);
+            compute_alpha(cx, P, K);
+        }
+        do_pivot(cx, P, S, K, r, q, to_upper, phase == 0);
+        pivots++;
+    }
+}
+
+// Rebuild W for the basis recorded in stat[] by pivoting the basic structurals into the slack basis
+// (Dict::refactor).  Returns 0, or -1 if the basis is singular.
+template <class CX>
+RSX_FN int refactor(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int m = P.m, n = P.n;
+    for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = n + i;
+    const size_t tot = (size_t)m * P.ldw;
+    for (size_t e = cx.tid; e < tot; e += cx.nt) S.W[e] = 0.0;
+    cx.sync();
+    for (int i = cx.tid; i < m; i += cx.nt) S.W[(size_t)i * P.ldw + i] = -1.0;
+    cx.sync();
+    for (int q = 0; q < n; q++) {
+        if (K.stat[q] != V_BASIC) continue;
+        compute_w(cx, P, S, K, q);
+        double best = TOL_PIVOT; int bi = -1, aux = 0;
+        for (int i = cx.tid; i < m; i += cx.nt) {
+            const int v = K.head[i];
+            if (v < n || K.stat[v] == V_BASIC) continue;  // already a structural, or a slack that stays basic
+            const double a = fabs(K.w[i]);
+            if (a > best) { best = a; bi = i; }
+        }
+        if (bi < 0) best = -1.0;
+        cx.argmax(best, bi, aux);
+        if (bi < 0) return -1;
+        load_rho(cx, P, S, K, bi);
+        update_W(cx, P, S, K, bi);
+        if (cx.leader()) K.head[bi] = q;
+        cx.sync();
+    }
+    return 0;
+}
+
+// x of the structurals into the plane, row activities into g; returns the largest relative residual |A x - r|
+template <class CX>
+RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
+    const int m = P.m, n = P.n, nv = n + m;
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        if (K.stat[v] == V_BASIC) continue;
+        const double val = nb_value(K, v);
+        if (v < n) S.x[(size_t)v * S.ld] = val; else K.g[v - n] = val;
+    }
+    for (int i = cx.tid; i < m; i += cx.nt) {
+        const int v = K.head[i];
+        if (v < n) S.x[(size_t)v * S.ld] = K.beta[i]; else K.g[v - n] = K.beta[i];
+    }
+    cx.sync();
+    double worst = -1.0; int bi = -1, aux = 0;
+    for (int i = cx.tid; i < m; i += cx.nt) {
+        double acc = 0.0;
+        for (int e = P.csr_ptr[i]; e < P.csr_ptr[i + 1]; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
+        const double gi = K.g[i];
+        double res = fabs(acc - gi) / (1.0 + fabs(gi));
+        if (res != res) res = INFINITY;
+        if (bi < 0 || res > worst) { worst = res; bi = i; }
+    }
+    cx.argmax(worst, bi, aux);
+    return worst;
+}
+
+// One scenario, one timestep: warm start from the stored basis (or the slack basis when `cold`), retry ladder
+// (re-factorise the same basis, then restart from the slack basis), state written back.
+template <class CX>
+RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, int &pivots, int &refactors) {
+    const int m = P.m, nv = P.n + P.m;
+    load_bounds(cx, P, S, K);
+    const bool valid = !cold && S.info[0] != 0;
+    if (valid) {
+        for (int v = cx.tid; v < nv; v += cx.nt) { K.stat[v] = S.stat[v]; K.d[v] = S.d[v]; }
+        for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = S.head[i];
+        cx.sync();
+    }
+    int status = R_OPTIMAL;
+    for (int attempt = valid ? 0 : 2; attempt < 3; attempt++) {
+        if (attempt == 1) {
+            refactors++;
+            if (refactor(cx, P, S, K) != 0) continue;
+            compute_d(cx, P, S, K);
+        } else if (attempt == 2) {
+            cold_init(cx, P, S, K);
+        } else if (P.cost_dynamic) {
+            compute_d(cx, P, S, K);
+        }
+        status = solve(cx, P, S, K, pivots);
+        if (status == R_OPTIMAL) {
+            const double res = write_solution(cx, P, S, K);
+            if (!(res <= 1e-7) && attempt < 2) status = R_NUMERIC;
+        }
+        if (status == R_OPTIMAL) break;
+    }
+    for (int v = cx.tid; v < nv; v += cx.nt) { S.stat[v] = K.stat[v]; S.d[v] = K.d[v]; }
+    for (int i = cx.tid; i < m; i += cx.nt) S.head[i] = K.head[i];
+    if (cx.leader()) S.info[0] = status == R_OPTIMAL ? 1 : 0;
+    cx.sync();
+    return status == R_NUMERIC ? R_SINGULAR : status;
+}
+
+}  // namespace rsx

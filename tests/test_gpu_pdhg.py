@@ -130,9 +130,10 @@ def test_pdhg_tail_kernel_agrees_with_streaming_path(force_pdhg):
     assert abs(iters[0] - iters[1]) <= 0.25 * iters[0] + 64 * S * T, iters
 
 
-def test_pdhg_is_selected_for_the_2000_node_network_and_matches_highs():
-    """SURVEY 8(d) config 4 fixture (2,073 nodes, LP 3,994 x 2,672): no simplex kernel fits, b200lp_create picks
-    the PDHG engine by itself; scenario 0 replays the recorded planes and must reproduce HiGHS's optimum of
+def test_pdhg_on_the_2000_node_network_matches_highs(monkeypatch):
+    """SURVEY 8(d) config 4 fixture (2,073 nodes, LP 3,994 x 2,672): no dictionary kernel fits, b200lp_create goes to
+    the large-LP path; B200LP_LARGE_ENGINE=pdhg selects the PDHG iterations on it (the default there is the revised
+    simplex, tests/test_gpu_rsx.py); scenario 0 replays the recorded planes and must reproduce HiGHS's optimum of
     every recorded timestep, scenario 1 is a world with half the inflow (no reference: convergence, and it
     cannot do better than scenario 0)."""
     from pywr_b200.engine import CudaEngine
@@ -142,6 +143,7 @@ def test_pdhg_is_selected_for_the_2000_node_network_and_matches_highs():
     s = LPStructure.load(fix + ".structure.npz")
     tr = np.load(fix + ".trace.npz")
     S, T = 2, 5
+    monkeypatch.setenv("B200LP_LARGE_ENGINE", "pdhg")
     gpu = CudaEngine(s, S, device=0)
     st = gpu.stats()
     assert st["kernel_variant"] == 200 and st["reduced_rows"] < st["n_rows"] // 2

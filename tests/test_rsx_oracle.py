@@ -1,0 +1,96 @@
+"""The revised-simplex core (pywr_b200/csrc/rsx_core.cuh) compiled for the host (oracle/rsx_host.cpp, one-thread
+context) against the golden traces: objectives equal to scipy HiGHS's and the dictionary oracle's, feasible
+points, warm starts that need no pivots, the seeded first timestep.  CPU only: this is how the algorithm the
+CUDA library runs is checked where no GPU exists; tests/test_gpu_rsx.py checks the device build."""
+import os
+
+import numpy as np
+import pytest
+
+from fixtures_util import golden_cases, load_case, replay, synth_batch
+from lp_numpy import residuals
+from oracle.oracle_engine import OracleEngine
+from oracle.rsx_oracle import RsxOracleEngine
+
+TOL = 1e-9  # a vertex method: far inside north_star's 1e-7
+
+
+def _static_cases():
+    out = []
+    for name in golden_cases():
+        s, _ = load_case(name)
+        if len(s.dyn_a_nz) == 0:
+            out.append(name)
+    return out
+
+
+@pytest.mark.parametrize("case", _static_cases())
+def test_rsx_core_matches_highs_on_golden_traces(case):
+    s, tr = load_case(case)
+    T = min(10, len(tr["days"]))
+    eng = RsxOracleEngine(s, tr["slots"].shape[2])
+    nf, cf, ob, nbad = replay(eng, s, tr["slots"][:T], tr["days"][:T])
+    assert nbad.sum() == 0
+    ref = tr["objective_highs"][:T]
+    assert np.max(np.abs(ob - ref) / np.maximum(1.0, np.abs(ref))) < TOL
+    for t in range(T):
+        viol, obj = residuals(s, tr["slots"][t], 0, float(tr["days"][t]), cf[t, :, 0])
+        assert viol < 1e-7 * max(1.0, np.abs(cf[t]).max())
+        assert abs(obj - ob[t, 0]) <= 1e-9 * max(1.0, abs(obj))
+
+
+@pytest.mark.parametrize("case,S", [("network24.edge", 9), ("two_reservoir.edge", 8), ("thames.edge", 7), ("network12.route", 6)])
+def test_rsx_core_batch_vs_dictionary_oracle(case, S):
+    s, tr = load_case(case)
+    T = 6
+    slots, days = synth_batch(s, tr, S, T, seed=11, common=True)
+    eng = RsxOracleEngine(s, S)
+    a = replay(eng, s, slots, days)
+    b = replay(OracleEngine(s, S), s, slots, days)
+    assert a[3].sum() == 0 and b[3].sum() == 0
+    assert np.max(np.abs(a[2] - b[2]) / np.maximum(1.0, np.abs(b[2]))) < TOL
+    st = eng.stats()
+    assert st["pivots"] > 0 and st["refactors"] == 0
+
+
+def test_rsx_warm_start_needs_no_pivots():
+    s, tr = load_case("network24.edge")
+    eng = RsxOracleEngine(s, 1)
+    replay(eng, s, tr["slots"][:1], tr["days"][:1])
+    cold = eng.stats()["pivots"]
+    sl = eng.alloc_planes(s.n_slots)
+    sl[:] = tr["slots"][0]
+    ob = eng.alloc_planes(1)
+    assert eng.step(float(tr["days"][0]), sl, None, None, ob) == 0   # same LP again: the stored basis is optimal
+    assert cold > 0 and eng.stats()["pivots"] == cold
+
+
+def test_rsx_core_on_the_2000_node_network():
+    """config 4 fixture (LP 3,994 x 2,672, reduced 1,242 x 2,672): scenario 0 reproduces HiGHS's optimum of every recorded
+    timestep; the seeded scenarios need a few pivots per timestep, not a cold start each."""
+    from pywr_b200.structure import LPStructure
+
+    fix = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures", "network600.edge")
+    s = LPStructure.load(fix + ".structure.npz")
+    tr = np.load(fix + ".trace.npz")
+    S, T = 2, 6
+    eng = RsxOracleEngine(s, S)
+    vol_slots = sorted({int(r) for r in s.st_vol_ref if r >= 0})
+    slots = eng.alloc_planes(s.n_slots); cf = eng.alloc_planes(s.n_cols); ob = eng.alloc_planes(1)
+    eng.reset(None)
+    per_step = []
+    for t in range(T):
+        base = tr["slots"][t][:, 0]
+        fin = np.isfinite(base)
+        slots[:, 0] = base
+        slots[:, 1] = np.where(fin, base * 0.5, base)
+        slots[vol_slots, 1] = base[vol_slots]
+        p0 = eng.stats()["pivots"]
+        assert eng.step(float(tr["days"][t]), slots, None, cf, ob) == 0
+        per_step.append(eng.stats()["pivots"] - p0)
+        ref = float(tr["objective_highs"][t, 0])
+        assert abs(ob[0, 0] - ref) <= TOL * max(1.0, abs(ref)), (t, ob[0, 0], ref)
+        assert ob[0, 1] >= ob[0, 0] - 1e-6 * abs(ob[0, 0])
+        assert cf.min() >= 0.0
+    assert per_step[0] > 500 and max(per_step[1:]) < per_step[0] // 4, per_step
+    assert eng.stats()["refactors"] == 0
