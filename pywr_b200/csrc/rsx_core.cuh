@@ -272,14 +272,24 @@ RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
         K.g[i] = acc;
     }
     cx.sync();
-    for (int i = cx.warp; i < m; i += cx.nw) {
-        const double *row = S.W + (size_t)i * P.ldw;
-        double a0 = 0.0, a1 = 0.0;
+    // two rows per warp and four independent 256-byte segments per row in flight: the pass is a pure HBM stream
+    for (int i = 2 * cx.warp; i < m; i += 2 * cx.nw) {
+        const double *r0 = S.W + (size_t)i * P.ldw;
+        const bool two = i + 1 < m;
+        const double *r1 = two ? r0 + P.ldw : r0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
         int k = cx.lane;
-        for (; k + cx.nl < m; k += 2 * cx.nl) { a0 = fma(row[k], K.g[k], a0); a1 = fma(row[k + cx.nl], K.g[k + cx.nl], a1); }
-        if (k < m) a0 = fma(row[k], K.g[k], a0);
-        const double acc = cx.warp_sum(a0 + a1);
-        if (cx.lane == 0) K.beta[i] = -acc;
+        const int nl = cx.nl;
+        for (; k + 3 * nl < m; k += 4 * nl) {
+            const double x0 = r0[k], x1 = r0[k + nl], x2 = r0[k + 2 * nl], x3 = r0[k + 3 * nl];
+            const double y0 = r1[k], y1 = r1[k + nl], y2 = r1[k + 2 * nl], y3 = r1[k + 3 * nl];
+            const double g0 = K.g[k], g1 = K.g[k + nl], g2 = K.g[k + 2 * nl], g3 = K.g[k + 3 * nl];
+            a0 = fma(x0, g0, a0); a1 = fma(x1, g1, a1); a2 = fma(x2, g2, a2); a3 = fma(x3, g3, a3);
+            b0 = fma(y0, g0, b0); b1 = fma(y1, g1, b1); b2 = fma(y2, g2, b2); b3 = fma(y3, g3, b3);
+        }
+        for (; k < m; k += nl) { a0 = fma(r0[k], K.g[k], a0); b0 = fma(r1[k], K.g[k], b0); }
+        const double sa = cx.warp_sum((a0 + a1) + (a2 + a3)), sb = cx.warp_sum((b0 + b1) + (b2 + b3));
+        if (cx.lane == 0) { K.beta[i] = -sa; if (two) K.beta[i + 1] = -sb; }
     }
     cx.sync();
 }
