@@ -128,7 +128,7 @@ typedef struct b200lp_stats {
     double h2d_bytes, d2h_bytes;
     double device_ms;        /* CUDA-event time of the solve kernels                                 */
     int32_t n_rows, n_cols, n_nonzero;
-    int32_t kernel_variant;  /* index of the register variant; 100: CTA-per-scenario simplex; 200: PDHG */
+    int32_t kernel_variant;  /* index of the register variant; 100: CTA-per-scenario simplex; 200: PDHG; 300: revised simplex, inverse in HBM */
     int64_t pdhg_iterations; /* PDHG path: scenario-iterations since create                           */
     int32_t reduced_rows, reduced_nonzero; /* PDHG path: rows / non-zeros left by the structural presolve */
 } b200lp_stats;
