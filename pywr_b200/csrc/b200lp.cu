@@ -123,7 +123,9 @@ struct b200lp_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of b200lp_run_pipelined
     std::vector<cudaEvent_t> pipe_events;
     std::vector<int> h_st_maxv_idx;  // V index of every storage's max_volume (host copy, for op pre-decoding)
-    struct PdhgEngine *pdhg = nullptr;  // restarted-PDHG path (pdhg_engine.cuh): LPs beyond the simplex kernels
+    struct PdhgEngine *pdhg = nullptr;  // large-LP path (pdhg_engine.cuh, rsx_kernels.cuh): LPs beyond the dictionary kernels
+    struct PlaneHost *plane = nullptr;  // device-resident program on the large-LP path (plane_program.inc)
+    std::vector<double> ts_days_host;
 };
 
 template <typename T>
@@ -158,7 +160,9 @@ __global__ void fill_kernel(double *p, size_t n, double v) {
 
 static void free_program(b200lp_handle *h);
 
+#include "plane_kernels.cuh"
 #include "pdhg_host.inc"
+#include "plane_program.inc"
 
 extern "C" {
 
@@ -382,7 +386,14 @@ int b200lp_reset(b200lp_handle *h, const double *initial_volume) {
 int b200lp_set_consts(b200lp_handle *h, const double *consts) {
     if (!h || !consts) return fail(B200LP_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->pdhg) return pdhg_set_consts(h, consts);
+    if (h->pdhg) {
+        const int rc = pdhg_set_consts(h, consts);
+        if (rc == 0 && h->plane) {
+            plane_fill_consts<<<(h->S + 127) / 128, 128, 0, h->stream>>>(h->plane->Q, h->d_consts);
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+        return rc;
+    }
     if (h->ds.n_consts > 0) {
         CUDA_TRY(cudaMemcpyAsync(h->d_consts, consts, sizeof(double) * h->ds.n_consts, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -418,7 +429,7 @@ int b200lp_step_device(b200lp_handle *h, double days, const double *d_slots, dou
     if (!(days > 0.0)) return fail(B200LP_E_INVALID, "days must be positive");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->pdhg)  // iterates to convergence: synchronises with the host between batches of iterations
-        return pdhg_step_device(h, days, d_slots ? d_slots : h->d_slots, d_node_flow, d_col_flow, d_objective);
+        return pdhg_step_device(h, days, d_slots ? d_slots : h->d_slots, d_node_flow, d_col_flow, d_objective, nullptr);
     return launch_step(h, days, d_slots ? d_slots : h->d_slots, d_node_flow, d_col_flow, d_objective);
 }
 
@@ -597,6 +608,7 @@ int b200lp_memcpy_d2h(b200lp_handle *h, void *dst, const void *d_src, size_t byt
 }  // extern "C" (reopened below)
 
 static void free_program(b200lp_handle *h) {
+    plane_free(h);
     for (void *p : h->prog_owned) cudaFree(p);
     h->prog_owned.clear(); h->rec_ptr.clear(); h->rec_kind.clear();
     h->has_program = false;
@@ -621,10 +633,9 @@ static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind
 extern "C" {
 
 int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
-    if (h && h->pdhg) return fail(B200LP_E_UNSUPPORTED, "device-resident programs are not available on the PDHG path yet");
     if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
     if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
-    if (h->use_cta)
+    if (h->use_cta && !h->pdhg)
         return fail(B200LP_E_UNSUPPORTED, "the device-resident run needs a register-resident kernel variant; "
                                           "this LP uses the CTA-per-scenario kernel (per-timestep path only)");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -908,6 +919,10 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     h->init_pc.assign(p->initial_pc, p->initial_pc + (size_t)nst * S);
     h->prog_steps = p->n_steps;
     h->has_program = true;
+    if (h->pdhg) {  // large-LP path: the program runs as plane kernels around the batched solve (plane_program.inc)
+        const int rc = plane_attach(h, p);
+        if (rc != 0) { free_program(h); return rc; }
+    }
     return b200lp_program_reset(h);
 }
 
@@ -937,6 +952,7 @@ int b200lp_program_reset(b200lp_handle *h) {
             }
     CUDA_TRY(cudaMemsetAsync(h->dp.last_x, 0, sizeof(double) * S * h->ds.n, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->dp.fail_step, 0xff, sizeof(int) * S, h->stream));
+    if (h->plane) CUDA_TRY(cudaMemsetAsync(h->plane->Q.dead, 0, sizeof(int) * S, h->stream));
     h->h_fail[0] = 0; h->h_fail[1] = INT_MAX;
     CUDA_TRY(cudaMemcpyAsync(h->state.fail, h->h_fail, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -947,6 +963,7 @@ int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n) {
     if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
     if (t0 < 0 || n <= 0 || t0 + n > h->prog_steps) return fail(B200LP_E_INVALID, "timestep range outside the program");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->plane) return plane_run(h, t0, n);
     const Variant &V = kVariants[h->variant];
     V.run(h->ds, h->state, h->dp, h->S, t0, n, h->stream, h->block);
     h->stats.kernel_launches++;

@@ -933,7 +933,10 @@ __device__ __forceinline__ double clamp_pc(double pc) {  // Storage.get_current_
 
 // scalar interpreter for the non-table ops (lane 0 of the group); same arithmetic as orc_eval_ops.
 // `code` is in shared memory; every operand is an index into V.
-__device__ __forceinline__ void eval_ops(const int *code, const int n_code, double *V, const int pc_base) {
+// VA: anything indexable that yields a double lvalue (a pointer into shared memory here, a strided plane view in
+// plane_program.inc).
+template <class VA>
+__device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V, const int pc_base) {
     int pos = 0;
     while (pos < n_code) {
         const int kind = code[pos], dst = code[pos + 1], na = code[pos + 2];
