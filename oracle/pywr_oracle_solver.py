@@ -42,3 +42,25 @@ def register(first=False):
 
 
 register()
+
+
+class OracleRsxEdgeSolver(OracleSolver):
+    """Edge formulation solved by the HOST build of the revised-simplex core (oracle/rsx_oracle.py): fast enough for
+    host runs of the 2,073-node network (benchmarks/make_network_program.py)."""
+    name = "oracle-rsx-edge"
+    formulation = "edge"
+
+    def _make_engine(self, structure, n_scenarios):
+        from oracle.rsx_oracle import RsxOracleEngine
+
+        return RsxOracleEngine(structure, n_scenarios)
+
+
+def _register_rsx():
+    import pywr.solvers as ps
+
+    if not any(getattr(c, "name", None) == OracleRsxEdgeSolver.name for c in ps.solver_registry):
+        ps.solver_registry.append(OracleRsxEdgeSolver)
+
+
+_register_rsx()

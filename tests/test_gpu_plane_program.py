@@ -134,3 +134,39 @@ def test_plane_program_pipelined_equals_serial(force_rsx):
     for a, b in zip(serial, outs):
         assert np.array_equal(a, b, equal_nan=True)
     gpu.close(); cpu.close()
+
+
+def test_plane_program_on_the_2000_node_network_matches_the_reference_host_run():
+    """SURVEY 8(d) config 4 end to end on the device: the 2,073-node network (LP 3,994 x 2,672, 1,201 ops, 601 tables, 30
+    recorders) for a year of daily timesteps.  b200lp_create picks the revised simplex by itself; the recorder arrays must
+    equal those of the reference framework's HOST run (Model.run with the reference's own Parameter / Storage.after /
+    Recorder code, benchmarks/make_network_program.py) within north_star's 1e-6 — observed: round-off."""
+    import os
+
+    from pywr_b200.engine import CudaEngine
+    from pywr_b200.program import Program
+    from pywr_b200.structure import LPStructure
+
+    fix = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures", "network600")
+    s = LPStructure.load(fix + ".pstructure.npz")
+    prog = Program.load(fix + ".program.npz")
+    z = np.load(fix + ".expected.npz")
+    names = [str(n) for n in z["names"]]
+    S = n_scenarios_of(s, prog)
+    gpu = CudaEngine(s, S, device=0)
+    assert gpu.stats()["kernel_variant"] == 300
+    outs, st, state = run_program(gpu, prog)
+    assert st[0] == 0
+    T = prog.n_steps
+    worst = 0.0
+    for i, (o, nm) in enumerate(zip(outs, names)):
+        if nm.startswith(("mf_", "df_")):
+            o = o / T
+        d = rel_diff(o, z[f"rec{i}"])
+        worst = max(worst, d)
+        assert d <= 1e-6, (nm, d)
+    stt = gpu.stats()
+    assert stt["refactors"] == 0 and stt["pivots"] > 1000
+    print(f"network600: T={T} S={S}, {len(names)} recorders, worst relative difference vs the reference host run {worst:.2e}, "
+          f"{stt['pivots']} pivots")
+    gpu.close()
