@@ -53,6 +53,11 @@ struct Lp {  // shared by all scenarios
     const int *csc_ptr, *csc_row;
     const double *csc_val;
     int cost_dynamic;  // costs change between timesteps: reduced costs are rebuilt every solve
+    // rows with more than `long_len` entries (aggregated nodes: one licence row spans every abstraction): their sums are
+    // taken by a whole warp, everything else by one thread per row (a 200-entry row walked by one thread is 200 dependent
+    // L2 round trips: 160 us of a 470 us scenario-timestep)
+    int n_long, long_len;
+    const int *long_rows;
 };
 
 struct Scen {  // one scenario: persistent state + this timestep's planes (element stride ld)
@@ -263,13 +268,26 @@ template <class CX>
 RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
     const int m = P.m, n = P.n;
     for (int i = cx.tid; i < m; i += cx.nt) {
+        const int e0 = P.csr_ptr[i], e1 = P.csr_ptr[i + 1];
+        if (e1 - e0 > P.long_len) continue;
         double acc = 0.0;
-        for (int e = P.csr_ptr[i]; e < P.csr_ptr[i + 1]; e++) {
+        for (int e = e0; e < e1; e++) {
             const int j = P.csr_col[e];
             if (K.stat[j] != V_BASIC) acc = fma(P.csr_val[e], nb_value(K, j), acc);
         }
         if (K.stat[n + i] != V_BASIC) acc -= nb_value(K, n + i);
         K.g[i] = acc;
+    }
+    for (int li = cx.warp; li < P.n_long; li += cx.nw) {
+        const int i = P.long_rows[li];
+        double acc = 0.0;
+        for (int e = P.csr_ptr[i] + cx.lane; e < P.csr_ptr[i + 1]; e += cx.nl) {
+            const int j = P.csr_col[e];
+            if (K.stat[j] != V_BASIC) acc = fma(P.csr_val[e], nb_value(K, j), acc);
+        }
+        acc = cx.warp_sum(acc);
+        if (K.stat[n + i] != V_BASIC) acc -= nb_value(K, n + i);
+        if (cx.lane == 0) K.g[i] = acc;
     }
     cx.sync();
     // two rows per warp and four independent 256-byte segments per row in flight: the pass is a pure HBM stream
@@ -517,12 +535,24 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
     cx.sync();
     double worst = -1.0; int bi = -1, aux = 0;
     for (int i = cx.tid; i < m; i += cx.nt) {
+        const int e0 = P.csr_ptr[i], e1 = P.csr_ptr[i + 1];
+        if (e1 - e0 > P.long_len) continue;
         double acc = 0.0;
-        for (int e = P.csr_ptr[i]; e < P.csr_ptr[i + 1]; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
+        for (int e = e0; e < e1; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
         const double gi = K.g[i];
         double res = fabs(acc - gi) / (1.0 + fabs(gi));
         if (res != res) res = INFINITY;
         if (bi < 0 || res > worst) { worst = res; bi = i; }
+    }
+    for (int li = cx.warp; li < P.n_long; li += cx.nw) {
+        const int i = P.long_rows[li];
+        double acc = 0.0;
+        for (int e = P.csr_ptr[i] + cx.lane; e < P.csr_ptr[i + 1]; e += cx.nl) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
+        acc = cx.warp_sum(acc);
+        const double gi = K.g[i];
+        double res = fabs(acc - gi) / (1.0 + fabs(gi));
+        if (res != res) res = INFINITY;
+        if (cx.lane == 0 && (bi < 0 || res > worst)) { worst = res; bi = i; }
     }
     cx.argmax(worst, bi, aux);
     return worst;

@@ -140,3 +140,61 @@ def test_population_evaluator_on_the_gpu():
     from test_optimisation import check_population
 
     check_population(None, P=12, n_inflow=4)
+
+
+def _network_model(solver, n_reaches=24, end="2100-03-31"):
+    """generated river network (benchmarks.workloads.synthetic_network_document) with a 3-member wetness scenario and
+    a few recorders; the same document as benchmarks/make_network_program.py at a size the oracle solves in seconds"""
+    from pywr.model import Model
+    from pywr.recorders import (MinimumVolumeStorageRecorder, NumpyArrayNodeRecorder, NumpyArrayStorageRecorder,
+                                TotalDeficitNodeRecorder)
+
+    from benchmarks.workloads import synthetic_network_document
+
+    doc = synthetic_network_document(n_reaches=n_reaches, end=end)
+    doc["scenarios"] = [{"name": "inflow", "size": 3}]
+    params = doc["parameters"]
+    params["wet"] = {"type": "constantscenario", "scenario": "inflow", "values": [1.0, 0.6, 1.3]}
+    for name in [k for k in params if k.startswith("inflow")]:
+        params[name] = {"type": "aggregated", "agg_func": "product", "parameters": [params[name], "wet"]}
+    m = Model.load(doc, solver=solver)
+    for n in m.nodes:
+        cn = type(n).__name__
+        if cn == "Storage":
+            NumpyArrayStorageRecorder(m, n, name=f"vol_{n.name}")
+            MinimumVolumeStorageRecorder(m, n, name=f"minv_{n.name}")
+        elif n.name.startswith(("town", "farm")):
+            TotalDeficitNodeRecorder(m, n, name=f"tdef_{n.name}")
+    NumpyArrayNodeRecorder(m, m.nodes["sea"], name="flow_sea")
+    return m
+
+
+def test_large_lp_path_as_a_pywr_user_sees_it(monkeypatch):
+    """The large-LP path (front end of pdhg_engine.cuh + revised simplex) behind both drop-in boundaries, on a generated
+    network in the edge formulation: Model(solver="b200-edge").run() — Pywr's own before()/after() around one
+    b200lp_step per timestep — and run_on_device(model) — the whole run as plane kernels around the batched solve —
+    against the same model solved by the CPU oracle."""
+    import oracle.pywr_oracle_solver  # noqa: F401
+    import pywr_b200  # noqa: F401
+    from pywr_b200.device_run import run_on_device
+
+    monkeypatch.setenv("B200LP_FORCE_PDHG", "1")
+    monkeypatch.setenv("B200LP_FORCE_RSX", "1")
+    m_host = _network_model("oracle-edge")
+    m_host.run()
+    want = _recorder_values(m_host)
+    m_step = _network_model("b200-edge")
+    m_step.run()
+    assert m_step.solver._engine.stats()["kernel_variant"] == 300
+    got = _recorder_values(m_step)
+    for k in want:
+        assert rel_diff(got[k], want[k]) <= 1e-6, k            # north_star: flows / volumes within 1e-6 relative
+    m_dev = _network_model("null")
+    res = run_on_device(m_dev, formulation="edge")
+    assert res.num_scenarios == 3 and res.timesteps == 91
+    got = _recorder_values(m_dev)
+    for k in want:
+        assert rel_diff(got[k], want[k]) <= 1e-6, k
+    for n_dev, n_host in zip(m_dev.nodes, m_host.nodes):
+        if hasattr(n_host, "volume"):
+            assert rel_diff(n_dev.volume, n_host.volume) <= 1e-6, n_dev.name
