@@ -1120,6 +1120,13 @@ int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, doubl
     return B200LP_OK;
 }
 
+#ifdef RSX_PHASE_TIMING
+int b200lp_debug_rsx_phases(b200lp_handle *h, unsigned long long *out16) {
+    if (!h || !h->pdhg || !pdhg_is_rsx(h)) return -1;
+    return cudaMemcpy(out16, pdhg_rsx_counters(h), sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 #ifdef B200LP_PHASE_TIMING
 int b200lp_debug_phase_cycles(unsigned long long *out16) {
     return cudaMemcpyFromSymbol(out16, b200lp::g_phase_cycles, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -3;

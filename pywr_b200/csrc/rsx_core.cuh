@@ -69,6 +69,11 @@ struct Scen {  // one scenario: persistent state + this timestep's planes (eleme
     const double *c, *lc, *uc, *lo, *hi;
     double *x;
     size_t ld;
+    // device: the scenario's bounds gathered into one contiguous vector [LO(n+m) | HI(n+m)] and its x written contiguously
+    // (rsx_gather_bounds / rsx_scatter_x transpose them from / to the planes with coalesced accesses on both sides): 14 k
+    // plane elements per scenario-timestep read 64 KB apart cost the stream of W a third of its bandwidth
+    const double *bt;  // nullptr: read the planes
+    size_t ldx;        // element stride of x
 };
 
 struct Work {  // block-shared
@@ -79,19 +84,37 @@ struct Work {  // block-shared
     int *cnt;                          // [8]
 };
 
-RSX_HD size_t work_bytes(int m, int n) {
+// Placement of the working vectors.  mode 0: everything in the block's fast memory (shared memory on the device).
+// mode 1: the reduced costs (true / working), the pivot row and the two index lists live in a per-block scratch area in
+// global memory (L2-resident: 104 KB per block for config 4) — they are touched once per timestep and per pivot, with
+// coalesced accesses — which halves the shared-memory footprint: two blocks per SM, so that one scenario's serial phases
+// overlap another's stream of W, and LPs twice as large still fit.
+RSX_HD size_t work_bytes(int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
-    return 8 * (5 * nv + 4 * (size_t)m) + 4 * (3 * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
+    const size_t fast_nv = mode == 0 ? 5 : 2, lists = mode == 0 ? 3 : 1;
+    return 8 * (fast_nv * nv + 4 * (size_t)m) + 4 * (lists * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
 }
-RSX_FN void work_carve(Work &K, unsigned char *base, int m, int n) {
+RSX_HD size_t scratch_bytes(int m, int n, int mode) {
+    const size_t nv = (size_t)n + m;
+    return mode == 0 ? 0 : 8 * (3 * nv) + 4 * (2 * (size_t)m) + 64;
+}
+RSX_FN void work_carve(Work &K, unsigned char *base, unsigned char *scratch, int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
     double *p = reinterpret_cast<double *>(base);
-    K.LO = p; p += nv; K.HI = p; p += nv; K.d = p; p += nv; K.dw = p; p += nv; K.alpha = p; p += nv;
+    K.LO = p; p += nv; K.HI = p; p += nv;
+    if (mode == 0) { K.d = p; p += nv; K.dw = p; p += nv; K.alpha = p; p += nv; }
     K.rho = p; p += m; K.w = p; p += m; K.beta = p; p += m; K.g = p; p += m;
     int *q = reinterpret_cast<int *>(p);
-    K.head = q; q += m; K.list_k = q; q += m; K.list_i = q; q += m;
+    K.head = q; q += m;
+    if (mode == 0) { K.list_k = q; q += m; K.list_i = q; q += m; }
     K.cnt = q; q += 8;
     K.stat = reinterpret_cast<unsigned char *>(q);
+    if (mode != 0) {
+        double *sp = reinterpret_cast<double *>(scratch);
+        K.d = sp; sp += nv; K.dw = sp; sp += nv; K.alpha = sp; sp += nv;
+        int *sq = reinterpret_cast<int *>(sp);
+        K.list_k = sq; sq += m; K.list_i = sq;
+    }
 }
 
 // value of a non-basic variable
@@ -105,7 +128,8 @@ RSX_FN void load_bounds(CX &cx, const Lp &P, const Scen &S, Work &K) {
     const int n = P.n, nv = P.n + P.m;
     for (int v = cx.tid; v < nv; v += cx.nt) {
         double lo, hi;
-        if (v < n) { lo = S.lc[(size_t)v * S.ld]; hi = S.uc[(size_t)v * S.ld]; }
+        if (S.bt != nullptr) { lo = S.bt[v]; hi = S.bt[nv + v]; }
+        else if (v < n) { lo = S.lc[(size_t)v * S.ld]; hi = S.uc[(size_t)v * S.ld]; }
         else { lo = S.lo[(size_t)(v - n) * S.ld]; hi = S.hi[(size_t)(v - n) * S.ld]; }
         K.LO[v] = lo <= -BIG ? -INFINITY : lo;
         K.HI[v] = hi >= BIG ? INFINITY : hi;
@@ -290,6 +314,7 @@ RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
         if (cx.lane == 0) K.g[i] = acc;
     }
     cx.sync();
+    cx.mark(4);
     // two rows per warp and four independent 256-byte segments per row in flight: the pass is a pure HBM stream
     for (int i = 2 * cx.warp; i < m; i += 2 * cx.nw) {
         const double *r0 = S.W + (size_t)i * P.ldw;
@@ -297,7 +322,10 @@ RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
         const double *r1 = two ? r0 + P.ldw : r0;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
         int k = cx.lane;
-        const int nl = cx.nl;
+        constexpr int nl = CX::nl;
+        // 4 x unrolled: 32 independent 256-byte loads per warp in flight (128 KB per SM); with 8 the stream reached 5.1 of the
+        // 7.1 TB/s the same loop sustains when the compiler unrolls it by itself (benchmarks/tools/stream_probe.cu)
+#pragma unroll 4
         for (; k + 3 * nl < m; k += 4 * nl) {
             const double x0 = r0[k], x1 = r0[k + nl], x2 = r0[k + 2 * nl], x3 = r0[k + 3 * nl];
             const double y0 = r1[k], y1 = r1[k + nl], y2 = r1[k + 2 * nl], y3 = r1[k + 3 * nl];
@@ -364,7 +392,9 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
     const int cap_bland = 20 * nv + 50, cap_fail = 200 * nv + 1000;
     int shifted = place_nonbasics(cx, P, K);
     cx.sync();
+    cx.mark(3);
     compute_beta(cx, P, S, K);
+    cx.mark(5);
     bool dw_ready = false;
     int phase = 0;
     for (int it = 0;; it++) {
@@ -526,11 +556,11 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
     for (int v = cx.tid; v < nv; v += cx.nt) {
         if (K.stat[v] == V_BASIC) continue;
         const double val = nb_value(K, v);
-        if (v < n) S.x[(size_t)v * S.ld] = val; else K.g[v - n] = val;
+        if (v < n) S.x[(size_t)v * S.ldx] = val; else K.g[v - n] = val;
     }
     for (int i = cx.tid; i < m; i += cx.nt) {
         const int v = K.head[i];
-        if (v < n) S.x[(size_t)v * S.ld] = K.beta[i]; else K.g[v - n] = K.beta[i];
+        if (v < n) S.x[(size_t)v * S.ldx] = K.beta[i]; else K.g[v - n] = K.beta[i];
     }
     cx.sync();
     double worst = -1.0; int bi = -1, aux = 0;
@@ -538,7 +568,7 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
         const int e0 = P.csr_ptr[i], e1 = P.csr_ptr[i + 1];
         if (e1 - e0 > P.long_len) continue;
         double acc = 0.0;
-        for (int e = e0; e < e1; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
+        for (int e = e0; e < e1; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ldx], acc);
         const double gi = K.g[i];
         double res = fabs(acc - gi) / (1.0 + fabs(gi));
         if (res != res) res = INFINITY;
@@ -547,7 +577,7 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
     for (int li = cx.warp; li < P.n_long; li += cx.nw) {
         const int i = P.long_rows[li];
         double acc = 0.0;
-        for (int e = P.csr_ptr[i] + cx.lane; e < P.csr_ptr[i + 1]; e += cx.nl) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ld], acc);
+        for (int e = P.csr_ptr[i] + cx.lane; e < P.csr_ptr[i + 1]; e += cx.nl) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ldx], acc);
         acc = cx.warp_sum(acc);
         const double gi = K.g[i];
         double res = fabs(acc - gi) / (1.0 + fabs(gi));
@@ -563,13 +593,16 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
 template <class CX>
 RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, int &pivots, int &refactors) {
     const int m = P.m, nv = P.n + P.m;
+    cx.mark(0);
     load_bounds(cx, P, S, K);
+    cx.mark(1);
     const bool valid = !cold && S.info[0] != 0;
     if (valid) {
         for (int v = cx.tid; v < nv; v += cx.nt) { K.stat[v] = S.stat[v]; K.d[v] = S.d[v]; }
         for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = S.head[i];
         cx.sync();
     }
+    cx.mark(2);
     int status = R_OPTIMAL;
     for (int attempt = valid ? 0 : 2; attempt < 3; attempt++) {
         if (attempt == 1) {
@@ -582,8 +615,10 @@ RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, i
             compute_d(cx, P, S, K);
         }
         status = solve(cx, P, S, K, pivots);
+        cx.mark(6);
         if (status == R_OPTIMAL) {
             const double res = write_solution(cx, P, S, K);
+            cx.mark(7);
             if (!(res <= 1e-7) && attempt < 2) status = R_NUMERIC;
         }
         if (status == R_OPTIMAL) break;
@@ -592,6 +627,7 @@ RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, i
     for (int i = cx.tid; i < m; i += cx.nt) S.head[i] = K.head[i];
     if (cx.leader()) S.info[0] = status == R_OPTIMAL ? 1 : 0;
     cx.sync();
+    cx.mark(8);
     return status == R_NUMERIC ? R_SINGULAR : status;
 }
 

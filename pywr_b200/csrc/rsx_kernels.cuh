@@ -12,9 +12,22 @@ namespace b200lp {
 constexpr int RSX_THREADS = 512;
 
 struct RsxCtx {
-    int tid, nt, lane, nl, warp, nw;
+    static constexpr int nl = 32;  // compile-time: the streaming loops unroll over it
+    int tid, nt, lane, warp, nw;
     double *rv;  // [32] reduction scratch (static shared memory)
     int *ri, *ra;
+    // phase timing of debug builds (-DRSX_PHASE_TIMING): cycles of thread 0 between marks, summed per phase
+#ifdef RSX_PHASE_TIMING
+    long long t_last;
+    unsigned long long ph[12];
+    __device__ __forceinline__ void mark(int k) {
+        const long long c = clock64();
+        if (k > 0) ph[k] += (unsigned long long)(c - t_last);
+        t_last = c;
+    }
+#else
+    __device__ __forceinline__ void mark(int) {}
+#endif
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ bool leader() const { return tid == 0; }
     __device__ __forceinline__ int atomic_inc(int *p) { return atomicAdd(p, 1); }
@@ -70,20 +83,34 @@ struct RsxDev {
     int *status;          // [ld] preset by the assembly (NaN / inconsistent bounds), result of the solve
     int *queue;           // [1] next scenario
     unsigned long long *counters;  // [0] pivots, [1] refactorisations
+    double *bt;           // [S][2 (n+m)] bounds of every scenario, contiguous per scenario (rsx_gather_bounds)
+    double *xt;           // [S][n] column values, contiguous per scenario (rsx_scatter_x moves them to the x planes)
+    unsigned char *scratch;        // MODE 1: [gridDim.x][scratch_stride] reduced costs / pivot row / index lists of each block
+    size_t scratch_stride;
 };
 
-__global__ void __launch_bounds__(RSX_THREADS, 1)
+// MODE 0: all working vectors in shared memory.  MODE 1: reduced costs, pivot row and index lists in an L2-resident scratch
+// (rsx_core.cuh::work_bytes), which halves the shared-memory footprint.  That matters for the STREAM, not for occupancy: with
+// more than ~164 KB of shared memory carved out of the SM's 256 KB, what is left as L1 cannot hold the sectors in flight and the
+// same loop drops from 7.1 to 5.2 TB/s (benchmarks/tools/stream_probe.cu, profiles/r1_stream_probe.md).  MINB = blocks per SM
+// (128 or 64 registers per thread).
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(RSX_THREADS, MINB)
 rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
     extern __shared__ __align__(16) unsigned char rsx_smem[];
     __shared__ double rv[32];
     __shared__ int ri[32], ra[32], s_next;
     RsxCtx cx;
-    cx.tid = threadIdx.x; cx.nt = blockDim.x; cx.lane = threadIdx.x & 31; cx.nl = 32;
+    cx.tid = threadIdx.x; cx.nt = blockDim.x; cx.lane = threadIdx.x & 31;
     cx.warp = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
     cx.rv = rv; cx.ri = ri; cx.ra = ra;
+#ifdef RSX_PHASE_TIMING
+    for (int k = 0; k < 12; k++) cx.ph[k] = 0;
+    cx.t_last = clock64();
+#endif
     const rsx::Lp &P = D.lp;
     rsx::Work K;
-    rsx::work_carve(K, rsx_smem, P.m, P.n);
+    rsx::work_carve(K, rsx_smem, MODE == 0 ? nullptr : D.scratch + (size_t)blockIdx.x * D.scratch_stride, P.m, P.n, MODE);
     const size_t wtot = (size_t)P.m * P.ldw;
     const int nv = P.n + P.m;
     int pivots = 0, refactors = 0;
@@ -100,14 +127,61 @@ rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
         sc.stat = D.stat + (size_t)s * nv;
         sc.d = D.d + (size_t)s * nv;
         sc.info = D.info + (size_t)s * 4;
-        sc.c = D.c + s; sc.lc = D.lc + s; sc.uc = D.uc + s; sc.lo = D.lo + s; sc.hi = D.hi + s; sc.x = D.x + s;
+        sc.c = D.c + s; sc.lc = D.lc + s; sc.uc = D.uc + s; sc.lo = D.lo + s; sc.hi = D.hi + s;
         sc.ld = (size_t)D.ld;
+        sc.bt = D.bt + (size_t)s * 2 * nv;
+        sc.x = D.xt + (size_t)s * P.n; sc.ldx = 1;
         const int st = rsx::run_scenario(cx, P, sc, K, cold, pivots, refactors);
         if (threadIdx.x == 0) D.status[s] = st;
     }
     if (threadIdx.x == 0) {
         if (pivots) atomicAdd(&D.counters[0], (unsigned long long)pivots);
         if (refactors) atomicAdd(&D.counters[1], (unsigned long long)refactors);
+#ifdef RSX_PHASE_TIMING
+        for (int k = 0; k < 12; k++) atomicAdd(&D.counters[2 + k], cx.ph[k]);
+#endif
+    }
+}
+
+// planes [item][ld] -> per-scenario vectors [S][2 (n+m)] (LO | HI), 32 x 32 tiles through shared memory: coalesced reads along
+// the scenario axis, coalesced writes along the item axis
+__global__ void rsx_gather_bounds(const RsxDev D) {
+    __shared__ double tile[32][33];
+    const int n = D.lp.n, nv = D.lp.n + D.lp.m, np = 2 * nv;
+    const int p0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, s = s0 + tx;
+        double v = 0.0;
+        if (p < np && s < D.S) {
+            const int q = p < nv ? p : p - nv;
+            const double *plane = p < nv ? (q < n ? D.lc + (size_t)q * D.ld : D.lo + (size_t)(q - n) * D.ld)
+                                         : (q < n ? D.uc + (size_t)q * D.ld : D.hi + (size_t)(q - n) * D.ld);
+            v = plane[s];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int s = s0 + r, p = p0 + tx;
+        if (s < D.S && p < np) D.bt[(size_t)s * np + p] = tile[tx][r];
+    }
+}
+
+// per-scenario x [S][n] -> planes [n][ld]
+__global__ void rsx_scatter_x(const RsxDev D) {
+    __shared__ double tile[32][33];
+    const int n = D.lp.n;
+    const int j0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int s = s0 + r, j = j0 + tx;
+        tile[r][tx] = (s < D.S && j < n) ? D.xt[(size_t)s * n + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, s = s0 + tx;
+        if (j < n && s < D.S && D.status[s] == 0) D.x[(size_t)j * D.ld + s] = tile[tx][r];
     }
 }
 

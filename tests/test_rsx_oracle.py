@@ -94,3 +94,15 @@ def test_rsx_core_on_the_2000_node_network():
         assert cf.min() >= 0.0
     assert per_step[0] > 500 and max(per_step[1:]) < per_step[0] // 4, per_step
     assert eng.stats()["refactors"] == 0
+
+
+def test_rsx_scratch_placement_takes_the_same_pivots():
+    """mode 1 (reduced costs / pivot row / index lists outside the block's fast memory: two blocks per SM on the device) is a
+    placement, not an algorithm: identical objectives and pivot counts"""
+    s, tr = load_case("network24.edge")
+    S, T = 5, 6
+    slots, days = synth_batch(s, tr, S, T, seed=4, common=True)
+    a_eng, b_eng = RsxOracleEngine(s, S, mode=0), RsxOracleEngine(s, S, mode=1)
+    a = replay(a_eng, s, slots, days)
+    b = replay(b_eng, s, slots, days)
+    assert np.array_equal(a[2], b[2]) and a_eng.stats()["pivots"] == b_eng.stats()["pivots"] > 0
