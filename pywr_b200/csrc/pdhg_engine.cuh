@@ -811,11 +811,24 @@ __global__ void pdhg_unscale(const PdhgDev P, const PdhgState Z, double *__restr
     if (col_flow) col_flow[(size_t)j * P.S + s] = x;
 }
 
+// objective = sum_j c_j x_j in the unscaled space.  Two stages with a fixed summation order (deterministic): partial sums of
+// PD_OBJ_CH columns per (scenario, chunk) into Z.part, then the chunks in ascending order.  (One thread walking all the columns
+// of its scenario took 1.9 ms of a 19.5 ms timestep at 8,192 scenarios x 2,672 columns.)
+constexpr int PD_OBJ_CH = 128;
+__global__ void pdhg_objective_partial(const PdhgDev P, const PdhgState Z) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.S) return;
+    const int j0 = blockIdx.y * PD_OBJ_CH, j1 = min(P.n, j0 + PD_OBJ_CH);
+    double acc = 0.0;
+    for (int j = j0; j < j1; j++) acc = fma(Z.c[(size_t)j * P.ld + s] / __ldg(&P.dc[j]), Z.xb[(size_t)j * P.ld + s], acc);
+    Z.part[(size_t)blockIdx.y * P.ld + s] = acc;
+}
 __global__ void pdhg_objective(const PdhgDev P, const PdhgState Z, double *__restrict__ objective) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.S) return;
+    const int nch = (P.n + PD_OBJ_CH - 1) / PD_OBJ_CH;
     double acc = 0.0;
-    for (int j = 0; j < P.n; j++) acc = fma(Z.c[(size_t)j * P.ld + s] / __ldg(&P.dc[j]), Z.xb[(size_t)j * P.ld + s], acc);
+    for (int c = 0; c < nch; c++) acc += Z.part[(size_t)c * P.ld + s];
     Z.objective[s] = acc;
     if (objective) objective[s] = acc;
 }

@@ -191,7 +191,7 @@ def test_large_lp_path_as_a_pywr_user_sees_it(monkeypatch):
         assert rel_diff(got[k], want[k]) <= 1e-6, k            # north_star: flows / volumes within 1e-6 relative
     m_dev = _network_model("null")
     res = run_on_device(m_dev, formulation="edge")
-    assert res.num_scenarios == 3 and res.timesteps == 91
+    assert res.num_scenarios == 3 and res.timesteps == 90
     got = _recorder_values(m_dev)
     for k in want:
         assert rel_diff(got[k], want[k]) <= 1e-6, k
