@@ -258,6 +258,26 @@ def _attr(obj, kind):
     return getattr(obj, kind)
 
 
+def _cross_domain_routes(model, BaseOutput, BaseInput):
+    """``model.find_all_routes(BaseOutput, BaseInput, max_length=2, domain_match="different")`` (cython_glpk.pyx:426,1192) without
+    its |outputs| x |inputs| calls of ``networkx.all_simple_paths`` (pywr/_model.pyx:543-546; 918 k calls and 7 s on the 2,073-node
+    network): a route of at most two nodes is a direct edge, so the result is every edge Output -> Input whose ends lie in
+    different domains, in the same order (both ends sorted by name)."""
+    nodes = sorted(model.graph.nodes(), key=lambda n: n.name)
+    inputs = [n for n in nodes if isinstance(n, BaseInput)]
+    routes = []
+    for out in nodes:
+        if not isinstance(out, BaseOutput):
+            continue
+        succ = set(model.graph.successors(out))
+        if not succ:
+            continue
+        for inp in inputs:
+            if inp in succ and inp is not out and inp.domain != out.domain:
+                routes.append([out, inp])
+    return routes
+
+
 def build_structure(model, formulation: str = "route") -> LPStructure:
     """Build the shared LP for ``model``.  Raises ``ModelStructureError`` exactly where the
     reference does (``cython_glpk.pyx:411,453,455,529`` / ``:1174,1222,1303,1308,1315``)."""
@@ -290,7 +310,7 @@ def build_structure(model, formulation: str = "route") -> LPStructure:
     else:
         routes = model.find_all_routes(BaseInput, BaseOutput, valid=(BaseLink, BaseInput, BaseOutput))
         n_cols = len(routes)
-    cross_domain_routes = model.find_all_routes(BaseOutput, BaseInput, max_length=2, domain_match="different")
+    cross_domain_routes = _cross_domain_routes(model, BaseOutput, BaseInput)
 
     non_storages, link_nodes, storages, virtual_storages, aggregated, aggregated_with_factors = [], [], [], [], [], []
     for node in all_nodes:
