@@ -147,8 +147,10 @@ def assemble(plan, slots_k, days, vol_k):
     for r, i in enumerate(plan.keep):
         lo[r], hi[r] = row_bounds(s, i, slots_k, days, vol_k)
     lc = np.zeros(n); uc = np.full(n, np.inf)
+    bad = False
     for i, j, a in zip(plan.sing_row, plan.sing_col, plan.sing_coef):
         l, u = row_bounds(s, i, slots_k, days, vol_k)
+        bad = bad or np.isnan(l) or np.isnan(u)   # max / min below would swallow a NaN (pdhg_assemble_cols: `bad |= isnan`)
         l, u = (l / a, u / a) if a > 0 else (u / a, l / a)
         lc[j] = max(lc[j], l); uc[j] = min(uc[j], u)
     c = np.zeros(n)
@@ -160,7 +162,7 @@ def assemble(plan, slots_k, days, vol_k):
             acc = 0.0
         c[j] = acc
     status = ST_OPTIMAL
-    if np.isnan(lo).any() or np.isnan(hi).any() or np.isnan(lc).any() or np.isnan(uc).any() or np.isnan(c).any():
+    if bad or np.isnan(lo).any() or np.isnan(hi).any() or np.isnan(lc).any() or np.isnan(uc).any() or np.isnan(c).any():
         status = ST_NAN
     elif (lo > hi).any() or (lc > uc + 1e-9).any():
         status = ST_INFEASIBLE

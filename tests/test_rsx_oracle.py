@@ -106,3 +106,39 @@ def test_rsx_scratch_placement_takes_the_same_pivots():
     a = replay(a_eng, s, slots, days)
     b = replay(b_eng, s, slots, days)
     assert np.array_equal(a[2], b[2]) and a_eng.stats()["pivots"] == b_eng.stats()["pivots"] > 0
+
+
+def test_rsx_drift_guard_refactorises_and_recovers():
+    """A damaged basis inverse (here: noise written into W between two timesteps) is caught — by the pivot-element consistency
+    test or by the residual check |A x - r| <= 1e-7 — and the basis is re-factorised from the slack basis by Gauss-Jordan pivots
+    (rsx_core.cuh::refactor); the answers stay those of the dictionary oracle."""
+    s, tr = load_case("network24.edge")
+    S, T = 3, 6
+    slots, days = synth_batch(s, tr, S, T, seed=8, common=True)
+    ref = replay(OracleEngine(s, S), s, slots, days)
+    eng = RsxOracleEngine(s, S)
+    sl = eng.alloc_planes(s.n_slots); ob = eng.alloc_planes(1)
+    eng.reset(None)
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        if t == 3:
+            eng.W[1] += 1e-3 * rng.standard_normal(eng.W[1].shape)   # scenario 1 only
+        sl[:] = slots[t]
+        assert eng.step(float(days[t]), sl, None, None, ob) == 0
+        assert np.max(np.abs(ob[0] - ref[2][t]) / np.maximum(1.0, np.abs(ref[2][t]))) < TOL, t
+    assert eng.stats()["refactors"] >= 1
+
+
+def test_rsx_scenarios_start_cold_when_the_seed_scenario_fails():
+    """scenario 0 carries a NaN in the first timestep: nothing seeds the others, each starts from its own slack basis"""
+    s, tr = load_case("network24.edge")
+    S, T = 4, 3
+    slots, days = synth_batch(s, tr, S, T, seed=6, common=True)
+    used = int(next(r for r in list(s.row_lb_ref) + list(s.row_ub_ref) if r >= 0))
+    bad = slots.copy()
+    bad[0, used, 0] = np.nan
+    a = replay(RsxOracleEngine(s, S), s, bad, days)
+    b = replay(OracleEngine(s, S), s, slots, days)
+    assert a[3][0] == 1 and a[3][1:].sum() == 0
+    assert np.max(np.abs(a[2][:, 1:] - b[2][:, 1:]) / np.maximum(1.0, np.abs(b[2][:, 1:]))) < TOL
+    assert np.max(np.abs(a[2][1:, 0] - b[2][1:, 0]) / np.maximum(1.0, np.abs(b[2][1:, 0]))) < TOL   # scenario 0 recovers next step
