@@ -1121,9 +1121,9 @@ int b200lp_fetch_state(b200lp_handle *h, double *col_flow, double *volume, doubl
 }
 
 #ifdef RSX_PHASE_TIMING
-int b200lp_debug_rsx_phases(b200lp_handle *h, unsigned long long *out16) {
+int b200lp_debug_rsx_phases(b200lp_handle *h, unsigned long long *out16) {  /* 18 values */
     if (!h || !h->pdhg || !pdhg_is_rsx(h)) return -1;
-    return cudaMemcpy(out16, pdhg_rsx_counters(h), sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+    return cudaMemcpy(out16, pdhg_rsx_counters(h), sizeof(unsigned long long) * 18, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
 #endif
 

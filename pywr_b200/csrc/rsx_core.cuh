@@ -37,6 +37,14 @@
 #define RSX_HD static inline
 #endif
 
+// read-only data shared by all scenarios (the sparse matrix): ld.global.nc on the device, so that the compiler may hoist these
+// loads above the stores of the surrounding loops (it cannot prove that the work vectors do not alias them)
+#ifdef __CUDA_ARCH__
+#define RSX_RO(p) __ldg(p)
+#else
+#define RSX_RO(p) (*(p))
+#endif
+
 namespace rsx {
 
 constexpr double TOL_PRIMAL = 1e-9, TOL_DUAL = 1e-9, TOL_PIVOT = 1e-9, TIE_REL = 1e-9, TIE_ABS = 1e-12;
@@ -85,24 +93,25 @@ struct Work {  // block-shared
 };
 
 // Placement of the working vectors.  mode 0: everything in the block's fast memory (shared memory on the device).
-// mode 1: the reduced costs (true / working), the pivot row and the two index lists live in a per-block scratch area in
-// global memory (L2-resident: 104 KB per block for config 4) — they are touched once per timestep and per pivot, with
+// mode 1: the reduced costs (true / working) and the two index lists live in a per-block scratch area in
+// global memory (L2-resident: 73 KB per block for config 4) — they are touched once per timestep and per pivot, with
 // coalesced accesses — which halves the shared-memory footprint: two blocks per SM, so that one scenario's serial phases
 // overlap another's stream of W, and LPs twice as large still fit.
 RSX_HD size_t work_bytes(int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
-    const size_t fast_nv = mode == 0 ? 5 : 2, lists = mode == 0 ? 3 : 1;
+    const size_t fast_nv = mode == 0 ? 5 : 3, lists = mode == 0 ? 3 : 1;
     return 8 * (fast_nv * nv + 4 * (size_t)m) + 4 * (lists * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
 }
 RSX_HD size_t scratch_bytes(int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
-    return mode == 0 ? 0 : 8 * (3 * nv) + 4 * (2 * (size_t)m) + 64;
+    return mode == 0 ? 0 : 8 * (2 * nv) + 4 * (2 * (size_t)m) + 64;
 }
 RSX_FN void work_carve(Work &K, unsigned char *base, unsigned char *scratch, int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
     double *p = reinterpret_cast<double *>(base);
     K.LO = p; p += nv; K.HI = p; p += nv;
-    if (mode == 0) { K.d = p; p += nv; K.dw = p; p += nv; K.alpha = p; p += nv; }
+    if (mode == 0) { K.d = p; p += nv; K.dw = p; p += nv; }
+    K.alpha = p; p += nv;  // the pivot row is read three to four times per pivot: always in fast memory
     K.rho = p; p += m; K.w = p; p += m; K.beta = p; p += m; K.g = p; p += m;
     int *q = reinterpret_cast<int *>(p);
     K.head = q; q += m;
@@ -111,7 +120,7 @@ RSX_FN void work_carve(Work &K, unsigned char *base, unsigned char *scratch, int
     K.stat = reinterpret_cast<unsigned char *>(q);
     if (mode != 0) {
         double *sp = reinterpret_cast<double *>(scratch);
-        K.d = sp; sp += nv; K.dw = sp; sp += nv; K.alpha = sp; sp += nv;
+        K.d = sp; sp += nv; K.dw = sp; sp += nv;
         int *sq = reinterpret_cast<int *>(sp);
         K.list_k = sq; sq += m; K.list_i = sq;
     }
@@ -168,7 +177,8 @@ RSX_FN void compute_alpha(CX &cx, const Lp &P, Work &K) {
         double a = 0.0;
         if (K.stat[v] != V_BASIC) {
             if (v < n) {
-                for (int e = P.csc_ptr[v]; e < P.csc_ptr[v + 1]; e++) a = fma(K.rho[P.csc_row[e]], P.csc_val[e], a);
+                const int e1 = RSX_RO(&P.csc_ptr[v + 1]);
+                for (int e = RSX_RO(&P.csc_ptr[v]); e < e1; e++) a = fma(K.rho[RSX_RO(&P.csc_row[e])], RSX_RO(&P.csc_val[e]), a);
                 a = -a;
             } else {
                 a = K.rho[v - n];
@@ -179,21 +189,44 @@ RSX_FN void compute_alpha(CX &cx, const Lp &P, Work &K) {
     cx.sync();
 }
 
-// w = W M_q
+// w = W M_q: a gather of the few columns of W that M_q touches (W is row-major: every element is its own DRAM sector).
+// Each thread takes four rows at a time and up to four column entries, so that up to 16 independent loads are in flight per
+// thread instead of one dependent DRAM round trip after the other (that was 14 k cycles per pivot).
 template <class CX>
 RSX_FN void compute_w(CX &cx, const Lp &P, const Scen &S, Work &K, int q) {
     const int m = P.m, n = P.n;
+    int ke[4] = {0, 0, 0, 0};
+    double ae[4] = {0.0, 0.0, 0.0, 0.0};
+    int e0 = 0, e1 = 0;
     if (q < n) {
-        const int e0 = P.csc_ptr[q], e1 = P.csc_ptr[q + 1];
-        for (int i = cx.tid; i < m; i += cx.nt) {
-            const double *row = S.W + (size_t)i * P.ldw;
+        e0 = RSX_RO(&P.csc_ptr[q]); e1 = RSX_RO(&P.csc_ptr[q + 1]);
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (e0 + t < e1) { ke[t] = RSX_RO(&P.csc_row[e0 + t]); ae[t] = RSX_RO(&P.csc_val[e0 + t]); }
+    } else {
+        ke[0] = q - n; ae[0] = -1.0; e0 = 0; e1 = 1;
+    }
+    const int ne = e1 - e0 < 4 ? e1 - e0 : 4;
+    for (int base = cx.tid; base < m; base += 4 * cx.nt) {
+        double x[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * cx.nt;
+            const double *row = S.W + (size_t)(i < m ? i : 0) * P.ldw;
+#pragma unroll
+            for (int t = 0; t < 4; t++) x[u][t] = (i < m && t < ne) ? row[ke[t]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * cx.nt;
+            if (i >= m) continue;
             double a = 0.0;
-            for (int e = e0; e < e1; e++) a = fma(row[P.csc_row[e]], P.csc_val[e], a);
+#pragma unroll
+            for (int t = 0; t < 4; t++) a = fma(x[u][t], ae[t], a);
+            if (q < n)
+                for (int e = e0 + 4; e < e1; e++) a = fma(S.W[(size_t)i * P.ldw + RSX_RO(&P.csc_row[e])], RSX_RO(&P.csc_val[e]), a);
             K.w[i] = a;
         }
-    } else {
-        const int k = q - n;
-        for (int i = cx.tid; i < m; i += cx.nt) K.w[i] = -S.W[(size_t)i * P.ldw + k];
     }
     cx.sync();
 }
@@ -292,12 +325,12 @@ template <class CX>
 RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
     const int m = P.m, n = P.n;
     for (int i = cx.tid; i < m; i += cx.nt) {
-        const int e0 = P.csr_ptr[i], e1 = P.csr_ptr[i + 1];
+        const int e0 = RSX_RO(&P.csr_ptr[i]), e1 = RSX_RO(&P.csr_ptr[i + 1]);
         if (e1 - e0 > P.long_len) continue;
         double acc = 0.0;
         for (int e = e0; e < e1; e++) {
-            const int j = P.csr_col[e];
-            if (K.stat[j] != V_BASIC) acc = fma(P.csr_val[e], nb_value(K, j), acc);
+            const int j = RSX_RO(&P.csr_col[e]);
+            if (K.stat[j] != V_BASIC) acc = fma(RSX_RO(&P.csr_val[e]), nb_value(K, j), acc);
         }
         if (K.stat[n + i] != V_BASIC) acc -= nb_value(K, n + i);
         K.g[i] = acc;
@@ -343,13 +376,20 @@ RSX_FN void compute_beta(CX &cx, const Lp &P, const Scen &S, Work &K) {
 template <class CX>
 RSX_FN void init_dw(CX &cx, const Lp &P, Work &K, int shifted) {
     const int nv = P.n + P.m;
-    for (int v = cx.tid; v < nv; v += cx.nt) {
-        double w = K.d[v];
-        if (shifted) {
-            const int s = K.stat[v];
-            if ((s == V_NL && w < -TOL_DUAL) || (s == V_NU && w > TOL_DUAL) || (s == V_NF && fabs(w) > TOL_DUAL)) w = 0.0;
+    for (int base = cx.tid; base < nv; base += 4 * cx.nt) {
+        double w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int v = base + u * cx.nt; w[u] = v < nv ? K.d[v] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int v = base + u * cx.nt;
+            if (v >= nv) continue;
+            if (shifted) {
+                const int s = K.stat[v];
+                if ((s == V_NL && w[u] < -TOL_DUAL) || (s == V_NU && w[u] > TOL_DUAL) || (s == V_NF && fabs(w[u]) > TOL_DUAL)) w[u] = 0.0;
+            }
+            K.dw[v] = w[u];
         }
-        K.dw[v] = w;
     }
     cx.sync();
 }
@@ -366,10 +406,28 @@ RSX_FN void do_pivot(CX &cx, const Lp &P, const Scen &S, Work &K, int r, int q, 
     const double xq_old = nb_value(K, q);
     const double rd = K.d[q] / a_rq, rw = use_dw ? K.dw[q] / a_rq : 0.0;
     cx.sync();
-    for (int v = cx.tid; v < nv; v += cx.nt) {
-        if (K.stat[v] == V_BASIC || v == q) continue;
-        K.d[v] = fma(-rd, K.alpha[v], K.d[v]);
-        if (use_dw) K.dw[v] = fma(-rw, K.alpha[v], K.dw[v]);
+    cx.mark(9);   // leaving / entering selection, pivot row and column
+    // four elements per thread at a time: all loads of a batch are issued before its stores (d / dw may live in the L2 scratch,
+    // where one dependent round trip per element made this loop 16 k cycles per pivot)
+    for (int base = cx.tid; base < nv; base += 4 * cx.nt) {
+        double dv[4], wv[4], av[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int v = base + u * cx.nt;
+            on[u] = v < nv && K.stat[v < nv ? v : 0] != V_BASIC && v != q;
+            av[u] = on[u] ? K.alpha[v] : 0.0;
+            dv[u] = on[u] ? K.d[v] : 0.0;
+            wv[u] = (on[u] && use_dw) ? K.dw[v] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int v = base + u * cx.nt;
+            if (on[u]) {
+                K.d[v] = fma(-rd, av[u], dv[u]);
+                if (use_dw) K.dw[v] = fma(-rw, av[u], wv[u]);
+            }
+        }
     }
     for (int i = cx.tid; i < m; i += cx.nt)
         if (i != r) K.beta[i] = fma(-theta, K.w[i], K.beta[i]);
@@ -382,7 +440,9 @@ RSX_FN void do_pivot(CX &cx, const Lp &P, const Scen &S, Work &K, int r, int q, 
         K.stat[q] = V_BASIC;
         K.stat[p] = (unsigned char)((plo == phi) ? V_NS : (to_upper ? V_NU : V_NL));
     }
+    cx.mark(10);  // reduced costs and basic values
     update_W(cx, P, S, K, r);  // syncs
+    cx.mark(11);  // rank-1 update of W
 }
 
 // the simplex proper (Dict::solve): dual phase on the (shifted) reduced costs, then primal clean-up
@@ -425,30 +485,46 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
             if (!dw_ready) { init_dw(cx, P, K, shifted); dw_ready = true; }
             r = bi;
             const double dir = (double)bd;
+            cx.mark(6);
             load_rho(cx, P, S, K, r);
+            cx.mark(12);
             compute_alpha(cx, P, K);
+            cx.mark(13);
+            // both passes of the ratio test visit the eligible non-basic variables in ascending order, four per thread at a time
+            // with the working reduced costs of a batch loaded together (they may live in the L2 scratch: one dependent round
+            // trip per eligible variable made the two passes the largest part of a pivot)
+            auto scan = [&](auto &&visit) {
+                for (int base = cx.tid; base < nv; base += 4 * cx.nt) {
+                    double a[4], dwv[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int v = base + u * cx.nt;
+                        const int s = v < nv ? K.stat[v] : V_BASIC;
+                        a[u] = v < nv ? K.alpha[v] * dir : 0.0;
+                        ok[u] = (s == V_NL && a[u] > TOL_PIVOT) || (s == V_NU && a[u] < -TOL_PIVOT) || (s == V_NF && fabs(a[u]) > TOL_PIVOT);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? K.dw[base + u * cx.nt] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (ok[u]) visit(base + u * cx.nt, a[u], dwv[u]);
+                }
+            };
             double rmin = INFINITY;
-            for (int v = cx.tid; v < nv; v += cx.nt) {
-                const int s = K.stat[v];
-                const double a = K.alpha[v] * dir;
-                const bool ok = (s == V_NL && a > TOL_PIVOT) || (s == V_NU && a < -TOL_PIVOT) || (s == V_NF && fabs(a) > TOL_PIVOT);
-                if (ok) rmin = fmin(rmin, fabs(K.dw[v]) / fabs(a));
-            }
+            scan([&](int, double a, double dwv) { rmin = fmin(rmin, fabs(dwv) / fabs(a)); });
             rmin = cx.min(rmin);
             if (rmin == INFINITY) return R_INFEASIBLE;
             const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
             double amax = -1.0; int aux = 0;
             q = -1;
-            for (int v = cx.tid; v < nv; v += cx.nt) {
-                const int s = K.stat[v];
-                const double a = K.alpha[v] * dir;
-                const bool ok = (s == V_NL && a > TOL_PIVOT) || (s == V_NU && a < -TOL_PIVOT) || (s == V_NF && fabs(a) > TOL_PIVOT);
-                if (!ok) continue;
-                if (fabs(K.dw[v]) / fabs(a) > thr) continue;
+            scan([&](int v, double a, double dwv) {
+                if (fabs(dwv) / fabs(a) > thr) return;
                 const double key = bland ? 1.0 : fabs(a);
                 if (q < 0 || key > amax) { amax = key; q = v; }
-            }
+            });
             cx.argmax(amax, q, aux);
+            cx.mark(14);
             to_upper = bd < 0;  // the leaving variable goes to the bound it violated
             compute_w(cx, P, S, K, q);
             if (!(fabs(K.alpha[q] + K.w[r]) <= 1e-6 * (1.0 + fabs(K.alpha[q])))) return R_NUMERIC;  // W has drifted
@@ -565,10 +641,10 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
     cx.sync();
     double worst = -1.0; int bi = -1, aux = 0;
     for (int i = cx.tid; i < m; i += cx.nt) {
-        const int e0 = P.csr_ptr[i], e1 = P.csr_ptr[i + 1];
+        const int e0 = RSX_RO(&P.csr_ptr[i]), e1 = RSX_RO(&P.csr_ptr[i + 1]);
         if (e1 - e0 > P.long_len) continue;
         double acc = 0.0;
-        for (int e = e0; e < e1; e++) acc = fma(P.csr_val[e], S.x[(size_t)P.csr_col[e] * S.ldx], acc);
+        for (int e = e0; e < e1; e++) acc = fma(RSX_RO(&P.csr_val[e]), S.x[(size_t)RSX_RO(&P.csr_col[e]) * S.ldx], acc);
         const double gi = K.g[i];
         double res = fabs(acc - gi) / (1.0 + fabs(gi));
         if (res != res) res = INFINITY;

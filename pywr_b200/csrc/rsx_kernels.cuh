@@ -19,7 +19,7 @@ struct RsxCtx {
     // phase timing of debug builds (-DRSX_PHASE_TIMING): cycles of thread 0 between marks, summed per phase
 #ifdef RSX_PHASE_TIMING
     long long t_last;
-    unsigned long long ph[12];
+    unsigned long long ph[16];
     __device__ __forceinline__ void mark(int k) {
         const long long c = clock64();
         if (k > 0) ph[k] += (unsigned long long)(c - t_last);
@@ -105,7 +105,7 @@ rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
     cx.warp = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
     cx.rv = rv; cx.ri = ri; cx.ra = ra;
 #ifdef RSX_PHASE_TIMING
-    for (int k = 0; k < 12; k++) cx.ph[k] = 0;
+    for (int k = 0; k < 16; k++) cx.ph[k] = 0;
     cx.t_last = clock64();
 #endif
     const rsx::Lp &P = D.lp;
@@ -138,7 +138,7 @@ rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
         if (pivots) atomicAdd(&D.counters[0], (unsigned long long)pivots);
         if (refactors) atomicAdd(&D.counters[1], (unsigned long long)refactors);
 #ifdef RSX_PHASE_TIMING
-        for (int k = 0; k < 12; k++) atomicAdd(&D.counters[2 + k], cx.ph[k]);
+        for (int k = 0; k < 16; k++) atomicAdd(&D.counters[2 + k], cx.ph[k]);
 #endif
     }
 }
