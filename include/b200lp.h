@@ -185,8 +185,12 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out);
 /*
  * Engine selection is automatic (b200lp_create): register-resident simplex for LPs up to 64 rows x 32
  * columns, CTA-per-scenario shared-memory simplex up to 227 KB of dictionary, and beyond that the
- * batched restarted-PDHG path (first-order; role of glp_simplex for networks too large for shared
- * memory).  The environment variables B200LP_FORCE_CTA / B200LP_FORCE_PDHG force the larger engines.
+ * large-LP path: structural presolve + scaling, then the revised simplex with every scenario's basis
+ * inverse in HBM while those fit (kernel_variant 300; warm-started from the scenario's previous basis
+ * like glp_simplex behind BasisManager, cython_glpk.pyx:197-232), else the batched restarted-PDHG
+ * iterations (first-order, kernel_variant 200).  The environment variables B200LP_FORCE_CTA /
+ * B200LP_FORCE_PDHG force the larger engines; B200LP_LARGE_ENGINE=rsx|pdhg picks the method of the
+ * large-LP path.  b200lp_load_program / b200lp_run work on every engine except the CTA-per-scenario one.
  * Options of the PDHG path: "pdhg_tol" (relative KKT tolerance, default 1e-8: objectives within 1e-7 relative), "pdhg_max_iter"
  * (default 200000), "pdhg_check" (iterations between convergence tests, default 64), "pdhg_tail" (when no
  * more than this many scenarios still iterate after a batch of the streaming kernels they finish in the
