@@ -140,6 +140,11 @@ int b200lp_device_count(void);
 
 /* Build the engine for `n_scenarios` scenarios on CUDA device `device`. */
 int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device, b200lp_handle **out);
+/* Same with flags.  B200LP_CREATE_FOR_PROGRAM: the handle is meant for b200lp_load_program / b200lp_run; LPs beyond the
+ * register-resident variants then take the large-LP path (which runs programs) instead of the CTA-per-scenario
+ * shared-memory simplex (per-timestep b200lp_step only). */
+#define B200LP_CREATE_FOR_PROGRAM 1u
+int b200lp_create_ex(const b200lp_structure *s, int32_t n_scenarios, int32_t device, uint32_t flags, b200lp_handle **out);
 void b200lp_destroy(b200lp_handle *h);
 
 /*

@@ -176,6 +176,10 @@ int b200lp_device_count(void) {
 }
 
 int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device, b200lp_handle **out) {
+    return b200lp_create_ex(s, n_scenarios, device, 0u, out);
+}
+
+int b200lp_create_ex(const b200lp_structure *s, int32_t n_scenarios, int32_t device, uint32_t flags, b200lp_handle **out) {
     if (!s || !out) return fail(B200LP_E_INVALID, "null argument");
     if (s->abi_version != B200LP_ABI_VERSION) return fail(B200LP_E_INVALID, "ABI version mismatch");
     if (n_scenarios <= 0 || s->n_rows <= 0 || s->n_cols <= 0) return fail(B200LP_E_INVALID, "empty problem");
@@ -197,8 +201,10 @@ int b200lp_create(const b200lp_structure *s, int32_t n_scenarios, int32_t device
     if (variant < 0 || getenv("B200LP_FORCE_CTA")) {
         const int n_val = s->n_slots + s->n_consts + 2 * s->n_storage;
         cta_smem = CtaDict<CTA_THREADS>::bytes(m, n, n_val);
-        // beyond shared memory: the batched restarted-PDHG path (pdhg_engine.cuh)
+        // beyond shared memory: the large-LP path (pdhg_engine.cuh front end; revised simplex or PDHG iterations); also for
+        // mid-size LPs when the handle is meant for device-resident programs, which the CTA-per-scenario engine does not run
         if (cta_smem > 227 * 1024) return create_pdhg(s, n_scenarios, device, out);
+        if ((flags & B200LP_CREATE_FOR_PROGRAM) && s->n_dyn_a == 0 && !getenv("B200LP_FORCE_CTA")) return create_pdhg(s, n_scenarios, device, out);
         use_cta = true;
         variant = 0;
     }

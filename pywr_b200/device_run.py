@@ -50,7 +50,8 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
     if engine_factory is None:
         from .engine import CudaEngine
 
-        engine_factory = CudaEngine
+        def engine_factory(structure, n_scenarios):
+            return CudaEngine(structure, n_scenarios, for_program=True)
     eng = engine_factory(s, S)
     try:
         eng.load_program(prog)
@@ -104,6 +105,10 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
             model.finish()
         t4 = time.perf_counter()
         counters = eng.counters()
+        try:
+            counters = dict(counters, kernel_variant=eng.stats().get("kernel_variant"))
+        except Exception:   # engines without stats() (test doubles)
+            pass
     finally:
         eng.close()
     return DeviceRunResult(

@@ -38,6 +38,7 @@ SYMBOLS = [
     ("b200lp_abi_version", ctypes.c_int, []),
     ("b200lp_device_count", ctypes.c_int, []),
     ("b200lp_create", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    ("b200lp_create_ex", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200lp_destroy", None, [ctypes.c_void_p]),
     ("b200lp_reset", ctypes.c_int, [ctypes.c_void_p, _dp]),
     ("b200lp_step", ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, _dp, _dp, _dp, _dp]),
@@ -129,7 +130,7 @@ class PinnedArray:
 class CudaEngine:
     """One engine per (LP structure, scenario count, device)."""
 
-    def __init__(self, structure, n_scenarios, device=None, **_):
+    def __init__(self, structure, n_scenarios, device=None, for_program=False, **_):
         self.L = load_library()
         self.structure = structure
         self.S = int(n_scenarios)
@@ -138,8 +139,9 @@ class CudaEngine:
         self.device = int(device)
         self._cs = structure.to_c()
         h = ctypes.c_void_p()
-        _check(self.L, self.L.b200lp_create(ctypes.addressof(self._cs), self.S, self.device, ctypes.byref(h)),
-               "b200lp_create")
+        # for_program: B200LP_CREATE_FOR_PROGRAM — mid-size LPs take the large-LP path, which runs device-resident programs
+        _check(self.L, self.L.b200lp_create_ex(ctypes.addressof(self._cs), self.S, self.device, 1 if for_program else 0,
+                                               ctypes.byref(h)), "b200lp_create")
         self.h = h
         self._pinned = []
 

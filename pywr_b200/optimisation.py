@@ -51,7 +51,8 @@ class PopulationEvaluator:
         if engine_factory is None:
             from .engine import CudaEngine
 
-            engine_factory = CudaEngine
+            def engine_factory(structure, n_scenarios):
+                return CudaEngine(structure, n_scenarios, for_program=True)
         self.engine = engine_factory(self.structure, self.S)
         self.engine.load_program(self.program)
         self.n_variables = self.variable_map[-1]

@@ -198,3 +198,29 @@ def test_large_lp_path_as_a_pywr_user_sees_it(monkeypatch):
     for n_dev, n_host in zip(m_dev.nodes, m_host.nodes):
         if hasattr(n_host, "volume"):
             assert rel_diff(n_dev.volume, n_host.volume) <= 1e-6, n_dev.name
+
+
+def test_mid_size_models_run_device_resident_without_any_override():
+    """LP 158 x 104 (edge form of the 24-reach network): too large for the register-resident variants, small enough for the
+    CTA-per-scenario simplex, which only serves b200lp_step.  run_on_device creates its engine with
+    B200LP_CREATE_FOR_PROGRAM, so the model takes the large-LP path (revised simplex, variant 300) and still runs as a
+    device-resident program; Model.run(solver="b200-edge") keeps the CTA engine (variant 100)."""
+    import oracle.pywr_oracle_solver  # noqa: F401
+    import pywr_b200  # noqa: F401
+    from pywr_b200.device_run import run_on_device
+
+    m_host = _network_model("oracle-edge")
+    m_host.run()
+    want = _recorder_values(m_host)
+    m_dev = _network_model("null")
+    res = run_on_device(m_dev, formulation="edge")
+    assert res.counters["kernel_variant"] == 300
+    got = _recorder_values(m_dev)
+    for k in want:
+        assert rel_diff(got[k], want[k]) <= 1e-6, k
+    m_step = _network_model("b200-edge")
+    m_step.run()
+    assert m_step.solver._engine.stats()["kernel_variant"] == 100
+    got = _recorder_values(m_step)
+    for k in want:
+        assert rel_diff(got[k], want[k]) <= 1e-6, k
