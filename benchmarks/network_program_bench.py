@@ -3,7 +3,7 @@
 warm-started revised simplex, flow commit, storage mass balance and recorders all on the GPU (b200lp_load_program +
 b200lp_run on the large-LP path: plane kernels around the batched solve), results fetched at the end.
 
-Scenarios 0 and 1 are the two worlds of the committed fixture (benchmarks/make_network_program.py), whose recorder arrays
+Scenarios 0 and 1 are the two worlds of the committed fixture (tests/golden/make_network_program.py), whose recorder arrays
 come from a host run of the reference framework: they are checked here at full size.  Prints one JSON line.
 
 usage: python benchmarks/network_program_bench.py [--scenarios 8192] [--steps 365] [--engine auto|rsx|pdhg]

@@ -1,6 +1,6 @@
 """the generated ~2,000-node network (edge formulation, LP 3,994 x 2,672)
 on the batched restarted-PDHG path, S scenarios x T daily steps replayed from the committed fixture
-(benchmarks/make_network_fixture.py).  Scenario k scales every recorded input plane by one
+(tests/golden/make_network_fixture.py).  Scenario k scales every recorded input plane by one
 log-normal factor (scenario 0: factor 1, so its objective must equal HiGHS's recorded optimum).
 
 Prints one JSON line: scenario-timesteps/s, PDHG iterations, and the achieved HBM bandwidth of the

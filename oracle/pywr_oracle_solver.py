@@ -46,7 +46,7 @@ register()
 
 class OracleRsxEdgeSolver(OracleSolver):
     """Edge formulation solved by the HOST build of the revised-simplex core (oracle/rsx_oracle.py): fast enough for
-    host runs of the 2,073-node network (benchmarks/make_network_program.py)."""
+    host runs of the 2,073-node network (tests/golden/make_network_program.py)."""
     name = "oracle-rsx-edge"
     formulation = "edge"
 

@@ -7,7 +7,7 @@ aggregated licence) is run in the edge formulation with a HiGHS-backed stand-in 
 timestep: the input planes the solver gathers (slots), the timestep length and HiGHS's optimal
 objective.  Output: benchmarks/fixtures/network600.edge.{structure,trace}.npz
 
-usage: python benchmarks/make_network_fixture.py [n_reaches] [steps]
+usage: python tests/golden/make_network_fixture.py [n_reaches] [steps]
 """
 import os
 import sys
@@ -16,7 +16,7 @@ import numpy as np
 import scipy.sparse as sp
 from scipy.optimize import linprog
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
 sys.path.insert(0, ROOT)
 

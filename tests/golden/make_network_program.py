@@ -1,5 +1,5 @@
 """Generates the device-run fixture of SURVEY.md 8(d) config 4 (BUILD container only: imports the reference framework
-from baseline/_ref).
+from baseline/_ref and, as test infrastructure, the oracle).
 
 The generated 2,073-node river network (benchmarks.workloads.synthetic_network_document, 600 reaches) gets a scenario axis
 `inflow`: every catchment inflow is its monthly profile times a per-scenario wetness factor (ConstantScenarioParameter), so
@@ -8,7 +8,7 @@ C-ABI, (2) the recorder arrays of a HOST run of the reference framework (Model.r
 Storage.after / Recorder code) with the host build of the revised-simplex core as solver.
 
 Output: benchmarks/fixtures/network600.{pstructure,program,expected}.npz
-usage: python benchmarks/make_network_program.py [n_reaches] [end-date]
+usage: python tests/golden/make_network_program.py [n_reaches] [end-date]
 """
 import os
 import sys
@@ -17,7 +17,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
 sys.path.insert(0, ROOT)
 warnings.filterwarnings("ignore")

@@ -75,6 +75,11 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "lp_oracle" not in src.replace("oracle/lp_oracle.c", ""), f
+    # the benchmark scripts measure the product only (bench.py's cpu_baseline / --impl reference legs are the one exception)
+    for f in os.listdir(os.path.join(ROOT, "benchmarks")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "benchmarks", f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
 
 
 def test_structure_roundtrip(tmp_path):

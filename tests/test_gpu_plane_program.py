@@ -140,7 +140,7 @@ def test_plane_program_on_the_2000_node_network_matches_the_reference_host_run()
     """SURVEY 8(d) config 4 end to end on the device: the 2,073-node network (LP 3,994 x 2,672, 1,201 ops, 601 tables, 30
     recorders) for a year of daily timesteps.  b200lp_create picks the revised simplex by itself; the recorder arrays must
     equal those of the reference framework's HOST run (Model.run with the reference's own Parameter / Storage.after /
-    Recorder code, benchmarks/make_network_program.py) within north_star's 1e-6 — observed: round-off."""
+    Recorder code, tests/golden/make_network_program.py) within north_star's 1e-6 — observed: round-off."""
     import os
 
     from pywr_b200.engine import CudaEngine

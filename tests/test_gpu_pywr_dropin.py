@@ -144,7 +144,7 @@ def test_population_evaluator_on_the_gpu():
 
 def _network_model(solver, n_reaches=24, end="2100-03-31"):
     """generated river network (benchmarks.workloads.synthetic_network_document) with a 3-member wetness scenario and
-    a few recorders; the same document as benchmarks/make_network_program.py at a size the oracle solves in seconds"""
+    a few recorders; the same document as tests/golden/make_network_program.py at a size the oracle solves in seconds"""
     from pywr.model import Model
     from pywr.recorders import (MinimumVolumeStorageRecorder, NumpyArrayNodeRecorder, NumpyArrayStorageRecorder,
                                 TotalDeficitNodeRecorder)
