@@ -7,6 +7,9 @@ Scenarios 0 and 1 are the two worlds of the committed fixture (tests/golden/make
 come from a host run of the reference framework: they are checked here at full size.  Prints one JSON line.
 
 usage: python benchmarks/network_program_bench.py [--scenarios 8192] [--steps 365] [--engine auto|rsx|pdhg]
+N GPUs of one box (weak scaling: --scenarios per GPU, scenario shards with their own wetness draws, no data-path collective;
+NCCL only for the barrier and the max-over-ranks time):
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P benchmarks/network_program_bench.py
 """
 import argparse
 import copy
@@ -27,9 +30,9 @@ from pywr_b200.structure import LPStructure  # noqa: E402
 FIX = os.path.join(ROOT, "benchmarks", "fixtures", "network600")
 
 
-def widen(s, base, S, T, seed=20240903):
+def widen(s, base, S, T, seed=20240903, rank=0):
     """S scenarios: the per-scenario table(s) (the wetness factor) get S columns; scenario k < 2 keeps the fixture's value"""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, rank])
     q = copy.copy(base)
     q.n_steps = T
     q.ts_days = base.ts_days[:T].copy()
@@ -82,29 +85,55 @@ def main():
     a = ap.parse_args()
     if a.engine != "auto":
         os.environ["B200LP_LARGE_ENGINE"] = a.engine
+    world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     s = LPStructure.load(FIX + ".pstructure.npz")
     base = Program.load(FIX + ".program.npz")
     S, T = a.scenarios, min(a.steps, base.n_steps)
-    q = widen(s, base, S, T)
-    eng = CudaEngine(s, S, device=0)
+    q = widen(s, base, S, T, rank=rank)
+    eng = CudaEngine(s, S, device=local_rank)
     st0 = eng.stats()
     w0 = time.perf_counter()
     eng.load_program(q)
     load_s = time.perf_counter() - w0
     eng.sync()
+    barrier()
     w0 = time.perf_counter()
     eng.mark(0)
     eng.run(0, T)
     eng.mark(1)
     eng.sync()
-    wall = time.perf_counter() - w0
-    dev_s = eng.elapsed_ms() / 1e3
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - w0)
+    dev_s = max_over_ranks(eng.elapsed_ms() / 1e3)
     status = eng.program_status()
     w0 = time.perf_counter()
     outs = [eng.fetch_recorder(r, q.rec_shape(r, S)) for r in range(q.n_recorders)]
     read_s = time.perf_counter() - w0
-    worst, checked = check_against_fixture(outs, q, T, base.n_steps)
+    worst, checked = check_against_fixture(outs, q, T, base.n_steps) if rank == 0 else (0.0, 0)
     st = eng.stats()
+    failed_all = int(max_over_ranks(float(status[0])))
+    S_total = S * world
     m_r = st["reduced_rows"]
     wbytes = 8 * m_r * ((m_r + 1) & ~1)
     peak = 6541.8
@@ -112,18 +141,21 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
     except Exception:
         pass
-    out = {"metric": "scenario-timesteps/sec (config 4, device-resident run)", "value": S * T / dev_s, "unit": "scenario-timesteps/s",
-           "scenarios": S, "timesteps": T, "device_s": dev_s, "wall_s": wall, "load_program_s": load_s, "readout_s": read_s,
+    out = {"metric": "scenario-timesteps/sec (config 4, device-resident run)", "value": S_total * T / dev_s, "unit": "scenario-timesteps/s",
+           "n_gpus": world, "scaling": "weak", "scenarios": S_total, "scenarios_per_gpu": S, "timesteps": T, "device_s": dev_s, "wall_s": wall, "load_program_s": load_s, "readout_s": read_s,
            "kernel_variant": st0["kernel_variant"], "rows": s.n_rows, "cols": s.n_cols, "reduced_rows": m_r, "nodes": s.n_nodes,
-           "ops": int(q.n_ops), "tables": int(q.n_tables), "recorders": int(q.n_recorders), "failed_scenarios": status[0],
+           "ops": int(q.n_ops), "tables": int(q.n_tables), "recorders": int(q.n_recorders), "failed_scenarios_max_over_ranks": failed_all,
            "pivots": st["pivots"], "refactors": st["refactors"], "pivots_per_scenario_timestep": st["pivots"] / (S * T),
            "pdhg_iterations": st["pdhg_iterations"], "kernel_launches": st["kernel_launches"],
            "max_rel_diff_vs_reference_host_run_scenarios_0_1": worst, "recorders_checked": checked,
            "roofline": {"bound": "hbm", "achieved": wbytes * S * T / dev_s / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": wbytes * S * T / dev_s / 1e9 / peak, "bytes_per_scenario_timestep": wbytes,
-                        "note": "algorithmic bytes = one read of the scenario's basis inverse per scenario-timestep"} if st0["kernel_variant"] == 300 else None}
-    print(json.dumps(out))
+                        "note": "per GPU; algorithmic bytes = one read of the scenario's basis inverse per scenario-timestep"} if st0["kernel_variant"] == 300 else None}
+    if rank == 0:
+        print(json.dumps(out))
     eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
