@@ -496,7 +496,8 @@ int b200lp_status(b200lp_handle *h, int32_t *first_bad_scenario, int32_t *code) 
 
 int b200lp_get_basis(b200lp_handle *h, int32_t *row_stat, int32_t *col_stat) {
     if (!h || !row_stat || !col_stat) return fail(B200LP_E_INVALID, "null argument");
-    if (h->pdhg) return fail(B200LP_E_UNSUPPORTED, "the PDHG path carries (x, y, omega) between timesteps, not a basis");
+    if (h->pdhg && pdhg_is_rsx(h)) { CUDA_TRY(cudaSetDevice(h->device)); return rsx_get_basis(h, row_stat, col_stat); }
+    if (h->pdhg) return fail(B200LP_E_UNSUPPORTED, "the PDHG iterations carry (x, y, omega) between timesteps, not a basis");
     CUDA_TRY(cudaSetDevice(h->device));
     const int m = h->ds.m, n = h->ds.n, rows_cap = h->ds.rows_cap, nc = h->ds.nc;
     const size_t S = (size_t)h->S;

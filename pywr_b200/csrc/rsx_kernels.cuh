@@ -185,6 +185,41 @@ __global__ void rsx_scatter_x(const RsxDev D) {
     }
 }
 
+// Basis of every scenario in the ORIGINAL row space, GLPK-coded (BasisManager.row_stat / col_stat, cython_glpk.pyx:197-232):
+// a kept row carries the status of its slack; a dropped row is basic; a column that is non-basic in the reduced LP at a bound
+// that came from one of its singleton rows (pdhg_assemble_cols) is, in the original LP, basic with THAT row non-basic at the
+// bound - the same vertex, the same number (m) of basic variables.  One thread per (scenario, column); the singleton rows of
+// different columns are disjoint.
+__global__ void rsx_basis_kernel(const RsxDev D, const PdhgDev P, const double *__restrict__ slots, const double *__restrict__ vol,
+                                 const double days, int *__restrict__ row_stat, int *__restrict__ col_stat) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (s >= D.S) return;
+    const int n = P.n, m = P.m, nv = n + D.lp.m;
+    const unsigned char *stat = D.stat + (size_t)s * nv;
+    int *rs = row_stat + (size_t)s * m, *cs = col_stat + (size_t)s * n;
+    if (j == 0) {  // this thread also maps the kept rows (after every thread of the scenario wrote "basic" below: disjoint rows)
+        for (int r = 0; r < D.lp.m; r++) rs[__ldg(&P.keep[r])] = stat[n + r];
+    }
+    int st = stat[j];
+    double lc = 0.0, uc = INFINITY;
+    int src_lo = -1, src_hi = -1, code_lo = 0, code_hi = 0;
+    for (int e = __ldg(&P.sing_ptr[j]); e < __ldg(&P.sing_ptr[j + 1]); e++) {
+        const int i = __ldg(&P.sing_row[e]);
+        double l, u;
+        pd_row_bounds(P, slots, vol, i, s, days, l, u);
+        const double a = __ldg(&P.sing_coef[e]);
+        const double l2 = a > 0.0 ? l / a : u / a, u2 = a > 0.0 ? u / a : l / a;
+        if (l2 > lc) { lc = l2; src_lo = i; code_lo = (l == u) ? rsx::V_NS : (a > 0.0 ? rsx::V_NL : rsx::V_NU); }
+        if (u2 < uc) { uc = u2; src_hi = i; code_hi = (l == u) ? rsx::V_NS : (a > 0.0 ? rsx::V_NU : rsx::V_NL); }
+        rs[i] = rsx::V_BASIC;
+    }
+    if (st == rsx::V_NS) st = src_lo >= 0 ? rsx::V_NL : (src_hi >= 0 ? rsx::V_NU : st);
+    if (st == rsx::V_NL && src_lo >= 0) { rs[src_lo] = code_lo; st = rsx::V_BASIC; }
+    else if (st == rsx::V_NU && src_hi >= 0) { rs[src_hi] = code_hi; st = rsx::V_BASIC; }
+    cs[j] = st;
+}
+
 // basis, reduced costs and inverse of scenario `src` become the starting point of every other scenario
 __global__ void rsx_seed_kernel(const RsxDev D, const int src, const int s_off) {
     const int s = s_off + blockIdx.y;
