@@ -151,6 +151,9 @@ def run_cpu(s, prog, info, steps, warmup, threads):
     return units * len(times) / sum(times), float(np.mean(times)), nfail
 
 
+E2E_CHUNKS = int(os.environ.get("B200_BENCH_CHUNKS", "16"))   # time slices of the pipelined end-to-end run
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -264,7 +267,7 @@ def main():
 
         def e2e_step():
             # the call a user makes: host table in, host recorder arrays out, time slices pipelined
-            eng.run_pipelined({inflow_table: host_in}, host_out, chunks=16)
+            eng.run_pipelined({inflow_table: host_in}, host_out, chunks=E2E_CHUNKS)
 
         for _ in range(2):
             e2e_step()
@@ -278,7 +281,7 @@ def main():
         e2e_time = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * units * args.steps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_time / args.steps * 1e3,
-               "api": "b200lp_run_pipelined: reset + upload + run + read-out of every recorder, 16 time slices on three "
+               "api": f"b200lp_run_pipelined: reset + upload + run + read-out of every recorder, {E2E_CHUNKS} time slices on three "
                       "streams (pinned host buffers)"}
 
     # ---- multi-GPU read-out: NCCL gather of the per-scenario recorder values -----------------
