@@ -54,6 +54,45 @@ static void launch_variant(const DevStructure &st, const DevState &state, int S,
 typedef void (*run_fn)(const DevStructure &, const DevState &, const DevProgram &, int S, int t0, int nsteps,
                        cudaStream_t stream, int block);
 
+// Blocks per SM of the run kernel (lp_kernel.cuh::lp_run_kernel MINB) for this batch.  The kernel is a latency-bound chain
+// per scenario, so a launch takes (number of waves) x (chain time): 4,096 thames scenarios are 512 blocks, two waves of the
+// 444 resident blocks of the 168-register build but ONE wave of the 592 of the 128-register build (measured on B200: 66.9 ->
+// 38.2 ms per 30-year run), while 1,024 two_reservoir scenarios fit one wave either way and the 168-register chain is 25 %
+// shorter (34.2 vs 42.7 ms).  B200LP_RUN_BLOCKS=3|4 overrides.
+template <int RPL, int NC>
+static int pick_run_blocks(int grid) {
+    if (RPL != 1) return 3;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const char *v = getenv("B200LP_RUN_BLOCKS");
+    const int forced = v ? atoi(v) : 0;
+    if (forced == 3 || forced == 4) return forced;
+    // up to two waves the blocks run in lockstep (whole waves count); beyond that the scheduler refills SMs as blocks finish
+    // (fractional waves) and the spilled values also cost issue slots.  Measured on B200 (ms per run, 3 / 4 blocks per SM):
+    // thames 4,096: 66.9 / 38.2; thames 65,536 x 3 y: 64.7 / 53.1; two_reservoir 2,048: 70.0 / 52.4; 32,768 x 5 y: 70.6 / 76.8
+    const double w3 = (double)grid / (3.0 * sms), w4 = (double)grid / (4.0 * sms);
+    if (w3 <= 1.0) return 3;
+    const bool lockstep = w3 <= 2.0;
+    const double waves3 = lockstep ? ceil(w3) : w3, waves4 = lockstep ? ceil(w4) : w4;
+    const double slowdown = NC <= 8 ? 1.05 : (NC <= 13 ? (lockstep ? 1.25 : 1.45) : 1.6);  // chain time, 128- / 168-register build
+    return waves4 * slowdown < waves3 ? 4 : 3;
+}
+
+template <int G, int RPL, int NC, int MINB>
+static void run_variant_mb(const DevStructure &st, const DevState &state, const DevProgram &pg, int S, int t0, int nsteps,
+                           cudaStream_t stream, int block, int grid, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    lp_run_kernel<G, RPL, NC, MINB><<<grid, block, smem, stream>>>(st, state, pg, S, t0, nsteps);
+}
+
 template <int G, int RPL, int NC>
 static void run_variant(const DevStructure &st, const DevState &state, const DevProgram &pg, int S, int t0, int nsteps,
                         cudaStream_t stream, int block) {
@@ -61,12 +100,10 @@ static void run_variant(const DevStructure &st, const DevState &state, const Dev
     const int grid = (S + groups_per_block - 1) / groups_per_block;
     const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
     const size_t smem = gbytes * groups_per_block + sizeof(int) * (size_t)(((pg.n_code + 3) & ~3) + pg.n_fop_levels * 32 * FOP_WORDS + 4);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
-    lp_run_kernel<G, RPL, NC><<<grid, block, smem, stream>>>(st, state, pg, S, t0, nsteps);
+    if (RPL == 1 && block == 128 && pick_run_blocks<RPL, NC>(grid) == 4)
+        run_variant_mb<G, RPL, NC, (RPL == 1 ? 4 : 1)>(st, state, pg, S, t0, nsteps, stream, block, grid, smem);
+    else
+        run_variant_mb<G, RPL, NC, (RPL == 1 ? B200LP_RUN_MIN_BLOCKS : 1)>(st, state, pg, S, t0, nsteps, stream, block, grid, smem);
 }
 
 struct Variant {

@@ -1044,8 +1044,11 @@ __device__ __forceinline__ double div_by_const(const double a, const double b, c
     return fma(r, y, q0);
 }
 
-template <int G, int RPL, int NC>
-__global__ void __launch_bounds__(128, (RPL == 1 ? B200LP_RUN_MIN_BLOCKS : 1))
+// MINB: resident blocks per SM the register allocation is sized for (RPL == 1 variants): 3 -> 168 registers, the shortest
+// per-timestep chain; 4 -> 128 registers (a few spilled values on the chain: +4 % for 8 columns, +25 % for 13) but a third more
+// resident warps, which decides when the batch does not fit one wave of the 3-block build (b200lp.cu::run_variant).
+template <int G, int RPL, int NC, int MINB>
+__global__ void __launch_bounds__(128, (RPL == 1 ? MINB : 1))
 lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, const int S, const int t0,
               const int nsteps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -95,3 +95,27 @@ def test_pipelined_run_equals_serial_run(name, S, chunks):
     for a, b in zip(serial, outs):
         assert np.array_equal(a, b, equal_nan=True)
     gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name,S,seed", [("two_reservoir.route", 300, 5), ("thames.route", 1000, 6), ("demand_saving2.route", 64, 7)])
+def test_run_kernel_register_builds_agree(monkeypatch, name, S, seed):
+    """The run kernel exists in a 168-register build (3 blocks per SM: shortest chain) and a 128-register build (4 blocks
+    per SM: a third more resident warps; chosen when the batch would otherwise need another wave, b200lp.cu::pick_run_blocks).
+    Same source, same arithmetic: bit-identical recorders, states and pivot counts, both equal to the oracle's."""
+    s, prog, _, names = load_program_case(name)
+    q = widen_program(s, prog, S, seed)
+    res = {}
+    for blocks in ("3", "4"):
+        monkeypatch.setenv("B200LP_RUN_BLOCKS", blocks)
+        cpu, gpu = _engines(s, S)
+        res[blocks] = run_program(gpu, q) + (gpu.counters()["pivots"],)
+        if blocks == "4":
+            o_cpu, st_cpu, _ = run_program(cpu, q)
+        gpu.close(); cpu.close()
+    a, b = res["3"], res["4"]
+    assert a[1] == b[1] == st_cpu and a[3] == b[3]
+    for x, y, z, nm in zip(a[0], b[0], o_cpu, names):
+        assert np.array_equal(x, y, equal_nan=True), nm
+        assert _rel(y, z) <= 1e-9, nm
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y, equal_nan=True)
