@@ -25,7 +25,7 @@ struct HostCtx {
 extern "C" int rsx_host_run(int m, int n, const int *csr_ptr, const int *csr_col, const double *csr_val, const int *csc_ptr,
                             const int *csc_row, const double *csc_val, int cost_dynamic, double *W, int *head,
                             unsigned char *stat, double *d, int *info, const double *c, const double *lc, const double *uc,
-                            const double *lo, const double *hi, double *x, int cold, int *pivots, int *refactors, int mode) {
+                            const double *lo, const double *hi, double *x, int cold, int *pivots, int *refactors, int mode, int refresh_pivots) {
     // rows longer than 12 entries take the "long row" path of the core (PD_LONG of the device front end)
     int n_long = 0;
     for (int i = 0; i < m; i++) n_long += csr_ptr[i + 1] - csr_ptr[i] > 12;
@@ -39,6 +39,7 @@ extern "C" int rsx_host_run(int m, int n, const int *csr_ptr, const int *csr_col
     P.csc_ptr = csc_ptr; P.csc_row = csc_row; P.csc_val = csc_val;
     P.cost_dynamic = cost_dynamic;
     P.n_long = n_long; P.long_len = 12; P.long_rows = long_rows;
+    P.refresh_pivots = refresh_pivots;
     rsx::Scen S;
     S.W = W; S.head = head; S.stat = stat; S.d = d; S.info = info;
     S.c = c; S.lc = lc; S.uc = uc; S.lo = lo; S.hi = hi; S.x = x; S.ld = 1; S.bt = nullptr; S.ldx = 1;

@@ -29,7 +29,7 @@ def lib():
         dp, ip, bp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
         L.rsx_host_run.restype = ctypes.c_int
         L.rsx_host_run.argtypes = [ctypes.c_int, ctypes.c_int, ip, ip, dp, ip, ip, dp, ctypes.c_int, dp, ip, bp, dp, ip,
-                                   dp, dp, dp, dp, dp, dp, ctypes.c_int, ip, ip, ctypes.c_int]
+                                   dp, dp, dp, dp, dp, dp, ctypes.c_int, ip, ip, ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -39,7 +39,8 @@ def _p(a, t):
 
 
 class RsxOracleEngine(PdhgOracleEngine):
-    def __init__(self, structure, n_scenarios, mode=0, **kw):
+    def __init__(self, structure, n_scenarios, mode=0, refresh_pivots=1000, **kw):
+        self.refresh_pivots = refresh_pivots   # rebuild the reduced costs after this many pivots of a scenario (device: 1000)
         self.mode = mode   # placement of the working vectors (rsx_core.cuh::work_carve); no effect on the arithmetic
         super().__init__(structure, n_scenarios, **kw)
         self._bind()
@@ -83,7 +84,7 @@ class RsxOracleEngine(PdhgOracleEngine):
         return L.rsx_host_run(p.m_r, p.n, _p(self.csr[0], i), _p(self.csr[1], i), _p(self.csr[2], d), _p(self.csc[0], i),
                               _p(self.csc[1], i), _p(self.csc[2], d), self.cost_dynamic, _p(self.W[k], d), _p(self.head[k], i),
                               _p(self.stat[k], b), _p(self.d[k], d), _p(self.info[k], i), *[_p(a, d) for a in arrs],
-                              _p(self.xs[k], d), int(cold), _p(self.pivots, i), _p(self.refactors, i), int(self.mode))
+                              _p(self.xs[k], d), int(cold), _p(self.pivots, i), _p(self.refactors, i), int(self.mode), int(self.refresh_pivots))
 
     def step(self, days, slots, node_flow=None, col_flow=None, objective=None):
         p = self.plan

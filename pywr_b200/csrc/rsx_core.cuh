@@ -66,6 +66,9 @@ struct Lp {  // shared by all scenarios
     // L2 round trips: 160 us of a 470 us scenario-timestep)
     int n_long, long_len;
     const int *long_rows;
+    // the reduced costs are carried from pivot to pivot and from timestep to timestep; after this many pivots of a scenario
+    // they are rebuilt from W and the costs (bounds the round-off a 30-year run could accumulate); 0: never
+    int refresh_pivots;
 };
 
 struct Scen {  // one scenario: persistent state + this timestep's planes (element stride ld)
@@ -680,6 +683,8 @@ RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, i
     }
     cx.mark(2);
     int status = R_OPTIMAL;
+    const int p_before = pivots;
+    const bool refresh = valid && P.refresh_pivots > 0 && S.info[1] >= P.refresh_pivots;
     for (int attempt = valid ? 0 : 2; attempt < 3; attempt++) {
         if (attempt == 1) {
             refactors++;
@@ -687,7 +692,7 @@ RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, i
             compute_d(cx, P, S, K);
         } else if (attempt == 2) {
             cold_init(cx, P, S, K);
-        } else if (P.cost_dynamic) {
+        } else if (P.cost_dynamic || refresh) {
             compute_d(cx, P, S, K);
         }
         status = solve(cx, P, S, K, pivots);
@@ -701,7 +706,10 @@ RSX_FN int run_scenario(CX &cx, const Lp &P, const Scen &S, Work &K, int cold, i
     }
     for (int v = cx.tid; v < nv; v += cx.nt) { S.stat[v] = K.stat[v]; S.d[v] = K.d[v]; }
     for (int i = cx.tid; i < m; i += cx.nt) S.head[i] = K.head[i];
-    if (cx.leader()) S.info[0] = status == R_OPTIMAL ? 1 : 0;
+    if (cx.leader()) {
+        S.info[0] = status == R_OPTIMAL ? 1 : 0;
+        S.info[1] = (refresh || !valid ? 0 : S.info[1]) + (pivots - p_before);   // pivots since the reduced costs were last rebuilt
+    }
     cx.sync();
     cx.mark(8);
     return status == R_NUMERIC ? R_SINGULAR : status;

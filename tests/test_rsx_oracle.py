@@ -142,3 +142,17 @@ def test_rsx_scenarios_start_cold_when_the_seed_scenario_fails():
     assert a[3][0] == 1 and a[3][1:].sum() == 0
     assert np.max(np.abs(a[2][:, 1:] - b[2][:, 1:]) / np.maximum(1.0, np.abs(b[2][:, 1:]))) < TOL
     assert np.max(np.abs(a[2][1:, 0] - b[2][1:, 0]) / np.maximum(1.0, np.abs(b[2][1:, 0]))) < TOL   # scenario 0 recovers next step
+
+
+def test_rsx_reduced_cost_refresh_changes_nothing():
+    """rebuilding the reduced costs from W and the costs every few pivots (the device does it every 1,000 pivots of a scenario to
+    bound accumulated round-off) gives the same pivots and objectives as carrying them"""
+    s, tr = load_case("network24.edge")
+    S, T = 4, 10
+    slots, days = synth_batch(s, tr, S, T, seed=12, common=True)
+    a_eng, b_eng = RsxOracleEngine(s, S, refresh_pivots=0), RsxOracleEngine(s, S, refresh_pivots=3)
+    a = replay(a_eng, s, slots, days)
+    b = replay(b_eng, s, slots, days)
+    assert a[3].sum() == 0 and b[3].sum() == 0
+    assert np.max(np.abs(a[2] - b[2]) / np.maximum(1.0, np.abs(a[2]))) < 1e-12
+    assert a_eng.stats()["pivots"] == b_eng.stats()["pivots"] > 3 * S
