@@ -41,5 +41,5 @@ rm -rf "$TMP"
 # be run against the CUDA engine on the GPU box (oracle/run_reference_tests.sh b200).  baseline/_ref/ is
 # git-ignored: nothing of the reference enters the history.
 rm -rf "$HERE/_ref/_reftests"
-cp -r "$REF/tests" "$HERE/_ref/_reftests"
+cp -r "$SRC/tests" "$HERE/_ref/_reftests"
 echo "built pywr into $HERE/_ref"

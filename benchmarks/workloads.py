@@ -114,11 +114,14 @@ def two_reservoir_document(start, end, control_curve=0.5):
 
 def thames_document(start, end):
     """examples/thames: catchment -> river -> (minimum residual flow gauge -> sea | abstraction ->
-    reservoir -> demand) with demand saving driven by the reservoir's control curves."""
+    reservoir -> demand) with demand saving driven by the reservoir's control curves; the shipped
+    5-member `demand` scenario (growth factors) is kept and sliced to its central member
+    (`slice: [2, 3]`, pywr/_core.pyx:122-124)."""
     prof = lambda a, b: [a, a, a, a, b, b, b, b, a, a, a, a]  # noqa: E731
     return {
         "metadata": {"title": "thames (benchmark)", "minimum_version": "0.1"},
         "timestepper": {"start": start, "end": end, "timestep": 1},
+        "scenarios": [{"name": "demand", "size": 5, "slice": [2, 3]}],
         "nodes": [
             {"name": "catchment1", "type": "catchment", "flow": 0.0},
             {"name": "river1", "type": "link"},
@@ -134,7 +137,8 @@ def thames_document(start, end):
             "demand_baseline": {"type": "constant", "value": 1.7},
             "demand_profile": {"type": "monthlyprofile", "values": prof(0.9, 1.2)},
             "demand_max_flow": {"type": "aggregated", "agg_func": "product",
-                                "parameters": ["demand_baseline", "demand_profile", "demand_saving_factor"]},
+                                "parameters": ["demand_baseline", "demand_profile", "demand_saving_factor",
+                                               "demand_growth_factor"]},
             "level1": {"type": "monthlyprofile", "values": [0.8, 0.85, 0.9, 0.92, 0.9, 0.85, 0.8, 0.7, 0.65, 0.7, 0.75, 0.8]},
             "level2": {"type": "monthlyprofile", "values": [0.5, 0.55, 0.6, 0.62, 0.6, 0.55, 0.5, 0.4, 0.35, 0.4, 0.45, 0.5]},
             "demand_saving_level": {"type": "controlcurveindex", "storage_node": "reservoir1",
@@ -144,6 +148,8 @@ def thames_document(start, end):
             "level0_factor": {"type": "constant", "value": 1.0},
             "level1_factor": {"type": "monthlyprofile", "values": prof(0.95, 0.9)},
             "level2_factor": {"type": "monthlyprofile", "values": prof(0.8, 0.75)},
+            "demand_growth_factor": {"type": "constantscenario", "scenario": "demand",
+                                     "values": [0.75, 0.9, 1.0, 1.1, 1.25]},
         },
         "recorders": {
             "volume": {"type": "NumpyArrayStorageRecorder", "node": "reservoir1"},
@@ -285,7 +291,7 @@ def load_workload(name, n_scenarios, years=None, first_scenario=0, inflow=None):
     for t in range(base.n_tables):
         r0, c0 = int(base.table_rows[t]), int(base.table_cols[t])
         data = base.table_data[base.table_offset[t]: base.table_offset[t] + r0 * c0].reshape(r0, c0)
-        if base.table_axis[t] >= 0:      # the inflow table (scenario axis "inflow")
+        if base.table_axis[t] >= 0 and r0 > 1:      # the inflow table ([T, members] over scenario axis "inflow")
             data = inflow
         elif r0 > 1:
             data = data[:T]
@@ -294,7 +300,13 @@ def load_workload(name, n_scenarios, years=None, first_scenario=0, inflow=None):
     q.table_rows, q.table_cols = np.array(rows, np.int32), np.array(cols, np.int32)
     q.table_axis, q.table_offset = np.array(axis, np.int32), np.array(offs, np.int64)
     q.table_data = np.concatenate(chunks)
-    q.scen_index = np.tile(np.arange(S, dtype=np.int32), (max(base.n_axes, 1), 1)).reshape(-1)
+    # scenario indices: the inflow axis (the one the [T, S] table is indexed by) counts the scenarios of this
+    # batch, every other axis keeps the member the fixture was compiled with (thames: `demand` sliced to member 2)
+    n_ax = max(base.n_axes, 1)
+    inflow_axes = {int(a) for a, r in zip(base.table_axis, base.table_rows) if a >= 0 and r > 1}
+    base_idx = np.asarray(base.scen_index, np.int32).reshape(n_ax, -1)[:, 0]
+    q.scen_index = np.stack([np.arange(S, dtype=np.int32) if (a in inflow_axes or base.n_axes == 0) else
+                             np.full(S, base_idx[a], np.int32) for a in range(n_ax)]).reshape(-1)
     nst = max(s.n_storage, 1)
     q.initial_volume = np.repeat(base.initial_volume.reshape(nst, -1)[:, :1], S, axis=1).reshape(-1)
     q.initial_pc = np.repeat(base.initial_pc.reshape(nst, -1)[:, :1], S, axis=1).reshape(-1)

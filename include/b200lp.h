@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 7
+#define B200LP_ABI_VERSION 8
 
 /* error codes */
 #define B200LP_OK 0
@@ -261,13 +261,19 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
 #define B200LP_REC_DEFICIT_FREQ 10    /* [S]     += 1 if |value-max_flow| > 1e-6   (:1808-1822)               */
 #define B200LP_REC_MIN_VOLUME 11      /* [S]     min(volume)                        (:1845-1852)               */
 
+/* program flags.  AGG_ONLY: the array recorders keep only their running temporal aggregates (sum / min / max over the
+ * timesteps, what Recorder.values() reduces _data to, pywr/recorders/_recorders.pyx:109-184,630-633); no [T][S] array is
+ * allocated or written, b200lp_fetch_recorder on them fails with B200LP_E_UNSUPPORTED.  For optimisation batches and
+ * ensembles that read objectives only (config 5: 11 GB of arrays otherwise). */
+#define B200LP_PROG_AGG_ONLY 1
+
 typedef struct b200lp_program {
     int32_t n_steps;     /* T: timesteps of the run                                                   */
     int32_t n_ops;
     int32_t n_tables;
     int32_t n_axes;      /* scenario axes (model.scenarios.scenarios)                                 */
     int32_t n_recorders;
-    int32_t reserved0;
+    int32_t flags;       /* B200LP_PROG_*                                                              */
     const double *ts_days;      /* [T] Timestep.days (pywr/_core.pyx:276-301)                          */
     const int32_t *op_kind;     /* [n_ops]                                                             */
     const int32_t *op_dst;      /* [n_ops] slot written                                                */
@@ -334,6 +340,11 @@ int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario
 int b200lp_update_table(b200lp_handle *h, int32_t table, const double *data);
 /* Copy recorder `rec` to the host: [T][S] doubles for the array kinds, [S] for the others. */
 int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out);
+/* Temporal aggregates of array recorder `rec`, accumulated on the device in timestep order while the run writes the
+ * array: sum, min and max over the timesteps executed since the last reset, [S] doubles each (any pointer may be NULL).
+ * The caller derives Recorder.values() for the recorder's temporal agg_func: "sum", "min", "max", "mean" = sum / T
+ * (Aggregator.aggregate_2d(axis=0), pywr/recorders/_recorders.pyx:109-184,630-633) without moving the [T][S] array. */
+int b200lp_fetch_recorder_agg(b200lp_handle *h, int32_t rec, double *sum, double *min, double *max);
 /* Device pointer of recorder `rec` (for NCCL gathers by the caller) and its element count. */
 void *b200lp_recorder_device_ptr(b200lp_handle *h, int32_t rec, int64_t *count);
 /* Column values x [n][S] of the last executed timestep (host mirrors of node flows) and the current

@@ -116,6 +116,7 @@ class OracleEngine:
     # -- program mode (device-resident run semantics) ------------------------------------------
     def load_program(self, prog):
         self._cp = prog.to_c()
+        self._prog = prog
         rc = self.L.orc_load_program(self.h, ctypes.addressof(self._cp))
         if rc != 0:
             raise RuntimeError(f"orc_load_program failed ({rc})")
@@ -147,6 +148,11 @@ class OracleEngine:
         if self.L.orc_fetch_recorder(self.h, int(r), _dp(out)) != 0:
             raise RuntimeError("orc_fetch_recorder failed")
         return out
+
+    def fetch_recorder_agg(self, r):
+        """(sum, min, max) over the timesteps of array recorder ``r`` (the CUDA engine accumulates them on the device)."""
+        a = self.fetch_recorder(r, (self._prog.n_steps, self.S))
+        return a.sum(axis=0), a.min(axis=0), a.max(axis=0)
 
     def fetch_state(self):
         s = self.structure

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,6 +35,25 @@ static int fail(int code, const std::string &msg) {
             return fail(B200LP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
     } while (0)
 
+
+// Opt-in to more than 48 KB of dynamic shared memory, per device and per kernel, raise-only: the attribute is a property of
+// (function, device), engines of different sizes share kernels, and a lower value set for a later engine would break the
+// launches of a larger one that is still alive.
+static cudaError_t ensure_smem(const void *func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> high;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &hw = high[std::make_pair(dev, func)];
+    if (bytes <= hw) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) hw = bytes;
+    return e;
+}
+
 typedef void (*launch_fn)(const DevStructure &, const DevState &, int S, double days, const double *slots,
                           double *node_flow, double *col_flow, double *objective, cudaStream_t stream, int block);
 
@@ -43,11 +64,7 @@ static void launch_variant(const DevStructure &st, const DevState &state, int S,
     const int grid = (S + groups_per_block - 1) / groups_per_block;
     const size_t gbytes = (GroupSmem<G, RPL, NC>::bytes(st.n_val) + 15) & ~(size_t)15;
     const size_t smem = gbytes * groups_per_block;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(lp_step_kernel<G, RPL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    ensure_smem((const void *)lp_step_kernel<G, RPL, NC>, smem);  // a failure surfaces as the launch error
     lp_step_kernel<G, RPL, NC><<<grid, block, smem, stream>>>(st, state, S, days, slots, node_flow, col_flow, objective);
 }
 
@@ -62,12 +79,9 @@ typedef void (*run_fn)(const DevStructure &, const DevState &, const DevProgram 
 template <int RPL, int NC>
 static int pick_run_blocks(int grid) {
     if (RPL != 1) return 3;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     const char *v = getenv("B200LP_RUN_BLOCKS");
     const int forced = v ? atoi(v) : 0;
     if (forced == 3 || forced == 4) return forced;
@@ -85,11 +99,7 @@ static int pick_run_blocks(int grid) {
 template <int G, int RPL, int NC, int MINB>
 static void run_variant_mb(const DevStructure &st, const DevState &state, const DevProgram &pg, int S, int t0, int nsteps,
                            cudaStream_t stream, int block, int grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(lp_run_kernel<G, RPL, NC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    ensure_smem((const void *)lp_run_kernel<G, RPL, NC, MINB>, smem);
     lp_run_kernel<G, RPL, NC, MINB><<<grid, block, smem, stream>>>(st, state, pg, S, t0, nsteps);
 }
 
@@ -151,6 +161,7 @@ struct b200lp_handle {
     std::vector<void *> prog_owned;
     std::vector<double *> rec_ptr;   // device outputs
     std::vector<int> rec_kind;
+    bool agg_only = false;           // B200LP_PROG_AGG_ONLY: array recorders keep aggregates only
     std::vector<double> init_vol, init_pc;
     std::vector<int> roll_len, roll_off;   // rolling virtual storages: ring-buffer rows per storage
     std::vector<double> roll_init;
@@ -188,6 +199,14 @@ static cudaError_t dalloc(b200lp_handle *h, size_t count, T **out) {
     h->owned.push_back(p);
     *out = p;
     return cudaMemset(p, 0, bytes);
+}
+
+// running aggregates [recorder][3][S]: sum = 0, min = +inf, max = -inf
+__global__ void agg_reset_kernel(double *p, size_t n, size_t S) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t which = (i / S) % 3;
+    p[i] = which == 0 ? 0.0 : (which == 1 ? INFINITY : -INFINITY);
 }
 
 __global__ void fill_kernel(double *p, size_t n, double v) {
@@ -447,11 +466,7 @@ int b200lp_set_consts(b200lp_handle *h, const double *consts) {
 static int launch_step(b200lp_handle *h, double days, const double *d_slots, double *d_node_flow, double *d_col_flow,
                        double *d_objective) {
     if (h->use_cta) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(lp_step_kernel_cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            attr_set = true;
-        }
+        ensure_smem((const void *)lp_step_kernel_cta<128>, h->cta_smem);
         lp_step_kernel_cta<128><<<h->S, 128, h->cta_smem, h->stream>>>(h->ds, h->state, h->S, days, d_slots, d_node_flow,
                                                                       d_col_flow, d_objective);
     } else {
@@ -861,7 +876,7 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
         const bool storage_kind = kind == B200LP_REC_STORAGE_VOLUME || kind == B200LP_REC_STORAGE_PC || kind == B200LP_REC_MIN_VOLUME;
         if (storage_kind && (p->rec_src[r] < 0 || p->rec_src[r] >= nstor)) return fail(B200LP_E_INVALID, "recorder storage index out of range");
         rec_src[r] = storage_kind ? p->rec_src[r] : 0;  // the kernel reads V[vol_base + src] unconditionally
-        if (p->rec_row[r] >= h->ds.m) return fail(B200LP_E_INVALID, "recorder row out of range");
+        if (p->rec_row[r] >= h->ds.m || p->rec_row[r] < -1) return fail(B200LP_E_INVALID, "recorder row out of range");
         for (int e = p->rec_indptr[r]; e < p->rec_indptr[r + 1]; e++)
             if (p->rec_col[e] < 0 || p->rec_col[e] >= h->ds.n) return fail(B200LP_E_INVALID, "recorder column out of range");
     }
@@ -873,6 +888,8 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     // scenario indices must address existing columns
     for (int t = 0; t < p->n_tables; t++) {
         const int ax = p->table_axis[t];
+        if (ax >= p->n_axes || ax < B200LP_COL_SCENARIO) return fail(B200LP_E_INVALID, "table axis out of range");
+        if (p->table_rows[t] < 1 || p->table_cols[t] < 1) return fail(B200LP_E_INVALID, "empty table");
         if (ax >= 0)
             for (size_t s = 0; s < S; s++)
                 if (p->scen_index[(size_t)ax * S + s] < 0 || p->scen_index[(size_t)ax * S + s] >= p->table_cols[t])
@@ -918,13 +935,18 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     };
     h->rec_kind.assign(p->rec_kind, p->rec_kind + p->n_recorders);
     h->rec_ptr.resize(p->n_recorders);
+    h->agg_only = (p->flags & B200LP_PROG_AGG_ONLY) != 0;
     for (int r = 0; r < p->n_recorders; r++) {
         const size_t count = rec_is_array(p->rec_kind[r]) ? (size_t)p->n_steps * S : S;
         void *q = nullptr;
+        h->rec_ptr[r] = nullptr;
+        if (rec_is_array(p->rec_kind[r]) && h->agg_only) continue;
         if (palloc(sizeof(double) * count, &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "recorder output allocation failed"); }
         h->rec_ptr[r] = (double *)q;
     }
     void *q = nullptr;
+    if (palloc(sizeof(double) * 3 * S * (p->n_recorders ? p->n_recorders : 1), &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
+    dp.rec_agg = (double *)q;
     if (palloc(sizeof(double *) * (p->n_recorders + 1), &q) != cudaSuccess) { free_program(h); return fail(B200LP_E_CUDA, "alloc"); }
     if (p->n_recorders) cudaMemcpy(q, h->rec_ptr.data(), sizeof(double *) * p->n_recorders, cudaMemcpyHostToDevice);
     dp.rec_out = (double *const *)q;
@@ -977,8 +999,14 @@ int b200lp_program_reset(b200lp_handle *h) {
     const size_t S = (size_t)h->S;
     if (h->ds.n_storage)
         CUDA_TRY(cudaMemcpyAsync(h->dp.pc, h->init_pc.data(), sizeof(double) * S * h->ds.n_storage, cudaMemcpyHostToDevice, h->stream));
+    if (!h->rec_ptr.empty()) {
+        const size_t count = 3 * S * h->rec_ptr.size();
+        agg_reset_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->dp.rec_agg, count, S);
+        h->stats.kernel_launches++;
+    }
     for (size_t r = 0; r < h->rec_ptr.size(); r++) {
         const size_t count = rec_is_array(h->rec_kind[r]) ? (size_t)h->prog_steps * S : S;
+        if (!h->rec_ptr[r]) continue;
         if (h->rec_kind[r] == B200LP_REC_MIN_VOLUME) {
             fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->rec_ptr[r], count, INFINITY);
             h->stats.kernel_launches++;
@@ -1018,9 +1046,25 @@ int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n) {
     return B200LP_OK;
 }
 
+static int run_pipelined_body(b200lp_handle *h, int32_t n_chunks, const double *const *table_src, double *const *rec_dst);
+
 int b200lp_run_pipelined(b200lp_handle *h, int32_t n_chunks, const double *const *table_src, double *const *rec_dst) {
     if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
     CUDA_TRY(cudaSetDevice(h->device));
+    const int rc = run_pipelined_body(h, n_chunks, table_src, rec_dst);
+    if (rc != 0) {
+        // no copy into or out of the caller's buffers may still be in flight when the call returns
+        const std::string msg = g_last_error;
+        if (h->s_in) cudaStreamSynchronize(h->s_in);
+        cudaStreamSynchronize(h->stream);
+        if (h->s_out) cudaStreamSynchronize(h->s_out);
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+static int run_pipelined_body(b200lp_handle *h, int32_t n_chunks, const double *const *table_src, double *const *rec_dst) {
     const int T = h->prog_steps;
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > T) n_chunks = T;
@@ -1067,7 +1111,7 @@ int b200lp_run_pipelined(b200lp_handle *h, int32_t n_chunks, const double *const
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, ev_run, 0));
         if (rec_dst)
             for (int r = 0; r < n_rec; r++) {
-                if (!rec_dst[r]) continue;
+                if (!rec_dst[r] || !h->rec_ptr[r]) continue;
                 if (rec_is_array(h->rec_kind[r])) {
                     const size_t off = (size_t)t0 * S, count = (size_t)(t1 - t0) * S;
                     CUDA_TRY(cudaMemcpyAsync(rec_dst[r] + off, h->rec_ptr[r] + off, sizeof(double) * count, cudaMemcpyDeviceToHost, h->s_out));
@@ -1133,6 +1177,7 @@ int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out) {
     if (!h || !h->has_program || !out) return fail(B200LP_E_INVALID, "no program loaded / null output");
     if (rec < 0 || rec >= (int)h->rec_ptr.size()) return fail(B200LP_E_INVALID, "recorder index out of range");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->rec_ptr[rec]) return fail(B200LP_E_UNSUPPORTED, "the program was loaded with B200LP_PROG_AGG_ONLY: this array recorder keeps aggregates only");
     const size_t count = rec_is_array(h->rec_kind[rec]) ? (size_t)h->prog_steps * h->S : (size_t)h->S;
     CUDA_TRY(cudaMemcpyAsync(out, h->rec_ptr[rec], sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1140,9 +1185,25 @@ int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out) {
     return B200LP_OK;
 }
 
+int b200lp_fetch_recorder_agg(b200lp_handle *h, int32_t rec, double *sum, double *mn, double *mx) {
+    if (!h || !h->has_program) return fail(B200LP_E_INVALID, "no program loaded");
+    if (rec < 0 || rec >= (int)h->rec_ptr.size()) return fail(B200LP_E_INVALID, "recorder index out of range");
+    if (!rec_is_array(h->rec_kind[rec])) return fail(B200LP_E_INVALID, "not an array recorder: use b200lp_fetch_recorder");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S;
+    double *dst[3] = {sum, mn, mx};
+    for (int k = 0; k < 3; k++)
+        if (dst[k]) {
+            CUDA_TRY(cudaMemcpyAsync(dst[k], h->dp.rec_agg + ((size_t)rec * 3 + k) * S, sizeof(double) * S, cudaMemcpyDeviceToHost, h->stream));
+            h->stats.d2h_bytes += (double)S * 8.0;
+        }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return B200LP_OK;
+}
+
 void *b200lp_recorder_device_ptr(b200lp_handle *h, int32_t rec, int64_t *count) {
     if (!h || !h->has_program || rec < 0 || rec >= (int)h->rec_ptr.size()) return nullptr;
-    if (count) *count = rec_is_array(h->rec_kind[rec]) ? (int64_t)h->prog_steps * h->S : (int64_t)h->S;
+    if (count) *count = !h->rec_ptr[rec] ? 0 : (rec_is_array(h->rec_kind[rec]) ? (int64_t)h->prog_steps * h->S : (int64_t)h->S);
     return h->rec_ptr[rec];
 }
 

@@ -29,11 +29,20 @@
 // whose indices are resolved on the host (b200lp_create), so the per-timestep path has no
 // "slot or constant?" branches and no global-memory indirections.
 #pragma once
+#ifndef __CUDACC_RTC__   // under NVRTC (jit_run.inc) the texts of b200lp.h and of this file are concatenated
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 
 #include "../../include/b200lp.h"
+#else
+#ifndef INFINITY
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#ifndef NAN
+#define NAN __longlong_as_double(0x7ff8000000000000LL)
+#endif
+#endif
 
 #ifndef B200LP_RUN_MIN_BLOCKS
 #define B200LP_RUN_MIN_BLOCKS 3
@@ -724,20 +733,11 @@ __device__ __forceinline__ int assemble_rows(const DevStructure &st, Dict<G, RPL
     return flags;
 }
 
-// (a7) warm-started solve with the oracle's retry ladder (role of retry_solve, cython_glpk.pyx:1034-1042).
-// `lane_flags` are the per-lane input flags of assemble_rows.
+// (a7) the general solve with the oracle's retry ladder (role of retry_solve, cython_glpk.pyx:1034-1042): re-factorise when
+// asked, run the simplex from the scenario's basis, on failure re-factorise the same basis, then restart from the slack basis.
 template <int G, int RPL, int NC>
-__device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC> &D, int &valid, int &npiv,
-                                        int &refactors, const int lane_flags) {
-    bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
-    if (!need_refactor && !st.cost_dynamic) {
-        const int f = D.fast_step(lane_flags);  // 93 % of the benchmark's timesteps end here
-        if (f >= 0) return f;
-    } else {
-        const unsigned all = group_or<G>((unsigned)lane_flags, D.gmask());
-        if (all & 1u) return B200LP_ST_NAN;
-        if (all & 2u) return B200LP_ST_INFEASIBLE;
-    }
+__device__ __forceinline__ int solve_lp_slow(const DevStructure &st, Dict<G, RPL, NC> &D, int &valid, int &npiv,
+                                             int &refactors, bool need_refactor) {
     const bool fresh0 = need_refactor;
     int status = B200LP_ST_OPTIMAL;
 #pragma unroll 1
@@ -762,6 +762,23 @@ __device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC>
     }
     if (status != B200LP_ST_OPTIMAL) valid = 0;
     return status;
+}
+
+// (a7) warm-started solve: the steady-state test first, the general solve when it does not settle the timestep.
+// `lane_flags` are the per-lane input flags of assemble_rows.
+template <int G, int RPL, int NC>
+__device__ __forceinline__ int solve_lp(const DevStructure &st, Dict<G, RPL, NC> &D, int &valid, int &npiv,
+                                        int &refactors, const int lane_flags) {
+    const bool need_refactor = !valid || st.n_dyn_a > 0 || npiv >= REFACTOR_PIVOTS;
+    if (!need_refactor && !st.cost_dynamic) {
+        const int f = D.fast_step(lane_flags);  // 93 % of the benchmark's timesteps end here
+        if (f >= 0) return f;
+    } else {
+        const unsigned all = group_or<G>((unsigned)lane_flags, D.gmask());
+        if (all & 1u) return B200LP_ST_NAN;
+        if (all & 2u) return B200LP_ST_INFEASIBLE;
+    }
+    return solve_lp_slow(st, D, valid, npiv, refactors, need_refactor);
 }
 
 // (a8) primal values of the columns into sm.f->x and the activities of the rows into sm.f->ract
@@ -923,7 +940,18 @@ struct DevProgram {
     double *roll_mem;        // [sum roll_len][S]
     double *last_x;          // [n][S]
     int *fail_step;          // [S]
+    // temporal aggregates of the array recorders, accumulated in timestep order while the arrays are written:
+    // [n_recorders][3][S] = sum, min, max over the timesteps run so far (Recorder.values() =
+    // Aggregator.aggregate_2d(_data, axis=0), pywr/recorders/_recorders.pyx:109-184,630-633, without shipping _data)
+    double *rec_agg;
 };
+
+// one sample of an array recorder into its running aggregates (NaN propagates like numpy's sum / min / max)
+__device__ __forceinline__ void agg_sample(double &sum, double &mn, double &mx, const double o) {
+    sum += o;
+    mn = (o < mn || o != o) ? o : mn;
+    mx = (o > mx || o != o) ? o : mx;
+}
 
 __device__ __forceinline__ double clamp_pc(double pc) {  // Storage.get_current_pc, pywr/_core.pyx:1027-1039
     if (pc > 1.0 || isnan(pc)) return 1.0;
@@ -1108,17 +1136,21 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
     // Per-scenario accumulators stay in a register for the whole launch.  Lanes without a recorder run the
     // same instruction stream on harmless operands (their accumulator is never stored).
     int rk = B200LP_REC_MEAN_FLOW, rrow = 0, ridx = st.k_base + K_ZERO, rsrc = 0, rbeg = 0, rend = 0;
-    double rfac = 0.0, racc = 0.0;
+    double rfac = 0.0, racc = 0.0, asum = 0.0, amin = INFINITY, amax = -INFINITY;
+    double *ragg = nullptr;   // array kinds: home of the temporal aggregates (sum, min, max)
     double *rout = nullptr;   // array kinds: next element to write; others: the accumulator's home
-    bool r_array = false, r_on = false;
+    bool r_array = false, r_on = false, r_store = false;
     if (gl < pg.n_recorders) {
         r_on = true;
         rk = __ldg(&pg.rec_kind[gl]); rrow = __ldg(&pg.rec_row[gl]); ridx = __ldg(&pg.rec_idx[gl]);
         rsrc = __ldg(&pg.rec_src[gl]); rbeg = __ldg(&pg.rec_indptr[gl]); rend = __ldg(&pg.rec_indptr[gl + 1]);
         rfac = __ldg(&pg.rec_factor[gl]);
         r_array = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
-        rout = pg.rec_out[gl] + (r_array ? (size_t)t0 * S + sidx : (size_t)sidx);
+        rout = pg.rec_out[gl];   // nullptr for an array recorder of a B200LP_PROG_AGG_ONLY program
+        r_store = r_array && rout != nullptr;
+        if (rout) rout += (r_array ? (size_t)t0 * S + sidx : (size_t)sidx);
         if (!r_array) racc = *rout;
+        else { ragg = pg.rec_agg + (size_t)gl * 3 * S + sidx; asum = ragg[0]; amin = ragg[S]; amax = ragg[2 * (size_t)S]; }
         const bool r_storage = rk == B200LP_REC_STORAGE_VOLUME || rk == B200LP_REC_STORAGE_PC || rk == B200LP_REC_MIN_VOLUME;
         if (r_storage) { rrow = 0; rbeg = rend = 0; } else { rsrc = 0; }
     }
@@ -1280,7 +1312,8 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             add = rk == B200LP_REC_TOTAL_DEFICIT ? df * days : add;
             add = rk == B200LP_REC_DEFICIT_FREQ ? (fabs(value - mf) > 1e-6 ? 1.0 : 0.0) : add;
             racc = rk == B200LP_REC_MIN_VOLUME ? fmin(racc, vv) : racc + add;
-            if (r_array) {
+            agg_sample(asum, amin, amax, o);
+            if (r_store) {
 #ifndef B200LP_EXP_NO_STORE
                 *rout = o;
 #endif
@@ -1298,13 +1331,22 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
                 else
                     for (int e = beg; e < end; e++) value = fma(__ldg(&pg.rec_w[e]), D.sm.f->x[__ldg(&pg.rec_col[e])], value);
                 const size_t ts_at = (size_t)t * S + sidx;
+                double o = 0.0;
                 switch (kind) {
-                case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
-                case B200LP_REC_NODE_DEFICIT: out[ts_at] = V[idx] - value; break;
-                case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
-                case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
-                case B200LP_REC_STORAGE_VOLUME: out[ts_at] = V[st.vol_base + src]; break;
-                case B200LP_REC_STORAGE_PC: out[ts_at] = V[st.pc_base + src]; break;
+                case B200LP_REC_NODE_FLOW: o = value * f; break;
+                case B200LP_REC_NODE_DEFICIT: o = V[idx] - value; break;
+                case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; o = mf == 0.0 ? 1.0 : value / mf; } break;
+                case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; o = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+                case B200LP_REC_STORAGE_VOLUME: o = V[st.vol_base + src]; break;
+                case B200LP_REC_STORAGE_PC: o = V[st.pc_base + src]; break;
+                default: break;
+                }
+                if (kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC) {
+                    if (out) out[ts_at] = o;
+                    double *ag = pg.rec_agg + (size_t)r * 3 * S + sidx;
+                    agg_sample(ag[0], ag[S], ag[2 * (size_t)S], o);
+                }
+                switch (kind) {
                 case B200LP_REC_TOTAL_DEFICIT: out[sidx] += (V[idx] - value) * days; break;
                 case B200LP_REC_TOTAL_FLOW: out[sidx] += value * f * days; break;
                 case B200LP_REC_MEAN_FLOW: out[sidx] += value * f; break;
@@ -1319,6 +1361,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
     }
     PHASE_FLUSH;
     if (r_on && !r_array) *rout = racc;
+    if (r_on && r_array) { ragg[0] = asum; ragg[S] = amin; ragg[2 * (size_t)S] = amax; }
     // ---- persist ------------------------------------------------------------------------------------
     store_state(state, D, sidx, true);
     for (int k = gl; k < nst; k += G) {
@@ -1338,6 +1381,109 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Support for the structure-specialised run kernel (one kernel per model, generated by jit_run.inc at
+// b200lp_load_program and compiled with NVRTC).  The generated code holds what depends on the model as
+// straight-line code with immediates: table look-ups, parameter ops, the bounds of the rows that change with
+// time, Storage.after and the recorders, all in registers.  What depends on the current BASIS lives here:
+// the lane that owns basic position i / non-basic position j / LP row k keeps, in registers, where its
+// operands come from, and every per-timestep exchange is a warp shuffle - no shared memory and no barrier
+// on the steady-state path.  When the steady-state test fails the lane state is written to the shared-memory
+// layout of Dict and the general solve (the same code the generic kernels run) takes over.
+// One lane per row (RPL == 1) and NC <= G, so lane gl also owns non-basic position gl.
+// ------------------------------------------------------------------------------------------------
+template <int G, int NC>
+struct JitLane {
+    static_assert(NC <= G, "one non-basic position per lane");
+    typedef Dict<G, 1, NC> DictT;
+    static constexpr int NCP = DictT::NCP;  // == G
+    // set by derive(): valid until the basis changes
+    int hsrc;    // lane whose row bounds are the bounds of this lane's basic variable (own lane for a column)
+    bool hcol;   // the basic variable is a column: bounds [0, +inf)
+    int nsrc;    // the same for the variable in this lane's non-basic position
+    bool ncol;
+    int nbv;     // variable in the non-basic position (-1: padding)
+    int nstat;   // its status (carried from timestep to timestep: boxed variables keep their side on ties)
+    double dj;   // its reduced cost
+    int rloc;    // where the row variable n + gl is: basic position p (p < G) or non-basic position G + j
+    // per timestep
+    double xn;   // value of the non-basic position
+
+    // positions of every variable from the dictionary's head / nb (shared-memory scratch: Dict's vstat)
+    __device__ __forceinline__ void derive(DictT &D) {
+        const int n = D.n, gl = D.gl;
+        const int h = D.head[0];
+        hcol = h >= 0 && h < n;
+        hsrc = h >= n ? h - n : gl;
+        nbv = D.sm.f->nb[gl];
+        nstat = D.sm.f->nbstat[gl];
+        dj = D.sm.f->d[gl];
+        ncol = nbv >= 0 && nbv < n;
+        nsrc = nbv >= n ? nbv - n : gl;
+        int *pos = D.sm.f->vstat;
+        D.sync();
+        if (h >= 0) pos[h < n ? h : NCP + (h - n)] = gl;
+        if (nbv >= 0) pos[nbv < n ? nbv : NCP + (nbv - n)] = G + gl;
+        D.sync();
+        rloc = gl < D.m ? pos[NCP + gl] : gl;
+    }
+    // uniform over the group: where row i / column c is (valid right after derive())
+    __device__ __forceinline__ int row_loc(const DictT &D, const int i) const { return D.sm.f->vstat[NCP + i]; }
+    __device__ __forceinline__ int col_loc(const DictT &D, const int c) const { return D.sm.f->vstat[c]; }
+
+    // value of the variable at location `loc` (any lane may ask for any location)
+    __device__ __forceinline__ double value_at(const DictT &D, const int loc) const {
+        const unsigned gm = D.gmask();
+        const double b = __shfl_sync(gm, D.beta[0], loc & (G - 1), G);
+        const double x = __shfl_sync(gm, xn, loc & (G - 1), G);
+        return loc < G ? b : x;
+    }
+
+    // Steady-state timestep (Dict::fast_step without shared memory).  mylo / myhi: bounds of LP row gl (free for
+    // lanes beyond the last row).  Leaves beta in D.beta[0], the non-basic value in xn.  Returns true when the
+    // general solve has to run (a basic variable out of bounds or a dual infeasible non-basic position).
+    template <int NREAL>
+    __device__ __forceinline__ bool fast_check(DictT &D, const double mylo, const double myhi) {
+        const unsigned gm = D.gmask();
+        const double tl = __shfl_sync(gm, mylo, hsrc, G), th = __shfl_sync(gm, myhi, hsrc, G);
+        const double nl = __shfl_sync(gm, mylo, nsrc, G), nh = __shfl_sync(gm, myhi, nsrc, G);
+        const double lob = hcol ? 0.0 : tl, hib = hcol ? INFINITY : th;
+        // Dict::place_nonbasics_lane for position gl
+        const double lo = ncol ? 0.0 : nl, hi = ncol ? INFINITY : nh;
+        const bool lo_fin = lo > -INFINITY, hi_fin = hi < INFINITY, fx = lo == hi;
+        const bool dpos = dj > TOL_DUAL, dneg = dj < -TOL_DUAL;
+        const int s0 = nstat;
+        const int s_box = dpos ? VS_NL : (dneg ? VS_NU : ((s0 == VS_NL || s0 == VS_NU) ? s0 : VS_NL));
+        int s = lo_fin ? (hi_fin ? s_box : VS_NL) : (hi_fin ? VS_NU : VS_NF);
+        s = fx ? VS_NS : s;
+        const bool bad = lo_fin ? (!hi_fin && dneg) : (hi_fin ? dpos : (dpos || dneg));
+        double xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
+        if (nbv < 0) { s = VS_NS; xv = 0.0; }
+        const bool infe = !fx && bad && nbv >= 0;
+        nstat = s;
+        xn = xv;
+        // beta = T xn, j ascending (Dict::basic_values; the padding columns contribute fma(0, 0, acc) = acc)
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NREAL; j++) acc = fma(D.T[0][j], __shfl_sync(gm, xv, j, G), acc);
+        D.beta[0] = acc;
+        const bool viol = (acc < lob - TOL_PRIMAL * (1.0 + fabs(lob))) || (acc > hib + TOL_PRIMAL * (1.0 + fabs(hib)));
+        return group_ballot<G>(viol || infe, gm) != 0u;
+    }
+
+    // lane state -> the shared-memory layout the general solve works on
+    __device__ __forceinline__ void materialize(DictT &D, const double mylo, const double myhi) {
+        if (D.gl < D.m) { D.sm.f->LO[1 + D.n + D.gl] = mylo; D.sm.f->HI[1 + D.n + D.gl] = myhi; }
+        D.sm.f->nbstat[D.gl] = nstat;
+        D.sync();
+    }
+    // ... and back after it returned B200LP_ST_OPTIMAL (D.beta is current, see extract_solution)
+    __device__ __forceinline__ void reload(DictT &D) {
+        derive(D);
+        xn = D.sm.f->xn[D.gl];
+    }
+};
 
 // reset: slack basis for every scenario (is_first_solve, cython_glpk.pyx:757-759)
 __global__ void lp_reset_kernel(const DevState state, const int S, const int m, const int n, const int rows_cap,

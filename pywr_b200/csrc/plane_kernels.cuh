@@ -119,13 +119,22 @@ __global__ void plane_after_kernel(const PlaneProg Q, const DevProgram pg, const
                     value = fma(__ldg(&pg.rec_w[e]), x[(size_t)__ldg(&pg.rec_col[e]) * ld], value);
         }
         const size_t ts_at = (size_t)t * S + s;
+        if (kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC) {
+            double o = 0.0;
+            switch (kind) {
+            case B200LP_REC_NODE_FLOW: o = value * f; break;
+            case B200LP_REC_NODE_DEFICIT: o = V[idx] - value; break;
+            case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; o = mf == 0.0 ? 1.0 : value / mf; } break;
+            case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; o = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
+            case B200LP_REC_STORAGE_VOLUME: o = V[Q.vol_base + src]; break;
+            default: o = V[Q.pc_base + src]; break;
+            }
+            if (out) out[ts_at] = o;
+            double *ag = pg.rec_agg + (size_t)r * 3 * S + s;   // running sum / min / max over the timesteps (values())
+            agg_sample(ag[0], ag[S], ag[2 * S], o);
+            continue;
+        }
         switch (kind) {
-        case B200LP_REC_NODE_FLOW: out[ts_at] = value * f; break;
-        case B200LP_REC_NODE_DEFICIT: out[ts_at] = V[idx] - value; break;
-        case B200LP_REC_NODE_SUPPLIED: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 1.0 : value / mf; } break;
-        case B200LP_REC_NODE_CURTAIL: { const double mf = V[idx]; out[ts_at] = mf == 0.0 ? 0.0 : 1.0 - value / mf; } break;
-        case B200LP_REC_STORAGE_VOLUME: out[ts_at] = V[Q.vol_base + src]; break;
-        case B200LP_REC_STORAGE_PC: out[ts_at] = V[Q.pc_base + src]; break;
         case B200LP_REC_TOTAL_DEFICIT: out[s] += (V[idx] - value) * days; break;
         case B200LP_REC_TOTAL_FLOW: out[s] += value * f * days; break;
         case B200LP_REC_MEAN_FLOW: out[s] += value * f; break;

@@ -67,6 +67,7 @@ SYMBOLS = [
     ("b200lp_mark", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     ("b200lp_elapsed_ms", ctypes.c_int, [ctypes.c_void_p, _dp]),
     ("b200lp_fetch_recorder", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp]),
+    ("b200lp_fetch_recorder_agg", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp, _dp, _dp]),
     ("b200lp_recorder_device_ptr", ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
     ("b200lp_fetch_state", ctypes.c_int, [ctypes.c_void_p, _dp, _dp, _dp]),
 ]
@@ -86,7 +87,7 @@ def load_library(path: str = LIB_PATH):
         fn = getattr(L, name)  # AttributeError if the library does not export it
         fn.restype = restype
         fn.argtypes = argtypes
-    if L.b200lp_abi_version() != 7:
+    if L.b200lp_abi_version() != 8:
         raise EngineUnavailable("libb200lp.so ABI version mismatch: rebuild")
     _lib = L
     return L
@@ -244,6 +245,13 @@ class CudaEngine:
             out = np.zeros(shape, dtype=np.float64)
         _check(self.L, self.L.b200lp_fetch_recorder(self.h, int(r), _ptr(out)), "b200lp_fetch_recorder")
         return out
+
+    def fetch_recorder_agg(self, r):
+        """(sum, min, max) over the executed timesteps of array recorder ``r``, [S] each, accumulated on the device."""
+        out = np.zeros((3, self.S), dtype=np.float64)
+        _check(self.L, self.L.b200lp_fetch_recorder_agg(self.h, int(r), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])),
+               "b200lp_fetch_recorder_agg")
+        return out[0], out[1], out[2]
 
     def update_table(self, table, data):
         """Asynchronous upload of one table (use a pinned array from alloc_pinned for full PCIe rate)."""

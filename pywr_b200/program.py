@@ -29,6 +29,7 @@ from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
 OP_STORAGE_RESET = 10
+PROG_AGG_ONLY = 1
 # virtual storages whose reset / activation follows the calendar only (pywr/nodes.py:596-757)
 SCHEDULED_STORAGES = ("AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage")
 AGG = {"sum": 0, "product": 1, "min": 2, "max": 3, "mean": 4}
@@ -48,7 +49,7 @@ class b200lp_program(ctypes.Structure):
     _f64p = ctypes.POINTER(ctypes.c_double)
     _fields_ = [
         ("n_steps", ctypes.c_int32), ("n_ops", ctypes.c_int32), ("n_tables", ctypes.c_int32),
-        ("n_axes", ctypes.c_int32), ("n_recorders", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("n_axes", ctypes.c_int32), ("n_recorders", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("ts_days", _f64p),
         ("op_kind", _i32p), ("op_dst", _i32p), ("op_arg_ptr", _i32p), ("op_args", _i32p),
         ("table_rows", _i32p), ("table_cols", _i32p), ("table_axis", _i32p), ("table_offset", _i64p),
@@ -103,6 +104,7 @@ class Program:
     months: Optional[np.ndarray] = None        # [T] calendar month of every timestep (population batches)
     st_roll_len: Optional[np.ndarray] = None   # [n_storage] RollingVirtualStorage: timesteps - 1 (0: not rolling)
     st_roll_init: Optional[np.ndarray] = None  # [n_storage] its _initial_utilisation
+    flags: int = 0                             # B200LP_PROG_*: 1 = array recorders keep their temporal aggregates only
 
     @property
     def n_ops(self):
@@ -123,6 +125,7 @@ class Program:
         cp = b200lp_program()
         cp.n_steps, cp.n_ops, cp.n_tables = self.n_steps, self.n_ops, self.n_tables
         cp.n_axes, cp.n_recorders = self.n_axes, self.n_recorders
+        cp.flags = int(self.flags)
         keep = []
         for names, dt, ct in ((_P_I32, np.int32, ctypes.c_int32), (_P_I64, np.int64, ctypes.c_int64),
                               (_P_F64, np.float64, ctypes.c_double)):

@@ -19,7 +19,7 @@ from typing import Any, List, Optional
 
 import numpy as np
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 ROW_FLOW = 0
 ROW_STORAGE = 1
 ST_KIND_STORAGE = 0

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.b200lp_abi_version() == 7
+    assert lib.b200lp_abi_version() == 8
 
 
 def test_structure_struct_layout_matches_header():
