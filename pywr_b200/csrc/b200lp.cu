@@ -136,6 +136,56 @@ static const Variant kVariants[] = {
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
+// Host copy of the LP structure with every ref resolved to an index into the per-scenario value vector
+//     V = [ slots | constants | storage volumes | storage pc | K_* built-ins ]
+// (what DevStructure holds as device arrays).  Pure host code: b200lp_create uploads it, b200lp_load_program pre-decodes
+// the ops against it and jit_run.inc generates the structure-specialised run kernel from it.
+struct HostStructure {
+    int m = 0, n = 0, n_slots = 0, n_consts = 0, n_storage = 0, n_dyn_a = 0, cost_dynamic = 0, rows_cap = 0;
+    int vol_base = 0, pc_base = 0, n_val = 0, k_base = 0;
+    std::vector<int> row_class, row_a, row_b, st_kind, st_row, st_vol, st_minv, st_maxv, st_act;
+};
+
+static bool resolve_structure(const b200lp_structure *s, int rows_cap, HostStructure &hs, std::string &err) {
+    const int m = s->n_rows, n = s->n_cols;
+    hs.m = m; hs.n = n; hs.n_slots = s->n_slots; hs.n_consts = s->n_consts; hs.n_storage = s->n_storage;
+    hs.n_dyn_a = s->n_dyn_a; hs.rows_cap = rows_cap;
+    hs.cost_dynamic = 0;
+    for (int k = 0; k < s->cost_indptr[n]; k++)
+        if (s->cost_ref[k] >= 0) hs.cost_dynamic = 1;
+    hs.vol_base = s->n_slots + s->n_consts;
+    hs.pc_base = hs.vol_base + s->n_storage;
+    hs.n_val = hs.pc_base + s->n_storage;
+    hs.k_base = hs.n_val;
+    const int n_slots = s->n_slots, n_consts = s->n_consts;
+    auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
+    auto vidx = [&](int ref) { return ref >= 0 ? ref : n_slots + (-ref - 1); };
+    hs.row_class.assign(rows_cap, ROWC_PAD); hs.row_a.assign(rows_cap, 0); hs.row_b.assign(rows_cap, 0);
+    hs.st_row.assign(s->n_storage ? s->n_storage : 1, 0);
+    for (int i = 0; i < m; i++) {
+        if (s->row_kind[i] == B200LP_ROW_FLOW) {
+            if (!ref_ok(s->row_lb_ref[i]) || !ref_ok(s->row_ub_ref[i])) { err = "row ref out of range"; return false; }
+            hs.row_class[i] = (s->row_lb_ref[i] < 0 && s->row_ub_ref[i] < 0) ? ROWC_STATIC : ROWC_FLOW;
+            hs.row_a[i] = vidx(s->row_lb_ref[i]); hs.row_b[i] = vidx(s->row_ub_ref[i]);
+        } else {
+            if (s->row_lb_ref[i] < 0 || s->row_lb_ref[i] >= s->n_storage) { err = "storage index out of range"; return false; }
+            hs.row_class[i] = ROWC_STORAGE; hs.row_a[i] = s->row_lb_ref[i];
+            hs.st_row[s->row_lb_ref[i]] = i;
+        }
+        for (int k = s->a_indptr[i]; k < s->a_indptr[i + 1]; k++)
+            if (s->a_col[k] < 0 || s->a_col[k] >= n) { err = "column index out of range"; return false; }
+    }
+    hs.st_kind.assign(s->st_kind, s->st_kind + s->n_storage);
+    hs.st_vol.resize(s->n_storage); hs.st_minv.resize(s->n_storage); hs.st_maxv.resize(s->n_storage); hs.st_act.resize(s->n_storage);
+    for (int k = 0; k < s->n_storage; k++) {
+        if (s->st_vol_ref[k] != B200LP_REF_STATE && !ref_ok(s->st_vol_ref[k])) { err = "storage volume ref out of range"; return false; }
+        if (!ref_ok(s->st_minv_ref[k]) || !ref_ok(s->st_maxv_ref[k]) || !ref_ok(s->st_active_ref[k])) { err = "storage ref out of range"; return false; }
+        hs.st_vol[k] = s->st_vol_ref[k] == B200LP_REF_STATE ? hs.vol_base + k : vidx(s->st_vol_ref[k]);
+        hs.st_minv[k] = vidx(s->st_minv_ref[k]); hs.st_maxv[k] = vidx(s->st_maxv_ref[k]); hs.st_act[k] = vidx(s->st_active_ref[k]);
+    }
+    return true;
+}
+
 struct b200lp_handle {
     int device = 0;
     int S = 0;
@@ -171,6 +221,7 @@ struct b200lp_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of b200lp_run_pipelined
     std::vector<cudaEvent_t> pipe_events;
     std::vector<int> h_st_maxv_idx;  // V index of every storage's max_volume (host copy, for op pre-decoding)
+    HostStructure hs;                // resolved LP structure (register / CTA engines)
     struct PdhgEngine *pdhg = nullptr;  // large-LP path (pdhg_engine.cuh, rsx_kernels.cuh): LPs beyond the dictionary kernels
     struct PlaneHost *plane = nullptr;  // device-resident program on the large-LP path (plane_program.inc)
     std::vector<double> ts_days_host;
@@ -285,36 +336,17 @@ int b200lp_create_ex(const b200lp_structure *s, int32_t n_scenarios, int32_t dev
     for (int k = 0; k < s->cost_indptr[n]; k++)
         if (s->cost_ref[k] >= 0) ds.cost_dynamic = 1;
 
-    ds.vol_base = s->n_slots + s->n_consts;
-    ds.pc_base = ds.vol_base + s->n_storage;
-    ds.n_val = ds.pc_base + s->n_storage;
-    ds.k_base = ds.n_val;
+    HostStructure &hs = h->hs;
+    {
+        std::string err;
+        if (!resolve_structure(s, rows_cap, hs, err)) { delete h; return fail(B200LP_E_INVALID, err); }
+    }
+    ds.vol_base = hs.vol_base; ds.pc_base = hs.pc_base; ds.n_val = hs.n_val; ds.k_base = hs.k_base;
     const int n_slots = s->n_slots, n_consts = s->n_consts;
-    // validate refs and resolve them to indices into the per-scenario value vector V
     auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
     auto vidx = [&](int ref) { return ref >= 0 ? ref : n_slots + (-ref - 1); };
-    std::vector<int> row_class(rows_cap, ROWC_PAD), row_a(rows_cap, 0), row_b(rows_cap, 0);
-    std::vector<int> st_row(s->n_storage ? s->n_storage : 1, 0);
-    for (int i = 0; i < m; i++) {
-        if (s->row_kind[i] == B200LP_ROW_FLOW) {
-            if (!ref_ok(s->row_lb_ref[i]) || !ref_ok(s->row_ub_ref[i])) { delete h; return fail(B200LP_E_INVALID, "row ref out of range"); }
-            row_class[i] = (s->row_lb_ref[i] < 0 && s->row_ub_ref[i] < 0) ? ROWC_STATIC : ROWC_FLOW;
-            row_a[i] = vidx(s->row_lb_ref[i]); row_b[i] = vidx(s->row_ub_ref[i]);
-        } else {
-            if (s->row_lb_ref[i] < 0 || s->row_lb_ref[i] >= s->n_storage) { delete h; return fail(B200LP_E_INVALID, "storage index out of range"); }
-            row_class[i] = ROWC_STORAGE; row_a[i] = s->row_lb_ref[i];
-            st_row[s->row_lb_ref[i]] = i;
-        }
-        for (int k = s->a_indptr[i]; k < s->a_indptr[i + 1]; k++)
-            if (s->a_col[k] < 0 || s->a_col[k] >= n) { delete h; return fail(B200LP_E_INVALID, "column index out of range"); }
-    }
-    std::vector<int> st_vol(s->n_storage), st_minv(s->n_storage), st_maxv(s->n_storage), st_act(s->n_storage);
-    for (int k = 0; k < s->n_storage; k++) {
-        if (s->st_vol_ref[k] != B200LP_REF_STATE && !ref_ok(s->st_vol_ref[k])) { delete h; return fail(B200LP_E_INVALID, "storage volume ref out of range"); }
-        if (!ref_ok(s->st_minv_ref[k]) || !ref_ok(s->st_maxv_ref[k]) || !ref_ok(s->st_active_ref[k])) { delete h; return fail(B200LP_E_INVALID, "storage ref out of range"); }
-        st_vol[k] = s->st_vol_ref[k] == B200LP_REF_STATE ? ds.vol_base + k : vidx(s->st_vol_ref[k]);
-        st_minv[k] = vidx(s->st_minv_ref[k]); st_maxv[k] = vidx(s->st_maxv_ref[k]); st_act[k] = vidx(s->st_active_ref[k]);
-    }
+    const std::vector<int> &row_class = hs.row_class, &row_a = hs.row_a, &row_b = hs.row_b, &st_row = hs.st_row;
+    const std::vector<int> &st_vol = hs.st_vol, &st_minv = hs.st_minv, &st_maxv = hs.st_maxv, &st_act = hs.st_act;
     h->h_st_maxv_idx = st_maxv;
     const int ncost = s->cost_indptr[n];
     std::vector<int> cost_idx(ncost), dyn_idx(s->n_dyn_a);
@@ -687,44 +719,34 @@ static cudaError_t pupload(b200lp_handle *h, const T *src, size_t count, const T
     return e;
 }
 
-static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC; }
+// Ops of a program with every operand resolved to an index into V (pure host code, shared by b200lp_load_program and the
+// specialised-kernel generator): table ops get one descriptor each, everything else is pre-decoded into `code` as
+// kind, dst, nargs, args...
+struct DecodedProgram {
+    std::vector<int> tab_dst, tab_table, tab_offset, code, rec_idx, rec_src;
+};
 
-extern "C" {
-
-int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
-    if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
-    if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
-    if (h->use_cta && !h->pdhg)
-        return fail(B200LP_E_UNSUPPORTED, "the device-resident run needs a register-resident kernel variant; "
-                                          "this LP uses the CTA-per-scenario kernel (per-timestep path only)");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    free_program(h);
-    const size_t S = (size_t)h->S;
-    const int nst = h->ds.n_storage;
-    DevProgram &dp = h->dp;
-    dp = DevProgram{};
-    dp.n_steps = p->n_steps; dp.n_tables = p->n_tables; dp.n_axes = p->n_axes;
-    dp.n_recorders = p->n_recorders;
+static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, int nstor, int vol_base, int pc_base, int m, int n,
+                           int S, const std::vector<int> &st_maxv_idx, DecodedProgram &dec, std::string &err) {
+    auto bad = [&](const char *msg) { err = msg; return false; };
     // validate ops; table ops get one descriptor each, everything else is pre-decoded into `code`
     // with every operand resolved to an index into V
     const int nargs = p->n_ops ? p->op_arg_ptr[p->n_ops] : 0;
-    const int n_slots = h->ds.n_slots, n_consts = h->ds.n_consts, nstor = h->ds.n_storage;
     auto ref_ok = [&](int ref) { return ref >= 0 ? ref < n_slots : (ref != B200LP_REF_STATE && (-ref - 1) < n_consts); };
     auto vidx = [&](int ref) { return ref >= 0 ? ref : n_slots + (-ref - 1); };
-    std::vector<int> tab_dst, tab_table, tab_offset, code;
+    std::vector<int> &tab_dst = dec.tab_dst, &tab_table = dec.tab_table, &tab_offset = dec.tab_offset, &code = dec.code;
     for (int k = 0; k < p->n_ops; k++) {
-        if (p->op_dst[k] < 0 || p->op_dst[k] >= n_slots) return fail(B200LP_E_INVALID, "op destination slot out of range");
+        if (p->op_dst[k] < 0 || p->op_dst[k] >= n_slots) return bad("op destination slot out of range");
         const int *a = p->op_args + p->op_arg_ptr[k];
         const int na = p->op_arg_ptr[k + 1] - p->op_arg_ptr[k];
         const int kind = p->op_kind[k];
         if (kind == B200LP_OP_TABLE) {
-            if (na < 2) return fail(B200LP_E_INVALID, "table op needs 2 arguments");
+            if (na < 2) return bad("table op needs 2 arguments");
             const int tb = a[0];
-            if (tb < 0 || tb >= p->n_tables) return fail(B200LP_E_INVALID, "table index out of range");
+            if (tb < 0 || tb >= p->n_tables) return bad("table index out of range");
             const int ax = p->table_axis[tb];
-            if (ax >= p->n_axes) return fail(B200LP_E_INVALID, "table axis out of range");
-            if (ax == B200LP_COL_SCENARIO && p->table_cols[tb] < h->S) return fail(B200LP_E_INVALID, "per-scenario table has too few columns");
+            if (ax >= p->n_axes) return bad("table axis out of range");
+            if (ax == B200LP_COL_SCENARIO && p->table_cols[tb] < S) return bad("per-scenario table has too few columns");
             tab_dst.push_back(p->op_dst[k]); tab_table.push_back(tb); tab_offset.push_back(a[1]);
             continue;
         }
@@ -760,17 +782,66 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
             ok = na >= 4 && a[0] >= 0 && a[0] < nstor;
             if (ok) {
-                out.push_back(h->ds.vol_base + a[0]); out.push_back(h->ds.pc_base + a[0]); out.push_back(h->h_st_maxv_idx[a[0]]);
+                out.push_back(vol_base + a[0]); out.push_back(pc_base + a[0]); out.push_back(st_maxv_idx[a[0]]);
                 ok = refs(1, 3);
             }
             break;
         default: ok = false;
         }
-        if (!ok) return fail(B200LP_E_INVALID, "malformed op");
+        if (!ok) return bad("malformed op");
         code.push_back(kind); code.push_back(p->op_dst[k]); code.push_back((int)out.size());
         code.insert(code.end(), out.begin(), out.end());
     }
     (void)nargs;
+    std::vector<int> &rec_idx = dec.rec_idx, &rec_src = dec.rec_src;
+    rec_idx.assign(p->n_recorders ? p->n_recorders : 1, 0); rec_src.assign(p->n_recorders ? p->n_recorders : 1, 0);
+    for (int r = 0; r < p->n_recorders; r++) {
+        const int kind = p->rec_kind[r];
+        const bool needs_ref = kind == B200LP_REC_NODE_DEFICIT || kind == B200LP_REC_NODE_SUPPLIED || kind == B200LP_REC_NODE_CURTAIL ||
+                               kind == B200LP_REC_TOTAL_DEFICIT || kind == B200LP_REC_DEFICIT_FREQ;
+        if (needs_ref) {
+            if (!ref_ok(p->rec_ref[r])) return bad("recorder max_flow ref out of range");
+            rec_idx[r] = vidx(p->rec_ref[r]);
+        }
+        const bool storage_kind = kind == B200LP_REC_STORAGE_VOLUME || kind == B200LP_REC_STORAGE_PC || kind == B200LP_REC_MIN_VOLUME;
+        if (storage_kind && (p->rec_src[r] < 0 || p->rec_src[r] >= nstor)) return bad("recorder storage index out of range");
+        rec_src[r] = storage_kind ? p->rec_src[r] : 0;  // the kernel reads V[vol_base + src] unconditionally
+        if (p->rec_row[r] >= m || p->rec_row[r] < -1) return bad("recorder row out of range");
+        for (int e = p->rec_indptr[r]; e < p->rec_indptr[r + 1]; e++)
+            if (p->rec_col[e] < 0 || p->rec_col[e] >= n) return bad("recorder column out of range");
+    }
+    return true;
+}
+
+static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC; }
+
+extern "C" {
+
+int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
+    if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
+    if (p->n_steps <= 0) return fail(B200LP_E_INVALID, "program has no timesteps");
+    if (h->use_cta && !h->pdhg)
+        return fail(B200LP_E_UNSUPPORTED, "the device-resident run needs a register-resident kernel variant; "
+                                          "this LP uses the CTA-per-scenario kernel (per-timestep path only)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    free_program(h);
+    const size_t S = (size_t)h->S;
+    const int nst = h->ds.n_storage;
+    DevProgram &dp = h->dp;
+    dp = DevProgram{};
+    dp.n_steps = p->n_steps; dp.n_tables = p->n_tables; dp.n_axes = p->n_axes;
+    dp.n_recorders = p->n_recorders;
+    DecodedProgram dec;
+    {
+        std::string err;
+        if (!decode_program(p, h->ds.n_slots, h->ds.n_consts, h->ds.n_storage, h->ds.vol_base, h->ds.pc_base, h->ds.m, h->ds.n,
+                            h->S, h->h_st_maxv_idx, dec, err))
+            return fail(B200LP_E_INVALID, err);
+    }
+    const int n_slots = h->ds.n_slots;
+    std::vector<int> &tab_dst = dec.tab_dst, &tab_table = dec.tab_table, &tab_offset = dec.tab_offset, &code = dec.code;
+    std::vector<int> &rec_idx = dec.rec_idx, &rec_src = dec.rec_src;
     dp.n_table_ops = (int)tab_dst.size();
     dp.n_code = (int)code.size();
     // ---- lane-parallel schedule of the non-table ops (falls back to the interpreter when an op does not fit)
@@ -864,22 +935,6 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
         if (getenv("B200LP_NO_FAST_OPS")) { n_levels = 0; fop.clear(); }
     }
     dp.n_fop_levels = n_levels;
-    std::vector<int> rec_idx(p->n_recorders ? p->n_recorders : 1, 0), rec_src(p->n_recorders ? p->n_recorders : 1, 0);
-    for (int r = 0; r < p->n_recorders; r++) {
-        const int kind = p->rec_kind[r];
-        const bool needs_ref = kind == B200LP_REC_NODE_DEFICIT || kind == B200LP_REC_NODE_SUPPLIED || kind == B200LP_REC_NODE_CURTAIL ||
-                               kind == B200LP_REC_TOTAL_DEFICIT || kind == B200LP_REC_DEFICIT_FREQ;
-        if (needs_ref) {
-            if (!ref_ok(p->rec_ref[r])) return fail(B200LP_E_INVALID, "recorder max_flow ref out of range");
-            rec_idx[r] = vidx(p->rec_ref[r]);
-        }
-        const bool storage_kind = kind == B200LP_REC_STORAGE_VOLUME || kind == B200LP_REC_STORAGE_PC || kind == B200LP_REC_MIN_VOLUME;
-        if (storage_kind && (p->rec_src[r] < 0 || p->rec_src[r] >= nstor)) return fail(B200LP_E_INVALID, "recorder storage index out of range");
-        rec_src[r] = storage_kind ? p->rec_src[r] : 0;  // the kernel reads V[vol_base + src] unconditionally
-        if (p->rec_row[r] >= h->ds.m || p->rec_row[r] < -1) return fail(B200LP_E_INVALID, "recorder row out of range");
-        for (int e = p->rec_indptr[r]; e < p->rec_indptr[r + 1]; e++)
-            if (p->rec_col[e] < 0 || p->rec_col[e] >= h->ds.n) return fail(B200LP_E_INVALID, "recorder column out of range");
-    }
     long long ndata = 0;
     for (int t = 0; t < p->n_tables; t++) {
         const long long end = (long long)p->table_offset[t] + (long long)p->table_rows[t] * p->table_cols[t];

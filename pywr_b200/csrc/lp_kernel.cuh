@@ -1406,7 +1406,6 @@ struct JitLane {
     int nbv;     // variable in the non-basic position (-1: padding)
     int nstat;   // its status (carried from timestep to timestep: boxed variables keep their side on ties)
     double dj;   // its reduced cost
-    int rloc;    // where the row variable n + gl is: basic position p (p < G) or non-basic position G + j
     // per timestep
     double xn;   // value of the non-basic position
 
@@ -1426,9 +1425,9 @@ struct JitLane {
         if (h >= 0) pos[h < n ? h : NCP + (h - n)] = gl;
         if (nbv >= 0) pos[nbv < n ? nbv : NCP + (nbv - n)] = G + gl;
         D.sync();
-        rloc = gl < D.m ? pos[NCP + gl] : gl;
     }
-    // uniform over the group: where row i / column c is (valid right after derive())
+    // uniform over the group: where row i / column c is: basic position p (p < G) or non-basic position G + j
+    // (valid right after derive())
     __device__ __forceinline__ int row_loc(const DictT &D, const int i) const { return D.sm.f->vstat[NCP + i]; }
     __device__ __forceinline__ int col_loc(const DictT &D, const int c) const { return D.sm.f->vstat[c]; }
 
@@ -1482,6 +1481,88 @@ struct JitLane {
     __device__ __forceinline__ void reload(DictT &D) {
         derive(D);
         xn = D.sm.f->xn[D.gl];
+    }
+    // end of the launch: what extract_solution / store_state read from shared memory
+    __device__ __forceinline__ void to_shared(DictT &D) {
+        D.sm.f->nbstat[D.gl] = nstat;
+        D.sm.f->xn[D.gl] = xn;
+        D.sync();
+    }
+};
+
+// Table ops of the specialised kernel: lane j of the group owns ops j, j + G, ... and fetches their values one timestep
+// ahead; the generated code broadcasts each value with one constant-lane shuffle.
+template <int G, int PF>
+struct JitTables {
+    TableDesc td[PF];
+    double pf[PF];
+    __device__ __forceinline__ void init(const DevStructure &st, const DevProgram &pg, const int gl, const int S, const int sidx,
+                                         const int t0) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const int j = gl + u * G;
+            td[u].ptr = pg.ts_days; td[u].last = 0; td[u].stride = 0; td[u].off = 0; td[u].dst = 0;
+            if (j < pg.n_table_ops) {
+                const int tb = __ldg(&pg.tab_table[j]);
+                const int ax = __ldg(&pg.table_axis[tb]);
+                const int col = ax == -1 ? 0 : (ax == -2 ? sidx : __ldg(&pg.scen_index[(size_t)ax * S + sidx]));
+                td[u].ptr = pg.table_data + __ldg(&pg.table_offset[tb]) + col;
+                td[u].last = __ldg(&pg.table_rows[tb]) - 1;
+                td[u].stride = __ldg(&pg.table_cols[tb]);
+                td[u].off = __ldg(&pg.tab_offset[j]);
+            }
+            pf[u] = td[u].at(t0);
+        }
+    }
+    __device__ __forceinline__ void prefetch(const int t) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) pf[u] = td[u].at(t);  // clamped to the table's last row
+    }
+};
+
+// Recorders of the specialised kernel: lane r % G owns recorder r (unit r / G).  The generated code computes every
+// recorder's sample as a group-uniform value and hands each lane the one it owns; accumulators, running aggregates and
+// the output cursor stay in the owner's registers for the whole launch.
+template <int G, int RU>
+struct JitRecorders {
+    double racc[RU], asum[RU], amin[RU], amax[RU];
+    double *rout[RU], *ragg[RU];
+    bool on[RU], arr[RU], store[RU], ismin[RU];
+    __device__ __forceinline__ void init(const DevProgram &pg, const int gl, const int S, const int sidx, const int t0) {
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const int r = gl + u * G;
+            racc[u] = 0.0; asum[u] = 0.0; amin[u] = INFINITY; amax[u] = -INFINITY;
+            rout[u] = nullptr; ragg[u] = nullptr;
+            on[u] = arr[u] = store[u] = ismin[u] = false;
+            if (r < pg.n_recorders) {
+                const int rk = __ldg(&pg.rec_kind[r]);
+                on[u] = true;
+                arr[u] = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
+                ismin[u] = rk == B200LP_REC_MIN_VOLUME;
+                rout[u] = pg.rec_out[r];  // nullptr: array recorder of a B200LP_PROG_AGG_ONLY program
+                store[u] = arr[u] && rout[u] != nullptr;
+                if (rout[u]) rout[u] += arr[u] ? (size_t)t0 * S + sidx : (size_t)sidx;
+                if (!arr[u]) racc[u] = *rout[u];
+                else {
+                    ragg[u] = pg.rec_agg + (size_t)r * 3 * S + sidx;
+                    asum[u] = ragg[u][0]; amin[u] = ragg[u][S]; amax[u] = ragg[u][2 * (size_t)S];
+                }
+            }
+        }
+    }
+    // o: sample of an array kind; add: increment of an accumulating kind; vv: volume of a minimum-volume recorder
+    __device__ __forceinline__ void sample(const int u, const double o, const double add, const double vv, const int S) {
+        agg_sample(asum[u], amin[u], amax[u], o);
+        if (store[u]) { *rout[u] = o; rout[u] += S; }
+        racc[u] = ismin[u] ? fmin(racc[u], vv) : racc[u] + add;
+    }
+    __device__ __forceinline__ void finish(const int S) {
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            if (on[u] && !arr[u]) *rout[u] = racc[u];
+            if (on[u] && arr[u]) { ragg[u][0] = asum[u]; ragg[u][S] = amin[u]; ragg[u][2 * (size_t)S] = amax[u]; }
+        }
     }
 };
 
