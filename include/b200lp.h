@@ -30,8 +30,10 @@
 #ifndef B200LP_H
 #define B200LP_H
 
+#ifndef __CUDACC_RTC__ /* the run-time compiled kernel (pywr_b200/csrc/jit_run.inc) sees this text without a libc */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -131,6 +133,8 @@ typedef struct b200lp_stats {
     int32_t kernel_variant;  /* index of the register variant; 100: CTA-per-scenario simplex; 200: PDHG; 300: revised simplex, inverse in HBM */
     int64_t pdhg_iterations; /* PDHG path: scenario-iterations since create                           */
     int32_t reduced_rows, reduced_nonzero; /* PDHG path: rows / non-zeros left by the structural presolve */
+    int32_t run_kernel_jit;  /* 1: b200lp_run launches the structure-specialised kernel compiled at b200lp_load_program */
+    int32_t reserved1;
 } b200lp_stats;
 
 const char *b200lp_last_error(void);
@@ -315,8 +319,16 @@ typedef struct b200lp_program {
     const double *st_roll_init;  /* [n_storage] */
 } b200lp_program;
 
-/* Load (copy) a program; allocates the recorder outputs on the device and resets the run state. */
+/* Load (copy) a program; allocates the recorder outputs on the device and resets the run state.
+ * For the register-resident engine this also generates the CUDA source of a run kernel specialised on (structure,
+ * program) - every index, row class, op and recorder kind an immediate, per-scenario scalars in registers - and compiles
+ * it with NVRTC (libnvrtc is dlopen'ed; when it is missing, the model is not covered or B200LP_JIT=0 is set, the generic
+ * run kernel is used: b200lp_stats.run_kernel_jit says which).  Same arithmetic, bit-identical results. */
 int b200lp_load_program(b200lp_handle *h, const b200lp_program *p);
+/* Diagnostic, needs no device: generate the specialised run kernel for (structure, program) and, with compile != 0,
+ * compile it with NVRTC for sm_100a.  log (may be NULL) receives the compiler output including the ptxas resource
+ * statistics.  B200LP_E_UNSUPPORTED: the generator does not cover this model (the generic run kernel would be used). */
+int b200lp_jit_probe(const b200lp_structure *s, const b200lp_program *p, int32_t n_scenarios, int32_t compile, char *log, size_t cap);
 /* Restart the loaded program: initial volumes, slack bases, zeroed recorders (Model.reset). */
 int b200lp_program_reset(b200lp_handle *h);
 /* Run timesteps [t0, t0+n) for all scenarios on the device.  Asynchronous on b200lp_stream();

@@ -186,6 +186,29 @@ static bool resolve_structure(const b200lp_structure *s, int rows_cap, HostStruc
     return true;
 }
 
+// Ops of a program with every operand resolved to an index into V (decode_program below).
+struct DecodedProgram {
+    std::vector<int> tab_dst, tab_table, tab_offset, code, rec_idx, rec_src;
+};
+
+namespace jit {
+// what the generator of the structure-specialised run kernel (jit_run.inc) needs, all host copies
+struct Spec {
+    int G = 0, NC = 0, minb = 3;
+    HostStructure hs;
+    std::vector<double> consts;
+    std::vector<int> st_kind;
+    DecodedProgram dec;
+    int n_recorders = 0;
+    std::vector<int> rec_kind, rec_row, rec_indptr, rec_col;
+    std::vector<double> rec_factor, rec_w;
+    std::vector<int> stflow_indptr, stflow_col;
+    std::vector<double> stflow_w;
+    std::vector<int> roll_len, roll_off;
+    bool valid = false;
+};
+}  // namespace jit
+
 struct b200lp_handle {
     int device = 0;
     int S = 0;
@@ -222,6 +245,12 @@ struct b200lp_handle {
     std::vector<cudaEvent_t> pipe_events;
     std::vector<int> h_st_maxv_idx;  // V index of every storage's max_volume (host copy, for op pre-decoding)
     HostStructure hs;                // resolved LP structure (register / CTA engines)
+    jit::Spec jspec;                 // what the loaded program's specialised kernel is generated from (jit_run.inc)
+    cudaKernel_t jit_kernel = nullptr;
+    bool jit_stale = false;          // constants changed since the kernel was generated
+    std::string jit_note;            // why the generic run kernel is used instead
+    std::vector<double> consts_host;
+    std::vector<int> st_kind_host;
     struct PdhgEngine *pdhg = nullptr;  // large-LP path (pdhg_engine.cuh, rsx_kernels.cuh): LPs beyond the dictionary kernels
     struct PlaneHost *plane = nullptr;  // device-resident program on the large-LP path (plane_program.inc)
     std::vector<double> ts_days_host;
@@ -348,6 +377,8 @@ int b200lp_create_ex(const b200lp_structure *s, int32_t n_scenarios, int32_t dev
     const std::vector<int> &row_class = hs.row_class, &row_a = hs.row_a, &row_b = hs.row_b, &st_row = hs.st_row;
     const std::vector<int> &st_vol = hs.st_vol, &st_minv = hs.st_minv, &st_maxv = hs.st_maxv, &st_act = hs.st_act;
     h->h_st_maxv_idx = st_maxv;
+    h->consts_host.assign(s->consts, s->consts + s->n_consts);
+    h->st_kind_host.assign(s->st_kind, s->st_kind + s->n_storage);
     const int ncost = s->cost_indptr[n];
     std::vector<int> cost_idx(ncost), dyn_idx(s->n_dyn_a);
     for (int k = 0; k < ncost; k++) {
@@ -491,6 +522,11 @@ int b200lp_set_consts(b200lp_handle *h, const double *consts) {
     if (h->ds.n_consts > 0) {
         CUDA_TRY(cudaMemcpyAsync(h->d_consts, consts, sizeof(double) * h->ds.n_consts, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->consts_host.assign(consts, consts + h->ds.n_consts);
+        if (h->has_program && h->jspec.valid) {  // the specialised kernel holds the constants as immediates
+            h->jspec.consts = h->consts_host;
+            h->jit_stale = true;
+        }
     }
     return B200LP_OK;
 }
@@ -703,6 +739,7 @@ static void free_program(b200lp_handle *h) {
     for (void *p : h->prog_owned) cudaFree(p);
     h->prog_owned.clear(); h->rec_ptr.clear(); h->rec_kind.clear();
     h->has_program = false;
+    h->jspec.valid = false; h->jit_kernel = nullptr; h->jit_stale = false; h->stats.run_kernel_jit = 0;
 }
 
 template <typename T>
@@ -722,10 +759,6 @@ static cudaError_t pupload(b200lp_handle *h, const T *src, size_t count, const T
 // Ops of a program with every operand resolved to an index into V (pure host code, shared by b200lp_load_program and the
 // specialised-kernel generator): table ops get one descriptor each, everything else is pre-decoded into `code` as
 // kind, dst, nargs, args...
-struct DecodedProgram {
-    std::vector<int> tab_dst, tab_table, tab_offset, code, rec_idx, rec_src;
-};
-
 static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, int nstor, int vol_base, int pc_base, int m, int n,
                            int S, const std::vector<int> &st_maxv_idx, DecodedProgram &dec, std::string &err) {
     auto bad = [&](const char *msg) { err = msg; return false; };
@@ -815,7 +848,100 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
 
 static bool rec_is_array(int kind) { return kind >= B200LP_REC_NODE_FLOW && kind <= B200LP_REC_STORAGE_PC; }
 
+#include "jit_run.inc"
+
+// Blocks of 128 threads per SM the specialised kernel is compiled for (its register budget): the most that still puts the
+// whole batch into one wave keeps the per-timestep chain shortest; large batches take the highest occupancy.
+static int jit_pick_blocks(int grid) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (grid <= 3 * sms) return 3;
+    return 4;
+}
+
+// everything the generator needs from (resolved structure, program)
+static void fill_spec(jit::Spec &sp, int G, int NC, const HostStructure &hs, const double *consts, const int *st_kind,
+                      const b200lp_program *p, const DecodedProgram &dec) {
+    sp = jit::Spec{};
+    sp.G = G; sp.NC = NC; sp.hs = hs;
+    sp.consts.assign(consts, consts + hs.n_consts);
+    sp.st_kind.assign(st_kind, st_kind + hs.n_storage);
+    sp.dec = dec;
+    const int nr = p->n_recorders, nst = hs.n_storage;
+    sp.n_recorders = nr;
+    sp.rec_kind.assign(p->rec_kind, p->rec_kind + nr);
+    sp.rec_row.assign(p->rec_row, p->rec_row + nr);
+    sp.rec_indptr.assign(p->rec_indptr, p->rec_indptr + nr + 1);
+    const int ne = nr ? p->rec_indptr[nr] : 0;
+    sp.rec_col.assign(p->rec_col, p->rec_col + ne);
+    sp.rec_w.assign(p->rec_w, p->rec_w + ne);
+    sp.rec_factor.assign(p->rec_factor, p->rec_factor + nr);
+    sp.stflow_indptr.assign(p->stflow_indptr, p->stflow_indptr + nst + 1);
+    const int nf = nst ? p->stflow_indptr[nst] : 0;
+    sp.stflow_col.assign(p->stflow_col, p->stflow_col + nf);
+    sp.stflow_w.assign(p->stflow_w, p->stflow_w + nf);
+    sp.roll_len.assign(nst ? nst : 1, 0); sp.roll_off.assign(nst ? nst : 1, 0);
+    int rows = 0;
+    for (int k = 0; k < nst; k++) {
+        sp.roll_len[k] = p->st_roll_len ? std::max(0, p->st_roll_len[k]) : 0;
+        sp.roll_off[k] = rows;
+        rows += sp.roll_len[k];
+    }
+    sp.valid = true;
+}
+
+// (re)build the specialised kernel of the loaded program; leaves h->jit_kernel null when the model is not covered
+static void jit_prepare(b200lp_handle *h) {
+    h->jit_kernel = nullptr;
+    h->stats.run_kernel_jit = 0;
+    if (!h->jspec.valid) return;
+    if (const char *v = getenv("B200LP_JIT")) if (atoi(v) == 0) return;
+    std::string why;
+    if (!jit::eligible(h->jspec, why)) { h->jit_note = why; return; }
+    const int groups_per_block = h->block / h->jspec.G;
+    const int grid = (h->S + groups_per_block - 1) / groups_per_block;
+    int minb = jit_pick_blocks(grid);
+    if (const char *v = getenv("B200LP_JIT_MINB")) { const int f = atoi(v); if (f >= 1 && f <= 8) minb = f; }
+    h->jspec.minb = minb;
+    const std::string src = jit::generate(h->jspec);
+    if (const char *path = getenv("B200LP_JIT_DUMP")) { FILE *f = fopen(path, "w"); if (f) { fputs(src.c_str(), f); fclose(f); } }
+    jit::Loaded *L = jit::get_kernel(src);
+    if (!L) { h->jit_note = "run-time compilation failed"; return; }
+    h->jit_kernel = L->kernel;
+    h->stats.run_kernel_jit = 1;
+    h->jit_note.clear();
+}
+
 extern "C" {
+
+int b200lp_jit_probe(const b200lp_structure *s, const b200lp_program *p, int32_t n_scenarios, int32_t compile, char *log, size_t cap) {
+    if (!s || !p) return fail(B200LP_E_INVALID, "null argument");
+    if (log && cap) log[0] = 0;
+    int variant = -1;
+    for (int v = 0; v < kNumVariants; v++)
+        if (s->n_rows <= kVariants[v].G * kVariants[v].RPL && s->n_cols <= kVariants[v].NC) { variant = v; break; }
+    if (variant < 0 || kVariants[variant].RPL != 1) return fail(B200LP_E_UNSUPPORTED, "no one-row-per-lane register variant fits this LP");
+    const Variant &V = kVariants[variant];
+    HostStructure hs;
+    std::string err;
+    if (!resolve_structure(s, V.G * V.RPL, hs, err)) return fail(B200LP_E_INVALID, err);
+    DecodedProgram dec;
+    if (!decode_program(p, hs.n_slots, hs.n_consts, hs.n_storage, hs.vol_base, hs.pc_base, hs.m, hs.n, n_scenarios, hs.st_maxv, dec, err))
+        return fail(B200LP_E_INVALID, err);
+    jit::Spec sp;
+    fill_spec(sp, V.G, V.NC, hs, s->consts, s->st_kind, p, dec);
+    if (!jit::eligible(sp, err)) return fail(B200LP_E_UNSUPPORTED, "not specialised: " + err);
+    const std::string src = jit::generate(sp);
+    if (const char *path = getenv("B200LP_JIT_DUMP")) { FILE *f = fopen(path, "w"); if (f) { fputs(src.c_str(), f); fclose(f); } }
+    if (!compile) return B200LP_OK;
+    std::vector<char> cubin;
+    std::string clog;
+    const bool ok = jit::compile(src, cubin, clog);
+    if (log && cap) { strncpy(log, clog.c_str(), cap - 1); log[cap - 1] = 0; }
+    if (!ok) return fail(B200LP_E_CUDA, "NVRTC: " + clog.substr(0, 400));
+    return B200LP_OK;
+}
 
 int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     if (!h || !p) return fail(B200LP_E_INVALID, "null argument");
@@ -1040,6 +1166,10 @@ int b200lp_load_program(b200lp_handle *h, const b200lp_program *p) {
     h->init_pc.assign(p->initial_pc, p->initial_pc + (size_t)nst * S);
     h->prog_steps = p->n_steps;
     h->has_program = true;
+    if (!h->pdhg && !h->use_cta && kVariants[h->variant].RPL == 1) {
+        fill_spec(h->jspec, kVariants[h->variant].G, kVariants[h->variant].NC, h->hs, h->consts_host.data(), h->st_kind_host.data(), p, dec);
+        jit_prepare(h);
+    }
     if (h->pdhg) {  // large-LP path: the program runs as plane kernels around the batched solve (plane_program.inc)
         const int rc = plane_attach(h, p);
         if (rc != 0) { free_program(h); return rc; }
@@ -1092,7 +1222,18 @@ int b200lp_run(b200lp_handle *h, int32_t t0, int32_t n) {
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->plane) return plane_run(h, t0, n);
     const Variant &V = kVariants[h->variant];
-    V.run(h->ds, h->state, h->dp, h->S, t0, n, h->stream, h->block);
+    if (h->jit_stale) { h->jit_stale = false; jit_prepare(h); }
+    if (h->jit_kernel) {
+        const int groups_per_block = h->block / V.G;
+        const int grid = (h->S + groups_per_block - 1) / groups_per_block;
+        const size_t smem = ((V.smem_per_group(h->ds.n_val) + 15) & ~(size_t)15) * groups_per_block;
+        if (smem > 48 * 1024) ensure_smem((const void *)h->jit_kernel, smem);
+        int S = h->S, t0_ = t0, n_ = n;
+        void *args[] = {&h->ds, &h->state, &h->dp, &S, &t0_, &n_};
+        CUDA_TRY(cudaLaunchKernel((const void *)h->jit_kernel, dim3(grid), dim3(h->block), args, smem, h->stream));
+    } else {
+        V.run(h->ds, h->state, h->dp, h->S, t0, n, h->stream, h->block);
+    }
     h->stats.kernel_launches++;
     h->stats.steps += n;
     h->stats.scenario_steps += (int64_t)n * h->S;

@@ -1439,6 +1439,12 @@ struct JitLane {
         return loc < G ? b : x;
     }
 
+    // the same with ONE shuffle: `loc` is uniform over the group, so every lane offers the kind of value that is asked for
+    __device__ __forceinline__ double pick(const DictT &D, const int loc) const {
+        const double mine = loc < G ? D.beta[0] : xn;
+        return __shfl_sync(D.gmask(), mine, loc & (G - 1), G);
+    }
+
     // Steady-state timestep (Dict::fast_step without shared memory).  mylo / myhi: bounds of LP row gl (free for
     // lanes beyond the last row).  Leaves beta in D.beta[0], the non-basic value in xn.  Returns true when the
     // general solve has to run (a basic variable out of bounds or a dual infeasible non-basic position).

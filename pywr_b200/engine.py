@@ -29,6 +29,7 @@ class b200lp_stats(ctypes.Structure):
         ("n_rows", ctypes.c_int32), ("n_cols", ctypes.c_int32), ("n_nonzero", ctypes.c_int32),
         ("kernel_variant", ctypes.c_int32),
         ("pdhg_iterations", ctypes.c_int64), ("reduced_rows", ctypes.c_int32), ("reduced_nonzero", ctypes.c_int32),
+        ("run_kernel_jit", ctypes.c_int32), ("reserved1", ctypes.c_int32),
     ]
 
 
@@ -59,6 +60,7 @@ SYMBOLS = [
     ("b200lp_memcpy_h2d", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     ("b200lp_memcpy_d2h", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     ("b200lp_load_program", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("b200lp_jit_probe", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t]),
     ("b200lp_program_reset", ctypes.c_int, [ctypes.c_void_p]),
     ("b200lp_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]),
     ("b200lp_run_pipelined", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),

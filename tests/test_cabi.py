@@ -94,3 +94,26 @@ def test_structure_roundtrip(tmp_path):
     assert np.array_equal(s.dense(), s2.dense())
     t, _ = load_case("thames.route")
     assert (t.n_rows, t.n_cols, t.nnz, t.n_nodes) == (15, 6, 23, 14)
+
+
+def test_specialised_run_kernel_compiles_for_every_golden_program():
+    """No device needed: b200lp_jit_probe generates the structure-specialised run kernel of every golden program and
+    compiles it with NVRTC for sm_100a (the compile b200lp_load_program does on the GPU box); no register spills."""
+    import ctypes
+
+    from fixtures_util import load_program_case, n_scenarios_of, program_cases
+    from pywr_b200.engine import load_library
+
+    L = load_library()
+    try:
+        ctypes.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc is not installed here")
+    for name in program_cases():
+        s, prog, _, _ = load_program_case(name)
+        cs, cp = s.to_c(), prog.to_c()
+        log = ctypes.create_string_buffer(1 << 16)
+        rc = L.b200lp_jit_probe(ctypes.addressof(cs), ctypes.addressof(cp), n_scenarios_of(s, prog), 1, log, len(log))
+        assert rc == 0, (name, L.b200lp_last_error().decode())
+        text = log.value.decode()
+        assert "lp_run_jit" in text and " 0 bytes spill stores" in text.split("lp_run_jit")[-1], (name, text[-400:])

@@ -119,3 +119,30 @@ def test_run_kernel_register_builds_agree(monkeypatch, name, S, seed):
         assert _rel(y, z) <= 1e-9, nm
     for x, y in zip(a[2], b[2]):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,S,seed", [(n, 96, 11 + i) for i, n in enumerate(program_cases())] +
+                         [("two_reservoir.route", 1024, 31), ("thames.route", 4096, 32)])
+def test_specialised_run_kernel_equals_generic_run_kernel(monkeypatch, name, S, seed):
+    """b200lp_load_program compiles a run kernel specialised on (structure, program) with NVRTC (csrc/jit_run.inc: ops, row
+    bounds, Storage.after and recorders as straight-line code over registers, no shared memory on the steady-state timestep).
+    Same arithmetic as the generic lp_run_kernel (B200LP_JIT=0): bit-identical recorders, final state and pivot counts, in
+    one launch and in time slices; both equal to the oracle's."""
+    s, prog, _, names = load_program_case(name)
+    q = widen_program(s, prog, S, seed)
+    res = {}
+    for jit in ("1", "0"):
+        monkeypatch.setenv("B200LP_JIT", jit)
+        cpu, gpu = _engines(s, S)
+        res[jit] = run_program(gpu, q, chunks=[7, 100] if jit == "1" else None) + (gpu.counters()["pivots"], gpu.stats()["run_kernel_jit"])
+        if jit == "0":
+            o_cpu, st_cpu, _ = run_program(cpu, q)
+        gpu.close(); cpu.close()
+    a, b = res["1"], res["0"]
+    assert a[4] == 1 and b[4] == 0, "the specialised kernel must be the one that ran by default"
+    assert a[1] == b[1] == st_cpu and a[3] == b[3]
+    for x, y, z, nm in zip(a[0], b[0], o_cpu, names):
+        assert np.array_equal(x, y, equal_nan=True), (nm, _rel(x, y))
+        assert _rel(y, z) <= 1e-9, nm
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y, equal_nan=True)
