@@ -205,6 +205,7 @@ struct Spec {
     std::vector<int> stflow_indptr, stflow_col;
     std::vector<double> stflow_w;
     std::vector<int> roll_len, roll_off;
+    double uniform_days = 0.0;  // > 0: every timestep of the program has this length
     bool valid = false;
 };
 }  // namespace jit
@@ -856,6 +857,7 @@ static int jit_pick_blocks(int grid) {
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (grid <= 2 * sms) return 2;
     if (grid <= 3 * sms) return 3;
     return 4;
 }
@@ -888,6 +890,10 @@ static void fill_spec(jit::Spec &sp, int G, int NC, const HostStructure &hs, con
         sp.roll_off[k] = rows;
         rows += sp.roll_len[k];
     }
+    sp.uniform_days = p->ts_days[0];
+    for (int t = 1; t < p->n_steps; t++)
+        if (p->ts_days[t] != sp.uniform_days) { sp.uniform_days = 0.0; break; }
+    if (!(sp.uniform_days > 0.0)) sp.uniform_days = 0.0;
     sp.valid = true;
 }
 
@@ -940,6 +946,10 @@ int b200lp_jit_probe(const b200lp_structure *s, const b200lp_program *p, int32_t
     const bool ok = jit::compile(src, cubin, clog);
     if (log && cap) { strncpy(log, clog.c_str(), cap - 1); log[cap - 1] = 0; }
     if (!ok) return fail(B200LP_E_CUDA, "NVRTC: " + clog.substr(0, 400));
+    if (const char *path = getenv("B200LP_JIT_DUMP")) {  // <path>.cubin for cuobjdump -sass
+        FILE *f = fopen((std::string(path) + ".cubin").c_str(), "wb");
+        if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    }
     return B200LP_OK;
 }
 

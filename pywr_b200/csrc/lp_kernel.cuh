@@ -153,6 +153,22 @@ __device__ __forceinline__ bool abs_below(double x, const unsigned long long thr
 }
 constexpr unsigned long long BITS_1E_8 = 0x3e45798ee2308c3aull;  // 1e-8
 
+// a if lane == which else b, as ONE compare and one select (selp): written in PTX because the optimiser turns a chain of
+// `if (lane == k) x = v_k;` into a tree of divergent branches
+__device__ __forceinline__ double sel_lane(const int lane, const int which, const double a, const double b) {
+    double r;
+    asm("{ .reg .pred p; setp.eq.s32 p, %3, %4; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"(lane), "r"(which));
+    return r;
+}
+__device__ __forceinline__ double sel_pred(const int c, const double a, const double b) {  // c != 0 ? a : b
+    double r;
+    asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"(c));
+    return r;
+}
+
+// fmax(x, 0.0) as one compare + select: the same bits for every input (NaN -> 0, -0 -> +0, like CUDA's fmax)
+__device__ __forceinline__ double max0(const double x) { return x > 0.0 ? x : 0.0; }
+
 // cython_glpk.pyx:934-945 and constraint_type :66-77
 __device__ __forceinline__ void type_bounds(double &lo, double &hi) {
     lo = abs_below(lo, BITS_1E_8) ? 0.0 : lo;
@@ -1406,6 +1422,7 @@ struct JitLane {
     int nbv;     // variable in the non-basic position (-1: padding)
     int nstat;   // its status (carried from timestep to timestep: boxed variables keep their side on ties)
     double dj;   // its reduced cost
+    int rloc;    // where the row variable of LP row gl is: basic position p (p < G) or non-basic position G + j
     // per timestep
     double xn;   // value of the non-basic position
 
@@ -1425,6 +1442,7 @@ struct JitLane {
         if (h >= 0) pos[h < n ? h : NCP + (h - n)] = gl;
         if (nbv >= 0) pos[nbv < n ? nbv : NCP + (nbv - n)] = G + gl;
         D.sync();
+        rloc = gl < D.m ? pos[NCP + gl] : gl;
     }
     // uniform over the group: where row i / column c is: basic position p (p < G) or non-basic position G + j
     // (valid right after derive())
@@ -1445,36 +1463,62 @@ struct JitLane {
         return __shfl_sync(D.gmask(), mine, loc & (G - 1), G);
     }
 
-    // Steady-state timestep (Dict::fast_step without shared memory).  mylo / myhi: bounds of LP row gl (free for
-    // lanes beyond the last row).  Leaves beta in D.beta[0], the non-basic value in xn.  Returns true when the
-    // general solve has to run (a basic variable out of bounds or a dual infeasible non-basic position).
-    template <int NREAL>
-    __device__ __forceinline__ bool fast_check(DictT &D, const double mylo, const double myhi) {
+    // activity of LP row gl, every lane its own row (the padding lanes read their own position: never used)
+    __device__ __forceinline__ double own_row_value(const DictT &D) const {
+        const unsigned gm = D.gmask();
+        const double b = __shfl_sync(gm, D.beta[0], rloc & (G - 1), G);
+        const double x = __shfl_sync(gm, xn, rloc & (G - 1), G);
+        return rloc < G ? b : x;
+    }
+
+    // Steady-state timestep (Dict::fast_step).  mylo / myhi: bounds of LP row gl (free for lanes beyond the last row);
+    // lane_flags: bit 0 NaN input, bit 1 inconsistent bounds of that row.  Leaves beta in D.beta[0], the non-basic value in
+    // xn.  Returns the OR over the group of lane_flags | dual infeasible non-basic position << 2 | basic variable out of
+    // bounds << 3: 0 means optimal as it stands.  SMEM_X: the non-basic values travel through shared memory (one STS, a
+    // warp barrier and NC / 2 LDS.128) instead of 2 NC shuffles.
+    template <int NREAL, bool SMEM_X>
+    __device__ __forceinline__ unsigned fast_check(DictT &D, const double mylo, const double myhi, const int lane_flags) {
         const unsigned gm = D.gmask();
         const double tl = __shfl_sync(gm, mylo, hsrc, G), th = __shfl_sync(gm, myhi, hsrc, G);
         const double nl = __shfl_sync(gm, mylo, nsrc, G), nh = __shfl_sync(gm, myhi, nsrc, G);
-        const double lob = hcol ? 0.0 : tl, hib = hcol ? INFINITY : th;
-        // Dict::place_nonbasics_lane for position gl
-        const double lo = ncol ? 0.0 : nl, hi = ncol ? INFINITY : nh;
+        const double lob = sel_pred(hcol, 0.0, tl), hib = sel_pred(hcol, INFINITY, th);
+        // Dict::place_nonbasics_lane for position gl, written without short-circuit operators: one instruction stream
+        const double lo = sel_pred(ncol, 0.0, nl), hi = sel_pred(ncol, INFINITY, nh);
         const bool lo_fin = lo > -INFINITY, hi_fin = hi < INFINITY, fx = lo == hi;
         const bool dpos = dj > TOL_DUAL, dneg = dj < -TOL_DUAL;
+        const bool pad = nbv < 0;
         const int s0 = nstat;
-        const int s_box = dpos ? VS_NL : (dneg ? VS_NU : ((s0 == VS_NL || s0 == VS_NU) ? s0 : VS_NL));
-        int s = lo_fin ? (hi_fin ? s_box : VS_NL) : (hi_fin ? VS_NU : VS_NF);
-        s = fx ? VS_NS : s;
-        const bool bad = lo_fin ? (!hi_fin && dneg) : (hi_fin ? dpos : (dpos || dneg));
-        double xv = (s == VS_NU) ? hi : (s == VS_NF ? 0.0 : lo);
-        if (nbv < 0) { s = VS_NS; xv = 0.0; }
-        const bool infe = !fx && bad && nbv >= 0;
+        const int keep = ((s0 == VS_NL) | (s0 == VS_NU)) ? s0 : VS_NL;
+        const int s_box = dpos ? VS_NL : (dneg ? VS_NU : keep);
+        const int s_fin = hi_fin ? s_box : VS_NL, s_inf = hi_fin ? VS_NU : VS_NF;
+        int s = lo_fin ? s_fin : s_inf;
+        s = (fx | pad) ? VS_NS : s;
+        const bool bad = (lo_fin & !hi_fin & dneg) | (!lo_fin & hi_fin & dpos) | (!lo_fin & !hi_fin & (dpos | dneg));
+        double xv = sel_pred(s == VS_NU, hi, sel_pred(s == VS_NF, 0.0, lo));
+        xv = sel_pred(pad, 0.0, xv);
+        const bool infe = !fx & bad & !pad;
         nstat = s;
         xn = xv;
         // beta = T xn, j ascending (Dict::basic_values; the padding columns contribute fma(0, 0, acc) = acc)
         double acc = 0.0;
+        if (SMEM_X) {
+            D.sm.f->xn[D.gl] = xv;
+            D.sync();
+            const double2 *x2 = reinterpret_cast<const double2 *>(D.sm.f->xn);
 #pragma unroll
-        for (int j = 0; j < NREAL; j++) acc = fma(D.T[0][j], __shfl_sync(gm, xv, j, G), acc);
+            for (int j = 0; j + 1 < NREAL; j += 2) {
+                const double2 p = x2[j / 2];
+                acc = fma(D.T[0][j], p.x, acc);
+                acc = fma(D.T[0][j + 1], p.y, acc);
+            }
+            if (NREAL & 1) acc = fma(D.T[0][NREAL - 1], D.sm.f->xn[NREAL - 1], acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NREAL; j++) acc = fma(D.T[0][j], __shfl_sync(gm, xv, j, G), acc);
+        }
         D.beta[0] = acc;
-        const bool viol = (acc < lob - TOL_PRIMAL * (1.0 + fabs(lob))) || (acc > hib + TOL_PRIMAL * (1.0 + fabs(hib)));
-        return group_ballot<G>(viol || infe, gm) != 0u;
+        const bool viol = (acc < lob - TOL_PRIMAL * (1.0 + fabs(lob))) | (acc > hib + TOL_PRIMAL * (1.0 + fabs(hib)));
+        return group_or<G>((unsigned)lane_flags | (infe ? 4u : 0u) | (viol ? 8u : 0u), gm);
     }
 
     // lane state -> the shared-memory layout the general solve works on
@@ -1534,27 +1578,27 @@ struct JitRecorders {
     double racc[RU], asum[RU], amin[RU], amax[RU];
     double *rout[RU], *ragg[RU];
     bool on[RU], arr[RU], store[RU], ismin[RU];
-    __device__ __forceinline__ void init(const DevProgram &pg, const int gl, const int S, const int sidx, const int t0) {
+    __device__ __forceinline__ void init() {
 #pragma unroll
         for (int u = 0; u < RU; u++) {
-            const int r = gl + u * G;
             racc[u] = 0.0; asum[u] = 0.0; amin[u] = INFINITY; amax[u] = -INFINITY;
             rout[u] = nullptr; ragg[u] = nullptr;
             on[u] = arr[u] = store[u] = ismin[u] = false;
-            if (r < pg.n_recorders) {
-                const int rk = __ldg(&pg.rec_kind[r]);
-                on[u] = true;
-                arr[u] = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
-                ismin[u] = rk == B200LP_REC_MIN_VOLUME;
-                rout[u] = pg.rec_out[r];  // nullptr: array recorder of a B200LP_PROG_AGG_ONLY program
-                store[u] = arr[u] && rout[u] != nullptr;
-                if (rout[u]) rout[u] += arr[u] ? (size_t)t0 * S + sidx : (size_t)sidx;
-                if (!arr[u]) racc[u] = *rout[u];
-                else {
-                    ragg[u] = pg.rec_agg + (size_t)r * 3 * S + sidx;
-                    asum[u] = ragg[u][0]; amin[u] = ragg[u][S]; amax[u] = ragg[u][2 * (size_t)S];
-                }
-            }
+        }
+    }
+    // this lane owns recorder r in unit u (the generated code calls it under `if (gl == owner lane)`)
+    __device__ __forceinline__ void bind(const int u, const int r, const DevProgram &pg, const int S, const int sidx, const int t0) {
+        const int rk = __ldg(&pg.rec_kind[r]);
+        on[u] = true;
+        arr[u] = rk >= B200LP_REC_NODE_FLOW && rk <= B200LP_REC_STORAGE_PC;
+        ismin[u] = rk == B200LP_REC_MIN_VOLUME;
+        rout[u] = pg.rec_out[r];  // nullptr: array recorder of a B200LP_PROG_AGG_ONLY program
+        store[u] = arr[u] && rout[u] != nullptr;
+        if (rout[u]) rout[u] += arr[u] ? (size_t)t0 * S + sidx : (size_t)sidx;
+        if (!arr[u]) racc[u] = *rout[u];
+        else {
+            ragg[u] = pg.rec_agg + (size_t)r * 3 * S + sidx;
+            asum[u] = ragg[u][0]; amin[u] = ragg[u][S]; amax[u] = ragg[u][2 * (size_t)S];
         }
     }
     // o: sample of an array kind; add: increment of an accumulating kind; vv: volume of a minimum-volume recorder
