@@ -4,10 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU path (oracle port, all host cores)
 
-Workload (config.workload): BASELINE.json configs[1] — two_reservoir, 1,024 synthetic stochastic
-inflow scenarios x 50 years daily (T = 18,262), per GPU (weak scaling: every rank runs its own
-contiguous block of 1,024 scenarios; scenarios never exchange data, so no collective on the data
-path; NCCL is used once after the timed region to gather the per-scenario recorder values).
+Workload (config.workload): BASELINE.json configs[2], the configuration north_star's target is quoted on —
+examples/thames with its 5-member `demand` scenario sliced to [2, 3] and 4,096 synthetic stochastic inflow
+scenarios x 30 years daily (T = 10,957).  Default `--scaling weak`: 4,096 scenarios PER GPU (every rank runs its
+own contiguous block of global scenario ids; scenarios never exchange data, so no collective on the data path;
+NCCL is used once after the timed region to gather the per-scenario recorder values).  `--scaling strong`: 4,096
+scenarios in TOTAL, 4,096 / N per GPU (north_star: "a 4,096-scenario Thames-scale model on one 8 x B200 box");
+under torchrun the default run also measures that split and reports it under "north_star_target".
+`--workload two_reservoir --scenarios 1024` is BASELINE.json configs[1] (reported under "config2" at N = 1).
 
 A "step" is one whole run of the workload: all T timesteps for all scenarios of the rank through the
 device-resident run (parameters -> bounds/costs -> warm-started simplex -> flow commit -> storage mass
@@ -15,8 +19,11 @@ balance -> recorders, one kernel launch).
   value : inputs resident in HBM when the timed region starts (program loaded, inflow table uploaded);
           timed with CUDA events on the engine's stream, max over ranks.
   e2e   : the same run through the C-ABI with HOST buffers (b200lp_run_pipelined): every step uploads the
-          inflow table from pinned host memory, resets, runs and reads every recorder back to the host, the
-          copies overlapped with the solve in 16 time slices; wall clock around the step, max over ranks.
+          inflow table from pinned host memory, resets, runs and reads every recorder's per-scenario result back
+          to the host — the [S] values of the accumulating recorders and, for the array recorders, their temporal
+          aggregates (sum / min / max per scenario = Recorder.values(), accumulated on the device); the copies
+          overlap the solve in 16 time slices; wall clock around the step, max over ranks.  "e2e_full_arrays" is
+          the same with every [T, S] recorder array shipped to the host as well.
 """
 from __future__ import annotations
 
@@ -35,8 +42,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "scenario-timesteps/sec"
 UNIT = "scenario-timesteps/s"
-WORKLOAD = "two_reservoir"
-S_PER_GPU = 1024
+WORKLOAD = "thames"
+S_DEFAULT = {"thames": 4096, "two_reservoir": 1024}
 
 
 def parse_args():
@@ -46,7 +53,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=WORKLOAD)
-    ap.add_argument("--scenarios", type=int, default=S_PER_GPU, help="scenarios per GPU")
+    ap.add_argument("--scenarios", type=int, default=None, help="scenarios per GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--years", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -154,6 +162,119 @@ def run_cpu(s, prog, info, steps, warmup, threads):
 E2E_CHUNKS = int(os.environ.get("B200_BENCH_CHUNKS", "16"))   # time slices of the pipelined end-to-end run
 
 
+def years_of(workload, years):
+    return years or (50 if workload == "two_reservoir" else 30)
+
+
+def workload_text(workload, S, years, scaling, world):
+    per = "per GPU" if scaling == "weak" else f"in total ({S // world} per GPU)"
+    extra = ", `demand` scenario (5 members) sliced to [2, 3]" if workload == "thames" else ""
+    return f"{workload}{extra}: {S} synthetic stochastic inflow scenarios {per} x {years_of(workload, years)} years daily, {scaling} scaling"
+
+
+def traffic_of(workload, S, T):
+    """DRAM bytes per launch of the run kernel from the committed ncu capture of exactly this launch (or None)."""
+    try:
+        entries = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("entries", {})
+        e = entries.get(f"{workload}:{S}:{T}")
+        return (int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])) if e else None
+    except Exception:
+        return None
+
+
+class Bench:
+    """The B200 arm for one (workload, scenarios per rank): program resident on the device, timed runs."""
+
+    def __init__(self, workload, S_rank, years, first_scenario, device):
+        from benchmarks.workloads import load_workload
+        from pywr_b200.engine import CudaEngine
+
+        self.workload, self.S = workload, S_rank
+        self.s, self.prog, self.info = load_workload(workload, S_rank, years=years, first_scenario=first_scenario)
+        self.T = self.info["timesteps"]
+        self.eng = CudaEngine(self.s, S_rank, device=device)
+        self.eng.load_program(self.prog)
+        self.inflow_table = int(np.nonzero(self.prog.table_axis >= 0)[0][0])
+        self.units = S_rank * self.T
+
+    def warm(self, n):
+        for _ in range(n):
+            self.eng.program_reset()
+            self.eng.run(0, self.T)
+        self.eng.sync()
+
+    def timed_runs(self, steps):
+        """kernel time of each of `steps` whole runs (CUDA events on the engine's stream)"""
+        ms = []
+        for _ in range(steps):
+            self.eng.program_reset()      # restores initial volumes / bases / zeroed recorders (not timed)
+            self.eng.mark(0)
+            self.eng.run(0, self.T)
+            self.eng.mark(1)
+            ms.append(self.eng.elapsed_ms())
+        self.eng.sync()
+        return ms
+
+    def e2e_setup(self, full_arrays):
+        from pywr_b200.program import ARRAY_KINDS
+
+        prog, eng, S = self.prog, self.eng, self.S
+        r0, c0 = int(prog.table_rows[self.inflow_table]), int(prog.table_cols[self.inflow_table])
+        if not hasattr(self, "host_in"):
+            self.host_in = eng.alloc_pinned((r0, c0))
+            off = int(prog.table_offset[self.inflow_table])
+            self.host_in[...] = prog.table_data[off: off + r0 * c0].reshape(r0, c0)
+        arrays = [r for r in range(prog.n_recorders) if int(prog.rec_kind[r]) in ARRAY_KINDS]
+        outs = [eng.alloc_pinned(prog.rec_shape(r, S)) if (full_arrays or r not in arrays) else None
+                for r in range(prog.n_recorders)]
+        d2h = sum(a.nbytes for a in outs if a is not None) + (0 if full_arrays else 3 * 8 * S * len(arrays))
+
+        def step():
+            # the call a user makes: host table in, per-scenario recorder results out, time slices pipelined
+            eng.run_pipelined({self.inflow_table: self.host_in}, outs, chunks=E2E_CHUNKS)
+            if not full_arrays:
+                for r in arrays:
+                    eng.fetch_recorder_agg(r)     # (sum, min, max) over time per scenario: Recorder.values()
+        return step, int(self.host_in.nbytes), int(d2h)
+
+    def close(self):
+        self.eng.close()
+
+
+def single_process_run(workload, S_total, years, n_devices, steps):
+    """S_total scenarios over n_devices GPUs driven by ONE process (pywr_b200.engine.ShardedEngine, what
+    run_on_device(model, devices="all") uses): wall clock around reset-excluded runs, synchronised on both sides."""
+    from benchmarks.workloads import load_workload
+    from pywr_b200.engine import ShardedEngine
+
+    s, prog, info = load_workload(workload, S_total, years=years)
+    eng = ShardedEngine(s, S_total, devices=list(range(n_devices)))
+    eng.load_program(prog)
+    T = info["timesteps"]
+    for _ in range(3):
+        eng.program_reset(); eng.run(0, T)
+    eng.sync()
+    times = []
+    for _ in range(steps):
+        eng.program_reset()
+        eng.sync()
+        t0 = time.perf_counter()
+        eng.run(0, T)
+        eng.sync()
+        times.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    outs = [eng.fetch_recorder_agg(r) if prog.rec_shape(r, S_total) != (S_total,) else eng.fetch_recorder(r, (S_total,))
+            for r in range(prog.n_recorders)]
+    readout = time.perf_counter() - t0
+    nfail = eng.program_status()[0]
+    eng.close()
+    del outs
+    return {"workload": workload_text(workload, S_total, years, "strong", n_devices), "value": S_total * T * len(times) / sum(times),
+            "unit": UNIT, "ms_per_step": float(np.mean(times)) * 1e3, "readout_ms": readout * 1e3, "devices": n_devices,
+            "failed_scenarios": nfail, "api": "pywr_b200.engine.ShardedEngine: one host process, one engine per GPU, "
+            "contiguous global_id blocks, per-scenario recorder results gathered into their column blocks; wall clock"}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -161,11 +282,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from benchmarks.workloads import algorithmic_bytes_per_scenario_step, load_workload
 
-    S = args.scenarios
-    config = {"workload": f"{args.workload}: {S} synthetic stochastic inflow scenarios per GPU x "
-                          f"{args.years or 50 if args.workload == 'two_reservoir' else args.years or 30} years daily",
+    S_arg = args.scenarios or S_DEFAULT.get(args.workload, 1024)
+    if args.scaling == "strong" and S_arg % world:
+        raise SystemExit(f"--scaling strong: {S_arg} scenarios do not divide over {world} GPUs")
+    S = S_arg if args.scaling == "weak" else S_arg // world          # scenarios of this rank
+    config = {"workload": workload_text(args.workload, S_arg, args.years, args.scaling, world),
               "scenarios_per_gpu": S, "formulation": "route", "kernel": "register-resident dictionary simplex, "
-              "device-resident run", "l2": "inputs+outputs per step (inflow table + recorder arrays) exceed the 126 MB L2",
+              "device-resident run, run kernel specialised on the model at load (NVRTC)",
+              "l2": "inputs+outputs per step (inflow table + recorder arrays) exceed the 126 MB L2",
               "parallelism": f"scenario-sharded x{world}, no data-path collective"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -173,17 +297,17 @@ def main():
         if rank != 0:
             return 0
         s, prog, info = load_workload(args.workload, S, years=args.years)
-        config.update(timesteps=info["timesteps"], lp_rows=info["rows"], lp_cols=info["cols"])
+        config.update(timesteps=info["timesteps"], lp_rows=info["rows"], lp_cols=info["cols"], recorders=info["n_recorders"])
         cores = cpu_cores()
         value, mean_t, nfail = run_cpu(s, prog, info, args.steps, max(args.warmup, 1), cores)
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"whole workload per step ({S} scenarios x {info['timesteps']} timesteps); "
-                                       "GLPK is not installable in this image, so the CPU arm is the oracle port "
-                                       "(oracle/lp_oracle.c, program mode, pthreads over scenario blocks)"},
+                             "sample": f"one rank's share of the workload per step ({S} scenarios x {info['timesteps']} timesteps) "
+                                       f"on all {cores} host threads; GLPK is not installable in this image, so the CPU arm is "
+                                       "the oracle port (oracle/lp_oracle.c, program mode, pthreads over scenario blocks)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "failed_scenarios": nfail,
         }
@@ -191,8 +315,6 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ B200 arm
-    from pywr_b200.engine import CudaEngine
-
     dist = None
     if world > 1:
         import torch
@@ -216,73 +338,53 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    s, prog, info = load_workload(args.workload, S, years=args.years, first_scenario=rank * S)
-    T = info["timesteps"]
-    config.update(timesteps=T, lp_rows=info["rows"], lp_cols=info["cols"], recorders=info["n_recorders"])
-    eng = CudaEngine(s, S, device=local_rank)
-    eng.load_program(prog)
-    inflow_table = int(np.nonzero(prog.table_axis >= 0)[0][0])
-    units = S * T
+    def measure(workload, S_rank, years, steps, with_e2e, with_full):
+        """value / e2e of one configuration, all ranks together: barrier + sync on both sides, max over ranks"""
+        b = Bench(workload, S_rank, years, rank * S_rank, local_rank)
+        b.warm(max(args.warmup, 3))
+        st0 = b.eng.stats()
+        barrier()
+        t_wall0 = time.perf_counter()
+        kernel_ms = b.timed_runs(steps)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        st1 = b.eng.stats()
+        dev_time = max_over_ranks(sum(kernel_ms) / 1e3)
+        out = {"bench": b, "kernel_ms": kernel_ms, "wall": wall, "window": (t_wall0, t_wall0 + wall), "st0": st0, "st1": st1,
+               "dev_time": dev_time, "value": world * b.units * steps / dev_time, "nfail": b.eng.program_status()[0]}
+        for key, full in (("e2e", False), ("e2e_full_arrays", True)):
+            if not with_e2e or (full and not with_full):
+                out[key] = None
+                continue
+            step, h2d, d2h = b.e2e_setup(full)
+            for _ in range(2):
+                step()
+            b.eng.sync()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            b.eng.sync()
+            barrier()
+            e2e_time = max_over_ranks(time.perf_counter() - t0)
+            what = ("every [T, S] recorder array and every per-scenario value" if full else
+                    "the per-scenario recorder results ([S] accumulators; sum / min / max over time of the array recorders)")
+            out[key] = {"value": world * b.units * steps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_time / steps * 1e3,
+                        "api": f"b200lp_run_pipelined: reset + upload + run + read-out of {what}, {E2E_CHUNKS} time slices on "
+                               "three streams (pinned host buffers)"}
+        return out
 
-    # ---- value: inputs resident in HBM, CUDA events on the engine's stream -------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        eng.program_reset()
-        eng.run(0, T)
-    eng.sync()
-    st0 = eng.stats()
     sampler.wait_first()
-    barrier()
-    kernel_ms = []
-    eng.sync()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.program_reset()           # restores initial volumes / bases / zeroed recorders (not timed below)
-        eng.mark(0)
-        eng.run(0, T)
-        eng.mark(1)
-        kernel_ms.append(eng.elapsed_ms())
-    eng.sync()
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop((t_wall0, t_wall0 + wall))
-    st1 = eng.stats()
-    nfail = eng.program_status()[0]
-    dev_time = max_over_ranks(sum(kernel_ms) / 1e3)
-    value = world * units * args.steps / dev_time
+    m = measure(args.workload, S, args.years, args.steps, not args.no_e2e, True)
+    b = m["bench"]
+    s, prog, info, eng, T, units = b.s, b.prog, b.info, b.eng, b.T, b.units
+    config.update(timesteps=T, lp_rows=info["rows"], lp_cols=info["cols"], recorders=info["n_recorders"])
+    clocks = sampler.stop(m["window"])
+    st0, st1, kernel_ms, value, e2e = m["st0"], m["st1"], m["kernel_ms"], m["value"], m["e2e"]
     launches = int(st1["kernel_launches"] - st0["kernel_launches"])
-
-    # ---- e2e: host buffers in, host buffers out, every step -----------------------------------
-    e2e = None
-    if not args.no_e2e:
-        r0, c0 = int(prog.table_rows[inflow_table]), int(prog.table_cols[inflow_table])
-        host_in = eng.alloc_pinned((r0, c0))
-        off = int(prog.table_offset[inflow_table])
-        host_in[...] = prog.table_data[off: off + r0 * c0].reshape(r0, c0)
-        host_out = [eng.alloc_pinned(prog.rec_shape(r, S)) for r in range(prog.n_recorders)]
-        h2d = host_in.nbytes
-        d2h = sum(a.nbytes for a in host_out)
-
-        def e2e_step():
-            # the call a user makes: host table in, host recorder arrays out, time slices pipelined
-            eng.run_pipelined({inflow_table: host_in}, host_out, chunks=E2E_CHUNKS)
-
-        for _ in range(2):
-            e2e_step()
-        eng.sync()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        eng.sync()
-        barrier()
-        e2e_time = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * units * args.steps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_time / args.steps * 1e3,
-               "api": f"b200lp_run_pipelined: reset + upload + run + read-out of every recorder, {E2E_CHUNKS} time slices on three "
-                      "streams (pinned host buffers)"}
 
     # ---- multi-GPU read-out: NCCL gather of the per-scenario recorder values -----------------
     gather_ms = None
@@ -308,15 +410,10 @@ def main():
     b_alg = algorithmic_bytes_per_scenario_step(info)
     mean_kernel_s = float(np.mean(kernel_ms)) / 1e3
     achieved = b_alg * units / mean_kernel_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("lp_run_kernel_bytes_per_launch")
-        except Exception:
-            traffic = None
+    jit = bool(st1.get("run_kernel_jit"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "lp_run_kernel",
+                "traffic": traffic_of(args.workload, S, T), "peak_source": peak_src,
+                "kernel": "lp_run_jit (run kernel specialised on the model, NVRTC)" if jit else "lp_run_kernel",
                 "algorithmic_bytes_per_scenario_timestep": b_alg, "units_per_launch": units,
                 "note": "the kernel is issue/latency bound (no dense contraction, per-scenario state in registers); "
                         "HBM fraction is reported as the contract asks"}
@@ -329,6 +426,32 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"whole workload once ({S} x {T}); oracle/lp_oracle.c program mode on {cores} threads "
                          "(GLPK is not installable in this image)"}
+    b.close()
+
+    # ---- north_star's target as stated: 4,096 thames scenarios in TOTAL over the GPUs of this run ----
+    target = None
+    if world > 1 and args.scaling == "weak" and args.workload == "thames" and S_arg % world == 0 and not args.no_e2e:
+        mt = measure("thames", S_arg // world, args.years, args.steps, True, False)
+        target = {"workload": workload_text("thames", S_arg, args.years, "strong", world), "value": mt["value"], "unit": UNIT,
+                  "ms_per_step": mt["dev_time"] / args.steps * 1e3, "e2e": mt["e2e"], "failed_scenarios": mt["nfail"]}
+        mt["bench"].close()
+    # ---- the same target through the product's one-process layer: rank 0 drives all GPUs of the run ----
+    single_process = None
+    if world > 1 and target is not None:
+        barrier()
+        if rank == 0:
+            try:
+                single_process = single_process_run("thames", S_arg, args.years, world, args.steps)
+            except Exception as exc:
+                single_process = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+        barrier()
+    # ---- BASELINE.json configs[1] beside it (N = 1 only) ---------------------------------------------
+    config2 = None
+    if world == 1 and args.workload == "thames" and not args.no_e2e:
+        m2 = measure("two_reservoir", S_DEFAULT["two_reservoir"], None, args.steps, True, False)
+        config2 = {"workload": workload_text("two_reservoir", S_DEFAULT["two_reservoir"], None, "weak", 1), "value": m2["value"],
+                   "unit": UNIT, "ms_per_step": m2["dev_time"] / args.steps * 1e3, "e2e": m2["e2e"], "failed_scenarios": m2["nfail"]}
+        m2["bench"].close()
 
     # ---- the same engine driven by the reference framework itself (only where Pywr is importable) ----
     pywr_extra = None
@@ -364,15 +487,17 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_time / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "failed_scenarios": nfail, "wall_ms_per_step_including_reset": wall / args.steps * 1e3,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["dev_time"] / args.steps * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": clocks, "e2e": e2e, "e2e_full_arrays": m["e2e_full_arrays"], "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "failed_scenarios": m["nfail"], "wall_ms_per_step_including_reset": m["wall"] / args.steps * 1e3,
             "pivots_per_scenario_timestep": (st1["pivots"] - st0["pivots"]) / max(1, units * args.steps),
-            "kernel_variant": st1["kernel_variant"], "gather_ms": gather_ms, "through_pywr": pywr_extra,
+            "kernel_variant": st1["kernel_variant"], "run_kernel_jit": jit, "gather_ms": gather_ms,
+            "north_star_target": target, "single_process_multi_gpu": single_process, "config2": config2,
+            "through_pywr": pywr_extra,
         }
         print(json.dumps(line))
-    eng.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -352,6 +352,11 @@ int b200lp_program_status(b200lp_handle *h, int32_t *n_failed, int32_t *scenario
 int b200lp_update_table(b200lp_handle *h, int32_t table, const double *data);
 /* Copy recorder `rec` to the host: [T][S] doubles for the array kinds, [S] for the others. */
 int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out);
+/* The same into a column block of a wider host array: row t of the recorder goes to out[t * ld .. t * ld + S), ld >= S
+ * (one cudaMemcpy2DAsync on b200lp_stream(); NOT synchronised: call b200lp_sync before reading).  This is how a host that
+ * shards one scenario batch over several handles / GPUs assembles the reference's _data[nts, ncomb] layout
+ * (pywr/recorders/_recorders.pyx:574-617) without a staging copy: `out` points at the shard's first column. */
+int b200lp_fetch_recorder_strided(b200lp_handle *h, int32_t rec, double *out, int64_t ld);
 /* Temporal aggregates of array recorder `rec`, accumulated on the device in timestep order while the run writes the
  * array: sum, min and max over the timesteps executed since the last reset, [S] doubles each (any pointer may be NULL).
  * The caller derives Recorder.values() for the recorder's temporal agg_func: "sum", "min", "max", "mean" = sum / T

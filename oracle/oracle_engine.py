@@ -152,7 +152,8 @@ class OracleEngine:
     def fetch_recorder_agg(self, r):
         """(sum, min, max) over the timesteps of array recorder ``r`` (the CUDA engine accumulates them on the device)."""
         a = self.fetch_recorder(r, (self._prog.n_steps, self.S))
-        return a.sum(axis=0), a.min(axis=0), a.max(axis=0)
+        # cumsum adds the rows one after the other, like the device (np.sum may reorder / pair the additions)
+        return np.cumsum(a, axis=0)[-1], a.min(axis=0), a.max(axis=0)
 
     def fetch_state(self):
         s = self.structure

@@ -112,6 +112,37 @@ def set_array_recorder(rec, double[:, :] data):
         raise TypeError(f"unsupported recorder {type(rec).__name__}")
 
 
+def temporal_agg_func(rec):
+    """The temporal aggregation function of a NumpyArray recorder (its `temporal_agg_func` property is write-only,
+    pywr/recorders/_recorders.pyx:607-609,1114-1116): a name, or the user's callable."""
+    cdef NumpyArrayNodeRecorder nr
+    cdef NumpyArrayAbstractStorageRecorder sr
+    if isinstance(rec, NumpyArrayNodeRecorder):
+        nr = rec
+        return nr._temporal_aggregator.func
+    if isinstance(rec, NumpyArrayAbstractStorageRecorder):
+        sr = rec
+        return sr._temporal_aggregator.func
+    return None
+
+
+def replace_array_recorder(rec, double[:, :] data):
+    """rec._data = data: the recorder's array becomes `data` itself (any number of rows).  Used when a device run keeps
+    the [T, S] arrays on the device: `data` is then ONE row holding the recorder's temporal aggregate per scenario, of which
+    `values()` = aggregate_2d(_data, axis=0) (pywr/recorders/_recorders.pyx:630-633) is that same row for the sum / mean /
+    min / max aggregation functions."""
+    cdef NumpyArrayNodeRecorder nr
+    cdef NumpyArrayAbstractStorageRecorder sr
+    if isinstance(rec, NumpyArrayNodeRecorder):
+        nr = rec
+        nr._data = data
+    elif isinstance(rec, NumpyArrayAbstractStorageRecorder):
+        sr = rec
+        sr._data = data
+    else:
+        raise TypeError(f"unsupported recorder {type(rec).__name__}")
+
+
 def set_constant_recorder(rec, double[:] values):
     """rec._values[:] = values for the one-value-per-scenario recorder families."""
     cdef BaseConstantNodeRecorder nr

@@ -327,6 +327,13 @@ int b200lp_create_ex(const b200lp_structure *s, int32_t n_scenarios, int32_t dev
     int variant = -1;
     for (int v = 0; v < kNumVariants; v++)
         if (m <= kVariants[v].G * kVariants[v].RPL && n <= kVariants[v].NC) { variant = v; break; }
+    // Small batches are latency bound (one dependent chain per scenario and timestep): a whole warp per scenario keeps a
+    // scenario that pivots from stalling the one it would share a warp with.  Measured on B200 (thames, specialised run
+    // kernel, M scenario-timesteps/s, 16 / 32 lanes per scenario): 512 scenarios 403 / 629, 1,024: 807 / 1,108, 2,048: 1,475 /
+    // 1,584, 4,096: 2,317 / 1,800 (profiles/r2_sweep_variants.log).
+    if (variant >= 0 && kVariants[variant].RPL == 1 && kVariants[variant].G < 32 && n_scenarios <= 2048)
+        for (int v = 0; v < kNumVariants; v++)
+            if (kVariants[v].G == 32 && kVariants[v].RPL == 1 && m <= 32 && n <= kVariants[v].NC) { variant = v; break; }
     if (const char *force = getenv("B200LP_VARIANT")) {
         int v = atoi(force);
         if (v >= 0 && v < kNumVariants && m <= kVariants[v].G * kVariants[v].RPL && n <= kVariants[v].NC) variant = v;
@@ -1388,6 +1395,19 @@ int b200lp_fetch_recorder(b200lp_handle *h, int32_t rec, double *out) {
     CUDA_TRY(cudaMemcpyAsync(out, h->rec_ptr[rec], sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->stats.d2h_bytes += (double)count * 8.0;
+    return B200LP_OK;
+}
+
+int b200lp_fetch_recorder_strided(b200lp_handle *h, int32_t rec, double *out, int64_t ld) {
+    if (!h || !h->has_program || !out) return fail(B200LP_E_INVALID, "no program loaded / null output");
+    if (rec < 0 || rec >= (int)h->rec_ptr.size()) return fail(B200LP_E_INVALID, "recorder index out of range");
+    if (ld < h->S) return fail(B200LP_E_INVALID, "leading dimension smaller than the scenario count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->rec_ptr[rec]) return fail(B200LP_E_UNSUPPORTED, "the program was loaded with B200LP_PROG_AGG_ONLY: this array recorder keeps aggregates only");
+    const size_t rows = rec_is_array(h->rec_kind[rec]) ? (size_t)h->prog_steps : 1, S = (size_t)h->S;
+    CUDA_TRY(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)ld, h->rec_ptr[rec], sizeof(double) * S, sizeof(double) * S, rows,
+                               cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (double)(rows * S) * 8.0;
     return B200LP_OK;
 }
 

@@ -14,15 +14,72 @@ import time
 
 import numpy as np
 
-from .program import ARRAY_KINDS, Unsupported, _flow_form, compile_program
+from .program import ARRAY_KINDS, PROG_AGG_ONLY, Unsupported, _flow_form, compile_program
+
+# temporal aggregation functions the device accumulates while it writes an array recorder (b200lp_fetch_recorder_agg)
+DEVICE_TEMPORAL_AGGS = ("sum", "mean", "min", "max")
 
 
 class DeviceRunResult(dict):
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def close(self):
+        """Releases the engine a run with ``arrays="lazy"`` keeps for later array fetches."""
+        rec = self.get("recorders")
+        if isinstance(rec, LazyRecorders):
+            rec.close()
+
+
+class LazyRecorders(dict):
+    """Recorder results of a run with ``arrays="lazy"``: per-scenario values are here already; the [T, S] array of an
+    array recorder is copied from the device when :meth:`data` asks for it (and cached)."""
+
+    def __init__(self, eng, prog, S):
+        super().__init__()
+        self._eng, self._prog, self._S, self._arrays = eng, prog, S, {}
+        self._index = {rec.name: r for r, rec in enumerate(prog.recorders)}
+
+    def data(self, name):
+        r = self._index[name]
+        if int(self._prog.rec_kind[r]) not in ARRAY_KINDS:
+            return self[name]
+        if name not in self._arrays:
+            if self._eng is None:
+                raise RuntimeError("the device run's engine has been closed")
+            self._arrays[name] = self._eng.fetch_recorder(r, self._prog.rec_shape(r, self._S))
+        return self._arrays[name]
+
+    def close(self):
+        if self._eng is not None:
+            self._eng.close()
+            self._eng = None
+
+
+def temporal_aggregate(rec, T, ssum, smin, smax):
+    """Recorder.values() of an array recorder from the device's running aggregates, or None when its temporal
+    aggregation needs the array itself (median, percentiles, custom callables, ignore_nan)."""
+    func = device_temporal_agg(rec)
+    if func is None:
+        return None
+    return {"sum": ssum, "mean": ssum / T, "min": smin, "max": smax}[func]
+
+
+def device_temporal_agg(rec):
+    """"sum" / "mean" / "min" / "max" when the device's running aggregates give this recorder's values(), else None."""
+    from .bridge import _bridge
+
+    func = _bridge.temporal_agg_func(rec)
+    if not isinstance(func, str) or func.lower() not in DEVICE_TEMPORAL_AGGS or getattr(rec, "ignore_nan", False):
+        return None
+    return func.lower()
 
 
 def run_on_device(model, engine_factory=None, formulation="route", chunk=None, writeback=True, threads=None,
-                  host_mirror=True):
+                  host_mirror=True, devices=None, arrays="eager"):
     """Returns a :class:`DeviceRunResult` (timings, counters, speed in scenario-timesteps/s).
 
     ``engine_factory(structure, n_scenarios)`` defaults to the CUDA engine.  Raises
@@ -35,7 +92,20 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
     the run proceeds one timestep per launch and, after each, the node flows and storage volumes are
     copied back into Pywr's objects (``_flow``, ``_volume``, ``_current_pc``) so that
     ``Model.before()`` (host copies of the parameters) and the recorders' ``after()`` see exactly the
-    state of a host run; models without them pay nothing."""
+    state of a host run; models without them pay nothing.
+
+    ``devices``: ``None`` = one GPU (``LOCAL_RANK``); ``"all"``, a count or a list of CUDA device indices = the scenario
+    batch is cut into contiguous ``global_id`` blocks, one per GPU, all driven by this process
+    (:class:`pywr_b200.engine.ShardedEngine`); results are identical to the one-GPU run.
+
+    ``arrays``: what happens to the ``[T, S]`` arrays of the NumpyArray recorders —
+    ``"eager"`` (default) copies them into the recorder objects like a host run;
+    ``"lazy"`` leaves them on the device: the recorder objects receive ONE row, their temporal aggregate per scenario
+    (accumulated on the device), so ``values()`` / ``aggregated_value()`` are unchanged, and ``result.recorders.data(name)``
+    fetches an array when it is wanted (call ``result.close()`` afterwards);
+    ``"none"`` does not even store them (``B200LP_PROG_AGG_ONLY``): objectives of optimisation batches and ensembles.
+    With ``"lazy"`` / ``"none"`` an array recorder whose temporal aggregation is not sum / mean / min / max (or that
+    ignores NaNs) is fetched eagerly / raises :class:`Unsupported`."""
     from .bridge import _bridge
 
     t0 = time.perf_counter()
@@ -44,15 +114,27 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
     else:
         model.reset()
     t1 = time.perf_counter()
+    if arrays not in ("eager", "lazy", "none"):
+        raise ValueError("arrays must be 'eager', 'lazy' or 'none'")
     s, prog = compile_program(model, formulation, allow_host_recorders=host_mirror)
     S, T = len(model.scenarios.combinations), prog.n_steps
     host_recs = list(prog.host_recorders)
+    if arrays == "none":
+        for r, rec in enumerate(prog.recorders):
+            if int(prog.rec_kind[r]) in ARRAY_KINDS and device_temporal_agg(rec) is None:
+                raise Unsupported(f"arrays='none': recorder {rec.name!r} aggregates over time with "
+                                  f"{_bridge.temporal_agg_func(rec)!r}" + (" ignoring NaNs" if rec.ignore_nan else "") +
+                                  ", which needs the array")
+        prog.flags |= PROG_AGG_ONLY
     if engine_factory is None:
-        from .engine import CudaEngine
+        from .engine import CudaEngine, ShardedEngine
 
         def engine_factory(structure, n_scenarios):
+            if devices is not None:
+                return ShardedEngine(structure, n_scenarios, devices=devices, for_program=True)
             return CudaEngine(structure, n_scenarios, for_program=True)
     eng = engine_factory(s, S)
+    keep_engine = False
     try:
         eng.load_program(prog)
         t2 = time.perf_counter()
@@ -73,12 +155,21 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
             raise RuntimeError('Simplex solver failed with message: "{}", status: "{}" '
                                "(scenario {}, timestep {}; {} scenario(s) failed).".format(
                                    _STATUS_TEXT.get(code, "solver failed"), "solution is undefined", scen, tstep, n_failed))
-        results = {}
+        results = {} if arrays != "lazy" else LazyRecorders(eng, prog, S)
+        keep_engine = arrays == "lazy"
         for r, rec in enumerate(prog.recorders):
+            is_array = int(prog.rec_kind[r]) in ARRAY_KINDS
+            if is_array and arrays != "eager":
+                row = temporal_aggregate(rec, T, *eng.fetch_recorder_agg(r))
+                if row is not None:
+                    results[rec.name] = row
+                    if writeback:
+                        _bridge.replace_array_recorder(rec, np.ascontiguousarray(row[None, :]))
+                    continue
             out = eng.fetch_recorder(r, prog.rec_shape(r, S))
             results[rec.name] = out
             if writeback:
-                if int(prog.rec_kind[r]) in ARRAY_KINDS:
+                if is_array:
                     _bridge.set_array_recorder(rec, out)
                 else:
                     _bridge.set_constant_recorder(rec, out)
@@ -109,8 +200,12 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
             counters = dict(counters, kernel_variant=eng.stats().get("kernel_variant"))
         except Exception:   # engines without stats() (test doubles)
             pass
+    except BaseException:
+        keep_engine = False
+        raise
     finally:
-        eng.close()
+        if not keep_engine:
+            eng.close()
     return DeviceRunResult(
         num_scenarios=S, timesteps=T, time_setup=t1 - t0, time_compile=t2 - t1, time_run=t3 - t2,
         time_readout=t4 - t3, speed=S * T / (t3 - t2) if t3 > t2 else float("nan"), recorders=results,

@@ -69,6 +69,7 @@ SYMBOLS = [
     ("b200lp_mark", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     ("b200lp_elapsed_ms", ctypes.c_int, [ctypes.c_void_p, _dp]),
     ("b200lp_fetch_recorder", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp]),
+    ("b200lp_fetch_recorder_strided", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]),
     ("b200lp_fetch_recorder_agg", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, _dp, _dp, _dp]),
     ("b200lp_recorder_device_ptr", ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
     ("b200lp_fetch_state", ctypes.c_int, [ctypes.c_void_p, _dp, _dp, _dp]),
@@ -248,6 +249,14 @@ class CudaEngine:
         _check(self.L, self.L.b200lp_fetch_recorder(self.h, int(r), _ptr(out)), "b200lp_fetch_recorder")
         return out
 
+    def fetch_recorder_into(self, r, out, col0):
+        """Queues the copy of recorder ``r`` into columns [col0, col0 + S) of the C-contiguous host array ``out``
+        ([T, S_total] or [S_total]); asynchronous: ``sync()`` before reading."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        ld = out.shape[-1]
+        _check(self.L, self.L.b200lp_fetch_recorder_strided(self.h, int(r), out.ctypes.data + 8 * int(col0), int(ld)),
+               "b200lp_fetch_recorder_strided")
+
     def fetch_recorder_agg(self, r):
         """(sum, min, max) over the executed timesteps of array recorder ``r``, [S] each, accumulated on the device."""
         out = np.zeros((3, self.S), dtype=np.float64)
@@ -302,3 +311,128 @@ class CudaEngine:
             self.close()
         except Exception:
             pass
+
+
+def scenario_blocks(n_scenarios, n_shards):
+    """Contiguous blocks of ``global_id`` (pywr/_core.pyx:210-240), sizes differing by at most one."""
+    base, extra = divmod(int(n_scenarios), int(n_shards))
+    out, lo = [], 0
+    for k in range(n_shards):
+        hi = lo + base + (1 if k < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return [b for b in out if b[1] > b[0]]
+
+
+class ShardedEngine:
+    """One scenario batch over several engines — one per GPU of the box — driven by ONE host process
+    (the ``devices`` of the boundary).  Scenarios are independent (cython_glpk.pyx:827-828), so the
+    batch is cut into contiguous ``global_id`` blocks; every call fans out to the shards (their work is queued on
+    per-device streams and runs concurrently), read-outs land in the right column block of the reference's
+    ``[T, ncomb]`` / ``[ncomb]`` layout.  No data-path collective exists or is needed.
+
+    ``devices``: ``"all"``, a count, or a list of CUDA device indices (a device may appear more than once: several
+    handles on one GPU); ``factory(structure, n, device)`` builds one shard engine (default: :class:`CudaEngine`)."""
+
+    def __init__(self, structure, n_scenarios, devices="all", for_program=False, factory=None):
+        self.structure, self.S = structure, int(n_scenarios)
+        if factory is None:
+            L = load_library()
+            if devices == "all":
+                devices = list(range(max(L.b200lp_device_count(), 1)))
+
+            def factory(s, n, device):
+                return CudaEngine(s, n, device=device, for_program=for_program)
+        if isinstance(devices, int):
+            devices = list(range(devices))
+        if devices == "all":
+            raise ValueError("devices='all' needs the CUDA engine (no factory given)")
+        devices = list(devices)[: self.S]
+        self.blocks = scenario_blocks(self.S, len(devices))
+        self.shards = []
+        try:
+            for (lo, hi), d in zip(self.blocks, devices):
+                self.shards.append(factory(structure, hi - lo, d))
+        except Exception:
+            self.close()
+            raise
+        self.devices = devices[: len(self.shards)]
+
+    # -- device-resident run ---------------------------------------------------------------------
+    def load_program(self, prog):
+        self._prog = prog
+        for (lo, hi), e in zip(self.blocks, self.shards):
+            e.load_program(prog.shard(lo, hi, self.S))
+
+    def program_reset(self):
+        for e in self.shards:
+            e.program_reset()
+
+    def run(self, t0, n):
+        for e in self.shards:     # asynchronous launches: the shards run concurrently
+            e.run(t0, n)
+        return 0
+
+    def sync(self):
+        for e in self.shards:
+            e.sync()
+
+    def program_status(self):
+        n_failed, first = 0, (-1, 0, -1)
+        for (lo, _), e in zip(self.blocks, self.shards):
+            n, scen, code, ts = e.program_status()
+            n_failed += n
+            if n and first[0] < 0:
+                first = (lo + scen, code, ts)
+        return (n_failed,) + first
+
+    def fetch_recorder(self, r, shape, out=None):
+        if out is None:
+            out = np.zeros(shape, dtype=np.float64)
+        for (lo, _), e in zip(self.blocks, self.shards):
+            if hasattr(e, "fetch_recorder_into"):
+                e.fetch_recorder_into(r, out, lo)
+            else:                                   # engines without the strided copy (test doubles, oracle)
+                part = e.fetch_recorder(r, shape[:-1] + (e.S,))
+                out[..., lo: lo + e.S] = part
+        self.sync()
+        return out
+
+    def fetch_recorder_agg(self, r):
+        out = np.zeros((3, self.S))
+        for (lo, hi), e in zip(self.blocks, self.shards):
+            a, b, c = e.fetch_recorder_agg(r)
+            out[0, lo:hi], out[1, lo:hi], out[2, lo:hi] = a, b, c
+        return out[0], out[1], out[2]
+
+    def fetch_state(self):
+        parts = [e.fetch_state() for e in self.shards]
+        return tuple(np.concatenate([p[k] for p in parts], axis=1) for k in range(3))
+
+    def update_table(self, table, data):
+        from .program import COL_SCENARIO
+
+        per_scenario = int(self._prog.table_axis[table]) == COL_SCENARIO
+        for (lo, hi), e in zip(self.blocks, self.shards):
+            e.update_table(table, np.ascontiguousarray(data[:, lo:hi]) if per_scenario else data)
+
+    def stats(self):
+        out = None
+        for e in self.shards:
+            st = e.stats()
+            if out is None:
+                out = dict(st)
+            else:
+                for k in ("scenario_steps", "pivots", "refactors", "kernel_launches", "h2d_bytes", "d2h_bytes", "pdhg_iterations"):
+                    if k in out:
+                        out[k] += st[k]
+        return out
+
+    def counters(self):
+        c = [e.counters() for e in self.shards]
+        return {"pivots": sum(x["pivots"] for x in c), "refactors": sum(x["refactors"] for x in c), "steps": c[0]["steps"]}
+
+    def close(self):
+        for e in getattr(self, "shards", []):
+            e.close()
+        self.shards = []

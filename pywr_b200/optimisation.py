@@ -46,6 +46,16 @@ class PopulationEvaluator:
         missing = [v.name for v in self.variables if id(v) not in self.program.variable_tables]
         if missing:
             raise Unsupported(f"variable parameters {missing} do not feed the LP or a device recorder")
+        # objectives need Recorder.values() only: when every array recorder aggregates over time with sum / mean / min /
+        # max the device keeps those aggregates and the [T, S] arrays are neither stored nor shipped (B200LP_PROG_AGG_ONLY)
+        from .device_run import temporal_aggregate
+        from .program import PROG_AGG_ONLY
+
+        dummy = np.zeros(1)
+        self._agg_only = all(int(k) not in ARRAY_KINDS or temporal_aggregate(rec, 1, dummy, dummy, dummy) is not None
+                             for k, rec in zip(self.program.rec_kind, self.program.recorders))
+        if self._agg_only:
+            self.program.flags |= PROG_AGG_ONLY
         self.S = len(model.scenarios.combinations)
         self.member = np.array([np.asarray(si.indices)[self.axis] for si in model.scenarios.combinations])
         if engine_factory is None:
@@ -87,7 +97,13 @@ class PopulationEvaluator:
         if n_failed:
             raise RuntimeError(f"{n_failed} scenario(s) failed; first: scenario {scen} (candidate {self.member[scen]}), "
                                f"status {code}, timestep {tstep}")
+        from .device_run import temporal_aggregate
+
         for r, rec in enumerate(prog.recorders):
+            if int(prog.rec_kind[r]) in ARRAY_KINDS and self._agg_only:
+                row = temporal_aggregate(rec, T, *eng.fetch_recorder_agg(r))
+                self._bridge.replace_array_recorder(rec, np.ascontiguousarray(row[None, :]))
+                continue
             out = eng.fetch_recorder(r, prog.rec_shape(r, self.S))
             if int(prog.rec_kind[r]) in ARRAY_KINDS:
                 self._bridge.set_array_recorder(rec, out)

@@ -144,6 +144,35 @@ class Program:
         cp._keepalive = keep
         return cp
 
+    def shard(self, lo, hi, S):
+        """The program of scenarios [lo, hi) of a batch of S (contiguous ``global_id`` block, pywr/_core.pyx:210-240):
+        per-scenario tables keep their columns lo..hi-1, scenario indices and initial states are sliced; tables
+        indexed by a scenario axis' members, ops and recorders are shared.  Scenarios are independent
+        (cython_glpk.pyx:827-828), so running the shards on different devices is the same computation."""
+        import copy
+
+        q = copy.copy(self)
+        n = hi - lo
+        rows, cols, offs, chunks, pos = [], [], [], [], 0
+        for t in range(self.n_tables):
+            r0, c0 = int(self.table_rows[t]), int(self.table_cols[t])
+            data = self.table_data[int(self.table_offset[t]): int(self.table_offset[t]) + r0 * c0].reshape(r0, c0)
+            if int(self.table_axis[t]) == COL_SCENARIO:
+                data = data[:, lo:hi]
+            rows.append(data.shape[0]); cols.append(data.shape[1]); offs.append(pos)
+            chunks.append(np.ascontiguousarray(data).reshape(-1)); pos += data.size
+        q.table_rows, q.table_cols = np.array(rows, np.int32), np.array(cols, np.int32)
+        q.table_offset = np.array(offs, np.int64)
+        q.table_data = np.concatenate(chunks) if chunks else np.zeros(0)
+        if self.n_axes > 0:
+            q.scen_index = np.ascontiguousarray(np.asarray(self.scen_index, np.int32).reshape(self.n_axes, S)[:, lo:hi]).reshape(-1)
+        nst = max(len(self.stflow_indptr) - 1, 0)
+        if nst > 0:
+            q.initial_volume = np.ascontiguousarray(np.asarray(self.initial_volume).reshape(nst, S)[:, lo:hi]).reshape(-1)
+            q.initial_pc = np.ascontiguousarray(np.asarray(self.initial_pc).reshape(nst, S)[:, lo:hi]).reshape(-1)
+        assert q.initial_volume.size == nst * n
+        return q
+
     def save(self, path):
         data = {name: np.asarray(getattr(self, name)) for name in _P_I32 + _P_I64 + _P_F64}
         data["meta"] = np.array([self.n_steps, self.n_axes], np.int64)

@@ -146,3 +146,31 @@ def test_specialised_run_kernel_equals_generic_run_kernel(monkeypatch, name, S, 
         assert _rel(y, z) <= 1e-9, nm
     for x, y in zip(a[2], b[2]):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,S,seed", [("two_reservoir.route", 301, 41), ("thames.route", 1000, 42), ("rolling_virtual_storage_long.route", 17, 43)])
+def test_sharded_cuda_engines_equal_one_engine(name, S, seed):
+    """One host process, several engines (pywr_b200.engine.ShardedEngine): contiguous global_id blocks, one per GPU of the
+    box — on a one-GPU box three handles on the same device.  Recorder arrays land in their column blocks through
+    b200lp_fetch_recorder_strided; everything is bit-identical to the single engine."""
+    from pywr_b200.engine import CudaEngine, ShardedEngine, load_library
+
+    s, prog, _, names = load_program_case(name)
+    q = widen_program(s, prog, S, seed)
+    ndev = load_library().b200lp_device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    one = CudaEngine(s, S, device=0)
+    many = ShardedEngine(s, S, devices=devices)
+    o1, st1, x1 = run_program(one, q)
+    o2, st2, x2 = run_program(many, q, chunks=[9, 77])
+    assert st1 == st2
+    for a, b, nm in zip(o1, o2, names):
+        assert np.array_equal(a, b, equal_nan=True), nm
+    for a, b in zip(x1, x2):
+        assert np.array_equal(a, b, equal_nan=True)
+    for r in range(q.n_recorders):
+        if q.rec_shape(r, S) != (S,):
+            for a, b in zip(one.fetch_recorder_agg(r), many.fetch_recorder_agg(r)):
+                assert np.array_equal(a, b, equal_nan=True)
+    assert many.counters()["pivots"] == one.counters()["pivots"]
+    one.close(); many.close()

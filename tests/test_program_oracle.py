@@ -134,3 +134,60 @@ def test_host_mirror_protocol_keeps_host_recorders_alive():
     m3, _, _ = make()
     with pytest.raises(Unsupported):
         run_on_device(m3, engine_factory=OracleEngine, host_mirror=False)
+
+
+@pytest.mark.parametrize("arrays", ["lazy", "none"])
+def test_run_on_device_without_shipping_arrays(arrays):
+    """arrays="lazy" / "none": the [T, S] arrays stay on (or never exist on) the device; Recorder.values() and
+    aggregated_value() come from the temporal aggregates accumulated during the run and equal the host run's
+    (pywr/recorders/_recorders.pyx:109-184,630-633); "lazy" still hands out any array on request."""
+    pytest.importorskip("pywr")
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.recorders import MeanFlowNodeRecorder, NumpyArrayNodeRecorder, NumpyArrayStorageRecorder
+    from pywr_b200.device_run import run_on_device
+    from pywr_b200.engine import ShardedEngine
+    from pywr_b200.program import Unsupported
+
+    def make(extra=None):
+        m = Model.load(path, solver="oracle")
+        m.timestepper.end = "2100-12-31"
+        recs = [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], temporal_agg_func="min", name="vmin"),
+                NumpyArrayNodeRecorder(m, m.nodes["demand1"], temporal_agg_func="mean", agg_func="max", name="supply"),
+                NumpyArrayNodeRecorder(m, m.nodes["demand1"], temporal_agg_func="sum", name="total"),
+                NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], temporal_agg_func="max", name="vmax"),
+                MeanFlowNodeRecorder(m, m.nodes["demand1"], name="mf")]
+        if extra:
+            recs.append(NumpyArrayNodeRecorder(m, m.nodes["demand1"], temporal_agg_func=extra, name="extra"))
+        return m, recs
+    m1, r1 = make(); m1.run()
+    # ... and through the one-process multi-device layer (two shards of the 5 scenarios)
+    factory = lambda s, S: ShardedEngine(s, S, devices=2, factory=lambda st, n, d: OracleEngine(st, n, threads=1))  # noqa: E731
+    for fac in (OracleEngine, factory):
+        m2, r2 = make(); res = run_on_device(m2, engine_factory=fac, arrays=arrays)
+        for a, b in zip(r1, r2):
+            assert _rel(np.array(b.values()), np.array(a.values())) <= 1e-12, a.name
+            assert abs(b.aggregated_value() - a.aggregated_value()) <= 1e-12 * max(1.0, abs(a.aggregated_value())), a.name
+        assert np.asarray(r2[0].data).shape == (1, 5)          # one row: the temporal aggregate
+        if arrays == "lazy":
+            assert _rel(res.recorders.data("supply"), np.array(r1[1].data)) <= 1e-12
+            assert np.array_equal(res.recorders.data("mf"), res.recorders["mf"])
+            res.close()
+            with pytest.raises(RuntimeError):
+                res.recorders.data("vmin")
+    # a temporal aggregation the device does not accumulate: fetched eagerly ("lazy") / refused ("none")
+    m3, r3 = make("median")
+    if arrays == "none":
+        with pytest.raises(Unsupported):
+            run_on_device(m3, engine_factory=OracleEngine, arrays=arrays)
+    else:
+        m4, r4 = make("median"); m4.run()
+        res = run_on_device(m3, engine_factory=OracleEngine, arrays=arrays)
+        assert np.asarray(r3[-1].data).shape == (365, 5)
+        assert _rel(np.array(r3[-1].values()), np.array(r4[-1].values())) <= 1e-12
+        res.close()
