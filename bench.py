@@ -324,6 +324,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier: waiting ranks must not keep a kernel spinning
 
     def barrier():
         if dist is not None:
@@ -438,13 +439,16 @@ def main():
     # ---- the same target through the product's one-process layer: rank 0 drives all GPUs of the run ----
     single_process = None
     if world > 1 and target is not None:
-        barrier()
+        import torch
+
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 single_process = single_process_run("thames", S_arg, args.years, world, args.steps)
             except Exception as exc:
                 single_process = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
-        barrier()
+        dist.barrier(group=cpu_group)
     # ---- BASELINE.json configs[1] beside it (N = 1 only) ---------------------------------------------
     config2 = None
     if world == 1 and args.workload == "thames" and not args.no_e2e:
