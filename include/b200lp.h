@@ -240,6 +240,13 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
                                      flag 1: volume = max_volume, pc = max_volume / max_volume;  flag 2: volume and pc =
                                      the initial ones;  0: nothing.  The op's slot receives the flag.                 */
 
+#define B200LP_OP_CC_INTERP 11     /* args: storage, n, curve_ref*n, value_ref*(n+2).  ControlCurveInterpolatedParameter.value
+                                     (_control_curves.pyx:176-216): linear interpolation between the values at 100 %, at each
+                                     control curve and at 0 %; two coinciding levels return the lower level's value           */
+#define B200LP_OP_CC_PIECEWISE 12  /* args: storage, n, curve_ref*n, upper_value_ref*(n+1), lower_value_ref*(n+1), minimum_ref,
+                                     maximum_ref.  ControlCurvePiecewiseInterpolatedParameter.value (:269-292): within the band
+                                     the storage is in, interpolation between that band's own pair of values (_interpolate, :10-24) */
+
 #define B200LP_AGG_SUM 0
 #define B200LP_AGG_PRODUCT 1
 #define B200LP_AGG_MIN 2

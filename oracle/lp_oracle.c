@@ -899,6 +899,46 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_CC_INTERP: {  /* ControlCurveInterpolatedParameter.value, _control_curves.pyx:176-216 */
+            const int32_t cnt = a[1];
+            const int32_t *cv = a + 2, *vv = a + 2 + cnt;
+            const double pc = clamp_pc(c->pc[a[0]]);
+            double cc_prev = 1.0;
+            int done = 0;
+            for (int i = 0; i < cnt && !done; i++) {
+                const double cc = pref(h, cv[i], p);
+                if (pc >= cc) {
+                    const double den = cc_prev - cc;
+                    if (den == 0.0) v = pref(h, vv[i + 1], p);   /* ZeroDivisionError branch */
+                    else { const double w = (pc - cc) / den; v = pref(h, vv[i], p) * w + pref(h, vv[i + 1], p) * (1.0 - w); }
+                    done = 1;
+                }
+                cc_prev = cc;
+            }
+            if (!done) {
+                const double den = cc_prev - 0.0;
+                if (den == 0.0) v = pref(h, vv[cnt], p);
+                else { const double w = (pc - 0.0) / den; v = pref(h, vv[cnt], p) * w + pref(h, vv[cnt + 1], p) * (1.0 - w); }
+            }
+        } break;
+        case B200LP_OP_CC_PIECEWISE: {  /* ControlCurvePiecewiseInterpolatedParameter.value, :269-292 and _interpolate :10-24 */
+            const int32_t cnt = a[1];
+            const int32_t *cv = a + 2, *up = a + 2 + cnt, *lw = a + 2 + cnt + (cnt + 1);
+            const double mn = pref(h, a[2 + cnt + 2 * (cnt + 1)], p), mx = pref(h, a[3 + cnt + 2 * (cnt + 1)], p);
+            const double pc = clamp_pc(c->pc[a[0]]);
+            double cc_prev = mx, lb = mn;
+            int32_t band = cnt;
+            for (int i = 0; i < cnt; i++) {
+                const double cc = pref(h, cv[i], p);
+                if (pc >= cc) { band = i; lb = cc; break; }
+                cc_prev = cc;
+            }
+            const double ub = cc_prev, lv = pref(h, lw[band], p), uv = pref(h, up[band], p);
+            if (pc < lb) v = lv;
+            else if (pc > ub) v = uv;
+            else if (ub == lb) v = lv;
+            else { const double f = (pc - lb) / (ub - lb); v = lv + (uv - lv) * f; }
+        } break;
         case B200LP_OP_STORAGE_RESET: {  /* node.before(): Storage._reset_storage_only, pywr/_core.pyx:1294-1333 */
             const int32_t q = a[0];
             v = pref(h, a[1], p);

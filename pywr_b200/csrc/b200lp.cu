@@ -814,6 +814,14 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             ok = na >= 2 && a[0] >= 0 && a[0] < nstor && a[1] >= 0;
             if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, a[1]); }
             break;
+        case B200LP_OP_CC_INTERP:
+            ok = na >= 2 && a[0] >= 0 && a[0] < nstor && a[1] >= 0;
+            if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, 2 * a[1] + 2); }
+            break;
+        case B200LP_OP_CC_PIECEWISE:
+            ok = na >= 2 && a[0] >= 0 && a[0] < nstor && a[1] >= 0;
+            if (ok) { out.push_back(a[0]); out.push_back(a[1]); ok = refs(2, 3 * a[1] + 4); }
+            break;
         case B200LP_OP_INDEXED:
             ok = na >= 2 && a[1] >= 1 && ref_ok(a[0]);
             if (ok) { out.push_back(vidx(a[0])); out.push_back(a[1]); ok = refs(2, a[1]); }

@@ -1020,6 +1020,46 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
         case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
+        case B200LP_OP_CC_INTERP: {  // ControlCurveInterpolatedParameter.value (_control_curves.pyx:176-216)
+            const int cnt = a[1];
+            const int *cv = a + 2, *vv = a + 2 + cnt;
+            const double c = clamp_pc(V[pc_base + a[0]]);
+            double cc_prev = 1.0;
+            bool done = false;
+            for (int i = 0; i < cnt && !done; i++) {
+                const double cc = V[cv[i]];
+                if (c >= cc) {
+                    const double den = cc_prev - cc;
+                    if (den == 0.0) v = V[vv[i + 1]];
+                    else { const double w = (c - cc) / den; v = V[vv[i]] * w + V[vv[i + 1]] * (1.0 - w); }
+                    done = true;
+                }
+                cc_prev = cc;
+            }
+            if (!done) {
+                const double den = cc_prev - 0.0;
+                if (den == 0.0) v = V[vv[cnt]];
+                else { const double w = (c - 0.0) / den; v = V[vv[cnt]] * w + V[vv[cnt + 1]] * (1.0 - w); }
+            }
+        } break;
+        case B200LP_OP_CC_PIECEWISE: {  // ControlCurvePiecewiseInterpolatedParameter.value (:269-292, _interpolate :10-24)
+            const int cnt = a[1];
+            const int *cv = a + 2, *up = a + 2 + cnt, *lw = a + 2 + cnt + (cnt + 1);
+            const double mn = V[a[2 + cnt + 2 * (cnt + 1)]], mx = V[a[3 + cnt + 2 * (cnt + 1)]];
+            const double c = clamp_pc(V[pc_base + a[0]]);
+            double cc_prev = mx, lb = mn;
+            int band = cnt;
+            for (int i = 0; i < cnt; i++) {
+                const double cc = V[cv[i]];
+                if (c >= cc) { band = i; lb = cc; break; }
+                cc_prev = cc;
+            }
+            const double ub = cc_prev, lv = V[lw[band]], uv = V[up[band]];
+            if (c < lb) v = lv;
+            else if (c > ub) v = uv;
+            else if (ub == lb) v = lv;
+            else { const double f = (c - lb) / (ub - lb); v = lv + (uv - lv) * f; }
+        } break;
         case B200LP_OP_STORAGE_RESET: {  // node.before(): Storage._reset_storage_only (pywr/_core.pyx:1294-1333)
             v = V[a[3]];                 // a: volume, pc, max_volume, flag, initial volume, initial pc (V indices)
             if (v == 1.0) { const double mxv = V[a[2]]; V[a[0]] = mxv; V[a[1]] = (mxv == 0.0) ? NAN : mxv / mxv; }

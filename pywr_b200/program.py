@@ -28,6 +28,7 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
+OP_CC_INTERP, OP_CC_PIECEWISE = 11, 12
 OP_STORAGE_RESET = 10
 PROG_AGG_ONLY = 1
 # virtual storages whose reset / activation follows the calendar only (pywr/nodes.py:596-757)
@@ -234,6 +235,7 @@ class _Compiler:
         # per candidate solution, so that a whole population is evaluated in one run (optimisation.PopulationEvaluator)
         self.population_axis = None
         self.variable_tables: Dict[int, int] = {}   # id(parameter) -> table index
+        self.extra_storages = []                    # AggregatedStorage nodes: device storages without an LP row
 
     # -- small helpers ---------------------------------------------------------------------
     def const(self, v) -> int:
@@ -333,6 +335,25 @@ class _Compiler:
             if len(vals) != len(curves) + 1:
                 raise Unsupported("ControlCurveParameter: len(values) != len(control_curves)+1")
             return self.emit(OP_CONTROL_CURVE, [k, len(curves)] + curves + vals)
+        if name == "ControlCurveInterpolatedParameter":   # pywr/parameters/_control_curves.pyx:98-228
+            k = self.storage_of(p.storage_node)
+            curves = [self.param(c) for c in p.control_curves]
+            if p.parameters is not None:
+                vals = [self.param(c) for c in p.parameters]
+            else:
+                vals = [self.const(v) for v in np.asarray(p.values)]
+            if len(vals) != len(curves) + 2:
+                raise Unsupported("ControlCurveInterpolatedParameter: len(values) != len(control_curves)+2")
+            return self.emit(OP_CC_INTERP, [k, len(curves)] + curves + vals)
+        if name == "ControlCurvePiecewiseInterpolatedParameter":   # :231-301
+            k = self.storage_of(p.storage_node)
+            curves = [self.param(c) for c in p.control_curves]
+            values = np.asarray(p.values, dtype=np.float64)
+            if values.shape != (len(curves) + 1, 2):
+                raise Unsupported("ControlCurvePiecewiseInterpolatedParameter: values must be [len(control_curves)+1, 2]")
+            upper = [self.const(v) for v in values[:, 0]]
+            lower = [self.const(v) for v in values[:, 1]]
+            return self.emit(OP_CC_PIECEWISE, [k, len(curves)] + curves + upper + lower + [self.const(p.minimum), self.const(p.maximum)])
         if name == "ControlCurveIndexParameter":
             k = self.storage_of(p.storage_node)
             curves = [self.param(c) for c in p.control_curves]
@@ -355,9 +376,38 @@ class _Compiler:
 
     def storage_of(self, node) -> int:
         k = self.storage_index.get(id(node))
-        if k is None or self.s.st_kind[k] == ST_KIND_VIRTUAL and type(node).__name__ != "VirtualStorage":
+        if k is None and type(node).__name__ == "AggregatedStorage":
+            k = self.aggregated_storage(node)
+        if k is None or (k < self.s.n_storage and self.s.st_kind[k] == ST_KIND_VIRTUAL and type(node).__name__ != "VirtualStorage"):
             raise Unsupported(f"control curve on {type(node).__name__} {getattr(node, 'name', '')!r}")
         return k
+
+    # -- aggregated storages ---------------------------------------------------------------------------
+    def aggregated_storage(self, node) -> int:
+        """An AggregatedStorage (pywr/_core.pyx:1363-1427) is not part of the LP: its volume follows the summed net inflow of
+        its member storages, its proportion divides by their summed max_volume.  On the device it is one more storage
+        without an LP row — kind "virtual" (mass balance from a linear form of the columns), always active — appended
+        after the LP's own storages; control-curve parameters and storage recorders address it like any other."""
+        k = self.storage_index.get(id(node))
+        if k is not None:
+            return k
+        members = list(node.storage_nodes)
+        for st in members:
+            if self.storage_index.get(id(st)) is None or type(st).__name__ not in ("Storage", "Reservoir"):
+                raise Unsupported(f"AggregatedStorage {node.name!r}: member {getattr(st, 'name', st)!r} is not a device storage")
+        k = self.s.n_storage + len(self.extra_storages)
+        self.storage_index[id(node)] = k
+        self.extra_storages.append(node)
+        return k
+
+    def summed(self, refs) -> int:
+        """ref of the sum of `refs` in member order (the order AggregatedStorage.after adds them in)"""
+        if all(r < 0 for r in refs):
+            total = 0.0
+            for r in refs:
+                total += self.consts[-r - 1]
+            return self.const(total)
+        return self.emit(OP_AGG, [AGG["sum"], len(refs)] + list(refs))
 
     # -- calendar-driven virtual storages ----------------------------------------------------------
     def schedule(self, node):
@@ -423,7 +473,7 @@ def _flow_form(structure: LPStructure, node, node_id, depth=0):
     recorders read (``AbstractNode._flow``).  Plain nodes: the solver's own sum (cython_glpk.pyx:
     1078-1088).  Storage: outputs minus inputs (``_core.pyx:942-979``).  AggregatedNode: weighted
     member sum (``_core.pyx:762-776``).  Compound nodes copy a sub-node (``nodes.py:880-887``...)."""
-    from pywr._core import AggregatedNode, Storage, VirtualStorage
+    from pywr._core import AggregatedNode, AggregatedStorage, Storage, VirtualStorage
 
     s = structure
     form: Dict[int, float] = {}
@@ -434,6 +484,10 @@ def _flow_form(structure: LPStructure, node, node_id, depth=0):
 
     if depth > 8:
         raise Unsupported("node nesting too deep")
+    if isinstance(node, AggregatedStorage):   # after(): sum of the members' flows (pywr/_core.pyx:1409-1413)
+        for st in node.storage_nodes:
+            add(_flow_form(s, st, node_id, depth + 1), 1.0)
+        return form
     if isinstance(node, VirtualStorage):
         for n, f in zip(node.nodes, node.factors):
             add(_flow_form(s, n, node_id, depth + 1), -float(f))
@@ -567,7 +621,9 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
                     if node_kinds[cname] in needs_max_flow and id(node) not in max_flow_ref:
                         raise Unsupported("no LP max_flow")
                 elif C.storage_index.get(id(node)) is None:
-                    raise Unsupported("not a device storage")
+                    if type(node).__name__ != "AggregatedStorage":
+                        raise Unsupported("not a device storage")
+                    C.aggregated_storage(node)
             except Unsupported:
                 host_recorders.append(rec)
                 continue
@@ -588,6 +644,8 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
                 rec_col.append(c); rec_w.append(form[c])
         elif cname in ("NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"):
             k = C.storage_index.get(id(node))
+            if k is None and type(node).__name__ == "AggregatedStorage":
+                k = C.aggregated_storage(node)
             if k is None:
                 raise Unsupported(f"{cname} on {type(node).__name__}")
             if cname == "MinimumVolumeStorageRecorder":
@@ -600,23 +658,46 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         rec_indptr.append(len(rec_col))
         rec_objs.append(rec)
 
+    # ---- aggregated storages: device storages without an LP row (C.aggregated_storage) -------------
+    st_kind_all = list(base.st_kind)
+    st_minv_all = list(_remap(base.st_minv_ref, mapping))
+    st_maxv_all = list(_remap(base.st_maxv_ref, mapping))
+    st_act_all = list(_remap(base.st_active_ref, mapping))
+    for node in C.extra_storages:
+        members = [C.storage_index[id(st)] for st in node.storage_nodes]
+        st_kind_all.append(ST_KIND_VIRTUAL)
+        st_minv_all.append(C.summed([int(st_minv_all[k]) for k in members]))
+        st_maxv_all.append(C.summed([int(st_maxv_all[k]) for k in members]))
+        st_act_all.append(C.const(1.0))
+        vol0 = np.vstack([vol0[: len(st_kind_all) - 1], np.asarray(node._volume)[None, :]])
+        pc0 = np.vstack([pc0[: len(st_kind_all) - 1], np.asarray(node._current_pc)[None, :]])
+        form = _flow_form(base, node, node_id)
+        for c in sorted(form):
+            sf_col.append(c)
+            sf_w.append(form[c])
+        sf_indptr.append(len(sf_col))
+    n_storage_all = len(st_kind_all)
+    if C.extra_storages:
+        roll_len = np.concatenate([roll_len[: base.n_storage], np.zeros(len(C.extra_storages), np.int32)])
+        roll_init = np.concatenate([roll_init[: base.n_storage], np.zeros(len(C.extra_storages))])
+
     # ---- assemble --------------------------------------------------------------------------------
     consts = np.asarray(C.consts, np.float64)
-    st_vol = np.full(base.n_storage, REF_STATE, np.int32)
+    st_vol = np.full(n_storage_all, REF_STATE, np.int32)
     s = LPStructure(
         formulation=base.formulation, n_rows=base.n_rows, n_cols=base.n_cols, n_nodes=base.n_nodes,
         cost_clip=base.cost_clip, a_indptr=base.a_indptr, a_col=base.a_col, a_val=base.a_val,
         row_kind=base.row_kind,
         row_lb_ref=np.where(base.row_kind == 0, _remap(base.row_lb_ref, mapping), base.row_lb_ref).astype(np.int32),
         row_ub_ref=np.where(base.row_kind == 0, _remap(base.row_ub_ref, mapping), base.row_ub_ref).astype(np.int32),
-        st_kind=base.st_kind, st_vol_ref=st_vol, st_minv_ref=_remap(base.st_minv_ref, mapping),
-        st_maxv_ref=_remap(base.st_maxv_ref, mapping), st_active_ref=_remap(base.st_active_ref, mapping),
+        st_kind=np.asarray(st_kind_all, np.int32), st_vol_ref=st_vol, st_minv_ref=np.asarray(st_minv_all, np.int32),
+        st_maxv_ref=np.asarray(st_maxv_all, np.int32), st_active_ref=np.asarray(st_act_all, np.int32),
         cost_indptr=base.cost_indptr, cost_ref=_remap(base.cost_ref, mapping), cost_w=base.cost_w,
         dyn_a_nz=base.dyn_a_nz, dyn_a_ref=_remap(base.dyn_a_ref, mapping), dyn_a_scale=base.dyn_a_scale,
         flow_indptr=base.flow_indptr, flow_col=base.flow_col, flow_w=base.flow_w,
         consts=consts, n_slots=max(C.n_slots, 1),
         node_names=base.node_names, row_names=base.row_names, col_names=base.col_names,
-        bindings=base.bindings, all_nodes=base.all_nodes, routes=base.routes, storages=base.storages,
+        bindings=base.bindings, all_nodes=base.all_nodes, routes=base.routes, storages=list(base.storages) + list(C.extra_storages),
     )
     if reset_ops:
         # op order = Model.before(): node.before() (scheduled resets) first, then the parameters.  Table ops

@@ -154,7 +154,7 @@ class BatchedLPSolver(_SolverBase):
                 node.commit_all(node_flow[i])
         if self.save_routes_flows:
             self.routes_flows_array = np.ascontiguousarray(self._col_flow.T)
-        self.last_objective = self._objective[0]
+        self.last_objective = self._objective[0].copy()
         t3 = time.perf_counter()
         st = self._stats
         st["bounds_update_nonstorage"] += t1 - t0
@@ -188,7 +188,11 @@ class BatchedLPSolver(_SolverBase):
                 else:
                     getattr(obj, "get_all_" + kind)(out)
             elif kind == "factor_check":
-                continue
+                # constant factors are part of the matrix: a ConstantParameter factor that was given a new value between
+                # runs (optimisation variables, value assignment) must reach the LP like it does in the reference
+                if float(np.asarray(obj.get_factors_norm(None))[b.index]) != b.baked:
+                    self.setup(model)
+                    return self._gather(model)
             else:
                 value = _current_value(obj, kind)
                 if isinstance(value, Parameter):

@@ -90,6 +90,7 @@ class Binding:
     const: int = -1
     index: int = 0
     loop: bool = False  # a Python subclass overrides the scalar getter: call it per scenario
+    baked: float = float("nan")  # factor_check: the normalised factor written into the matrix at setup
 
     @property
     def ref(self) -> int:
@@ -467,7 +468,9 @@ def build_structure(model, formulation: str = "route") -> LPStructure:
             if constant:
                 for c in cols_i:
                     row[c] = row.get(c, 0.0) - float(norm[i])
-                B.bindings.append(Binding(kind="factor_check", obj=agg, index=i, const=-1))
+                # the reference re-reads get_factors_norm every scenario and timestep (cython_glpk.pyx:663-673) unless
+                # set_fixed_factors_once; the solver compares with `baked` and rebuilds when a constant factor was changed
+                B.bindings.append(Binding(kind="factor_check", obj=agg, index=i, const=-1, baked=float(norm[i])))
             else:
                 b = B.bind("factor_norm", agg, None, index=i, force_slot=True)
                 for c in cols_i:

@@ -45,7 +45,41 @@ CASES = [
     # rolling licence: per-scenario ring buffer of past use on the device
     ("rolling_virtual_storage", "tests/models/rolling_virtual_storage.json", "route", None),
     ("rolling_virtual_storage_long", "licence:rolling", "route", None),
+    # interpolated control curves (ops B200LP_OP_CC_INTERP / CC_PIECEWISE) and an AggregatedStorage on the device
+    ("cc_interpolated", "custom:interpolated", "route", "2101-12-31"),
+    ("aggregated_storage", "custom:aggregated_storage", "route", None),
 ]
+
+
+def custom_document(kind):
+    import json
+
+    if kind == "interpolated":
+        # examples/thames with the demand scaled by a ControlCurveInterpolatedParameter of the reservoir level (values at
+        # 100 %, level1, level2, 0 %) and the abstraction capped by a ControlCurvePiecewiseInterpolatedParameter
+        doc = json.load(open(os.path.join(REF, "examples/thames/thames.json")))
+        for tab in doc.get("tables", {}).values():
+            if "url" in tab and not os.path.isabs(tab["url"]):
+                tab["url"] = os.path.join(REF, "examples/thames", tab["url"])
+        for prm in doc["parameters"].values():
+            if isinstance(prm, dict) and "url" in prm and not os.path.isabs(prm["url"]):
+                prm["url"] = os.path.join(REF, "examples/thames", prm["url"])
+        P = doc["parameters"]
+        P["interp_factor"] = {"type": "controlcurveinterpolated", "storage_node": "reservoir1",
+                              "control_curves": ["level1", "level2"], "values": [1.0, 0.9, 0.7, 0.4]}
+        P["release_cap"] = {"type": "controlcurvepiecewiseinterpolated", "storage_node": "reservoir1",
+                            "control_curves": ["level2"], "values": [[3.5, 2.0], [1.5, 0.5]], "minimum": 0.05, "maximum": 0.95}
+        P["demand_max_flow"]["parameters"].append("interp_factor")
+        next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "release_cap"
+        return doc
+    if kind == "aggregated_storage":
+        # tests/models/three_storage.json: the inflow of reservoir 0 is switched by a control curve on the AGGREGATED storage
+        doc = json.load(open(os.path.join(REF, "tests/models/three_storage.json")))
+        doc["parameters"] = {"top_up": {"type": "controlcurve", "storage_node": "Total Storage", "control_curves": [0.45, 0.3],
+                                        "values": [0.0, 6.0, 14.0]}}
+        next(n for n in doc["nodes"] if n["name"] == "Input 0")["max_flow"] = "top_up"
+        return doc
+    raise KeyError(kind)
 
 
 def licence_document(kind):
@@ -80,7 +114,7 @@ def add_recorders(m):
     for n in list(m.nodes):
         cn = type(n).__name__
         if cn in ("Storage", "Reservoir", "AnnualVirtualStorage", "SeasonalVirtualStorage", "MonthlyVirtualStorage",
-                  "RollingVirtualStorage"):
+                  "RollingVirtualStorage") or (cn == "AggregatedStorage" and "aggregated_storage" in str(m.metadata.get("b200_case", ""))):
             recs += [NumpyArrayStorageRecorder(m, n, name=f"vol_{n.name}"),
                      NumpyArrayStorageRecorder(m, n, proportional=True, name=f"pc_{n.name}"),
                      MinimumVolumeStorageRecorder(m, n, name=f"minv_{n.name}")]
@@ -98,7 +132,10 @@ def add_recorders(m):
 
 
 def load(path, formulation, end):
-    src = licence_document(path.split(":")[1]) if path.startswith("licence:") else os.path.join(REF, path)
+    if path.startswith("custom:"):
+        src = custom_document(path.split(":")[1])
+    else:
+        src = licence_document(path.split(":")[1]) if path.startswith("licence:") else os.path.join(REF, path)
     m = Model.load(src, solver="oracle" if formulation == "route" else "oracle-edge")
     if end:
         m.timestepper.end = end
@@ -109,10 +146,12 @@ def load(path, formulation, end):
 
 def run_case(name, path, formulation, end):
     m = load(path, formulation, end)
+    m.metadata["b200_case"] = name
     recs = add_recorders(m)
     m.run()
     expected = {r.name: (np.array(r.data) if hasattr(r, "data") else np.array(r.values())) for r in recs}
     m2 = load(path, formulation, end)
+    m2.metadata["b200_case"] = name
     recs2 = add_recorders(m2)
     m2.setup()
     s, prog = compile_program(m2, formulation, recorders=recs2)

@@ -151,6 +151,7 @@ def test_plane_program_on_the_2000_node_network_matches_the_reference_host_run()
     s = LPStructure.load(fix + ".pstructure.npz")
     prog = Program.load(fix + ".program.npz")
     z = np.load(fix + ".expected.npz")
+    zd = np.load(fix + ".expected_dict.npz")    # the same program on the dictionary oracle (independent simplex)
     names = [str(n) for n in z["names"]]
     S = n_scenarios_of(s, prog)
     gpu = CudaEngine(s, S, device=0)
@@ -165,6 +166,8 @@ def test_plane_program_on_the_2000_node_network_matches_the_reference_host_run()
         d = rel_diff(o, z[f"rec{i}"])
         worst = max(worst, d)
         assert d <= 1e-6, (nm, d)
+        od = zd[f"rec{i}"] / T if nm.startswith(("mf_", "df_")) else zd[f"rec{i}"]
+        assert rel_diff(o, od) <= 1e-6, (nm, rel_diff(o, od))
     stt = gpu.stats()
     assert stt["refactors"] == 0 and stt["pivots"] > 1000
     print(f"network600: T={T} S={S}, {len(names)} recorders, worst relative difference vs the reference host run {worst:.2e}, "

@@ -89,24 +89,28 @@ def test_rsx_nan_status_warm_start_and_reset(force_rsx):
 
 
 def test_rsx_infeasible_scenario_is_reported(force_rsx):
-    """a demand that must be met (min_flow = max_flow > supply) has no feasible flow: status 1 for that scenario only"""
+    """A catchment that must deliver a NEGATIVE flow (lb = ub = -5 on a row whose columns are all x >= 0 with coefficient +1)
+    has no feasible solution: status 1 ("no primal feasible solution", cython_glpk.pyx:1060) for that scenario only, exactly
+    like the dictionary oracle; the other scenarios are solved as if nothing had happened."""
+    from oracle.oracle_engine import OracleEngine
+
     s, tr = load_case("network24.edge")
     S = 4
     slots, days = synth_batch(s, tr, S, 1, seed=3, common=True)
-    lb_slots = [int(r) for r in s.row_lb_ref if r >= 0]
-    if not lb_slots:
-        pytest.skip("no dynamic lower bound in this fixture")
+    forced = [int(lb) for lb, ub in zip(s.row_lb_ref, s.row_ub_ref) if lb >= 0 and lb == ub]
+    assert forced, "the fixture has catchment rows (lb = ub = inflow slot)"
     gpu = _gpu(s, S)
+    good = replay(gpu, s, slots, days)
+    assert good[3].sum() == 0
     bad = slots.copy()
-    for r in lb_slots:
-        bad[:, r, 1] = 1e9
-    for i in range(s.n_rows):
-        if s.row_lb_ref[i] >= 0 and s.row_ub_ref[i] >= 0:
-            bad[:, s.row_ub_ref[i], 1] = 1e9
+    bad[:, forced[0], 1] = -5.0
     c = replay(gpu, s, bad, days)
-    first, code = gpu.status()
-    if c[3].sum() > 0:
-        assert first == 1 and code in (1, 2)
+    assert c[3].sum() == 1                     # the step reports failed scenarios ...
+    assert gpu.status() == (1, 1)              # ... the first (only) one is scenario 1, B200LP_ST_INFEASIBLE
+    o = replay(OracleEngine(s, S), s, bad, days)
+    assert o[3].sum() == 1
+    ok = [0, 2, 3]
+    assert np.allclose(c[2][:, ok], good[2][:, ok], rtol=1e-12)
     gpu.close()
 
 

@@ -191,3 +191,35 @@ def test_run_on_device_without_shipping_arrays(arrays):
         assert np.asarray(r3[-1].data).shape == (365, 5)
         assert _rel(np.array(r3[-1].values()), np.array(r4[-1].values())) <= 1e-12
         res.close()
+
+
+def test_constant_factor_changed_between_runs_reaches_the_lp():
+    """Aggregated-node factors that are ConstantParameters are baked into the matrix at setup; the reference re-reads
+    get_factors_norm every scenario and timestep (cython_glpk.pyx:663-673), so a factor given a new value between two runs
+    (an optimisation variable) changes the flow ratio without the model being marked dirty.  The plug-in notices the change
+    when it gathers the timestep's inputs and rebuilds."""
+    pytest.importorskip("pywr")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.nodes import AggregatedNode, Input, Output
+
+    def make(f1):
+        m = Model(solver="oracle")
+        A = Input(m, "A", max_flow=10.0)
+        B = Input(m, "B", max_flow=10.0)
+        Z = Output(m, "Z", cost=-10)
+        A.connect(Z); B.connect(Z)
+        agg = AggregatedNode(m, "agg", [A, B])
+        agg.max_flow = 9.0
+        agg.factors = [1.0, f1]
+        return m, A, B, agg
+    m, A, B, agg = make(2.0)
+    m.step()
+    assert np.allclose([A.flow[0], B.flow[0]], [3.0, 6.0])
+    assert not m.dirty
+    agg.factors[1].set_double_variables(np.array([0.5]))     # the optimisation wrappers' way of changing a ConstantParameter
+    assert not m.dirty
+    m.step()
+    m2, A2, B2, _ = make(0.5)
+    m2.step()
+    assert np.allclose([A.flow[0], B.flow[0]], [A2.flow[0], B2.flow[0]]) and np.allclose(B.flow[0], 3.0)

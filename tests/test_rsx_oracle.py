@@ -156,3 +156,25 @@ def test_rsx_reduced_cost_refresh_changes_nothing():
     assert a[3].sum() == 0 and b[3].sum() == 0
     assert np.max(np.abs(a[2] - b[2]) / np.maximum(1.0, np.abs(a[2]))) < 1e-12
     assert a_eng.stats()["pivots"] == b_eng.stats()["pivots"] > 3 * S
+
+
+def test_config4_fixture_is_pinned_by_the_dictionary_oracle():
+    """benchmarks/fixtures/network600.expected.npz (what the CUDA run of config 4 is compared with) comes from a host run
+    of the reference framework whose LP solver is the host build of the product's own revised simplex.  The same device
+    program executed by the DICTIONARY oracle's program mode — an independent dense simplex, with its own parameter /
+    Storage.after / recorder restatement — over all 365 timesteps (tests/golden/make_network_program_dict.py, 5,136 pivots)
+    gives the same recorder arrays: the fixture is not self-referential."""
+    fix = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures", "network600")
+    a, b = np.load(fix + ".expected.npz"), np.load(fix + ".expected_dict.npz")
+    names = [str(n) for n in a["names"]]
+    assert names == [str(n) for n in b["names"]] and len(names) == 30
+    T = 365
+    worst = 0.0
+    for i, nm in enumerate(names):
+        x, y = a[f"rec{i}"], b[f"rec{i}"]
+        if nm.startswith(("mf_", "df_")):       # the reference divides by the number of timesteps in finish()
+            y = y / T
+        assert x.shape == y.shape
+        d = float(np.max(np.abs(x - y) / np.maximum(1.0, np.abs(y))))
+        worst = max(worst, d)
+    assert worst <= 1e-9, worst
