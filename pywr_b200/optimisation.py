@@ -138,3 +138,98 @@ class PopulationEvaluator:
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+
+
+class PlatypusPopulationWrapper:
+    """Platypus front end of :class:`PopulationEvaluator` — the batched counterpart of the reference's
+    ``PlatypusWrapper`` (``pywr/optimisation/platypus.py:31-154``): the same ``platypus.Problem`` (one ``Real`` per double /
+    integer variable with the parameter's bounds, the same ``Constraint`` objects for lower / upper / equality / double
+    bounded recorders, :60-112), but a generation is evaluated in ONE device-resident run instead of one ``Model.run()`` per
+    candidate.  Platypus algorithms hand their unevaluated solutions to ``algorithm.evaluator.evaluate_all(jobs)``;
+    :attr:`evaluator` is a ``platypus.Evaluator`` that packs them into populations of ``population_size`` candidates
+    (the last one padded by repeating a candidate), calls :meth:`PopulationEvaluator.evaluate` and stores objectives,
+    constraints, constraint violation and feasibility on every solution the way ``platypus.Problem.evaluate`` does.
+
+        wrapper = PlatypusPopulationWrapper(make_model, population_size=256)
+        algorithm = platypus.NSGAII(wrapper.problem, population_size=256, evaluator=wrapper.evaluator)
+        algorithm.run(10000)
+
+    ``platypus``: the module to build the problem with (default: ``import platypus``)."""
+
+    def __init__(self, make_model, population_size, platypus=None, **kwargs):
+        if platypus is None:
+            import platypus  # noqa: PLC0415 - optional dependency, exactly like the reference's wrapper
+        self.platypus = platypus
+        self.batch = PopulationEvaluator(make_model, population_size, **kwargs)
+        b = self.batch
+        n_con = sum(2 if c.is_double_bounded_constraint else 1 for c in b.constraints)
+        if len(b.variables) < 1:
+            raise ValueError("At least one variable must be defined.")
+        if len(b.objectives) < 1:
+            raise ValueError("At least one objective must be defined.")
+        self.problem = platypus.Problem(b.n_variables, len(b.objectives), n_con)
+        self.problem.function = self._evaluate_one
+        self.problem.wrapper = self
+        ix = 0
+        for var in b.variables:           # _make_variables, :60-79 (integer variables are refused by the evaluator)
+            lower, upper = var.get_double_lower_bounds(), var.get_double_upper_bounds()
+            for i in range(var.double_size):
+                self.problem.types[ix] = platypus.Real(lower[i], upper[i])
+                ix += 1
+        ic = 0
+        for c in b.constraints:           # _make_constraints, :81-112
+            if c.is_double_bounded_constraint:
+                self.problem.constraints[ic] = platypus.Constraint(">=", value=c.constraint_lower_bounds)
+                self.problem.constraints[ic + 1] = platypus.Constraint("<=", value=c.constraint_upper_bounds)
+                ic += 2
+            elif c.is_equality_constraint:
+                self.problem.constraints[ic] = platypus.Constraint("==", value=c.constraint_lower_bounds)
+                ic += 1
+            elif c.is_lower_bounded_constraint:
+                self.problem.constraints[ic] = platypus.Constraint(">=", value=c.constraint_lower_bounds)
+                ic += 1
+            elif c.is_upper_bounded_constraint:
+                self.problem.constraints[ic] = platypus.Constraint("<=", value=c.constraint_upper_bounds)
+                ic += 1
+            else:
+                raise RuntimeError(f'The bounds of constraint "{c.name}" could not be identified correctly.')
+        wrapper = self
+
+        class _BatchEvaluator(platypus.Evaluator):
+            def evaluate_all(self, jobs, **kw):
+                jobs = list(jobs)
+                wrapper.evaluate_solutions([job.solution for job in jobs])
+                return jobs
+
+        self.evaluator = _BatchEvaluator()
+
+    def _decode(self, solution):
+        return [t.decode(v) for t, v in zip(self.problem.types, solution.variables)]
+
+    def evaluate_solutions(self, solutions):
+        """Evaluates any number of platypus solutions, ``population_size`` candidates per device run."""
+        P = self.batch.P
+        todo = [s for s in solutions if not getattr(s, "evaluated", False)]
+        for start in range(0, len(todo), P):
+            chunk = todo[start: start + P]
+            X = np.array([self._decode(s) for s in chunk], dtype=np.float64)
+            if len(chunk) < P:
+                X = np.vstack([X, np.repeat(X[-1:], P - len(chunk), axis=0)])
+            objectives, constraints = self.batch.evaluate(X)
+            for p, s in enumerate(chunk):
+                s.objectives[:] = [float(v) for v in objectives[p]]
+                s.constraints[:] = [float(v) for v in constraints[p]]
+                s.constraint_violation = sum(abs(f(x)) for f, x in zip(self.problem.constraints, s.constraints))
+                s.feasible = s.constraint_violation == 0.0
+                s.evaluated = True
+
+    def _evaluate_one(self, variables):
+        """``problem.function`` for callers that evaluate one solution at a time (the whole batch carries that candidate)."""
+        X = np.repeat(np.asarray(variables, dtype=np.float64)[None, :], self.batch.P, axis=0)
+        objectives, constraints = self.batch.evaluate(X)
+        if constraints.shape[1] > 0:
+            return list(objectives[0]), list(constraints[0])
+        return list(objectives[0])
+
+    def close(self):
+        self.batch.close()

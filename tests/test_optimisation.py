@@ -88,3 +88,81 @@ def test_population_evaluator_matches_reference_evaluate_on_the_oracle():
     from oracle.oracle_engine import OracleEngine
 
     check_population(OracleEngine)
+
+
+class _FakePlatypus:
+    """The slice of the Platypus API the reference's wrapper and ours use (platypus-opt is not installable here): Problem with
+    types / constraints lists and a function, Real with bounds and decode, Constraint as a callable distance to feasibility,
+    Solution, Evaluator, and an EvaluateJob-like object carrying a solution."""
+
+    class Real:
+        def __init__(self, lo, hi):
+            self.min_value, self.max_value = float(lo), float(hi)
+
+        def decode(self, v):
+            return v
+
+    class Constraint:
+        def __init__(self, op, value=0.0):
+            self.op, self.value = op, float(value)
+
+        def __call__(self, x):
+            if self.op == ">=":
+                return 0.0 if x >= self.value else self.value - x
+            if self.op == "<=":
+                return 0.0 if x <= self.value else x - self.value
+            return abs(x - self.value)
+
+    class Problem:
+        def __init__(self, nvars, nobjs, nconstrs=0):
+            self.nvars, self.nobjs, self.nconstrs = nvars, nobjs, nconstrs
+            self.types, self.constraints, self.function = [None] * nvars, [None] * nconstrs, None
+
+    class Solution:
+        def __init__(self, problem):
+            self.problem = problem
+            self.variables = [None] * problem.nvars
+            self.objectives, self.constraints = [None] * problem.nobjs, [None] * problem.nconstrs
+            self.constraint_violation, self.feasible, self.evaluated = 0.0, True, False
+
+    class Evaluator:
+        def evaluate_all(self, jobs, **kwargs):
+            raise NotImplementedError
+
+    class Job:
+        def __init__(self, solution):
+            self.solution = solution
+
+
+def test_platypus_wrapper_evaluates_a_generation_in_batches():
+    """PlatypusPopulationWrapper: the reference's platypus.Problem (pywr/optimisation/platypus.py:31-112), evaluated
+    population_size candidates per device run through a platypus.Evaluator; every solution receives what the reference's
+    one-Model.run()-per-candidate evaluate (:115-154) returns, plus platypus' constraint violation / feasibility."""
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from oracle.oracle_engine import OracleEngine
+    from pywr_b200.optimisation import PlatypusPopulationWrapper
+
+    make = make_model_factory(n_inflow=2)
+    P = 4
+    w = PlatypusPopulationWrapper(make, P, platypus=_FakePlatypus, engine_factory=OracleEngine)
+    pb = w.problem
+    assert (pb.nvars, pb.nobjs, pb.nconstrs) == (13, 2, 1)
+    assert all(isinstance(t, _FakePlatypus.Real) for t in pb.types) and sorted({t.max_value for t in pb.types}) == [1.0, 3.0]
+    assert pb.constraints[0].op == ">=" and pb.constraints[0].value == 10.0
+    X = random_population(w.batch, 6, seed=5)            # 6 solutions: one full batch of 4 and a padded one
+    sols = []
+    for x in X:
+        s = _FakePlatypus.Solution(pb)
+        s.variables[:] = list(x)
+        sols.append(s)
+    jobs = w.evaluator.evaluate_all([_FakePlatypus.Job(s) for s in sols])
+    assert len(jobs) == 6 and w.batch.evaluations == 2
+    for s, x in zip(sols, X):
+        o_ref, c_ref = reference_evaluate(make, x)
+        assert s.evaluated and np.allclose(s.objectives, o_ref, rtol=1e-9, atol=1e-12)
+        assert np.allclose(s.constraints, c_ref, rtol=1e-9, atol=1e-12)
+        assert s.constraint_violation == pytest.approx(max(0.0, 10.0 - c_ref[0]), abs=1e-9)
+        assert s.feasible == (s.constraint_violation == 0.0)
+    one = pb.function(list(X[2]))                           # single-solution entry point
+    assert np.allclose(one[0], sols[2].objectives, rtol=1e-12) and np.allclose(one[1], sols[2].constraints, rtol=1e-12)
+    w.close()
