@@ -625,7 +625,8 @@ int b200lp_status(b200lp_handle *h, int32_t *first_bad_scenario, int32_t *code) 
 int b200lp_get_basis(b200lp_handle *h, int32_t *row_stat, int32_t *col_stat) {
     if (!h || !row_stat || !col_stat) return fail(B200LP_E_INVALID, "null argument");
     if (h->pdhg && pdhg_is_rsx(h)) { CUDA_TRY(cudaSetDevice(h->device)); return rsx_get_basis(h, row_stat, col_stat); }
-    if (h->pdhg) return fail(B200LP_E_UNSUPPORTED, "the PDHG iterations carry (x, y, omega) between timesteps, not a basis");
+    if (h->pdhg) return fail(B200LP_E_UNSUPPORTED, "the PDHG iterations carry (x, y, omega) between timesteps, not a basis "
+                                                   "(crossover disabled, or its state does not fit beside the PDHG state)");
     CUDA_TRY(cudaSetDevice(h->device));
     const int m = h->ds.m, n = h->ds.n, rows_cap = h->ds.rows_cap, nc = h->ds.nc;
     const size_t S = (size_t)h->S;
@@ -671,6 +672,7 @@ int b200lp_get_stats(b200lp_handle *h, b200lp_stats *out) {
     CUDA_TRY(cudaMemcpyAsync(h->h_counters, h->state.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (h->pdhg && pdhg_is_rsx(h)) {
+        if (h->pdhg->xover) h->stats.pdhg_iterations = (int64_t)h->h_counters[0];   // PDHG iterations + crossover pivots
         CUDA_TRY(cudaMemcpy(h->h_counters, pdhg_rsx_counters(h), 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         h->stats.pivots = (int64_t)h->h_counters[0];
         h->stats.refactors = (int64_t)h->h_counters[1];

@@ -667,6 +667,111 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
     return worst;
 }
 
+// Crossover to a vertex (north_star: "a batched restarted-PDHG path ... followed by crossover to a vertex").  x0 is a point
+// that is optimal within the first-order method's tolerance (structural values of the scaled LP, element stride ldx0).
+//  1. every variable is classified against its bounds: on a bound -> non-basic there, strictly between -> wanted basic;
+//  2. the basis is crashed from the slack basis: every wanted structural is pivoted in against the slack of a row that
+//     sits on a bound (largest pivot element; a structural without an acceptable pivot stays non-basic at its nearer bound,
+//     a slack that could not leave stays basic) - m basic variables, non-singular by construction;
+//  3. the simplex of this file finishes from that basis (dual phase with shifted costs, primal clean-up): normally a handful
+//     of pivots, because the crashed basis is the optimal one up to degenerate ties.
+// The result is a vertex with a GLPK-style basis (b200lp_get_basis), like the one GLPK hands to BasisManager
+// (cython_glpk.pyx:197-232).  Falls back to a cold start of the simplex if the crashed basis fails.
+template <class CX>
+RSX_FN int crossover(CX &cx, const Lp &P, const Scen &S, Work &K, const double *x0, const size_t ldx0, int &pivots, int &refactors,
+                     int &crashed) {
+    const int m = P.m, n = P.n, nv = n + m;
+    load_bounds(cx, P, S, K);
+    // row activities of x0 into g
+    for (int i = cx.tid; i < m; i += cx.nt) {
+        const int e0 = RSX_RO(&P.csr_ptr[i]), e1 = RSX_RO(&P.csr_ptr[i + 1]);
+        if (e1 - e0 > P.long_len) continue;
+        double acc = 0.0;
+        for (int e = e0; e < e1; e++) acc = fma(RSX_RO(&P.csr_val[e]), x0[(size_t)RSX_RO(&P.csr_col[e]) * ldx0], acc);
+        K.g[i] = acc;
+    }
+    for (int li = cx.warp; li < P.n_long; li += cx.nw) {
+        const int i = P.long_rows[li];
+        double acc = 0.0;
+        for (int e = P.csr_ptr[i] + cx.lane; e < P.csr_ptr[i + 1]; e += cx.nl) acc = fma(P.csr_val[e], x0[(size_t)P.csr_col[e] * ldx0], acc);
+        acc = cx.warp_sum(acc);
+        if (cx.lane == 0) K.g[i] = acc;
+    }
+    cx.sync();
+    // 1. classification (alpha keeps the value of every variable at x0 for the "nearer bound" decisions)
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        const double val = v < n ? x0[(size_t)v * ldx0] : K.g[v - n];
+        const double lo = K.LO[v], hi = K.HI[v];
+        const double tl = 1e-6 * (1.0 + fabs(lo)), th = 1e-6 * (1.0 + fabs(hi));
+        int st;
+        if (lo == hi) st = V_NS;
+        else if (lo > -INFINITY && val <= lo + tl) st = V_NL;
+        else if (hi < INFINITY && val >= hi - th) st = V_NU;
+        else st = V_BASIC;
+        K.stat[v] = (unsigned char)st;
+        K.alpha[v] = val;
+    }
+    // 2. crash: W = -I, head = slacks
+    for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = n + i;
+    const size_t tot = (size_t)m * P.ldw;
+    for (size_t e = cx.tid; e < tot; e += cx.nt) S.W[e] = 0.0;
+    cx.sync();
+    for (int i = cx.tid; i < m; i += cx.nt) S.W[(size_t)i * P.ldw + i] = -1.0;
+    cx.sync();
+    int entered = 0;
+    for (int q = 0; q < n; q++) {
+        if (K.stat[q] != V_BASIC) continue;
+        compute_w(cx, P, S, K, q);
+        double best = 1e-7; int bi = -1, aux = 0;
+        for (int i = cx.tid; i < m; i += cx.nt) {
+            const int v = K.head[i];
+            if (v < n || K.stat[v] == V_BASIC) continue;  // already a structural, or a slack that is wanted basic
+            const double a = fabs(K.w[i]);
+            if (a > best) { best = a; bi = i; }
+        }
+        if (bi < 0) best = -1.0;
+        cx.argmax(best, bi, aux);
+        if (bi < 0) {  // no slack on a bound can give way: the structural goes to its nearer bound
+            if (cx.leader()) {
+                const double lo = K.LO[q], hi = K.HI[q], val = K.alpha[q];
+                K.stat[q] = (unsigned char)(!(lo > -INFINITY) ? (hi < INFINITY ? V_NU : V_NF) : (!(hi < INFINITY) ? V_NL : (val - lo <= hi - val ? V_NL : V_NU)));
+            }
+            cx.sync();
+            continue;
+        }
+        load_rho(cx, P, S, K, bi);
+        update_W(cx, P, S, K, bi);
+        if (cx.leader()) K.head[bi] = q;
+        cx.sync();
+        entered++;
+    }
+    for (int i = cx.tid; i < m; i += cx.nt) {
+        const int v = K.head[i];
+        if (v >= n) K.stat[v] = V_BASIC;     // slacks that did not leave are basic, whatever their classification said
+    }
+    cx.sync();
+    crashed += entered;
+    // 3. finish with the simplex
+    compute_d(cx, P, S, K);
+    const int p_before = pivots;
+    int status = solve(cx, P, S, K, pivots);
+    if (status == R_OPTIMAL) {
+        const double res = write_solution(cx, P, S, K);
+        if (!(res <= 1e-7)) status = R_NUMERIC;
+    }
+    if (status != R_OPTIMAL) {  // cold start of the simplex (the retry ladder's last rung)
+        refactors++;
+        cold_init(cx, P, S, K);
+        status = solve(cx, P, S, K, pivots);
+        if (status == R_OPTIMAL) write_solution(cx, P, S, K);
+    }
+    for (int v = cx.tid; v < nv; v += cx.nt) { S.stat[v] = K.stat[v]; S.d[v] = K.d[v]; }
+    for (int i = cx.tid; i < m; i += cx.nt) S.head[i] = K.head[i];
+    if (cx.leader()) { S.info[0] = status == R_OPTIMAL ? 1 : 0; S.info[1] = pivots - p_before; }
+    cx.sync();
+    return status == R_NUMERIC ? R_SINGULAR : status;
+}
+
 // One scenario, one timestep: warm start from the stored basis (or the slack basis when `cold`), retry ladder
 // (re-factorise the same basis, then restart from the slack basis), state written back.
 template <class CX>

@@ -143,6 +143,55 @@ rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
     }
 }
 
+// Crossover of the PDHG path (rsx_core.cuh::crossover): same CTA layout as rsx_solve_kernel; x0 = the scenario's column of the
+// x planes (the first-order method's answer), the vertex goes to xt.  counters[20] counts the structurals the crash pivoted in.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(RSX_THREADS, MINB)
+rsx_crossover_kernel(const RsxDev D, const int s0, const int s1) {
+    extern __shared__ __align__(16) unsigned char rsx_smem[];
+    __shared__ double rv[32];
+    __shared__ int ri[32], ra[32], s_next;
+    RsxCtx cx;
+    cx.tid = threadIdx.x; cx.nt = blockDim.x; cx.lane = threadIdx.x & 31;
+    cx.warp = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
+    cx.rv = rv; cx.ri = ri; cx.ra = ra;
+#ifdef RSX_PHASE_TIMING
+    for (int k = 0; k < 16; k++) cx.ph[k] = 0;
+    cx.t_last = clock64();
+#endif
+    const rsx::Lp &P = D.lp;
+    rsx::Work K;
+    rsx::work_carve(K, rsx_smem, MODE == 0 ? nullptr : D.scratch + (size_t)blockIdx.x * D.scratch_stride, P.m, P.n, MODE);
+    const size_t wtot = (size_t)P.m * P.ldw;
+    const int nv = P.n + P.m;
+    int pivots = 0, refactors = 0, crashed = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_next = s0 + atomicAdd(D.queue, 1);
+        __syncthreads();
+        const int s = s_next;
+        __syncthreads();
+        if (s >= s1) break;
+        if (D.status[s] != 0) continue;
+        rsx::Scen sc;
+        sc.W = D.W + (size_t)s * wtot;
+        sc.head = D.head + (size_t)s * P.m;
+        sc.stat = D.stat + (size_t)s * nv;
+        sc.d = D.d + (size_t)s * nv;
+        sc.info = D.info + (size_t)s * 4;
+        sc.c = D.c + s; sc.lc = D.lc + s; sc.uc = D.uc + s; sc.lo = D.lo + s; sc.hi = D.hi + s;
+        sc.ld = (size_t)D.ld;
+        sc.bt = D.bt + (size_t)s * 2 * nv;
+        sc.x = D.xt + (size_t)s * P.n; sc.ldx = 1;
+        const int st = rsx::crossover(cx, P, sc, K, D.x + s, (size_t)D.ld, pivots, refactors, crashed);
+        if (threadIdx.x == 0) D.status[s] = st;
+    }
+    if (threadIdx.x == 0) {
+        if (pivots) atomicAdd(&D.counters[0], (unsigned long long)pivots);
+        if (refactors) atomicAdd(&D.counters[1], (unsigned long long)refactors);
+        if (crashed) atomicAdd(&D.counters[20], (unsigned long long)crashed);
+    }
+}
+
 // planes [item][ld] -> per-scenario vectors [S][2 (n+m)] (LO | HI), 32 x 32 tiles through shared memory: coalesced reads along
 // the scenario axis, coalesced writes along the item axis
 __global__ void rsx_gather_bounds(const RsxDev D) {

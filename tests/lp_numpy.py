@@ -83,3 +83,37 @@ def residuals(s, slots, k, days, x, vol_state=None):
     A, lo, hi, c = assemble(s, slots, k, days, vol_state)
     r = A @ x
     return max(0.0, float(np.max(lo - r)), float(np.max(r - hi)), float(np.max(-x))), float(c @ x)
+
+
+def check_glpk_basis(s, slots_t, days, k, x, row, col):
+    """`row` [m] / `col` [n]: GLPK-coded statuses of scenario k (BasisManager.row_stat / col_stat, cython_glpk.pyx:197-232) for
+    the LP of this timestep, `x` the engine's column values.  Exactly m variables are basic, every non-basic variable sits on
+    the bound its status names, and the basic columns / rows form a non-singular basis matrix whose solution is x."""
+    BS, NL, NU, NF, NS = 1, 2, 3, 4, 5
+    m, n = s.n_rows, s.n_cols
+    A, lo, hi, c = assemble(s, slots_t, k, days)
+    A = np.asarray(A.todense()) if hasattr(A, "todense") else np.asarray(A)
+    r = A @ x
+    assert (row == BS).sum() + (col == BS).sum() == m, ((row == BS).sum(), (col == BS).sum(), m)
+    scale = max(1.0, np.abs(x).max())
+    for j in range(n):
+        if col[j] in (NL, NS):
+            assert abs(x[j]) <= 1e-7 * scale, (j, x[j])
+        assert col[j] != NU            # original columns are x >= 0 without an upper bound
+    for i in range(m):
+        if row[i] == NL or row[i] == NS:
+            assert abs(r[i] - lo[i]) <= 1e-7 * scale, (i, r[i], lo[i])
+        elif row[i] == NU:
+            assert abs(r[i] - hi[i]) <= 1e-7 * scale, (i, r[i], hi[i])
+    # basis matrix of [A | -I] v = 0: basic columns of A and -e_i of the basic rows; non-singular, and solving with the
+    # non-basic variables on their bounds reproduces x
+    bc = np.nonzero(col == BS)[0]
+    br = np.nonzero(row == BS)[0]
+    B = np.hstack([A[:, bc], -np.eye(m)[:, br]])
+    assert np.linalg.matrix_rank(B) == m
+    rhs = np.zeros(m)
+    for i in range(m):
+        if row[i] != BS:
+            rhs[i] += (hi[i] if row[i] == NU else (0.0 if row[i] == NF else lo[i]))
+    sol = np.linalg.solve(B, rhs)      # A_B x_B - r_B = r_N  (non-basic columns are at 0)
+    assert np.allclose(sol[: len(bc)], x[bc], rtol=1e-7, atol=1e-7 * scale)

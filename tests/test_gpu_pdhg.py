@@ -165,3 +165,46 @@ def test_pdhg_on_the_2000_node_network_matches_highs(monkeypatch):
         assert cf.min() >= 0.0 and cf[:, 1].sum() < cf[:, 0].sum()
     assert gpu.stats()["pdhg_iterations"] > 0
     gpu.close()
+
+
+@pytest.mark.parametrize("case,S", [("network24.edge", 17), ("two_reservoir.edge", 5), ("network12.route", 9), ("thames.edge", 7)])
+def test_pdhg_crossover_returns_a_vertex_with_a_valid_glpk_basis(force_pdhg, case, S):
+    """north_star: "a batched restarted-PDHG path ... followed by crossover to a vertex".  After the first-order iterations
+    every scenario's point is classified against its bounds, a basis is crashed from it and the revised simplex finishes
+    (rsx_core.cuh::crossover).  The answer is then a VERTEX: objectives equal the dictionary oracle's to simplex accuracy
+    (1e-9, not the first-order 1e-7), primal residuals at round-off, and b200lp_get_basis returns a valid GLPK-coded basis of
+    the original LP (BasisManager, cython_glpk.pyx:197-232) on kernel variant 200.  With B200LP_PDHG_CROSSOVER=0 the path
+    returns the first-order point and no basis, as before."""
+    from lp_numpy import check_glpk_basis
+    from oracle.oracle_engine import OracleEngine
+
+    s, tr = load_case(case)
+    slots, days = synth_batch(s, tr, S, 3, seed=13, common=True)
+    T = len(days)
+    gpu = _gpu(s, S)
+    g = replay(gpu, s, slots, days)
+    c = replay(OracleEngine(s, S), s, slots, days)
+    assert g[3].sum() == 0 and c[3].sum() == 0
+    err = np.abs(g[2] - c[2]) / np.maximum(1.0, np.abs(c[2]))
+    assert err.max() < 1e-9, f"objective rel diff {err.max():.3e}"
+    st = gpu.stats()
+    assert st["pdhg_iterations"] > 0            # the iterations ran ...
+    row, col = gpu.get_basis()                   # ... and a basis exists
+    for k in (0, S // 2, S - 1):
+        viol, obj = residuals(s, slots[T - 1], k, float(days[T - 1]), g[1][T - 1, :, k])
+        assert viol < 1e-7 * max(1.0, np.abs(g[1][T - 1, :, k]).max())
+        check_glpk_basis(s, slots[T - 1], float(days[T - 1]), k, g[1][T - 1, :, k], row[k], col[k])
+    print(f"{case}: {st['pdhg_iterations']} PDHG scenario-iterations, {st['pivots']} simplex pivots after the crash "
+          f"({st['pivots'] / (S * T):.1f} per scenario-timestep)")
+    gpu.close()
+
+
+def test_pdhg_without_crossover_has_no_basis(force_pdhg, monkeypatch):
+    monkeypatch.setenv("B200LP_PDHG_CROSSOVER", "0")
+    s, tr = load_case("thames.edge")
+    slots, days = synth_batch(s, tr, 4, 2, seed=5, common=True)
+    gpu = _gpu(s, 4)
+    assert replay(gpu, s, slots, days)[3].sum() == 0
+    with pytest.raises(RuntimeError):
+        gpu.get_basis()
+    gpu.close()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from fixtures_util import load_case, replay, synth_batch
-from lp_numpy import residuals
+from lp_numpy import check_glpk_basis, residuals
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -97,13 +97,13 @@ def test_rsx_infeasible_scenario_is_reported(force_rsx):
     s, tr = load_case("network24.edge")
     S = 4
     slots, days = synth_batch(s, tr, S, 1, seed=3, common=True)
-    forced = [int(lb) for lb, ub in zip(s.row_lb_ref, s.row_ub_ref) if lb >= 0 and lb == ub]
-    assert forced, "the fixture has catchment rows (lb = ub = inflow slot)"
+    i = next(k for k, nm in enumerate(s.row_names) if str(nm).startswith("flow:catch") and s.row_lb_ref[k] >= 0 and s.row_ub_ref[k] >= 0)
     gpu = _gpu(s, S)
     good = replay(gpu, s, slots, days)
     assert good[3].sum() == 0
     bad = slots.copy()
-    bad[:, forced[0], 1] = -5.0
+    bad[:, int(s.row_lb_ref[i]), 1] = -5.0      # min_flow = max_flow = -5 for scenario 1
+    bad[:, int(s.row_ub_ref[i]), 1] = -5.0
     c = replay(gpu, s, bad, days)
     assert c[3].sum() == 1                     # the step reports failed scenarios ...
     assert gpu.status() == (1, 1)              # ... the first (only) one is scenario 1, B200LP_ST_INFEASIBLE
@@ -159,8 +159,6 @@ def test_rsx_get_basis_is_a_valid_basis_of_the_original_lp(force_rsx, case, S):
     """b200lp_get_basis on the large-LP path (BasisManager.row_stat / col_stat, cython_glpk.pyx:197-232): GLPK-coded statuses
     in the ORIGINAL row space.  Exactly m variables are basic, every non-basic variable sits on the bound its status names,
     and the basic columns / rows form a non-singular basis matrix whose solution is the engine's x."""
-    from lp_numpy import assemble
-
     s, tr = load_case(case)
     slots, days = synth_batch(s, tr, S, 3, seed=13, common=True)
     T = len(days)
@@ -168,34 +166,6 @@ def test_rsx_get_basis_is_a_valid_basis_of_the_original_lp(force_rsx, case, S):
     g = replay(gpu, s, slots, days)
     assert g[3].sum() == 0
     row, col = gpu.get_basis()
-    m, n = s.n_rows, s.n_cols
-    BS, NL, NU, NF, NS = 1, 2, 3, 4, 5
     for k in (0, S // 2, S - 1):
-        A, lo, hi, c = assemble(s, slots[T - 1], k, float(days[T - 1]))
-        A = np.asarray(A.todense()) if hasattr(A, "todense") else np.asarray(A)
-        x = g[1][T - 1, :, k]
-        r = A @ x
-        assert (row[k] == BS).sum() + (col[k] == BS).sum() == m, ((row[k] == BS).sum(), (col[k] == BS).sum(), m)
-        scale = max(1.0, np.abs(x).max())
-        for j in range(n):
-            if col[k, j] in (NL, NS):
-                assert abs(x[j]) <= 1e-7 * scale, (j, x[j])
-            assert col[k, j] != NU            # original columns are x >= 0 without an upper bound
-        for i in range(m):
-            if row[k, i] == NL or row[k, i] == NS:
-                assert abs(r[i] - lo[i]) <= 1e-7 * scale, (i, r[i], lo[i])
-            elif row[k, i] == NU:
-                assert abs(r[i] - hi[i]) <= 1e-7 * scale, (i, r[i], hi[i])
-        # basis matrix of [A | -I] v = 0: basic columns of A and -e_i of the basic rows; non-singular, and solving with the
-        # non-basic variables on their bounds reproduces x
-        bc = np.nonzero(col[k] == BS)[0]
-        br = np.nonzero(row[k] == BS)[0]
-        B = np.hstack([A[:, bc], -np.eye(m)[:, br]])
-        assert np.linalg.matrix_rank(B) == m
-        rhs = np.zeros(m)
-        for i in range(m):
-            if row[k, i] != BS:
-                rhs[i] += (hi[i] if row[k, i] == NU else (0.0 if row[k, i] == NF else lo[i]))
-        sol = np.linalg.solve(B, rhs)      # A_B x_B - r_B = r_N  (non-basic columns are at 0)
-        assert np.allclose(sol[: len(bc)], x[bc], rtol=1e-7, atol=1e-7 * scale)
+        check_glpk_basis(s, slots[T - 1], float(days[T - 1]), k, g[1][T - 1, :, k], row[k], col[k])
     gpu.close()
