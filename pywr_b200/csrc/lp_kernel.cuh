@@ -112,8 +112,18 @@ struct DevState {
 };
 
 
+// minimum over the group of values that are >= 0 or +inf (ratios of the ratio tests).  A whole warp: the bit pattern of a
+// non-negative double orders like the number, so two REDUX (high word, then low word among the lanes that hold the smallest
+// high word) replace five dependent shuffle + DSETP rounds.
 template <int G>
 __device__ __forceinline__ double group_min(double v, unsigned mask) {
+    if (G == 32) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);   // -0.0 -> +0.0
+        const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    }
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, off, G));
     return v;
@@ -122,6 +132,24 @@ __device__ __forceinline__ double group_min(double v, unsigned mask) {
 // arg-max of (key, lowest idx on ties); idx < 0 means "no candidate"
 template <int G>
 __device__ __forceinline__ void group_argmax(double &key, int &idx, int &aux, unsigned mask) {
+    if (G == 32) {
+        // keys of candidates are > 0 (bound violations, |pivot elements|, 1.0 under Bland's rule): bit patterns order like the
+        // numbers.  Largest key by two REDUX, lowest index among the lanes that hold it by a third, winner's data by shuffles.
+        const bool cand = idx >= 0;
+        const unsigned long long b = cand ? (unsigned long long)__double_as_longlong(key) + 1ull : 0ull;
+        const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const bool top = cand && hi == mh && lo == ml;
+        const int best = (int)__reduce_min_sync(0xffffffffu, top ? (unsigned)idx : 0xffffffffu);
+        if (best < 0) { idx = -1; return; }   // no candidate anywhere (0xffffffff)
+        const unsigned who = __ballot_sync(0xffffffffu, top && idx == best);
+        const int src = __ffs(who) - 1;
+        key = __shfl_sync(0xffffffffu, key, src);
+        aux = __shfl_sync(0xffffffffu, aux, src);
+        idx = best;
+        return;
+    }
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
         const double k2 = __shfl_xor_sync(mask, key, off, G);
@@ -525,6 +553,7 @@ struct Dict {
                 publish_row(pl, ps);
                 // ---- dual ratio test ------------------------------------------------------------
                 double rmin = INFINITY;
+                double ratio1 = INFINITY, a1 = 0.0;   // NCP == G: this lane's one column, kept for the second pass
                 _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
                     const int s = sm.f->nbstat[j];
                     const double a = sm.f->prow[j] * (double)dir;
@@ -532,13 +561,16 @@ struct Dict {
                     if (s == VS_NL) ok = a > TOL_PIVOT;
                     else if (s == VS_NU) ok = a < -TOL_PIVOT;
                     else if (s == VS_NF) ok = fabs(a) > TOL_PIVOT;
-                    if (ok) rmin = fmin(rmin, fabs(sm.f->dw[j]) / fabs(a));
+                    if (ok) { ratio1 = fabs(sm.f->dw[j]) / fabs(a); a1 = a; rmin = fmin(rmin, ratio1); }
                 }
                 rmin = group_min<G>(rmin, gmask());
                 if (rmin == INFINITY) return B200LP_ST_INFEASIBLE;
                 const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
                 double amax = -1.0; int aux = 0;
                 q = -1;
+                if (NCP == G) {   // the same candidates and ratios as the first pass (one column per lane)
+                    if (ratio1 < INFINITY && !(ratio1 > thr)) { amax = bland ? 1.0 : fabs(a1); q = gl; }
+                } else {
                 _Pragma("unroll") for (int j = gl; j < NCP; j += G) {
                     const int s = sm.f->nbstat[j];
                     const double a = sm.f->prow[j] * (double)dir;
@@ -550,6 +582,7 @@ struct Dict {
                     if (fabs(sm.f->dw[j]) / fabs(a) > thr) continue;
                     const double key = bland ? 1.0 : fabs(a);
                     if (q < 0 || key > amax) { amax = key; q = j; }
+                }
                 }
                 group_argmax<G>(amax, q, aux, gmask());
                 to_upper = dir < 0;  // leaving variable goes to the bound it violated
