@@ -206,6 +206,7 @@ struct Spec {
     std::vector<double> stflow_w;
     std::vector<int> roll_len, roll_off;
     double uniform_days = 0.0;  // > 0: every timestep of the program has this length
+    bool defer_recorders = false;  // recorder samples of timestep t taken at the top of t + 1 (latency-bound batches)
     bool valid = false;
 };
 }  // namespace jit
@@ -927,6 +928,13 @@ static void jit_prepare(b200lp_handle *h) {
     int minb = jit_pick_blocks(grid);
     if (const char *v = getenv("B200LP_JIT_MINB")) { const int f = atoi(v); if (f >= 1 && f <= 8) minb = f; }
     h->jspec.minb = minb;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || sms <= 0) sms = 148;
+        const long long warps = ((long long)h->S * h->jspec.G + 31) / 32;
+        h->jspec.defer_recorders = warps <= 4LL * sms;   // at most one warp per scheduler
+        if (const char *v = getenv("B200LP_JIT_DEFER")) h->jspec.defer_recorders = atoi(v) != 0;
+    }
     const std::string src = jit::generate(h->jspec);
     if (const char *path = getenv("B200LP_JIT_DUMP")) { FILE *f = fopen(path, "w"); if (f) { fputs(src.c_str(), f); fclose(f); } }
     jit::Loaded *L = jit::get_kernel(src);

@@ -1680,6 +1680,18 @@ struct JitRecorders {
         if (store[u]) { *rout[u] = o; rout[u] += S; }
         racc[u] = ismin[u] ? fmin(racc[u], vv) : racc[u] + add;
     }
+    // the same, only when `on_now` (group-uniform): lets the generated code take the samples of timestep t-1 at the top of
+    // timestep t, where they fill the issue slots the recurrence (volume -> bounds -> basic values) leaves empty
+    __device__ __forceinline__ void sample_if(const int u, const bool on_now, const double o, const double add, const double vv, const int S) {
+        const double s2 = asum[u] + o;
+        asum[u] = on_now ? s2 : asum[u];
+        amin[u] = (on_now & ((o < amin[u]) | (o != o))) ? o : amin[u];
+        amax[u] = (on_now & ((o > amax[u]) | (o != o))) ? o : amax[u];
+        if (store[u] & on_now) *rout[u] = o;
+        rout[u] += (store[u] & on_now) ? S : 0;
+        const double r2 = ismin[u] ? fmin(racc[u], vv) : racc[u] + add;
+        racc[u] = on_now ? r2 : racc[u];
+    }
     __device__ __forceinline__ void finish(const int S) {
 #pragma unroll
         for (int u = 0; u < RU; u++) {
