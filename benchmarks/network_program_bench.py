@@ -27,11 +27,22 @@ from pywr_b200.engine import CudaEngine  # noqa: E402
 from pywr_b200.program import Program  # noqa: E402
 from pywr_b200.structure import LPStructure  # noqa: E402
 
-FIX = os.path.join(ROOT, "benchmarks", "fixtures", "network600")
+FIXTURES = {
+    # round-1 network: 2,073 nodes, one licence node, monthly-profile inflows x a per-scenario constant
+    "network600": os.path.join(ROOT, "benchmarks", "fixtures", "network600"),
+    # SURVEY 8(d) config 4 as specified: 40 aggregated nodes (20 with factors), 60 piecewise links, cycles, per-scenario DAILY
+    # AR(1) inflows (benchmarks/workloads.py::spec_network_document, tests/golden/make_netspec.py full)
+    "netspec2000": os.path.join(ROOT, "benchmarks", "fixtures", "netspec2000"),
+}
+FIX = FIXTURES["network600"]
 
 
 def widen(s, base, S, T, seed=20240903, rank=0):
-    """S scenarios: the per-scenario table(s) (the wetness factor) get S columns; scenario k < 2 keeps the fixture's value"""
+    """S scenarios: the per-scenario table(s) (the wetness factor) get S columns; scenario k < 2 keeps the fixture's value.
+    Time-indexed per-scenario tables (netspec2000: the regional daily AR(1) series) are regenerated for the global scenario
+    ids of this rank with the generator that made the fixture (benchmarks.workloads.regional_wetness)."""
+    from benchmarks.workloads import regional_wetness
+
     rng = np.random.default_rng([seed, rank])
     q = copy.copy(base)
     q.n_steps = T
@@ -40,7 +51,10 @@ def widen(s, base, S, T, seed=20240903, rank=0):
     for t in range(base.n_tables):
         r0, c0 = int(base.table_rows[t]), int(base.table_cols[t])
         data = base.table_data[base.table_offset[t]: base.table_offset[t] + r0 * c0].reshape(r0, c0)
-        if base.table_axis[t] >= 0:
+        if base.table_axis[t] >= 0 and r0 > 1:
+            region = next(r for r in range(16) if np.array_equal(regional_wetness(r0, 1, r)[:, 0], data[:, 0]))
+            data = regional_wetness(r0, S, region, first_scenario=rank * S)[:T]
+        elif base.table_axis[t] >= 0:
             wide = np.repeat(data[:, :1], S, axis=1) * rng.uniform(0.5, 1.25, size=(1, S))
             wide[:, : min(c0, S)] = data[:, : min(c0, S)]
             data = wide
@@ -82,7 +96,10 @@ def main():
     ap.add_argument("--scenarios", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=365)
     ap.add_argument("--engine", choices=["auto", "pdhg", "rsx"], default="auto")
+    ap.add_argument("--fixture", choices=sorted(FIXTURES), default="network600")
     a = ap.parse_args()
+    global FIX
+    FIX = FIXTURES[a.fixture]
     if a.engine != "auto":
         os.environ["B200LP_LARGE_ENGINE"] = a.engine
     world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
@@ -141,7 +158,7 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
     except Exception:
         pass
-    out = {"metric": "scenario-timesteps/sec (config 4, device-resident run)", "value": S_total * T / dev_s, "unit": "scenario-timesteps/s",
+    out = {"metric": "scenario-timesteps/sec (config 4, device-resident run)", "fixture": a.fixture, "value": S_total * T / dev_s, "unit": "scenario-timesteps/s",
            "n_gpus": world, "scaling": "weak", "scenarios": S_total, "scenarios_per_gpu": S, "timesteps": T, "device_s": dev_s, "wall_s": wall, "load_program_s": load_s, "readout_s": read_s,
            "kernel_variant": st0["kernel_variant"], "rows": s.n_rows, "cols": s.n_cols, "reduced_rows": m_r, "nodes": s.n_nodes,
            "ops": int(q.n_ops), "tables": int(q.n_tables), "recorders": int(q.n_recorders), "failed_scenarios_max_over_ranks": failed_all,

@@ -320,3 +320,148 @@ def algorithmic_bytes_per_scenario_step(info):
     """B = 8(n + 2m) + 2(m + n) + 16 n_st + 8 N + 8 n_rec."""
     m, n = info["rows"], info["cols"]
     return 8 * (n + 2 * m) + 2 * (m + n) + 16 * info["n_storage"] + 8 * info["nodes"] + 8 * info["n_recorders"]
+
+
+# ---- SURVEY.md 8(d) config 4 as specified ----------------------------------------------------------------------------
+def spec_network_document(scale=1.0, seed=20240903, start="2100-01-01", end="2100-12-31"):
+    """The generated network of config 4 with SURVEY 8(d)'s mix (at scale 1.0: ~2,000 primitive nodes — 150 reservoirs, 250
+    catchments, 300 demands, links for the rest — 40 AggregatedNodes, half of them with factors, 60 PiecewiseLinks of 2-3 steps,
+    river-TREE topology plus 4 transfers that close cycles; edge formulation).  Catchment inflows are monthly profiles here;
+    ``add_stochastic_inflows`` multiplies them by per-scenario daily AR(1) series.
+
+    Topology: reach k (k > 0) flows into an earlier reach chosen near k, so the tree is a few dozen reaches deep; leaves and
+    some inner reaches carry a catchment; every few reaches a tributary reservoir (reach -> abstraction -> storage -> town),
+    a direct river abstraction, or a minimum-residual-flow gauge; 60 reaches are PiecewiseLinks (a cheap channel of limited
+    capacity and a costly overflow); licences (AggregatedNode max_flow over ~6 abstractions) and paired intakes whose flows must
+    keep a fixed ratio (AggregatedNode factors); transfers take water from a reservoir back to a reach upstream of its own
+    intake (the only cycles)."""
+    rng = np.random.default_rng(seed)
+    n_reach = max(12, int(round(430 * scale)))
+    n_res, n_catch, n_farm = max(3, int(round(150 * scale))), max(6, int(round(250 * scale))), max(3, int(round(150 * scale)))
+    n_gauge, n_pw = max(2, int(round(35 * scale))), max(2, int(round(60 * scale)))
+    n_lic, n_fac, n_transfer = max(1, int(round(20 * scale))), max(1, int(round(20 * scale))), min(4, max(1, int(round(4 * scale))))
+    nodes, edges, params = [], [], {}
+    # river tree: reach k drains into parent[k] < k; the outlet is reach 0
+    parent = [-1] + [int(max(0, k - 1 - rng.integers(0, min(k, 12)))) for k in range(1, n_reach)]
+    children = [[] for _ in range(n_reach)]
+    for k in range(1, n_reach):
+        children[parent[k]].append(k)
+    leaves = [k for k in range(n_reach) if not children[k]]
+    inner = [k for k in range(1, n_reach) if children[k]]
+    catch_at = list(leaves)[:n_catch]
+    if len(catch_at) < n_catch:
+        catch_at += [int(k) for k in rng.choice(inner, size=min(len(inner), n_catch - len(catch_at)), replace=False)]
+    pw_at = set(int(k) for k in rng.choice(np.arange(1, n_reach), size=min(n_pw, n_reach - 1), replace=False))
+    gauge_at = set(int(k) for k in rng.choice([k for k in range(1, n_reach) if k not in pw_at], size=n_gauge, replace=False))
+    reach_name = [f"reach{k:04d}" for k in range(n_reach)]
+    for k in range(n_reach):
+        if k in pw_at:   # cheap channel of limited capacity, then a costly overflow (2 or 3 steps)
+            steps = int(rng.integers(2, 4))
+            caps = sorted(float(v) for v in rng.uniform(20.0, 120.0, steps - 1))
+            nodes.append({"name": reach_name[k], "type": "piecewiselink", "nsteps": steps, "max_flows": caps + [None],
+                          "costs": [0.0] + [float(v) for v in np.sort(rng.uniform(0.5, 3.0, steps - 1))]})
+        else:
+            nodes.append({"name": reach_name[k], "type": "link"})
+    out_of = {}   # what flows on downstream from reach k (the reach itself, or its gauge)
+    for k in range(n_reach):
+        out_of[k] = reach_name[k]
+        if k in gauge_at:
+            g = f"gauge{k:04d}"
+            nodes.append({"name": g, "type": "rivergauge", "mrf": float(rng.uniform(0.5, 3.0)), "mrf_cost": -1000.0})
+            edges.append([reach_name[k], g])
+            out_of[k] = g
+    for k in range(1, n_reach):
+        edges.append([out_of[k], reach_name[parent[k]]])
+    nodes.append({"name": "sea", "type": "output"})
+    edges.append([out_of[0], "sea"])
+    for i, k in enumerate(catch_at):
+        c = f"catch{i:04d}"
+        params[f"inflow{i:04d}"] = {"type": "monthlyprofile", "values": [float(v) for v in rng.uniform(1.0, 9.0, 12)]}
+        nodes.append({"name": c, "type": "catchment", "flow": f"inflow{i:04d}"})
+        edges.append([c, reach_name[k]])
+    # tributary reservoirs and direct abstractions on distinct reaches
+    sites = [int(k) for k in rng.permutation(np.arange(1, n_reach))]
+    res_at, farm_at = sites[:n_res], sites[n_res:n_res + n_farm]
+    abstractions, reservoirs = [], []
+    for i, k in enumerate(res_at):
+        ab, res, town = f"abs{i:04d}", f"res{i:04d}", f"town{i:04d}"
+        nodes.append({"name": ab, "type": "link", "max_flow": float(rng.uniform(3.0, 9.0)), "cost": 1.0})
+        nodes.append({"name": res, "type": "storage", "max_volume": float(rng.uniform(80, 400)), "initial_volume_pc": 0.8,
+                      "cost": -float(rng.uniform(2, 20))})
+        nodes.append({"name": town, "type": "output", "max_flow": float(rng.uniform(2.0, 7.0)), "cost": -float(rng.uniform(200, 600))})
+        edges += [[reach_name[k], ab], [ab, res], [res, town]]
+        abstractions.append(ab); reservoirs.append((res, k))
+    farms = []
+    for i, k in enumerate(farm_at):
+        intake, farm = f"intake{i:04d}", f"farm{i:04d}"
+        nodes.append({"name": intake, "type": "link", "max_flow": float(rng.uniform(0.5, 4.0))})
+        nodes.append({"name": farm, "type": "output", "max_flow": float(rng.uniform(0.5, 3.0)), "cost": -float(rng.uniform(50, 150))})
+        edges += [[reach_name[k], intake], [intake, farm]]
+        farms.append(intake)
+    # transfers: reservoir -> a reach upstream of its own intake (cycle), with a cost so that nothing circulates for free
+    upstream_of = lambda k: [c for c in children[k]] or [k]  # noqa: E731
+    for i in range(n_transfer):
+        res, k = reservoirs[int(rng.integers(0, len(reservoirs)))]
+        dest = upstream_of(k)[0]
+        t = f"transfer{i}"
+        nodes.append({"name": t, "type": "link", "max_flow": 2.0, "cost": 5.0})
+        if i % 2 == 0:   # from the reservoir (a cycle through storage: water can go round over several timesteps)
+            edges += [[res, t], [t, reach_name[dest]]]
+        else:            # pumped straight from the reach back upstream: a cycle of the graph itself
+            edges += [[reach_name[k], t], [t, reach_name[dest]]]
+    # licences: total abstraction of a group
+    pool = list(abstractions)
+    rng.shuffle(pool)
+    for i in range(n_lic):
+        group = pool[i * 6:(i + 1) * 6] or pool[:3]
+        nodes.append({"name": f"licence{i:02d}", "type": "aggregatednode", "nodes": group, "max_flow": float(3.5 * len(group))})
+    # paired intakes that must keep a fixed ratio
+    fp = list(farms)
+    rng.shuffle(fp)
+    for i in range(min(n_fac, len(fp) // 2)):
+        a, b = fp[2 * i], fp[2 * i + 1]
+        nodes.append({"name": f"ratio{i:02d}", "type": "aggregatednode", "nodes": [a, b], "factors": [1.0, float(rng.choice([0.5, 1.0, 2.0]))]})
+    return {"metadata": {"title": "generated network (SURVEY 8d config 4 mix)", "minimum_version": "0.1"},
+            "timestepper": {"start": start, "end": end, "timestep": 1},
+            "nodes": nodes, "edges": edges, "parameters": params, "recorders": {}}
+
+
+STOCHASTIC_SEED = 20240905
+
+
+def regional_wetness(T, n_scenarios, region, seed=STOCHASTIC_SEED, first_scenario=0, rho=0.9, sigma=0.45):
+    """[T, n_scenarios] log-normal AR(1) wetness factor of one region (mean 1): scenario k of the GLOBAL batch always gets the
+    same series (its generator is seeded with (seed, region, k)), whatever the batch size or the number of ranks."""
+    innov = sigma * np.sqrt(1.0 - rho * rho)
+    e = np.empty((T, n_scenarios))
+    z0 = np.empty(n_scenarios)
+    for k in range(n_scenarios):
+        rng = np.random.default_rng([seed, region, first_scenario + k])
+        e[:, k] = rng.standard_normal(T) * innov
+        z0[k] = rng.standard_normal() * sigma
+    z = np.empty((T, n_scenarios))
+    z[0] = z0
+    for t in range(1, T):
+        z[t] = rho * z[t - 1] + e[t]
+    return np.exp(z - 0.5 * sigma * sigma)
+
+
+def add_stochastic_inflows(model, n_scenarios, n_regions=4, seed=STOCHASTIC_SEED, first_scenario=0, rho=0.9, sigma=0.45):
+    """Scenario axis "inflow" with per-scenario DAILY stochastic inflows: every catchment's monthly profile is
+    multiplied by the log-normal AR(1) wetness series of its region (n_regions series per scenario, [T, S] each; scenario k of
+    the global batch always gets the same series).  All of it is device-evaluable (tables indexed by the scenario axis +
+    product ops)."""
+    from pywr.core import Scenario
+    from pywr.parameters import AggregatedParameter, ArrayIndexedScenarioParameter
+
+    T = len(model.timestepper) if model.timestepper._periods is not None else None
+    if T is None:
+        model.timestepper.setup()
+        T = len(model.timestepper)
+    axis = Scenario(model, "inflow", size=n_scenarios)
+    regions = [ArrayIndexedScenarioParameter(model, axis, regional_wetness(T, n_scenarios, r, seed, first_scenario, rho, sigma),
+                                             name=f"wetness{r}") for r in range(n_regions)]
+    catchments = sorted((n for n in model.nodes if n.name.startswith("catch")), key=lambda n: n.name)
+    for i, node in enumerate(catchments):
+        node.flow = AggregatedParameter(model, [node.max_flow, regions[i % n_regions]], agg_func="product", name=f"stoch_{node.name}")
+    return axis
