@@ -83,3 +83,30 @@ def test_param_sets_batch_on_gpu():
     for name in ra.recorders:
         assert rel_diff(ra.recorders[name], rb.recorders[name]) <= 1e-9, name
     assert ra.counters["pivots"] == rb.counters["pivots"]
+
+
+def test_config5_full_batch_objectives_equal_oracle():
+    """BASELINE.json configs[4] at its full batch: 256 control-curve parameter sets x 128 inflow scenarios = 32,768 scenario
+    combinations (10 of the 30 years, so that the CPU oracle finishes in seconds and its arrays fit the host), through the live
+    Pywr objects with arrays="none": the device keeps the temporal aggregates only and EVERY scenario's per-scenario recorder
+    value equals the oracle's; the pivot counts are identical."""
+    pytest.importorskip("pywr")
+    from benchmarks.workloads import build_model_param_sets
+    from oracle.oracle_engine import OracleEngine
+    from pywr_b200.device_run import run_on_device
+
+    P, I = 256, 128
+    a = build_model_param_sets(P, I, years=10, solver="null")
+    b = build_model_param_sets(P, I, years=10, solver="null")
+    ra = run_on_device(a, arrays="none")
+    rb = run_on_device(b, engine_factory=lambda s, S: OracleEngine(s, S, threads=16), arrays="none")
+    assert ra.num_scenarios == P * I == 32768 and ra.timesteps == 3652
+    for name in ra.recorders:
+        assert ra.recorders[name].shape == (P * I,)
+        assert rel_diff(ra.recorders[name], rb.recorders[name]) <= 1e-9, name
+    assert ra.counters["pivots"] == rb.counters["pivots"]
+    # objectives per parameter set the way the optimisation wrappers read them
+    for rec_a, rec_b in zip(a.recorders, b.recorders):
+        if hasattr(rec_a, "values"):
+            assert np.allclose(np.asarray(rec_a.values()), np.asarray(rec_b.values()), rtol=1e-9, atol=1e-12)
+    print(f"config 5: {ra.speed / 1e6:.0f} M scenario-timesteps/s on the device, read-out {ra.time_readout:.3f} s")
