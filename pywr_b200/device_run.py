@@ -59,6 +59,23 @@ class LazyRecorders(dict):
             self._eng = None
 
 
+def park_timestepper(model):
+    """Leaves the timestepper where a host run leaves it — ``current`` one past the end (pywr/timestepper.py:86-103),
+    ``model.timestep`` the last timestep — without stepping through the whole calendar: MeanFlow / DeficitFrequency
+    recorders divide by ``timestepper.current.index`` in ``finish()``."""
+    from pywr import _core
+
+    ts = model.timestepper
+    ts.reset()
+    last = len(ts._periods) - 1
+    ts._next = _core.Timestep(ts._periods[last], last, ts._deltas[last])
+    model.timestep = ts.next()
+    try:
+        ts.next()
+    except StopIteration:
+        pass
+
+
 def temporal_aggregate(rec, T, ssum, smin, smax):
     """Recorder.values() of an array recorder from the device's running aggregates, or None when its temporal
     aggregation needs the array itself (median, percentiles, custom callables, ignore_nan)."""
@@ -190,9 +207,7 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
             # park the timestepper one past the end, as after a host run (pywr/timestepper.py:86-103):
             # MeanFlow / DeficitFrequency recorders divide by current.index in finish()
             if not host_recs:
-                model.timestepper.reset()
-                for ts in model.timestepper:
-                    model.timestep = ts
+                park_timestepper(model)
             model.finish()
         t4 = time.perf_counter()
         counters = eng.counters()

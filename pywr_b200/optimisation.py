@@ -110,9 +110,9 @@ class PopulationEvaluator:
             else:
                 self._bridge.set_constant_recorder(rec, out)
         # MeanFlow / DeficitFrequency recorders divide by timestepper.current.index in finish() (parked past the end)
-        self.model.timestepper.reset()
-        for ts in self.model.timestepper:
-            self.model.timestep = ts
+        from .device_run import park_timestepper
+
+        park_timestepper(self.model)
         for rec in prog.recorders:
             rec.finish()
         self.evaluations += 1
