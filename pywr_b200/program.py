@@ -217,14 +217,16 @@ class _Compiler:
         self.S = len(model.scenarios.combinations)
         ts = model.timestepper
         self.T = len(ts)
-        self.timesteps = [_core.Timestep(ts._periods[i], i, ts._deltas[i]) for i in range(self.T)]
+        self._timesteps = None          # Timestep objects are built on first use (10,957 of them cost half a second)
+        self.days = np.asarray(ts._deltas[: self.T], dtype=np.float64)
+        self.months = np.asarray(ts._periods.month[: self.T], dtype=np.int32)
         self.combinations = list(model.scenarios.combinations)
         self.n_axes = len(model.scenarios.scenarios)
         self.scen_index = np.zeros((max(self.n_axes, 1), self.S), np.int32)
-        for si in self.combinations:
-            idx = np.asarray(si.indices)
-            for a in range(self.n_axes):
-                self.scen_index[a, si.global_id] = idx[a]
+        if self.n_axes and self.S:
+            idx = np.array([np.asarray(si.indices) for si in self.combinations], dtype=np.int32).reshape(self.S, -1)
+            gid = np.fromiter((si.global_id for si in self.combinations), dtype=np.int64, count=self.S)
+            self.scen_index[: self.n_axes, gid] = idx[:, : self.n_axes].T
         self.consts = list(structure.consts)
         self.n_slots = 0
         self.ops = []      # (kind, dst, args)
@@ -236,6 +238,35 @@ class _Compiler:
         self.population_axis = None
         self.variable_tables: Dict[int, int] = {}   # id(parameter) -> table index
         self.extra_storages = []                    # AggregatedStorage nodes: device storages without an LP row
+
+    @property
+    def timesteps(self):
+        if self._timesteps is None:
+            from pywr import _core
+
+            ts = self.model.timestepper
+            periods, deltas = list(ts._periods[: self.T]), list(ts._deltas[: self.T])
+            self._timesteps = [_core.Timestep(periods[i], i, deltas[i]) for i in range(self.T)]
+        return self._timesteps
+
+    def monthly_rows(self, sample):
+        """[T, k] table of a quantity that depends on the calendar month only: `sample(ts)` (a row of k numbers) is taken
+        at the first timestep of every month that occurs and the rows are expanded by the month of each timestep."""
+        from pywr import _core
+
+        ts = self.model.timestepper
+        first = {}
+        for i, mth in enumerate(self.months):
+            if int(mth) not in first:
+                first[int(mth)] = i
+                if len(first) == 12:
+                    break
+        rows = {mth: np.asarray(sample(_core.Timestep(ts._periods[i], i, ts._deltas[i])), dtype=np.float64) for mth, i in first.items()}
+        k = len(next(iter(rows.values())))
+        table = np.zeros((13, k))
+        for mth, row in rows.items():
+            table[mth] = row
+        return table[self.months]
 
     # -- small helpers ---------------------------------------------------------------------
     def const(self, v) -> int:
@@ -293,7 +324,10 @@ class _Compiler:
                 raise Unsupported(f"variable parameter of type {name} in a population batch")
             P = self.model.scenarios.scenarios[self.population_axis].size
             si = self.representative(None, 0)
-            rows = [[p.get_constant_value()] * P] if name == "ConstantParameter" else [[p.value(ts, si)] * P for ts in self.timesteps]
+            if name == "ConstantParameter":
+                rows = np.full((1, P), p.get_constant_value(), dtype=np.float64)
+            else:
+                rows = np.repeat(self.monthly_rows(lambda ts: [p.value(ts, si)]), P, axis=1)
             self.tables.append((np.ascontiguousarray(rows, dtype=np.float64), int(self.population_axis)))
             self.variable_tables[id(p)] = len(self.tables) - 1
             return self.emit(OP_TABLE, [len(self.tables) - 1, 0])
@@ -313,11 +347,15 @@ class _Compiler:
             return self.table(values, axis, int(info["offset"]))
         if name in _VALUE_LEAVES:
             si = self.representative(None, 0)
+            if name == "MonthlyProfileParameter":   # value(ts) = values[ts.month - 1]: 12 samples instead of T
+                return self.table(self.monthly_rows(lambda ts: [p.value(ts, si)]), None)
             return self.table(np.array([[p.value(ts, si)] for ts in self.timesteps]), None)
         if name in _SCENARIO_PROFILES:
             axis = _bridge.scenario_axis(p)
             size = self.model.scenarios.scenarios[axis].size
             sis = [self.representative(axis, c) for c in range(size)]
+            if name == "ScenarioMonthlyProfileParameter":
+                return self.table(self.monthly_rows(lambda ts: [p.value(ts, si) for si in sis]), axis)
             return self.table(np.array([[p.value(ts, si) for si in sis] for ts in self.timesteps]), axis)
         if name == "AggregatedParameter":
             func = p.agg_func
@@ -718,7 +756,7 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     f64 = lambda x: np.asarray(x, dtype=np.float64)  # noqa: E731
     prog = Program(
         n_steps=T, n_axes=C.n_axes,
-        ts_days=f64([ts.days for ts in C.timesteps]),
+        ts_days=f64(C.days),
         op_kind=i32([k for k, _, _ in C.ops]), op_dst=i32([d for _, d, _ in C.ops]),
         op_arg_ptr=i32(op_arg_ptr), op_args=i32(op_args),
         table_rows=i32([v.shape[0] for v, _ in C.tables]), table_cols=i32([v.shape[1] for v, _ in C.tables]),
@@ -733,7 +771,7 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     )
     prog.host_recorders = host_recorders
     prog.variable_tables = dict(C.variable_tables)
-    prog.months = np.array([ts.month for ts in C.timesteps], np.int32)
+    prog.months = np.asarray(C.months, np.int32)
     if roll_len.any():
         prog.st_roll_len, prog.st_roll_init = roll_len, roll_init
     return s, prog
