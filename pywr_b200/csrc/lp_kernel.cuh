@@ -44,6 +44,9 @@
 #endif
 #endif
 
+#ifndef B200LP_SUBWARP_REDUX   // REDUX over a sub-warp member mask (groups of 4 / 8 / 16 lanes); 0: shuffle rounds for those
+#define B200LP_SUBWARP_REDUX 1
+#endif
 #ifndef B200LP_RUN_MIN_BLOCKS
 #define B200LP_RUN_MIN_BLOCKS 3
 #endif
@@ -117,11 +120,12 @@ struct DevState {
 // high word) replace five dependent shuffle + DSETP rounds.
 template <int G>
 __device__ __forceinline__ double group_min(double v, unsigned mask) {
-    if (G == 32) {
+    if (G == 32 || B200LP_SUBWARP_REDUX) {   // sub-warp groups: every group reduces over its own member mask
+        const unsigned gm = G == 32 ? 0xffffffffu : mask;
         const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);   // -0.0 -> +0.0
         const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
-        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        const unsigned mh = __reduce_min_sync(gm, hi);
+        const unsigned ml = __reduce_min_sync(gm, hi == mh ? lo : 0xffffffffu);
         return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
     }
 #pragma unroll
@@ -132,21 +136,22 @@ __device__ __forceinline__ double group_min(double v, unsigned mask) {
 // arg-max of (key, lowest idx on ties); idx < 0 means "no candidate"
 template <int G>
 __device__ __forceinline__ void group_argmax(double &key, int &idx, int &aux, unsigned mask) {
-    if (G == 32) {
+    if (G == 32 || B200LP_SUBWARP_REDUX) {
         // keys of candidates are > 0 (bound violations, |pivot elements|, 1.0 under Bland's rule): bit patterns order like the
         // numbers.  Largest key by two REDUX, lowest index among the lanes that hold it by a third, winner's data by shuffles.
+        const unsigned gm = G == 32 ? 0xffffffffu : mask;
         const bool cand = idx >= 0;
         const unsigned long long b = cand ? (unsigned long long)__double_as_longlong(key) + 1ull : 0ull;
         const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const unsigned mh = __reduce_max_sync(gm, hi);
+        const unsigned ml = __reduce_max_sync(gm, hi == mh ? lo : 0u);
         const bool top = cand && hi == mh && lo == ml;
-        const int best = (int)__reduce_min_sync(0xffffffffu, top ? (unsigned)idx : 0xffffffffu);
+        const int best = (int)__reduce_min_sync(gm, top ? (unsigned)idx : 0xffffffffu);
         if (best < 0) { idx = -1; return; }   // no candidate anywhere (0xffffffff)
-        const unsigned who = __ballot_sync(0xffffffffu, top && idx == best);
-        const int src = __ffs(who) - 1;
-        key = __shfl_sync(0xffffffffu, key, src);
-        aux = __shfl_sync(0xffffffffu, aux, src);
+        const unsigned who = __ballot_sync(gm, top && idx == best) & gm;
+        const int src = (__ffs(who) - 1) & (G - 1);   // lane within the group
+        key = __shfl_sync(gm, key, src, G);
+        aux = __shfl_sync(gm, aux, src, G);
         idx = best;
         return;
     }
