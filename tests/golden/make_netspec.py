@@ -42,8 +42,11 @@ VARIANTS = {
 }
 
 
+SOLVER = os.environ.get("NETSPEC_SOLVER", "oracle-edge")   # oracle-rsx-edge: host build of the revised simplex (minutes, not an hour)
+
+
 def build(scale, S, end):
-    m = Model.load(spec_network_document(scale=scale, end=end), solver="oracle-edge")
+    m = Model.load(spec_network_document(scale=scale, end=end), solver=SOLVER)
     add_stochastic_inflows(m, S)
     return m
 
@@ -71,6 +74,8 @@ def add_recorders(m):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "small"
     scale, S, end, n_trace, base = VARIANTS[which]
+    if SOLVER != "oracle-edge":
+        base += "_" + SOLVER.replace("oracle-", "").replace("-edge", "")
     os.makedirs(os.path.dirname(base), exist_ok=True)
     m = build(scale, S, end)
     recs = add_recorders(m)
@@ -88,7 +93,8 @@ def main():
     sol._engine.step = step
     t0 = time.time()
     m.run()
-    print(f"host run (dictionary oracle): {time.time() - t0:.1f} s, {sol._engine.counters()}")
+    eng = sol._engine
+    print(f"host run ({SOLVER}): {time.time() - t0:.1f} s, {eng.counters() if hasattr(eng, 'counters') else eng.stats()}")
     expected = {r.name: (np.array(r.data) if hasattr(r, "data") else np.array(r.values())) for r in recs}
     s = sol.structure
     slots = np.array(trace["slots"])
