@@ -37,34 +37,46 @@ struct RsxCtx {
         return v;
     }
     __device__ __forceinline__ int bor(int v) { return __syncthreads_or(v); }
+    // arg-max of (key, lowest idx on ties) over a warp: keys of candidates are > 0 (bound violations, |pivot elements|, 1.0 under
+    // Bland's rule), so their bit patterns order like the numbers - two REDUX for the largest key, one for the lowest index
+    // among the lanes that hold it, the winner's data by shuffle (lp_kernel.cuh::group_argmax)
+    __device__ __forceinline__ void warp_argmax(double &key, int &idx, int &aux) {
+        const bool cand = idx >= 0;
+        const unsigned long long b = cand ? (unsigned long long)__double_as_longlong(key) + 1ull : 0ull;
+        const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const bool top = cand && hi == mh && lo == ml;
+        const int best = (int)__reduce_min_sync(0xffffffffu, top ? (unsigned)idx : 0xffffffffu);
+        if (best < 0) { idx = -1; return; }
+        const int src = __ffs(__ballot_sync(0xffffffffu, top && idx == best)) - 1;
+        key = __shfl_sync(0xffffffffu, key, src);
+        aux = __shfl_sync(0xffffffffu, aux, src);
+        idx = best;
+    }
     // arg-max of (key, lowest idx on ties) over the thread-local candidates; idx < 0: no candidate
     __device__ __forceinline__ void argmax(double &key, int &idx, int &aux) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double k2 = __shfl_xor_sync(0xffffffffu, key, off);
-            const int i2 = __shfl_xor_sync(0xffffffffu, idx, off);
-            const int a2 = __shfl_xor_sync(0xffffffffu, aux, off);
-            const bool take = (i2 >= 0) && (idx < 0 || k2 > key || (k2 == key && i2 < idx));
-            if (take) { key = k2; idx = i2; aux = a2; }
-        }
+        warp_argmax(key, idx, aux);
         if (lane == 0) { rv[warp] = key; ri[warp] = idx; ra[warp] = aux; }
         __syncthreads();
-        key = rv[0]; idx = ri[0]; aux = ra[0];
-        for (int w = 1; w < nw; w++) {
-            const double k2 = rv[w];
-            const int i2 = ri[w], a2 = ra[w];
-            const bool take = (i2 >= 0) && (idx < 0 || k2 > key || (k2 == key && i2 < idx));
-            if (take) { key = k2; idx = i2; aux = a2; }
-        }
+        // every warp reduces the per-warp winners again (at most 32 warps): no serial pass
+        key = lane < nw ? rv[lane] : -1.0; idx = lane < nw ? ri[lane] : -1; aux = lane < nw ? ra[lane] : 0;
+        warp_argmax(key, idx, aux);
         __syncthreads();
     }
+    // minimum of values that are >= 0 or +inf (ratios)
+    __device__ __forceinline__ double warp_min(double v) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);   // -0.0 -> +0.0
+        const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    }
     __device__ __forceinline__ double min(double v) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+        v = warp_min(v);
         if (lane == 0) rv[warp] = v;
         __syncthreads();
-        v = rv[0];
-        for (int w = 1; w < nw; w++) v = fmin(v, rv[w]);
+        v = warp_min(lane < nw ? rv[lane] : INFINITY);
         __syncthreads();
         return v;
     }

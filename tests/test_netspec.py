@@ -116,3 +116,41 @@ def test_cuda_trace_objectives_equal_highs(monkeypatch, engine):
             viol, obj = residuals(s, tr["slots"][t], k, float(tr["days"][t]), g[1][t, :, k])
             assert viol < 1e-7 * max(1.0, np.abs(g[1][t, :, k]).max())
     gpu.close()
+
+
+@pytest.mark.gpu
+def test_cuda_full_scale_network_first_month_equals_reference_host_run():
+    """The full-scale network of config 4 as specified (2,316 graph nodes: 150 reservoirs, 250 catchments, 301 outputs, 40
+    aggregated nodes, 60 piecewise links; LP 3,105 x 2,010; benchmarks/fixtures/netspec2000*): the first 30 days of the
+    device-resident run against the reference framework's host run (array recorders), and the traced timesteps against HiGHS."""
+    from pywr_b200.engine import CudaEngine
+    from pywr_b200.program import ARRAY_KINDS
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures")
+    base = os.path.join(root, "netspec2000")
+    if not os.path.exists(base + ".expected.npz"):
+        base = os.path.join(root, "netspec2000_rsx")
+    s = LPStructure.load(base + ".pstructure.npz")
+    prog = Program.load(base + ".program.npz")
+    z = np.load(base + ".expected.npz")
+    T = 30
+    gpu = CudaEngine(s, 2, device=0)
+    assert gpu.stats()["kernel_variant"] == 300
+    gpu.load_program(prog)
+    gpu.run(0, T)
+    gpu.sync()
+    assert gpu.program_status()[0] == 0
+    checked = 0
+    for r in range(prog.n_recorders):
+        if int(prog.rec_kind[r]) in ARRAY_KINDS:
+            out = gpu.fetch_recorder(r, prog.rec_shape(r, 2))
+            assert rel_diff(out[:T], z[f"rec{r}"][:T]) <= 1e-8, str(z["names"][r])
+            checked += 1
+    assert checked >= 10
+    gpu.close()
+    st = LPStructure.load(base + ".edge.structure.npz")
+    tr = np.load(base + ".edge.trace.npz")
+    gpu = CudaEngine(st, tr["slots"].shape[2], device=0)
+    g = replay(gpu, st, tr["slots"], tr["days"])
+    assert g[3].sum() == 0 and rel_diff(g[2], tr["objective_highs"]) <= 1e-9
+    gpu.close()
