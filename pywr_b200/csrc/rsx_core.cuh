@@ -100,10 +100,12 @@ struct Work {  // block-shared
 // global memory (L2-resident: 73 KB per block for config 4) — they are touched once per timestep and per pivot, with
 // coalesced accesses — which halves the shared-memory footprint: two blocks per SM, so that one scenario's serial phases
 // overlap another's stream of W, and LPs twice as large still fit.
+// g (right-hand side N x_N at the start of a solve, row activities at its end, y in compute_d) and w (the pivot column,
+// live only inside a pivot) are never live together: they share one vector.
 RSX_HD size_t work_bytes(int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
     const size_t fast_nv = mode == 0 ? 5 : 3, lists = mode == 0 ? 3 : 1;
-    return 8 * (fast_nv * nv + 4 * (size_t)m) + 4 * (lists * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
+    return 8 * (fast_nv * nv + 3 * (size_t)m) + 4 * (lists * (size_t)m) + ((nv + 15) & ~(size_t)15) + 64;
 }
 RSX_HD size_t scratch_bytes(int m, int n, int mode) {
     const size_t nv = (size_t)n + m;
@@ -115,7 +117,7 @@ RSX_FN void work_carve(Work &K, unsigned char *base, unsigned char *scratch, int
     K.LO = p; p += nv; K.HI = p; p += nv;
     if (mode == 0) { K.d = p; p += nv; K.dw = p; p += nv; }
     K.alpha = p; p += nv;  // the pivot row is read three to four times per pivot: always in fast memory
-    K.rho = p; p += m; K.w = p; p += m; K.beta = p; p += m; K.g = p; p += m;
+    K.rho = p; p += m; K.w = p; K.g = p; p += m; K.beta = p; p += m;
     int *q = reinterpret_cast<int *>(p);
     K.head = q; q += m;
     if (mode == 0) { K.list_k = q; q += m; K.list_i = q; q += m; }
