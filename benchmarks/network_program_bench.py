@@ -32,7 +32,7 @@ FIXTURES = {
     "network600": os.path.join(ROOT, "benchmarks", "fixtures", "network600"),
     # SURVEY 8(d) config 4 as specified: 40 aggregated nodes (20 with factors), 60 piecewise links, cycles, per-scenario DAILY
     # AR(1) inflows (benchmarks/workloads.py::spec_network_document, tests/golden/make_netspec.py full)
-    "netspec2000": os.path.join(ROOT, "benchmarks", "fixtures", "netspec2000_rsx"),
+    "netspec2000": os.path.join(ROOT, "benchmarks", "fixtures", "netspec2000"),
 }
 FIX = FIXTURES["network600"]
 

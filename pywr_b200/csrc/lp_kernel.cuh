@@ -1599,7 +1599,111 @@ struct JitLane {
         return group_or<G>((unsigned)lane_flags | (infe ? 4u : 0u) | (viol ? 8u : 0u), gm);
     }
 
-    // lane state -> the shared-memory layout the general solve works on
+    // beta = T xn with the non-basic values exchanged like in fast_check (same order of operations as Dict::basic_values)
+    template <int NREAL, bool SMEM_X>
+    __device__ __forceinline__ double basic_value(DictT &D, const double xv) const {
+        double acc = 0.0;
+        if (SMEM_X) {
+            D.sm.f->xn[D.gl] = xv;
+            D.sync();
+            const double2 *x2 = reinterpret_cast<const double2 *>(D.sm.f->xn);
+#pragma unroll
+            for (int j = 0; j + 1 < NREAL; j += 2) {
+                const double2 p = x2[j / 2];
+                acc = fma(D.T[0][j], p.x, acc);
+                acc = fma(D.T[0][j + 1], p.y, acc);
+            }
+            if (NREAL & 1) acc = fma(D.T[0][NREAL - 1], D.sm.f->xn[NREAL - 1], acc);
+            D.sync();   // xn is rewritten by the next exchange
+        } else {
+#pragma unroll
+            for (int j = 0; j < NREAL; j++) acc = fma(D.T[0][j], __shfl_sync(D.gmask(), xv, j, G), acc);
+        }
+        return acc;
+    }
+
+    // The common case of a timestep that pivots: the basis is dual feasible (no reduced cost has to be shifted) and a few
+    // dual simplex pivots restore primal feasibility.  This is phase 0 of Dict::solve with shifted == 0, on the lane state:
+    // the same leaving row (largest violation), the same ratio test (ties: largest pivot element, lowest position) and the
+    // same arithmetic for the dictionary, the reduced costs and the basic values, so the result is bit for bit what the
+    // general solve computes - without its shared-memory round trips.  Returns true when the basis is optimal; false hands
+    // over to the general solve (no entering candidate = infeasible LP, or more than MAXP pivots), which continues from the
+    // state reached so far.  Either way the lane state is written through to shared memory (nb, nbstat, d, xn) at the end.
+    template <int NREAL, bool SMEM_X, int MAXP>
+    __device__ __forceinline__ bool dual_pivots(DictT &D, const double mylo, const double myhi, int &npiv) {
+        const unsigned gm = D.gmask();
+        const int gl = D.gl, n = D.n;
+        double lob = sel_pred(hcol, 0.0, __shfl_sync(gm, mylo, hsrc, G)), hib = sel_pred(hcol, INFINITY, __shfl_sync(gm, myhi, hsrc, G));
+        bool optimal = false;
+#pragma unroll 1
+        for (int it = 0;; it++) {
+            const double b = D.beta[0];
+            double viol = 0.0; int dd = 0;
+            if (b < lob - TOL_PRIMAL * (1.0 + fabs(lob))) { viol = lob - b; dd = +1; }
+            else if (b > hib + TOL_PRIMAL * (1.0 + fabs(hib))) { viol = b - hib; dd = -1; }
+            double worst = -1.0; int bi = -1, dir = 0;
+            if (dd != 0) { worst = viol; bi = gl; dir = dd; }
+            if (group_ballot<G>(bi >= 0, gm) == 0u) { optimal = true; break; }
+            if (it >= MAXP) break;
+            group_argmax<G>(worst, bi, dir, gm);
+            const int pl = bi;
+            if (gl == pl) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) D.sm.f->prow[j] = D.T[0][j];
+            }
+            D.sync();
+            // dual ratio test: this lane's non-basic position (NCP == G)
+            const double a = D.sm.f->prow[gl] * (double)dir;
+            bool ok = false;
+            if (nstat == VS_NL) ok = a > TOL_PIVOT;
+            else if (nstat == VS_NU) ok = a < -TOL_PIVOT;
+            else if (nstat == VS_NF) ok = fabs(a) > TOL_PIVOT;
+            double ratio1 = INFINITY;
+            if (ok) ratio1 = fabs(dj) / fabs(a);
+            const double rmin = group_min<G>(ratio1, gm);
+            if (rmin == INFINITY) break;   // no entering candidate: the general solve reports it
+            const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
+            double amax = -1.0; int q = -1, aux = 0;
+            if (ratio1 < INFINITY && !(ratio1 > thr)) { amax = fabs(a); q = gl; }
+            group_argmax<G>(amax, q, aux, gm);
+            const bool to_upper = dir < 0;
+            const double vlo = __shfl_sync(gm, lob, pl, G), vhi = __shfl_sync(gm, hib, pl, G);
+            // Dict::pivot(pl, 0, q, use_dw) with dw == d
+            const double inv = 1.0 / D.sm.f->prow[q];
+            double pr[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) pr[j] = (j == q) ? inv : -D.sm.f->prow[j] * inv;
+            const bool is_piv = gl == pl;
+            const double f = D.col_of(0, q);
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const double tn = (j == q) ? f * inv : fma(f, pr[j], D.T[0][j]);
+                D.T[0][j] = is_piv ? pr[j] : tn;
+            }
+            const double fd = __shfl_sync(gm, dj, q, G);
+            const int vin = __shfl_sync(gm, nbv, q, G), vout = __shfl_sync(gm, D.head[0], pl, G);
+            const double prj = (gl == q) ? inv : -D.sm.f->prow[gl] * inv;
+            dj = (gl == q) ? fd * inv : fma(fd, prj, dj);
+            if (is_piv) D.head[0] = vin;
+            if (gl == q) {
+                nbv = vout;
+                nstat = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
+                xn = to_upper ? vhi : vlo;
+            }
+            D.pivots++; npiv++;
+            // bounds of the new basic variable of position pl (Dict::load_basic_bounds)
+            const int vrow = vin >= n ? vin - n : 0;
+            const double nlo = __shfl_sync(gm, mylo, vrow, G), nhi = __shfl_sync(gm, myhi, vrow, G);
+            if (is_piv) { lob = vin < n ? 0.0 : nlo; hib = vin < n ? INFINITY : nhi; }
+            D.sync();   // prow is rewritten by the next iteration
+            D.beta[0] = basic_value<NREAL, SMEM_X>(D, xn);
+        }
+        D.sm.f->nb[gl] = nbv; D.sm.f->nbstat[gl] = nstat; D.sm.f->d[gl] = dj; D.sm.f->xn[gl] = xn;
+        D.sync();
+        return optimal;
+    }
+
+    // lane state -> the shared-memory layout the general solve works on    // lane state -> the shared-memory layout the general solve works on
     __device__ __forceinline__ void materialize(DictT &D, const double mylo, const double myhi) {
         if (D.gl < D.m) { D.sm.f->LO[1 + D.n + D.gl] = mylo; D.sm.f->HI[1 + D.n + D.gl] = myhi; }
         D.sm.f->nbstat[D.gl] = nstat;

@@ -128,8 +128,6 @@ def test_cuda_full_scale_network_first_month_equals_reference_host_run():
 
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures")
     base = os.path.join(root, "netspec2000")
-    if not os.path.exists(base + ".expected.npz"):
-        base = os.path.join(root, "netspec2000_rsx")
     s = LPStructure.load(base + ".pstructure.npz")
     prog = Program.load(base + ".program.npz")
     z = np.load(base + ".expected.npz")
@@ -154,3 +152,14 @@ def test_cuda_full_scale_network_first_month_equals_reference_host_run():
     g = replay(gpu, st, tr["slots"], tr["days"])
     assert g[3].sum() == 0 and rel_diff(g[2], tr["objective_highs"]) <= 1e-9
     gpu.close()
+
+
+def test_full_scale_fixture_two_independent_simplexes_agree():
+    """benchmarks/fixtures/netspec2000.expected.npz: host run of the reference framework over all 365 days with the DICTIONARY
+    oracle as LP solver (15,121 pivots, 51 minutes); netspec2000_rsx.expected.npz: the same run with the host build of the
+    revised simplex (13,144 pivots, 13 seconds).  Two independent simplex implementations, one set of recorder arrays."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "fixtures")
+    a, b = np.load(os.path.join(root, "netspec2000.expected.npz")), np.load(os.path.join(root, "netspec2000_rsx.expected.npz"))
+    assert [str(n) for n in a["names"]] == [str(n) for n in b["names"]]
+    for i in range(len(a["names"])):
+        assert rel_diff(a[f"rec{i}"], b[f"rec{i}"]) <= 1e-9, str(a["names"][i])
