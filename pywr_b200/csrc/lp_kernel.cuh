@@ -1684,11 +1684,16 @@ struct JitLane {
             const int vin = __shfl_sync(gm, nbv, q, G), vout = __shfl_sync(gm, D.head[0], pl, G);
             const double prj = (gl == q) ? inv : -D.sm.f->prow[gl] * inv;
             dj = (gl == q) ? fd * inv : fma(fd, prj, dj);
-            if (is_piv) D.head[0] = vin;
+            if (is_piv) { D.head[0] = vin; hcol = vin < n; hsrc = vin >= n ? vin - n : gl; }
             if (gl == q) {
-                nbv = vout;
+                nbv = vout; ncol = vout < n; nsrc = vout >= n ? vout - n : gl;
                 nstat = (vlo == vhi) ? VS_NS : (to_upper ? VS_NU : VS_NL);
                 xn = to_upper ? vhi : vlo;
+            }
+            if (gl == 0) {   // the position table derive() built (row_loc / col_loc / rloc read it)
+                int *pos = D.sm.f->vstat;
+                pos[vin < n ? vin : NCP + (vin - n)] = pl;
+                pos[vout < n ? vout : NCP + (vout - n)] = G + q;
             }
             D.pivots++; npiv++;
             // bounds of the new basic variable of position pl (Dict::load_basic_bounds)
@@ -1698,15 +1703,15 @@ struct JitLane {
             D.sync();   // prow is rewritten by the next iteration
             D.beta[0] = basic_value<NREAL, SMEM_X>(D, xn);
         }
-        D.sm.f->nb[gl] = nbv; D.sm.f->nbstat[gl] = nstat; D.sm.f->d[gl] = dj; D.sm.f->xn[gl] = xn;
         D.sync();
+        rloc = gl < D.m ? D.sm.f->vstat[NCP + gl] : gl;
         return optimal;
     }
 
     // lane state -> the shared-memory layout the general solve works on    // lane state -> the shared-memory layout the general solve works on
     __device__ __forceinline__ void materialize(DictT &D, const double mylo, const double myhi) {
         if (D.gl < D.m) { D.sm.f->LO[1 + D.n + D.gl] = mylo; D.sm.f->HI[1 + D.n + D.gl] = myhi; }
-        D.sm.f->nbstat[D.gl] = nstat;
+        D.sm.f->nb[D.gl] = nbv; D.sm.f->nbstat[D.gl] = nstat; D.sm.f->d[D.gl] = dj;
         D.sync();
     }
     // ... and back after it returned B200LP_ST_OPTIMAL (D.beta is current, see extract_solution)
@@ -1716,7 +1721,7 @@ struct JitLane {
     }
     // end of the launch: what extract_solution / store_state read from shared memory
     __device__ __forceinline__ void to_shared(DictT &D) {
-        D.sm.f->nbstat[D.gl] = nstat;
+        D.sm.f->nb[D.gl] = nbv; D.sm.f->nbstat[D.gl] = nstat; D.sm.f->d[D.gl] = dj;
         D.sm.f->xn[D.gl] = xn;
         D.sync();
     }
