@@ -159,7 +159,15 @@ def run_cpu(s, prog, info, steps, warmup, threads):
     return units * len(times) / sum(times), float(np.mean(times)), nfail
 
 
-E2E_CHUNKS = int(os.environ.get("B200_BENCH_CHUNKS", "16"))   # time slices of the pipelined end-to-end run
+E2E_CHUNKS = int(os.environ.get("B200_BENCH_CHUNKS", "0"))   # time slices of the pipelined end-to-end run; 0: by input size
+
+
+def e2e_chunks(table_bytes):
+    """16 slices for the full-size tables (measured best at 150 - 360 MB), about one per 12 MB below that (a slice costs a
+    launch and a pair of event waits: 512 thames scenarios, 45 MB: 4 slices 6.92 ms, 16 slices 7.26 ms)."""
+    if E2E_CHUNKS > 0:
+        return E2E_CHUNKS
+    return int(max(2, min(16, round(table_bytes / 12e6))))
 
 
 def years_of(workload, years):
@@ -229,9 +237,11 @@ class Bench:
                 for r in range(prog.n_recorders)]
         d2h = sum(a.nbytes for a in outs if a is not None) + (0 if full_arrays else 3 * 8 * S * len(arrays))
 
+        chunks = self.chunks = e2e_chunks(self.host_in.nbytes)
+
         def step():
             # the call a user makes: host table in, per-scenario recorder results out, time slices pipelined
-            eng.run_pipelined({self.inflow_table: self.host_in}, outs, chunks=E2E_CHUNKS)
+            eng.run_pipelined({self.inflow_table: self.host_in}, outs, chunks=chunks)
             if not full_arrays:
                 for r in arrays:
                     eng.fetch_recorder_agg(r)     # (sum, min, max) over time per scenario: Recorder.values()
@@ -372,7 +382,7 @@ def main():
                     "the per-scenario recorder results ([S] accumulators; sum / min / max over time of the array recorders)")
             out[key] = {"value": world * b.units * steps / e2e_time, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_time / steps * 1e3,
-                        "api": f"b200lp_run_pipelined: reset + upload + run + read-out of {what}, {E2E_CHUNKS} time slices on "
+                        "api": f"b200lp_run_pipelined: reset + upload + run + read-out of {what}, {b.chunks} time slices on "
                                "three streams (pinned host buffers)"}
         return out
 
