@@ -144,6 +144,9 @@ struct HostStructure {
     int m = 0, n = 0, n_slots = 0, n_consts = 0, n_storage = 0, n_dyn_a = 0, cost_dynamic = 0, rows_cap = 0;
     int vol_base = 0, pc_base = 0, n_val = 0, k_base = 0;
     std::vector<int> row_class, row_a, row_b, st_kind, st_row, st_vol, st_minv, st_maxv, st_act;
+    int cost_clip = 0;
+    std::vector<int> cost_indptr, cost_idx;   // objective: c_j = sum cost_w[k] * V[cost_idx[k]] (a3)
+    std::vector<double> cost_w;
 };
 
 static bool resolve_structure(const b200lp_structure *s, int rows_cap, HostStructure &hs, std::string &err) {
@@ -153,6 +156,15 @@ static bool resolve_structure(const b200lp_structure *s, int rows_cap, HostStruc
     hs.cost_dynamic = 0;
     for (int k = 0; k < s->cost_indptr[n]; k++)
         if (s->cost_ref[k] >= 0) hs.cost_dynamic = 1;
+    hs.cost_clip = s->cost_clip;
+    hs.cost_indptr.assign(s->cost_indptr, s->cost_indptr + n + 1);
+    hs.cost_w.assign(s->cost_w, s->cost_w + s->cost_indptr[n]);
+    hs.cost_idx.resize(s->cost_indptr[n]);
+    for (int k = 0; k < s->cost_indptr[n]; k++) {
+        const int ref = s->cost_ref[k];
+        if (ref >= 0 ? ref >= s->n_slots : (ref == B200LP_REF_STATE || (-ref - 1) >= s->n_consts)) { err = "cost ref out of range"; return false; }
+        hs.cost_idx[k] = ref >= 0 ? ref : s->n_slots + (-ref - 1);
+    }
     hs.vol_base = s->n_slots + s->n_consts;
     hs.pc_base = hs.vol_base + s->n_storage;
     hs.n_val = hs.pc_base + s->n_storage;

@@ -48,6 +48,8 @@ CASES = [
     # interpolated control curves (ops B200LP_OP_CC_INTERP / CC_PIECEWISE) and an AggregatedStorage on the device
     ("cc_interpolated", "custom:interpolated", "route", "2101-12-31"),
     ("aggregated_storage", "custom:aggregated_storage", "route", None),
+    # a reservoir whose COST is an interpolated control curve: the objective changes every timestep (a3, cost_dynamic)
+    ("reservoir_with_cc", "tests/models/reservoir_with_cc.json", "route", None),
 ]
 
 
