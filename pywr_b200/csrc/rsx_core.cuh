@@ -672,9 +672,10 @@ RSX_FN double write_solution(CX &cx, const Lp &P, const Scen &S, Work &K) {
 // Crossover to a vertex (north_star: "a batched restarted-PDHG path ... followed by crossover to a vertex").  x0 is a point
 // that is optimal within the first-order method's tolerance (structural values of the scaled LP, element stride ldx0).
 //  1. every variable is classified against its bounds: on a bound -> non-basic there, strictly between -> wanted basic;
-//  2. the basis is crashed from the slack basis: every wanted structural is pivoted in against the slack of a row that
-//     sits on a bound (largest pivot element; a structural without an acceptable pivot stays non-basic at its nearer bound,
-//     a slack that could not leave stays basic) - m basic variables, non-singular by construction;
+//  2. the basis is crashed: starting from the scenario's vertex of the previous timestep (or from the slack basis after a
+//     reset) every wanted structural that is not basic is pivoted in against a basic variable that should sit on a bound
+//     (largest pivot element; a structural without an acceptable pivot stays non-basic at its nearer bound, a variable that
+//     could not leave stays basic) - m basic variables, non-singular by construction, a handful of pivots per timestep;
 //  3. the simplex of this file finishes from that basis (dual phase with shifted costs, primal clean-up): normally a handful
 //     of pivots, because the crashed basis is the optimal one up to degenerate ties.
 // The result is a vertex with a GLPK-style basis (b200lp_get_basis), like the one GLPK hands to BasisManager
@@ -700,7 +701,7 @@ RSX_FN int crossover(CX &cx, const Lp &P, const Scen &S, Work &K, const double *
         if (cx.lane == 0) K.g[i] = acc;
     }
     cx.sync();
-    // 1. classification (alpha keeps the value of every variable at x0 for the "nearer bound" decisions)
+    // 1. classification: the status every variable should have (in dw, as a number) and its value at x0 (in alpha)
     for (int v = cx.tid; v < nv; v += cx.nt) {
         const double val = v < n ? x0[(size_t)v * ldx0] : K.g[v - n];
         const double lo = K.LO[v], hi = K.HI[v];
@@ -710,46 +711,58 @@ RSX_FN int crossover(CX &cx, const Lp &P, const Scen &S, Work &K, const double *
         else if (lo > -INFINITY && val <= lo + tl) st = V_NL;
         else if (hi < INFINITY && val >= hi - th) st = V_NU;
         else st = V_BASIC;
-        K.stat[v] = (unsigned char)st;
+        K.dw[v] = (double)st;
         K.alpha[v] = val;
     }
-    // 2. crash: W = -I, head = slacks
-    for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = n + i;
-    const size_t tot = (size_t)m * P.ldw;
-    for (size_t e = cx.tid; e < tot; e += cx.nt) S.W[e] = 0.0;
-    cx.sync();
-    for (int i = cx.tid; i < m; i += cx.nt) S.W[(size_t)i * P.ldw + i] = -1.0;
+    // 2. crash.  Warm: the scenario's vertex of the previous timestep (its W is the inverse of that basis) is repaired - only the
+    // structurals that should be basic and are not get pivoted in, against basic variables that should sit on a bound.  Cold
+    // (first timestep after a reset): the same from the slack basis, W = -I.
+    const bool warm = S.info[0] != 0;
+    if (warm) {
+        for (int v = cx.tid; v < nv; v += cx.nt) K.stat[v] = S.stat[v];
+        for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = S.head[i];
+    } else {
+        for (int v = cx.tid; v < nv; v += cx.nt) K.stat[v] = (unsigned char)(v < n ? V_NL : V_BASIC);
+        for (int i = cx.tid; i < m; i += cx.nt) K.head[i] = n + i;
+        const size_t tot = (size_t)m * P.ldw;
+        for (size_t e = cx.tid; e < tot; e += cx.nt) S.W[e] = 0.0;
+        cx.sync();
+        for (int i = cx.tid; i < m; i += cx.nt) S.W[(size_t)i * P.ldw + i] = -1.0;
+    }
     cx.sync();
     int entered = 0;
     for (int q = 0; q < n; q++) {
-        if (K.stat[q] != V_BASIC) continue;
+        if ((int)K.dw[q] != V_BASIC || K.stat[q] == V_BASIC) continue;
         compute_w(cx, P, S, K, q);
         double best = 1e-7; int bi = -1, aux = 0;
         for (int i = cx.tid; i < m; i += cx.nt) {
-            const int v = K.head[i];
-            if (v < n || K.stat[v] == V_BASIC) continue;  // already a structural, or a slack that is wanted basic
+            if ((int)K.dw[K.head[i]] == V_BASIC) continue;   // this basic variable is where it should be
             const double a = fabs(K.w[i]);
             if (a > best) { best = a; bi = i; }
         }
         if (bi < 0) best = -1.0;
         cx.argmax(best, bi, aux);
-        if (bi < 0) {  // no slack on a bound can give way: the structural goes to its nearer bound
-            if (cx.leader()) {
-                const double lo = K.LO[q], hi = K.HI[q], val = K.alpha[q];
-                K.stat[q] = (unsigned char)(!(lo > -INFINITY) ? (hi < INFINITY ? V_NU : V_NF) : (!(hi < INFINITY) ? V_NL : (val - lo <= hi - val ? V_NL : V_NU)));
-            }
-            cx.sync();
-            continue;
-        }
+        if (bi < 0) continue;   // nothing can give way: the structural stays non-basic (status set below)
         load_rho(cx, P, S, K, bi);
         update_W(cx, P, S, K, bi);
-        if (cx.leader()) K.head[bi] = q;
+        if (cx.leader()) {
+            const int p = K.head[bi];
+            K.stat[p] = (unsigned char)(int)K.dw[p];
+            K.head[bi] = q;
+            K.stat[q] = V_BASIC;
+        }
         cx.sync();
         entered++;
     }
-    for (int i = cx.tid; i < m; i += cx.nt) {
-        const int v = K.head[i];
-        if (v >= n) K.stat[v] = V_BASIC;     // slacks that did not leave are basic, whatever their classification said
+    // non-basic variables go where the point has them; one that should be basic but could not enter goes to its nearer bound
+    for (int v = cx.tid; v < nv; v += cx.nt) {
+        if (K.stat[v] == V_BASIC) continue;
+        int st = (int)K.dw[v];
+        if (st == V_BASIC) {
+            const double lo = K.LO[v], hi = K.HI[v], val = K.alpha[v];
+            st = !(lo > -INFINITY) ? (hi < INFINITY ? V_NU : V_NF) : (!(hi < INFINITY) ? V_NL : (val - lo <= hi - val ? V_NL : V_NU));
+        }
+        K.stat[v] = (unsigned char)st;
     }
     cx.sync();
     crashed += entered;
