@@ -486,7 +486,13 @@ def main():
             steps1 = (res1.timestep.index + 1) * S
             m2 = build_model(args.workload, S, years=yrs, solver="null")
             res2 = run_on_device(m2)
+            m3 = build_model(args.workload, S, years=yrs, solver="b200", solver_args={"device_run": True})
+            res3 = m3.run()
             pywr_extra = {
+                "model_run_solver_b200_device_run": {
+                    "value": res3.timesteps * S / res3.time_taken, "unit": UNIT, "years": yrs,
+                    "note": "Model.run() of a model whose solver entry says {\"name\": \"b200\", \"device_run\": true}: the literal "
+                            "drop-in call, routed to the device-resident run; compile + run + read-out into Pywr's objects"},
                 "model_run_solver_b200": {"value": steps1 / res1.time_taken, "unit": UNIT, "years": yrs,
                                           "note": "Model.run(): Pywr's own before()/after() on the host every timestep, "
                                                   "one b200lp_step per timestep"},

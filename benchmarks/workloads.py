@@ -167,7 +167,7 @@ WORKLOADS = {
 }
 
 
-def build_model(name, n_scenarios, years=None, solver=None, inflow=None, first_scenario=0):
+def build_model(name, n_scenarios, years=None, solver=None, inflow=None, first_scenario=0, solver_args=None):
     """The workload as a live Pywr model (needs the reference framework): the document above plus a
     Scenario("inflow", size=S) and an ArrayIndexedScenarioParameter with the synthetic inflow feeding
     every catchment."""
@@ -180,6 +180,8 @@ def build_model(name, n_scenarios, years=None, solver=None, inflow=None, first_s
     idx = daily_index(w["start"], years=years)
     doc = w["document"](str(idx[0].date()), str(idx[-1].date()))
     kwargs = {"solver": solver} if solver else {}
+    if solver_args:
+        kwargs["solver_args"] = dict(solver_args)
     model = Model.load(doc, **kwargs)
     scenario = Scenario(model, "inflow", size=n_scenarios)
     if inflow is None:

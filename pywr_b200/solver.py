@@ -54,8 +54,16 @@ class BatchedLPSolver(_SolverBase):
     name = "batched-lp"
     formulation = "route"
 
-    def __init__(self, save_routes_flows=False, retry_solve=False, use_presolve=False, check_nan=True, **kwargs):
+    def __init__(self, save_routes_flows=False, retry_solve=False, use_presolve=False, check_nan=True, device_run=False,
+                 device_run_devices=None, device_run_arrays="eager", **kwargs):
         super().__init__()
+        # device_run (JSON: "solver": {"name": "b200", "device_run": true}): Model.run() executes the whole run on the
+        # device (pywr_b200.device_run.run_on_device) instead of one solve per timestep; "require" raises when the model
+        # needs the host every timestep, True falls back to the per-timestep loop then.  device_run_devices / _arrays are
+        # run_on_device's `devices` and `arrays`.
+        self.device_run = device_run
+        self.device_run_devices = device_run_devices
+        self.device_run_arrays = device_run_arrays
         self.save_routes_flows = save_routes_flows
         self.retry_solve = retry_solve  # the engine always retries from the standard basis
         self.use_presolve = use_presolve
@@ -96,6 +104,10 @@ class BatchedLPSolver(_SolverBase):
 
     def _make_engine(self, structure, n_scenarios):  # pragma: no cover - abstract
         raise NotImplementedError
+
+    def _make_program_engine(self, structure, n_scenarios):
+        """engine of a device-resident run (``device_run``); the same kind as the per-timestep one by default"""
+        return self._make_engine(structure, n_scenarios)
 
     # -- Solver API -----------------------------------------------------------------------------
     def setup(self, model):
@@ -247,6 +259,13 @@ class B200Solver(BatchedLPSolver):
 
         return CudaEngine(structure, n_scenarios, **self.engine_args)
 
+    def _make_program_engine(self, structure, n_scenarios):
+        from .engine import CudaEngine, ShardedEngine
+
+        if self.device_run_devices is not None:
+            return ShardedEngine(structure, n_scenarios, devices=self.device_run_devices, for_program=True)
+        return CudaEngine(structure, n_scenarios, for_program=True, **self.engine_args)
+
 
 class B200EdgeSolver(B200Solver):
     """Edge formulation (role of ``CythonGLPKEdgeSolver``, ``cython_glpk.pyx:1098-1918``)."""
@@ -255,9 +274,57 @@ class B200EdgeSolver(B200Solver):
     formulation = "edge"
 
 
+def _install_device_run():
+    """``Model.run()`` (``pywr/_model.pyx:637-682``) is a loop of ``solver.solve`` calls that a solver cannot take over from
+    the inside.  For models whose solver was created with ``device_run`` the method is routed to the device-resident run,
+    which returns the same :class:`ModelResult`; every other model runs the reference's own method untouched."""
+    import time
+
+    import pywr
+    from pywr import _model
+
+    if getattr(_model.Model.run, "_b200_device_run", False):
+        return
+    original = _model.Model.run
+
+    def run(self):
+        solver = self.solver
+        mode = getattr(solver, "device_run", False)
+        if not mode:
+            return original(self)
+        from .device_run import run_on_device
+        from .program import Unsupported
+
+        t0 = time.time()
+        try:
+            res = run_on_device(self, formulation=solver.formulation, arrays=solver.device_run_arrays,
+                                engine_factory=solver._make_program_engine)
+        except Unsupported:
+            if mode == "require":
+                raise
+            return original(self)
+        total = time.time() - t0
+        timestep = self.timestep
+        time_taken = res.time_compile + res.time_run + res.time_readout
+        return _model.ModelResult(
+            num_scenarios=res.num_scenarios, timestep=timestep, time_taken=time_taken, time_taken_before=0.0,
+            time_taken_after=0.0, time_taken_with_overhead=total,
+            speed=(timestep.index * res.num_scenarios) / time_taken if time_taken > 0 else float("nan"),
+            solver_name=solver.name, solver_settings=dict(solver.settings, device_run=True),
+            solver_stats=dict(solver.stats or {}, device_run_s=res.time_run, compile_s=res.time_compile, readout_s=res.time_readout,
+                              pivots=res.counters.get("pivots")),
+            version=pywr.__version__)
+
+    run._b200_device_run = True
+    run.__doc__ = original.__doc__
+    _model.Model.run = run
+
+
 def register():
     """Append the solvers to ``pywr.solvers.solver_registry`` (``pywr/solvers/__init__.py:14``)."""
     import pywr.solvers as ps
+
+    _install_device_run()
 
     for cls in (B200Solver, B200EdgeSolver):
         if not any(getattr(c, "name", None) == cls.name for c in ps.solver_registry):

@@ -224,3 +224,25 @@ def test_mid_size_models_run_device_resident_without_any_override():
     got = _recorder_values(m_step)
     for k in want:
         assert rel_diff(got[k], want[k]) <= 1e-6, k
+
+
+def test_model_run_on_the_device_through_the_solver_option():
+    """The literal drop-in on the GPU: ``Model.load(doc, solver="b200", solver_args={"device_run": True}).run()`` executes the
+    whole run on the device (one launch of the specialised run kernel) and leaves Pywr's recorder objects as the per-timestep
+    ``solver="b200"`` run leaves them; ``device_run_devices`` shards the scenarios over handles / GPUs."""
+    from benchmarks.workloads import build_model
+
+    S = 96
+    host = build_model("thames", S, years=2, solver="b200")
+    rh = host.run()
+    dev = build_model("thames", S, years=2, solver="b200", solver_args={"device_run": "require"})
+    rd = dev.run()
+    assert rd.timesteps == rh.timesteps and rd.num_scenarios == S and rd.solver_settings.get("device_run") is True
+    for name in ("volume", "supplied", "deficit"):
+        a, b = host.recorders[name], dev.recorders[name]
+        assert np.allclose(np.asarray(b.values()), np.asarray(a.values()), rtol=1e-9, atol=1e-12), name
+    assert np.allclose(np.array(dev.recorders["volume"].data), np.array(host.recorders["volume"].data), rtol=1e-9, atol=1e-12)
+    assert rd.speed > 20 * rh.speed
+    many = build_model("thames", S, years=2, solver="b200", solver_args={"device_run": "require", "device_run_devices": [0, 0]})
+    many.run()
+    assert np.array_equal(np.array(many.recorders["volume"].data), np.array(dev.recorders["volume"].data))

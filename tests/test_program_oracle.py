@@ -223,3 +223,53 @@ def test_constant_factor_changed_between_runs_reaches_the_lp():
     m2, A2, B2, _ = make(0.5)
     m2.step()
     assert np.allclose([A.flow[0], B.flow[0]], [A2.flow[0], B2.flow[0]]) and np.allclose(B.flow[0], 3.0)
+
+
+def test_model_run_with_device_run_solver_option():
+    """The literal drop-in: a model document whose solver entry says ``device_run`` runs ENTIRELY on the device when the
+    user calls ``Model.run()`` (pywr/_model.pyx:637-682) — same ModelResult, same recorder contents — and falls back to the
+    per-timestep loop for a model the device cannot evaluate (a custom Python parameter here), unless "require" is given."""
+    pytest.importorskip("pywr")
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.parameters import Parameter
+    from pywr.recorders import NumpyArrayNodeRecorder, NumpyArrayStorageRecorder, TotalDeficitNodeRecorder
+    from pywr_b200.program import Unsupported
+
+    def make(**solver_args):
+        m = Model.load(path, solver="oracle", solver_args=solver_args)
+        m.timestepper.end = "2100-12-31"
+        return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"]), NumpyArrayNodeRecorder(m, m.nodes["demand1"]),
+                   TotalDeficitNodeRecorder(m, m.nodes["demand1"])]
+    m1, r1 = make(); res1 = m1.run()
+    m2, r2 = make(device_run=True)
+    calls = []
+    orig_solve = m2.solver.solve
+    m2.solver.solve = lambda model: (calls.append(1), orig_solve(model))[1]
+    res2 = m2.run()
+    assert not calls, "no per-timestep solve may happen on a device run"
+    assert res2.timesteps == res1.timesteps == 365 and res2.num_scenarios == 5 and res2.solver_settings["device_run"] is True
+    assert res2.timestep.index == res1.timestep.index and "device_run_s" in res2.solver_stats
+    for a, b in zip(r1, r2):
+        assert _rel(np.asarray(b.values()), np.asarray(a.values())) <= 1e-12
+    assert _rel(np.array(r2[0].data), np.array(r1[0].data)) <= 1e-12
+    res2.to_dataframe()
+
+    class Custom(Parameter):          # something only the host can evaluate
+        def value(self, ts, si):
+            return 3.5
+
+    m3, r3 = make(device_run=True)
+    m3.nodes["abs1"].max_flow = Custom(m3)
+    res3 = m3.run()                   # falls back to the reference's loop
+    assert res3.timesteps == 365 and "device_run" not in res3.solver_settings
+    assert _rel(np.array(r3[0].data), np.array(r1[0].data)) <= 1e-12
+    m4, _ = make(device_run="require")
+    m4.nodes["abs1"].max_flow = Custom(m4)
+    with pytest.raises(Unsupported):
+        m4.run()
