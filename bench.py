@@ -486,13 +486,21 @@ def main():
             steps1 = (res1.timestep.index + 1) * S
             m2 = build_model(args.workload, S, years=yrs, solver="null")
             res2 = run_on_device(m2)
-            m3 = build_model(args.workload, S, years=yrs, solver="b200", solver_args={"device_run": True})
-            res3 = m3.run()
+            full = years_of(args.workload, args.years)
+            drop = {}
+            for arrays in ("eager", "lazy"):    # the WHOLE workload through the literal call
+                m3 = build_model(args.workload, S, years=full, solver="b200", solver_args={"device_run": True, "device_run_arrays": arrays})
+                res3 = m3.run()
+                drop[arrays] = {"value": res3.timesteps * S / res3.time_taken, "unit": UNIT, "years": full,
+                                "compile_s": res3.solver_stats["compile_s"], "run_s": res3.solver_stats["device_run_s"],
+                                "readout_s": res3.solver_stats["readout_s"]}
+                del m3, res3
             pywr_extra = {
-                "model_run_solver_b200_device_run": {
-                    "value": res3.timesteps * S / res3.time_taken, "unit": UNIT, "years": yrs,
-                    "note": "Model.run() of a model whose solver entry says {\"name\": \"b200\", \"device_run\": true}: the literal "
-                            "drop-in call, routed to the device-resident run; compile + run + read-out into Pywr's objects"},
+                "model_run_solver_b200_device_run": dict(
+                    drop["eager"], arrays_lazy=drop["lazy"],
+                    note="Model.run() of a model whose solver entry says {\"name\": \"b200\", \"device_run\": true}: the literal "
+                         "drop-in call, routed to the device-resident run; time = compile + run + read-out into Pywr's objects "
+                         "(every [T, S] array by default; arrays_lazy: per-scenario values only, arrays on request)"),
                 "model_run_solver_b200": {"value": steps1 / res1.time_taken, "unit": UNIT, "years": yrs,
                                           "note": "Model.run(): Pywr's own before()/after() on the host every timestep, "
                                                   "one b200lp_step per timestep"},
