@@ -64,21 +64,99 @@ class PdhgPlan:
         def const_of(ref):
             return consts[-ref - 1] if ref < 0 else None
 
-        keep, sing_row, sing_col, sing_coef = [], [], [], []
+        # rows as sorted (column, value) lists without zeros
+        rows = []
         for i in range(m):
             k0, k1 = A.indptr[i], A.indptr[i + 1]
-            vals = A.data[k0:k1]
-            nzmask = vals != 0.0
-            cnt = int(nzmask.sum())
-            if cnt == 1:
-                k = k0 + int(np.nonzero(nzmask)[0][0])
-                sing_row.append(i); sing_col.append(int(A.indices[k])); sing_coef.append(float(A.data[k]))
+            rows.append([(int(j), float(v)) for j, v in sorted(zip(A.indices[k0:k1], A.data[k0:k1])) if v != 0.0])
+        # doubleton elimination (PdhgPlan::build in pdhg_engine.cuh, same order of decisions): a row  a x_p + b x_q = 0  with
+        # constant zero bounds and a b < 0 (the mass balance of a link with one edge in and one out) fixes x_q = rho x_p,
+        # rho = -a / b > 0: column q is folded into column p (in every other row, in the cost and - through its singleton
+        # rows - in the bounds) and the row disappears.  Repeated until nothing changes: chains of links collapse.
+        alias_root = np.arange(n)
+        alias_ratio = np.ones(n)
+        elim_row = np.full(n, -1, np.int32)
+        gone = np.zeros(m, bool)
+
+        def zero_bounds(i):
+            if s.row_kind[i] != 0:
+                return False
+            lb, ub = const_of(int(s.row_lb_ref[i])), const_of(int(s.row_ub_ref[i]))
+            return lb is not None and ub is not None and abs(lb) < 1e-8 and abs(ub) < 1e-8
+
+        import os
+        changed = not os.environ.get("B200LP_NO_DOUBLETON")
+        while changed:
+            changed = False
+            ccount = np.zeros(n, np.int64)
+            for i in range(m):
+                if not gone[i]:
+                    for j, _ in rows[i]:
+                        ccount[j] += 1
+            for i in range(m):
+                r = rows[i]
+                if gone[i] or len(r) != 2 or not zero_bounds(i):
+                    continue
+                (p0, a), (p1, b) = r
+                if a * b >= 0.0:
+                    continue
+                q = p0 if (ccount[p0] < ccount[p1] or (ccount[p0] == ccount[p1] and p0 > p1)) else p1
+                pcol = p1 if q == p0 else p0
+                aq, ap = (a, b) if q == p0 else (b, a)
+                rho = -ap / aq
+                for k in range(m):
+                    if k == i or gone[k]:
+                        continue
+                    rk = rows[k]
+                    hit = [t for t, (j, _) in enumerate(rk) if j == q]
+                    if not hit:
+                        continue
+                    v = rk[hit[0]][1]
+                    d = dict(rk)
+                    del d[q]
+                    nv = d.get(pcol, 0.0) + v * rho
+                    if nv != 0.0:
+                        d[pcol] = nv
+                    elif pcol in d:
+                        del d[pcol]
+                    rows[k] = sorted(d.items())
+                gone[i] = True
+                alias_root[q], alias_ratio[q], elim_row[q] = pcol, rho, i
+                ccount[q] = 0
+                ccount[pcol] = sum(1 for k in range(m) if not gone[k] and any(j == pcol for j, _ in rows[k]))
+                changed = True
+        for j in range(n):          # chains: q -> p -> ... -> root
+            root, ratio = j, 1.0
+            while alias_root[root] != root:
+                ratio *= alias_ratio[root]
+                root = alias_root[root]
+            alias_root[j], alias_ratio[j] = root, ratio
+        self.alias_root, self.alias_ratio, self.elim_row = alias_root, alias_ratio, elim_row
+        self.members = [[(j, 1.0)] if alias_root[j] == j else [] for j in range(n)]
+        for q in range(n):
+            if alias_root[q] != q:
+                self.members[alias_root[q]].append((q, alias_ratio[q]))
+        keep, sing_row, sing_col, sing_coef = [], [], [], []
+        for i in range(m):
+            if gone[i]:
                 continue
-            if s.row_kind[i] == 0 and cnt > 0 and np.all(vals >= 0.0):
+            r = rows[i]
+            cnt = len(r)
+            if cnt == 1:
+                sing_row.append(i); sing_col.append(r[0][0]); sing_coef.append(r[0][1])
+                continue
+            if s.row_kind[i] == 0 and cnt > 0 and all(v >= 0.0 for _, v in r):
                 lb, ub = const_of(int(s.row_lb_ref[i])), const_of(int(s.row_ub_ref[i]))
                 if lb is not None and ub is not None and lb < 1e-8 and ub >= BIG:
                     continue  # can never bind
             keep.append(i)
+        # the transformed matrix (folded columns) replaces A from here on
+        ri, ci, vi = [], [], []
+        for i in range(m):
+            if not gone[i]:
+                for j, v in rows[i]:
+                    ri.append(i); ci.append(j); vi.append(v)
+        A = sp.csr_matrix((vi, (ri, ci)), shape=(m, n))
         self.keep = np.array(keep, np.int32)
         self.sing_row = np.array(sing_row, np.int32)
         self.sing_col = np.array(sing_col, np.int32)
@@ -155,12 +233,17 @@ def assemble(plan, slots_k, days, vol_k):
         lc[j] = max(lc[j], l); uc[j] = min(uc[j], u)
     c = np.zeros(n)
     for j in range(n):
-        acc = 0.0
-        for t in range(s.cost_indptr[j], s.cost_indptr[j + 1]):
-            acc += s.cost_w[t] * _ref_value(s, s.cost_ref[t], slots_k)
-        if s.cost_clip and abs(acc) < 1e-8:
+        tot = 0.0
+        for col, ratio in plan.members[j]:          # the column itself and every column folded into it
             acc = 0.0
-        c[j] = acc
+            for t in range(s.cost_indptr[col], s.cost_indptr[col + 1]):
+                acc += s.cost_w[t] * _ref_value(s, s.cost_ref[t], slots_k)
+            if s.cost_clip and abs(acc) < 1e-8:
+                acc = 0.0
+            tot += ratio * acc
+        c[j] = tot
+    dead = plan.alias_root != np.arange(n)
+    uc[dead] = 0.0                                  # folded columns: fixed at 0 in the reduced LP, rebuilt in snap_unscale
     status = ST_OPTIMAL
     if bad or np.isnan(lo).any() or np.isnan(hi).any() or np.isnan(lc).any() or np.isnan(uc).any() or np.isnan(c).any():
         status = ST_NAN
@@ -247,6 +330,8 @@ def snap_unscale(plan, xs, lc, uc):
     l, u = lc * plan.dc, uc * plan.dc
     x = np.where(np.abs(x - l) <= 1e-9 * (1.0 + np.abs(l)), l, x)
     x = np.where(np.abs(x - u) <= 1e-9 * (1.0 + np.abs(_fin(u))), u, x)
+    dead = plan.alias_root != np.arange(plan.n)
+    x[dead] = plan.alias_ratio[dead] * x[plan.alias_root[dead]]     # x_q = rho x_p of the folded columns
     return x
 
 

@@ -262,6 +262,11 @@ __global__ void rsx_basis_kernel(const RsxDev D, const PdhgDev P, const double *
     if (j == 0) {  // this thread also maps the kept rows (after every thread of the scenario wrote "basic" below: disjoint rows)
         for (int r = 0; r < D.lp.m; r++) rs[__ldg(&P.keep[r])] = stat[n + r];
     }
+    if (__ldg(&P.alias_root[j]) != j) {   // folded column (doubleton elimination): basic, its row an equality on its bound
+        rs[__ldg(&P.elim_row[j])] = rsx::V_NS;
+        cs[j] = rsx::V_BASIC;
+        return;
+    }
     int st = stat[j];
     double lc = 0.0, uc = INFINITY;
     int src_lo = -1, src_hi = -1, code_lo = 0, code_hi = 0;
