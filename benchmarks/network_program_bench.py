@@ -97,6 +97,7 @@ def main():
     ap.add_argument("--steps", type=int, default=365)
     ap.add_argument("--engine", choices=["auto", "pdhg", "rsx"], default="auto")
     ap.add_argument("--fixture", choices=sorted(FIXTURES), default="network600")
+    ap.add_argument("--phases", action="store_true", help="per-phase cycles of rsx_solve_kernel (needs B200LP_LIB = a -DRSX_PHASE_TIMING build)")
     a = ap.parse_args()
     global FIX
     FIX = FIXTURES[a.fixture]
@@ -168,6 +169,19 @@ def main():
            "roofline": {"bound": "hbm", "achieved": wbytes * S * T / dev_s / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": wbytes * S * T / dev_s / 1e9 / peak, "bytes_per_scenario_timestep": wbytes,
                         "note": "per GPU; algorithmic bytes = one read of the scenario's basis inverse per scenario-timestep"} if st0["kernel_variant"] == 300 else None}
+    if a.phases and rank == 0:
+        import ctypes
+
+        names = ["-", "load_bounds", "load_state", "place_nonbasics", "g = N x_N", "beta = -W g", "leaving row / exit", "write_solution+residual",
+                 "store_state", "pivot: column w + check", "pivot: d / beta", "pivot: update W", "pivot: row rho", "pivot: alpha", "pivot: ratio tests"]
+        buf = (ctypes.c_ulonglong * 18)()
+        eng.L.b200lp_debug_rsx_phases.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
+        assert eng.L.b200lp_debug_rsx_phases(eng.h, buf) == 0
+        d = [float(v) for v in buf]
+        tot = sum(d[2:17])
+        out["rsx_phases"] = {"cycles_per_scenario_timestep": tot / (S * T),
+                             "share": {names[k]: d[2 + k] / tot for k in range(1, 15)},
+                             "cycles_per_pivot": {names[k]: d[2 + k] / max(d[0], 1.0) for k in (6, 12, 13, 14, 9, 10, 11)}}
     if rank == 0:
         print(json.dumps(out))
     eng.close()

@@ -1,5 +1,5 @@
 """Phase cycles of rsx_solve_kernel (debug build: nvcc -DRSX_PHASE_TIMING -o pywr_b200/libb200lp_phase.so, see
-benchmarks/tools/exp.sh) on the config-4 fixture: python benchmarks/tools/rsx_phases.py [S] [steps] [mode]"""
+benchmarks/tools/exp.sh) on the config-4 fixture: RSX_FIXTURE=network600|netspec2000 python benchmarks/tools/rsx_phases.py [S] [steps] [mode]"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -10,7 +10,7 @@ if len(sys.argv) > 3:
 import numpy as np
 from pywr_b200.engine import CudaEngine
 from pywr_b200.structure import LPStructure
-FIX = os.path.join(ROOT, "benchmarks", "fixtures", "network600.edge")
+FIX = os.path.join(ROOT, "benchmarks", "fixtures", os.environ.get("RSX_FIXTURE", "network600") + ".edge")
 s = LPStructure.load(FIX + ".structure.npz"); tr = np.load(FIX + ".trace.npz")
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -21,8 +21,8 @@ names = ["-", "load_bounds", "load_state", "place_nonbasics", "g = N x_N", "beta
          "pivot: column w + check", "pivot: d / beta", "pivot: update W", "pivot: row rho", "pivot: alpha", "pivot: ratio tests"]
 prev = np.zeros(18, np.uint64)
 for t in range(T):
-    base = tr["slots"][t][:, 0]
-    slots[:] = base[:, None]
+    base = tr["slots"][t]
+    slots[:] = base[:, np.arange(S) % base.shape[1]]
     eng.step(float(tr["days"][t]), slots, None, None, None)
     out = (ctypes.c_ulonglong * 18)()
     eng.L.b200lp_debug_rsx_phases.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]

@@ -49,6 +49,7 @@ class PdhgPlan:
     """Steps 1 and 2 (host side, shared by all scenarios)."""
 
     RUIZ_SWEEPS = 10
+    AGG_LEN = 12
     POWER_ITERS = 300
 
     def __init__(self, s):
@@ -69,14 +70,22 @@ class PdhgPlan:
         for i in range(m):
             k0, k1 = A.indptr[i], A.indptr[i + 1]
             rows.append([(int(j), float(v)) for j, v in sorted(zip(A.indices[k0:k1], A.data[k0:k1])) if v != 0.0])
-        # doubleton elimination (PdhgPlan::build in pdhg_engine.cuh, same order of decisions): a row  a x_p + b x_q = 0  with
-        # constant zero bounds and a b < 0 (the mass balance of a link with one edge in and one out) fixes x_q = rho x_p,
-        # rho = -a / b > 0: column q is folded into column p (in every other row, in the cost and - through its singleton
-        # rows - in the bounds) and the row disappears.  Repeated until nothing changes: chains of links collapse.
-        alias_root = np.arange(n)
-        alias_ratio = np.ones(n)
+        # equality-row elimination (PdhgPlan::build in pdhg_engine.cuh, same order of decisions and of floating-point operations),
+        # two rules applied until neither fires:
+        #  (1) doubletons: a row  a x_p + b x_q = 0  with constant zero bounds and a b < 0 (the mass balance of a link with one edge
+        #      in and one out) fixes x_q = rho x_p, rho = -a / b > 0: column q is folded into column p (in every other row, in the
+        #      cost and - through its singleton rows - in the bounds) and the row disappears.  Chains of links collapse.
+        #  (2) confluences: a row  b x_q + sum a_k x_k = 0  (3..AGG_LEN entries, constant zero bounds) where x_q is the only entry of
+        #      its sign fixes x_q = sum rho_k x_k, rho_k = -a_k / b > 0; x_q >= 0 is implied, so q goes if every singleton row on
+        #      it can never bind.  q is replaced by the combination in every other row.
         elim_row = np.full(n, -1, np.int32)
         gone = np.zeros(m, bool)
+        comb = [[] for _ in range(n)]           # folded column -> [(surviving column, ratio)]
+        colrows = [set() for _ in range(n)]     # rows (gone or not) that list the column
+        for i in range(m):
+            for j, _ in rows[i]:
+                colrows[j].add(i)
+        combcols = [set() for _ in range(n)]    # folded columns whose combination lists the column
 
         def zero_bounds(i):
             if s.row_kind[i] != 0:
@@ -84,8 +93,49 @@ class PdhgPlan:
             lb, ub = const_of(int(s.row_lb_ref[i])), const_of(int(s.row_ub_ref[i]))
             return lb is not None and ub is not None and abs(lb) < 1e-8 and abs(ub) < 1e-8
 
+        def never_binds(i):
+            r = rows[i]
+            if s.row_kind[i] != 0 or not r or any(v < 0.0 for _, v in r):
+                return False
+            lb, ub = const_of(int(s.row_lb_ref[i])), const_of(int(s.row_ub_ref[i]))
+            return lb is not None and ub is not None and lb < 1e-8 and ub >= BIG
+
+        def substitute(lst, q, C):
+            """entry q (coefficient v) of the sorted list replaced by v * C, merged into the entries already there"""
+            d = dict(lst)
+            if q not in d:
+                return lst
+            v = d.pop(q)
+            for col, rho in C:
+                nv = d.get(col, 0.0) + v * rho
+                if nv != 0.0:
+                    d[col] = nv
+                elif col in d:
+                    del d[col]
+            return sorted(d.items())
+
+        def eliminate(i, q, C):
+            for k in sorted(colrows[q]):
+                if k == i or gone[k]:
+                    continue
+                rows[k] = substitute(rows[k], q, C)
+                for col, _ in C:
+                    colrows[col].add(k)         # a superset is enough: membership is re-checked where it matters
+            for j in sorted(combcols[q]):
+                comb[j] = substitute(comb[j], q, C)
+                for col, _ in C:
+                    combcols[col].add(j)
+            combcols[q] = set()
+            comb[q] = list(C)
+            for col, _ in C:
+                combcols[col].add(q)
+            gone[i] = True
+            elim_row[q] = i
+
         import os
-        changed = not os.environ.get("B200LP_NO_DOUBLETON")
+        rule1 = not os.environ.get("B200LP_NO_DOUBLETON")
+        rule2 = rule1 and not os.environ.get("B200LP_NO_AGGREGATE")
+        changed = rule1
         while changed:
             changed = False
             ccount = np.zeros(n, np.int64)
@@ -103,39 +153,38 @@ class PdhgPlan:
                 q = p0 if (ccount[p0] < ccount[p1] or (ccount[p0] == ccount[p1] and p0 > p1)) else p1
                 pcol = p1 if q == p0 else p0
                 aq, ap = (a, b) if q == p0 else (b, a)
-                rho = -ap / aq
-                for k in range(m):
-                    if k == i or gone[k]:
-                        continue
-                    rk = rows[k]
-                    hit = [t for t, (j, _) in enumerate(rk) if j == q]
-                    if not hit:
-                        continue
-                    v = rk[hit[0]][1]
-                    d = dict(rk)
-                    del d[q]
-                    nv = d.get(pcol, 0.0) + v * rho
-                    if nv != 0.0:
-                        d[pcol] = nv
-                    elif pcol in d:
-                        del d[pcol]
-                    rows[k] = sorted(d.items())
-                gone[i] = True
-                alias_root[q], alias_ratio[q], elim_row[q] = pcol, rho, i
+                eliminate(i, q, [(pcol, -ap / aq)])
                 ccount[q] = 0
-                ccount[pcol] = sum(1 for k in range(m) if not gone[k] and any(j == pcol for j, _ in rows[k]))
+                ccount[pcol] = sum(1 for k in colrows[pcol] if not gone[k] and any(j == pcol for j, _ in rows[k]))
                 changed = True
-        for j in range(n):          # chains: q -> p -> ... -> root
-            root, ratio = j, 1.0
-            while alias_root[root] != root:
-                ratio *= alias_ratio[root]
-                root = alias_root[root]
-            alias_root[j], alias_ratio[j] = root, ratio
-        self.alias_root, self.alias_ratio, self.elim_row = alias_root, alias_ratio, elim_row
-        self.members = [[(j, 1.0)] if alias_root[j] == j else [] for j in range(n)]
+            if not rule2:
+                continue
+            for i in range(m):
+                r = rows[i]
+                if gone[i] or len(r) < 3 or len(r) > self.AGG_LEN or not zero_bounds(i):
+                    continue
+                pos = [t for t, (_, v) in enumerate(r) if v > 0.0]
+                if len(pos) == 1:
+                    at = pos[0]
+                elif len(pos) == len(r) - 1:
+                    at = [t for t, (_, v) in enumerate(r) if not v > 0.0][0]
+                else:
+                    continue
+                q, b = r[at]
+                if any(k != i and not gone[k] and len(rows[k]) == 1 and rows[k][0][0] == q and not never_binds(k) for k in colrows[q]):
+                    continue
+                eliminate(i, q, [(col, -v / b) for t, (col, v) in enumerate(r) if t != at])
+                changed = True
+        alias_root = np.arange(n)
+        for j in range(n):
+            if comb[j]:
+                alias_root[j] = comb[j][0][0]       # != j: marks the column as folded
+        self.alias_root, self.elim_row = alias_root, elim_row
+        self.comb = [comb[j] if comb[j] else [(j, 1.0)] for j in range(n)]
+        self.members = [[] if comb[j] else [(j, 1.0)] for j in range(n)]
         for q in range(n):
-            if alias_root[q] != q:
-                self.members[alias_root[q]].append((q, alias_ratio[q]))
+            for col, ratio in comb[q]:
+                self.members[col].append((q, ratio))
         keep, sing_row, sing_col, sing_coef = [], [], [], []
         for i in range(m):
             if gone[i]:
@@ -330,9 +379,14 @@ def snap_unscale(plan, xs, lc, uc):
     l, u = lc * plan.dc, uc * plan.dc
     x = np.where(np.abs(x - l) <= 1e-9 * (1.0 + np.abs(l)), l, x)
     x = np.where(np.abs(x - u) <= 1e-9 * (1.0 + np.abs(_fin(u))), u, x)
-    dead = plan.alias_root != np.arange(plan.n)
-    x[dead] = plan.alias_ratio[dead] * x[plan.alias_root[dead]]     # x_q = rho x_p of the folded columns
-    return x
+    out = x.copy()
+    for q in np.nonzero(plan.alias_root != np.arange(plan.n))[0]:   # folded columns: x_q = sum rho_k x_k over the surviving columns
+        acc = None
+        for col, ratio in plan.comb[q]:
+            term = ratio * x[col]
+            acc = term if acc is None else acc + term
+        out[q] = acc
+    return out
 
 
 class PdhgOracleEngine:
