@@ -422,6 +422,7 @@ RSX_FN void do_pivot(CX &cx, const Lp &P, const Scen &S, Work &K, int r, int q, 
             const int v = base + u * cx.nt;
             on[u] = v < nv && K.stat[v < nv ? v : 0] != V_BASIC && v != q;
             av[u] = on[u] ? K.alpha[v] : 0.0;
+            on[u] = on[u] && av[u] != 0.0;   // the pivot row is sparse: most reduced costs do not move (and are not fetched)
             dv[u] = on[u] ? K.d[v] : 0.0;
             wv[u] = (on[u] && use_dw) ? K.dw[v] : 0.0;
         }
