@@ -518,17 +518,57 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
                 }
             };
             double rmin = INFINITY;
-            scan([&](int, double a, double dwv) { rmin = fmin(rmin, fabs(dwv) / fabs(a)); });
-            rmin = cx.min(rmin);
-            if (rmin == INFINITY) return R_INFEASIBLE;
-            const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
             double amax = -1.0; int aux = 0;
             q = -1;
-            scan([&](int v, double a, double dwv) {
-                if (fabs(dwv) / fabs(a) > thr) return;
-                const double key = bland ? 1.0 : fabs(a);
-                if (q < 0 || key > amax) { amax = key; q = v; }
-            });
+            // up to RC x 4 variables per thread: the ratios of the first pass stay in registers for the second (a double division
+            // is a ~30-instruction subroutine: recomputing them was 13 % of the kernel's instructions, and the second pass would
+            // fetch the working reduced costs again)
+            constexpr int RC = 2;
+            if (nv <= RC * 4 * cx.nt) {
+                double rc[RC][4];
+#pragma unroll
+                for (int bb = 0; bb < RC; bb++) {
+                    const int base = cx.tid + bb * 4 * cx.nt;
+                    double a[4], dwv[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int v = base + u * cx.nt;
+                        const int s = v < nv ? K.stat[v] : V_BASIC;
+                        a[u] = v < nv ? K.alpha[v] * dir : 0.0;
+                        ok[u] = (s == V_NL && a[u] > TOL_PIVOT) || (s == V_NU && a[u] < -TOL_PIVOT) || (s == V_NF && fabs(a[u]) > TOL_PIVOT);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? K.dw[base + u * cx.nt] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        rc[bb][u] = ok[u] ? fabs(dwv[u]) / fabs(a[u]) : INFINITY;
+                        rmin = fmin(rmin, rc[bb][u]);
+                    }
+                }
+                rmin = cx.min(rmin);
+                if (rmin == INFINITY) return R_INFEASIBLE;
+                const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
+#pragma unroll
+                for (int bb = 0; bb < RC; bb++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (rc[bb][u] > thr) continue;
+                        const int v = cx.tid + (bb * 4 + u) * cx.nt;
+                        const double key = bland ? 1.0 : fabs(K.alpha[v]);
+                        if (q < 0 || key > amax) { amax = key; q = v; }
+                    }
+            } else {
+                scan([&](int, double a, double dwv) { rmin = fmin(rmin, fabs(dwv) / fabs(a)); });
+                rmin = cx.min(rmin);
+                if (rmin == INFINITY) return R_INFEASIBLE;
+                const double thr = rmin * (1.0 + TIE_REL) + TIE_ABS;
+                scan([&](int v, double a, double dwv) {
+                    if (fabs(dwv) / fabs(a) > thr) return;
+                    const double key = bland ? 1.0 : fabs(a);
+                    if (q < 0 || key > amax) { amax = key; q = v; }
+                });
+            }
             cx.argmax(amax, q, aux);
             cx.mark(14);
             to_upper = bd < 0;  // the leaving variable goes to the bound it violated

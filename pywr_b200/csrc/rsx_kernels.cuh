@@ -10,6 +10,11 @@
 namespace b200lp {
 
 constexpr int RSX_THREADS = 512;
+// threads of a block when two blocks share an SM (MINB = 2): 512 leaves 64 registers per thread, 384 leaves 85
+#ifndef RSX_THREADS2
+#define RSX_THREADS2 512
+#endif
+constexpr int rsx_threads(int minb) { return minb == 2 ? RSX_THREADS2 : RSX_THREADS; }
 
 struct RsxCtx {
     static constexpr int nl = 32;  // compile-time: the streaming loops unroll over it
@@ -107,7 +112,7 @@ struct RsxDev {
 // same loop drops from 7.1 to 5.2 TB/s (benchmarks/tools/stream_probe.cu, profiles/r1_stream_probe.md).  MINB = blocks per SM
 // (128 or 64 registers per thread).
 template <int MODE, int MINB>
-__global__ void __launch_bounds__(RSX_THREADS, MINB)
+__global__ void __launch_bounds__(rsx_threads(MINB), MINB)
 rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
     extern __shared__ __align__(16) unsigned char rsx_smem[];
     __shared__ double rv[32];
@@ -158,7 +163,7 @@ rsx_solve_kernel(const RsxDev D, const int s0, const int s1, const int cold) {
 // Crossover of the PDHG path (rsx_core.cuh::crossover): same CTA layout as rsx_solve_kernel; x0 = the scenario's column of the
 // x planes (the first-order method's answer), the vertex goes to xt.  counters[20] counts the structurals the crash pivoted in.
 template <int MODE, int MINB>
-__global__ void __launch_bounds__(RSX_THREADS, MINB)
+__global__ void __launch_bounds__(rsx_threads(MINB), MINB)
 rsx_crossover_kernel(const RsxDev D, const int s0, const int s1) {
     extern __shared__ __align__(16) unsigned char rsx_smem[];
     __shared__ double rv[32];
