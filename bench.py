@@ -12,6 +12,8 @@ NCCL is used once after the timed region to gather the per-scenario recorder val
 scenarios in TOTAL, 4,096 / N per GPU (north_star: "a 4,096-scenario Thames-scale model on one 8 x B200 box");
 under torchrun the default run also measures that split and reports it under "north_star_target".
 `--workload two_reservoir --scenarios 1024` is BASELINE.json configs[1] (reported under "config2" at N = 1).
+BASELINE.json configs[3] (the 2,000-node network, large-LP path) is measured by benchmarks/network_program_bench.py, which the
+default N = 1 run executes once in its own process and reports under "config4".
 
 A "step" is one whole run of the workload: all T timesteps for all scenarios of the rank through the
 device-resident run (parameters -> bounds/costs -> warm-started simplex -> flow commit -> storage mass
@@ -467,6 +469,25 @@ def main():
                    "unit": UNIT, "ms_per_step": m2["dev_time"] / args.steps * 1e3, "e2e": m2["e2e"], "failed_scenarios": m2["nfail"]}
         m2["bench"].close()
 
+    # ---- BASELINE.json configs[3] (the 2,000-node network as SURVEY 8(d) specifies it) on the large-LP path, N = 1 only: its own
+    # process (benchmarks/network_program_bench.py), after this process has released its engines
+    config4 = None
+    if world == 1 and args.workload == "thames" and not args.no_e2e:
+        try:
+            import subprocess
+
+            cmd = [sys.executable, os.path.join(ROOT, "benchmarks", "network_program_bench.py"), "--fixture", "netspec2000",
+                   "--scenarios", "8192", "--steps", "365"]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+            r4 = json.loads(out.stdout.strip().splitlines()[-1])
+            config4 = {"workload": "netspec2000: 2,316-node generated network (150 reservoirs, 40 aggregated nodes, 60 piecewise links), edge "
+                                   "formulation, LP 3,105 x 2,010, daily AR(1) inflows per scenario; 8,192 scenarios x 365 days, device-resident",
+                       **{k: r4[k] for k in ("value", "unit", "device_s", "wall_s", "reduced_rows", "pivots_per_scenario_timestep", "kernel_variant",
+                                             "kernel_launches", "failed_scenarios_max_over_ranks",
+                                             "max_rel_diff_vs_reference_host_run_scenarios_0_1", "recorders_checked", "roofline")}}
+        except Exception as exc:
+            config4 = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
     # ---- the same engine driven by the reference framework itself (only where Pywr is importable) ----
     pywr_extra = None
     if world == 1 and not args.no_e2e:
@@ -522,7 +543,7 @@ def main():
             "failed_scenarios": m["nfail"], "wall_ms_per_step_including_reset": m["wall"] / args.steps * 1e3,
             "pivots_per_scenario_timestep": (st1["pivots"] - st0["pivots"]) / max(1, units * args.steps),
             "kernel_variant": st1["kernel_variant"], "run_kernel_jit": jit, "gather_ms": gather_ms,
-            "north_star_target": target, "single_process_multi_gpu": single_process, "config2": config2,
+            "north_star_target": target, "single_process_multi_gpu": single_process, "config2": config2, "config4": config4,
             "through_pywr": pywr_extra,
         }
         print(json.dumps(line))
