@@ -484,7 +484,7 @@ def main():
                                    "formulation, LP 3,105 x 2,010, daily AR(1) inflows per scenario; 8,192 scenarios x 365 days, device-resident",
                        **{k: r4[k] for k in ("value", "unit", "device_s", "wall_s", "reduced_rows", "pivots_per_scenario_timestep", "kernel_variant",
                                              "kernel_launches", "failed_scenarios_max_over_ranks",
-                                             "max_rel_diff_vs_reference_host_run_scenarios_0_1", "recorders_checked", "roofline")}}
+                                             "max_rel_diff_vs_reference_host_run_scenarios_0_1", "recorders_checked", "roofline", "roofline_algorithmic")}}
         except Exception as exc:
             config4 = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 

@@ -169,6 +169,13 @@ def main():
            "roofline": {"bound": "hbm", "achieved": wbytes * S * T / dev_s / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": wbytes * S * T / dev_s / 1e9 / peak, "bytes_per_scenario_timestep": wbytes,
                         "note": "per GPU; algorithmic bytes = one read of the scenario's basis inverse per scenario-timestep"} if st0["kernel_variant"] == 300 else None}
+    # SURVEY 8(d)'s algorithmic bytes of one scenario-timestep of the ORIGINAL LP: bounds of rows and columns, statuses, storage state,
+    # node flows, recorder samples = 8 (n + 2 m) + 2 (m + n) + 16 n_storage + 8 N + 8 n_rec
+    alg = 8 * (s.n_cols + 2 * s.n_rows) + 2 * (s.n_rows + s.n_cols) + 16 * s.n_storage + 8 * s.n_nodes + 8 * int(q.n_recorders)
+    out["roofline_algorithmic"] = {"bound": "hbm", "bytes_per_scenario_timestep": alg, "achieved": alg * S * T / dev_s / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": alg * S * T / dev_s / 1e9 / peak,
+                                   "note": "per GPU, against SURVEY 8(d)'s per-unit bytes of the LP itself; the engine's own stream (the dense "
+                                           "basis inverse, `roofline`) is an implementation cost on top of these"}
     if a.phases and rank == 0:
         import ctypes
 
