@@ -257,15 +257,36 @@ RSX_FN void update_W(CX &cx, const Lp &P, const Scen &S, Work &K, int r) {
     double *rowr = S.W + (size_t)r * P.ldw;
     if (sparse) { for (int t = cx.tid; t < nk; t += cx.nt) { const int k = K.list_k[t]; rowr[k] = K.rho[k]; } }
     else { for (int k = cx.tid; k < m; k += cx.nt) rowr[k] = K.rho[k]; }
-    for (int li = cx.warp; li < ni; li += cx.nw) {
-        const int i = K.list_i[li];
-        const double wi = -K.w[i];
-        double *row = S.W + (size_t)i * P.ldw;
+    // two rows per warp at a time, four segments of each in flight: the update is a chain of read-modify-write round trips to
+    // L2 / HBM, and with one row per warp a pivot spent 12-15 k cycles here
+    for (int li = 2 * cx.warp; li < ni; li += 2 * cx.nw) {
+        const int i0 = K.list_i[li];
+        const bool two = li + 1 < ni;
+        const int i1 = two ? K.list_i[li + 1] : i0;
+        const double w0 = -K.w[i0], w1 = -K.w[i1];
+        double *r0 = S.W + (size_t)i0 * P.ldw, *r1 = S.W + (size_t)i1 * P.ldw;
+        constexpr int nl = CX::nl;
         if (sparse) {
-            for (int t = cx.lane; t < nk; t += cx.nl) { const int k = K.list_k[t]; row[k] = fma(wi, K.rho[k], row[k]); }
+            for (int t = cx.lane; t < nk; t += nl) {
+                const int k = K.list_k[t];
+                const double rk = K.rho[k], x0 = r0[k], x1 = r1[k];
+                r0[k] = fma(w0, rk, x0);
+                if (two) r1[k] = fma(w1, rk, x1);
+            }
         } else {
-#pragma unroll 4
-            for (int k = cx.lane; k < m; k += cx.nl) row[k] = fma(wi, K.rho[k], row[k]);
+            int k = cx.lane;
+            for (; k + 3 * nl < m; k += 4 * nl) {
+                const double x0 = r0[k], x1 = r0[k + nl], x2 = r0[k + 2 * nl], x3 = r0[k + 3 * nl];
+                const double y0 = r1[k], y1 = r1[k + nl], y2 = r1[k + 2 * nl], y3 = r1[k + 3 * nl];
+                const double g0 = K.rho[k], g1 = K.rho[k + nl], g2 = K.rho[k + 2 * nl], g3 = K.rho[k + 3 * nl];
+                r0[k] = fma(w0, g0, x0); r0[k + nl] = fma(w0, g1, x1); r0[k + 2 * nl] = fma(w0, g2, x2); r0[k + 3 * nl] = fma(w0, g3, x3);
+                if (two) { r1[k] = fma(w1, g0, y0); r1[k + nl] = fma(w1, g1, y1); r1[k + 2 * nl] = fma(w1, g2, y2); r1[k + 3 * nl] = fma(w1, g3, y3); }
+            }
+            for (; k < m; k += nl) {
+                const double g = K.rho[k], x = r0[k], y = r1[k];
+                r0[k] = fma(w0, g, x);
+                if (two) r1[k] = fma(w1, g, y);
+            }
         }
     }
     cx.sync();
