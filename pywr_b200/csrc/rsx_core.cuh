@@ -460,8 +460,8 @@ RSX_FN void do_pivot(CX &cx, const Lp &P, const Scen &S, Work &K, int r, int q, 
         if (i != r) K.beta[i] = fma(-theta, K.w[i], K.beta[i]);
     cx.sync();
     if (cx.leader()) {
-        K.d[p] = rd; K.dw[p] = use_dw ? rw : rd;
-        K.d[q] = 0.0; K.dw[q] = 0.0;
+        K.d[p] = rd; K.d[q] = 0.0;
+        if (use_dw) { K.dw[p] = rw; K.dw[q] = 0.0; }
         K.beta[r] = xq_old + theta;
         K.head[r] = q;
         K.stat[q] = V_BASIC;
@@ -509,7 +509,10 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
                 continue;
             }
             if (bd == 2) return R_NUMERIC;
-            if (!dw_ready) { init_dw(cx, P, K, shifted); dw_ready = true; }
+            // working reduced costs: a copy with the dual infeasibilities shifted away - only when there are any; otherwise (the
+            // usual warm start) the true reduced costs serve as they are and nothing is copied or updated twice
+            if (shifted && !dw_ready) { init_dw(cx, P, K, shifted); dw_ready = true; }
+            const double *rcw = shifted ? K.dw : K.d;
             r = bi;
             const double dir = (double)bd;
             cx.mark(6);
@@ -532,7 +535,7 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
                         ok[u] = (s == V_NL && a[u] > TOL_PIVOT) || (s == V_NU && a[u] < -TOL_PIVOT) || (s == V_NF && fabs(a[u]) > TOL_PIVOT);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? K.dw[base + u * cx.nt] : 0.0;
+                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? rcw[base + u * cx.nt] : 0.0;
 #pragma unroll
                     for (int u = 0; u < 4; u++)
                         if (ok[u]) visit(base + u * cx.nt, a[u], dwv[u]);
@@ -560,7 +563,7 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
                         ok[u] = (s == V_NL && a[u] > TOL_PIVOT) || (s == V_NU && a[u] < -TOL_PIVOT) || (s == V_NF && fabs(a[u]) > TOL_PIVOT);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? K.dw[base + u * cx.nt] : 0.0;
+                    for (int u = 0; u < 4; u++) dwv[u] = ok[u] ? rcw[base + u * cx.nt] : 0.0;
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         rc[bb][u] = ok[u] ? fabs(dwv[u]) / fabs(a[u]) : INFINITY;
@@ -655,7 +658,7 @@ RSX_FN int solve(CX &cx, const Lp &P, const Scen &S, Work &K, int &pivots) {
             load_rho(cx, P, S, K, r);
             compute_alpha(cx, P, K);
         }
-        do_pivot(cx, P, S, K, r, q, to_upper, phase == 0);
+        do_pivot(cx, P, S, K, r, q, to_upper, phase == 0 && shifted);
         pivots++;
     }
 }
