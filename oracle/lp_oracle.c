@@ -899,6 +899,18 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_THRESHOLD: {  /* AbstractThresholdParameter.index / value, _thresholds.pyx:78-131 (no ratchet) */
+            const double x = a[0] == 1 ? c->vol[a[1]] : pref(h, a[1], p), th = pref(h, a[3], p);
+            int on;
+            switch (a[2]) {
+            case B200LP_PRED_LT: on = x < th; break;
+            case B200LP_PRED_GT: on = x > th; break;
+            case B200LP_PRED_LE: on = x <= th; break;
+            case B200LP_PRED_GE: on = x >= th; break;
+            default: on = x == th;
+            }
+            v = on ? pref(h, a[5], p) : pref(h, a[4], p);
+        } break;
         case B200LP_OP_CC_INTERP: {  /* ControlCurveInterpolatedParameter.value, _control_curves.pyx:176-216 */
             const int32_t cnt = a[1];
             const int32_t *cv = a + 2, *vv = a + 2 + cnt;

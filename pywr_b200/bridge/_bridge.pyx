@@ -18,8 +18,9 @@ from pywr._core cimport AbstractNode, AbstractStorage, RollingVirtualStorage
 from pywr.parameters._parameters cimport (
     Parameter, ConstantScenarioParameter, ArrayIndexedParameter, ArrayIndexedScenarioParameter,
     DataFrameParameter, ScenarioMonthlyProfileParameter, ScenarioDailyProfileParameter,
-    ScenarioWeeklyProfileParameter, ArrayIndexedScenarioMonthlyFactorsParameter,
+    ScenarioWeeklyProfileParameter, ArrayIndexedScenarioMonthlyFactorsParameter, ConstantScenarioIndexParameter,
 )
+from pywr.parameters._thresholds cimport AbstractThresholdParameter
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder,
     BaseConstantStorageRecorder, NodeRecorder, StorageRecorder,
@@ -62,7 +63,11 @@ def scenario_axis(Parameter p):
     cdef ScenarioDailyProfileParameter b
     cdef ScenarioWeeklyProfileParameter c
     cdef ArrayIndexedScenarioMonthlyFactorsParameter d
+    cdef ConstantScenarioIndexParameter e
     name = type(p).__name__
+    if name == "ConstantScenarioIndexParameter":
+        e = p
+        return e._scenario_index
     if name == "ScenarioMonthlyProfileParameter":
         a = p
         return a._scenario_index
@@ -76,6 +81,18 @@ def scenario_axis(Parameter p):
         d = p
         return d._scenario_index
     return None
+
+
+def threshold_predicate(AbstractThresholdParameter p):
+    """``AbstractThresholdParameter.predicate`` (pywr/parameters/_thresholds.pxd:12; enum Predicates, _thresholds.pyx:5-10)"""
+    return int(p.predicate)
+
+
+def threshold_values(AbstractThresholdParameter p):
+    """``AbstractThresholdParameter.values`` (the pair the index selects from), or None"""
+    if p.values is None:
+        return None
+    return np.asarray(p.values).copy()
 
 
 def set_node_flow(AbstractNode node, double[:] flow):

@@ -843,6 +843,11 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             break;
         case B200LP_OP_NEG: ok = refs(0, 1); break;
         case B200LP_OP_MAX0: case B200LP_OP_MIN0: case B200LP_OP_DIV: ok = refs(0, 2); break;
+        case B200LP_OP_THRESHOLD:  // -> V index of X, predicate, V indices of threshold, value0, value1
+            ok = na >= 6 && a[2] >= B200LP_PRED_LT && a[2] <= B200LP_PRED_GE &&
+                 ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
+            if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 3); }
+            break;
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
             ok = na >= 4 && a[0] >= 0 && a[0] < nstor;
             if (ok) {

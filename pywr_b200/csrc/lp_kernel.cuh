@@ -1058,6 +1058,13 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
         case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
+        case B200LP_OP_THRESHOLD: {  // AbstractThresholdParameter.index / value (_thresholds.pyx:78-131), no ratchet
+            const double x = V[a[0]], th = V[a[2]];
+            const int pr = a[1];
+            const bool on = pr == B200LP_PRED_LT ? x < th : pr == B200LP_PRED_GT ? x > th : pr == B200LP_PRED_LE ? x <= th
+                          : pr == B200LP_PRED_GE ? x >= th : x == th;
+            v = on ? V[a[4]] : V[a[3]];
+        } break;
         case B200LP_OP_CC_INTERP: {  // ControlCurveInterpolatedParameter.value (_control_curves.pyx:176-216)
             const int cnt = a[1];
             const int *cv = a + 2, *vv = a + 2 + cnt;

@@ -28,7 +28,8 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
-OP_CC_INTERP, OP_CC_PIECEWISE = 11, 12
+OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD = 11, 12, 13
+PRED = {"LT": 0, "GT": 1, "EQ": 2, "LE": 3, "GE": 4}
 OP_STORAGE_RESET = 10
 PROG_AGG_ONLY = 1
 # virtual storages whose reset / activation follows the calendar only (pywr/nodes.py:596-757)
@@ -202,6 +203,8 @@ _VALUE_LEAVES = {  # state- and scenario-independent: sampled through their publ
     "MonthlyProfileParameter", "DailyProfileParameter", "WeeklyProfileParameter",
     "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter",
 }
+_THRESHOLDS = {"ParameterThresholdParameter", "StorageThresholdParameter", "CurrentYearThresholdParameter",
+               "CurrentOrdinalDayThresholdParameter"}
 _SCENARIO_PROFILES = {
     "ScenarioMonthlyProfileParameter", "ScenarioDailyProfileParameter", "ScenarioWeeklyProfileParameter",
     "ArrayIndexedScenarioMonthlyFactorsParameter",
@@ -397,7 +400,7 @@ class _Compiler:
             curves = [self.param(c) for c in p.control_curves]
             return self.emit(OP_CC_INDEX, [k, len(curves)] + curves)
         if name == "IndexedArrayParameter":
-            idx = self.param(p.index_parameter)
+            idx = self.index_param(p.index_parameter)
             refs = [self.param(c) for c in p.params]
             return self.emit(OP_INDEXED, [idx, len(refs)] + refs)
         if name == "NegativeParameter":
@@ -410,7 +413,67 @@ class _Compiler:
             return self.emit(OP_MAX0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
         if name == "NegativeMinParameter":
             return self.emit(OP_MIN0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
+        if name == "DivisionParameter":                 # pywr/parameters/_parameters.pyx:1688-1739
+            return self.emit(OP_DIV, [self.param(p.numerator), self.param(p.denominator)])
+        if name == "OffsetParameter":                   # :1858-1907: parameter + offset
+            return self.emit(OP_AGG, [AGG["sum"], 2, self.param(p.parameter), self.const(p.offset)])
+        if name == "ScaledProfileParameter":            # pywr/parameters/parameters.py:102-121: scale * profile
+            return self.emit(OP_AGG, [AGG["product"], 2, self.const(p.scale), self.param(p.profile)])
+        if name == "ConstantScenarioIndexParameter":    # :1228-1260 (value() of an IndexParameter is its index)
+            return self.index_param(p)
+        if name == "AggregatedIndexParameter":          # :1559-1685
+            return self.index_param(p)
+        if name in _THRESHOLDS:                         # pywr/parameters/_thresholds.pyx
+            v = _bridge.threshold_values(p)
+            if v is None:
+                raise Unsupported(f"{name} without values used as a value")
+            return self.threshold(p, self.const(v[0]), self.const(v[1]))
         raise Unsupported(f"parameter type {name} is not available on the device")
+
+    def index_param(self, p) -> int:
+        """ref of an IndexParameter's INDEX (as a double), for IndexedArrayParameter / AggregatedIndexParameter"""
+        from .bridge import _bridge
+
+        name = type(p).__name__
+        key = ("index", id(p))
+        if key in self.memo:
+            return self.memo[key]
+        if name in _THRESHOLDS:
+            ref = self.threshold(p, self.const(0.0), self.const(1.0))
+        elif name == "ConstantScenarioIndexParameter":
+            axis = _bridge.scenario_axis(p)
+            size = self.model.scenarios.scenarios[axis].size
+            ts0 = self.timesteps[0]
+            ref = self.table(np.array([[float(p.index(ts0, self.representative(axis, c))) for c in range(size)]]), axis)
+        elif name == "AggregatedIndexParameter":
+            func = p.agg_func
+            if not isinstance(func, str) or func not in ("sum", "min", "max", "product"):
+                raise Unsupported(f"AggregatedIndexParameter agg_func {func!r}")
+            refs = [self.index_param(c) for c in p.parameters]
+            ref = self.emit(OP_AGG, [AGG[func], len(refs)] + refs)
+        else:                                           # value() of the remaining IndexParameters is float(index)
+            ref = self.param(p)
+        self.memo[key] = ref
+        return ref
+
+    def threshold(self, p, v0, v1) -> int:
+        """value1 if predicate(X, threshold) else value0 (AbstractThresholdParameter.index, _thresholds.pyx:78-112)"""
+        from .bridge import _bridge
+
+        name = type(p).__name__
+        if getattr(p, "ratchet", False):
+            raise Unsupported(f"{name} with ratchet=True keeps state on the host")
+        pred = _bridge.threshold_predicate(p)
+        thr = self.value_ref(p.threshold)
+        if name == "ParameterThresholdParameter":
+            return self.emit(OP_THRESHOLD, [0, self.param(p.param), pred, thr, v0, v1])
+        if name == "StorageThresholdParameter":
+            return self.emit(OP_THRESHOLD, [1, self.storage_of(p.storage), pred, thr, v0, v1])
+        if name == "CurrentYearThresholdParameter":
+            x = self.table(np.array([[float(ts.year)] for ts in self.timesteps]), None)
+        else:                                           # CurrentOrdinalDayThresholdParameter
+            x = self.table(np.array([[float(ts.datetime.toordinal())] for ts in self.timesteps]), None)
+        return self.emit(OP_THRESHOLD, [0, x, pred, thr, v0, v1])
 
     def storage_of(self, node) -> int:
         k = self.storage_index.get(id(node))

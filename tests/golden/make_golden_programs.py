@@ -50,6 +50,10 @@ CASES = [
     ("aggregated_storage", "custom:aggregated_storage", "route", None),
     # a reservoir whose COST is an interpolated control curve: the objective changes every timestep (a3, cost_dynamic)
     ("reservoir_with_cc", "tests/models/reservoir_with_cc.json", "route", None),
+    # derived parameters: thresholds (B200LP_OP_THRESHOLD) on a parameter, a storage volume, the calendar year and the ordinal
+    # day; DivisionParameter, OffsetParameter, ScaledProfileParameter; AggregatedIndexParameter and
+    # ConstantScenarioIndexParameter as the index of IndexedArrayParameters
+    ("derived_parameters", "custom:derived", "route", "2103-12-31"),
 ]
 
 
@@ -73,6 +77,38 @@ def custom_document(kind):
                             "control_curves": ["level2"], "values": [[3.5, 2.0], [1.5, 0.5]], "minimum": 0.05, "maximum": 0.95}
         P["demand_max_flow"]["parameters"].append("interp_factor")
         next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "release_cap"
+        return doc
+    if kind == "derived":
+        import datetime
+
+        doc = json.load(open(os.path.join(REF, "examples/thames/thames.json")))
+        for prm in doc["parameters"].values():
+            if isinstance(prm, dict) and "url" in prm and not os.path.isabs(prm["url"]):
+                prm["url"] = os.path.join(REF, "examples/thames", prm["url"])
+        P = doc["parameters"]
+        max_volume = next(n for n in doc["nodes"] if n["name"] == "reservoir1")["max_volume"]
+        start = datetime.datetime.strptime(str(doc["timestepper"]["start"])[:10], "%Y-%m-%d").date()
+        # demand steps up from the second calendar year on, and again whenever the seasonal profile is in its high months
+        P["year_step"] = {"type": "currentyearthreshold", "threshold": start.year + 1, "predicate": ">=", "values": [1.0, 1.08]}
+        P["summer_extra"] = {"type": "parameterthreshold", "parameter": "demand_profile", "threshold": 1.0, "predicate": "GT",
+                             "values": [1.0, 1.05]}
+        # restriction when the reservoir holds less than 45 % of its capacity (absolute volume)
+        P["low_volume"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.45 * max_volume,
+                           "predicate": "<", "values": [1.0, 0.85]}
+        P["profile_ratio"] = {"type": "division", "numerator": "level1", "denominator": "level2"}         # 1.4 - 1.86
+        P["ratio_offset"] = {"type": "offset", "parameter": "profile_ratio", "offset": -0.6}             # 0.8 - 1.26
+        P["scaled"] = {"type": "scaledprofile", "scale": 0.5, "profile": "ratio_offset"}                 # 0.4 - 0.63
+        P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume"]
+        # abstraction capacity: chosen by the sum of two indices (late in the run? storage low?) ...
+        P["late"] = {"type": "currentordinaldaythreshold", "threshold": start.toordinal() + 500, "predicate": ">"}
+        P["low_volume_index"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.6 * max_volume, "predicate": "LE"}
+        P["cap_index"] = {"type": "aggregatedindex", "agg_func": "sum", "parameters": ["late", "low_volume_index"]}
+        P["cap_by_state"] = {"type": "indexedarray", "index_parameter": "cap_index", "params": [3.5, 3.0, {"type": "aggregated", "agg_func": "sum", "parameters": [2.0, "scaled"]}]}
+        # ... and capped per member of the demand scenario
+        P["member_class"] = {"type": "constantscenarioindex", "scenario": "demand", "values": [0, 1, 1, 0, 2]}
+        P["cap_by_member"] = {"type": "indexedarray", "index_parameter": "member_class", "params": [3.5, 3.2, 2.4]}
+        P["abs_cap"] = {"type": "aggregated", "agg_func": "min", "parameters": ["cap_by_state", "cap_by_member"]}
+        next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "abs_cap"
         return doc
     if kind == "aggregated_storage":
         # tests/models/three_storage.json: the inflow of reservoir 0 is switched by a control curve on the AGGREGATED storage
