@@ -253,6 +253,11 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
                                      (ParameterThresholdParameter :294-318, calendar thresholds :362-395 through a table);
                                      source 1: X = the current volume of storage x (StorageThresholdParameter :134-157).
                                      predicate: B200LP_PRED_* */
+#define B200LP_OP_INTERP 14        /* args: source, x, n (>= 2), xk_ref*n (ascending), yk_ref*n, below_ref, above_ref.  Piecewise-linear
+                                     interpolation of X (source 0: the value behind ref x; source 1: the current volume of storage x):
+                                     InterpolatedParameter / InterpolatedVolumeParameter (pywr/parameters/parameters.py:124-242,
+                                     scipy interp1d kind="linear" = slope * (X - xk[j]) + yk[j]).  X below xk[0] / above xk[n-1] gives
+                                     below / above (NaN refs reproduce bounds_error=True: the scenario then fails with B200LP_ST_NAN) */
 #define B200LP_PRED_LT 0
 #define B200LP_PRED_GT 1
 #define B200LP_PRED_EQ 2

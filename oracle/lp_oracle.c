@@ -899,6 +899,23 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_INTERP: {  /* AbstractInterpolatedParameter.value, pywr/parameters/parameters.py:156-158 (linear interp1d) */
+            const int32_t cnt = a[2];
+            const int32_t *xk = a + 3, *yk = a + 3 + cnt;
+            const double x = a[0] == 1 ? c->vol[a[1]] : pref(h, a[1], p);
+            const double x0 = pref(h, xk[0], p), xl = pref(h, xk[cnt - 1], p);
+            if (x != x) v = NAN;
+            else if (x < x0) v = pref(h, a[3 + 2 * cnt], p);
+            else if (x > xl) v = pref(h, a[4 + 2 * cnt], p);
+            else if (x == xl) v = pref(h, yk[cnt - 1], p);
+            else {
+                int j = 0;
+                for (int i = 1; i < cnt - 1; i++) if (x >= pref(h, xk[i], p)) j = i;
+                const double xa = pref(h, xk[j], p), ya = pref(h, yk[j], p);
+                const double slope = (pref(h, yk[j + 1], p) - ya) / (pref(h, xk[j + 1], p) - xa);
+                v = slope * (x - xa) + ya;
+            }
+        } break;
         case B200LP_OP_THRESHOLD: {  /* AbstractThresholdParameter.index / value, _thresholds.pyx:78-131 (no ratchet) */
             const double x = a[0] == 1 ? c->vol[a[1]] : pref(h, a[1], p), th = pref(h, a[3], p);
             int on;

@@ -848,6 +848,10 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
                  ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
             if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 3); }
             break;
+        case B200LP_OP_INTERP:  // -> V index of X, n, V indices of the knots' x, y, below, above
+            ok = na >= 3 && a[2] >= 2 && ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
+            if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 2 * a[2] + 2); }
+            break;
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
             ok = na >= 4 && a[0] >= 0 && a[0] < nstor;
             if (ok) {

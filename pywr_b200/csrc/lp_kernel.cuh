@@ -1065,6 +1065,22 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
                           : pr == B200LP_PRED_GE ? x >= th : x == th;
             v = on ? V[a[4]] : V[a[3]];
         } break;
+        case B200LP_OP_INTERP: {  // AbstractInterpolatedParameter.value (pywr/parameters/parameters.py:156-158), linear interp1d
+            const int cnt = a[1];
+            const int *xk = a + 2, *yk = a + 2 + cnt;
+            const double x = V[a[0]], x0 = V[xk[0]], xl = V[xk[cnt - 1]];
+            if (x != x) v = NAN;
+            else if (x < x0) v = V[a[2 + 2 * cnt]];
+            else if (x > xl) v = V[a[3 + 2 * cnt]];
+            else if (x == xl) v = V[yk[cnt - 1]];
+            else {
+                int j = 0;
+                for (int i = 1; i < cnt - 1; i++) if (x >= V[xk[i]]) j = i;
+                const double xa = V[xk[j]], ya = V[yk[j]];
+                const double slope = (V[yk[j + 1]] - ya) / (V[xk[j + 1]] - xa);
+                v = slope * (x - xa) + ya;
+            }
+        } break;
         case B200LP_OP_CC_INTERP: {  // ControlCurveInterpolatedParameter.value (_control_curves.pyx:176-216)
             const int cnt = a[1];
             const int *cv = a + 2, *vv = a + 2 + cnt;

@@ -28,7 +28,7 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
-OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD = 11, 12, 13
+OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD, OP_INTERP = 11, 12, 13, 14
 PRED = {"LT": 0, "GT": 1, "EQ": 2, "LE": 3, "GE": 4}
 OP_STORAGE_RESET = 10
 PROG_AGG_ONLY = 1
@@ -423,6 +423,26 @@ class _Compiler:
             return self.index_param(p)
         if name == "AggregatedIndexParameter":          # :1559-1685
             return self.index_param(p)
+        if name in ("InterpolatedParameter", "InterpolatedVolumeParameter"):   # pywr/parameters/parameters.py:124-242
+            kw = dict(p.interp_kwargs)
+            if kw.pop("kind", "linear") != "linear":
+                raise Unsupported(f"{name}: only linear interpolation runs on the device")
+            bounds_error = kw.pop("bounds_error", True)
+            fill = kw.pop("fill_value", np.nan)
+            if kw or isinstance(fill, str):
+                raise Unsupported(f"{name}: interp_kwargs {sorted(kw) or fill!r}")
+            xs, ys = np.asarray(p.x, dtype=np.float64).reshape(-1), np.asarray(p.y, dtype=np.float64)
+            if ys.ndim != 1 or len(xs) != len(ys) or len(xs) < 2:
+                raise Unsupported(f"{name}: x / y must be two 1-D arrays of the same length")
+            order = np.argsort(xs, kind="mergesort")     # interp1d sorts its knots (assume_sorted=False)
+            xs, ys = xs[order], ys[order]
+            if bounds_error:                             # the reference raises ValueError: here the scenario fails with ST_NAN
+                below = above = np.nan
+            else:
+                below, above = (fill if isinstance(fill, tuple) else (fill, fill))
+            src = [1, self.storage_of(p._node)] if name == "InterpolatedVolumeParameter" else [0, self.param(p.parameter)]
+            return self.emit(OP_INTERP, src + [len(xs)] + [self.const(v) for v in xs] + [self.const(v) for v in ys]
+                             + [self.const(below), self.const(above)])
         if name in _THRESHOLDS:                         # pywr/parameters/_thresholds.pyx
             v = _bridge.threshold_values(p)
             if v is None:

@@ -52,7 +52,8 @@ CASES = [
     ("reservoir_with_cc", "tests/models/reservoir_with_cc.json", "route", None),
     # derived parameters: thresholds (B200LP_OP_THRESHOLD) on a parameter, a storage volume, the calendar year and the ordinal
     # day; DivisionParameter, OffsetParameter, ScaledProfileParameter; AggregatedIndexParameter and
-    # ConstantScenarioIndexParameter as the index of IndexedArrayParameters
+    # ConstantScenarioIndexParameter as the index of IndexedArrayParameters; InterpolatedVolumeParameter / InterpolatedParameter
+    # (B200LP_OP_INTERP)
     ("derived_parameters", "custom:derived", "route", "2103-12-31"),
 ]
 
@@ -98,7 +99,16 @@ def custom_document(kind):
         P["profile_ratio"] = {"type": "division", "numerator": "level1", "denominator": "level2"}         # 1.4 - 1.86
         P["ratio_offset"] = {"type": "offset", "parameter": "profile_ratio", "offset": -0.6}             # 0.8 - 1.26
         P["scaled"] = {"type": "scaledprofile", "scale": 0.5, "profile": "ratio_offset"}                 # 0.4 - 0.63
-        P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume"]
+        # piecewise-linear curves (B200LP_OP_INTERP): of the stored volume (outside the knots: the fill values) and of a parameter
+        P["level_factor"] = {"type": "interpolatedvolume", "node": "reservoir1",
+                             "volumes": [0.05 * max_volume, 0.3 * max_volume, 0.7 * max_volume, 0.98 * max_volume],
+                             "values": [0.7, 0.9, 0.97, 1.0], "interp_kwargs": {"bounds_error": False, "fill_value": [0.65, 1.01]}}
+        P["curve_of_level1"] = {"type": "interpolated", "parameter": "level1", "x": [0.95, 0.6, 0.75], "y": [1.02, 1.0, 0.98],
+                                "interp_kwargs": {"bounds_error": False, "fill_value": [1.0, 1.02]}}
+        # default bounds_error=True (outside the knots the reference raises, the device run fails the scenario with ST_NAN): on a
+        # constant, so that the widened batches of the GPU tests stay inside
+        P["curve_of_baseline"] = {"type": "interpolated", "parameter": "demand_baseline", "x": [1.0, 2.0], "y": [0.99, 1.01]}
+        P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume", "level_factor", "curve_of_level1", "curve_of_baseline"]
         # abstraction capacity: chosen by the sum of two indices (late in the run? storage low?) ...
         P["late"] = {"type": "currentordinaldaythreshold", "threshold": start.toordinal() + 500, "predicate": ">"}
         P["low_volume_index"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.6 * max_volume, "predicate": "LE"}
