@@ -20,7 +20,7 @@ from pywr.parameters._parameters cimport (
     DataFrameParameter, ScenarioMonthlyProfileParameter, ScenarioDailyProfileParameter,
     ScenarioWeeklyProfileParameter, ArrayIndexedScenarioMonthlyFactorsParameter, ConstantScenarioIndexParameter,
 )
-from pywr.parameters._thresholds cimport AbstractThresholdParameter
+from pywr.parameters._thresholds cimport AbstractThresholdParameter, MultipleThresholdParameterIndexParameter
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder,
     BaseConstantStorageRecorder, NodeRecorder, StorageRecorder,
@@ -86,6 +86,11 @@ def scenario_axis(Parameter p):
 def threshold_predicate(AbstractThresholdParameter p):
     """``AbstractThresholdParameter.predicate`` (pywr/parameters/_thresholds.pxd:12; enum Predicates, _thresholds.pyx:5-10)"""
     return int(p.predicate)
+
+
+def multiple_thresholds(MultipleThresholdParameterIndexParameter p):
+    """``MultipleThresholdParameterIndexParameter.thresholds`` (pywr/parameters/_thresholds.pxd:29)"""
+    return list(p.thresholds)
 
 
 def threshold_values(AbstractThresholdParameter p):

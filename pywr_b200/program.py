@@ -421,7 +421,7 @@ class _Compiler:
             return self.emit(OP_AGG, [AGG["product"], 2, self.const(p.scale), self.param(p.profile)])
         if name == "ConstantScenarioIndexParameter":    # :1228-1260 (value() of an IndexParameter is its index)
             return self.index_param(p)
-        if name == "AggregatedIndexParameter":          # :1559-1685
+        if name in ("AggregatedIndexParameter", "MultipleThresholdParameterIndexParameter"):   # :1559-1685, _thresholds.pyx:242-292
             return self.index_param(p)
         if name in ("InterpolatedParameter", "InterpolatedVolumeParameter"):   # pywr/parameters/parameters.py:124-242
             kw = dict(p.interp_kwargs)
@@ -465,6 +465,12 @@ class _Compiler:
             size = self.model.scenarios.scenarios[axis].size
             ts0 = self.timesteps[0]
             ref = self.table(np.array([[float(p.index(ts0, self.representative(axis, c))) for c in range(size)]]), axis)
+        elif name == "MultipleThresholdParameterIndexParameter":   # _thresholds.pyx:242-292: first threshold the value is not below
+            x = self.param(p.parameter)
+            thresholds = _bridge.multiple_thresholds(p)
+            ref = self.const(float(len(thresholds)))
+            for j in range(len(thresholds) - 1, -1, -1):
+                ref = self.emit(OP_THRESHOLD, [0, x, PRED["GE"], self.param(thresholds[j]), ref, self.const(float(j))])
         elif name == "AggregatedIndexParameter":
             func = p.agg_func
             if not isinstance(func, str) or func not in ("sum", "min", "max", "product"):

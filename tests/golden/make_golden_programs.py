@@ -108,7 +108,11 @@ def custom_document(kind):
         # default bounds_error=True (outside the knots the reference raises, the device run fails the scenario with ST_NAN): on a
         # constant, so that the widened batches of the GPU tests stay inside
         P["curve_of_baseline"] = {"type": "interpolated", "parameter": "demand_baseline", "x": [1.0, 2.0], "y": [0.99, 1.01]}
-        P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume", "level_factor", "curve_of_level1", "curve_of_baseline"]
+        # index = first threshold the parameter value reaches (MultipleThresholdParameterIndexParameter)
+        P["level1_class"] = {"type": "multiplethresholdparameterindex", "parameter": "level1", "thresholds": [0.9, 0.8, 0.7]}
+        P["class_factor"] = {"type": "indexedarray", "index_parameter": "level1_class", "params": [1.0, 0.995, 1.005, 0.99]}
+        P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume", "level_factor", "curve_of_level1", "curve_of_baseline",
+                                               "class_factor"]
         # abstraction capacity: chosen by the sum of two indices (late in the run? storage low?) ...
         P["late"] = {"type": "currentordinaldaythreshold", "threshold": start.toordinal() + 500, "predicate": ">"}
         P["low_volume_index"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.6 * max_volume, "predicate": "LE"}
