@@ -43,14 +43,15 @@ def parameter_arrays(Parameter p):
         df = p
         if df.scenario is None:
             return dict(values=np.asarray(df._values)[:, :1].copy(), axis=None, offset=df.timestep_offset, col_map=None)
-        return dict(values=np.asarray(df._values).copy(), axis=df._scenario_index, offset=df.timestep_offset,
+        # a view, not a copy: the caller packs it into the program's table block (one copy of a [T, S] array instead of two)
+        return dict(values=np.asarray(df._values), axis=df._scenario_index, offset=df.timestep_offset,
                     col_map=None if df._scenario_ids is None else np.asarray(df._scenario_ids).copy())
     if type(p).__name__ == "ArrayIndexedParameter":
         ai = p
         return dict(values=np.asarray(ai.values).reshape(-1, 1).copy(), axis=None, offset=0, col_map=None)
     if type(p).__name__ == "ArrayIndexedScenarioParameter":
         ais = p
-        return dict(values=np.asarray(ais.values).copy(), axis=ais._scenario_index, offset=0, col_map=None)
+        return dict(values=np.asarray(ais.values), axis=ais._scenario_index, offset=0, col_map=None)
     if type(p).__name__ == "ConstantScenarioParameter":
         cs = p
         return dict(values=np.asarray(cs._values).reshape(1, -1).copy(), axis=cs._scenario_index, offset=0, col_map=None)
