@@ -22,7 +22,8 @@ from pywr.parameters._parameters cimport (
 )
 from pywr.parameters._thresholds cimport AbstractThresholdParameter, MultipleThresholdParameterIndexParameter
 from pywr.recorders._recorders cimport (
-    NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder,
+    NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder, NumpyArrayParameterRecorder,
+    NumpyArrayIndexParameterRecorder,
     BaseConstantStorageRecorder, NodeRecorder, StorageRecorder,
 )
 
@@ -125,12 +126,20 @@ def set_array_recorder(rec, double[:, :] data):
     """rec._data[:, :] = data for the NumpyArray node / storage recorder families."""
     cdef NumpyArrayNodeRecorder nr
     cdef NumpyArrayAbstractStorageRecorder sr
+    cdef NumpyArrayParameterRecorder pr
+    cdef NumpyArrayIndexParameterRecorder ir
     if isinstance(rec, NumpyArrayNodeRecorder):
         nr = rec
         nr._data[:, :] = data
     elif isinstance(rec, NumpyArrayAbstractStorageRecorder):
         sr = rec
         sr._data[:, :] = data
+    elif isinstance(rec, NumpyArrayParameterRecorder):
+        pr = rec
+        pr._data[:, :] = data
+    elif isinstance(rec, NumpyArrayIndexParameterRecorder):
+        ir = rec
+        ir._data = np.asarray(data).astype(np.int32)
     else:
         raise TypeError(f"unsupported recorder {type(rec).__name__}")
 
@@ -146,6 +155,8 @@ def temporal_agg_func(rec):
     if isinstance(rec, NumpyArrayAbstractStorageRecorder):
         sr = rec
         return sr._temporal_aggregator.func
+    if isinstance(rec, NumpyArrayParameterRecorder):
+        return rec._temporal_aggregator.func
     return None
 
 
@@ -162,6 +173,8 @@ def replace_array_recorder(rec, double[:, :] data):
     elif isinstance(rec, NumpyArrayAbstractStorageRecorder):
         sr = rec
         sr._data = data
+    elif isinstance(rec, NumpyArrayParameterRecorder):
+        (<NumpyArrayParameterRecorder>rec)._data = data
     else:
         raise TypeError(f"unsupported recorder {type(rec).__name__}")
 

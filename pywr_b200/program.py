@@ -733,6 +733,20 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         cname = type(rec).__name__
         if cname == "AggregatedRecorder":
             continue  # reduces other recorders' values() on the host at read-out (a13)
+        if cname in ("NumpyArrayParameterRecorder", "NumpyArrayIndexParameterRecorder"):
+            # the value (index) a parameter took in each timestep (pywr/recorders/_recorders.pyx:1361-1424, 1480-1540): a sample of
+            # its V slot, expressed as the deficit recorder of an EMPTY flow form (value - 0): no new recorder kind in the kernels
+            try:
+                ref = C.param(rec._param) if cname == "NumpyArrayParameterRecorder" else C.index_param(rec._param)
+            except Unsupported:
+                if not allow_host_recorders:
+                    raise
+                host_recorders.append(rec)
+                continue
+            rec_kind.append(REC_NODE_DEFICIT); rec_src.append(-1); rec_ref.append(ref); rec_factor.append(1.0); rec_row.append(-1)
+            rec_indptr.append(len(rec_col))
+            rec_objs.append(rec)
+            continue
         try:
             node = _bridge.recorder_node(rec)
         except Exception:

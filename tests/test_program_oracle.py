@@ -87,9 +87,10 @@ def test_run_on_device_with_pywr_objects():
 
 
 def test_host_mirror_protocol_keeps_host_recorders_alive():
-    """recorders the device cannot evaluate (a parameter recorder, a custom Python recorder
-    reading node.flow / storage.volume every timestep) run on the host against mirrored state and see
-    exactly what they see in a host run; device recorders of the same model are unaffected."""
+    """recorders the device cannot evaluate (a custom Python recorder reading node.flow /
+    storage.volume every timestep) run on the host against mirrored state and see exactly what they see in a
+    host run; device recorders of the same model are unaffected.  Parameter recorders (value and index) are
+    device recorders: samples of the parameter's slot."""
     pytest.importorskip("pywr")
     import os
     ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
@@ -98,7 +99,8 @@ def test_host_mirror_protocol_keeps_host_recorders_alive():
         pytest.skip("reference model documents not available")
     import oracle.pywr_oracle_solver  # noqa: F401
     from pywr.model import Model
-    from pywr.recorders import NumpyArrayNodeRecorder, NumpyArrayParameterRecorder, NumpyArrayStorageRecorder, Recorder
+    from pywr.recorders import (NumpyArrayIndexParameterRecorder, NumpyArrayNodeRecorder, NumpyArrayParameterRecorder,
+                                NumpyArrayStorageRecorder, Recorder)
     from pywr_b200.device_run import run_on_device
     from pywr_b200.program import Unsupported
 
@@ -123,14 +125,17 @@ def test_host_mirror_protocol_keeps_host_recorders_alive():
         level = [p for p in m.parameters if type(p).__name__ == "ControlCurveIndexParameter"][0]
         return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"]), NumpyArrayNodeRecorder(m, m.nodes["demand1"]),
                    FlowAndVolume(m, m.nodes["demand1"], m.nodes["reservoir1"], name="custom"),
-                   NumpyArrayParameterRecorder(m, m.parameters["demand_max_flow"], name="param")], level
+                   NumpyArrayParameterRecorder(m, m.parameters["demand_max_flow"], name="param"),
+                   NumpyArrayIndexParameterRecorder(m, level, name="level")], level
 
     m1, r1, _ = make(); m1.run()
     m2, r2, _ = make(); res = run_on_device(m2, engine_factory=OracleEngine)
-    assert sorted(res.host_recorders) == ["custom", "param"]
+    assert sorted(res.host_recorders) == ["custom"]
     for a, b in zip(r1, r2):
         assert _rel(np.array(b.data), np.array(a.data)) <= 1e-12, b.name
-    assert np.ptp(np.array(r1[2].data)) > 0 and np.ptp(np.array(r1[3].data)) > 0
+    assert np.array(r2[4].data).dtype == np.array(r1[4].data).dtype and np.array_equal(np.array(r2[4].data), np.array(r1[4].data))
+    assert np.allclose(np.asarray(r2[3].values()), np.asarray(r1[3].values()), rtol=1e-12)
+    assert np.ptp(np.array(r1[2].data)) > 0 and np.ptp(np.array(r1[3].data)) > 0 and np.ptp(np.array(r1[4].data)) > 0
     m3, _, _ = make()
     with pytest.raises(Unsupported):
         run_on_device(m3, engine_factory=OracleEngine, host_mirror=False)
