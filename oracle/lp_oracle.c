@@ -899,6 +899,10 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_LAG:  /* FlowParameter / AbstractNode._prev_flow: the array recorder's sample of timestep t - 1 */
+            /* pg is the first member of its orc_program, whose rec_out are the recorders' arrays */
+            v = t == 0 ? pref(h, a[1], p) : ((const orc_program *)pg)->rec_out[a[0]][(size_t)(t - 1) * h->S + sidx];
+            break;
         case B200LP_OP_INTERP: {  /* AbstractInterpolatedParameter.value, pywr/parameters/parameters.py:156-158 (linear interp1d) */
             const int32_t cnt = a[2];
             const int32_t *xk = a + 3, *yk = a + 3 + cnt;

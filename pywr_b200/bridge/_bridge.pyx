@@ -20,7 +20,8 @@ from pywr.parameters._parameters cimport (
     DataFrameParameter, ScenarioMonthlyProfileParameter, ScenarioDailyProfileParameter,
     ScenarioWeeklyProfileParameter, ArrayIndexedScenarioMonthlyFactorsParameter, ConstantScenarioIndexParameter,
 )
-from pywr.parameters._thresholds cimport AbstractThresholdParameter, MultipleThresholdParameterIndexParameter
+from pywr.parameters._thresholds cimport (AbstractThresholdParameter, MultipleThresholdParameterIndexParameter,
+                                          MultipleThresholdIndexParameter)
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder, NumpyArrayParameterRecorder,
     NumpyArrayIndexParameterRecorder,
@@ -90,9 +91,11 @@ def threshold_predicate(AbstractThresholdParameter p):
     return int(p.predicate)
 
 
-def multiple_thresholds(MultipleThresholdParameterIndexParameter p):
-    """``MultipleThresholdParameterIndexParameter.thresholds`` (pywr/parameters/_thresholds.pxd:29)"""
-    return list(p.thresholds)
+def multiple_thresholds(p):
+    """``thresholds`` of MultipleThresholdParameterIndexParameter / MultipleThresholdIndexParameter (_thresholds.pxd:24,29)"""
+    if isinstance(p, MultipleThresholdIndexParameter):
+        return list((<MultipleThresholdIndexParameter>p).thresholds)
+    return list((<MultipleThresholdParameterIndexParameter?>p).thresholds)
 
 
 def threshold_values(AbstractThresholdParameter p):

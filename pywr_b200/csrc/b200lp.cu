@@ -201,6 +201,7 @@ static bool resolve_structure(const b200lp_structure *s, int rows_cap, HostStruc
 // Ops of a program with every operand resolved to an index into V (decode_program below).
 struct DecodedProgram {
     std::vector<int> tab_dst, tab_table, tab_offset, code, rec_idx, rec_src;
+    bool has_lag = false;   // some op reads a recorder's sample of the previous timestep (B200LP_OP_LAG)
 };
 
 namespace jit {
@@ -852,6 +853,11 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             ok = na >= 3 && a[2] >= 2 && ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
             if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 2 * a[2] + 2); }
             break;
+        case B200LP_OP_LAG:  // -> recorder, V index of the initial value
+            ok = na >= 2 && a[0] >= 0 && a[0] < p->n_recorders && p->rec_kind[a[0]] == B200LP_REC_NODE_FLOW && ref_ok(a[1]) &&
+                 !(p->flags & B200LP_PROG_AGG_ONLY);
+            if (ok) { out.push_back(a[0]); out.push_back(vidx(a[1])); dec.has_lag = true; }
+            break;
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
             ok = na >= 4 && a[0] >= 0 && a[0] < nstor;
             if (ok) {
@@ -954,6 +960,7 @@ static void jit_prepare(b200lp_handle *h) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || sms <= 0) sms = 148;
         const long long warps = ((long long)h->S * h->jspec.G + 31) / 32;
         h->jspec.defer_recorders = warps <= 4LL * sms;   // at most one warp per scheduler
+        if (h->jspec.dec.has_lag) h->jspec.defer_recorders = false;   // a lagged sample must be in memory before the next timestep reads it
         if (const char *v = getenv("B200LP_JIT_DEFER")) h->jspec.defer_recorders = atoi(v) != 0;
     }
     const std::string src = jit::generate(h->jspec);

@@ -1017,8 +1017,14 @@ __device__ __forceinline__ double clamp_pc(double pc) {  // Storage.get_current_
 // `code` is in shared memory; every operand is an index into V.
 // VA: anything indexable that yields a double lvalue (a pointer into shared memory here, a strided plane view in
 // plane_program.inc).
+// where B200LP_OP_LAG finds yesterday's sample: the recorders' [T, S] output arrays, this scenario, this timestep
+struct LagCtx {
+    double *const *rec_out;
+    int t, S, sidx;
+};
+
 template <class VA>
-__device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V, const int pc_base) {
+__device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V, const int pc_base, const LagCtx lag) {
     int pos = 0;
     while (pos < n_code) {
         const int kind = code[pos], dst = code[pos + 1], na = code[pos + 2];
@@ -1058,6 +1064,11 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
         case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
+        case B200LP_OP_LAG: {  // FlowParameter / AbstractNode._prev_flow: the recorder's sample of timestep t - 1 (written by this
+                               // group before its last barrier, or by an earlier launch); a plain (not read-only-path) load
+            if (lag.t == 0) v = V[a[1]];
+            else v = *(const volatile double *)(lag.rec_out[a[0]] + (size_t)(lag.t - 1) * lag.S + lag.sidx);
+        } break;
         case B200LP_OP_THRESHOLD: {  // AbstractThresholdParameter.index / value (_thresholds.pyx:78-131), no ratchet
             const double x = V[a[0]], th = V[a[2]];
             const int pr = a[1];
@@ -1336,7 +1347,7 @@ lp_run_kernel(const DevStructure st, const DevState state, const DevProgram pg, 
             }
         } else if (pg.n_code > 0) {
             // generic interpreter: every lane evaluates the op list and stores the same values
-            eval_ops(code, pg.n_code, V, st.pc_base);
+            eval_ops(code, pg.n_code, V, st.pc_base, LagCtx{pg.rec_out, t, S, sidx});
             D.sync();
         }
         // ---- solve() ------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ __global__ void plane_ops_kernel(const PlaneProg Q, const DevProgram pg, const i
         q.last = __ldg(&pg.table_rows[tb]) - 1; q.stride = __ldg(&pg.table_cols[tb]); q.off = __ldg(&pg.tab_offset[j]);
         V[__ldg(&pg.tab_dst[j])] = q.at(t);
     }
-    if (pg.n_code > 0) eval_ops(pg.code, pg.n_code, V, Q.pc_base);
+    if (pg.n_code > 0) eval_ops(pg.code, pg.n_code, V, Q.pc_base, LagCtx{pg.rec_out, t, Q.S, s});
 }
 
 __global__ void plane_clear_status(const PlaneProg Q) {

@@ -142,7 +142,8 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
                 raise Unsupported(f"arrays='none': recorder {rec.name!r} aggregates over time with "
                                   f"{_bridge.temporal_agg_func(rec)!r}" + (" ignoring NaNs" if rec.ignore_nan else "") +
                                   ", which needs the array")
-        prog.flags |= PROG_AGG_ONLY
+        if not prog.has_lag:     # lagged flows read yesterday's sample from the recorder's array: it has to exist
+            prog.flags |= PROG_AGG_ONLY
     if engine_factory is None:
         from .engine import CudaEngine, ShardedEngine
 

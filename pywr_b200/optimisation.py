@@ -55,7 +55,8 @@ class PopulationEvaluator:
         self._agg_only = all(int(k) not in ARRAY_KINDS or temporal_aggregate(rec, 1, dummy, dummy, dummy) is not None
                              for k, rec in zip(self.program.rec_kind, self.program.recorders))
         if self._agg_only:
-            self.program.flags |= PROG_AGG_ONLY
+            if not self.program.has_lag:
+                self.program.flags |= PROG_AGG_ONLY
         self.S = len(model.scenarios.combinations)
         self.member = np.array([np.asarray(si.indices)[self.axis] for si in model.scenarios.combinations])
         if engine_factory is None:

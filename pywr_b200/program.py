@@ -28,7 +28,7 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
-OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD, OP_INTERP = 11, 12, 13, 14
+OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD, OP_INTERP, OP_LAG = 11, 12, 13, 14, 15
 PRED = {"LT": 0, "GT": 1, "EQ": 2, "LE": 3, "GE": 4}
 OP_STORAGE_RESET = 10
 PROG_AGG_ONLY = 1
@@ -120,6 +120,11 @@ class Program:
     def n_recorders(self):
         return int(self.rec_kind.shape[0])
 
+    @property
+    def has_lag(self):
+        """some op reads a recorder's sample of the previous timestep: the recorder arrays are state (no PROG_AGG_ONLY)"""
+        return bool(np.any(np.asarray(self.op_kind) == OP_LAG))
+
     def rec_shape(self, r, S):
         return (self.n_steps, S) if int(self.rec_kind[r]) in ARRAY_KINDS else (S,)
 
@@ -204,7 +209,7 @@ _VALUE_LEAVES = {  # state- and scenario-independent: sampled through their publ
     "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter",
 }
 _THRESHOLDS = {"ParameterThresholdParameter", "StorageThresholdParameter", "CurrentYearThresholdParameter",
-               "CurrentOrdinalDayThresholdParameter"}
+               "CurrentOrdinalDayThresholdParameter", "NodeThresholdParameter"}
 _SCENARIO_PROFILES = {
     "ScenarioMonthlyProfileParameter", "ScenarioDailyProfileParameter", "ScenarioWeeklyProfileParameter",
     "ArrayIndexedScenarioMonthlyFactorsParameter",
@@ -413,6 +418,8 @@ class _Compiler:
             return self.emit(OP_MAX0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
         if name == "NegativeMinParameter":
             return self.emit(OP_MIN0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
+        if name == "FlowParameter":                     # pywr/parameters/_parameters.pyx:1959-2008: the node's flow of the day before
+            return self.prev_flow(p.node, float(p.initial_value))
         if name == "DivisionParameter":                 # pywr/parameters/_parameters.pyx:1688-1739
             return self.emit(OP_DIV, [self.param(p.numerator), self.param(p.denominator)])
         if name == "OffsetParameter":                   # :1858-1907: parameter + offset
@@ -421,7 +428,7 @@ class _Compiler:
             return self.emit(OP_AGG, [AGG["product"], 2, self.const(p.scale), self.param(p.profile)])
         if name == "ConstantScenarioIndexParameter":    # :1228-1260 (value() of an IndexParameter is its index)
             return self.index_param(p)
-        if name in ("AggregatedIndexParameter", "MultipleThresholdParameterIndexParameter"):   # :1559-1685, _thresholds.pyx:242-292
+        if name in ("AggregatedIndexParameter", "MultipleThresholdParameterIndexParameter", "MultipleThresholdIndexParameter"):
             return self.index_param(p)
         if name in ("InterpolatedParameter", "InterpolatedVolumeParameter"):   # pywr/parameters/parameters.py:124-242
             kw = dict(p.interp_kwargs)
@@ -471,6 +478,12 @@ class _Compiler:
             ref = self.const(float(len(thresholds)))
             for j in range(len(thresholds) - 1, -1, -1):
                 ref = self.emit(OP_THRESHOLD, [0, x, PRED["GE"], self.param(thresholds[j]), ref, self.const(float(j))])
+        elif name == "MultipleThresholdIndexParameter":            # _thresholds.pyx:190-240: the same on yesterday's flow of a node
+            x = self.prev_flow(p.node)
+            thresholds = _bridge.multiple_thresholds(p)
+            ref = self.const(float(len(thresholds)))
+            for j in range(len(thresholds) - 1, -1, -1):
+                ref = self.emit(OP_THRESHOLD, [0, x, PRED["GE"], self.param(thresholds[j]), ref, self.const(float(j))])
         elif name == "AggregatedIndexParameter":
             func = p.agg_func
             if not isinstance(func, str) or func not in ("sum", "min", "max", "product"):
@@ -479,6 +492,19 @@ class _Compiler:
             ref = self.emit(OP_AGG, [AGG[func], len(refs)] + refs)
         else:                                           # value() of the remaining IndexParameters is float(index)
             ref = self.param(p)
+        self.memo[key] = ref
+        return ref
+
+    def prev_flow(self, node, initial=0.0) -> int:
+        """ref of the node's flow in the previous timestep (``AbstractNode._prev_flow``; ``initial`` at timestep 0): op LAG on a
+        flow recorder of the node, which compile_program appends (or finds) once the recorders are known"""
+        key = ("lag", id(node), float(initial))
+        if key in self.memo:
+            return self.memo[key]
+        if not hasattr(self, "lag_nodes"):
+            self.lag_nodes = []
+        self.lag_nodes.append(node)
+        ref = self.emit(OP_LAG, [-len(self.lag_nodes), self.const(initial)])    # recorder index patched in compile_program
         self.memo[key] = ref
         return ref
 
@@ -495,6 +521,10 @@ class _Compiler:
             return self.emit(OP_THRESHOLD, [0, self.param(p.param), pred, thr, v0, v1])
         if name == "StorageThresholdParameter":
             return self.emit(OP_THRESHOLD, [1, self.storage_of(p.storage), pred, thr, v0, v1])
+        if name == "NodeThresholdParameter":            # _thresholds.pyx:159-188: yesterday's flow; index 0 on the first timestep
+            inner = self.emit(OP_THRESHOLD, [0, self.prev_flow(p.node), pred, thr, v0, v1])
+            first = self.table(np.array([[1.0 if i == 0 else 0.0] for i in range(self.T)]), None)
+            return self.emit(OP_THRESHOLD, [0, first, PRED["EQ"], self.const(1.0), inner, v0])
         if name == "CurrentYearThresholdParameter":
             x = self.table(np.array([[float(ts.year)] for ts in self.timesteps]), None)
         else:                                           # CurrentOrdinalDayThresholdParameter
@@ -799,6 +829,29 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         rec_indptr.append(len(rec_col))
         rec_objs.append(rec)
 
+    # ---- lagged node flows (op LAG): the state is a flow recorder's [T, S] array; reuse the user's, else append a hidden one ----
+    n_visible = len(rec_objs)
+    rec_names_all = [str(getattr(r, "name", "")) for r in rec_objs]
+    lag_rec = []
+    for node in getattr(C, "lag_nodes", []):
+        found = next((r for r in range(len(rec_kind)) if rec_kind[r] == REC_NODE_FLOW and rec_factor[r] == 1.0 and r < n_visible
+                      and _bridge.recorder_node(rec_objs[r]) is node), None)
+        if found is None:
+            found = next((r for r, nd in lag_rec if nd is node), None)
+        if found is None:
+            form = _flow_form(base, node, node_id)
+            rec_kind.append(REC_NODE_FLOW); rec_src.append(node_id.get(id(node), -1)); rec_ref.append(0); rec_factor.append(1.0)
+            rec_row.append(flow_row.get(getattr(node, "fully_qualified_name", None), -1) if id(node) in node_id else -1)
+            for c in sorted(form):
+                rec_col.append(c); rec_w.append(form[c])
+            rec_indptr.append(len(rec_col))
+            rec_names_all.append(f"__prev_flow__{node.name}")
+            found = len(rec_kind) - 1
+        lag_rec.append((found, node))
+    for kind, _, args in C.ops:
+        if kind == OP_LAG and args[0] < 0:
+            args[0] = lag_rec[-args[0] - 1][0]
+
     # ---- aggregated storages: device storages without an LP row (C.aggregated_storage) -------------
     st_kind_all = list(base.st_kind)
     st_minv_all = list(_remap(base.st_minv_ref, mapping))
@@ -870,7 +923,7 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         initial_volume=vol0.reshape(-1), initial_pc=pc0.reshape(-1),
         rec_kind=i32(rec_kind), rec_src=i32(rec_src), rec_ref=i32(rec_ref), rec_factor=f64(rec_factor), rec_row=i32(rec_row),
         rec_indptr=i32(rec_indptr), rec_col=i32(rec_col), rec_w=f64(rec_w), recorders=rec_objs,
-        rec_names=[str(getattr(r, "name", "")) for r in rec_objs],
+        rec_names=rec_names_all,
     )
     prog.host_recorders = host_recorders
     prog.variable_tables = dict(C.variable_tables)

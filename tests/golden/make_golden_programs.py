@@ -55,6 +55,9 @@ CASES = [
     # ConstantScenarioIndexParameter as the index of IndexedArrayParameters; InterpolatedVolumeParameter / InterpolatedParameter
     # (B200LP_OP_INTERP)
     ("derived_parameters", "custom:derived", "route", "2103-12-31"),
+    # parameters of YESTERDAY's node flows (op B200LP_OP_LAG on hidden / shared flow recorders): FlowParameter,
+    # NodeThresholdParameter, MultipleThresholdIndexParameter
+    ("lagged_flows", "custom:lagged", "route", "2102-12-31"),
 ]
 
 
@@ -123,6 +126,24 @@ def custom_document(kind):
         P["cap_by_member"] = {"type": "indexedarray", "index_parameter": "member_class", "params": [3.5, 3.2, 2.4]}
         P["abs_cap"] = {"type": "aggregated", "agg_func": "min", "parameters": ["cap_by_state", "cap_by_member"]}
         next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "abs_cap"
+        return doc
+    if kind == "lagged":
+        doc = json.load(open(os.path.join(REF, "examples/thames/thames.json")))
+        for prm in doc["parameters"].values():
+            if isinstance(prm, dict) and "url" in prm and not os.path.isabs(prm["url"]):
+                prm["url"] = os.path.join(REF, "examples/thames", prm["url"])
+        P = doc["parameters"]
+        # today's abstraction is capped by yesterday's river flow past the gauge plus an allowance (FlowParameter with an
+        # initial value), demand is cut when yesterday's supply was short (NodeThresholdParameter: index 0 on day one) and
+        # scaled by a class of yesterday's inflow (MultipleThresholdIndexParameter)
+        P["river_yesterday"] = {"type": "flow", "node": "term1", "initial_value": 2.5}
+        P["abs_cap"] = {"type": "aggregated", "agg_func": "min",
+                        "parameters": [3.5, {"type": "aggregated", "agg_func": "sum", "parameters": ["river_yesterday", 0.8]}]}
+        next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "abs_cap"
+        P["short_yesterday"] = {"type": "nodethreshold", "node": "demand1", "threshold": 1.5, "predicate": "LT", "values": [1.0, 0.9]}
+        P["inflow_class"] = {"type": "multiplethresholdindex", "node": "catchment1", "thresholds": [6.0, 3.0, 1.5]}
+        P["inflow_factor"] = {"type": "indexedarray", "index_parameter": "inflow_class", "params": [1.05, 1.0, 0.97, 0.92]}
+        P["demand_max_flow"]["parameters"] += ["short_yesterday", "inflow_factor"]
         return doc
     if kind == "aggregated_storage":
         # tests/models/three_storage.json: the inflow of reservoir 0 is switched by a control curve on the AGGREGATED storage

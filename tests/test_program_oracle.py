@@ -278,3 +278,48 @@ def test_model_run_with_device_run_solver_option():
     m4.nodes["abs1"].max_flow = Custom(m4)
     with pytest.raises(Unsupported):
         m4.run()
+
+
+@pytest.mark.parametrize("arrays", ["eager", "none"])
+def test_lagged_flow_parameters_without_a_user_recorder_on_the_node(arrays):
+    """FlowParameter / NodeThresholdParameter read yesterday's flow of a node (op B200LP_OP_LAG).  The state is a flow recorder's
+    [T, S] array: with no user recorder on the node the compiler appends a hidden one, and a read-out without arrays keeps
+    storing them (no B200LP_PROG_AGG_ONLY)."""
+    pytest.importorskip("pywr")
+    import json
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.recorders import NumpyArrayStorageRecorder, TotalDeficitNodeRecorder
+    from pywr_b200.device_run import run_on_device
+    from pywr_b200.program import PROG_AGG_ONLY
+
+    def make():
+        doc = json.load(open(path))
+        for prm in doc["parameters"].values():
+            if isinstance(prm, dict) and "url" in prm and not os.path.isabs(prm["url"]):
+                prm["url"] = os.path.join(ref, "examples/thames", prm["url"])
+        P = doc["parameters"]
+        P["river_yesterday"] = {"type": "flow", "node": "term1", "initial_value": 1.0}
+        P["abs_cap"] = {"type": "aggregated", "agg_func": "min",
+                        "parameters": [3.5, {"type": "aggregated", "agg_func": "sum", "parameters": ["river_yesterday", 0.5]}]}
+        next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "abs_cap"
+        P["short"] = {"type": "nodethreshold", "node": "demand1", "threshold": 1.6, "predicate": "LT", "values": [1.0, 0.93]}
+        P["demand_max_flow"]["parameters"].append("short")
+        m = Model.load(doc, solver="oracle")
+        m.timestepper.end = "2100-12-31"
+        return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], name="vol"), TotalDeficitNodeRecorder(m, m.nodes["demand1"], name="tdef")]
+
+    m1, r1 = make(); m1.run()
+    m2, r2 = make(); res = run_on_device(m2, engine_factory=OracleEngine, arrays=arrays)
+    assert res.program.n_recorders == 4 and len(res.program.recorders) == 2          # two hidden flow recorders
+    assert res.program.has_lag and not (res.program.flags & PROG_AGG_ONLY)
+    for a, b in zip(r1, r2):
+        assert np.allclose(np.asarray(b.values()), np.asarray(a.values()), rtol=1e-12, atol=0), b.name
+    if arrays == "eager":
+        assert _rel(np.array(r2[0].data), np.array(r1[0].data)) <= 1e-12
+    assert np.ptp(np.array(r1[0].data)) > 0
