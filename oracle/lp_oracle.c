@@ -901,7 +901,7 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
         case B200LP_OP_LAG:  /* FlowParameter / AbstractNode._prev_flow: the array recorder's sample of timestep t - 1 */
             /* pg is the first member of its orc_program, whose rec_out are the recorders' arrays */
-            v = t == 0 ? pref(h, a[1], p) : ((const orc_program *)pg)->rec_out[a[0]][(size_t)(t - 1) * h->S + sidx];
+            v = t < a[2] ? pref(h, a[1], p) : ((const orc_program *)pg)->rec_out[a[0]][(size_t)(t - a[2]) * h->S + sidx];
             break;
         case B200LP_OP_INTERP: {  /* AbstractInterpolatedParameter.value, pywr/parameters/parameters.py:156-158 (linear interp1d) */
             const int32_t cnt = a[2];

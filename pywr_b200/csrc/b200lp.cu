@@ -853,10 +853,10 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             ok = na >= 3 && a[2] >= 2 && ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
             if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 2 * a[2] + 2); }
             break;
-        case B200LP_OP_LAG:  // -> recorder, V index of the initial value
-            ok = na >= 2 && a[0] >= 0 && a[0] < p->n_recorders && p->rec_kind[a[0]] == B200LP_REC_NODE_FLOW && ref_ok(a[1]) &&
-                 !(p->flags & B200LP_PROG_AGG_ONLY);
-            if (ok) { out.push_back(a[0]); out.push_back(vidx(a[1])); dec.has_lag = true; }
+        case B200LP_OP_LAG:  // -> recorder, V index of the initial value, steps
+            ok = na >= 3 && a[0] >= 0 && a[0] < p->n_recorders && ref_ok(a[1]) && a[2] >= 1 && !(p->flags & B200LP_PROG_AGG_ONLY) &&
+                 (p->rec_kind[a[0]] == B200LP_REC_NODE_FLOW || p->rec_kind[a[0]] == B200LP_REC_NODE_DEFICIT);
+            if (ok) { out.push_back(a[0]); out.push_back(vidx(a[1])); out.push_back(a[2]); dec.has_lag = true; }
             break;
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc
             ok = na >= 4 && a[0] >= 0 && a[0] < nstor;

@@ -1066,8 +1066,8 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
         case B200LP_OP_LAG: {  // FlowParameter / AbstractNode._prev_flow: the recorder's sample of timestep t - 1 (written by this
                                // group before its last barrier, or by an earlier launch); a plain (not read-only-path) load
-            if (lag.t == 0) v = V[a[1]];
-            else v = *(const volatile double *)(lag.rec_out[a[0]] + (size_t)(lag.t - 1) * lag.S + lag.sidx);
+            if (lag.t < a[2]) v = V[a[1]];
+            else v = *(const volatile double *)(lag.rec_out[a[0]] + (size_t)(lag.t - a[2]) * lag.S + lag.sidx);
         } break;
         case B200LP_OP_THRESHOLD: {  // AbstractThresholdParameter.index / value (_thresholds.pyx:78-131), no ratchet
             const double x = V[a[0]], th = V[a[2]];

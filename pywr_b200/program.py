@@ -420,6 +420,25 @@ class _Compiler:
             return self.emit(OP_MIN0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
         if name == "FlowParameter":                     # pywr/parameters/_parameters.pyx:1959-2008: the node's flow of the day before
             return self.prev_flow(p.node, float(p.initial_value))
+        if name == "DeficitParameter":                  # :1910-1957: yesterday's max_flow - flow, 0 on the first timestep
+            return self.prev_flow(p.node, 0.0, 1, deficit=True)
+        if name in ("FlowDelayParameter", "RollingMeanFlowNodeParameter"):   # :2105-2163, :2191-2264
+            n = int(p.timesteps)
+            if int(p.days) > 0:
+                delta = self.model.timestepper.delta
+                delta = int(getattr(delta, "days", delta))
+                n = int(p.days) // delta
+            if n < 1 or n > 64:
+                raise Unsupported(f"{name} over {n} timesteps")
+            if name == "FlowDelayParameter":
+                return self.prev_flow(p.node, float(p.initial_flow), n)
+            # mean of the last min(t, n) flows; the initial flow on the first timestep
+            lags = [self.prev_flow(p.node, 0.0, j) for j in range(1, n + 1)]
+            total = self.emit(OP_AGG, [AGG["sum"], n] + lags)
+            count = self.table(np.array([[float(min(max(i, 1), n))] for i in range(self.T)]), None)
+            mean = self.emit(OP_DIV, [total, count])
+            first = self.table(np.array([[1.0 if i == 0 else 0.0] for i in range(self.T)]), None)
+            return self.emit(OP_THRESHOLD, [0, first, PRED["EQ"], self.const(1.0), mean, self.const(float(p.initial_flow))])
         if name == "DivisionParameter":                 # pywr/parameters/_parameters.pyx:1688-1739
             return self.emit(OP_DIV, [self.param(p.numerator), self.param(p.denominator)])
         if name == "OffsetParameter":                   # :1858-1907: parameter + offset
@@ -495,16 +514,17 @@ class _Compiler:
         self.memo[key] = ref
         return ref
 
-    def prev_flow(self, node, initial=0.0) -> int:
-        """ref of the node's flow in the previous timestep (``AbstractNode._prev_flow``; ``initial`` at timestep 0): op LAG on a
-        flow recorder of the node, which compile_program appends (or finds) once the recorders are known"""
-        key = ("lag", id(node), float(initial))
+    def prev_flow(self, node, initial=0.0, steps=1, deficit=False) -> int:
+        """ref of the node's flow (or deficit) ``steps`` timesteps ago (``AbstractNode._prev_flow`` for one step; ``initial`` during
+        the first ``steps`` timesteps): op LAG on a flow / deficit recorder of the node, which compile_program finds or appends
+        once the recorders are known"""
+        key = ("lag", id(node), float(initial), int(steps), bool(deficit))
         if key in self.memo:
             return self.memo[key]
         if not hasattr(self, "lag_nodes"):
             self.lag_nodes = []
-        self.lag_nodes.append(node)
-        ref = self.emit(OP_LAG, [-len(self.lag_nodes), self.const(initial)])    # recorder index patched in compile_program
+        self.lag_nodes.append((node, bool(deficit)))
+        ref = self.emit(OP_LAG, [-len(self.lag_nodes), self.const(initial), int(steps)])   # recorder index patched in compile_program
         self.memo[key] = ref
         return ref
 
@@ -833,21 +853,27 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     n_visible = len(rec_objs)
     rec_names_all = [str(getattr(r, "name", "")) for r in rec_objs]
     lag_rec = []
-    for node in getattr(C, "lag_nodes", []):
-        found = next((r for r in range(len(rec_kind)) if rec_kind[r] == REC_NODE_FLOW and rec_factor[r] == 1.0 and r < n_visible
+    for node, deficit in getattr(C, "lag_nodes", []):
+        want = REC_NODE_DEFICIT if deficit else REC_NODE_FLOW
+        found = next((r for r in range(n_visible) if rec_kind[r] == want and rec_factor[r] == 1.0
                       and _bridge.recorder_node(rec_objs[r]) is node), None)
         if found is None:
-            found = next((r for r, nd in lag_rec if nd is node), None)
+            found = next((r for r, nd, df in lag_rec if nd is node and df == deficit), None)
         if found is None:
             form = _flow_form(base, node, node_id)
-            rec_kind.append(REC_NODE_FLOW); rec_src.append(node_id.get(id(node), -1)); rec_ref.append(0); rec_factor.append(1.0)
+            ref = 0
+            if deficit:
+                if id(node) not in max_flow_ref:
+                    raise Unsupported(f"DeficitParameter on {type(node).__name__} without an LP max_flow")
+                ref = max_flow_ref[id(node)]
+            rec_kind.append(want); rec_src.append(node_id.get(id(node), -1)); rec_ref.append(ref); rec_factor.append(1.0)
             rec_row.append(flow_row.get(getattr(node, "fully_qualified_name", None), -1) if id(node) in node_id else -1)
             for c in sorted(form):
                 rec_col.append(c); rec_w.append(form[c])
             rec_indptr.append(len(rec_col))
-            rec_names_all.append(f"__prev_flow__{node.name}")
+            rec_names_all.append(f"__prev_{'deficit' if deficit else 'flow'}__{node.name}")
             found = len(rec_kind) - 1
-        lag_rec.append((found, node))
+        lag_rec.append((found, node, deficit))
     for kind, _, args in C.ops:
         if kind == OP_LAG and args[0] < 0:
             args[0] = lag_rec[-args[0] - 1][0]

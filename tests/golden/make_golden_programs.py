@@ -143,7 +143,18 @@ def custom_document(kind):
         P["short_yesterday"] = {"type": "nodethreshold", "node": "demand1", "threshold": 1.5, "predicate": "LT", "values": [1.0, 0.9]}
         P["inflow_class"] = {"type": "multiplethresholdindex", "node": "catchment1", "thresholds": [6.0, 3.0, 1.5]}
         P["inflow_factor"] = {"type": "indexedarray", "index_parameter": "inflow_class", "params": [1.05, 1.0, 0.97, 0.92]}
-        P["demand_max_flow"]["parameters"] += ["short_yesterday", "inflow_factor"]
+        # yesterday's deficit eases today's demand a little (DeficitParameter), the flow past the gauge three days ago and the
+        # mean abstraction of the last week feed the compensation flow (FlowDelayParameter, RollingMeanFlowNodeParameter)
+        P["deficit_yesterday"] = {"type": "deficit", "node": "demand1"}
+        P["easing"] = {"type": "aggregated", "agg_func": "max",
+                       "parameters": [0.9, {"type": "aggregated", "agg_func": "sum", "parameters": [1.0, {"type": "negative", "parameter": "deficit_yesterday"}]}]}
+        P["gauge_3_days_ago"] = {"type": "flowdelay", "node": "mrf1", "timesteps": 3, "initial_flow": 0.4}
+        P["abs_last_week"] = {"type": "rollingmeanflownode", "node": "abs1", "timesteps": 7, "initial_flow": 1.0}
+        P["mrf_today"] = {"type": "aggregated", "agg_func": "sum",
+                          "parameters": [0.5, {"type": "aggregated", "agg_func": "product", "parameters": [0.1, "gauge_3_days_ago"]},
+                                         {"type": "aggregated", "agg_func": "product", "parameters": [0.05, "abs_last_week"]}]}
+        next(n for n in doc["nodes"] if n["name"] == "mrf1")["mrf"] = "mrf_today"
+        P["demand_max_flow"]["parameters"] += ["short_yesterday", "inflow_factor", "easing"]
         return doc
     if kind == "aggregated_storage":
         # tests/models/three_storage.json: the inflow of reservoir 0 is switched by a control curve on the AGGREGATED storage
