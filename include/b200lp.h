@@ -266,6 +266,9 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
                                      deficit: DeficitParameter (:1910-1957); older flows: FlowDelayParameter (:2105-2163),
                                      RollingMeanFlowNodeParameter (:2191-2264).  The recorder's [T, S] array is the state: not
                                      available with B200LP_PROG_AGG_ONLY */
+#define B200LP_OP_STATE 16         /* args: source, storage.  A storage's state as a value: source 1 its current volume, 2 its proportional
+                                     volume as stored, 3 the same clamped to [0, 1] (Storage.get_current_pc, pywr/_core.pyx:1027-1039).
+                                     StorageParameter (pywr/parameters/_parameters.pyx:2011-2044), Polynomial1DParameter on a storage */
 #define B200LP_PRED_LT 0
 #define B200LP_PRED_GT 1
 #define B200LP_PRED_EQ 2

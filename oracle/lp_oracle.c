@@ -899,6 +899,9 @@ static void orc_eval_ops(const orc_handle *h, const b200lp_program *pg, orc_scen
         case B200LP_OP_MAX0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = pref(h, a[0], p), th = pref(h, a[1], p); v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = pref(h, a[0], p) / pref(h, a[1], p); break;
+        case B200LP_OP_STATE:  /* StorageParameter.value, _parameters.pyx:2032-2036 */
+            v = a[0] == 1 ? c->vol[a[1]] : (a[0] == 3 ? clamp_pc(c->pc[a[1]]) : c->pc[a[1]]);
+            break;
         case B200LP_OP_LAG:  /* FlowParameter / AbstractNode._prev_flow: the array recorder's sample of timestep t - 1 */
             /* pg is the first member of its orc_program, whose rec_out are the recorders' arrays */
             v = t < a[2] ? pref(h, a[1], p) : ((const orc_program *)pg)->rec_out[a[0]][(size_t)(t - a[2]) * h->S + sidx];

@@ -22,6 +22,7 @@ from pywr.parameters._parameters cimport (
 )
 from pywr.parameters._thresholds cimport (AbstractThresholdParameter, MultipleThresholdParameterIndexParameter,
                                           MultipleThresholdIndexParameter)
+from pywr.parameters._polynomial cimport Polynomial1DParameter
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder, NumpyArrayParameterRecorder,
     NumpyArrayIndexParameterRecorder,
@@ -96,6 +97,13 @@ def multiple_thresholds(p):
     if isinstance(p, MultipleThresholdIndexParameter):
         return list((<MultipleThresholdIndexParameter>p).thresholds)
     return list((<MultipleThresholdParameterIndexParameter?>p).thresholds)
+
+
+def polynomial1d_info(Polynomial1DParameter p):
+    """the non-public members of Polynomial1DParameter (pywr/parameters/_polynomial.pxd:5-12)"""
+    return dict(coefficients=np.asarray(p.coefficients).copy(), node=p._other_node, storage_node=p._storage_node,
+                parameter=p._parameter, use_proportional_volume=bool(p.use_proportional_volume), offset=float(p.offset),
+                scale=float(p.scale))
 
 
 def threshold_values(AbstractThresholdParameter p):

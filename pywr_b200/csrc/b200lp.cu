@@ -853,6 +853,10 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             ok = na >= 3 && a[2] >= 2 && ((a[0] == 0 && ref_ok(a[1])) || (a[0] == 1 && a[1] >= 0 && a[1] < nstor));
             if (ok) { out.push_back(a[0] == 0 ? vidx(a[1]) : vol_base + a[1]); out.push_back(a[2]); ok = refs(3, 2 * a[2] + 2); }
             break;
+        case B200LP_OP_STATE:  // -> V index of the volume / proportional volume, clamp flag
+            ok = na >= 2 && a[0] >= 1 && a[0] <= 3 && a[1] >= 0 && a[1] < nstor;
+            if (ok) { out.push_back(a[0] == 1 ? vol_base + a[1] : pc_base + a[1]); out.push_back(a[0] == 3 ? 1 : 0); }
+            break;
         case B200LP_OP_LAG:  // -> recorder, V index of the initial value, steps
             ok = na >= 3 && a[0] >= 0 && a[0] < p->n_recorders && ref_ok(a[1]) && a[2] >= 1 && !(p->flags & B200LP_PROG_AGG_ONLY) &&
                  (p->rec_kind[a[0]] == B200LP_REC_NODE_FLOW || p->rec_kind[a[0]] == B200LP_REC_NODE_DEFICIT);

@@ -1064,6 +1064,7 @@ __device__ __forceinline__ void eval_ops(const int *code, const int n_code, VA V
         case B200LP_OP_MAX0: { const double x = V[a[0]], th = V[a[1]]; v = x > th ? x : th; } break;
         case B200LP_OP_MIN0: { const double x = V[a[0]], th = V[a[1]]; v = x < th ? x : th; } break;
         case B200LP_OP_DIV: v = V[a[0]] / V[a[1]]; break;
+        case B200LP_OP_STATE: v = a[1] ? clamp_pc(V[a[0]]) : V[a[0]]; break;   // StorageParameter.value (_parameters.pyx:2032-2036)
         case B200LP_OP_LAG: {  // FlowParameter / AbstractNode._prev_flow: the recorder's sample of timestep t - 1 (written by this
                                // group before its last barrier, or by an earlier launch); a plain (not read-only-path) load
             if (lag.t < a[2]) v = V[a[1]];

@@ -28,7 +28,7 @@ import numpy as np
 from .structure import LPStructure, build_structure, REF_STATE, ST_KIND_VIRTUAL
 
 OP_TABLE, OP_AGG, OP_CONTROL_CURVE, OP_CC_INDEX, OP_INDEXED, OP_NEG, OP_MAX0, OP_MIN0, OP_DIV = range(1, 10)
-OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD, OP_INTERP, OP_LAG = 11, 12, 13, 14, 15
+OP_CC_INTERP, OP_CC_PIECEWISE, OP_THRESHOLD, OP_INTERP, OP_LAG, OP_STATE = 11, 12, 13, 14, 15, 16
 PRED = {"LT": 0, "GT": 1, "EQ": 2, "LE": 3, "GE": 4}
 OP_STORAGE_RESET = 10
 PROG_AGG_ONLY = 1
@@ -206,7 +206,7 @@ class Program:
 # ----------------------------------------------------------------------------------------------
 _VALUE_LEAVES = {  # state- and scenario-independent: sampled through their public ``value(ts, si)``
     "MonthlyProfileParameter", "DailyProfileParameter", "WeeklyProfileParameter",
-    "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter",
+    "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter", "DiscountFactorParameter",
 }
 _THRESHOLDS = {"ParameterThresholdParameter", "StorageThresholdParameter", "CurrentYearThresholdParameter",
                "CurrentOrdinalDayThresholdParameter", "NodeThresholdParameter"}
@@ -420,6 +420,30 @@ class _Compiler:
             return self.emit(OP_MIN0, [self.emit(OP_NEG, [self.param(p.parameter)]), self.const(p.threshold)])
         if name == "FlowParameter":                     # pywr/parameters/_parameters.pyx:1959-2008: the node's flow of the day before
             return self.prev_flow(p.node, float(p.initial_value))
+        if name == "StorageParameter":                  # :2011-2044: the storage's volume / proportional volume as they stand
+            return self.emit(OP_STATE, [2 if p.use_proportional_volume else 1, self.storage_of(p.storage_node)])
+        if name == "Polynomial1DParameter":             # pywr/parameters/_polynomial.pyx:5-88: sum c_i x^i of a parameter / a storage
+            info = _bridge.polynomial1d_info(p)
+            if info["parameter"] is not None:
+                x = self.param(info["parameter"])
+            elif info["storage_node"] is not None:
+                x = self.emit(OP_STATE, [3 if info["use_proportional_volume"] else 1, self.storage_of(info["storage_node"])])
+            else:
+                raise Unsupported("Polynomial1DParameter of a node's flow of the same timestep")
+            x = self.emit(OP_AGG, [AGG["sum"], 2, self.emit(OP_AGG, [AGG["product"], 2, x, self.const(info["scale"])]), self.const(info["offset"])])
+            terms, power = [], None
+            for i, c in enumerate(info["coefficients"]):
+                if i == 0:
+                    terms.append(self.const(c))              # c_0 * x**0
+                    continue
+                power = x if i == 1 else self.emit(OP_AGG, [AGG["product"], 2, power, x])
+                terms.append(self.emit(OP_AGG, [AGG["product"], 2, self.const(c), power]))
+            return self.emit(OP_AGG, [AGG["sum"], len(terms)] + terms)
+        if name == "ScenarioWrapperParameter":          # pywr/parameters/parameters.py:359-404: one child parameter per scenario member
+            axis = self.model.scenarios.get_scenario_index(p.scenario)
+            size = p.scenario.size
+            member = self.table(np.arange(size, dtype=np.float64).reshape(1, -1), axis)
+            return self.emit(OP_INDEXED, [member, size] + [self.param(c) for c in p.parameters])
         if name == "DeficitParameter":                  # :1910-1957: yesterday's max_flow - flow, 0 on the first timestep
             return self.prev_flow(p.node, 0.0, 1, deficit=True)
         if name in ("FlowDelayParameter", "RollingMeanFlowNodeParameter"):   # :2105-2163, :2191-2264

@@ -114,8 +114,20 @@ def custom_document(kind):
         # index = first threshold the parameter value reaches (MultipleThresholdParameterIndexParameter)
         P["level1_class"] = {"type": "multiplethresholdparameterindex", "parameter": "level1", "thresholds": [0.9, 0.8, 0.7]}
         P["class_factor"] = {"type": "indexedarray", "index_parameter": "level1_class", "params": [1.0, 0.995, 1.005, 0.99]}
+        # the storage's own state as a parameter (B200LP_OP_STATE), polynomials of it and of a parameter, one child per scenario
+        # member, a time-only discount factor
+        P["stored"] = {"type": "storage", "storage_node": "reservoir1"}
+        P["stored_factor"] = {"type": "aggregated", "agg_func": "sum",
+                              "parameters": [0.98, {"type": "aggregated", "agg_func": "product", "parameters": [0.0002, "stored"]}]}
+        P["poly_of_level"] = {"type": "polynomial1d", "storage_node": "reservoir1", "use_proportional_volume": True,
+                              "coefficients": [0.97, 0.08, -0.05], "scale": 0.9, "offset": 0.05}
+        P["poly_of_profile"] = {"type": "polynomial1d", "parameter": "demand_profile", "coefficients": [1.0, -0.02, 0.015, 0.001]}
+        P["by_member"] = {"type": "scenariowrapper", "scenario": "demand",
+                          "parameters": [{"type": "constant", "value": 1.0}, "poly_of_profile", {"type": "constant", "value": 0.99},
+                                         "curve_of_baseline", {"type": "constant", "value": 1.01}]}
+        P["discount"] = {"type": "discountfactor", "rate": 0.035, "base_year": 2100}
         P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume", "level_factor", "curve_of_level1", "curve_of_baseline",
-                                               "class_factor"]
+                                               "class_factor", "stored_factor", "poly_of_level", "by_member"]
         # abstraction capacity: chosen by the sum of two indices (late in the run? storage low?) ...
         P["late"] = {"type": "currentordinaldaythreshold", "threshold": start.toordinal() + 500, "predicate": ">"}
         P["low_volume_index"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.6 * max_volume, "predicate": "LE"}
@@ -124,7 +136,8 @@ def custom_document(kind):
         # ... and capped per member of the demand scenario
         P["member_class"] = {"type": "constantscenarioindex", "scenario": "demand", "values": [0, 1, 1, 0, 2]}
         P["cap_by_member"] = {"type": "indexedarray", "index_parameter": "member_class", "params": [3.5, 3.2, 2.4]}
-        P["abs_cap"] = {"type": "aggregated", "agg_func": "min", "parameters": ["cap_by_state", "cap_by_member"]}
+        P["abs_cap"] = {"type": "aggregated", "agg_func": "min", "parameters": [
+            "cap_by_state", "cap_by_member", {"type": "aggregated", "agg_func": "product", "parameters": [3.45, "discount"]}]}
         next(n for n in doc["nodes"] if n["name"] == "abs1")["max_flow"] = "abs_cap"
         return doc
     if kind == "lagged":
