@@ -76,6 +76,11 @@ def park_timestepper(model):
         pass
 
 
+PLAIN_ARRAY_RECORDERS = {"NumpyArrayNodeRecorder", "NumpyArrayNodeDeficitRecorder", "NumpyArrayNodeSuppliedRatioRecorder",
+                         "NumpyArrayNodeCurtailmentRatioRecorder", "NumpyArrayStorageRecorder", "NumpyArrayParameterRecorder",
+                         "NumpyArrayLevelRecorder", "NumpyArrayAreaRecorder"}
+
+
 def temporal_aggregate(rec, T, ssum, smin, smax):
     """Recorder.values() of an array recorder from the device's running aggregates, or None when its temporal
     aggregation needs the array itself (median, percentiles, custom callables, ignore_nan)."""
@@ -89,6 +94,8 @@ def device_temporal_agg(rec):
     """"sum" / "mean" / "min" / "max" when the device's running aggregates give this recorder's values(), else None."""
     from .bridge import _bridge
 
+    if type(rec).__name__ not in PLAIN_ARRAY_RECORDERS:      # duration curves etc.: values() is not a temporal aggregate of the array
+        return None
     func = _bridge.temporal_agg_func(rec)
     if not isinstance(func, str) or func.lower() not in DEVICE_TEMPORAL_AGGS or getattr(rec, "ignore_nan", False):
         return None

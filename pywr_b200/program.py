@@ -800,7 +800,11 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
         "NumpyArrayNodeCurtailmentRatioRecorder": REC_NODE_CURTAIL,
         "TotalDeficitNodeRecorder": REC_TOTAL_DEFICIT, "TotalFlowNodeRecorder": REC_TOTAL_FLOW,
         "MeanFlowNodeRecorder": REC_MEAN_FLOW, "DeficitFrequencyNodeRecorder": REC_DEFICIT_FREQ,
+        # subclasses of NumpyArrayNodeRecorder that only add a finish() over the recorded array (:814-990)
+        "FlowDurationCurveRecorder": REC_NODE_FLOW, "SeasonalFlowDurationCurveRecorder": REC_NODE_FLOW,
+        "FlowDurationCurveDeviationRecorder": REC_NODE_FLOW,
     }
+    storage_array_recorders = ("NumpyArrayStorageRecorder", "StorageDurationCurveRecorder")   # the latter: finish() only (:1243-1302)
     needs_max_flow = {REC_NODE_DEFICIT, REC_NODE_SUPPLIED, REC_NODE_CURTAIL, REC_TOTAL_DEFICIT, REC_DEFICIT_FREQ}
     host_recorders = []
     for rec in recorders:
@@ -821,12 +825,27 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
             rec_indptr.append(len(rec_col))
             rec_objs.append(rec)
             continue
+        if cname in ("NumpyArrayLevelRecorder", "NumpyArrayAreaRecorder"):
+            # Storage.get_level / get_area (pywr/_core.pyx:1256-1280, recorders :1305-1358): the value of the storage's level /
+            # area parameter (or constant) in each timestep - a parameter sample like the two above
+            try:
+                st_node = _bridge.recorder_node(rec)
+                ref = C.value_ref(st_node.level if cname == "NumpyArrayLevelRecorder" else st_node.area)
+            except Unsupported:
+                if not allow_host_recorders:
+                    raise
+                host_recorders.append(rec)
+                continue
+            rec_kind.append(REC_NODE_DEFICIT); rec_src.append(-1); rec_ref.append(ref); rec_factor.append(1.0); rec_row.append(-1)
+            rec_indptr.append(len(rec_col))
+            rec_objs.append(rec)
+            continue
         try:
             node = _bridge.recorder_node(rec)
         except Exception:
             node = None
-        if allow_host_recorders and (node is None or (cname not in node_kinds and cname not in (
-                "NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"))):
+        if allow_host_recorders and (node is None or (cname not in node_kinds and cname not in storage_array_recorders
+                                                      and cname != "MinimumVolumeStorageRecorder")):
             host_recorders.append(rec)
             continue
         if allow_host_recorders:
@@ -857,7 +876,7 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
             rec_row.append(flow_row.get(getattr(node, "fully_qualified_name", None), -1) if id(node) in node_id else -1)
             for c in sorted(form):
                 rec_col.append(c); rec_w.append(form[c])
-        elif cname in ("NumpyArrayStorageRecorder", "MinimumVolumeStorageRecorder"):
+        elif cname in storage_array_recorders or cname == "MinimumVolumeStorageRecorder":
             k = C.storage_index.get(id(node))
             if k is None and type(node).__name__ == "AggregatedStorage":
                 k = C.aggregated_storage(node)

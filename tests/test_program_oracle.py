@@ -323,3 +323,38 @@ def test_lagged_flow_parameters_without_a_user_recorder_on_the_node(arrays):
     if arrays == "eager":
         assert _rel(np.array(r2[0].data), np.array(r1[0].data)) <= 1e-12
     assert np.ptp(np.array(r1[0].data)) > 0
+
+
+def test_duration_curve_and_level_recorders_run_on_the_device():
+    """Subclasses that only post-process the recorded array in finish() (flow / storage duration curves) ride on the device's array
+    recorders; NumpyArrayLevelRecorder samples the storage's level parameter (an InterpolatedVolumeParameter here)."""
+    pytest.importorskip("pywr")
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.parameters import InterpolatedVolumeParameter
+    from pywr.recorders import FlowDurationCurveRecorder, NumpyArrayLevelRecorder, StorageDurationCurveRecorder
+    from pywr_b200.device_run import run_on_device
+
+    def make():
+        m = Model.load(path, solver="oracle")
+        m.timestepper.end = "2100-12-31"
+        res = m.nodes["reservoir1"]
+        res.level = InterpolatedVolumeParameter(m, res, [0.0, 60.0, 140.0, 200.0], [10.0, 14.0, 17.5, 19.0],
+                                                interp_kwargs={"bounds_error": False, "fill_value": (10.0, 19.0)})
+        pct = [5.0, 25.0, 50.0, 75.0, 95.0]
+        return m, [FlowDurationCurveRecorder(m, m.nodes["term1"], pct, name="fdc"),
+                   StorageDurationCurveRecorder(m, res, pct, name="sdc"), NumpyArrayLevelRecorder(m, res, name="level")]
+
+    m1, r1 = make(); m1.run()
+    m2, r2 = make(); out = run_on_device(m2, engine_factory=OracleEngine, arrays="lazy")
+    assert out.host_recorders == []
+    assert _rel(np.array(r2[0].fdc), np.array(r1[0].fdc)) <= 1e-12 and np.ptp(np.array(r1[0].fdc)) > 0
+    assert _rel(np.array(r2[1].sdc), np.array(r1[1].sdc)) <= 1e-12
+    assert np.allclose(np.asarray(r2[2].values()), np.asarray(r1[2].values()), rtol=1e-12)
+    for a, b in zip(r1, r2):
+        assert np.allclose(np.asarray(b.values()), np.asarray(a.values()), rtol=1e-12, equal_nan=True), b.name
