@@ -36,4 +36,30 @@ ps.solver_registry.insert(0, cls)
 if os.environ.get("B200_REFSUITE_ALIAS"):
     cls.name = "glpk-edge" if name.endswith("edge") else "glpk"
     name = cls.name
+# B200_REFSUITE_DEVICE_RUN=1: every Model.run() of the suite goes through the device-resident run (solver option device_run,
+# pywr_b200/solver.py) - the program compiler, the program mode of the engine and the write-back into Pywr's objects are then
+# pinned by the reference's known answers too; models the device program does not cover fall back to the per-timestep loop
+if os.environ.get("B200_REFSUITE_DEVICE_RUN"):
+    _init = cls.__init__
+
+    def _init_device_run(self, *args, **kwargs):
+        kwargs.setdefault("device_run", True)
+        _init(self, *args, **kwargs)
+
+    cls.__init__ = _init_device_run
 os.environ["PYWR_SOLVER"] = name
+
+
+def pytest_terminal_summary(terminalreporter):
+    """with B200_REFSUITE_DEVICE_RUN: how many Model.run() calls ran as device programs, and why the others did not"""
+    if not os.environ.get("B200_REFSUITE_DEVICE_RUN"):
+        return
+    import collections
+
+    from pywr_b200.solver import device_run_log
+
+    n_dev = sum(1 for kind, _ in device_run_log if kind == "device")
+    terminalreporter.write_line(f"device_run: {n_dev} of {len(device_run_log)} Model.run() calls ran as device programs")
+    why = collections.Counter(reason.split(":")[0][:70] for kind, reason in device_run_log if kind == "host")
+    for reason, count in why.most_common(25):
+        terminalreporter.write_line(f"  host x{count}: {reason}")

@@ -739,8 +739,16 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     ``allow_host_recorders``: recorders the device cannot evaluate (event / parameter / custom Python
     recorders ...) do not raise; they are returned in ``program.host_recorders`` and the caller keeps
     them alive with the host mirror protocol (``device_run.run_on_device``)."""
+    from pywr.parameters import Parameter
+    from pywr.recorders import Recorder
+
     from .bridge import _bridge
 
+    for comp in model.components:
+        # a bare Component (neither Parameter nor Recorder) has before() / after() hooks the reference calls every timestep
+        # (pywr/_component.pyx; tests/test_components.py): only the per-timestep run honours them
+        if not isinstance(comp, (Parameter, Recorder)):
+            raise Unsupported(f"component {getattr(comp, 'name', comp)!r} of type {type(comp).__name__} runs on the host every timestep")
     base = build_structure(model, formulation)
     C = _Compiler(model, base)
     C.population_axis = population_axis
@@ -815,6 +823,21 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
             # the value (index) a parameter took in each timestep (pywr/recorders/_recorders.pyx:1361-1424, 1480-1540): a sample of
             # its V slot, expressed as the deficit recorder of an EMPTY flow form (value - 0): no new recorder kind in the kernels
             try:
+                if type(rec._param).__name__ == "DeficitParameter":
+                    # the one parameter whose value changes in after(): a recorder sees TODAY's deficit of the node (the LP saw
+                    # yesterday's; pywr/parameters/_parameters.pyx:1910-1957, tests/test_parameters.py::test_deficit_parameter)
+                    dnode = rec._param.node
+                    form = _flow_form(base, dnode, node_id)
+                    if id(dnode) not in max_flow_ref:
+                        raise Unsupported("DeficitParameter on a node without an LP max_flow")
+                    rec_kind.append(REC_NODE_DEFICIT); rec_src.append(node_id.get(id(dnode), -1)); rec_ref.append(max_flow_ref[id(dnode)])
+                    rec_factor.append(1.0)
+                    rec_row.append(flow_row.get(getattr(dnode, "fully_qualified_name", None), -1) if id(dnode) in node_id else -1)
+                    for c in sorted(form):
+                        rec_col.append(c); rec_w.append(form[c])
+                    rec_indptr.append(len(rec_col))
+                    rec_objs.append(rec)
+                    continue
                 ref = C.param(rec._param) if cname == "NumpyArrayParameterRecorder" else C.index_param(rec._param)
             except Unsupported:
                 if not allow_host_recorders:

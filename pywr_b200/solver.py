@@ -274,6 +274,10 @@ class B200EdgeSolver(B200Solver):
     formulation = "edge"
 
 
+# what Model.run() did for models whose solver asked for device_run: ("device", None) or ("host", reason) per call
+device_run_log = []
+
+
 def _install_device_run():
     """``Model.run()`` (``pywr/_model.pyx:637-682``) is a loop of ``solver.solve`` calls that a solver cannot take over from
     the inside.  For models whose solver was created with ``device_run`` the method is routed to the device-resident run,
@@ -292,17 +296,27 @@ def _install_device_run():
         mode = getattr(solver, "device_run", False)
         if not mode:
             return original(self)
+        from pywr.parameters import Parameter
+        from pywr.recorders import Recorder
+
         from .device_run import run_on_device
         from .program import Unsupported
 
+        # bare components have per-timestep hooks: decided before anything is set up or reset, so that the reference's run()
+        # sees the model exactly as it would have
+        if mode != "require" and any(not isinstance(c, (Parameter, Recorder)) for c in self.components):
+            device_run_log.append(("host", "bare component"))
+            return original(self)
         t0 = time.time()
         try:
             res = run_on_device(self, formulation=solver.formulation, arrays=solver.device_run_arrays,
                                 engine_factory=solver._make_program_engine)
-        except Unsupported:
+        except Unsupported as exc:
             if mode == "require":
                 raise
+            device_run_log.append(("host", str(exc)))
             return original(self)
+        device_run_log.append(("device", None))
         total = time.time() - t0
         timestep = self.timestep
         time_taken = res.time_compile + res.time_run + res.time_readout

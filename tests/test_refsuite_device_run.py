@@ -1,0 +1,40 @@
+"""The reference's OWN known-answer test-suite with every ``Model.run()`` routed through the device-resident run (solver option
+``device_run``; B200_REFSUITE_DEVICE_RUN in oracle/refsuite_plugin.py): the program compiler, the engines' program mode and the
+write-back into Pywr's objects are pinned by the reference's answers for every parameter / recorder / node type the suite
+exercises.  Models the device program does not cover fall back to the per-timestep loop (counted below).  CPU: the oracle's
+program mode; GPU (-m gpu): the CUDA engine, with the generic and with the per-model specialised run kernel."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(solver, extra_env):
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "_reftests")) and not os.path.isdir("/root/reference/tests"):
+        pytest.skip("reference test-suite not staged (baseline/build_ref.sh)")
+    pytest.importorskip("pywr")
+    env = dict(os.environ, B200_REFSUITE_DEVICE_RUN="1", **extra_env)
+    out = subprocess.run(["bash", os.path.join(ROOT, "oracle", "run_reference_tests.sh"), solver, "--timeout", "300"],
+                         capture_output=True, text=True, timeout=1500, env=env).stdout
+    failed = {ln.split(" - ")[0] for ln in out.splitlines() if ln.startswith(("FAILED", "ERROR"))}
+    known = {ln.strip() for ln in open(os.path.join(ROOT, "profiles", "refsuite", "b200_failed_tests.txt")) if ln.strip()}
+    m = re.search(r"(\d+) passed", out)
+    d = re.search(r"device_run: (\d+) of (\d+) Model.run\(\) calls ran as device programs", out)
+    assert m and d, out[-2000:]
+    assert failed <= known, sorted(failed - known)
+    assert int(m.group(1)) >= 590
+    assert int(d.group(1)) >= 290 and int(d.group(2)) >= 320, d.group(0)   # 301 of 327 when this was written
+
+
+def test_reference_suite_through_the_device_run_of_the_oracle():
+    _run("oracle", {})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("jit", ["0", "1"])
+def test_reference_suite_through_the_device_run_of_the_cuda_engine(jit):
+    """generic run kernel (20 s) and the kernel specialised per model (one NVRTC compile per model of the suite: 100 s)"""
+    _run("b200", {"B200LP_JIT": jit})
