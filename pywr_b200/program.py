@@ -350,6 +350,8 @@ class _Compiler:
                 ok = cmap < values.shape[1]
                 full[:, ok] = values[:, cmap[ok]]
                 values = full
+            if values.shape[0] > self.T and name in ("ArrayIndexedParameter", "ArrayIndexedScenarioParameter"):
+                values = values[: self.T]          # values[ts.index]: the rows past the run are never read
             if values.shape[0] not in (1, self.T):
                 raise Unsupported(f"{name}: {values.shape[0]} rows for {self.T} timesteps")
             return self.table(values, axis, int(info["offset"]))
