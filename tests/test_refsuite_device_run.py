@@ -38,3 +38,23 @@ def test_reference_suite_through_the_device_run_of_the_oracle():
 def test_reference_suite_through_the_device_run_of_the_cuda_engine(jit):
     """generic run kernel (20 s) and the kernel specialised per model (one NVRTC compile per model of the suite: 100 s)"""
     _run("b200", {"B200LP_JIT": jit})
+
+
+def test_edge_formulation_through_the_device_run_fails_nothing_the_per_timestep_run_passes():
+    """the same on the edge formulation (CythonGLPKEdgeSolver's LP): the set of failing reference tests is that of the
+    per-timestep run with the same solver"""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "_reftests")) and not os.path.isdir("/root/reference/tests"):
+        pytest.skip("reference test-suite not staged (baseline/build_ref.sh)")
+    pytest.importorskip("pywr")
+    sets = {}
+    for routed in ("", "1"):
+        env = dict(os.environ)
+        env.pop("B200_REFSUITE_DEVICE_RUN", None)
+        if routed:
+            env["B200_REFSUITE_DEVICE_RUN"] = "1"
+        out = subprocess.run(["bash", os.path.join(ROOT, "oracle", "run_reference_tests.sh"), "oracle-edge", "--timeout", "300"],
+                             capture_output=True, text=True, timeout=1500, env=env).stdout
+        sets[routed] = {ln.split(" - ")[0] for ln in out.splitlines() if ln.startswith(("FAILED", "ERROR"))}
+        m = re.search(r"(\d+) passed", out)
+        assert m and int(m.group(1)) >= 585, out[-1500:]
+    assert sets["1"] <= sets[""], sorted(sets["1"] - sets[""])
