@@ -581,7 +581,7 @@ class _Compiler:
         k = self.storage_index.get(id(node))
         if k is None and type(node).__name__ == "AggregatedStorage":
             k = self.aggregated_storage(node)
-        if k is None or (k < self.s.n_storage and self.s.st_kind[k] == ST_KIND_VIRTUAL and type(node).__name__ != "VirtualStorage"):
+        if k is None:
             raise Unsupported(f"control curve on {type(node).__name__} {getattr(node, 'name', '')!r}")
         return k
 
