@@ -195,7 +195,10 @@ def run_on_device(model, engine_factory=None, formulation="route", chunk=None, w
             results[rec.name] = out
             if writeback:
                 if is_array:
-                    _bridge.set_array_recorder(rec, out)
+                    try:        # the fetched [T, S] array BECOMES the recorder's array: no second pass over it
+                        _bridge.replace_array_recorder(rec, out)
+                    except TypeError:
+                        _bridge.set_array_recorder(rec, out)
                 else:
                     _bridge.set_constant_recorder(rec, out)
         if writeback:
