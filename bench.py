@@ -332,8 +332,8 @@ def main():
         import torch
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line (the box's nccl.conf asks for the banner)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")   # host-side barrier: waiting ranks must not keep a kernel spinning
