@@ -335,7 +335,20 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line (the box's nccl.conf asks for the banner)
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the communicator's creation prints NCCL's version banner through C stdio on rank 0: fd 1 points at stderr meanwhile
+        import ctypes
+
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+            ctypes.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         cpu_group = dist.new_group(backend="gloo")   # host-side barrier: waiting ranks must not keep a kernel spinning
 
     def barrier():

@@ -112,7 +112,19 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # one JSON line on stdout
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import ctypes
+
+        sys.stdout.flush()
+        saved_fd = os.dup(1)          # NCCL's version banner (C stdio, rank 0) goes to stderr: stdout carries the JSON line only
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+            ctypes.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:
