@@ -148,7 +148,8 @@ def test_specialised_run_kernel_equals_generic_run_kernel(monkeypatch, name, S, 
         assert np.array_equal(x, y, equal_nan=True)
 
 
-@pytest.mark.parametrize("name,S,seed", [("two_reservoir.route", 301, 41), ("thames.route", 1000, 42), ("rolling_virtual_storage_long.route", 17, 43)])
+@pytest.mark.parametrize("name,S,seed", [("two_reservoir.route", 301, 41), ("thames.route", 1000, 42), ("rolling_virtual_storage_long.route", 17, 43),
+                                         ("lagged_flows.route", 45, 44)])
 def test_sharded_cuda_engines_equal_one_engine(name, S, seed):
     """One host process, several engines (pywr_b200.engine.ShardedEngine): contiguous global_id blocks, one per GPU of the
     box — on a one-GPU box three handles on the same device.  Recorder arrays land in their column blocks through

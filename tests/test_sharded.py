@@ -16,7 +16,8 @@ def test_scenario_blocks_are_contiguous_and_cover_the_batch():
 
 
 @pytest.mark.parametrize("name,S,shards", [("two_reservoir.route", 10, 3), ("thames.route", 7, 4), ("demand_saving2.route", 5, 2),
-                                           ("rolling_virtual_storage_long.route", 6, 3)])
+                                           ("rolling_virtual_storage_long.route", 6, 3), ("lagged_flows.route", 9, 4),
+                                           ("derived_parameters.route", 8, 3)])
 def test_sharded_engine_equals_single_engine(name, S, shards):
     s, prog, _, names = load_program_case(name)
     q = widen_program(s, prog, S, seed=17)
