@@ -25,6 +25,7 @@ from pywr.parameters._thresholds cimport (AbstractThresholdParameter, MultipleTh
 from pywr.parameters._polynomial cimport Polynomial1DParameter
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder, NumpyArrayParameterRecorder,
+    BaseConstantParameterRecorder,
     NumpyArrayIndexParameterRecorder,
     BaseConstantStorageRecorder, NodeRecorder, StorageRecorder,
 )
@@ -200,6 +201,8 @@ def set_constant_recorder(rec, double[:] values):
     elif isinstance(rec, BaseConstantStorageRecorder):
         sr = rec
         sr._values[:] = values
+    elif isinstance(rec, BaseConstantParameterRecorder):
+        (<BaseConstantParameterRecorder>rec)._values[:] = values
     else:
         raise TypeError(f"unsupported recorder {type(rec).__name__}")
 

@@ -850,6 +850,25 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
             rec_indptr.append(len(rec_col))
             rec_objs.append(rec)
             continue
+        if cname in ("TotalParameterRecorder", "MeanParameterRecorder"):
+            # sum over time of value * factor (* days with integrate=True; pywr/recorders/_recorders.pyx:2274-2354; the mean divides
+            # in the reference's own finish()): the accumulating deficit recorder of an empty flow form adds V[ref] * days, so the
+            # slot holds value * factor, divided by the timestep length where that must not count (exact for daily timesteps)
+            try:
+                ref = C.param(rec._param)
+                if float(rec.factor) != 1.0:
+                    ref = C.emit(OP_AGG, [AGG["product"], 2, ref, C.const(float(rec.factor))])
+                if not (cname == "TotalParameterRecorder" and rec.integrate) and np.any(np.asarray(C.days, dtype=np.float64) != 1.0):
+                    ref = C.emit(OP_DIV, [ref, C.table(np.asarray(C.days, dtype=np.float64).reshape(-1, 1), None)])
+            except Unsupported:
+                if not allow_host_recorders:
+                    raise
+                host_recorders.append(rec)
+                continue
+            rec_kind.append(REC_TOTAL_DEFICIT); rec_src.append(-1); rec_ref.append(ref); rec_factor.append(1.0); rec_row.append(-1)
+            rec_indptr.append(len(rec_col))
+            rec_objs.append(rec)
+            continue
         if cname in ("NumpyArrayLevelRecorder", "NumpyArrayAreaRecorder"):
             # Storage.get_level / get_area (pywr/_core.pyx:1256-1280, recorders :1305-1358): the value of the storage's level /
             # area parameter (or constant) in each timestep - a parameter sample like the two above

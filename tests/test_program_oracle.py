@@ -327,7 +327,8 @@ def test_lagged_flow_parameters_without_a_user_recorder_on_the_node(arrays):
 
 def test_duration_curve_and_level_recorders_run_on_the_device():
     """Subclasses that only post-process the recorded array in finish() (flow / storage duration curves) ride on the device's array
-    recorders; NumpyArrayLevelRecorder samples the storage's level parameter (an InterpolatedVolumeParameter here)."""
+    recorders; NumpyArrayLevelRecorder samples the storage's level parameter (an InterpolatedVolumeParameter here); Total / Mean
+    parameter recorders accumulate a parameter's slot."""
     pytest.importorskip("pywr")
     import os
     ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
@@ -337,7 +338,8 @@ def test_duration_curve_and_level_recorders_run_on_the_device():
     import oracle.pywr_oracle_solver  # noqa: F401
     from pywr.model import Model
     from pywr.parameters import InterpolatedVolumeParameter
-    from pywr.recorders import FlowDurationCurveRecorder, NumpyArrayLevelRecorder, StorageDurationCurveRecorder
+    from pywr.recorders import (FlowDurationCurveRecorder, MeanParameterRecorder, NumpyArrayLevelRecorder, StorageDurationCurveRecorder,
+                                TotalParameterRecorder)
     from pywr_b200.device_run import run_on_device
 
     def make():
@@ -348,7 +350,10 @@ def test_duration_curve_and_level_recorders_run_on_the_device():
                                                 interp_kwargs={"bounds_error": False, "fill_value": (10.0, 19.0)})
         pct = [5.0, 25.0, 50.0, 75.0, 95.0]
         return m, [FlowDurationCurveRecorder(m, m.nodes["term1"], pct, name="fdc"),
-                   StorageDurationCurveRecorder(m, res, pct, name="sdc"), NumpyArrayLevelRecorder(m, res, name="level")]
+                   StorageDurationCurveRecorder(m, res, pct, name="sdc"), NumpyArrayLevelRecorder(m, res, name="level"),
+                   TotalParameterRecorder(m, m.parameters["demand_max_flow"], factor=2.0, integrate=True, name="total"),
+                   TotalParameterRecorder(m, m.parameters["demand_max_flow"], name="plain_total"),
+                   MeanParameterRecorder(m, m.parameters["demand_saving_factor"], factor=0.5, name="mean")]
 
     m1, r1 = make(); m1.run()
     m2, r2 = make(); out = run_on_device(m2, engine_factory=OracleEngine, arrays="lazy")
