@@ -39,6 +39,8 @@
 extern "C" {
 #endif
 
+/* layout version of the structs below.  Program op codes are additive within a version: B200LP_OP_THRESHOLD .. B200LP_OP_STATE
+   (13-16) were added to version 8 without touching a struct; a library that does not know an op rejects the program. */
 #define B200LP_ABI_VERSION 8
 
 /* error codes */
