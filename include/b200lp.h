@@ -250,8 +250,9 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
                                      the storage is in, interpolation between that band's own pair of values (_interpolate, :10-24) */
 
 #define B200LP_OP_THRESHOLD 13     /* args: source, x, predicate, threshold_ref, value0_ref, value1_ref.  AbstractThresholdParameter
-                                     (pywr/parameters/_thresholds.pyx:19-131) without the ratchet: value1 if predicate(X, threshold)
-                                     else value0 (values 0 / 1: the parameter's index).  source 0: X = the value behind ref x
+                                     (pywr/parameters/_thresholds.pyx:19-131): value1 if predicate(X, threshold)
+                                     else value0 (values 0 / 1: the parameter's index; a ratchet chains it with B200LP_OP_LAG on a
+                                     recorder of its own slot).  source 0: X = the value behind ref x
                                      (ParameterThresholdParameter :294-318, calendar thresholds :362-395 through a table);
                                      source 1: X = the current volume of storage x (StorageThresholdParameter :134-157).
                                      predicate: B200LP_PRED_* */

@@ -559,8 +559,23 @@ class _Compiler:
         from .bridge import _bridge
 
         name = type(p).__name__
-        if getattr(p, "ratchet", False):
-            raise Unsupported(f"{name} with ratchet=True keeps state on the host")
+        if getattr(p, "ratchet", False) and not getattr(self, "_in_ratchet", False):
+            # once triggered it stays triggered (:95-112): index(t) = 1 if index(t-1) == 1 else predicate(t); yesterday's index is
+            # the lagged sample of a hidden recorder of this very slot
+            key = ("ratchet", id(p))
+            if key not in self.memo:
+                cell = {"slot": None}
+                if not hasattr(self, "lag_nodes"):
+                    self.lag_nodes = []
+                self.lag_nodes.append((cell, "slot"))
+                prev = self.emit(OP_LAG, [-len(self.lag_nodes), self.const(0.0), 1])
+                self._in_ratchet = True
+                try:
+                    now = self.threshold(p, self.const(0.0), self.const(1.0))
+                finally:
+                    self._in_ratchet = False
+                cell["slot"] = self.memo[key] = self.emit(OP_THRESHOLD, [0, prev, PRED["EQ"], self.const(1.0), now, self.const(1.0)])
+            return self.emit(OP_THRESHOLD, [0, self.memo[key], PRED["EQ"], self.const(1.0), v0, v1])
         pred = _bridge.threshold_predicate(p)
         thr = self.value_ref(p.threshold)
         if name == "ParameterThresholdParameter":
@@ -941,6 +956,12 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     rec_names_all = [str(getattr(r, "name", "")) for r in rec_objs]
     lag_rec = []
     for node, deficit in getattr(C, "lag_nodes", []):
+        if deficit == "slot":      # a ratchet's own index of the day before: hidden sample of its slot (empty flow form)
+            rec_kind.append(REC_NODE_DEFICIT); rec_src.append(-1); rec_ref.append(node["slot"]); rec_factor.append(1.0); rec_row.append(-1)
+            rec_indptr.append(len(rec_col))
+            rec_names_all.append(f"__ratchet__{len(rec_kind)}")
+            lag_rec.append((len(rec_kind) - 1, node, deficit))
+            continue
         want = REC_NODE_DEFICIT if deficit else REC_NODE_FLOW
         found = next((r for r in range(n_visible) if rec_kind[r] == want and rec_factor[r] == 1.0
                       and _bridge.recorder_node(rec_objs[r]) is node), None)

@@ -95,8 +95,9 @@ def load_program_case(name):
     s = LPStructure.load(os.path.join(GOLDEN, name + ".pstructure.npz"))
     prog = Program.load(os.path.join(GOLDEN, name + ".program.npz"))
     z = np.load(os.path.join(GOLDEN, name + ".expected.npz"))
-    expected = [z[f"rec{i}"] for i in range(prog.n_recorders)]
-    return s, prog, expected, [str(n) for n in z["names"]]
+    names = [str(n) for n in z["names"]]      # the model's own recorders; hidden ones (lag state) follow them in the program
+    expected = [z[f"rec{i}"] for i in range(len(names))]
+    return s, prog, expected, names
 
 
 def n_scenarios_of(s, prog):

@@ -167,7 +167,9 @@ def custom_document(kind):
                           "parameters": [0.5, {"type": "aggregated", "agg_func": "product", "parameters": [0.1, "gauge_3_days_ago"]},
                                          {"type": "aggregated", "agg_func": "product", "parameters": [0.05, "abs_last_week"]}]}
         next(n for n in doc["nodes"] if n["name"] == "mrf1")["mrf"] = "mrf_today"
-        P["demand_max_flow"]["parameters"] += ["short_yesterday", "inflow_factor", "easing"]
+        # a ratchet: once the river past the gauge has run low, a restriction stays for the rest of the run
+        P["ever_low"] = {"type": "nodethreshold", "node": "term1", "threshold": 0.9, "predicate": "LT", "values": [1.0, 0.96], "ratchet": True}
+        P["demand_max_flow"]["parameters"] += ["short_yesterday", "inflow_factor", "easing", "ever_low"]
         return doc
     if kind == "aggregated_storage":
         # tests/models/three_storage.json: the inflow of reservoir 0 is switched by a control curve on the AGGREGATED storage

@@ -363,3 +363,45 @@ def test_duration_curve_and_level_recorders_run_on_the_device():
     assert np.allclose(np.asarray(r2[2].values()), np.asarray(r1[2].values()), rtol=1e-12)
     for a, b in zip(r1, r2):
         assert np.allclose(np.asarray(b.values()), np.asarray(a.values()), rtol=1e-12, equal_nan=True), b.name
+
+
+def test_ratcheting_thresholds_run_on_the_device():
+    """AbstractThresholdParameter(ratchet=True): once the predicate has fired the index stays 1 until the model is reset
+    (pywr/parameters/_thresholds.pyx:95-112).  On the device the index of the day before is the lagged sample of a hidden recorder
+    of the parameter's own slot."""
+    pytest.importorskip("pywr")
+    import json
+    import os
+    ref = os.environ.get("PYWR_REFERENCE", "/root/reference")
+    path = os.path.join(ref, "examples", "thames", "thames.json")
+    if not os.path.exists(path):
+        pytest.skip("reference model documents not available")
+    import oracle.pywr_oracle_solver  # noqa: F401
+    from pywr.model import Model
+    from pywr.recorders import NumpyArrayIndexParameterRecorder, NumpyArrayNodeRecorder, NumpyArrayStorageRecorder
+    from pywr_b200.device_run import run_on_device
+
+    def make():
+        doc = json.load(open(path))
+        for prm in doc["parameters"].values():
+            if isinstance(prm, dict) and "url" in prm and not os.path.isabs(prm["url"]):
+                prm["url"] = os.path.join(ref, "examples/thames", prm["url"])
+        P = doc["parameters"]
+        mv = next(n for n in doc["nodes"] if n["name"] == "reservoir1")["max_volume"]
+        P["drought_order"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.7 * mv, "predicate": "LT",
+                              "values": [1.0, 0.8], "ratchet": True}
+        P["river_low"] = {"type": "nodethreshold", "node": "term1", "threshold": 1.0, "predicate": "LT", "values": [1.0, 0.97], "ratchet": True}
+        P["demand_max_flow"]["parameters"] += ["drought_order", "river_low"]
+        m = Model.load(doc, solver="oracle")
+        m.timestepper.end = "2101-12-31"
+        return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], name="vol"), NumpyArrayNodeRecorder(m, m.nodes["demand1"], name="supplied"),
+                   NumpyArrayIndexParameterRecorder(m, m.parameters["drought_order"], name="order"),
+                   NumpyArrayIndexParameterRecorder(m, m.parameters["river_low"], name="low")]
+
+    m1, r1 = make(); m1.run()
+    m2, r2 = make(); out = run_on_device(m2, engine_factory=OracleEngine)
+    assert out.host_recorders == []
+    for a, b in zip(r1, r2):
+        assert _rel(np.array(b.data, dtype=float), np.array(a.data, dtype=float)) <= 1e-12, b.name
+    order = np.array(r1[2].data)
+    assert order.min() == 0 and order.max() == 1 and np.all(np.diff(order, axis=0) >= 0)      # it did fire, and never released
