@@ -261,8 +261,8 @@ int b200lp_set_option(b200lp_handle *h, const char *name, double value);
                                      InterpolatedParameter / InterpolatedVolumeParameter (pywr/parameters/parameters.py:124-242,
                                      scipy interp1d kind="linear" = slope * (X - xk[j]) + yk[j]).  X below xk[0] / above xk[n-1] gives
                                      below / above (NaN refs reproduce bounds_error=True: the scenario then fails with B200LP_ST_NAN) */
-#define B200LP_OP_LAG 15           /* args: recorder, initial_ref, steps (>= 1).  The sample array recorder `recorder` (kind
-                                     B200LP_REC_NODE_FLOW or B200LP_REC_NODE_DEFICIT) took `steps` timesteps ago; initial_ref during the
+#define B200LP_OP_LAG 15           /* args: recorder, initial_ref, steps (>= 1).  The sample array recorder `recorder` (any of the
+                                     [T, S] kinds) took `steps` timesteps ago; initial_ref during the
                                      first `steps` timesteps.  A node's flow of the day before: FlowParameter
                                      (pywr/parameters/_parameters.pyx:1959-2008), AbstractNode._prev_flow as read by
                                      NodeThresholdParameter / MultipleThresholdIndexParameter (_thresholds.pyx:159-240); yesterday's

@@ -859,7 +859,7 @@ static bool decode_program(const b200lp_program *p, int n_slots, int n_consts, i
             break;
         case B200LP_OP_LAG:  // -> recorder, V index of the initial value, steps
             ok = na >= 3 && a[0] >= 0 && a[0] < p->n_recorders && ref_ok(a[1]) && a[2] >= 1 && !(p->flags & B200LP_PROG_AGG_ONLY) &&
-                 (p->rec_kind[a[0]] == B200LP_REC_NODE_FLOW || p->rec_kind[a[0]] == B200LP_REC_NODE_DEFICIT);
+                 p->rec_kind[a[0]] >= B200LP_REC_NODE_FLOW && p->rec_kind[a[0]] <= B200LP_REC_STORAGE_PC;   // the [T, S] kinds
             if (ok) { out.push_back(a[0]); out.push_back(vidx(a[1])); out.push_back(a[2]); dec.has_lag = true; }
             break;
         case B200LP_OP_STORAGE_RESET:  // -> V indices: volume, pc, max_volume, flag, initial volume, initial pc

@@ -209,7 +209,7 @@ _VALUE_LEAVES = {  # state- and scenario-independent: sampled through their publ
     "UniformDrawdownProfileParameter", "RbfProfileParameter", "AnnualHarmonicSeriesParameter", "DiscountFactorParameter",
 }
 _THRESHOLDS = {"ParameterThresholdParameter", "StorageThresholdParameter", "CurrentYearThresholdParameter",
-               "CurrentOrdinalDayThresholdParameter", "NodeThresholdParameter"}
+               "CurrentOrdinalDayThresholdParameter", "NodeThresholdParameter", "RecorderThresholdParameter"}
 _SCENARIO_PROFILES = {
     "ScenarioMonthlyProfileParameter", "ScenarioDailyProfileParameter", "ScenarioWeeklyProfileParameter",
     "ArrayIndexedScenarioMonthlyFactorsParameter",
@@ -586,6 +586,14 @@ class _Compiler:
             inner = self.emit(OP_THRESHOLD, [0, self.prev_flow(p.node), pred, thr, v0, v1])
             first = self.table(np.array([[1.0 if i == 0 else 0.0] for i in range(self.T)]), None)
             return self.emit(OP_THRESHOLD, [0, first, PRED["EQ"], self.const(1.0), inner, v0])
+        if name == "RecorderThresholdParameter":        # _thresholds.pyx:320-360: yesterday's row of an array recorder; initial_value on day one
+            if not hasattr(self, "lag_nodes"):
+                self.lag_nodes = []
+            self.lag_nodes.append((p.recorder, "recorder"))
+            x = self.emit(OP_LAG, [-len(self.lag_nodes), self.const(0.0), 1])
+            inner = self.emit(OP_THRESHOLD, [0, x, pred, thr, v0, v1])
+            first = self.table(np.array([[1.0 if i == 0 else 0.0] for i in range(self.T)]), None)
+            return self.emit(OP_THRESHOLD, [0, first, PRED["EQ"], self.const(1.0), inner, v1 if int(p.initial_value) else v0])
         if name == "CurrentYearThresholdParameter":
             x = self.table(np.array([[float(ts.year)] for ts in self.timesteps]), None)
         else:                                           # CurrentOrdinalDayThresholdParameter
@@ -961,6 +969,12 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
             rec_indptr.append(len(rec_col))
             rec_names_all.append(f"__ratchet__{len(rec_kind)}")
             lag_rec.append((len(rec_kind) - 1, node, deficit))
+            continue
+        if deficit == "recorder":  # RecorderThresholdParameter: the user's own array recorder, which has to be a device recorder
+            found = next((r for r in range(n_visible) if rec_objs[r] is node and rec_kind[r] in ARRAY_KINDS), None)
+            if found is None:
+                raise Unsupported(f"RecorderThresholdParameter on recorder {getattr(node, 'name', node)!r}, which does not record an array on the device")
+            lag_rec.append((found, node, deficit))
             continue
         want = REC_NODE_DEFICIT if deficit else REC_NODE_FLOW
         found = next((r for r in range(n_visible) if rec_kind[r] == want and rec_factor[r] == 1.0

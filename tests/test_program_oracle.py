@@ -378,6 +378,7 @@ def test_ratcheting_thresholds_run_on_the_device():
         pytest.skip("reference model documents not available")
     import oracle.pywr_oracle_solver  # noqa: F401
     from pywr.model import Model
+    from pywr.parameters import RecorderThresholdParameter
     from pywr.recorders import NumpyArrayIndexParameterRecorder, NumpyArrayNodeRecorder, NumpyArrayStorageRecorder
     from pywr_b200.device_run import run_on_device
 
@@ -394,14 +395,19 @@ def test_ratcheting_thresholds_run_on_the_device():
         P["demand_max_flow"]["parameters"] += ["drought_order", "river_low"]
         m = Model.load(doc, solver="oracle")
         m.timestepper.end = "2101-12-31"
-        return m, [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], name="vol"), NumpyArrayNodeRecorder(m, m.nodes["demand1"], name="supplied"),
-                   NumpyArrayIndexParameterRecorder(m, m.parameters["drought_order"], name="order"),
-                   NumpyArrayIndexParameterRecorder(m, m.parameters["river_low"], name="low")]
+        recs = [NumpyArrayStorageRecorder(m, m.nodes["reservoir1"], name="vol"), NumpyArrayNodeRecorder(m, m.nodes["demand1"], name="supplied"),
+                NumpyArrayIndexParameterRecorder(m, m.parameters["drought_order"], name="order"),
+                NumpyArrayIndexParameterRecorder(m, m.parameters["river_low"], name="low")]
+        # yesterday's row of an array recorder against a threshold (RecorderThresholdParameter, :320-360; initial_value on day one)
+        by_rec = RecorderThresholdParameter(m, recs[0], 150.0, values=[1.0, 0.98], predicate="LT", initial_value=0, name="vol_was_low")
+        m.parameters["demand_max_flow"].add(by_rec)
+        return m, recs + [NumpyArrayIndexParameterRecorder(m, by_rec, name="by_rec")]
 
     m1, r1 = make(); m1.run()
     m2, r2 = make(); out = run_on_device(m2, engine_factory=OracleEngine)
     assert out.host_recorders == []
     for a, b in zip(r1, r2):
         assert _rel(np.array(b.data, dtype=float), np.array(a.data, dtype=float)) <= 1e-12, b.name
+    assert np.ptp(np.array(r1[4].data)) > 0
     order = np.array(r1[2].data)
     assert order.min() == 0 and order.max() == 1 and np.all(np.diff(order, axis=0) >= 0)      # it did fire, and never released
