@@ -22,7 +22,7 @@ from pywr.parameters._parameters cimport (
 )
 from pywr.parameters._thresholds cimport (AbstractThresholdParameter, MultipleThresholdParameterIndexParameter,
                                           MultipleThresholdIndexParameter)
-from pywr.parameters._polynomial cimport Polynomial1DParameter
+from pywr.parameters._polynomial cimport Polynomial1DParameter, Polynomial2DStorageParameter
 from pywr.recorders._recorders cimport (
     NumpyArrayNodeRecorder, NumpyArrayAbstractStorageRecorder, BaseConstantNodeRecorder, NumpyArrayParameterRecorder,
     BaseConstantParameterRecorder,
@@ -105,6 +105,13 @@ def polynomial1d_info(Polynomial1DParameter p):
     return dict(coefficients=np.asarray(p.coefficients).copy(), node=p._other_node, storage_node=p._storage_node,
                 parameter=p._parameter, use_proportional_volume=bool(p.use_proportional_volume), offset=float(p.offset),
                 scale=float(p.scale))
+
+
+def polynomial2d_info(Polynomial2DStorageParameter p):
+    """the non-public members of Polynomial2DStorageParameter (pywr/parameters/_polynomial.pxd:14-23)"""
+    return dict(coefficients=np.asarray(p.coefficients).copy(), storage_node=p._storage_node, parameter=p._parameter,
+                use_proportional_volume=bool(p.use_proportional_volume), storage_offset=float(p.storage_offset),
+                storage_scale=float(p.storage_scale), parameter_offset=float(p.parameter_offset), parameter_scale=float(p.parameter_scale))
 
 
 def threshold_values(AbstractThresholdParameter p):

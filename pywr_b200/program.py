@@ -441,6 +441,25 @@ class _Compiler:
                 power = x if i == 1 else self.emit(OP_AGG, [AGG["product"], 2, power, x])
                 terms.append(self.emit(OP_AGG, [AGG["product"], 2, self.const(c), power]))
             return self.emit(OP_AGG, [AGG["sum"], len(terms)] + terms)
+        if name == "Polynomial2DStorageParameter":      # _polynomial.pyx:90-175: sum c_ij x^i y^j of a storage and a parameter
+            info = _bridge.polynomial2d_info(p)
+            x = self.emit(OP_STATE, [3 if info["use_proportional_volume"] else 1, self.storage_of(info["storage_node"])])
+            x = self.emit(OP_AGG, [AGG["sum"], 2, self.emit(OP_AGG, [AGG["product"], 2, self.const(info["storage_scale"]), x]),
+                                   self.const(info["storage_offset"])])
+            y = self.emit(OP_AGG, [AGG["sum"], 2, self.emit(OP_AGG, [AGG["product"], 2, self.const(info["parameter_scale"]),
+                                                                      self.param(info["parameter"])]), self.const(info["parameter_offset"])])
+            coef = info["coefficients"]
+
+            def powers(base, n):
+                out = [self.const(1.0)]
+                for i in range(1, n):
+                    out.append(base if i == 1 else self.emit(OP_AGG, [AGG["product"], 2, out[-1], base]))
+                return out
+
+            xp, yp = powers(x, coef.shape[0]), powers(y, coef.shape[1])
+            terms = [self.emit(OP_AGG, [AGG["product"], 3, self.const(coef[i, j]), xp[i], yp[j]])
+                     for i in range(coef.shape[0]) for j in range(coef.shape[1])]
+            return self.emit(OP_AGG, [AGG["sum"], len(terms)] + terms)
         if name == "ScenarioWrapperParameter":          # pywr/parameters/parameters.py:359-404: one child parameter per scenario member
             axis = self.model.scenarios.get_scenario_index(p.scenario)
             size = p.scenario.size

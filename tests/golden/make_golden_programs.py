@@ -122,12 +122,15 @@ def custom_document(kind):
         P["poly_of_level"] = {"type": "polynomial1d", "storage_node": "reservoir1", "use_proportional_volume": True,
                               "coefficients": [0.97, 0.08, -0.05], "scale": 0.9, "offset": 0.05}
         P["poly_of_profile"] = {"type": "polynomial1d", "parameter": "demand_profile", "coefficients": [1.0, -0.02, 0.015, 0.001]}
+        P["poly_2d"] = {"type": "polynomial2dstorage", "storage_node": "reservoir1", "parameter": "level2", "use_proportional_volume": True,
+                        "coefficients": [[1.0, -0.02, 0.01], [0.03, 0.015, -0.01]], "storage_scale": 0.8, "storage_offset": 0.1,
+                        "parameter_scale": 1.5, "parameter_offset": -0.2}
         P["by_member"] = {"type": "scenariowrapper", "scenario": "demand",
                           "parameters": [{"type": "constant", "value": 1.0}, "poly_of_profile", {"type": "constant", "value": 0.99},
                                          "curve_of_baseline", {"type": "constant", "value": 1.01}]}
         P["discount"] = {"type": "discountfactor", "rate": 0.035, "base_year": 2100}
         P["demand_max_flow"]["parameters"] += ["year_step", "summer_extra", "low_volume", "level_factor", "curve_of_level1", "curve_of_baseline",
-                                               "class_factor", "stored_factor", "poly_of_level", "by_member"]
+                                               "class_factor", "stored_factor", "poly_of_level", "by_member", "poly_2d"]
         # abstraction capacity: chosen by the sum of two indices (late in the run? storage low?) ...
         P["late"] = {"type": "currentordinaldaythreshold", "threshold": start.toordinal() + 500, "predicate": ">"}
         P["low_volume_index"] = {"type": "storagethreshold", "storage_node": "reservoir1", "threshold": 0.6 * max_volume, "predicate": "LE"}
