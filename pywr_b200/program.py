@@ -460,6 +460,15 @@ class _Compiler:
             terms = [self.emit(OP_AGG, [AGG["product"], 3, self.const(coef[i, j]), xp[i], yp[j]])
                      for i in range(coef.shape[0]) for j in range(coef.shape[1])]
             return self.emit(OP_AGG, [AGG["sum"], len(terms)] + terms)
+        if name == "KeatingStreamFlowParameter":        # pywr/parameters/groundwater.py:5-62: sum over the stream levels below the
+            level = self.value_ref(p.storage_node.level)     # aquifer's level of 2 T C (level - stream level)
+            terms = []
+            for L, Tn in zip(np.asarray(p.levels, dtype=np.float64), np.asarray(p.transmissivity, dtype=np.float64)):
+                k = 2 * float(Tn) * float(p.coefficient)
+                diff = self.emit(OP_AGG, [AGG["sum"], 2, level, self.const(-float(L))])
+                term = self.emit(OP_AGG, [AGG["product"], 2, self.const(k), diff])
+                terms.append(self.emit(OP_THRESHOLD, [0, level, PRED["GT"], self.const(float(L)), self.const(0.0), term]))
+            return self.emit(OP_AGG, [AGG["sum"], len(terms)] + terms) if terms else self.const(0.0)
         if name == "ScenarioWrapperParameter":          # pywr/parameters/parameters.py:359-404: one child parameter per scenario member
             axis = self.model.scenarios.get_scenario_index(p.scenario)
             size = p.scenario.size
@@ -818,7 +827,8 @@ def compile_program(model, formulation="route", recorders=None, allow_host_recor
     roll_init = np.zeros(max(base.n_storage, 1), np.float64)
     for k, st in enumerate(base.storages):
         cname = type(st).__name__
-        if cname not in ("Storage", "Reservoir", "VirtualStorage", "RollingVirtualStorage") + SCHEDULED_STORAGES:
+        # KeatingAquifer (pywr/domains/groundwater.py): a Storage with several inputs whose bounds are parameters; no state of its own
+        if cname not in ("Storage", "Reservoir", "VirtualStorage", "RollingVirtualStorage", "KeatingAquifer") + SCHEDULED_STORAGES:
             raise Unsupported(f"storage type {cname} keeps extra state on the host")
         vol0[k] = np.asarray(st._volume)
         pc0[k] = np.asarray(st._current_pc)
