@@ -209,6 +209,13 @@ rsx_crossover_kernel(const RsxDev D, const int s0, const int s1) {
     }
 }
 
+// Scenarios the first-order iterations left at their iteration limit go through the crossover as well: the simplex finishes from
+// whatever point they reached (and reports infeasibility where that was the reason), instead of the run failing on them.
+__global__ void rsx_requeue_unconverged(int *__restrict__ status, const int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S && status[s] == B200LP_ST_ITERLIMIT) status[s] = B200LP_ST_OPTIMAL;
+}
+
 // planes [item][ld] -> per-scenario vectors [S][2 (n+m)] (LO | HI), 32 x 32 tiles through shared memory: coalesced reads along
 // the scenario axis, coalesced writes along the item axis
 __global__ void rsx_gather_bounds(const RsxDev D) {

@@ -85,3 +85,23 @@ def test_reference_suite_through_the_large_lp_path():
     m = re.search(r"(\d+) passed", out)
     d = re.search(r"device_run: (\d+) of (\d+)", out)
     assert m and int(m.group(1)) >= 584 and d and int(d.group(1)) >= 295, out[-1500:]
+
+
+@pytest.mark.gpu
+def test_reference_suite_subset_through_pdhg_and_crossover():
+    """the first-order method of the large-LP path followed by the crossover to a vertex (B200LP_LARGE_ENGINE=pdhg) on the modules
+    around the analytical reservoir model, delays, piecewise and aggregated nodes, licences: scenarios the iterations leave at their
+    limit are finished by the simplex of the crossover (test_analytical.py::test_analytical needs that).  The whole suite this way:
+    586 passed, 50 s (profiles/refsuite/device_run_summary.txt)."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "_reftests")) and not os.path.isdir("/root/reference/tests"):
+        pytest.skip("reference test-suite not staged (baseline/build_ref.sh)")
+    pytest.importorskip("pywr")
+    env = dict(os.environ, B200_REFSUITE_DEVICE_RUN="1", B200LP_FORCE_PDHG="1", B200LP_LARGE_ENGINE="pdhg")
+    out = subprocess.run(["bash", os.path.join(ROOT, "oracle", "run_reference_tests.sh"), "b200-edge", "--timeout", "200", "-k",
+                          "not TestSpecifyingSolver and (test_analytical or test_delay or test_piecewise or test_license or test_aggregated)"],
+                         capture_output=True, text=True, timeout=1200, env=env).stdout
+    base = {ln.strip() for ln in open(os.path.join(ROOT, "profiles", "refsuite", "edge_failed_tests.txt")) if ln.strip()}
+    extra = {ln.split(" - ")[0] for ln in out.splitlines() if ln.startswith(("FAILED", "ERROR"))} - base
+    assert not extra, sorted(extra)
+    m = re.search(r"(\d+) passed", out)
+    assert m and int(m.group(1)) >= 40, out[-1500:]
